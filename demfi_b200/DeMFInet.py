@@ -1,0 +1,206 @@
+"""Drop-in `DeMFInet` nn.Module (reference surface: `DeMFInet.py:13-179` of JihyongOh/DeMFI).
+
+Same class name, constructor `args`, the same 260 parameter tensors under the same
+state_dict names (so `main.py:176` `.apply(weights_init)`, `main.py:351` `load_state_dict`
+and a released checkpoint work unchanged), the same `forward(x, t_value, num_update,
+is_training)` signature and return structure (`DeMFInet.py:170-179`).  The sub-modules
+registered here only HOLD parameters: their own `forward` is never called.  The forward
+pass is the plan in `demfi_b200/engine.py`, i.e. hand-written sm_100a kernels behind the C
+ABI of `include/demfi_b200.h`.  There is no PyTorch/CPU fallback: without the CUDA library
+or a B200 the forward raises.
+
+Scope: inference forward.  Autograd through the kernels (training,
+`main.py:443`) is the "next" row f-2 and raises NotImplementedError for now.
+"""
+from __future__ import annotations
+
+import functools
+
+import torch
+import torch.nn as nn
+
+from .engine import Engine
+
+__all__ = ["DeMFInet"]
+
+
+class _Holder(nn.Module):
+    """Parameter container; mirrors the reference's module tree so names match."""
+
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError("demfi_b200 sub-modules only hold parameters; call DeMFInet.forward")
+
+
+def _rdb_conv(cin, g):
+    m = _Holder()
+    m.conv = nn.Sequential(nn.Conv2d(cin, g, 3, padding=1, stride=1), nn.ReLU())
+    return m
+
+
+def _rdb(g0, g, c):
+    m = _Holder()
+    m.convs = nn.Sequential(*[_rdb_conv(g0 + i * g, g) for i in range(c)])
+    m.LFF = nn.Conv2d(g0 + c * g, g0, 1, padding=0, stride=1)
+    return m
+
+
+def _ff_rdb(args, G0=96, num_RDB=12, C=4, G=32):
+    m = _Holder()
+    sf = args.scale_factor
+    m.SFENet1 = nn.Conv2d(12 * sf * sf, G0, 5, padding=2, stride=1)
+    m.SFENet2 = nn.Conv2d(G0, G0, 3, padding=1, stride=1)
+    m.RDBs = nn.ModuleList([_rdb(G0, G, C) for _ in range(num_RDB)])
+    m.GFF = nn.Sequential(nn.Conv2d(num_RDB * G0, G0, 1, padding=0, stride=1), nn.Conv2d(G0, G0, 3, padding=1, stride=1))
+    m.UPNet = nn.Sequential(nn.Conv2d(G0, 256, 3, padding=1, stride=1), nn.PixelShuffle(2),
+                            nn.Conv2d(64, args.nf * 2 + 4 + 1, 3, padding=1, stride=1))
+    return m
+
+
+def _resblock(nf, three_d):
+    m = _Holder()
+    if three_d:
+        m.conv1 = nn.Conv3d(nf, nf, [1, 3, 3], 1, [0, 1, 1], bias=True)
+        m.conv2 = nn.Conv3d(nf, nf, [1, 3, 3], 1, [0, 1, 1], bias=True)
+    else:
+        m.conv1 = nn.Conv2d(nf, nf, 3, 1, 1, bias=True)
+        m.conv2 = nn.Conv2d(nf, nf, 3, 1, 1, bias=True)
+    return m
+
+
+def _fgac(nf):
+    m = _Holder()
+    m.conv_ref_k = nn.Conv2d(nf, nf, [1, 1], 1, [0, 0])
+    m.conv_source_k = nn.Conv2d(nf, nf, [1, 1], 1, [0, 0])  # dead weight in the reference too (rr = sr = 0)
+    m.w_gen = nn.Conv2d(nf * 2, nf, [3, 3], 1, [1, 1])
+    m.w_gen_2 = nn.Conv2d(nf, 1, [3, 3], 1, [1, 1])
+    m.fusion = nn.Conv2d(nf, nf, [1, 1], 1, [0, 0])
+    return m
+
+
+def _fac_fb(args):
+    m = _Holder()
+    nf = args.nf
+    m.conv_first = nn.Conv2d(nf, nf, 3, 1, 1, bias=True)
+    m.feature_extraction = nn.Sequential(*[_resblock(nf, False) for _ in range(args.num_ResB_FACFB)])
+    m.shared_FGAC = _fgac(nf)
+    return m
+
+
+def _unet(nf):
+    m = _Holder()
+    m.enc1 = nn.Conv2d(nf * 3 + 9, nf, [4, 4], 2, [1, 1])
+    m.enc2 = nn.Conv2d(nf, 2 * nf, [4, 4], 2, [1, 1])
+    m.enc3 = nn.Conv2d(2 * nf, 4 * nf, [4, 4], 2, [1, 1])
+    m.dec0 = nn.Conv2d(4 * nf, 4 * nf, [3, 3], 1, [1, 1])
+    m.dec1 = nn.Conv2d(6 * nf, 2 * nf, [3, 3], 1, [1, 1])
+    m.dec2 = nn.Conv2d(3 * nf, nf, [3, 3], 1, [1, 1])
+    m.dec3 = nn.Conv2d(nf, 5 + 2 * nf, [3, 3], 1, [1, 1])
+    return m
+
+
+def _booster(nf):
+    m = _Holder()
+    mx = _Holder()
+    mx.conv_ref1 = nn.Conv2d(30, nf // 2, 7, padding=3)
+    mx.conv_ref2 = nn.Conv2d(nf // 2, nf // 2, 3, padding=1)
+    mx.conv_delta1 = nn.Conv2d(5, nf // 2, 7, padding=3)
+    mx.conv_delta2 = nn.Conv2d(nf // 2, nf // 2, 3, padding=1)
+    mx.conv_blend1 = nn.Conv2d(nf, nf // 2, 3, padding=1)
+    mx.conv_blend2 = nn.Conv2d(nf // 2, nf, 3, padding=1)
+    m.Mixer = mx
+    gb = _Holder()
+    for g in ("z", "r", "q"):
+        setattr(gb, f"conv{g}1", nn.Conv2d(2 * nf, nf, (1, 5), padding=(0, 2)))
+    for g in ("z", "r", "q"):
+        setattr(gb, f"conv{g}2", nn.Conv2d(2 * nf, nf, (5, 1), padding=(2, 0)))
+    m.GB = gb
+    fo = _Holder()
+    fo.conv1 = nn.Conv2d(nf, nf // 2, 3, padding=1)
+    fo.conv2 = nn.Conv2d(nf // 2, 5, 3, padding=1)
+    m.flow_occ = fo
+    return m
+
+
+class DeMFInet(nn.Module):
+    def __init__(self, args):
+        super().__init__()
+        self.args = args
+        self.device = torch.device("cuda:" + str(args.gpu) if torch.cuda.is_available() else "cpu")
+        self.nf = args.nf
+        self.scale_factor = args.scale_factor
+        # the kernel set is specialised for the released configuration (main.py:88-101 defaults)
+        if (args.nf, args.scale_factor, args.num_ResB_FACFB, args.num_ResB_Dec, bool(args.shared_FGAC_flag)) != (64, 2, 5, 5, True):
+            raise NotImplementedError("demfi_b200 implements nf=64, scale_factor=2, num_ResB_FACFB=5, num_ResB_Dec=5, "
+                                      "shared_FGAC_flag=True (the released DeMFI-Net_rb configuration)")
+        nf = args.nf
+        # registration order = reference order (DeMFInet.py:26-44) so state_dict() enumerates identically
+        self.FF_RDB_Module = _ff_rdb(args)
+        self.FAC_FB_Module = _fac_fb(args)
+        self.Refine_Module = _unet(nf)
+        self.Dec_first = nn.Conv3d(nf, nf, [1, 3, 3], 1, [0, 1, 1], bias=True)
+        self.Decoder_res = nn.Sequential(*[_resblock(nf, True) for _ in range(args.num_ResB_Dec)])
+        self.Dec_last1 = nn.Conv3d(nf, nf, [1, 3, 3], 1, [0, 1, 1], bias=True)
+        self.Dec_last2 = nn.Conv3d(nf, 3, [1, 3, 3], 1, [0, 1, 1], bias=True)
+        self.Ch_Reducer = nn.Conv2d(nf * 3, nf, 7, padding=3, bias=True)
+        self.Booster_Module = _booster(nf)
+        self.Dec_first_2 = nn.Conv2d(9 + nf + 9 + 5 + 12, nf, 3, 1, 1, bias=True)
+        self.Decoder_res_2 = nn.Sequential(*[_resblock(nf, False) for _ in range(args.num_ResB_Dec)])
+        self.Dec_last1_2 = nn.Conv2d(nf, nf, 3, 1, 1, bias=True)
+        self.Dec_last2_2 = nn.Conv2d(nf, 9, 3, 1, 1, bias=True)
+        self._engines = {}
+        self._weights_version = None
+        # inference options that keep the returned final frames bit-identical
+        self.final_only = False
+
+    # ------------------------------------------------------------------
+    def _version(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def _engine(self, B, H, W, device) -> Engine:
+        ver = self._version()
+        if ver != self._weights_version:  # weights were (re)loaded or updated: repack
+            self._engines.clear()
+            self._weights_version = ver
+        key = (B, H, W, device.index)
+        if key not in self._engines:
+            self._engines.clear()  # one resolution at a time keeps the HBM footprint bounded
+            self._engines[key] = Engine(self.state_dict(), B, H, W, device)
+        return self._engines[key]
+
+    def forward(self, x, t_value, num_update=None, is_training=None, reuse_prefix=False):
+        """x: [B,3,4,H,W] fp32 in [-1,1] (frame order B0,B1,B-1,B2); t_value: [B,1] in (0,1).
+        Returns the reference's tuple (DeMFInet.py:170-179)."""
+        if not torch.cuda.is_available():
+            raise RuntimeError("demfi_b200.DeMFInet needs a B200 (sm_100a) GPU: there is no CPU fallback")
+        if is_training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError("backward through the sm_100a kernels is not implemented yet (SURVEY.md 8f-2); "
+                                      "wrap the call in torch.no_grad()")
+        dev = x.device if x.is_cuda else self.device
+        B, C, T, H, W = x.size()
+        if num_update is None:  # `summary()` dry run, DeMFInet.py:126-128
+            num_update = 1
+        eng = self._engine(B, H, W, dev)
+        res = eng.forward(x, t_value, int(num_update), reuse_prefix=reuse_prefix,
+                          final_only=self.final_only and not is_training)
+        sharps_dec1, sharps_final, flows, occs, two_blurry = res
+        if not (is_training or self.args.visualization_flag):
+            return sharps_dec1, sharps_final, flows, occs, two_blurry
+        # surface parity for the training / visualisation tuples (not on the inference hot path)
+        v = eng.views
+        diffs = []
+        weights = []
+        for d in range(2):
+            src = v["SE"].frames(d * B, B).ch(0, 64).to_nchw()
+            out = v["AGG1"].ch(64 * d, 64).to_nchw()
+            diff = torch.mean(torch.abs(out - src), 1, keepdim=True).view(B, -1)
+            diff = diff - diff.min(1, keepdim=True)[0]
+            diff = diff / diff.max(1, keepdim=True)[0]
+            diffs.append(diff.view(B, 1, H, W))
+            weights.append(v["WL"].frames(d * B, B).ch(0, 1).to_nchw())
+        difference_maps = [diffs[0], diffs[1], diffs[0], diffs[1]]
+        if is_training:
+            return (sharps_dec1, sharps_final, flows, occs, two_blurry, difference_maps,
+                    [[flows[0][:, 0:2], flows[0][:, 2:4]]])
+        if self.args.visualization_flag:
+            raise NotImplementedError("visualization_flag maps (utils.py:1480-1754) are out of scope (SURVEY.md 2, row 11)")
+        return sharps_dec1, sharps_final, flows, occs, two_blurry

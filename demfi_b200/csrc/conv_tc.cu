@@ -1,0 +1,424 @@
+// tcgen05 implicit-GEMM convolution for sm_100a: NHWC fp32 activations, fp32-parity via 3xTF32.
+//
+// GEMM view of a stride-1 "same" convolution: M = output pixels, N = output
+// channels (cout_pad, <= 256), K = taps x input channels.  One CTA tile is 8 rows x 16 columns of
+// output pixels (M = 128).  K is consumed in stages of (one tap, 32 input channels):
+//   * A stage  : a TMA 4-D box {32 ch, 16 x, 8 y, 1 n} of the NHWC source at the tap's offset,
+//                landed 128-byte-swizzled = the canonical K-major UMMA layout (row = pixel).
+//                Out-of-image coordinates and channels past the source's C are zero-filled by
+//                TMA: that IS the conv's zero padding and the ragged-K handling.
+//   * B stage  : the pre-packed [cout_pad x 32] weight tile, tf32 "hi" part and fp32 residual
+//                "lo" part, pre-swizzled on the host, fetched with one cp.async.bulk.
+//   * split    : four warps turn the fp32 A tile into hi = a & ~0x1fff (in place) and
+//                lo = a - hi (second buffer); D += Ahi*Bhi + Alo*Bhi + Ahi*Blo (fp32 accum in TMEM).
+// Persistent CTAs (one per SM) walk the tile list; warp roles:
+//   warps 0-3 split A | warps 4-7 epilogue (TMEM -> regs -> fused epilogue -> HBM)
+//   warp 8 TMA producer | warp 9 TMEM allocator + single-thread tcgen05.mma issuer
+// The accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <cuda.h>
+
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+namespace demfi {
+
+constexpr int TC_TH = 8, TC_TW = 16, TC_BM = 128, TC_KC = 32;
+constexpr int TC_A_BYTES = TC_BM * TC_KC * 4;  // 16 KiB
+constexpr int TC_THREADS = 320;
+constexpr int TC_MAX_STAGES = 6;
+constexpr int TC_SMEM_BUDGET = 200 * 1024;
+
+struct TcParams {
+  CUtensorMap tmap[DEMFI_MAX_SRC];
+  demfi_conv_t c;
+  int tiles_x, tiles_y, ntiles;
+  int stages, acc_stride, tmem_cols;
+  int mask_hi, split;
+};
+
+// ---- PTX wrappers -----------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug becomes a trapped launch (reported error), never a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 8000000000ll) {
+      printf("demfi conv_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", (int)blockIdx.x,
+             (int)threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128-byte-swizzle shared-memory matrix descriptor (sm_100 format): start address >> 4 in
+// bits [0,14), SBO (1024 B between 8-row groups) >> 4 in [32,46), version 1 in [46,48), layout
+// SWIZZLE_128B (2) in [61,64).  LBO is unused for a single 128-byte swizzle atom along K.
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// ---- kernel -----------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const demfi_conv_t& c = P.c;
+  const int N = c.cout_pad;
+  const uint32_t b_bytes = (uint32_t)N * 128u;
+  const uint32_t stage_bytes = 2u * TC_A_BYTES + 2u * b_bytes;
+  const int S = P.stages;
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bars = smem_base + (uint32_t)S * stage_bytes;  // 8-byte aligned (stage_bytes % 1024 == 0)
+  auto bar_full = [&](int s) { return bars + 8u * (uint32_t)s; };
+  auto bar_split = [&](int s) { return bars + 8u * (uint32_t)(S + s); };
+  auto bar_empty = [&](int s) { return bars + 8u * (uint32_t)(2 * S + s); };
+  auto bar_tfull = [&](int a) { return bars + 8u * (uint32_t)(3 * S + a); };
+  auto bar_tempty = [&](int a) { return bars + 8u * (uint32_t)(3 * S + 2 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (size_t)S * stage_bytes + 8 * (3 * S + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int taps = c.KH * c.KW;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_split(s), 128);
+      mbar_init(bar_empty(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull(a), 1);
+      mbar_init(bar_tempty(a), 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 9) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)P.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ===== A splitter: hi = a & ~0x1fff (tf32 bits), lo = a - hi (exact in fp32) =====
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+      for (int s = 0; s < c.nsrc; ++s)
+        for (int c0 = 0; c0 < c.src[s].C; c0 += TC_KC)
+          for (int tap = 0; tap < taps; ++tap) {
+            mbar_wait(bar_full(stage), phase);
+            if (P.split == 3) {
+              float4* a = reinterpret_cast<float4*>(smem + (size_t)stage * stage_bytes);
+              float4* lo = reinterpret_cast<float4*>(smem + (size_t)stage * stage_bytes + TC_A_BYTES);
+#pragma unroll
+              for (int j = 0; j < TC_A_BYTES / 16 / 128; ++j) {
+                const int i = threadIdx.x + j * 128;
+                const float4 v = a[i];
+                float4 h;
+                h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+                h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+                h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+                h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+                lo[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                if (P.mask_hi) a[i] = h;
+              }
+              fence_async_smem();
+            }
+            mbar_arrive(bar_split(stage));
+            if (++stage == S) { stage = 0; phase ^= 1; }
+          }
+    }
+  } else if (warp < 8) {
+    // ===== epilogue: TMEM lane = pixel row of the tile; warp w owns lanes 32*(w%4).. =====
+    const int wq = warp & 3;
+    const int m = wq * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+      int t = tile;
+      const int tx0 = (t % P.tiles_x) * TC_TW;
+      t /= P.tiles_x;
+      const int ty0 = (t % P.tiles_y) * TC_TH;
+      const int n = t / P.tiles_y;
+      const int oy = ty0 + (m >> 4), ox = tx0 + (m & 15);
+      const bool valid = (oy < c.H) && (ox < c.W);
+      mbar_wait(bar_tfull(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * P.acc_stride);
+      for (int col = 0; col < N; col += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + (uint32_t)col, r);
+        if (valid) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 b = ld4(c.bias + col + q * 4);
+            epilogue_store4(c, n, oy, ox, col + q * 4,
+                            make_float4(__uint_as_float(r[q * 4 + 0]) + b.x, __uint_as_float(r[q * 4 + 1]) + b.y,
+                                        __uint_as_float(r[q * 4 + 2]) + b.z, __uint_as_float(r[q * 4 + 3]) + b.w));
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_tempty(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp == 8) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+        int t = tile;
+        const int tx0 = (t % P.tiles_x) * TC_TW;
+        t /= P.tiles_x;
+        const int ty0 = (t % P.tiles_y) * TC_TH;
+        const int n = t / P.tiles_y;
+        int chunk = 0;
+        for (int s = 0; s < c.nsrc; ++s)
+          for (int c0 = 0; c0 < c.src[s].C; c0 += TC_KC, ++chunk)
+            for (int tap = 0; tap < taps; ++tap) {
+              const int ky = tap / c.KW, kx = tap - ky * c.KW;
+              mbar_wait(bar_empty(stage), phase ^ 1);
+              mbar_arrive_expect_tx(bar_full(stage), (uint32_t)TC_A_BYTES + 2u * b_bytes);
+              const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
+              tma_load_4d(sa, &P.tmap[s], bar_full(stage), c0, tx0 + kx - c.pad_w, ty0 + ky - c.pad_h, n);
+              const float* wsrc = c.wpack + ((size_t)chunk * taps + tap) * 2 * (size_t)N * TC_KC;
+              bulk_load(sa + 2u * TC_A_BYTES, wsrc, 2u * b_bytes, bar_full(stage));
+              if (++stage == S) { stage = 0; phase ^= 1; }
+            }
+      }
+    }
+  } else {
+    // ===== MMA issuer (warp 9, one thread) =====
+    if (lane == 0) {
+      // instruction descriptor: D=f32 (1<<4), A=B=tf32 (2<<7, 2<<10), both K-major, N>>3 at 17, M>>4 at 24
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+        mbar_wait(bar_tempty(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * P.acc_stride);
+        uint32_t accum = 0;
+        for (int s = 0; s < c.nsrc; ++s)
+          for (int c0 = 0; c0 < c.src[s].C; c0 += TC_KC)
+            for (int tap = 0; tap < taps; ++tap) {
+              mbar_wait(bar_split(stage), phase);
+              tc_fence_after();
+              const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
+              const uint64_t a_hi = make_desc_sw128(sa), a_lo = make_desc_sw128(sa + TC_A_BYTES);
+              const uint64_t b_hi = make_desc_sw128(sa + 2u * TC_A_BYTES), b_lo = make_desc_sw128(sa + 2u * TC_A_BYTES + b_bytes);
+#pragma unroll
+              for (int k = 0; k < TC_KC / 8; ++k) {
+                const uint64_t kk = (uint64_t)(k * 2);  // 32 bytes >> 4 per k-step of 8 tf32
+                umma_tf32(d_tmem, a_hi + kk, b_hi + kk, idesc, accum);
+                accum = 1;
+                if (P.split == 3) {
+                  umma_tf32(d_tmem, a_lo + kk, b_hi + kk, idesc, 1);
+                  umma_tf32(d_tmem, a_hi + kk, b_lo + kk, idesc, 1);
+                }
+              }
+              umma_commit(bar_empty(stage));
+              if (++stage == S) { stage = 0; phase ^= 1; }
+            }
+        umma_commit(bar_tfull(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)P.tmem_cols)
+                 : "memory");
+  }
+}
+
+// ---- host --------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+int launch_conv_tc(const demfi_conv_t& c, cudaStream_t st) {
+  DEMFI_REQUIRE(c.stride == 1 && c.Hi == c.H && c.Wi == c.W, "conv_tc: only stride-1 'same' convolutions");
+  DEMFI_REQUIRE(c.cout_pad % 16 == 0 && c.cout_pad >= 16 && c.cout_pad <= 256, "conv_tc: cout_pad %d not in 16..256 step 16", c.cout_pad);
+  EncodeTiledFn enc = get_encode_fn();
+  DEMFI_REQUIRE(enc != nullptr, "conv_tc: cuTensorMapEncodeTiled not available from the driver");
+  static thread_local TcParams P;  // CUtensorMap needs 64-byte alignment; thread_local storage gives it
+  memset(&P, 0, sizeof(P));
+  P.c = c;
+  for (int s = 0; s < c.nsrc; ++s) {
+    const demfi_src_t& S = c.src[s];
+    DEMFI_REQUIRE(S.up == 0, "conv_tc: up-sampled sources are not supported");
+    cuuint64_t dims[4] = {(cuuint64_t)S.C, (cuuint64_t)c.W, (cuuint64_t)c.H, (cuuint64_t)c.N};
+    cuuint64_t strides[3] = {(cuuint64_t)S.ld * 4, (cuuint64_t)S.ld * 4 * c.W, (cuuint64_t)S.ld * 4 * c.W * c.H};
+    cuuint32_t box[4] = {TC_KC, TC_TW, TC_TH, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&P.tmap[s], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(S.ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    DEMFI_REQUIRE(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled failed for source %d (CUresult %d)", s, (int)r);
+  }
+  P.tiles_x = (c.W + TC_TW - 1) / TC_TW;
+  P.tiles_y = (c.H + TC_TH - 1) / TC_TH;
+  const long long nt = (long long)P.tiles_x * P.tiles_y * c.N;
+  DEMFI_REQUIRE(nt > 0 && nt < (1ll << 31), "conv_tc: bad tile count");
+  P.ntiles = (int)nt;
+  const int stage_bytes = 2 * TC_A_BYTES + 2 * c.cout_pad * 128;
+  int stages = TC_SMEM_BUDGET / stage_bytes;
+  if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+  DEMFI_REQUIRE(stages >= 2, "conv_tc: not enough shared memory for two stages");
+  P.stages = stages;
+  int acc_stride = 32;
+  while (acc_stride < c.cout_pad) acc_stride *= 2;
+  P.acc_stride = acc_stride;
+  P.tmem_cols = 2 * acc_stride;
+  P.mask_hi = get_option("tc_mask_hi");
+  P.split = get_option("tc_split");
+  const int smem = stages * stage_bytes + 8 * (3 * stages + 4) + 16 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    DEMFI_REQUIRE(e == cudaSuccess, "conv_tc: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int grid = P.ntiles < num_sms() ? P.ntiles : num_sms();
+  conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(P);
+  DEMFI_LAUNCH_CHECK("conv_tc");
+  return 0;
+}
+
+// packed layout: for chunk (source-major, 32 channels) and tap: [hi tile][lo tile], each tile
+// [cout_pad rows][32 floats] with the 16-byte groups of row n XOR-ed by (n & 7) (128B swizzle).
+size_t tc_packed_floats(int KH, int KW, const int32_t* src_C, int nsrc, int cout_pad) {
+  size_t chunks = 0;
+  for (int s = 0; s < nsrc; ++s) chunks += (size_t)(src_C[s] + TC_KC - 1) / TC_KC;
+  return chunks * KH * KW * 2 * (size_t)cout_pad * TC_KC;
+}
+
+int tc_pack_weights(const float* w, int Co, int Ci, int KH, int KW, const int32_t* in_map, const int32_t* src_C,
+                    int nsrc, const int32_t* out_map, int cout_pad, float* out) {
+  DEMFI_REQUIRE(cout_pad % 16 == 0 && cout_pad <= 256, "tc_pack_weights: cout_pad must be a multiple of 16 and <= 256");
+  const int taps = KH * KW;
+  const size_t tile = (size_t)cout_pad * TC_KC;
+  size_t chunk = 0;
+  int kbase = 0;
+  for (int s = 0; s < nsrc; ++s) {
+    for (int c0 = 0; c0 < src_C[s]; c0 += TC_KC, ++chunk) {
+      for (int tap = 0; tap < taps; ++tap) {
+        float* hi = out + (chunk * taps + tap) * 2 * tile;
+        float* lo = hi + tile;
+        for (int n = 0; n < cout_pad; ++n)
+          for (int k = 0; k < TC_KC; ++k) {
+            float v = 0.0f;
+            const int c = c0 + k;
+            if (c < src_C[s]) {
+              const int ci = in_map[kbase + c], co = out_map[n];
+              if (ci >= 0 && co >= 0) v = w[((size_t)co * Ci + ci) * taps + tap];
+            }
+            uint32_t bits;
+            memcpy(&bits, &v, 4);
+            bits &= 0xffffe000u;
+            float h;
+            memcpy(&h, &bits, 4);
+            const size_t off = (size_t)n * TC_KC + (size_t)(((k >> 2) ^ (n & 7)) << 2) + (k & 3);
+            hi[off] = h;
+            lo[off] = v - h;
+          }
+      }
+    }
+    kbase += src_C[s];
+  }
+  return 0;
+}
+
+}  // namespace demfi

@@ -1,0 +1,394 @@
+// HBM-bound operators of the DeMFI-Net hot path (NHWC fp32, 128-bit accesses):
+// input unpack, complementary-flow-reversal splat, bwarp + Eq.(2) blend, FGAC sampling and
+// Eq.(4) blend, channel-slice copies and NCHW import/export.
+#include "common.cuh"
+
+namespace demfi {
+
+// ------------------------------------------------------------------------------------------
+// Bilinear corner setup with the reference's coordinate arithmetic.
+// bwarp (DeMFInet.py:750-757): g = 2*(x + f)/max(W-1,1) - 1, then grid_sample(align_corners=True)
+// un-normalises ((g+1)/2)*(W-1).  The fp32 round trip is kept so that floor() and the 0.999
+// validity threshold see the same numbers the reference sees.
+struct Corners {
+  int x0, y0;
+  float w00, w01, w10, w11;  // [dy][dx], already zeroed for out-of-image corners
+  float wsum;
+};
+
+__device__ __forceinline__ Corners make_corners(float px, float py, int H, int W) {
+  Corners c;
+  const float fx0 = floorf(px), fy0 = floorf(py);
+  // ATen grid_sampler: w_nw = (x_se - x)*(y_se - y) etc.
+  const float wx0 = (fx0 + 1.0f) - px, wx1 = px - fx0;
+  const float wy0 = (fy0 + 1.0f) - py, wy1 = py - fy0;
+  // clamp before the int conversion so absurd flows cannot overflow
+  c.x0 = (int)fminf(fmaxf(fx0, -2.0f), (float)W);
+  c.y0 = (int)fminf(fmaxf(fy0, -2.0f), (float)H);
+  const bool x0in = (c.x0 >= 0 && c.x0 < W), x1in = (c.x0 + 1 >= 0 && c.x0 + 1 < W);
+  const bool y0in = (c.y0 >= 0 && c.y0 < H), y1in = (c.y0 + 1 >= 0 && c.y0 + 1 < H);
+  c.w00 = (x0in && y0in) ? wx0 * wy0 : 0.0f;
+  c.w01 = (x1in && y0in) ? wx1 * wy0 : 0.0f;
+  c.w10 = (x0in && y1in) ? wx0 * wy1 : 0.0f;
+  c.w11 = (x1in && y1in) ? wx1 * wy1 : 0.0f;
+  c.wsum = ((c.w00 + c.w01) + c.w10) + c.w11;
+  return c;
+}
+
+__device__ __forceinline__ float bwarp_coord(int i, float f, int size) {
+  const float g = 2.0f * ((float)i + f) / (float)max(size - 1, 1) - 1.0f;
+  return ((g + 1.0f) / 2.0f) * (float)(size - 1);
+}
+
+__device__ __forceinline__ float4 gather4(const float* img, int ld, int n, int H, int W, const Corners& c, int ch) {
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* base = img + (size_t)n * H * W * ld + ch;
+  if (c.w00 != 0.0f) { const float4 v = __ldg((const float4*)(base + ((size_t)c.y0 * W + c.x0) * ld));
+    r.x += v.x * c.w00; r.y += v.y * c.w00; r.z += v.z * c.w00; r.w += v.w * c.w00; }
+  if (c.w01 != 0.0f) { const float4 v = __ldg((const float4*)(base + ((size_t)c.y0 * W + c.x0 + 1) * ld));
+    r.x += v.x * c.w01; r.y += v.y * c.w01; r.z += v.z * c.w01; r.w += v.w * c.w01; }
+  if (c.w10 != 0.0f) { const float4 v = __ldg((const float4*)(base + ((size_t)(c.y0 + 1) * W + c.x0) * ld));
+    r.x += v.x * c.w10; r.y += v.y * c.w10; r.z += v.z * c.w10; r.w += v.w * c.w10; }
+  if (c.w11 != 0.0f) { const float4 v = __ldg((const float4*)(base + ((size_t)(c.y0 + 1) * W + c.x0 + 1) * ld));
+    r.x += v.x * c.w11; r.y += v.y * c.w11; r.z += v.z * c.w11; r.w += v.w * c.w11; }
+  return r;
+}
+
+__device__ __forceinline__ float gather1(const float* img, int ld, int n, int H, int W, const Corners& c, int ch) {
+  float r = 0.f;
+  const float* base = img + (size_t)n * H * W * ld + ch;
+  if (c.w00 != 0.0f) r += __ldg(base + ((size_t)c.y0 * W + c.x0) * ld) * c.w00;
+  if (c.w01 != 0.0f) r += __ldg(base + ((size_t)c.y0 * W + c.x0 + 1) * ld) * c.w01;
+  if (c.w10 != 0.0f) r += __ldg(base + ((size_t)(c.y0 + 1) * W + c.x0) * ld) * c.w10;
+  if (c.w11 != 0.0f) r += __ldg(base + ((size_t)(c.y0 + 1) * W + c.x0 + 1) * ld) * c.w11;
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// bwarp + Eq.(2).  LPP lanes cooperate on one pixel, each lane owning 4 channels per pass.
+template <int LPP>
+__global__ void __launch_bounds__(256)
+bwarp_blend_kernel(const float* __restrict__ a, int a_ld, const float* __restrict__ b, int b_ld,
+                   const float* __restrict__ flow, int flow_ld, const float* __restrict__ occ, int occ_ld,
+                   const float* __restrict__ tv, int B, int H, int W, int C, float* __restrict__ out, int out_ld,
+                   float* __restrict__ occ_out, int occ_out_ld) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long pix = gid / LPP;
+  const int lane = (int)(gid % LPP);
+  const long long npix = (long long)B * H * W;
+  if (pix >= npix) return;
+  const int x = (int)(pix % W);
+  const int y = (int)((pix / W) % H);
+  const int n = (int)(pix / ((long long)W * H));
+  const float4 f = __ldg((const float4*)(flow + pix * flow_ld));
+  const float o0 = sigmoid_f(__ldg(occ + pix * occ_ld));
+  const float o1 = 1.0f - o0;
+  const float t = __ldg(tv + n);
+  const Corners ca = make_corners(bwarp_coord(x, f.x, W), bwarp_coord(y, f.y, H), H, W);
+  const Corners cb = make_corners(bwarp_coord(x, f.z, W), bwarp_coord(y, f.w, H), H, W);
+  // bwarp's validity mask: warped ones < 0.999 -> 0 (DeMFInet.py:758-766)
+  const float ma = ca.wsum < 0.999f ? 0.0f : 1.0f;
+  const float mb = cb.wsum < 0.999f ? 0.0f : 1.0f;
+  const float ka = (1.0f - t) * o0, kb = t * o1;
+  const float den = ka + kb;
+  if (lane == 0 && occ_out != nullptr) occ_out[pix * occ_out_ld] = o0;
+  if (C % 4 == 0) {
+    for (int ch = lane * 4; ch < C; ch += LPP * 4) {
+      const float4 va = gather4(a, a_ld, n, H, W, ca, ch);
+      const float4 vb = gather4(b, b_ld, n, H, W, cb, ch);
+      float4 r;
+      r.x = (ka * (va.x * ma) + kb * (vb.x * mb)) / den;
+      r.y = (ka * (va.y * ma) + kb * (vb.y * mb)) / den;
+      r.z = (ka * (va.z * ma) + kb * (vb.z * mb)) / den;
+      r.w = (ka * (va.w * ma) + kb * (vb.w * mb)) / den;
+      st4(out + pix * out_ld + ch, r);
+    }
+  } else {
+    for (int ch = lane; ch < C; ch += LPP) {
+      const float va = gather1(a, a_ld, n, H, W, ca, ch);
+      const float vb = gather1(b, b_ld, n, H, W, cb, ch);
+      out[pix * out_ld + ch] = (ka * (va * ma) + kb * (vb * mb)) / den;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// FGAC sampling: absolute coordinates = flow values (DeMFInet.py:413-419, 499-508).
+template <int LPP>
+__global__ void __launch_bounds__(256)
+fgac_sample_kernel(const float* __restrict__ refk, int refk_ld, const float* __restrict__ flow, int flow_ld, int B,
+                   int H, int W, int C, float* __restrict__ out, int out_ld) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long pix = gid / LPP;
+  const int lane = (int)(gid % LPP);
+  const long long npix = (long long)B * H * W;
+  if (pix >= npix) return;
+  const int n = (int)(pix / ((long long)W * H));
+  const float2 f = __ldg((const float2*)(flow + pix * flow_ld));
+  // bilinear_sampler: g = 2*f/(W-1) - 1; grid_sample: ((g+1)/2)*(W-1)
+  const float gx = 2.0f * f.x / (float)(W - 1) - 1.0f;
+  const float gy = 2.0f * f.y / (float)(H - 1) - 1.0f;
+  const Corners c = make_corners(((gx + 1.0f) / 2.0f) * (float)(W - 1), ((gy + 1.0f) / 2.0f) * (float)(H - 1), H, W);
+  for (int ch = lane * 4; ch < C; ch += LPP * 4) st4(out + pix * out_ld + ch, gather4(refk, refk_ld, n, H, W, c, ch));
+}
+
+template <int LPP>
+__global__ void __launch_bounds__(256)
+fgac_blend_kernel(const float* __restrict__ w, int w_ld, const float* __restrict__ src, int src_ld,
+                  const float* __restrict__ e, int e_ld, long long npix, int C, float* __restrict__ out, int out_ld) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long pix = gid / LPP;
+  const int lane = (int)(gid % LPP);
+  if (pix >= npix) return;
+  const float ww = __ldg(w + pix * w_ld);
+  for (int ch = lane * 4; ch < C; ch += LPP * 4) {
+    const float4 s = __ldg((const float4*)(src + pix * src_ld + ch));
+    const float4 v = __ldg((const float4*)(e + pix * e_ld + ch));
+    float4 r;
+    r.x = ww * s.x + (1.0f - ww) * v.x; r.y = ww * s.y + (1.0f - ww) * v.y;
+    r.z = ww * s.z + (1.0f - ww) * v.z; r.w = ww * s.w + (1.0f - ww) * v.w;
+    st4(out + pix * out_ld + ch, r);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// CFR: Gaussian forward splat.  acc layout per pixel: {a01.x, a01.y, n0, -, a10.x, a10.y, n1, -}.
+__device__ __forceinline__ void splat_one(float* acc, int n, int H, int W, int r, int c, float vx, float vy, float dx,
+                                          float dy, int slot) {
+  const float fy = floorf(dy), fx = floorf(dx);
+  const int iy = (int)fminf(fmaxf(fy, -(float)H - 2.f), (float)H + 2.f);
+  const int ix = (int)fminf(fmaxf(fx, -(float)W - 2.f), (float)W + 2.f);
+#pragma unroll
+  for (int oy = 0; oy < 2; ++oy)
+#pragma unroll
+    for (int ox = 0; ox < 2; ++ox) {
+      const float cy = fy + (float)oy, cx = fx + (float)ox;
+      // get_gaussian_weights, DeMFInet.py:674-680 (x there is the row displacement)
+      const float wgt = expf(-((dy - cy) * (dy - cy) + (dx - cx) * (dx - cx)));
+      const int tr = r + iy + oy, tc = c + ix + ox;
+      if (tr >= 0 && tr < H && tc >= 0 && tc < W) {
+        float* d = acc + (((size_t)n * H + tr) * W + tc) * 8 + slot;
+        atomicAdd(d + 0, vx * wgt);
+        atomicAdd(d + 1, vy * wgt);
+        atomicAdd(d + 2, wgt);
+      }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+cfr_splat_kernel(const float* __restrict__ fo, int fo_ld, const float* __restrict__ tv, int B, int H, int W,
+                 float* __restrict__ acc) {
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= (long long)B * H * W) return;
+  const int c = (int)(pix % W);
+  const int r = (int)((pix / W) % H);
+  const int n = (int)(pix / ((long long)W * H));
+  const float t = __ldg(tv + n);
+  const float4 f = __ldg((const float4*)(fo + pix * fo_ld));
+  // fwarp(flow_01, t*flow_01); fwarp(flow_10, (1-t)*flow_10)  (DeMFInet.py:609-612)
+  splat_one(acc, n, H, W, r, c, f.x, f.y, t * f.x, t * f.y, 0);
+  splat_one(acc, n, H, W, r, c, f.z, f.w, (1.0f - t) * f.z, (1.0f - t) * f.w, 4);
+}
+
+__global__ void __launch_bounds__(256)
+cfr_finalize_kernel(const float* __restrict__ acc, const float* __restrict__ tv, int B, int H, int W,
+                    float* __restrict__ out, int out_ld) {
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= (long long)B * H * W) return;
+  const int n = (int)(pix / ((long long)W * H));
+  const float t = __ldg(tv + n);
+  const float4 a = __ldg((const float4*)(acc + pix * 8));
+  const float4 b = __ldg((const float4*)(acc + pix * 8 + 4));
+  // DeMFInet.py:614-620
+  const float k00 = -(1.0f - t) * t, k01 = t * t, k10 = (1.0f - t) * (1.0f - t), k11 = t * (1.0f - t);
+  float4 r;
+  r.x = k00 * a.x + k01 * b.x;
+  r.y = k00 * a.y + k01 * b.y;
+  r.z = k10 * a.x - k11 * b.x;
+  r.w = k10 * a.y - k11 * b.y;
+  const float norm = (1.0f - t) * a.z + t * b.z;
+  if (norm > 0.0f) { r.x /= norm; r.y /= norm; r.z /= norm; r.w /= norm; }
+  st4(out + pix * out_ld, r);
+}
+
+// ------------------------------------------------------------------------------------------
+// Input unpack: x [B,3,4,H,W] -> s2d [B,H/2,W/2,48], frames12 slices, mean(B0,B1) NCHW.
+__global__ void __launch_bounds__(256)
+pack_input_kernel(const float* __restrict__ x, int B, int H, int W, float* __restrict__ s2d, float* __restrict__ f12a,
+                  int f12a_ld, float* __restrict__ f12b, int f12b_ld, float* __restrict__ mean01) {
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= (long long)B * H * W) return;
+  const int xx = (int)(pix % W);
+  const int yy = (int)((pix / W) % H);
+  const int n = (int)(pix / ((long long)W * H));
+  const size_t plane = (size_t)H * W;
+  const float* xb = x + (size_t)n * 12 * plane + (size_t)yy * W + xx;
+  float v[12];  // v[t*3 + c] = x[n, c, t, yy, xx]
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int t = 0; t < 4; ++t) v[t * 3 + c] = __ldg(xb + (size_t)(c * 4 + t) * plane);
+  if (f12a) {
+#pragma unroll
+    for (int k = 0; k < 12; ++k) f12a[pix * f12a_ld + k] = v[k];
+  }
+  if (f12b) {
+#pragma unroll
+    for (int k = 0; k < 12; ++k) f12b[pix * f12b_ld + k] = v[k];
+  }
+  if (mean01) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) mean01[((size_t)n * 3 + c) * plane + (size_t)yy * W + xx] = (v[c] + v[3 + c]) / 2.0f;
+  }
+  if (s2d) {
+    // pixel_reshuffle: out channel = cc*4 + dy*2 + dx, cc = t*3 + c  (DeMFInet.py:311-316)
+    const int h2 = H >> 1, w2 = W >> 1;
+    float* d = s2d + (((size_t)n * h2 + (yy >> 1)) * w2 + (xx >> 1)) * 48 + (yy & 1) * 2 + (xx & 1);
+#pragma unroll
+    for (int k = 0; k < 12; ++k) d[k * 4] = v[k];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+copy_channels_kernel(const float* __restrict__ src, int src_ld, float* __restrict__ dst, int dst_ld, int nch,
+                     long long npix, int act) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix * nch) return;
+  const long long pix = i / nch;
+  const int c = (int)(i % nch);
+  dst[pix * dst_ld + c] = act_scalar(act, __ldg(src + pix * src_ld + c));
+}
+
+__global__ void __launch_bounds__(256)
+export_nchw_kernel(const float* __restrict__ src, int src_ld, int B, int H, int W, int C, int act,
+                   float* __restrict__ dst) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long plane = (long long)H * W;
+  if (i >= (long long)B * C * plane) return;
+  const long long p = i % plane;
+  const int c = (int)((i / plane) % C);
+  const long long n = i / (plane * C);
+  dst[i] = act_scalar(act, __ldg(src + (n * plane + p) * src_ld + c));
+}
+
+__global__ void __launch_bounds__(256)
+import_nchw_kernel(const float* __restrict__ src, int B, int H, int W, int C, float* __restrict__ dst, int dst_ld) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long plane = (long long)H * W;
+  if (i >= (long long)B * C * plane) return;
+  const int c = (int)(i % C);
+  const long long p = (i / C) % plane;
+  const long long n = i / (plane * C);
+  dst[(n * plane + p) * dst_ld + c] = __ldg(src + (n * C + c) * plane + p);
+}
+
+static inline unsigned blocks_for(long long n, int per = 256) { return (unsigned)((n + per - 1) / per); }
+
+}  // namespace demfi
+
+using namespace demfi;
+
+extern "C" {
+
+int demfi_bwarp_blend(const float* a, int32_t a_ld, const float* b, int32_t b_ld, const float* flow, int32_t flow_ld,
+                      const float* occ, int32_t occ_ld, const float* t, int32_t B, int32_t H, int32_t W, int32_t C,
+                      float* out, int32_t out_ld, float* occ_out, int32_t occ_out_ld, void* stream) {
+  if (check_device()) return 3;
+  DEMFI_REQUIRE(B > 0 && H > 1 && W > 1 && C > 0, "bwarp_blend: bad shape B=%d H=%d W=%d C=%d", B, H, W, C);
+  DEMFI_REQUIRE(flow_ld % 4 == 0 && ((uintptr_t)flow % 16) == 0, "bwarp_blend: flow slice must be 16-byte aligned");
+  if (C % 4 == 0)
+    DEMFI_REQUIRE(a_ld % 4 == 0 && b_ld % 4 == 0 && out_ld % 4 == 0 && ((uintptr_t)a % 16) == 0 &&
+                      ((uintptr_t)b % 16) == 0 && ((uintptr_t)out % 16) == 0,
+                  "bwarp_blend: vector path needs 16-byte aligned slices");
+  const long long npix = (long long)B * H * W;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C >= 64)
+    bwarp_blend_kernel<16><<<blocks_for(npix * 16), 256, 0, st>>>(a, a_ld, b, b_ld, flow, flow_ld, occ, occ_ld, t, B, H,
+                                                                  W, C, out, out_ld, occ_out, occ_out_ld);
+  else
+    bwarp_blend_kernel<1><<<blocks_for(npix), 256, 0, st>>>(a, a_ld, b, b_ld, flow, flow_ld, occ, occ_ld, t, B, H, W, C,
+                                                            out, out_ld, occ_out, occ_out_ld);
+  DEMFI_LAUNCH_CHECK("bwarp_blend");
+  return 0;
+}
+
+int demfi_fgac_sample(const float* refk, int32_t refk_ld, const float* flow, int32_t flow_ld, int32_t B, int32_t H,
+                      int32_t W, int32_t C, float* out, int32_t out_ld, void* stream) {
+  if (check_device()) return 3;
+  DEMFI_REQUIRE(B > 0 && H > 1 && W > 1 && C > 0 && C % 4 == 0, "fgac_sample: bad shape");
+  DEMFI_REQUIRE(refk_ld % 4 == 0 && out_ld % 4 == 0 && flow_ld % 2 == 0 && ((uintptr_t)flow % 8) == 0 &&
+                    ((uintptr_t)refk % 16) == 0 && ((uintptr_t)out % 16) == 0, "fgac_sample: misaligned slices");
+  const long long npix = (long long)B * H * W;
+  fgac_sample_kernel<16><<<blocks_for(npix * 16), 256, 0, (cudaStream_t)stream>>>(refk, refk_ld, flow, flow_ld, B, H, W,
+                                                                                   C, out, out_ld);
+  DEMFI_LAUNCH_CHECK("fgac_sample");
+  return 0;
+}
+
+int demfi_fgac_blend(const float* w, int32_t w_ld, const float* src, int32_t src_ld, const float* e, int32_t e_ld,
+                     int64_t npix, int32_t C, float* out, int32_t out_ld, void* stream) {
+  if (check_device()) return 3;
+  DEMFI_REQUIRE(npix > 0 && C > 0 && C % 4 == 0 && src_ld % 4 == 0 && e_ld % 4 == 0 && out_ld % 4 == 0,
+                "fgac_blend: bad shape");
+  fgac_blend_kernel<16><<<blocks_for(npix * 16), 256, 0, (cudaStream_t)stream>>>(w, w_ld, src, src_ld, e, e_ld, npix, C,
+                                                                                  out, out_ld);
+  DEMFI_LAUNCH_CHECK("fgac_blend");
+  return 0;
+}
+
+int demfi_cfr_splat(const float* fo, int32_t fo_ld, const float* t, int32_t B, int32_t H, int32_t W, float* acc,
+                    void* stream) {
+  if (check_device()) return 3;
+  DEMFI_REQUIRE(B > 0 && H > 0 && W > 0 && fo_ld % 4 == 0 && ((uintptr_t)fo % 16) == 0, "cfr_splat: bad arguments");
+  cfr_splat_kernel<<<blocks_for((long long)B * H * W), 256, 0, (cudaStream_t)stream>>>(fo, fo_ld, t, B, H, W, acc);
+  DEMFI_LAUNCH_CHECK("cfr_splat");
+  return 0;
+}
+
+int demfi_cfr_finalize(const float* acc, const float* t, int32_t B, int32_t H, int32_t W, float* out, int32_t out_ld,
+                       void* stream) {
+  if (check_device()) return 3;
+  DEMFI_REQUIRE(B > 0 && H > 0 && W > 0 && out_ld % 4 == 0 && ((uintptr_t)out % 16) == 0, "cfr_finalize: bad arguments");
+  cfr_finalize_kernel<<<blocks_for((long long)B * H * W), 256, 0, (cudaStream_t)stream>>>(acc, t, B, H, W, out, out_ld);
+  DEMFI_LAUNCH_CHECK("cfr_finalize");
+  return 0;
+}
+
+int demfi_pack_input(const float* x, int32_t B, int32_t H, int32_t W, float* s2d, float* f12a, int32_t f12a_ld,
+                     float* f12b, int32_t f12b_ld, float* mean01, void* stream) {
+  if (check_device()) return 3;
+  DEMFI_REQUIRE(B > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "pack_input: H and W must be even");
+  pack_input_kernel<<<blocks_for((long long)B * H * W), 256, 0, (cudaStream_t)stream>>>(x, B, H, W, s2d, f12a, f12a_ld,
+                                                                                         f12b, f12b_ld, mean01);
+  DEMFI_LAUNCH_CHECK("pack_input");
+  return 0;
+}
+
+int demfi_copy_channels(const float* src, int32_t src_ld, float* dst, int32_t dst_ld, int32_t nch, int64_t npix,
+                        int32_t act, void* stream) {
+  if (check_device()) return 3;
+  DEMFI_REQUIRE(nch > 0 && npix > 0, "copy_channels: bad shape");
+  copy_channels_kernel<<<blocks_for(npix * nch), 256, 0, (cudaStream_t)stream>>>(src, src_ld, dst, dst_ld, nch, npix, act);
+  DEMFI_LAUNCH_CHECK("copy_channels");
+  return 0;
+}
+
+int demfi_export_nchw(const float* src, int32_t src_ld, int32_t B, int32_t H, int32_t W, int32_t C, int32_t act,
+                      float* dst, void* stream) {
+  if (check_device()) return 3;
+  DEMFI_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0, "export_nchw: bad shape");
+  export_nchw_kernel<<<blocks_for((long long)B * C * H * W), 256, 0, (cudaStream_t)stream>>>(src, src_ld, B, H, W, C, act, dst);
+  DEMFI_LAUNCH_CHECK("export_nchw");
+  return 0;
+}
+
+int demfi_import_nchw(const float* src, int32_t B, int32_t H, int32_t W, int32_t C, float* dst, int32_t dst_ld,
+                      void* stream) {
+  if (check_device()) return 3;
+  DEMFI_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0, "import_nchw: bad shape");
+  import_nchw_kernel<<<blocks_for((long long)B * C * H * W), 256, 0, (cudaStream_t)stream>>>(src, B, H, W, C, dst, dst_ld);
+  DEMFI_LAUNCH_CHECK("import_nchw");
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,489 @@
+"""Host-side plan of the DeMFI-Net forward / recursive-boosting path on one B200.
+
+The engine owns, for one (batch, H, W):
+  * the NHWC fp32 activation buffers in HBM (every `torch.cat` of DeMFInet.py is a channel
+    slice of one of these buffers -- producers write straight into their consumer's slot);
+  * the repacked weights (channel orders permuted to the internal slot orders, see `_Maps`);
+  * the list of C-ABI calls (`include/demfi_b200.h`) that make up `DeMFInet.forward`
+    (DeMFInet.py:46-179).  PyTorch is used for device memory and the stream only.
+
+Internal channel orders differ from the reference's concat orders where that keeps 16-byte
+alignment; the permutation is folded into the weight packing (in_map / out_map), so results
+are those of the reference graph.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _abi as A
+
+NF = 64
+
+
+def _ru(x, m):
+    return (x + m - 1) // m * m
+
+
+class View:
+    """A channel slice of an NHWC fp32 buffer: element (n,y,x,c) at ptr + (((n*H+y)*W+x)*ld + c)*4."""
+    __slots__ = ("t", "N", "H", "W", "ld", "c0", "C", "n0")
+
+    def __init__(self, t: torch.Tensor, N, H, W, ld, c0=0, C_=None, n0=0):
+        self.t, self.N, self.H, self.W, self.ld, self.c0, self.n0 = t, N, H, W, ld, c0, n0
+        self.C = ld - c0 if C_ is None else C_
+
+    @property
+    def ptr(self) -> int:
+        return self.t.data_ptr() + 4 * (self.n0 * self.H * self.W * self.ld + self.c0)
+
+    def ch(self, c0, C_):
+        assert c0 + C_ <= self.C + (self.ld - self.c0 - self.C) + 0 or True
+        return View(self.t, self.N, self.H, self.W, self.ld, self.c0 + c0, C_, self.n0)
+
+    def frames(self, n0, N):
+        """batch sub-range [n0, n0+N)"""
+        return View(self.t, N, self.H, self.W, self.ld, self.c0, self.C, self.n0 + n0)
+
+    def npix(self):
+        return self.N * self.H * self.W
+
+    def to_nchw(self) -> torch.Tensor:
+        """debug / test read-back (torch indexing, not a product path)"""
+        full = self.t.view(-1, self.H, self.W, self.ld)[self.n0:self.n0 + self.N, :, :, self.c0:self.c0 + self.C]
+        return full.permute(0, 3, 1, 2).contiguous()
+
+
+class Engine:
+    def __init__(self, state_dict: Dict[str, torch.Tensor], B: int, H: int, W: int, device: torch.device,
+                 conv_kind: Optional[str] = None, dry: bool = False):
+        """dry=True builds the plan (buffers, channel maps, packed weights) on the host without a
+        GPU so that the host logic can be checked on CPU; such an engine cannot run."""
+        if H % 8 or W % 8:
+            raise ValueError(f"H and W must be multiples of 8 (UNet's three stride-2 convs, DeMFInet.py:575-577); got {H}x{W}")
+        self.lib = A.lib()
+        self.B, self.H, self.W, self.dev = B, H, W, device
+        self.dry = dry
+        if not dry:
+            A.check(self.lib.demfi_device_check(device.index or 0), "demfi_device_check")
+        self.conv_kind = (conv_kind or os.environ.get("DEMFI_CONV_KIND", "auto")).lower()
+        assert self.conv_kind in ("auto", "ffma", "tc")
+        self._keep: list = []  # weights, ctypes structs
+        self.bufs: Dict[str, torch.Tensor] = {}
+        self.views: Dict[str, View] = {}
+        self._alloc()
+        self._sd = {k: v.detach().to("cpu", torch.float32).contiguous() for k, v in state_dict.items()}
+        self._wcache: Dict[tuple, tuple] = {}
+        self._build()
+
+    # ------------------------------------------------------------------ memory
+    def _buf(self, name, N, H, W, ld) -> View:
+        t = torch.zeros(N * H * W * ld, dtype=torch.float32, device=self.dev)
+        self.bufs[name] = t
+        return View(t, N, H, W, ld)
+
+    def _alloc(self):
+        B, H, W = self.B, self.H, self.W
+        h, w = H // 2, W // 2
+        v = self.views
+        v["S2D"] = self._buf("S2D", B, h, w, 48)
+        v["F1"] = self._buf("F1", B, h, w, 96)
+        v["T"] = self._buf("T", B, h, w, 96 + 12 * 224)
+        v["G"] = self._buf("G", B, h, w, 1152)
+        v["GF0"] = self._buf("GF0", B, h, w, 96)
+        v["TR"] = self._buf("TR", B, h, w, 96)
+        v["U"] = self._buf("U", B, H, W, 64)
+        v["F01"] = self._buf("F01", 2 * B, H, W, 64)
+        v["FO"] = self._buf("FO", B, H, W, 8)
+        v["ACC"] = self._buf("ACC", B, H, W, 8)
+        v["AGG1"] = self._buf("AGG1", B, H, W, 204)
+        for i in range(3):
+            v[f"P{i}"] = self._buf(f"P{i}", 3 * B, H, W, 64)  # ResBlock ping-pong pool (FAC-FB enc, D1, D2)
+        v["SE"] = self._buf("SE", 2 * B, H, W, 128)
+        v["RK"] = self._buf("RK", 2 * B, H, W, 64)
+        v["SMP"] = self._buf("SMP", 2 * B, H, W, 64)
+        v["WG"] = self._buf("WG", 2 * B, H, W, 64)
+        v["WL"] = self._buf("WL", 2 * B, H, W, 4)
+        v["EN1"] = self._buf("EN1", B, h, w, 64)
+        v["EN2"] = self._buf("EN2", B, h // 2, w // 2, 128)
+        v["EN3"] = self._buf("EN3", B, h // 4, w // 4, 256)
+        v["DE0"] = self._buf("DE0", B, h // 4, w // 4, 256)
+        v["DE1"] = self._buf("DE1", B, h // 2, w // 2, 128)
+        v["DE2"] = self._buf("DE2", B, h, w, 64)
+        v["DECIN"] = self._buf("DECIN", 3 * B, H, W, 64)
+        v["SP"] = self._buf("SP", 3 * B, H, W, 4)
+        v["DL0"] = self._buf("DL0", B, H, W, 8)
+        v["DL1"] = self._buf("DL1", B, H, W, 8)
+        v["REF"] = self._buf("REF", B, H, W, 32)
+        v["A3"] = self._buf("A3", B, H, W, 36)
+        for i in range(3):
+            v[f"FR{i}"] = self._buf(f"FR{i}", B, H, W, 64)
+        v["R1"] = self._buf("R1", B, H, W, 32)
+        v["RD"] = self._buf("RD", B, H, W, 64)
+        v["D1B"] = self._buf("D1B", B, H, W, 32)
+        v["BL1"] = self._buf("BL1", B, H, W, 32)
+        v["X"] = self._buf("X", B, H, W, 64)
+        v["Z"] = self._buf("Z", B, H, W, 64)
+        v["RH"] = self._buf("RH", B, H, W, 64)
+        v["FO1"] = self._buf("FO1", B, H, W, 32)
+        v["D2O"] = self._buf("D2O", B, H, W, 12)
+        self.t_dev = torch.zeros(B, dtype=torch.float32, device=self.dev)
+
+    def workspace_bytes(self) -> int:
+        return sum(t.numel() * 4 for t in self.bufs.values())
+
+    # ------------------------------------------------------------------ op construction
+    def _weight(self, names: Sequence[str]) -> Tuple[np.ndarray, np.ndarray]:
+        ws, bs = [], []
+        for n in names:
+            w = self._sd[n + ".weight"]
+            if w.dim() == 5:  # Conv3d [Co,Ci,1,3,3] == per-frame Conv2d (DeMFInet.py:30-34)
+                w = w[:, :, 0]
+            ws.append(w)
+            bs.append(self._sd[n + ".bias"])
+        return (np.ascontiguousarray(torch.cat(ws, 0).numpy()), np.ascontiguousarray(torch.cat(bs, 0).numpy()))
+
+    def _pick_kind(self, KH, KW, stride, pad, srcs, cout_pad):
+        eligible = (stride == 1 and all(u == 0 for _, u in srcs) and pad == (KH // 2, KW // 2)
+                    and KH % 2 == 1 and KW % 2 == 1 and cout_pad % 16 == 0 and cout_pad <= 256)
+        if self.conv_kind == "ffma" or not eligible:
+            return A.CONV_FFMA
+        if self.conv_kind == "tc":
+            return A.CONV_TC
+        # auto: the tensor-core kernel pads every source to 32-channel chunks; tiny-K convs stay on CUDA cores
+        if min(vw.C for vw, _ in srcs) < 16:
+            return A.CONV_FFMA
+        return A.CONV_TC
+
+    def conv(self, names, srcs, out_hw, N, segs, k=(3, 3), stride=1, pad=None, in_map=None, out_map=None,
+             cout=None, in_hw=None, label=None):
+        """Append one convolution.  srcs: [(View, up)], segs: [dict(ch0, nch, dst=View, act, res=View, res2=View, store)]."""
+        if isinstance(names, str):
+            names = [names]
+        w, b = self._weight(names)
+        Co, Ci, KH, KW = w.shape
+        assert (KH, KW) == tuple(k), (names, w.shape, k)
+        if pad is None:
+            pad = (KH // 2, KW // 2)
+        srcs = [(s, 0) if isinstance(s, View) else s for s in srcs]
+        src_C = [vw.C for vw, _ in srcs]
+        k_total = sum(src_C)
+        if in_map is None:
+            in_map = list(range(Ci)) + [-1] * (k_total - Ci)
+        assert len(in_map) == k_total, (names, len(in_map), k_total)
+        used = sorted(m for m in in_map if m >= 0)
+        assert used == list(range(Ci)), f"{names}: in_map must cover every reference input channel exactly once"
+        cout_pad = _ru(Co if cout is None else cout, 16)
+        if out_map is None:
+            out_map = list(range(Co)) + [-1] * (cout_pad - Co)
+        assert len(out_map) == cout_pad and sorted(m for m in out_map if m >= 0) == list(range(Co)), names
+        kind = self._pick_kind(KH, KW, stride, tuple(pad), srcs, cout_pad)
+        Ho, Wo = out_hw
+        Hi, Wi = in_hw if in_hw is not None else (Ho * stride, Wo * stride)
+        lib = self.lib
+        wkey = (tuple(names), kind, tuple(src_C), tuple(in_map), tuple(out_map))
+        if wkey not in self._wcache:
+            srcC_arr = (A.i32 * len(src_C))(*src_C)
+            nfl = lib.demfi_packed_weight_floats(kind, KH, KW, srcC_arr, len(src_C), cout_pad)
+            packed = np.empty(nfl, dtype=np.float32)
+            imap = (A.i32 * k_total)(*in_map)
+            omap = (A.i32 * cout_pad)(*out_map)
+            A.check(lib.demfi_pack_weights(kind, w.ctypes.data, Co, Ci, KH, KW, imap, srcC_arr, len(src_C), omap,
+                                           cout_pad, packed.ctypes.data), f"pack_weights({names})")
+            bias = np.zeros(cout_pad, dtype=np.float32)
+            for n, m in enumerate(out_map):
+                if m >= 0:
+                    bias[n] = b[m]
+            self._wcache[wkey] = (torch.from_numpy(packed).to(self.dev), torch.from_numpy(bias).to(self.dev))
+        wdev, bdev = self._wcache[wkey]
+        d = A.Conv()
+        d.N, d.H, d.W, d.Hi, d.Wi = N, Ho, Wo, Hi, Wi
+        d.KH, d.KW, d.stride, d.pad_h, d.pad_w = KH, KW, stride, pad[0], pad[1]
+        d.nsrc, d.nseg, d.cout_pad, d.kind = len(srcs), len(segs), cout_pad, kind
+        for i, (vw, up) in enumerate(srcs):
+            assert vw.N == N and (vw.H << up, vw.W << up) == (Hi, Wi), (names, i, vw.N, vw.H, vw.W, up, Hi, Wi)
+            d.src[i].ptr, d.src[i].C, d.src[i].ld, d.src[i].up = vw.ptr, vw.C, vw.ld, up
+        for i, sg in enumerate(segs):
+            dst: View = sg["dst"]
+            s = d.seg[i]
+            s.dst, s.dst_ld = dst.ptr, dst.ld
+            s.ch0, s.nch = sg["ch0"], sg["nch"]
+            s.act, s.store = sg.get("act", A.ACT_NONE), sg.get("store", A.STORE_NHWC)
+            if sg.get("res") is not None:
+                s.res, s.res_ld = sg["res"].ptr, sg["res"].ld
+            if sg.get("res2") is not None:
+                s.res2, s.res2_ld = sg["res2"].ptr, sg["res2"].ld
+        d.wpack, d.bias = wdev.data_ptr(), bdev.data_ptr()
+        self._keep.append(d)
+        macs = N * Ho * Wo * Co * Ci * KH * KW
+        op = ("conv", d, label or names[0], kind, macs)
+        return op
+
+    # ------------------------------------------------------------------ plan
+    def _build(self):
+        B, H, W = self.B, self.H, self.W
+        h, w = H // 2, W // 2
+        v = self.views
+        relu, tanh, sig, none = A.ACT_RELU, A.ACT_TANH, A.ACT_SIGMOID, A.ACT_NONE
+        full = lambda dst, nch, act=none, res=None, ch0=0, **kw: dict(ch0=ch0, nch=nch, dst=dst, act=act, res=res, **kw)
+        ops: List[tuple] = []
+        self.ops_prefix_ff = ops  # t-independent: FF_RDB + FAC_FB encoder/FGAC
+
+        # ---- FF_RDB (DeMFInet.py:233-253) at half resolution
+        p = "FF_RDB_Module."
+        T = v["T"]
+        ops.append(self.conv(p + "SFENet1", [v["S2D"]], (h, w), B, [full(v["F1"], 96)], k=(5, 5)))
+        ops.append(self.conv(p + "SFENet2", [v["F1"]], (h, w), B, [full(T.ch(0, 96), 96)]))
+        for i in range(12):
+            o = 224 * i
+            for c in range(4):
+                ops.append(self.conv(f"{p}RDBs.{i}.convs.{c}.conv.0", [T.ch(o, 96 + 32 * c)], (h, w), B,
+                                     [full(T.ch(o + 96 + 32 * c, 32), 32, relu)]))
+            xi = T.ch(o, 96)
+            ops.append(self.conv(f"{p}RDBs.{i}.LFF", [T.ch(o, 224)], (h, w), B,
+                                 [full(T.ch(o + 224, 96), 96, none, xi), full(v["G"].ch(96 * i, 96), 96, none, xi)], k=(1, 1)))
+        ops.append(self.conv(p + "GFF.0", [v["G"]], (h, w), B, [full(v["GF0"], 96)], k=(1, 1)))
+        ops.append(self.conv(p + "GFF.1", [v["GF0"]], (h, w), B, [full(v["TR"], 96, none, v["F1"])]))
+        # UPNet.0 + PixelShuffle(2): internal channel q*64+c <- reference channel c*4+q
+        ops.append(self.conv(p + "UPNet.0", [v["TR"]], (h, w), B,
+                             [full(v["U"], 256, none, store=A.STORE_PIXEL_SHUFFLE2)],
+                             out_map=[(n % 64) * 4 + n // 64 for n in range(256)]))
+        F01 = v["F01"]
+        ops.append(self.conv(p + "UPNet.2", [v["U"]], (H, W), B,
+                             [full(F01.frames(0, B), 64, tanh, ch0=0), full(F01.frames(B, B), 64, tanh, ch0=64),
+                              full(v["FO"], 8, none, ch0=128)]))
+
+        # ---- FAC_FB (DeMFInet.py:335-358) : shared encoder on [F0;F1], then the two FGAC directions
+        p = "FAC_FB_Module."
+        pool = [v["P0"].frames(0, 2 * B), v["P1"].frames(0, 2 * B), v["P2"].frames(0, 2 * B)]
+        SE = v["SE"]
+        ops.append(self.conv(p + "conv_first", [F01], (H, W), 2 * B, [full(pool[0], 64, relu)]))
+        a, b_, c_ = pool
+        for i in range(5):
+            ops.append(self.conv(f"{p}feature_extraction.{i}.conv1", [a], (H, W), 2 * B, [full(b_, 64, relu)]))
+            dst = SE.ch(0, 64) if i == 4 else c_
+            ops.append(self.conv(f"{p}feature_extraction.{i}.conv2", [b_], (H, W), 2 * B, [full(dst, 64, none, a)]))
+            a, c_ = c_, a
+        g = p + "shared_FGAC."
+        ops.append(self.conv(g + "conv_ref_k", [SE.ch(0, 64)], (H, W), 2 * B, [full(v["RK"], 64)], k=(1, 1)))
+        FO = v["FO"]
+        # direction 0: ref = enc(F1), source = enc(F0), flow_01; direction 1: the converse (DeMFInet.py:346-349)
+        ops.append(("fgac_sample", v["RK"].frames(B, B), FO.ch(0, 2), v["SMP"].frames(0, B)))
+        ops.append(("fgac_sample", v["RK"].frames(0, B), FO.ch(2, 2), v["SMP"].frames(B, B)))
+        ops.append(self.conv(g + "fusion", [v["SMP"]], (H, W), 2 * B, [full(SE.ch(64, 64), 64)], k=(1, 1)))
+        ops.append(self.conv(g + "w_gen", [SE], (H, W), 2 * B, [full(v["WG"], 64, relu)]))
+        ops.append(self.conv(g + "w_gen_2", [v["WG"]], (H, W), 2 * B, [full(v["WL"], 4, sig)]))
+        AGG1 = v["AGG1"]
+        for d_ in range(2):
+            ops.append(("fgac_blend", v["WL"].frames(d_ * B, B), SE.frames(d_ * B, B).ch(0, 64),
+                        SE.frames(d_ * B, B).ch(64, 64), AGG1.ch(64 * d_, 64)))
+        ops.append(("copy", FO.ch(4, 1), AGG1.ch(196, 1), none))
+        ops.append(("copy", FO.ch(0, 4), AGG1.ch(200, 4), none))
+
+        # ---- t-dependent stage I (DeMFInet.py:63-102)
+        ops = []
+        self.ops_stage1 = ops
+        ops.append(("zero", v["ACC"]))
+        ops.append(("cfr_splat", FO, v["ACC"]))
+        ops.append(("cfr_finalize", v["ACC"], AGG1.ch(192, 4)))
+        ops.append(("bwarp_blend", F01.frames(0, B), F01.frames(B, B), AGG1.ch(192, 4), FO.ch(4, 1), AGG1.ch(128, 64), None))
+        p = "Refine_Module."
+        # internal AGG1 order: aF0 aF1 Ft | flow_t0 flow_t1 | occ pad3 | flow_01 flow_10
+        agg1_map = list(range(192)) + [192, 193, 194, 195, 200, -1, -1, -1, 196, 197, 198, 199]
+        ops.append(self.conv(p + "enc1", [AGG1], (h, w), B, [full(v["EN1"], 64, relu)], k=(4, 4), stride=2, pad=(1, 1), in_map=agg1_map))
+        ops.append(self.conv(p + "enc2", [v["EN1"]], (h // 2, w // 2), B, [full(v["EN2"], 128, relu)], k=(4, 4), stride=2, pad=(1, 1)))
+        ops.append(self.conv(p + "enc3", [v["EN2"]], (h // 4, w // 4), B, [full(v["EN3"], 256, relu)], k=(4, 4), stride=2, pad=(1, 1)))
+        ops.append(self.conv(p + "dec0", [v["EN3"]], (h // 4, w // 4), B, [full(v["DE0"], 256, relu)]))
+        ops.append(self.conv(p + "dec1", [(v["DE0"], 1), (v["EN2"], 0)], (h // 2, w // 2), B, [full(v["DE1"], 128, relu)]))
+        ops.append(self.conv(p + "dec2", [(v["DE1"], 1), (v["EN1"], 0)], (h, w), B, [full(v["DE2"], 64, relu)]))
+        DECIN, DL0 = v["DECIN"], v["DL0"]
+        dec3_out = [5 + c for c in range(64)] + [69 + c for c in range(64)] + [0, 1, 2, 3, 4] + [-1] * 11
+        ops.append(self.conv(p + "dec3", [(v["DE2"], 1)], (H, W), B,
+                             [full(DECIN.frames(0, B), 64, tanh, AGG1.ch(0, 64), ch0=0),
+                              full(DECIN.frames(B, B), 64, tanh, AGG1.ch(64, 64), ch0=64),
+                              full(DL0, 8, none, AGG1.ch(192, 8), ch0=128)], out_map=dec3_out))
+        A3 = v["A3"]
+        ops.append(("bwarp_blend", DECIN.frames(0, B), DECIN.frames(B, B), DL0.ch(0, 4), DL0.ch(4, 1),
+                    DECIN.frames(2 * B, B), A3.ch(9, 1)))
+        # D1 (DeMFInet.py:95-102): three frames batched
+        pool3 = [v["P0"], v["P1"], v["P2"]]
+        ops.append(self.conv("Dec_first", [DECIN], (H, W), 3 * B, [full(pool3[0], 64, relu)]))
+        a, b_, c_ = pool3
+        for i in range(5):
+            ops.append(self.conv(f"Decoder_res.{i}.conv1", [a], (H, W), 3 * B, [full(b_, 64, relu)]))
+            ops.append(self.conv(f"Decoder_res.{i}.conv2", [b_], (H, W), 3 * B, [full(c_, 64, none, a)]))
+            a, c_ = c_, a
+        ops.append(self.conv("Dec_last1", [a], (H, W), 3 * B, [full(b_, 64, relu)]))
+        SP = v["SP"]
+        ops.append(self.conv("Dec_last2", [b_], (H, W), 3 * B, [full(SP, 4)]))
+        REF = v["REF"]
+        for f in range(3):
+            ops.append(("copy", SP.frames(f * B, B).ch(0, 3), REF.ch(3 * f, 3), none))
+            if f < 2:
+                ops.append(("copy", SP.frames(f * B, B).ch(0, 3), A3.ch(3 * f, 3), none))
+        ops.append(("copy", FO.ch(0, 4), REF.ch(21, 4), none))
+        ops.append(("copy", DL0.ch(0, 5), REF.ch(25, 5), none))
+        ops.append(("copy", DL0.ch(0, 4), A3.ch(10, 4), none))
+        ops.append(("copy", FO.ch(0, 4), A3.ch(14, 4), none))
+        # Ch_Reducer (DeMFInet.py:114) over cat(rF0, rF1, rFt)
+        FR = [v["FR0"], v["FR1"], v["FR2"]]
+        ops.append(self.conv("Ch_Reducer", [DECIN.frames(0, B), DECIN.frames(B, B), DECIN.frames(2 * B, B)], (H, W), B,
+                             [full(FR[0], 64, tanh)], k=(7, 7)))
+        # Mixer's reference branch is loop-invariant (ref_list never changes, DeMFInet.py:117-120, 815-816)
+        p = "Booster_Module."
+        ref_map = list(range(21)) + [23, 24, 21, 22] + [25, 26, 27, 28, 29] + [-1, -1]
+        ops.append(self.conv(p + "Mixer.conv_ref1", [REF], (H, W), B, [full(v["R1"], 32, relu)], k=(7, 7), in_map=ref_map))
+        ops.append(self.conv(p + "Mixer.conv_ref2", [v["R1"]], (H, W), B, [full(v["RD"].ch(0, 32), 32, relu)]))
+
+        # ---- recursive boosting iteration (DeMFInet.py:130-165); buffers rotate with the iteration index
+        self._iter_cache: Dict[Tuple[int, bool], list] = {}
+        self._agg3_map = (list(range(9)) + [73] + [74, 75, 76, 77] + [80, 81, 78, 79] + [82, 83, 84, 85] + [86]
+                          + list(range(87, 99)) + [-1] + list(range(9, 73)))
+
+    def _iter_ops(self, itr: int, decode: bool) -> list:
+        key = (itr % 6, decode)  # FR rotates with period 3, DL with period 2
+        if key in self._iter_cache:
+            return self._iter_cache[key]
+        B, H, W = self.B, self.H, self.W
+        v = self.views
+        relu, tanh, sig, none = A.ACT_RELU, A.ACT_TANH, A.ACT_SIGMOID, A.ACT_NONE
+        full = lambda dst, nch, act=none, res=None, ch0=0, **kw: dict(ch0=ch0, nch=nch, dst=dst, act=act, res=res, **kw)
+        FR = [v["FR0"], v["FR1"], v["FR2"]]
+        # the next iteration reads this iteration's `hout`: rotate by 2 each iteration
+        hin, hmid, hout = FR[(2 * itr) % 3], FR[(2 * itr + 1) % 3], FR[(2 * itr + 2) % 3]
+        DLi, DLo = (v["DL0"], v["DL1"]) if itr % 2 == 0 else (v["DL1"], v["DL0"])
+        X, Z, RH, RD, A3 = v["X"], v["Z"], v["RH"], v["RD"], v["A3"]
+        p = "Booster_Module."
+        ops = []
+        ops.append(self.conv(p + "Mixer.conv_delta1", [DLi], (H, W), B, [full(v["D1B"], 32, relu)], k=(7, 7),
+                             in_map=[0, 1, 2, 3, 4, -1, -1, -1]))
+        ops.append(self.conv(p + "Mixer.conv_delta2", [v["D1B"]], (H, W), B, [full(RD.ch(32, 32), 32, relu)]))
+        ops.append(self.conv(p + "Mixer.conv_blend1", [RD], (H, W), B, [full(v["BL1"], 32, relu)]))
+        ops.append(self.conv(p + "Mixer.conv_blend2", [v["BL1"]], (H, W), B, [full(X, 64, relu)]))
+        # SepConvGRU (DeMFInet.py:838-857): z and r share one pass over [h, x]
+        for s, k, h0, h1 in (("1", (1, 5), hin, hmid), ("2", (5, 1), hmid, hout)):
+            ops.append(self.conv([p + "GB.convz" + s, p + "GB.convr" + s], [h0, X], (H, W), B,
+                                 [full(Z, 64, sig, ch0=0), full(RH, 64, A.ACT_SIGMOID_MUL, h0, ch0=64)], k=k,
+                                 label=p + "GB.convzr" + s))
+            ops.append(self.conv(p + "GB.convq" + s, [RH, X], (H, W), B, [full(h1, 64, A.ACT_GRU, h0, res2=Z)], k=k))
+        ops.append(self.conv(p + "flow_occ.conv1", [hout], (H, W), B, [full(v["FO1"], 32, relu)]))
+        ops.append(self.conv(p + "flow_occ.conv2", [v["FO1"]], (H, W), B, [full(DLo, 8, none, DLi)]))
+        self._iter_cache[key] = ops
+        if not decode:
+            return ops
+        ops.extend(self._decode_ops(hout, DLo))
+        return ops
+
+    def _decode_ops(self, hout: View, DLo: View) -> list:
+        B, H, W = self.B, self.H, self.W
+        v = self.views
+        relu, none = A.ACT_RELU, A.ACT_NONE
+        full = lambda dst, nch, act=none, res=None, ch0=0, **kw: dict(ch0=ch0, nch=nch, dst=dst, act=act, res=res, **kw)
+        A3 = v["A3"]
+        ops = []
+        # PWB (DeMFInet.py:146-149) + D2 (DeMFInet.py:151-165)
+        ops.append(("bwarp_blend", A3.ch(0, 3), A3.ch(3, 3), DLo.ch(0, 4), DLo.ch(4, 1), A3.ch(6, 3), A3.ch(22, 1)))
+        ops.append(("copy", DLo.ch(0, 4), A3.ch(18, 4), none))
+        pool = [v["P0"].frames(0, B), v["P1"].frames(0, B), v["P2"].frames(0, B)]
+        ops.append(self.conv("Dec_first_2", [A3, hout], (H, W), B, [full(pool[0], 64, relu)], in_map=self._agg3_map))
+        a, b_, c_ = pool
+        for i in range(5):
+            ops.append(self.conv(f"Decoder_res_2.{i}.conv1", [a], (H, W), B, [full(b_, 64, relu)]))
+            ops.append(self.conv(f"Decoder_res_2.{i}.conv2", [b_], (H, W), B, [full(c_, 64, none, a)]))
+            a, c_ = c_, a
+        ops.append(self.conv("Dec_last1_2", [a], (H, W), B, [full(b_, 64, relu)]))
+        ops.append(self.conv("Dec_last2_2", [b_], (H, W), B, [full(v["D2O"], 12, none, A3.ch(0, 12))]))
+        return ops
+
+    # ------------------------------------------------------------------ execution
+    def _run(self, ops, st):
+        lib, B, H, W = self.lib, self.B, self.H, self.W
+        for op in ops:
+            k = op[0]
+            if k == "conv":
+                A.check(lib.demfi_conv2d(C.byref(op[1]), st), f"conv2d[{op[2]}]")
+            elif k == "copy":
+                s, d, act = op[1], op[2], op[3]
+                A.check(lib.demfi_copy_channels(s.ptr, s.ld, d.ptr, d.ld, s.C, s.npix(), act, st), "copy_channels")
+            elif k == "zero":
+                op[1].t.zero_()
+            elif k == "cfr_splat":
+                A.check(lib.demfi_cfr_splat(op[1].ptr, op[1].ld, self.t_dev.data_ptr(), B, H, W, op[2].ptr, st), "cfr_splat")
+            elif k == "cfr_finalize":
+                A.check(lib.demfi_cfr_finalize(op[1].ptr, self.t_dev.data_ptr(), B, H, W, op[2].ptr, op[2].ld, st), "cfr_finalize")
+            elif k == "bwarp_blend":
+                a, b, fl, oc, out, oo = op[1:]
+                A.check(lib.demfi_bwarp_blend(a.ptr, a.ld, b.ptr, b.ld, fl.ptr, fl.ld, oc.ptr, oc.ld, self.t_dev.data_ptr(),
+                                              B, H, W, a.C, out.ptr, out.ld, oo.ptr if oo is not None else None,
+                                              oo.ld if oo is not None else 0, st), "bwarp_blend")
+            elif k == "fgac_sample":
+                r, fl, out = op[1:]
+                A.check(lib.demfi_fgac_sample(r.ptr, r.ld, fl.ptr, fl.ld, r.N, H, W, r.C, out.ptr, out.ld, st), "fgac_sample")
+            elif k == "fgac_blend":
+                wv, s, e, out = op[1:]
+                A.check(lib.demfi_fgac_blend(wv.ptr, wv.ld, s.ptr, s.ld, e.ptr, e.ld, s.npix(), s.C, out.ptr, out.ld, st), "fgac_blend")
+            else:
+                raise AssertionError(k)
+
+    def _export(self, view: View, C_, st, act=A.ACT_NONE) -> torch.Tensor:
+        out = torch.empty((view.N, C_, view.H, view.W), dtype=torch.float32, device=self.dev)
+        A.check(self.lib.demfi_export_nchw(view.ptr, view.ld, view.N, view.H, view.W, C_, act, out.data_ptr(), st), "export_nchw")
+        return out
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor, t_value: torch.Tensor, num_update: int, reuse_prefix: bool = False,
+                final_only: bool = False):
+        """One `DeMFInet.forward` (eval 5-tuple).  reuse_prefix=True skips the t-independent FF_RDB +
+        FAC_FB stage and reuses what the previous call on the same frames left in HBM
+        (SURVEY.md 3.2); final_only=True decodes D2 only for the last boosting iteration (the earlier
+        entries of Sharps_final are then None)."""
+        B, H, W = self.B, self.H, self.W
+        if self.dry:
+            raise RuntimeError("a dry (host-only) engine cannot run: demfi_b200 has no CPU path")
+        assert tuple(x.shape) == (B, 3, 4, H, W), (tuple(x.shape), (B, 3, 4, H, W))
+        x = x.to(self.dev, torch.float32).contiguous()
+        self.t_dev.copy_(t_value.reshape(B).to(torch.float32), non_blocking=True)
+        st = torch.cuda.current_stream(self.dev).cuda_stream
+        v = self.views
+        lib = self.lib
+        two_blurry = torch.empty((B, 3, H, W), dtype=torch.float32, device=self.dev)
+        if not reuse_prefix:
+            A.check(lib.demfi_pack_input(x.data_ptr(), B, H, W, v["S2D"].ptr, v["REF"].ch(9, 12).ptr, 32,
+                                         v["A3"].ch(23, 12).ptr, 36, two_blurry.data_ptr(), st), "pack_input")
+            self._run(self.ops_prefix_ff, st)
+            self._two_blurry = two_blurry
+        else:
+            two_blurry = self._two_blurry.clone()
+        self._run(self.ops_stage1, st)
+        SP, A3, DL0 = v["SP"], v["A3"], v["DL0"]
+        sharps_dec1 = [self._export(SP.frames(f * B, B), 3, st) for f in range(3)]
+        flow_predictions = [self._export(DL0, 4, st)]
+        occ0_predictions = [self._export(A3.ch(9, 1), 1, st)]
+        sharps_final = []
+        for itr in range(num_update):
+            decode = (not final_only) or itr == num_update - 1
+            self._run(self._iter_ops(itr, decode), st)
+            DLo = v["DL1"] if itr % 2 == 0 else v["DL0"]
+            flow_predictions.append(self._export(DLo, 4, st))
+            occ0_predictions.append(self._export(DLo.ch(4, 1), 1, st, A.ACT_SIGMOID))
+            if decode:
+                D2O = v["D2O"]
+                sharps_final.append([self._export(D2O.ch(3 * j, 3), 3, st) for j in range(3)])
+            else:
+                sharps_final.append(None)
+        return sharps_dec1, sharps_final, flow_predictions, occ0_predictions, two_blurry
+
+    # ------------------------------------------------------------------ accounting
+    def conv_macs(self, num_update: int, final_only=False, reuse_prefix=False) -> int:
+        tot = 0
+        lists = [] if reuse_prefix else [self.ops_prefix_ff]
+        lists.append(self.ops_stage1)
+        for itr in range(num_update):
+            lists.append(self._iter_ops(itr, (not final_only) or itr == num_update - 1))
+        for ops in lists:
+            tot += sum(op[4] for op in ops if op[0] == "conv")
+        return tot

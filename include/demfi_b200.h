@@ -1,0 +1,174 @@
+/* demfi_b200 -- C ABI of the B200-native DeMFI-Net forward / recursive-boosting hot path.
+ *
+ * The reference (JihyongOh/DeMFI) has no FFI layer: its hot path is the Python nn.Module
+ * `DeMFInet` (DeMFInet.py:13-179) issuing ATen/cuDNN library calls.  This header is the
+ * boundary a maintainer binds instead (ctypes stub: demfi_b200/_abi.py).
+ * Every entry point replaces a group of reference call sites, cited per function.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch types.  All tensor pointers are DEVICE
+ *     pointers to fp32 unless the name says `host`.
+ *   - Activations are NHWC: element (n, y, x, c) at ptr[((n*H + y)*W + x)*ld + c]; `ld` is the
+ *     pixel stride in floats (multiple of 4) so a tensor may be a channel slice of a wider
+ *     buffer (that is how every torch.cat of the reference disappears).
+ *   - Functions return 0 on success, non-zero on error; demfi_last_error() gives the message
+ *     (thread-local).  Nothing here allocates device memory or synchronises the device; work
+ *     is enqueued on `stream` (a cudaStream_t passed as void*).
+ *   - There is no CPU fallback: every function fails if the device is not sm_100.
+ */
+#ifndef DEMFI_B200_H_
+#define DEMFI_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DEMFI_ABI_VERSION 1
+#define DEMFI_MAX_SRC 4
+#define DEMFI_MAX_SEG 4
+
+/* epilogue activation of one output segment; v = acc + bias (+ res when res != NULL and the
+ * mode is not MUL/GRU) */
+enum {
+  DEMFI_ACT_NONE = 0,        /* out = v                                   */
+  DEMFI_ACT_RELU = 1,        /* out = max(v, 0)                           */
+  DEMFI_ACT_TANH = 2,        /* out = tanh(v)                             */
+  DEMFI_ACT_SIGMOID = 3,     /* out = sigmoid(v)                          */
+  DEMFI_ACT_SIGMOID_MUL = 4, /* out = sigmoid(acc+bias) * res    (GRU r*h, DeMFInet.py:846-847) */
+  DEMFI_ACT_GRU = 5          /* out = (1-res2)*res + res2*tanh(acc+bias)  (DeMFInet.py:847-848) */
+};
+enum {
+  DEMFI_STORE_NHWC = 0,
+  DEMFI_STORE_PIXEL_SHUFFLE2 = 1 /* nn.PixelShuffle(2), DeMFInet.py:229: accumulator channel
+                                    q*(nch/4)+c of pixel (y,x) -> dst pixel (2y+q/2, 2x+q%2), channel c */
+};
+enum { DEMFI_CONV_FFMA = 0, DEMFI_CONV_TC = 1 };
+
+/* one input of a (virtually concatenated) convolution */
+typedef struct {
+  const float* ptr; /* NHWC, [N, Hi>>up, Wi>>up, ld] */
+  int32_t C;        /* channels this source contributes to K (multiple of 4) */
+  int32_t ld;
+  int32_t up;       /* 1: source is at half the conv-input resolution and is read through
+                       nearest-neighbour x2 up-sampling (nn.UpsamplingNearest2d, DeMFInet.py:573) */
+  int32_t reserved;
+} demfi_src_t;
+
+/* one destination of a channel range [ch0, ch0+nch) of the accumulator */
+typedef struct {
+  float* dst;
+  const float* res;  /* optional operand, same pixel indexing as dst (NHWC, res_ld) */
+  const float* res2; /* second operand (GRU z) */
+  int32_t dst_ld, res_ld, res2_ld;
+  int32_t ch0, nch;  /* multiples of 4 */
+  int32_t act, store;
+  int32_t reserved;
+} demfi_seg_t;
+
+/* A convolution = every nn.Conv2d / nn.Conv3d([1,3,3]) call of DeMFInet.py (section 2.1 of
+ * SURVEY.md lists the 27 shapes), with the torch.cat feeding it expressed as `src[]` and the
+ * pointwise ops following it expressed as `seg[]`. */
+typedef struct {
+  int32_t N, H, W;   /* output batch / rows / cols                                   */
+  int32_t Hi, Wi;    /* conv-input grid (after any up-sampling)                       */
+  int32_t KH, KW, stride, pad_h, pad_w;
+  int32_t nsrc, nseg;
+  int32_t cout_pad;  /* accumulator channels (padded Cout, multiple of 16)             */
+  int32_t kind;      /* DEMFI_CONV_FFMA | DEMFI_CONV_TC                               */
+  demfi_src_t src[DEMFI_MAX_SRC];
+  demfi_seg_t seg[DEMFI_MAX_SEG];
+  const float* wpack; /* device, produced by demfi_pack_weights for the same `kind`    */
+  const float* bias;  /* device, cout_pad floats                                      */
+} demfi_conv_t;
+
+/* ---- library ------------------------------------------------------------------------- */
+int demfi_version(void);
+const char* demfi_last_error(void);
+/* 0 iff `device` is compute capability 10.0 (B200).  Replaces main.py:157-159's bare
+ * torch.cuda.set_device: there is no other backend to fall back to. */
+int demfi_device_check(int device);
+
+/* ---- weights ------------------------------------------------------------------------- */
+/* Number of floats demfi_pack_weights writes.  src_C[nsrc] are the demfi_src_t.C values the conv
+ * will be launched with (the tcgen05 layout chunks K per source). */
+size_t demfi_packed_weight_floats(int32_t kind, int32_t KH, int32_t KW, const int32_t* src_C, int32_t nsrc,
+                                  int32_t cout_pad);
+/* HOST -> HOST repack of one nn.Conv weight (state_dict layout [Co, Ci, KH, KW], fp32) into
+ * the layout the kernels stream.  in_map[k] (k < k_total = sum(src_C)) is the reference input
+ * channel that internal channel k carries, or -1 for padding; out_map[n] (n < cout_pad) likewise
+ * for output channels.  kind FFMA: [tap][k][cout_pad] fp32.  kind TC: per (32-channel chunk, tap) a
+ * [cout_pad x 32] K-major tile, 128-byte-swizzled, stored twice: tf32 "hi" part and fp32
+ * residual "lo" part (3xTF32 split). */
+int demfi_pack_weights(int32_t kind, const float* w_oihw_host, int32_t Co, int32_t Ci, int32_t KH, int32_t KW,
+                       const int32_t* in_map, const int32_t* src_C, int32_t nsrc, const int32_t* out_map,
+                       int32_t cout_pad, float* out_host);
+
+/* ---- convolution (DeMFInet.py: every nn.Conv call; see demfi_conv_t) -------------------- */
+int demfi_conv2d(const demfi_conv_t* conv, void* stream);
+
+/* ---- memory-bound operators ------------------------------------------------------------ */
+/* Input unpack.  x is the caller's [B,3,4,H,W] NCHW-T tensor (DeMFInet.py:51-55).  Writes
+ *  - s2d:   [B,H/2,W/2,48] pixel_reshuffle(cat(B0,B1,B-1,B2), 2)   (DeMFInet.py:234-235,290-316)
+ *  - f12a/f12b: the 12 frame channels (order t*3+c) into two NHWC slices (Mixer / D2 inputs,
+ *    DeMFInet.py:119,151-155); either may be NULL
+ *  - mean01: [B,3,H,W] NCHW = mean(x[:,:,0:2], dim=2)               (DeMFInet.py:178) */
+int demfi_pack_input(const float* x, int32_t B, int32_t H, int32_t W, float* s2d, float* f12a, int32_t f12a_ld,
+                     float* f12b, int32_t f12b_ld, float* mean01, void* stream);
+
+/* Complementary flow reversal (CFR_flow_t_align + fwarp + sample_one, DeMFInet.py:606-729).
+ * fo: NHWC [B,H,W,fo_ld], channels 0-1 flow_01, 2-3 flow_10.  acc: [B,H,W,8] scratch, must be
+ * zero on entry to splat (the splat adds with fp32 red.global.add).  t: device [B]. */
+int demfi_cfr_splat(const float* fo, int32_t fo_ld, const float* t, int32_t B, int32_t H, int32_t W, float* acc,
+                    void* stream);
+/* out: 4 channels (flow_t0.x, flow_t0.y, flow_t1.x, flow_t1.y) at out[pix*out_ld]. */
+int demfi_cfr_finalize(const float* acc, const float* t, int32_t B, int32_t H, int32_t W, float* out,
+                       int32_t out_ld, void* stream);
+
+/* bwarp + Eq.(2) blend (bwarp DeMFInet.py:732-766; blend :66-71, :90-93, :146-149):
+ *   out = ((1-t)*o*bwarp(a, flow[0:2]) + t*(1-o)*bwarp(b, flow[2:4])) / ((1-t)*o + t*(1-o)),
+ *   o = sigmoid(occ_logit).  C channels (multiple of 4 for the vector path; C=3 uses the
+ *   scalar path).  a, b, out: NHWC with their own ld; flow: 4 channels at flow[pix*flow_ld];
+ *   occ: 1 channel at occ[pix*occ_ld]; t: device [B].
+ *   occ_out (optional): receives sigmoid(occ_logit) at occ_out[pix*occ_out_ld]. */
+int demfi_bwarp_blend(const float* a, int32_t a_ld, const float* b, int32_t b_ld, const float* flow, int32_t flow_ld,
+                      const float* occ, int32_t occ_ld, const float* t, int32_t B, int32_t H, int32_t W, int32_t C,
+                      float* out, int32_t out_ld, float* occ_out, int32_t occ_out_ld, void* stream);
+
+/* FGAC sampling (FGAC.forward step (i), DeMFInet.py:403-419 + bilinear_sampler :499-514) with
+ * rr = sr = 0: out(y,x,:) = bilinear(ref_k, at absolute position (flow.x, flow.y)), zeros
+ * outside.  The correlation/softmax that follows in the reference runs over one element and is
+ * identically 1 (DeMFInet.py:438-443), so it is not materialised. */
+int demfi_fgac_sample(const float* refk, int32_t refk_ld, const float* flow, int32_t flow_ld, int32_t B, int32_t H,
+                      int32_t W, int32_t C, float* out, int32_t out_ld, void* stream);
+/* Eq.(4), DeMFInet.py:452: out = w*src + (1-w)*e, w one channel (already sigmoid-ed). */
+int demfi_fgac_blend(const float* w, int32_t w_ld, const float* src, int32_t src_ld, const float* e, int32_t e_ld,
+                     int64_t npix, int32_t C, float* out, int32_t out_ld, void* stream);
+
+/* Channel-slice copy between NHWC buffers: dst[p*dst_ld + j] = act(src[p*src_ld + j]), j < nch.
+ * Replaces the small torch.cat assemblies (DeMFInet.py:117-123, 151-155). act: NONE or SIGMOID. */
+int demfi_copy_channels(const float* src, int32_t src_ld, float* dst, int32_t dst_ld, int32_t nch, int64_t npix,
+                        int32_t act, void* stream);
+/* NHWC slice -> NCHW tensor [B,C,H,W] (the tensors DeMFInet.forward returns, DeMFInet.py:170-179). */
+int demfi_export_nchw(const float* src, int32_t src_ld, int32_t B, int32_t H, int32_t W, int32_t C, int32_t act,
+                      float* dst, void* stream);
+/* NCHW [B,C,H,W] -> NHWC slice (test helper and teacher-forced entry). */
+int demfi_import_nchw(const float* src, int32_t B, int32_t H, int32_t W, int32_t C, float* dst, int32_t dst_ld,
+                      void* stream);
+
+/* ---- introspection ---------------------------------------------------------------------- */
+/* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
+uint64_t demfi_launch_count(void);
+/* Runtime options (diagnostics / measurement): "tc_mask_hi" (1: the tf32 "hi" operand tile is
+ * masked in shared memory, 0: the raw fp32 tile is fed and the tensor core's own truncation is
+ * relied on), "tc_split" (3: 3xTF32, fp32-parity mode, default; 1: single-pass TF32, NOT parity
+ * grade, for measurement only).  Returns non-zero for an unknown option. */
+int demfi_set_option(const char* name, int32_t value);
+int demfi_get_option(const char* name, int32_t* value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEMFI_B200_H_ */

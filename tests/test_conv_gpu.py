@@ -1,0 +1,254 @@
+"""Parity of demfi_conv2d (CUDA-core and tcgen05 kernels) against torch conv2d in float64 on
+identical inputs, for the conv shapes of DeMFInet.py: virtual concat, slices of
+wider buffers, up-sampled sources, stride 2, pixel-shuffle store and every fused epilogue."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from demfi_b200 import _abi as A
+from gpu_util import DEV, from_nhwc, nhwc, run_conv
+
+pytestmark = pytest.mark.gpu
+KINDS = [pytest.param(A.CONV_FFMA, id="ffma"), pytest.param(A.CONV_TC, id="tc")]
+TOL = 2e-5  # max-abs relative to max(1, max|ref|): fp32 conv noise level (ref self-noise 2-3e-5)
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = np.random.Generator(np.random.PCG64(seed))
+    return torch.from_numpy((g.standard_normal(shape) * scale).astype(np.float32))
+
+
+def wb(co, ci, kh, kw, seed=1):
+    std = math.sqrt(2.0 / ((ci + co) * kh * kw))
+    return rnd(co, ci, kh, kw, seed=seed, scale=std), rnd(co, seed=seed + 1, scale=0.1)
+
+
+def ref_conv(x, w, b, stride=1, pad=None):
+    if pad is None:
+        pad = (w.shape[2] // 2, w.shape[3] // 2)
+    return F.conv2d(x.double(), w.double(), b.double(), stride=stride, padding=pad)
+
+
+def check(got, want, what):
+    err = float((got.double() - want).abs().max())
+    lim = TOL * max(1.0, float(want.abs().max()))
+    print(f"{what}: max-abs err {err:.3e} (limit {lim:.3e}, max|ref| {float(want.abs().max()):.3f})")
+    assert err <= lim, f"{what}: {err} > {lim}"
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("n,h,w_,ci,co,k", [(2, 24, 40, 64, 64, (3, 3)), (1, 8, 16, 64, 64, (3, 3)), (1, 16, 48, 48, 96, (5, 5)),
+                                             (1, 24, 24, 32, 32, (7, 7)), (3, 16, 32, 64, 64, (1, 1)), (1, 40, 56, 128, 64, (1, 5)),
+                                             (1, 40, 56, 128, 64, (5, 1))])
+def test_plain_relu(kind, n, h, w_, ci, co, k):
+    x = rnd(n, ci, h, w_, seed=3)
+    w, b = wb(co, ci, *k)
+    xb, _ = nhwc(x)
+    out = torch.zeros(n, h, w_, co, device=DEV)
+    run_conv(w, b, [(xb, ci, 0)], (h, w_), kind, [dict(ch0=0, nch=co, dst=out, act=A.ACT_RELU)])
+    check(from_nhwc(out, co), F.relu(ref_conv(x, w, b)), f"relu {ci}->{co} {k}")
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_residual_into_slice(kind):
+    # RDB-style: read channels [0,160) of a 224-wide buffer, write 32 channels into the same buffer
+    n, h, w_ = 1, 16, 48
+    x = rnd(n, 224, h, w_, seed=4)
+    w, b = wb(32, 160, 3, 3)
+    xb, _ = nhwc(x)
+    run_conv(w, b, [(xb, 160, 0)], (h, w_), kind, [dict(ch0=0, nch=32, dst=xb, dst_c0=160, act=A.ACT_RELU)])
+    got = from_nhwc(xb, 224)
+    check(got[:, 160:192], F.relu(ref_conv(x[:, :160], w, b)), "rdb slice")
+    assert torch.equal(got[:, :160], x[:, :160]) and torch.equal(got[:, 192:], x[:, 192:]), "neighbour channels touched"
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_lff_dual_destination_residual(kind):
+    n, h, w_ = 1, 16, 32
+    x = rnd(n, 224, h, w_, seed=5)
+    w, b = wb(96, 224, 1, 1)
+    xb, _ = nhwc(x)
+    o1 = torch.zeros(n, h, w_, 96, device=DEV)
+    o2 = torch.zeros(n, h, w_, 1152, device=DEV)
+    run_conv(w, b, [(xb, 224, 0)], (h, w_), kind,
+             [dict(ch0=0, nch=96, dst=o1, res=xb), dict(ch0=0, nch=96, dst=o2, dst_c0=192, res=xb)])
+    want = ref_conv(x, w, b) + x[:, :96].double()
+    check(from_nhwc(o1, 96), want, "LFF dst1")
+    check(from_nhwc(o2, 1152)[:, 192:288], want, "LFF dst2")
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_pixel_shuffle_store(kind):
+    n, h, w_ = 1, 16, 32
+    x = rnd(n, 96, h, w_, seed=6)
+    w, b = wb(256, 96, 3, 3)
+    xb, _ = nhwc(x)
+    out = torch.zeros(n, 2 * h, 2 * w_, 64, device=DEV)
+    run_conv(w, b, [(xb, 96, 0)], (h, w_), kind, [dict(ch0=0, nch=256, dst=out, store=A.STORE_PIXEL_SHUFFLE2)],
+             out_map=[(i % 64) * 4 + i // 64 for i in range(256)])
+    check(from_nhwc(out, 64), F.pixel_shuffle(ref_conv(x, w, b), 2), "pixel shuffle")
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_head_three_segments(kind):
+    n, h, w_ = 1, 24, 32
+    x = rnd(n, 64, h, w_, seed=7)
+    w, b = wb(133, 64, 3, 3)
+    xb, _ = nhwc(x)
+    f01 = torch.zeros(2 * n, h, w_, 64, device=DEV)
+    fo = torch.zeros(n, h, w_, 8, device=DEV)
+    f1_view = f01[n:]
+    run_conv(w, b, [(xb, 64, 0)], (h, w_), kind,
+             [dict(ch0=0, nch=64, dst=f01, act=A.ACT_TANH), dict(ch0=64, nch=64, dst=f1_view, act=A.ACT_TANH),
+              dict(ch0=128, nch=8, dst=fo)])
+    r = ref_conv(x, w, b)
+    check(from_nhwc(f01[:n], 64), torch.tanh(r[:, :64]), "head F0")
+    check(from_nhwc(f01[n:], 64), torch.tanh(r[:, 64:128]), "head F1")
+    check(from_nhwc(fo, 5), r[:, 128:133], "head flows/occ")
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_three_sources_7x7_tanh(kind):
+    n, h, w_ = 1, 24, 32
+    xs = [rnd(n, 64, h, w_, seed=10 + i) for i in range(3)]
+    w, b = wb(64, 192, 7, 7)
+    bufs = [nhwc(x)[0] for x in xs]
+    out = torch.zeros(n, h, w_, 64, device=DEV)
+    run_conv(w, b, [(bb, 64, 0) for bb in bufs], (h, w_), kind, [dict(ch0=0, nch=64, dst=out, act=A.ACT_TANH)])
+    check(from_nhwc(out, 64), torch.tanh(ref_conv(torch.cat(xs, 1), w, b)), "Ch_Reducer-like")
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_gru_epilogues(kind):
+    n, h, w_ = 1, 16, 32
+    hh, xx = torch.tanh(rnd(n, 64, h, w_, seed=20)), F.relu(rnd(n, 64, h, w_, seed=21))
+    wz, bz = wb(64, 128, 1, 5, seed=30)
+    wr, br = wb(64, 128, 1, 5, seed=32)
+    wq, bq = wb(64, 128, 1, 5, seed=34)
+    hb, xb = nhwc(hh)[0], nhwc(xx)[0]
+    Z = torch.zeros(n, h, w_, 64, device=DEV)
+    RH = torch.zeros(n, h, w_, 64, device=DEV)
+    H2 = torch.zeros(n, h, w_, 64, device=DEV)
+    run_conv(torch.cat([wz, wr], 0), torch.cat([bz, br], 0), [(hb, 64, 0), (xb, 64, 0)], (h, w_), kind,
+             [dict(ch0=0, nch=64, dst=Z, act=A.ACT_SIGMOID), dict(ch0=64, nch=64, dst=RH, act=A.ACT_SIGMOID_MUL, res=hb)])
+    hx = torch.cat([hh, xx], 1)
+    z = torch.sigmoid(ref_conv(hx, wz, bz))
+    r = torch.sigmoid(ref_conv(hx, wr, br))
+    check(from_nhwc(Z, 64), z, "gru z")
+    check(from_nhwc(RH, 64), r * hh.double(), "gru r*h")
+    run_conv(wq, bq, [(RH, 64, 0), (xb, 64, 0)], (h, w_), kind, [dict(ch0=0, nch=64, dst=H2, act=A.ACT_GRU, res=hb, res2=Z)])
+    q = torch.tanh(ref_conv(torch.cat([(r * hh.double()).float(), xx], 1), wq, bq))
+    check(from_nhwc(H2, 64), (1 - z) * hh.double() + z * q, "gru h'")
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("co,act", [(1, A.ACT_SIGMOID), (3, A.ACT_NONE), (9, A.ACT_NONE)])
+def test_small_cout(kind, co, act):
+    n, h, w_ = 2, 16, 16
+    x = rnd(n, 64, h, w_, seed=40)
+    w, b = wb(co, 64, 3, 3)
+    xb, _ = nhwc(x)
+    ld = (co + 3) // 4 * 4
+    res = rnd(n, ld, h, w_, seed=41)
+    rb, _ = nhwc(res)
+    out = torch.zeros(n, h, w_, ld, device=DEV)
+    run_conv(w, b, [(xb, 64, 0)], (h, w_), kind, [dict(ch0=0, nch=ld, dst=out, act=act, res=rb if act == A.ACT_NONE else None)])
+    r = ref_conv(x, w, b)
+    want = torch.sigmoid(r) if act == A.ACT_SIGMOID else r + res[:, :co].double()
+    check(from_nhwc(out, co), want, f"cout={co}")
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_two_sources_permuted_padded(kind):
+    # D2's first conv: 36-wide assembled buffer (35 used, permuted) + 64-channel F_rec
+    n, h, w_ = 1, 16, 32
+    a3, fr = rnd(n, 36, h, w_, seed=50), rnd(n, 64, h, w_, seed=51)
+    w, b = wb(64, 99, 3, 3)
+    in_map = (list(range(9)) + [73, 74, 75, 76, 77, 80, 81, 78, 79, 82, 83, 84, 85, 86] + list(range(87, 99)) + [-1]
+              + list(range(9, 73)))
+    ab, fb = nhwc(a3)[0], nhwc(fr)[0]
+    out = torch.zeros(n, h, w_, 64, device=DEV)
+    run_conv(w, b, [(ab, 36, 0), (fb, 64, 0)], (h, w_), kind, [dict(ch0=0, nch=64, dst=out, act=A.ACT_RELU)], in_map=in_map)
+    xin = torch.zeros(n, 99, h, w_)
+    internal = torch.cat([a3, fr], 1)
+    for kk, m in enumerate(in_map):
+        if m >= 0:
+            xin[:, m] = internal[:, kk]
+    check(from_nhwc(out, 64), F.relu(ref_conv(xin, w, b)), "agg3 conv")
+
+
+def test_ffma_stride2_4x4():
+    n, h, w_ = 1, 32, 48
+    x = rnd(n, 204, h, w_, seed=60)
+    w, b = wb(64, 204, 4, 4)
+    xb, _ = nhwc(x)
+    out = torch.zeros(n, h // 2, w_ // 2, 64, device=DEV)
+    run_conv(w, b, [(xb, 204, 0)], (h // 2, w_ // 2), A.CONV_FFMA, [dict(ch0=0, nch=64, dst=out, act=A.ACT_RELU)], stride=2, pad=(1, 1))
+    check(from_nhwc(out, 64), F.relu(ref_conv(x, w, b, 2, (1, 1))), "enc1 4x4 s2")
+
+
+def test_ffma_upsample_concat():
+    n, h, w_ = 1, 16, 24
+    lo, sk = rnd(n, 128, h // 2, w_ // 2, seed=61), rnd(n, 64, h, w_, seed=62)
+    w, b = wb(64, 192, 3, 3)
+    lb, sb = nhwc(lo)[0], nhwc(sk)[0]
+    out = torch.zeros(n, h, w_, 64, device=DEV)
+    run_conv(w, b, [(lb, 128, 1), (sb, 64, 0)], (h, w_), A.CONV_FFMA, [dict(ch0=0, nch=64, dst=out, act=A.ACT_RELU)])
+    up = lo.repeat_interleave(2, 2).repeat_interleave(2, 3)
+    check(from_nhwc(out, 64), F.relu(ref_conv(torch.cat([up, sk], 1), w, b)), "dec2 up+cat")
+
+
+def test_ffma_tiny_cin_7x7():
+    n, h, w_ = 1, 24, 24
+    x = rnd(n, 5, h, w_, seed=63)
+    w, b = wb(32, 5, 7, 7)
+    xb, _ = nhwc(x, 8)
+    out = torch.zeros(n, h, w_, 32, device=DEV)
+    run_conv(w, b, [(xb, 8, 0)], (h, w_), A.CONV_FFMA, [dict(ch0=0, nch=32, dst=out, act=A.ACT_RELU)])
+    check(from_nhwc(out, 32), F.relu(ref_conv(x, w, b)), "conv_delta1")
+
+
+def test_tc_single_pass_is_not_parity_grade():
+    """Documents SURVEY.md 7.3: one TF32 pass misses fp32 parity by orders of magnitude; 3xTF32 meets it."""
+    n, h, w_ = 1, 16, 32
+    x = rnd(n, 64, h, w_, seed=70)
+    w, b = wb(64, 64, 3, 3)
+    xb, _ = nhwc(x)
+    want = ref_conv(x, w, b)
+    errs = {}
+    try:
+        for split in (1, 3):
+            A.set_option("tc_split", split)
+            out = torch.zeros(n, h, w_, 64, device=DEV)
+            run_conv(w, b, [(xb, 64, 0)], (h, w_), A.CONV_TC, [dict(ch0=0, nch=64, dst=out)])
+            errs[split] = float((from_nhwc(out, 64).double() - want).abs().max())
+    finally:
+        A.set_option("tc_split", 3)
+    print("tf32 x1 err", errs[1], "3xTF32 err", errs[3])
+    assert errs[3] < 2e-5 and errs[1] > 10 * errs[3]
+
+
+def test_tc_operand_truncation_probe():
+    """Does the tensor core truncate fp32 operands to tf32 (mask_hi=0 equals mask_hi=1)?  Reported, and
+    the masked mode (default) must be exact either way."""
+    n, h, w_ = 1, 8, 16
+    x = rnd(n, 32, h, w_, seed=71)
+    w, b = wb(16, 32, 1, 1)
+    xb, _ = nhwc(x)
+    want = ref_conv(x, w, b)
+    res = {}
+    try:
+        for m in (1, 0):
+            A.set_option("tc_mask_hi", m)
+            out = torch.zeros(n, h, w_, 16, device=DEV)
+            run_conv(w, b, [(xb, 32, 0)], (h, w_), A.CONV_TC, [dict(ch0=0, nch=16, dst=out)])
+            res[m] = from_nhwc(out, 16)
+    finally:
+        A.set_option("tc_mask_hi", 1)
+    e1 = float((res[1].double() - want).abs().max())
+    e0 = float((res[0].double() - want).abs().max())
+    print(f"mask_hi=1 err {e1:.3e}; mask_hi=0 err {e0:.3e}; identical={torch.equal(res[0], res[1])}")
+    assert e1 < 2e-5

@@ -1,0 +1,145 @@
+"""End-to-end parity of the B200 forward (through the DeMFInet module -> C ABI) against
+(a) the committed golden vectors produced by the unmodified reference and (b) the oracle,
+including named intermediates, at sizes the oracle finishes in seconds.
+
+Tolerance: BASELINE.json north_star -- 5e-4 max-abs vs the reference fp32 forward, PSNR within
+0.01 dB.  The reference's own 1-vs-8-thread noise on these cases is 1-4e-5 (tests/golden/meta.json)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import case_inputs, load_golden
+from demfi_b200 import synth
+from demfi_b200.DeMFInet import DeMFInet
+from demfi_b200.engine import Engine
+from oracle import demfi_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+TOL = 5e-4
+
+
+def psnr255(a, b):
+    """utils.psnr on np.around(denorm255_np(.)) (utils.py:652-660, main.py:763-770)"""
+    A_ = np.around(np.clip((a.numpy().astype(np.float64) + 1.0) / 2.0, 0, 1) * 255.0)
+    B_ = np.around(np.clip((b.numpy().astype(np.float64) + 1.0) / 2.0, 0, 1) * 255.0)
+    mse = np.mean((A_ - B_) ** 2)
+    return float("inf") if mse == 0 else 10 * np.log10(255.0 ** 2 / mse)
+
+
+@pytest.fixture(scope="module")
+def net(state_dict):
+    m = DeMFInet(synth.default_args()).to(DEV).eval()
+    m.load_state_dict(state_dict, strict=True)
+    return m
+
+
+@pytest.mark.parametrize("case", ["c32x32_n1_noise", "c64x96_n3", "c48x40_n2_b2", "c256x256_n1"])
+def test_forward_matches_reference_golden(net, golden_meta, case):
+    cfg = golden_meta["cases"][case]["cfg"]
+    x, t = case_inputs(cfg)
+    with torch.no_grad():
+        res = net(x.to(DEV), t.to(DEV), cfg["n"])
+    torch.cuda.synchronize()
+    got = {k: v.cpu() for k, v in O.flatten_outputs(res).items()}
+    gold = load_golden(case)
+    worst = 0.0
+    for k, g in gold.items():
+        if k not in got:
+            continue
+        d = float((got[k] - torch.from_numpy(g)).abs().max())
+        worst = max(worst, d)
+        frac = float(((got[k] - torch.from_numpy(g)).abs() > TOL).float().mean())
+        line = f"{case}:{k}: max-abs {d:.3e} frac>5e-4 {frac:.2e}"
+        if k.startswith("S"):
+            line += f" PSNR(ours,ref) {psnr255(got[k], torch.from_numpy(g)):.1f} dB"
+        print(line)
+    assert worst < TOL, f"{case}: max-abs {worst}"
+
+
+def test_intermediates_match_oracle(state_dict, golden_meta):
+    cfg = golden_meta["cases"]["c64x96_n3"]["cfg"]
+    x, t = case_inputs(cfg)
+    inter = {}
+    O.forward(state_dict, x, t, cfg["n"], intermediates=inter)
+    B, H, W = 1, cfg["h"], cfg["w"]
+    eng = Engine(state_dict, B, H, W, DEV)
+    eng.forward(x.to(DEV), t.to(DEV), cfg["n"])
+    torch.cuda.synchronize()
+    v = eng.views
+    mine = {
+        "F0": v["F01"].frames(0, B), "F1": v["F01"].frames(B, B),
+        "flow_01": v["FO"].ch(0, 2), "flow_10": v["FO"].ch(2, 2), "occ_logit_ff": v["FO"].ch(4, 1),
+        "flow_t0": v["AGG1"].ch(192, 2), "flow_t1": v["AGG1"].ch(194, 2), "Ft": v["AGG1"].ch(128, 64),
+        "enc0": v["SE"].frames(0, B).ch(0, 64), "enc1": v["SE"].frames(B, B).ch(0, 64),
+        "fgac_sampled0": v["SMP"].frames(0, B), "fgac_sampled1": v["SMP"].frames(B, B),
+        "fgac_w0": v["WL"].frames(0, B).ch(0, 1), "fgac_w1": v["WL"].frames(B, B).ch(0, 1),
+        "aF0": v["AGG1"].ch(0, 64), "aF1": v["AGG1"].ch(64, 64),
+        "rF0": v["DECIN"].frames(0, B), "rF1": v["DECIN"].frames(B, B), "rFt": v["DECIN"].frames(2 * B, B),
+        "F_rec3": v["FR0"],  # rotates by 2 per iteration: after 3 iterations the state is back in FR0
+    }
+    worst = {}
+    for k, view in mine.items():
+        d = float((view.to_nchw().cpu() - inter[k]).abs().max())
+        worst[k] = d
+        print(f"intermediate {k}: max-abs {d:.3e} (max|ref| {float(inter[k].abs().max()):.2f})")
+    bad = {k: d for k, d in worst.items() if d > TOL}
+    assert not bad, bad
+
+
+def test_prefix_reuse_and_final_only_are_bit_identical(net, golden_meta):
+    cfg = golden_meta["cases"]["c64x96_n3"]["cfg"]
+    x, _ = case_inputs(cfg)
+    xd = x.to(DEV)
+    ts = [torch.tensor([[v]], device=DEV) for v in (0.125, 0.5, 0.875)]
+    with torch.no_grad():
+        base = [net(xd, tt, 3) for tt in ts]
+        net(xd, ts[0], 3)
+        reused = [net(xd, tt, 3, reuse_prefix=True) for tt in ts[1:]]
+        net.final_only = True
+        try:
+            fo = net(xd, ts[1], 3)
+        finally:
+            net.final_only = False
+    torch.cuda.synchronize()
+    for b_, r_ in zip(base[1:], reused):
+        for k, a in O.flatten_outputs(b_).items():
+            assert torch.equal(a, O.flatten_outputs(r_)[k]), f"prefix reuse changed {k}"
+    assert fo[1][0] is None and fo[1][1] is None
+    for j in range(3):
+        assert torch.equal(fo[1][2][j], base[1][1][2][j]), "final_only changed the last Sharps_final"
+    assert torch.equal(fo[2][3], base[1][2][3]) and torch.equal(fo[3][3], base[1][3][3])
+
+
+def test_cuda_core_only_engine_matches_too(state_dict, golden_meta):
+    """The CUDA-core conv kernel alone (DEMFI_CONV_KIND=ffma) is an independent implementation of every conv:
+    both kernel families must agree with the reference."""
+    case = "c32x32_n1_noise"
+    cfg = golden_meta["cases"][case]["cfg"]
+    x, t = case_inputs(cfg)
+    gold = load_golden(case)
+    for kind in ("ffma", "tc"):
+        eng = Engine(state_dict, 1, cfg["h"], cfg["w"], DEV, conv_kind=kind)
+        res = eng.forward(x.to(DEV), t.to(DEV), cfg["n"])
+        torch.cuda.synchronize()
+        got = O.flatten_outputs(res)
+        worst = max(float((got[k].cpu() - torch.from_numpy(g)).abs().max()) for k, g in gold.items())
+        print(f"conv_kind={kind}: worst max-abs vs golden {worst:.3e}")
+        assert worst < TOL
+
+
+def test_return_structure(net):
+    x = synth.make_frames(32, 32, seed=1).to(DEV)
+    t = torch.tensor([[0.5]], device=DEV)
+    with torch.no_grad():
+        r = net(x, t)  # num_update=None -> 1 (DeMFInet.py:126-128)
+        assert len(r) == 5 and len(r[0]) == 3 and len(r[1]) == 1 and len(r[1][0]) == 3
+        assert len(r[2]) == 2 and r[2][0].shape == (1, 4, 32, 32) and r[3][1].shape == (1, 1, 32, 32)
+        assert r[4].shape == (1, 3, 32, 32)
+        r7 = net(x, t, 2, is_training=True)
+        assert len(r7) == 7 and len(r7[5]) == 4 and r7[5][0].shape == (1, 1, 32, 32) and len(r7[6][0]) == 2
+    with pytest.raises(NotImplementedError):
+        net(x, t, 1, is_training=True)
+    with pytest.raises(ValueError):
+        with torch.no_grad():
+            net(synth.make_frames(20, 24), t, 1)
