@@ -1,0 +1,111 @@
+"""CPU: the C-ABI library loads, exports every symbol include/demfi_b200.h declares, the ctypes
+mirror has the C layout, and the host-side weight repacking is correct (no GPU calls)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from demfi_b200 import _abi as A
+
+HEADER = os.path.join(ROOT, "include", "demfi_b200.h")
+
+
+def declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(demfi_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    names = declared_functions()
+    assert len(names) >= 18
+    lib = C.CDLL(A.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in the header but not exported by the library"
+        assert n in A.SYMBOLS, f"{n} has no ctypes prototype in demfi_b200/_abi.py"
+    assert set(A.SYMBOLS) == set(names)
+    assert A.lib().demfi_version() == 1
+
+
+def test_ctypes_struct_layout_matches_c(tmp_path):
+    prog = tmp_path / "sz.c"
+    prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "demfi_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n",'
+                    'sizeof(demfi_src_t),sizeof(demfi_seg_t),sizeof(demfi_conv_t),offsetof(demfi_conv_t,src),'
+                    'offsetof(demfi_conv_t,seg),offsetof(demfi_conv_t,wpack),offsetof(demfi_seg_t,ch0));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    want = [C.sizeof(A.Src), C.sizeof(A.Seg), C.sizeof(A.Conv), A.Conv.src.offset, A.Conv.seg.offset, A.Conv.wpack.offset,
+            A.Seg.ch0.offset]
+    assert got == want, (got, want)
+
+
+def _pack(kind, w, src_C, in_map, out_map, cout_pad):
+    lib = A.lib()
+    Co, Ci, KH, KW = w.shape
+    sC = (A.i32 * len(src_C))(*src_C)
+    n = lib.demfi_packed_weight_floats(kind, KH, KW, sC, len(src_C), cout_pad)
+    out = np.full(n, np.nan, dtype=np.float32)
+    kt = sum(src_C)
+    A.check(lib.demfi_pack_weights(kind, w.ctypes.data, Co, Ci, KH, KW, (A.i32 * kt)(*in_map), sC, len(src_C),
+                                   (A.i32 * cout_pad)(*out_map), cout_pad, out.ctypes.data), "pack")
+    return out
+
+
+def test_pack_weights_ffma_layout():
+    rng = np.random.default_rng(0)
+    w = rng.standard_normal((5, 7, 3, 3)).astype(np.float32)
+    in_map = [6, 5, 4, 3, 2, 1, 0, -1]
+    out_map = [4, 3, 2, 1, 0] + [-1] * 11
+    p = _pack(A.CONV_FFMA, w, [8], in_map, out_map, 16).reshape(9, 8, 16)
+    for tap in range(9):
+        for k in range(8):
+            for n in range(16):
+                want = 0.0 if in_map[k] < 0 or out_map[n] < 0 else w[out_map[n], in_map[k], tap // 3, tap % 3]
+                assert p[tap, k, n] == want
+
+
+def test_pack_weights_tc_layout_hi_lo_swizzle():
+    rng = np.random.default_rng(1)
+    w = rng.standard_normal((20, 44, 1, 5)).astype(np.float32)
+    src_C = [36, 8]  # two sources -> chunks: [0,32) [32,36)+pad | [0,8)+pad
+    in_map = list(range(36)) + list(range(36, 44))
+    out_map = list(range(20)) + [-1] * 12
+    N = 32
+    p = _pack(A.CONV_TC, w, src_C, in_map, out_map, N)
+    assert not np.isnan(p).any()
+    chunks = [(0, 0), (0, 32), (1, 0)]
+    p = p.reshape(len(chunks), 5, 2, N, 32)
+    kbase = [0, 36]
+    for ci, (s, c0) in enumerate(chunks):
+        for tap in range(5):
+            for n in range(N):
+                for k in range(32):
+                    c = c0 + k
+                    v = np.float32(0.0)
+                    if c < src_C[s] and out_map[n] >= 0:
+                        v = w[out_map[n], in_map[kbase[s] + c], 0, tap]
+                    hi = (np.array([v]).view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)[0]
+                    col = ((k >> 2) ^ (n & 7)) * 4 + (k & 3)  # 128-byte swizzle of the 16-byte groups
+                    assert p[ci, tap, 0, n, col] == hi
+                    assert p[ci, tap, 1, n, col] == np.float32(v - hi)
+                    assert abs(float(hi) + float(p[ci, tap, 1, n, col]) - float(v)) == 0.0  # exact split
+
+
+def test_pack_weights_rejects_bad_maps():
+    w = np.zeros((4, 4, 1, 1), dtype=np.float32)
+    with pytest.raises(A.DemfiError):
+        _pack(A.CONV_FFMA, w, [4], [0, 1, 2, 9], [0, 1, 2, 3] + [-1] * 12, 16)
+
+
+def test_no_gpu_means_loud_failure():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    rc = A.lib().demfi_copy_channels(None, 4, None, 4, 1, 1, 0, None)
+    assert rc != 0 and b"no CPU path" in A.lib().demfi_last_error() or rc != 0

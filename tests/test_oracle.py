@@ -1,0 +1,86 @@
+"""CPU: pins oracle/demfi_oracle.py to the golden vectors generated from the unmodified reference
+(oracle/gen_golden.py) and its closed-form primitives to the torch library ops the reference calls."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import case_inputs, load_golden
+from oracle import demfi_oracle as O
+
+# the reference's own 1-thread vs 8-thread noise on these cases is up to 3.8e-5 (tests/golden/meta.json)
+ORACLE_TOL = 1e-4
+
+
+@pytest.mark.parametrize("case", ["c32x32_n1_noise", "c64x96_n3", "c48x40_n2_b2", "c256x256_n1"])
+def test_oracle_matches_reference_golden(state_dict, golden_meta, case):
+    cfg = golden_meta["cases"][case]["cfg"]
+    x, t = case_inputs(cfg)
+    inter = {}
+    res = O.forward(state_dict, x, t, cfg["n"], intermediates=inter)
+    got = O.flatten_outputs(res)
+    got.update({"F0_c8": inter["F0"][:, ::8], "aF0_c8": inter["aF0"][:, ::8], "aF1_c8": inter["aF1"][:, ::8],
+                "F_rec0_c8": inter["F_rec0"][:, ::8], "flow_01": inter["flow_01"], "flow_10": inter["flow_10"],
+                "occ_logit_ff": inter["occ_logit_ff"]})
+    gold = load_golden(case)
+    assert len(gold) >= 4
+    for k, g in gold.items():
+        d = float((got[k] - torch.from_numpy(g)).abs().max())
+        assert d < ORACLE_TOL, f"{case}:{k} max-abs {d}"
+    assert len(res[1]) == cfg["n"] and len(res[2]) == cfg["n"] + 1
+
+
+def test_bilinear_gather_is_grid_sample_align_corners_true():
+    g = torch.Generator().manual_seed(0)
+    img = torch.randn(2, 5, 9, 13, generator=g)
+    px = torch.rand(2, 9, 13, generator=g) * 18 - 3
+    py = torch.rand(2, 9, 13, generator=g) * 14 - 3
+    out, wsum = O.bilinear_gather(img, px, py)
+    grid = torch.stack([2 * px / 12 - 1, 2 * py / 8 - 1], -1)
+    want = F.grid_sample(img, grid, mode="bilinear", padding_mode="zeros", align_corners=True)
+    ones = F.grid_sample(torch.ones_like(img), grid, mode="bilinear", padding_mode="zeros", align_corners=True)
+    assert float((out - want).abs().max()) < 1e-5
+    assert float((wsum - ones[:, :1]).abs().max()) < 1e-5
+
+
+def test_bwarp_identity_and_border_mask():
+    img = torch.arange(2 * 3 * 6 * 7, dtype=torch.float32).reshape(2, 3, 6, 7)
+    assert float((O.bwarp(img, torch.zeros(2, 2, 6, 7)) - img).abs().max()) < 1e-4
+    flo = torch.zeros(2, 2, 6, 7)
+    flo[:, 0] = 0.5  # half a pixel to the right: the last column mixes an out-of-image corner -> masked to 0
+    out = O.bwarp(img, flo)
+    assert float(out[..., -1].abs().max()) == 0.0
+    assert float((out[..., :-1] - 0.5 * (img[..., :-1] + img[..., 1:])).abs().max()) < 1e-4
+
+
+def test_gaussian_splat_against_scalar_loops():
+    """restates sample_one (DeMFInet.py:683-729) with python loops on a tiny case"""
+    g = torch.Generator().manual_seed(1)
+    H, W = 5, 6
+    img = torch.randn(1, 2, H, W, generator=g)
+    flo = torch.randn(1, 2, H, W, generator=g) * 2
+    flo[0, :, 0, 0] = torch.tensor([1.0, -2.0])  # integer displacement
+    acc, nrm = O.gaussian_splat(img, flo)
+    ea = np.zeros((2, H, W))
+    en = np.zeros((H, W))
+    for r in range(H):
+        for c in range(W):
+            dx, dy = float(flo[0, 0, r, c]), float(flo[0, 1, r, c])
+            for oy in (0, 1):
+                for ox in (0, 1):
+                    cy, cx = np.floor(dy) + oy, np.floor(dx) + ox
+                    wgt = np.exp(-((dy - cy) ** 2 + (dx - cx) ** 2))
+                    tr, tc = r + int(cy), c + int(cx)
+                    if 0 <= tr < H and 0 <= tc < W:
+                        ea[:, tr, tc] += img[0, :, r, c].numpy() * wgt
+                        en[tr, tc] += wgt
+    assert np.abs(acc[0].numpy() - ea).max() < 1e-5 and np.abs(nrm[0, 0].numpy() - en).max() < 1e-5
+
+
+def test_space_to_depth_channel_order():
+    x = torch.arange(1 * 2 * 4 * 6, dtype=torch.float32).reshape(1, 2, 4, 6)
+    y = O.space_to_depth(x, 2)
+    for c in range(2):
+        for dy in range(2):
+            for dx in range(2):
+                assert torch.equal(y[0, c * 4 + dy * 2 + dx], x[0, c, dy::2, dx::2])

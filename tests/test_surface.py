@@ -1,0 +1,80 @@
+"""CPU: the drop-in boundary -- DeMFInet nn.Module surface and the host-side plan."""
+import json
+import os
+
+import pytest
+import torch
+
+from conftest import GOLD
+from demfi_b200 import synth
+from demfi_b200.DeMFInet import DeMFInet
+from demfi_b200.engine import Engine
+from demfi_b200 import _abi as A
+
+
+def ref_keys():
+    with open(os.path.join(GOLD, "state_dict_keys.json")) as f:
+        return json.load(f)  # dumped from the reference DeMFInet(args).state_dict() by oracle/gen_golden.py
+
+
+def test_state_dict_names_shapes_order_match_reference():
+    net = DeMFInet(synth.default_args())
+    sd = net.state_dict()
+    keys = ref_keys()
+    assert list(sd.keys()) == list(keys.keys())
+    assert all(list(sd[k].shape) == s and sd[k].dtype == torch.float32 for k, s in keys.items())
+    assert len(sd) == 260 and sum(v.numel() for v in sd.values()) == 7408284
+    assert [n for n, _ in net.named_parameters()] == list(keys.keys())
+
+
+def test_strict_load_and_weights_init_apply():
+    net = DeMFInet(synth.default_args())
+    net.load_state_dict(synth.make_state_dict(0), strict=True)
+
+    def weights_init(m):  # semantics of utils.py:173-180, applied at main.py:176
+        cn = m.__class__.__name__
+        if cn.find("Conv2d") != -1 or cn.find("Conv3d") != -1:
+            torch.nn.init.xavier_normal_(m.weight)
+            torch.nn.init.zeros_(m.bias)
+    net.apply(weights_init)
+    assert float(net.Dec_last2.bias.detach().abs().max()) == 0.0
+
+
+def test_unsupported_configuration_is_an_error_not_a_fallback():
+    with pytest.raises(NotImplementedError):
+        DeMFInet(synth.default_args(nf=32))
+
+
+def test_forward_without_gpu_raises():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    net = DeMFInet(synth.default_args())
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        net(synth.make_frames(32, 32), torch.tensor([[0.5]]), 1)
+
+
+def test_plan_builds_on_host_and_accounts_for_every_conv(state_dict):
+    e = Engine(state_dict, 1, 64, 96, torch.device("cpu"), dry=True)
+    for i in range(6):
+        e._iter_ops(i, True)
+    px = 64 * 96
+    # reference conv work: 3 919 552 + 843 520*N MAC/px.  The plan skips the dead
+    # conv_source_k (2 x 4096 MAC/px, DeMFInet.py:388) and runs the loop-invariant Mixer reference
+    # branch (conv_ref1+conv_ref2 = 56 256 MAC/px, DeMFInet.py:815-816) once instead of N times.
+    for n in (1, 3, 5):
+        want = 3919552 + 843520 * n - 2 * 4096 - 56256 * (n - 1)
+        assert e.conv_macs(n) == want * px, (n, e.conv_macs(n) / px, want)
+    assert e.conv_macs(3, final_only=True) < e.conv_macs(3)
+    n_conv = sum(1 for ops in (e.ops_prefix_ff, e.ops_stage1) for op in ops if op[0] == "conv")
+    # reference: 108 conv calls before the loop.  Here: the two FGAC directions are batched (10 -> 4 launches,
+    # the 2 dead conv_source_k dropped) and the 2 loop-invariant Mixer convs are hoisted in front of the loop.
+    assert n_conv == 108 - 10 + 4 + 2
+    n_iter = sum(1 for op in e._iter_ops(0, True) if op[0] == "conv")
+    assert n_iter == 27 - 2 - 2  # conv_ref1/2 hoisted; z and r of each GRU half share one launch
+    with pytest.raises(RuntimeError):
+        e.forward(torch.zeros(1, 3, 4, 64, 96), torch.tensor([[0.5]]), 1)
+
+
+def test_shape_constraints():
+    with pytest.raises(ValueError):
+        Engine(synth.make_state_dict(0), 1, 36, 64, torch.device("cpu"), dry=True)
