@@ -9,12 +9,19 @@
 //                TMA: that IS the conv's zero padding and the ragged-K handling.
 //   * B stage  : the pre-packed [cout_pad x 32] weight tile, tf32 "hi" part and fp32 residual
 //                "lo" part, pre-swizzled on the host, fetched with one cp.async.bulk.
-//   * split    : four warps turn the fp32 A tile into hi = a & ~0x1fff (in place) and
-//                lo = a - hi (second buffer); D += Ahi*Bhi + Alo*Bhi + Ahi*Blo (fp32 accum in TMEM).
+//   * split    : four warps write lo = a - (a & ~0x1fff) to a second buffer; the raw fp32 tile serves
+//                as the "hi" operand because the tensor core ignores the low 13 mantissa bits
+//                (verified on B200 by tests/test_conv_gpu.py::test_tc_operand_truncation_probe).
+//   * MMA      : per 8-wide k-step two instructions: Ahi x [Bhi;Blo] (N' = 2N: hi*hi into the main
+//                accumulator, hi*lo into the correction accumulator next to it) and Alo x Bhi into the
+//                correction accumulator.  Main and correction are summed in fp32 (RN) by the epilogue:
+//                the tensor core accumulates with truncation, so keeping the small terms out of the main
+//                chain cuts its length 3x (measured: error grows linearly with the chain length).
 // Persistent CTAs (one per SM) walk the tile list; warp roles:
 //   warps 0-3 split A | warps 4-7 epilogue (TMEM -> regs -> fused epilogue -> HBM)
 //   warp 8 TMA producer | warp 9 TMEM allocator + single-thread tcgen05.mma issuer
-// The accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
+// The accumulator pair is double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
+// cout_pad > 128 is processed as N blocks of <= 128 channels (a tile = pixel tile x N block).
 #include <cuda.h>
 
 #include <cstring>
@@ -34,7 +41,8 @@ struct TcParams {
   CUtensorMap tmap[DEMFI_MAX_SRC];
   demfi_conv_t c;
   int tiles_x, tiles_y, ntiles;
-  int stages, acc_stride, tmem_cols;
+  int n_blocks, nb_max;  // N blocking: blocks of nb_max (<=128) channels, the last one may be smaller
+  int stages, buf_stride, tmem_cols;
   int mask_hi, split;
 };
 
@@ -100,6 +108,15 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -122,9 +139,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const demfi_conv_t& c = P.c;
-  const int N = c.cout_pad;
-  const uint32_t b_bytes = (uint32_t)N * 128u;
-  const uint32_t stage_bytes = 2u * TC_A_BYTES + 2u * b_bytes;
+  const uint32_t stage_bytes = 2u * TC_A_BYTES + 2u * (uint32_t)P.nb_max * 128u;
+  auto n_of = [&](int nb) { return min(P.nb_max, c.cout_pad - nb * P.nb_max); };
   const int S = P.stages;
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t bars = smem_base + (uint32_t)S * stage_bytes;  // 8-byte aligned (stage_bytes % 1024 == 0)
@@ -199,25 +215,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
       int t = tile;
+      const int nb = t % P.n_blocks;
+      t /= P.n_blocks;
       const int tx0 = (t % P.tiles_x) * TC_TW;
       t /= P.tiles_x;
       const int ty0 = (t % P.tiles_y) * TC_TH;
       const int n = t / P.tiles_y;
+      const int N = n_of(nb), n0 = nb * P.nb_max;
       const int oy = ty0 + (m >> 4), ox = tx0 + (m & 15);
       const bool valid = (oy < c.H) && (ox < c.W);
       mbar_wait(bar_tfull(acc), acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * P.acc_stride);
+      const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * P.buf_stride);
       for (int col = 0; col < N; col += 16) {
-        uint32_t r[16];
-        tmem_ld16(taddr + (uint32_t)col, r);
+        uint32_t r[16], rc[16];
+        tmem_ld16_nowait(taddr + (uint32_t)col, r);
+        if (P.split == 3) tmem_ld16_nowait(taddr + (uint32_t)(N + col), rc);
+        tmem_ld_wait();
         if (valid) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const float4 b = ld4(c.bias + col + q * 4);
-            epilogue_store4(c, n, oy, ox, col + q * 4,
-                            make_float4(__uint_as_float(r[q * 4 + 0]) + b.x, __uint_as_float(r[q * 4 + 1]) + b.y,
-                                        __uint_as_float(r[q * 4 + 2]) + b.z, __uint_as_float(r[q * 4 + 3]) + b.w));
+            const float4 b = ld4(c.bias + n0 + col + q * 4);
+            float4 v = make_float4(__uint_as_float(r[q * 4 + 0]), __uint_as_float(r[q * 4 + 1]),
+                                   __uint_as_float(r[q * 4 + 2]), __uint_as_float(r[q * 4 + 3]));
+            if (P.split == 3) {
+              v.x += __uint_as_float(rc[q * 4 + 0]); v.y += __uint_as_float(rc[q * 4 + 1]);
+              v.z += __uint_as_float(rc[q * 4 + 2]); v.w += __uint_as_float(rc[q * 4 + 3]);
+            }
+            epilogue_store4(c, n, oy, ox, n0 + col + q * 4, make_float4(v.x + b.x, v.y + b.y, v.z + b.z, v.w + b.w));
           }
         }
       }
@@ -232,10 +257,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
         int t = tile;
+        const int nb = t % P.n_blocks;
+        t /= P.n_blocks;
         const int tx0 = (t % P.tiles_x) * TC_TW;
         t /= P.tiles_x;
         const int ty0 = (t % P.tiles_y) * TC_TH;
         const int n = t / P.tiles_y;
+        const int N = n_of(nb), n0 = nb * P.nb_max;
+        const uint32_t b_bytes = (uint32_t)N * 128u;
         int chunk = 0;
         for (int s = 0; s < c.nsrc; ++s)
           for (int c0 = 0; c0 < c.src[s].C; c0 += TC_KC, ++chunk)
@@ -245,8 +274,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               mbar_arrive_expect_tx(bar_full(stage), (uint32_t)TC_A_BYTES + 2u * b_bytes);
               const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
               tma_load_4d(sa, &P.tmap[s], bar_full(stage), c0, tx0 + kx - c.pad_w, ty0 + ky - c.pad_h, n);
-              const float* wsrc = c.wpack + ((size_t)chunk * taps + tap) * 2 * (size_t)N * TC_KC;
-              bulk_load(sa + 2u * TC_A_BYTES, wsrc, 2u * b_bytes, bar_full(stage));
+              // [Bhi rows n0..n0+N | Blo rows n0..n0+N] land contiguously: one 2N-row K-major tile
+              const float* wsrc = c.wpack + ((size_t)chunk * taps + tap) * 2 * (size_t)c.cout_pad * TC_KC + (size_t)n0 * TC_KC;
+              bulk_load(sa + 2u * TC_A_BYTES, wsrc, b_bytes, bar_full(stage));
+              bulk_load(sa + 2u * TC_A_BYTES + b_bytes, wsrc + (size_t)c.cout_pad * TC_KC, b_bytes, bar_full(stage));
               if (++stage == S) { stage = 0; phase ^= 1; }
             }
       }
@@ -255,13 +286,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     // ===== MMA issuer (warp 9, one thread) =====
     if (lane == 0) {
       // instruction descriptor: D=f32 (1<<4), A=B=tf32 (2<<7, 2<<10), both K-major, N>>3 at 17, M>>4 at 24
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      const uint32_t idesc0 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BM >> 4) << 24);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+        const int N = n_of(tile % P.n_blocks);
+        const uint32_t idesc_n = idesc0 | ((uint32_t)(N >> 3) << 17);         // N columns
+        const uint32_t idesc_2n = idesc0 | ((uint32_t)((2 * N) >> 3) << 17);  // [hi;lo] weight tile: 2N columns
         mbar_wait(bar_tempty(acc), acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * P.acc_stride);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * P.buf_stride);  // main [0,N), correction [N,2N)
         uint32_t accum = 0;
         for (int s = 0; s < c.nsrc; ++s)
           for (int c0 = 0; c0 < c.src[s].C; c0 += TC_KC)
@@ -270,16 +304,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               tc_fence_after();
               const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
               const uint64_t a_hi = make_desc_sw128(sa), a_lo = make_desc_sw128(sa + TC_A_BYTES);
-              const uint64_t b_hi = make_desc_sw128(sa + 2u * TC_A_BYTES), b_lo = make_desc_sw128(sa + 2u * TC_A_BYTES + b_bytes);
+              const uint64_t b_hi = make_desc_sw128(sa + 2u * TC_A_BYTES);
 #pragma unroll
               for (int k = 0; k < TC_KC / 8; ++k) {
                 const uint64_t kk = (uint64_t)(k * 2);  // 32 bytes >> 4 per k-step of 8 tf32
-                umma_tf32(d_tmem, a_hi + kk, b_hi + kk, idesc, accum);
-                accum = 1;
                 if (P.split == 3) {
-                  umma_tf32(d_tmem, a_lo + kk, b_hi + kk, idesc, 1);
-                  umma_tf32(d_tmem, a_hi + kk, b_lo + kk, idesc, 1);
+                  umma_tf32(d_tmem, a_hi + kk, b_hi + kk, idesc_2n, accum);             // hi*hi | hi*lo
+                  umma_tf32(d_tmem + (uint32_t)N, a_lo + kk, b_hi + kk, idesc_n, 1);     // lo*hi -> correction
+                } else {
+                  umma_tf32(d_tmem, a_hi + kk, b_hi + kk, idesc_n, accum);
                 }
+                accum = 1;
               }
               umma_commit(bar_empty(stage));
               if (++stage == S) { stage = 0; phase ^= 1; }
@@ -351,17 +386,19 @@ int launch_conv_tc(const demfi_conv_t& c, cudaStream_t st) {
   P.tiles_x = (c.W + TC_TW - 1) / TC_TW;
   P.tiles_y = (c.H + TC_TH - 1) / TC_TH;
   const long long nt = (long long)P.tiles_x * P.tiles_y * c.N;
-  DEMFI_REQUIRE(nt > 0 && nt < (1ll << 31), "conv_tc: bad tile count");
-  P.ntiles = (int)nt;
-  const int stage_bytes = 2 * TC_A_BYTES + 2 * c.cout_pad * 128;
+  P.nb_max = c.cout_pad < 128 ? c.cout_pad : 128;
+  P.n_blocks = (c.cout_pad + P.nb_max - 1) / P.nb_max;
+  DEMFI_REQUIRE(nt > 0 && nt * P.n_blocks < (1ll << 31), "conv_tc: bad tile count");
+  P.ntiles = (int)nt * P.n_blocks;
+  const int stage_bytes = 2 * TC_A_BYTES + 2 * P.nb_max * 128;
   int stages = TC_SMEM_BUDGET / stage_bytes;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   DEMFI_REQUIRE(stages >= 2, "conv_tc: not enough shared memory for two stages");
   P.stages = stages;
-  int acc_stride = 32;
-  while (acc_stride < c.cout_pad) acc_stride *= 2;
-  P.acc_stride = acc_stride;
-  P.tmem_cols = 2 * acc_stride;
+  int buf_stride = 32;  // columns per accumulator pair (main + correction), power of two
+  while (buf_stride < 2 * P.nb_max) buf_stride *= 2;
+  P.buf_stride = buf_stride;
+  P.tmem_cols = 2 * buf_stride;
   P.mask_hi = get_option("tc_mask_hi");
   P.split = get_option("tc_split");
   const int smem = stages * stage_bytes + 8 * (3 * stages + 4) + 16 + 1024;

@@ -53,6 +53,31 @@ def test_plain_relu(kind, n, h, w_, ci, co, k):
 
 
 @pytest.mark.parametrize("kind", KINDS)
+def test_more_tiles_than_sms(kind):
+    """persistent tile loop: 2*20*20 = 800 tiles > 148 CTAs, ragged right/bottom tiles (152 = 9.5*16, 156 = 19.5*8)"""
+    n, h, w_ = 2, 156, 312
+    x = rnd(n, 64, h, w_, seed=80)
+    w, b = wb(64, 64, 3, 3)
+    xb, _ = nhwc(x)
+    res = rnd(n, 64, h, w_, seed=81)
+    rb, _ = nhwc(res)
+    out = torch.zeros(n, h, w_, 64, device=DEV)
+    run_conv(w, b, [(xb, 64, 0)], (h, w_), kind, [dict(ch0=0, nch=64, dst=out, res=rb)])
+    check(from_nhwc(out, 64), ref_conv(x, w, b) + res.double(), "many tiles + residual")
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_wide_cout_two_n_blocks(kind):
+    n, h, w_ = 1, 40, 48
+    x = rnd(n, 96, h, w_, seed=82)
+    w, b = wb(144, 96, 3, 3)
+    xb, _ = nhwc(x)
+    out = torch.zeros(n, h, w_, 144, device=DEV)
+    run_conv(w, b, [(xb, 96, 0)], (h, w_), kind, [dict(ch0=0, nch=144, dst=out, act=A.ACT_TANH)])
+    check(from_nhwc(out, 144), torch.tanh(ref_conv(x, w, b)), "cout 144 = 128 + 16")
+
+
+@pytest.mark.parametrize("kind", KINDS)
 def test_residual_into_slice(kind):
     # RDB-style: read channels [0,160) of a 224-wide buffer, write 32 channels into the same buffer
     n, h, w_ = 1, 16, 48

@@ -87,7 +87,10 @@ def test_intermediates_match_oracle(state_dict, golden_meta):
     assert not bad, bad
 
 
-def test_prefix_reuse_and_final_only_are_bit_identical(net, golden_meta):
+def test_prefix_reuse_and_final_only_change_nothing(net, golden_meta):
+    """Skipping the t-independent prefix / the D2 decodes of non-final iterations must not change what is
+    returned.  The CFR splat adds with fp32 atomics (as the reference's CUDA put_ does), so two runs agree to
+    rounding, not bit-for-bit: compare at 2e-5."""
     cfg = golden_meta["cases"]["c64x96_n3"]["cfg"]
     x, _ = case_inputs(cfg)
     xd = x.to(DEV)
@@ -102,13 +105,14 @@ def test_prefix_reuse_and_final_only_are_bit_identical(net, golden_meta):
         finally:
             net.final_only = False
     torch.cuda.synchronize()
+    close = lambda a, b: float((a - b).abs().max()) < 2e-5
     for b_, r_ in zip(base[1:], reused):
         for k, a in O.flatten_outputs(b_).items():
-            assert torch.equal(a, O.flatten_outputs(r_)[k]), f"prefix reuse changed {k}"
+            assert close(a, O.flatten_outputs(r_)[k]), f"prefix reuse changed {k}"
     assert fo[1][0] is None and fo[1][1] is None
     for j in range(3):
-        assert torch.equal(fo[1][2][j], base[1][1][2][j]), "final_only changed the last Sharps_final"
-    assert torch.equal(fo[2][3], base[1][2][3]) and torch.equal(fo[3][3], base[1][3][3])
+        assert close(fo[1][2][j], base[1][1][2][j]), "final_only changed the last Sharps_final"
+    assert close(fo[2][3], base[1][2][3]) and close(fo[3][3], base[1][3][3])
 
 
 def test_cuda_core_only_engine_matches_too(state_dict, golden_meta):
