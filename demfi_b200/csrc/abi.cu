@@ -21,9 +21,11 @@ void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_r
 
 static std::atomic<int> g_opt_mask_hi{0};
 static std::atomic<int> g_opt_split{3};
+static std::atomic<int> g_opt_flush{4};
 int get_option(const char* name) {
   if (!strcmp(name, "tc_mask_hi")) return g_opt_mask_hi.load();
   if (!strcmp(name, "tc_split")) return g_opt_split.load();
+  if (!strcmp(name, "tc_flush")) return g_opt_flush.load();
   return -1;
 }
 
@@ -79,6 +81,7 @@ int demfi_set_option(const char* name, int32_t value) {
     g_opt_split.store(value);
     return 0;
   }
+  if (!strcmp(name, "tc_flush")) { g_opt_flush.store(value < 0 ? 0 : value); return 0; }
   set_error("set_option: unknown option '%s'", name);
   return 1;
 }

@@ -44,6 +44,8 @@ struct TcParams {
   int n_blocks, nb_max;  // N blocking: blocks of nb_max (<=128) channels, the last one may be smaller
   int stages, buf_stride, tmem_cols;
   int mask_hi, split;
+  int flush;         // K stages accumulated inside the tensor core before the partial sum is drained to registers
+  int stages_per_tile;
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------
@@ -135,6 +137,7 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
 }
 
 // ---- kernel -----------------------------------------------------------------------------
+template <int NMAX>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -224,31 +227,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const int N = n_of(nb), n0 = nb * P.nb_max;
       const int oy = ty0 + (m >> 4), ox = tx0 + (m & 15);
       const bool valid = (oy < c.H) && (ox < c.W);
-      mbar_wait(bar_tfull(acc), acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * P.buf_stride);
-      for (int col = 0; col < N; col += 16) {
-        uint32_t r[16], rc[16];
-        tmem_ld16_nowait(taddr + (uint32_t)col, r);
-        if (P.split == 3) tmem_ld16_nowait(taddr + (uint32_t)(N + col), rc);
-        tmem_ld_wait();
-        if (valid) {
+      // The tensor core accumulates with truncation (a biased error that compounds over ~100 layers), so
+      // the K loop is cut into segments of P.flush stages: each segment's partial sum is drained from
+      // TMEM and added here in fp32 round-to-nearest while the MMAs of the next segment run.
+      float sum[NMAX];
+      bool first = true;
+      for (int done = 0; done < P.stages_per_tile; done += P.flush) {
+        mbar_wait(bar_tfull(acc), acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * P.buf_stride);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 b = ld4(c.bias + n0 + col + q * 4);
-            float4 v = make_float4(__uint_as_float(r[q * 4 + 0]), __uint_as_float(r[q * 4 + 1]),
-                                   __uint_as_float(r[q * 4 + 2]), __uint_as_float(r[q * 4 + 3]));
-            if (P.split == 3) {
-              v.x += __uint_as_float(rc[q * 4 + 0]); v.y += __uint_as_float(rc[q * 4 + 1]);
-              v.z += __uint_as_float(rc[q * 4 + 2]); v.w += __uint_as_float(rc[q * 4 + 3]);
+        for (int col = 0; col < NMAX; col += 16) {
+          if (col < N) {
+            uint32_t r[16], rc[16];
+            tmem_ld16_nowait(taddr + (uint32_t)col, r);
+            if (P.split == 3) tmem_ld16_nowait(taddr + (uint32_t)(N + col), rc);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float v = __uint_as_float(r[j]);
+              if (P.split == 3) v += __uint_as_float(rc[j]);
+              sum[col + j] = first ? v : sum[col + j] + v;
             }
-            epilogue_store4(c, n, oy, ox, n0 + col + q * 4, make_float4(v.x + b.x, v.y + b.y, v.z + b.z, v.w + b.w));
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(bar_tempty(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        first = false;
+      }
+      if (valid) {
+#pragma unroll
+        for (int col = 0; col < NMAX; col += 4) {
+          if (col < N) {
+            const float4 b = ld4(c.bias + n0 + col);
+            epilogue_store4(c, n, oy, ox, n0 + col,
+                            make_float4(sum[col] + b.x, sum[col + 1] + b.y, sum[col + 2] + b.z, sum[col + 3] + b.w));
           }
         }
       }
-      tc_fence_before();
-      mbar_arrive(bar_tempty(acc));
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp == 8) {
     // ===== TMA producer =====
@@ -293,13 +310,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const int N = n_of(tile % P.n_blocks);
         const uint32_t idesc_n = idesc0 | ((uint32_t)(N >> 3) << 17);         // N columns
         const uint32_t idesc_2n = idesc0 | ((uint32_t)((2 * N) >> 3) << 17);  // [hi;lo] weight tile: 2N columns
-        mbar_wait(bar_tempty(acc), acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * P.buf_stride);  // main [0,N), correction [N,2N)
-        uint32_t accum = 0;
+        int in_seg = 0, done = 0;
+        uint32_t d_tmem = 0, accum = 0;
         for (int s = 0; s < c.nsrc; ++s)
           for (int c0 = 0; c0 < c.src[s].C; c0 += TC_KC)
             for (int tap = 0; tap < taps; ++tap) {
+              if (in_seg == 0) {  // new accumulation segment: fresh accumulator pair
+                mbar_wait(bar_tempty(acc), acc_phase ^ 1);
+                d_tmem = tmem_base + (uint32_t)(acc * P.buf_stride);  // main [0,N), correction [N,2N)
+                accum = 0;
+              }
               mbar_wait(bar_split(stage), phase);
               tc_fence_after();
               const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
@@ -318,9 +338,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               }
               umma_commit(bar_empty(stage));
               if (++stage == S) { stage = 0; phase ^= 1; }
+              ++done;
+              if (++in_seg == P.flush || done == P.stages_per_tile) {
+                umma_commit(bar_tfull(acc));
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                in_seg = 0;
+              }
             }
-        umma_commit(bar_tfull(acc));
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   }
@@ -401,15 +425,23 @@ int launch_conv_tc(const demfi_conv_t& c, cudaStream_t st) {
   P.tmem_cols = 2 * buf_stride;
   P.mask_hi = get_option("tc_mask_hi");
   P.split = get_option("tc_split");
+  P.stages_per_tile = 0;
+  for (int s = 0; s < c.nsrc; ++s) P.stages_per_tile += ((c.src[s].C + TC_KC - 1) / TC_KC) * c.KH * c.KW;
+  P.flush = get_option("tc_flush");
+  if (P.flush <= 0 || P.flush > P.stages_per_tile) P.flush = P.stages_per_tile;
   const int smem = stages * stage_bytes + 8 * (3 * stages + 4) + 16 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     DEMFI_REQUIRE(e == cudaSuccess, "conv_tc: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
     attr_set = true;
   }
   const int grid = P.ntiles < num_sms() ? P.ntiles : num_sms();
-  conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(P);
+  if (P.nb_max <= 32) conv_tc_kernel<32><<<grid, TC_THREADS, smem, st>>>(P);
+  else if (P.nb_max <= 64) conv_tc_kernel<64><<<grid, TC_THREADS, smem, st>>>(P);
+  else conv_tc_kernel<128><<<grid, TC_THREADS, smem, st>>>(P);
   DEMFI_LAUNCH_CHECK("conv_tc");
   return 0;
 }

@@ -164,7 +164,9 @@ uint64_t demfi_launch_count(void);
 /* Runtime options (diagnostics / measurement): "tc_mask_hi" (1: the tf32 "hi" operand tile is
  * masked in shared memory, 0: the raw fp32 tile is fed and the tensor core's own truncation is
  * relied on), "tc_split" (3: 3xTF32, fp32-parity mode, default; 1: single-pass TF32, NOT parity
- * grade, for measurement only).  Returns non-zero for an unknown option. */
+ * grade, for measurement only), "tc_flush" (K stages of 32 channels accumulated inside the tensor core
+ * before the partial sum is drained and added in fp32 round-to-nearest; default 4, 0 = whole K).
+ * Returns non-zero for an unknown option. */
 int demfi_set_option(const char* name, int32_t value);
 int demfi_get_option(const char* name, int32_t* value);
 
