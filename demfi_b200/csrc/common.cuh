@@ -46,46 +46,77 @@ __device__ __forceinline__ float act_scalar(int act, float v) {
   }
 }
 
-// Epilogue shared by the CUDA-core and the tcgen05 convolution kernels: four consecutive
-// accumulator channels [co, co+4) of output pixel (n, y, x).  `acc` already holds the bias.
-// Every segment whose channel range covers `co` receives the values (ranges may overlap: that
-// is how one conv output is written to two consumers' buffers).
-__device__ __forceinline__ void epilogue_store4(const demfi_conv_t& p, int n, int y, int x, int co, float4 acc) {
-#pragma unroll 1
-  for (int s = 0; s < p.nseg; ++s) {
-    const demfi_seg_t& sg = p.seg[s];
-    const int c = co - sg.ch0;
-    if (c < 0 || c >= sg.nch) continue;
-    size_t pix;
-    int cc = c;
-    if (sg.store == DEMFI_STORE_PIXEL_SHUFFLE2) {
-      const int cq = sg.nch >> 2;
-      const int q = c / cq;
-      cc = c - q * cq;
-      pix = ((size_t)n * (2 * p.H) + (2 * y + (q >> 1))) * (size_t)(2 * p.W) + (2 * x + (q & 1));
-    } else {
-      pix = ((size_t)n * p.H + y) * (size_t)p.W + x;
+// Epilogue shared by the CUDA-core and the tcgen05 convolution kernels.
+//
+// seg_store4: final value of four consecutive channels -> activation/residual/GRU math -> one
+// 128-bit store.  Deliberately NOT inlined: the conv kernels call it from unrolled loops and an
+// inlined copy per call site blew the instruction cache (ncu: stall_no_instruction dominated the
+// epilogue warps, profiles/r1_conv_tc_epilogue.md).
+static __device__ __noinline__ void seg_store4(float* d, const float* r, const float* r2, int act, float4 v) {
+  if (act == DEMFI_ACT_SIGMOID_MUL) {
+    const float4 h = ld4(r);
+    v.x = sigmoid_f(v.x) * h.x; v.y = sigmoid_f(v.y) * h.y; v.z = sigmoid_f(v.z) * h.z; v.w = sigmoid_f(v.w) * h.w;
+  } else if (act == DEMFI_ACT_GRU) {
+    const float4 h = ld4(r);
+    const float4 z = ld4(r2);
+    v.x = (1.0f - z.x) * h.x + z.x * tanhf(v.x);
+    v.y = (1.0f - z.y) * h.y + z.y * tanhf(v.y);
+    v.z = (1.0f - z.z) * h.z + z.z * tanhf(v.z);
+    v.w = (1.0f - z.w) * h.w + z.w * tanhf(v.w);
+  } else {
+    if (r != nullptr) {
+      const float4 h = ld4(r);
+      v.x += h.x; v.y += h.y; v.z += h.z; v.w += h.w;
     }
-    float4 v = acc;
-    if (sg.act == DEMFI_ACT_SIGMOID_MUL) {
-      const float4 r = ld4(sg.res + pix * sg.res_ld + cc);
-      v.x = sigmoid_f(v.x) * r.x; v.y = sigmoid_f(v.y) * r.y; v.z = sigmoid_f(v.z) * r.z; v.w = sigmoid_f(v.w) * r.w;
-    } else if (sg.act == DEMFI_ACT_GRU) {
-      const float4 h = ld4(sg.res + pix * sg.res_ld + cc);
-      const float4 z = ld4(sg.res2 + pix * sg.res2_ld + cc);
-      v.x = (1.0f - z.x) * h.x + z.x * tanhf(v.x);
-      v.y = (1.0f - z.y) * h.y + z.y * tanhf(v.y);
-      v.z = (1.0f - z.z) * h.z + z.z * tanhf(v.z);
-      v.w = (1.0f - z.w) * h.w + z.w * tanhf(v.w);
-    } else {
-      if (sg.res != nullptr) {
-        const float4 r = ld4(sg.res + pix * sg.res_ld + cc);
-        v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
-      }
-      v.x = act_scalar(sg.act, v.x); v.y = act_scalar(sg.act, v.y);
-      v.z = act_scalar(sg.act, v.z); v.w = act_scalar(sg.act, v.w);
+    if (act == DEMFI_ACT_RELU) {
+      v.x = fmaxf(v.x, 0.0f); v.y = fmaxf(v.y, 0.0f); v.z = fmaxf(v.z, 0.0f); v.w = fmaxf(v.w, 0.0f);
+    } else if (act == DEMFI_ACT_TANH) {
+      v.x = tanhf(v.x); v.y = tanhf(v.y); v.z = tanhf(v.z); v.w = tanhf(v.w);
+    } else if (act == DEMFI_ACT_SIGMOID) {
+      v.x = sigmoid_f(v.x); v.y = sigmoid_f(v.y); v.z = sigmoid_f(v.z); v.w = sigmoid_f(v.w);
     }
-    st4(sg.dst + pix * sg.dst_ld + cc, v);
+  }
+  st4(d, v);
+}
+
+// Per (output pixel, segment) addressing, computed once and reused for every channel group.
+struct SegCursor {
+  float* dst;        // address of the segment's channel 0 at this pixel (NHWC store)
+  float* dst_base;   // segment base (pixel-shuffle store addresses four other pixels)
+  const float* res;  // same for the optional operands
+  const float* res2;
+  int lo, hi;        // accumulator-channel range [lo, hi) the segment takes
+  int act, store, cq;
+  int dst_ld, n, y, x, H2, W2;  // pixel-shuffle store addresses the four pixels (2y+dy, 2x+dx)
+};
+
+__device__ __forceinline__ SegCursor seg_cursor(const demfi_conv_t& p, const demfi_seg_t& sg, int n, int y, int x) {
+  SegCursor c;
+  const size_t pix = ((size_t)n * p.H + y) * (size_t)p.W + x;
+  c.lo = sg.ch0;
+  c.hi = sg.ch0 + sg.nch;
+  c.act = sg.act;
+  c.store = sg.store;
+  c.cq = sg.nch >> 2;
+  c.dst_ld = sg.dst_ld;
+  c.dst = sg.dst + pix * sg.dst_ld;
+  c.dst_base = sg.dst;
+  c.res = sg.res ? sg.res + pix * sg.res_ld : nullptr;
+  c.res2 = sg.res2 ? sg.res2 + pix * sg.res2_ld : nullptr;
+  c.n = n; c.y = y; c.x = x; c.H2 = 2 * p.H; c.W2 = 2 * p.W;
+  return c;
+}
+
+// channels [co, co+4) (co = absolute accumulator channel) of the cursor's pixel; v already holds the bias
+__device__ __forceinline__ void seg_emit4(const SegCursor& c, int co, float4 v) {
+  if (co < c.lo || co >= c.hi) return;
+  const int cc = co - c.lo;
+  if (c.store == DEMFI_STORE_PIXEL_SHUFFLE2) {
+    const int q = cc / c.cq;
+    const size_t pq = ((size_t)c.n * c.H2 + (2 * c.y + (q >> 1))) * (size_t)c.W2 + (2 * c.x + (q & 1));
+    seg_store4(c.dst_base + pq * c.dst_ld + (cc - q * c.cq), nullptr, nullptr, c.act, v);
+  } else {
+    seg_store4(c.dst + cc, c.res ? c.res + cc : nullptr, c.res2 ? c.res2 + cc : nullptr, c.act, v);
   }
 }
 

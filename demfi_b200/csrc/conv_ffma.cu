@@ -144,13 +144,18 @@ conv_ffma_kernel(const __grid_constant__ demfi_conv_t p, int tiles_x, int tiles_
   const int co = co0 + ctx * 4;
   if (co >= p.cout_pad) return;
   const float4 bias = ld4(p.bias + co);
+#pragma unroll 1
+  for (int s = 0; s < p.nseg; ++s) {
+    if (co < p.seg[s].ch0 || co >= p.seg[s].ch0 + p.seg[s].nch) continue;
 #pragma unroll
-  for (int i = 0; i < TM; ++i) {
-    const int px = cty * TM + i;
-    const int oy = ty0 + (px >> 4), ox = tx0 + (px & 15);
-    if (oy < p.H && ox < p.W)
-      epilogue_store4(p, n, oy, ox, co,
-                      make_float4(acc[i][0] + bias.x, acc[i][1] + bias.y, acc[i][2] + bias.z, acc[i][3] + bias.w));
+    for (int i = 0; i < TM; ++i) {
+      const int px = cty * TM + i;
+      const int oy = ty0 + (px >> 4), ox = tx0 + (px & 15);
+      if (oy < p.H && ox < p.W) {
+        const SegCursor cur = seg_cursor(p, p.seg[s], n, oy, ox);
+        seg_emit4(cur, co, make_float4(acc[i][0] + bias.x, acc[i][1] + bias.y, acc[i][2] + bias.z, acc[i][3] + bias.w));
+      }
+    }
   }
 }
 

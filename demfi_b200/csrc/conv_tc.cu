@@ -72,8 +72,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug becomes a trapped launch (reported error), never a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 8000000000ll) {
@@ -82,6 +81,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       __trap();
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
                                             int c3) {
@@ -257,12 +259,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         first = false;
       }
       if (valid) {
+#pragma unroll 1
+        for (int sgi = 0; sgi < c.nseg; ++sgi) {
+          if (c.seg[sgi].ch0 >= n0 + N || c.seg[sgi].ch0 + c.seg[sgi].nch <= n0) continue;
+          const SegCursor cur = seg_cursor(c, c.seg[sgi], n, oy, ox);
 #pragma unroll
-        for (int col = 0; col < NMAX; col += 4) {
-          if (col < N) {
-            const float4 b = ld4(c.bias + n0 + col);
-            epilogue_store4(c, n, oy, ox, n0 + col,
-                            make_float4(sum[col] + b.x, sum[col + 1] + b.y, sum[col + 2] + b.z, sum[col + 3] + b.w));
+          for (int col = 0; col < NMAX; col += 4) {
+            if (col < N) {
+              const float4 b = ld4(c.bias + n0 + col);
+              seg_emit4(cur, n0 + col, make_float4(sum[col] + b.x, sum[col + 1] + b.y, sum[col + 2] + b.z, sum[col + 3] + b.w));
+            }
           }
         }
       }
@@ -417,6 +423,7 @@ int launch_conv_tc(const demfi_conv_t& c, cudaStream_t st) {
   const int stage_bytes = 2 * TC_A_BYTES + 2 * P.nb_max * 128;
   int stages = TC_SMEM_BUDGET / stage_bytes;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+  if (get_option("tc_stages") >= 2 && get_option("tc_stages") < stages) stages = get_option("tc_stages");
   DEMFI_REQUIRE(stages >= 2, "conv_tc: not enough shared memory for two stages");
   P.stages = stages;
   int buf_stride = 32;  // columns per accumulator pair (main + correction), power of two
@@ -438,7 +445,8 @@ int launch_conv_tc(const demfi_conv_t& c, cudaStream_t st) {
     DEMFI_REQUIRE(e == cudaSuccess, "conv_tc: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  const int grid = P.ntiles < num_sms() ? P.ntiles : num_sms();
+  int grid = P.ntiles < num_sms() ? P.ntiles : num_sms();
+  if (get_option("tc_grid") > 0 && get_option("tc_grid") < grid) grid = get_option("tc_grid");
   if (P.nb_max <= 32) conv_tc_kernel<32><<<grid, TC_THREADS, smem, st>>>(P);
   else if (P.nb_max <= 64) conv_tc_kernel<64><<<grid, TC_THREADS, smem, st>>>(P);
   else conv_tc_kernel<128><<<grid, TC_THREADS, smem, st>>>(P);

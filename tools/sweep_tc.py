@@ -1,0 +1,30 @@
+"""Diagnostic sweeps of the tcgen05 conv (one shape) over runtime knobs."""
+import json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from demfi_b200 import _abi as A
+from tools.bench_conv import make_conv, time_conv
+
+H, W = 736, 1280
+shape = dict(n=1, h=H, w=W, srcC=[64], co=64, k=(3, 3))
+d, keep = make_conv(A.CONV_TC, **shape)
+macs = H * W * 64 * 64 * 9
+base = dict(tc_flush=0, tc_stages=0, tc_grid=0, tc_split=3, tc_mask_hi=0)
+def run(**kw):
+    o = dict(base); o.update(kw)
+    for k, v in o.items():
+        A.set_option(k, v)
+    ms = time_conv(d)
+    print(json.dumps({**kw, "ms": round(ms, 3), "TFLOPs": round(2 * macs / ms / 1e9, 1)}), flush=True)
+for f in (0, 8, 4, 2, 1):
+    run(tc_flush=f)
+for s in (2, 3, 4):
+    run(tc_stages=s)
+for g in (148, 111, 74, 37):
+    run(tc_grid=g)
+run(tc_split=1)
+run(tc_split=1, tc_stages=2)
+run(tc_mask_hi=1)
+run(tc_flush=2, tc_grid=74)
+for k, v in base.items():
+    A.set_option(k, v)
