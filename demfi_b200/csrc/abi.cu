@@ -19,7 +19,7 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
-static std::atomic<int> g_opt_mask_hi{0};
+static std::atomic<int> g_opt_mask_hi{1};
 static std::atomic<int> g_opt_split{3};
 static std::atomic<int> g_opt_flush{2};
 static std::atomic<int> g_opt_stages{0};  // diagnostics: cap on pipeline stages (0 = as many as fit)

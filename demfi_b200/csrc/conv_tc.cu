@@ -199,10 +199,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 const int i = threadIdx.x + j * 128;
                 const float4 v = a[i];
                 float4 h;
-                h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
-                h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
-                h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
-                h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+                // mask_hi: hi = tf32 round-to-nearest of a (written back in place; lo gets a random sign, so
+                // the tensor core's truncation of lo is unbiased).  otherwise hi = truncation = what the tensor
+                // core sees in the raw tile, nothing to write back.
+                const uint32_t rnd = P.mask_hi ? 0x1000u : 0u;
+                h.x = __uint_as_float((__float_as_uint(v.x) + rnd) & 0xffffe000u);
+                h.y = __uint_as_float((__float_as_uint(v.y) + rnd) & 0xffffe000u);
+                h.z = __uint_as_float((__float_as_uint(v.z) + rnd) & 0xffffe000u);
+                h.w = __uint_as_float((__float_as_uint(v.w) + rnd) & 0xffffe000u);
                 lo[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
                 if (P.mask_hi) a[i] = h;
               }
@@ -484,7 +488,7 @@ int tc_pack_weights(const float* w, int Co, int Ci, int KH, int KW, const int32_
             }
             uint32_t bits;
             memcpy(&bits, &v, 4);
-            bits &= 0xffffe000u;
+            bits = (bits + 0x1000u) & 0xffffe000u;  // tf32 round-to-nearest (ties away): residual sign is random
             float h;
             memcpy(&h, &bits, 4);
             const size_t off = (size_t)n * TC_KC + (size_t)(((k >> 2) ^ (n & 7)) << 2) + (k & 3);

@@ -78,6 +78,7 @@ class Engine:
         self._alloc()
         self._sd = {k: v.detach().to("cpu", torch.float32).contiguous() for k, v in state_dict.items()}
         self._wcache: Dict[tuple, tuple] = {}
+        self.profile: Optional[list] = None  # when a list: (op, start_event, end_event) per launched op
         self._build()
 
     # ------------------------------------------------------------------ memory
@@ -402,7 +403,22 @@ class Engine:
     # ------------------------------------------------------------------ execution
     def _run(self, ops, st):
         lib, B, H, W = self.lib, self.B, self.H, self.W
+        prof = self.profile
         for op in ops:
+            k = op[0]
+            if prof is not None:
+                e0 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+                self._run_one(op, st)
+                e1 = torch.cuda.Event(enable_timing=True)
+                e1.record()
+                prof.append((op, e0, e1))
+            else:
+                self._run_one(op, st)
+
+    def _run_one(self, op, st):
+        lib, B, H, W = self.lib, self.B, self.H, self.W
+        if True:
             k = op[0]
             if k == "conv":
                 A.check(lib.demfi_conv2d(C.byref(op[1]), st), f"conv2d[{op[2]}]")
@@ -476,6 +492,27 @@ class Engine:
             else:
                 sharps_final.append(None)
         return sharps_dec1, sharps_final, flow_predictions, occ0_predictions, two_blurry
+
+    def profile_summary(self) -> Dict[str, dict]:
+        """Aggregate self.profile (CUDA-event durations on the launch stream) per kernel family."""
+        out: Dict[str, dict] = {}
+        for op, e0, e1 in self.profile or []:
+            ms = e0.elapsed_time(e1)
+            if op[0] == "conv":
+                fam = "conv_tc" if op[3] == A.CONV_TC else "conv_ffma"
+                macs = op[4]
+            else:
+                fam, macs = op[0], 0
+            d = out.setdefault(fam, {"launches": 0, "ms": 0.0, "macs": 0, "by_label": {}})
+            d["launches"] += 1
+            d["ms"] += ms
+            d["macs"] += macs
+            if op[0] == "conv":
+                b = d["by_label"].setdefault(op[2].split(".")[-1] if False else op[2], {"launches": 0, "ms": 0.0, "macs": 0})
+                b["launches"] += 1
+                b["ms"] += ms
+                b["macs"] += macs
+        return out
 
     # ------------------------------------------------------------------ accounting
     def conv_macs(self, num_update: int, final_only=False, reuse_prefix=False) -> int:

@@ -161,11 +161,12 @@ int demfi_import_nchw(const float* src, int32_t B, int32_t H, int32_t W, int32_t
 /* ---- introspection ---------------------------------------------------------------------- */
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 uint64_t demfi_launch_count(void);
-/* Runtime options (diagnostics / measurement): "tc_mask_hi" (1: the tf32 "hi" operand tile is
- * masked in shared memory, 0: the raw fp32 tile is fed and the tensor core's own truncation is
- * relied on), "tc_split" (3: 3xTF32, fp32-parity mode, default; 1: single-pass TF32, NOT parity
+/* Runtime options (diagnostics / measurement): "tc_mask_hi" (1, default: the activation tile is split as
+ * hi = tf32 round-to-nearest, written back to shared memory, lo = a - hi; 0: hi = truncation, i.e. the raw
+ * fp32 tile is fed and the tensor core's own truncation is relied on -- measured identical operand
+ * behaviour on B200, slightly more biased residual), "tc_split" (3: 3xTF32, fp32-parity mode, default; 1: single-pass TF32, NOT parity
  * grade, for measurement only), "tc_flush" (K stages of 32 channels accumulated inside the tensor core
- * before the partial sum is drained and added in fp32 round-to-nearest; default 4, 0 = whole K).
+ * before the partial sum is drained and added in fp32 round-to-nearest; default 2, 0 = whole K), "tc_stages" / "tc_grid" (caps on pipeline depth / persistent CTAs, 0 = auto).
  * Returns non-zero for an unknown option. */
 int demfi_set_option(const char* name, int32_t value);
 int demfi_get_option(const char* name, int32_t* value);

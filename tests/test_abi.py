@@ -90,7 +90,7 @@ def test_pack_weights_tc_layout_hi_lo_swizzle():
                     v = np.float32(0.0)
                     if c < src_C[s] and out_map[n] >= 0:
                         v = w[out_map[n], in_map[kbase[s] + c], 0, tap]
-                    hi = (np.array([v]).view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)[0]
+                    hi = ((np.array([v]).view(np.uint32) + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)[0]
                     col = ((k >> 2) ^ (n & 7)) * 4 + (k & 3)  # 128-byte swizzle of the 16-byte groups
                     assert p[ci, tap, 0, n, col] == hi
                     assert p[ci, tap, 1, n, col] == np.float32(v - hi)
