@@ -46,6 +46,9 @@ struct TcParams {
   int mask_hi, split;
   int flush;         // K stages accumulated inside the tensor core before the partial sum is drained to registers
   int stages_per_tile;
+  int diag;              // diagnostics bitmask (tc_diag): 1 no global stores, 2 interleaved (not grouped) MMA order,
+                         // 4 separate lo*hi accumulator, 8/16 skip A/B loads, 32 free-running issuer (timing only)
+  int a_stages, a_base;  // A-in-TMEM variant: ring of a_stages x 64 TMEM columns (hi 32 | lo 32) starting at a_base
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------
@@ -97,6 +100,18 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+// One elected lane of a converged warp.  With elect.sync the compiler knows a single lane is active and that the
+// surrounding values are warp-uniform, so tcgen05.mma / TMA operands stay in uniform registers; a plain
+// `lane == 0` test made it wrap every UTCHMMA in a 6x R2UR "waterfall" loop (~230 cycles per MMA, measured).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -108,6 +123,36 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
+}
+// A operand from tensor memory (lane = pixel row, one tf32 per 32-bit column), B from shared memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -139,12 +184,17 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
 }
 
 // ---- kernel -----------------------------------------------------------------------------
-template <int NMAX>
+// ATMEM = true: the A operand (activations) goes through tensor memory: the splitter warps read the TMA-landed
+// tile once (each thread its own pixel row), split in registers and tcgen05.st hi | lo into a TMEM ring; the
+// MMAs take A from TMEM and only B (weights) from shared memory.  Shared-memory traffic per K stage drops from
+// ~136 KB (TMA A+B, split read + 2 writes, MMA A hi+hi+lo and B reads) to ~72 KB (TMA A+B, split read, MMA B).
+template <int NMAX, bool ATMEM>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const demfi_conv_t& c = P.c;
-  const uint32_t stage_bytes = 2u * TC_A_BYTES + 2u * (uint32_t)P.nb_max * 128u;
+  constexpr uint32_t A_SLOTS = ATMEM ? 1u : 2u;  // shared-memory A tiles per stage (raw | lo)
+  const uint32_t stage_bytes = A_SLOTS * TC_A_BYTES + 2u * (uint32_t)P.nb_max * 128u;
   auto n_of = [&](int nb) { return min(P.nb_max, c.cout_pad - nb * P.nb_max); };
   const int S = P.stages;
   const uint32_t smem_base = smem_u32(smem);
@@ -154,9 +204,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   auto bar_empty = [&](int s) { return bars + 8u * (uint32_t)(2 * S + s); };
   auto bar_tfull = [&](int a) { return bars + 8u * (uint32_t)(3 * S + a); };
   auto bar_tempty = [&](int a) { return bars + 8u * (uint32_t)(3 * S + 2 + a); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (size_t)S * stage_bytes + 8 * (3 * S + 4));
+  auto bar_aempty = [&](int a) { return bars + 8u * (uint32_t)(3 * S + 4 + a); };  // ATMEM: TMEM A slot free
+  auto bar_aready = [&](int a) { return bars + 8u * (uint32_t)(S + a); };          // ATMEM: reuses the split[] slots
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (size_t)S * stage_bytes + 8 * (3 * S + 8));
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // provably warp-uniform
+  const int lane = threadIdx.x & 31;
   const int taps = c.KH * c.KW;
 
   if (threadIdx.x == 0) {
@@ -169,6 +222,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       mbar_init(bar_tfull(a), 1);
       mbar_init(bar_tempty(a), 128);
     }
+    for (int a = 0; a < 4; ++a) mbar_init(bar_aempty(a), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 9) {
@@ -183,7 +237,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 4) {
-    // ===== A splitter: hi = a & ~0x1fff (tf32 bits), lo = a - hi (exact in fp32) =====
+    // ===== A splitter =====
+    if constexpr (ATMEM) {
+      // thread m owns pixel row m of the tile: 128 contiguous bytes whose 16-byte groups sit at (g ^ (m & 7))
+      const int m = threadIdx.x;
+      const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32) << 16);
+      int stage = 0, sa = 0;
+      uint32_t phase = 0, aphase = 0;
+      for (int tile = blockIdx.x; tile < P.ntiles && !(P.diag & 32); tile += gridDim.x) {
+        for (int st_ = 0; st_ < P.stages_per_tile; ++st_) {
+          mbar_wait(bar_full(stage), phase);
+          const uint32_t row = smem_base + (uint32_t)stage * stage_bytes + (uint32_t)m * 128u;
+          uint32_t hi[32], lo[32];
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const uint4 v = lds128(row + (uint32_t)((g ^ (m & 7)) << 4));
+            hi[4 * g + 0] = v.x; hi[4 * g + 1] = v.y; hi[4 * g + 2] = v.z; hi[4 * g + 3] = v.w;
+          }
+          if (P.split == 3) {
+            const uint32_t rnd = P.mask_hi ? 0x1000u : 0u;  // tf32 round-to-nearest vs truncation
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const uint32_t h = (hi[j] + rnd) & 0xffffe000u;
+              lo[j] = __float_as_uint(__uint_as_float(hi[j]) - __uint_as_float(h));
+              hi[j] = h;
+            }
+          }
+          mbar_wait(bar_aempty(sa), aphase ^ 1);
+          tc_fence_after();
+          const uint32_t ta = tmem_base + lane_addr + (uint32_t)(P.a_base + sa * 64);
+          tmem_st32(ta, hi);
+          if (P.split == 3) tmem_st32(ta + 32u, lo);
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(bar_aready(sa));
+          if (++stage == S) { stage = 0; phase ^= 1; }
+          if (++sa == P.a_stages) { sa = 0; aphase ^= 1; }
+        }
+      }
+    } else {
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
@@ -215,6 +307,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             mbar_arrive(bar_split(stage));
             if (++stage == S) { stage = 0; phase ^= 1; }
           }
+    }
     }
   } else if (warp < 8) {
     // ===== epilogue: TMEM lane = pixel row of the tile; warp w owns lanes 32*(w%4).. =====
@@ -255,6 +348,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               if (P.split == 3) v += __uint_as_float(rc[j]);
               sum[col + j] = first ? v : sum[col + j] + v;
             }
+            if (P.split == 3 && (P.diag & 4)) {
+              tmem_ld16(taddr + (uint32_t)(2 * N + col), rc);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) sum[col + j] += __uint_as_float(rc[j]);
+            }
           }
         }
         tc_fence_before();
@@ -262,7 +360,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         first = false;
       }
-      if (valid) {
+      if (valid && !(P.diag & 1)) {
 #pragma unroll 1
         for (int sgi = 0; sgi < c.nseg; ++sgi) {
           if (c.seg[sgi].ch0 >= n0 + N || c.seg[sgi].ch0 + c.seg[sgi].nch <= n0) continue;
@@ -279,10 +377,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     }
   } else if (warp == 8) {
     // ===== TMA producer =====
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < P.ntiles && !(P.diag & 32); tile += gridDim.x) {
         int t = tile;
         const int nb = t % P.n_blocks;
         t /= P.n_blocks;
@@ -298,24 +396,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             for (int tap = 0; tap < taps; ++tap) {
               const int ky = tap / c.KW, kx = tap - ky * c.KW;
               mbar_wait(bar_empty(stage), phase ^ 1);
-              mbar_arrive_expect_tx(bar_full(stage), (uint32_t)TC_A_BYTES + 2u * b_bytes);
+              const bool do_a = !(P.diag & 8), do_b = !(P.diag & 16);  // timing diagnostics only (results are garbage)
+              mbar_arrive_expect_tx(bar_full(stage), (do_a ? (uint32_t)TC_A_BYTES : 0u) + (do_b ? 2u * b_bytes : 0u));
               const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
-              tma_load_4d(sa, &P.tmap[s], bar_full(stage), c0, tx0 + kx - c.pad_w, ty0 + ky - c.pad_h, n);
+              if (do_a) tma_load_4d(sa, &P.tmap[s], bar_full(stage), c0, tx0 + kx - c.pad_w, ty0 + ky - c.pad_h, n);
               // [Bhi rows n0..n0+N | Blo rows n0..n0+N] land contiguously: one 2N-row K-major tile
               const float* wsrc = c.wpack + ((size_t)chunk * taps + tap) * 2 * (size_t)c.cout_pad * TC_KC + (size_t)n0 * TC_KC;
-              bulk_load(sa + 2u * TC_A_BYTES, wsrc, b_bytes, bar_full(stage));
-              bulk_load(sa + 2u * TC_A_BYTES + b_bytes, wsrc + (size_t)c.cout_pad * TC_KC, b_bytes, bar_full(stage));
+              if (do_b) {
+                bulk_load(sa + A_SLOTS * TC_A_BYTES, wsrc, b_bytes, bar_full(stage));
+                bulk_load(sa + A_SLOTS * TC_A_BYTES + b_bytes, wsrc + (size_t)c.cout_pad * TC_KC, b_bytes, bar_full(stage));
+              }
               if (++stage == S) { stage = 0; phase ^= 1; }
             }
       }
     }
   } else {
-    // ===== MMA issuer (warp 9, one thread) =====
-    if (lane == 0) {
+    // ===== MMA issuer (warp 9: the whole warp walks the loop, one elected lane issues) =====
+    {
       // instruction descriptor: D=f32 (1<<4), A=B=tf32 (2<<7, 2<<10), both K-major, N>>3 at 17, M>>4 at 24
       const uint32_t idesc0 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BM >> 4) << 24);
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
+      int stage = 0, acc = 0, sa_ = 0;
+      uint32_t phase = 0, acc_phase = 0, aphase = 0;
       for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
         const int N = n_of(tile % P.n_blocks);
         const uint32_t idesc_n = idesc0 | ((uint32_t)(N >> 3) << 17);         // N columns
@@ -330,27 +431,72 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 d_tmem = tmem_base + (uint32_t)(acc * P.buf_stride);  // main [0,N), correction [N,2N)
                 accum = 0;
               }
-              mbar_wait(bar_split(stage), phase);
-              tc_fence_after();
               const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
-              const uint64_t a_hi = make_desc_sw128(sa), a_lo = make_desc_sw128(sa + TC_A_BYTES);
-              const uint64_t b_hi = make_desc_sw128(sa + 2u * TC_A_BYTES);
-#pragma unroll
-              for (int k = 0; k < TC_KC / 8; ++k) {
-                const uint64_t kk = (uint64_t)(k * 2);  // 32 bytes >> 4 per k-step of 8 tf32
-                if (P.split == 3) {
-                  umma_tf32(d_tmem, a_hi + kk, b_hi + kk, idesc_2n, accum);             // hi*hi | hi*lo
-                  umma_tf32(d_tmem + (uint32_t)N, a_lo + kk, b_hi + kk, idesc_n, 1);     // lo*hi -> correction
-                } else {
-                  umma_tf32(d_tmem, a_hi + kk, b_hi + kk, idesc_n, accum);
+              const uint64_t b_hi = make_desc_sw128(sa + A_SLOTS * TC_A_BYTES);
+              if constexpr (ATMEM) {
+                if (!(P.diag & 32)) {
+                  mbar_wait(bar_aready(sa_), aphase);
+                  mbar_wait(bar_full(stage), phase);  // already complete (the splitter waited on it): orders the B tile
+                  tc_fence_after();
                 }
+                const uint32_t ta = tmem_base + (uint32_t)(P.a_base + sa_ * 64);
+                const uint32_t d_lohi = d_tmem + (uint32_t)((P.diag & 4) ? 2 * N : N);
+                const uint32_t acc_lohi = (P.diag & 4) ? accum : 1u;
+                if (elect_one()) {
+                if (P.split == 3 && !(P.diag & 2)) {
+#pragma unroll
+                  for (int k = 0; k < TC_KC / 8; ++k)
+                    umma_tf32_ts(d_tmem, ta + (uint32_t)(k * 8), b_hi + (uint64_t)(k * 2), idesc_2n, k == 0 ? accum : 1u);
+#pragma unroll
+                  for (int k = 0; k < TC_KC / 8; ++k)
+                    umma_tf32_ts(d_lohi, ta + 32u + (uint32_t)(k * 8), b_hi + (uint64_t)(k * 2), idesc_n, k == 0 ? acc_lohi : 1u);
+                } else {
+                  uint32_t ac = accum;
+#pragma unroll
+                  for (int k = 0; k < TC_KC / 8; ++k) {
+                    const uint64_t kk = (uint64_t)(k * 2);
+                    if (P.split == 3) {
+                      umma_tf32_ts(d_tmem, ta + (uint32_t)(k * 8), b_hi + kk, idesc_2n, ac);  // hi*hi | hi*lo
+                      umma_tf32_ts(d_lohi, ta + 32u + (uint32_t)(k * 8), b_hi + kk, idesc_n, k == 0 ? acc_lohi : 1u);  // lo*hi
+                    } else {
+                      umma_tf32_ts(d_tmem, ta + (uint32_t)(k * 8), b_hi + kk, idesc_n, ac);
+                    }
+                    ac = 1;
+                  }
+                }
+                if (!(P.diag & 32) || (P.diag & 64)) umma_commit(bar_aempty(sa_));  // 64: keep the per-stage commits
+                }
+                __syncwarp();
+                accum = 1;
+                if (++sa_ == P.a_stages) { sa_ = 0; aphase ^= 1; }
+              } else {
+                mbar_wait(bar_split(stage), phase);
+                tc_fence_after();
+                const uint64_t a_hi = make_desc_sw128(sa), a_lo = make_desc_sw128(sa + TC_A_BYTES);
+                if (elect_one()) {
+                  uint32_t ac = accum;
+#pragma unroll
+                  for (int k = 0; k < TC_KC / 8; ++k) {
+                    const uint64_t kk = (uint64_t)(k * 2);  // 32 bytes >> 4 per k-step of 8 tf32
+                    if (P.split == 3) {
+                      umma_tf32(d_tmem, a_hi + kk, b_hi + kk, idesc_2n, ac);               // hi*hi | hi*lo
+                      umma_tf32(d_tmem + (uint32_t)N, a_lo + kk, b_hi + kk, idesc_n, 1);   // lo*hi -> correction
+                    } else {
+                      umma_tf32(d_tmem, a_hi + kk, b_hi + kk, idesc_n, ac);
+                    }
+                    ac = 1;
+                  }
+                }
+                __syncwarp();
                 accum = 1;
               }
-              umma_commit(bar_empty(stage));
+              if ((!(P.diag & 32) || (P.diag & 64)) && elect_one()) umma_commit(bar_empty(stage));
+              __syncwarp();
               if (++stage == S) { stage = 0; phase ^= 1; }
               ++done;
               if (++in_seg == P.flush || done == P.stages_per_tile) {
-                umma_commit(bar_tfull(acc));
+                if (elect_one()) umma_commit(bar_tfull(acc));
+                __syncwarp();
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 in_seg = 0;
               }
@@ -420,40 +566,68 @@ int launch_conv_tc(const demfi_conv_t& c, cudaStream_t st) {
   P.tiles_x = (c.W + TC_TW - 1) / TC_TW;
   P.tiles_y = (c.H + TC_TH - 1) / TC_TH;
   const long long nt = (long long)P.tiles_x * P.tiles_y * c.N;
-  P.nb_max = c.cout_pad < 128 ? c.cout_pad : 128;
+  const bool atmem = get_option("tc_a_tmem") != 0;
+  if (atmem) P.nb_max = c.cout_pad <= 96 ? c.cout_pad : 64;  // 2 accumulator pairs + the A ring must fit 512 TMEM columns
+  else P.nb_max = c.cout_pad < 128 ? c.cout_pad : 128;
   P.n_blocks = (c.cout_pad + P.nb_max - 1) / P.nb_max;
   DEMFI_REQUIRE(nt > 0 && nt * P.n_blocks < (1ll << 31), "conv_tc: bad tile count");
   P.ntiles = (int)nt * P.n_blocks;
-  const int stage_bytes = 2 * TC_A_BYTES + 2 * P.nb_max * 128;
+  const int stage_bytes = (atmem ? 1 : 2) * TC_A_BYTES + 2 * P.nb_max * 128;
   int stages = TC_SMEM_BUDGET / stage_bytes;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
-  if (get_option("tc_stages") >= 2 && get_option("tc_stages") < stages) stages = get_option("tc_stages");
+  {
+    int cap = get_option("tc_stages");
+    if (atmem && cap > 0 && cap < 4) cap = 4;  // the TMEM A ring variant is only validated with >= 4 smem stages
+    if (cap >= 2 && cap < stages) stages = cap;
+  }
   DEMFI_REQUIRE(stages >= 2, "conv_tc: not enough shared memory for two stages");
   P.stages = stages;
-  int buf_stride = 32;  // columns per accumulator pair (main + correction), power of two
-  while (buf_stride < 2 * P.nb_max) buf_stride *= 2;
-  P.buf_stride = buf_stride;
-  P.tmem_cols = 2 * buf_stride;
+  if (atmem && P.a_stages > stages) P.a_stages = stages;  // the aready[] barriers reuse the split[] slots
+  P.diag = get_option("tc_diag");
+  if (!atmem) P.diag &= (1 | 8 | 16);
+  if (P.diag & 32) P.diag |= 1;  // free-running MMA issuer: timing only
+  if ((P.diag & 4) && P.nb_max > 64) P.diag &= ~4;
+  if (atmem) {
+    P.buf_stride = ((P.diag & 4) ? 3 : 2) * P.nb_max;
+    P.a_base = 2 * P.buf_stride;
+    P.a_stages = (512 - P.a_base) / 64;
+    if (P.a_stages > 4) P.a_stages = 4;
+    P.tmem_cols = 512;
+  } else {
+    int buf_stride = 32;  // columns per accumulator pair (main + correction), power of two
+    while (buf_stride < 2 * P.nb_max) buf_stride *= 2;
+    P.buf_stride = buf_stride;
+    P.tmem_cols = 2 * buf_stride;
+  }
   P.mask_hi = get_option("tc_mask_hi");
   P.split = get_option("tc_split");
   P.stages_per_tile = 0;
   for (int s = 0; s < c.nsrc; ++s) P.stages_per_tile += ((c.src[s].C + TC_KC - 1) / TC_KC) * c.KH * c.KW;
   P.flush = get_option("tc_flush");
   if (P.flush <= 0 || P.flush > P.stages_per_tile) P.flush = P.stages_per_tile;
-  const int smem = stages * stage_bytes + 8 * (3 * stages + 4) + 16 + 1024;
+  const int smem = stages * stage_bytes + 8 * (3 * stages + 8) + 16 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    DEMFI_REQUIRE(e == cudaSuccess, "conv_tc: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
+    const void* fns[] = {(const void*)conv_tc_kernel<32, false>, (const void*)conv_tc_kernel<64, false>,
+                         (const void*)conv_tc_kernel<128, false>, (const void*)conv_tc_kernel<32, true>,
+                         (const void*)conv_tc_kernel<64, true>, (const void*)conv_tc_kernel<96, true>};
+    for (const void* f : fns) {
+      cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      DEMFI_REQUIRE(e == cudaSuccess, "conv_tc: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
+    }
     attr_set = true;
   }
   int grid = P.ntiles < num_sms() ? P.ntiles : num_sms();
   if (get_option("tc_grid") > 0 && get_option("tc_grid") < grid) grid = get_option("tc_grid");
-  if (P.nb_max <= 32) conv_tc_kernel<32><<<grid, TC_THREADS, smem, st>>>(P);
-  else if (P.nb_max <= 64) conv_tc_kernel<64><<<grid, TC_THREADS, smem, st>>>(P);
-  else conv_tc_kernel<128><<<grid, TC_THREADS, smem, st>>>(P);
+  if (atmem) {
+    if (P.nb_max <= 32) conv_tc_kernel<32, true><<<grid, TC_THREADS, smem, st>>>(P);
+    else if (P.nb_max <= 64) conv_tc_kernel<64, true><<<grid, TC_THREADS, smem, st>>>(P);
+    else conv_tc_kernel<96, true><<<grid, TC_THREADS, smem, st>>>(P);
+  } else {
+    if (P.nb_max <= 32) conv_tc_kernel<32, false><<<grid, TC_THREADS, smem, st>>>(P);
+    else if (P.nb_max <= 64) conv_tc_kernel<64, false><<<grid, TC_THREADS, smem, st>>>(P);
+    else conv_tc_kernel<128, false><<<grid, TC_THREADS, smem, st>>>(P);
+  }
   DEMFI_LAUNCH_CHECK("conv_tc");
   return 0;
 }

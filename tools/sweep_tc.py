@@ -9,22 +9,14 @@ H, W = 736, 1280
 shape = dict(n=1, h=H, w=W, srcC=[64], co=64, k=(3, 3))
 d, keep = make_conv(A.CONV_TC, **shape)
 macs = H * W * 64 * 64 * 9
-base = dict(tc_flush=0, tc_stages=0, tc_grid=0, tc_split=3, tc_mask_hi=0)
+base = dict(tc_flush=0, tc_stages=0, tc_grid=0, tc_split=3, tc_mask_hi=1, tc_a_tmem=1, tc_diag=0)
 def run(**kw):
     o = dict(base); o.update(kw)
     for k, v in o.items():
         A.set_option(k, v)
     ms = time_conv(d)
     print(json.dumps({**kw, "ms": round(ms, 3), "TFLOPs": round(2 * macs / ms / 1e9, 1)}), flush=True)
-for f in (0, 8, 4, 2, 1):
-    run(tc_flush=f)
-for s in (2, 3, 4):
-    run(tc_stages=s)
-for g in (148, 111, 74, 37):
-    run(tc_grid=g)
-run(tc_split=1)
-run(tc_split=1, tc_stages=2)
-run(tc_mask_hi=1)
-run(tc_flush=2, tc_grid=74)
+for args in sys.argv[1:]:
+    run(**{k: int(v) for k, v in (kv.split("=") for kv in args.split(","))})
 for k, v in base.items():
     A.set_option(k, v)
