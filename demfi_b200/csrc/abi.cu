@@ -21,9 +21,10 @@ void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_r
 
 static std::atomic<int> g_opt_mask_hi{1};
 static std::atomic<int> g_opt_split{3};
-static std::atomic<int> g_opt_flush{2};
+static std::atomic<int> g_opt_flush{8};
 static std::atomic<int> g_opt_atmem{1};   // A operand through tensor memory (1) or shared memory (0)
 static std::atomic<int> g_opt_diag{0};
+static std::atomic<int> g_opt_comp{270};
 static std::atomic<int> g_opt_stages{0};  // diagnostics: cap on pipeline stages (0 = as many as fit)
 static std::atomic<int> g_opt_grid{0};    // diagnostics: cap on persistent CTAs (0 = one per SM)
 int get_option(const char* name) {
@@ -32,6 +33,7 @@ int get_option(const char* name) {
   if (!strcmp(name, "tc_flush")) return g_opt_flush.load();
   if (!strcmp(name, "tc_stages")) return g_opt_stages.load();
   if (!strcmp(name, "tc_diag")) return g_opt_diag.load();
+  if (!strcmp(name, "tc_comp_milli")) return g_opt_comp.load();
   if (!strcmp(name, "tc_a_tmem")) return g_opt_atmem.load();
   if (!strcmp(name, "tc_grid")) return g_opt_grid.load();
   return -1;
@@ -92,6 +94,7 @@ int demfi_set_option(const char* name, int32_t value) {
   if (!strcmp(name, "tc_flush")) { g_opt_flush.store(value < 0 ? 0 : value); return 0; }
   if (!strcmp(name, "tc_stages")) { g_opt_stages.store(value < 0 ? 0 : value); return 0; }
   if (!strcmp(name, "tc_diag")) { g_opt_diag.store(value); return 0; }
+  if (!strcmp(name, "tc_comp_milli")) { g_opt_comp.store(value); return 0; }
   if (!strcmp(name, "tc_a_tmem")) { g_opt_atmem.store(value ? 1 : 0); return 0; }
   if (!strcmp(name, "tc_grid")) { g_opt_grid.store(value < 0 ? 0 : value); return 0; }
   set_error("set_option: unknown option '%s'", name);

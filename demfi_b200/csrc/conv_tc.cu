@@ -48,6 +48,7 @@ struct TcParams {
   int stages_per_tile;
   int diag;              // diagnostics bitmask (tc_diag): 1 no global stores, 2 interleaved (not grouped) MMA order,
                          // 4 separate lo*hi accumulator, 8/16 skip A/B loads, 32 free-running issuer (timing only)
+  float comp;            // per-MMA gain correction of the truncating tensor-core accumulation (0 = off)
   int a_stages, a_base;  // A-in-TMEM variant: ring of a_stages x 64 TMEM columns (hi 32 | lo 32) starting at a_base
 };
 
@@ -332,6 +333,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       float sum[NMAX];
       bool first = true;
       for (int done = 0; done < P.stages_per_tile; done += P.flush) {
+        const float gain = 1.0f + P.comp * (float)(4 * min(P.flush, P.stages_per_tile - done));
         mbar_wait(bar_tfull(acc), acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * P.buf_stride);
@@ -344,7 +346,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              float v = __uint_as_float(r[j]);
+              float v = __uint_as_float(r[j]) * gain;
               if (P.split == 3) v += __uint_as_float(rc[j]);
               sum[col + j] = first ? v : sum[col + j] + v;
             }
@@ -584,6 +586,7 @@ int launch_conv_tc(const demfi_conv_t& c, cudaStream_t st) {
   P.stages = stages;
   if (atmem && P.a_stages > stages) P.a_stages = stages;  // the aready[] barriers reuse the split[] slots
   P.diag = get_option("tc_diag");
+  P.comp = (float)get_option("tc_comp_milli") * 1e-3f * 5.9604645e-8f;  // milli-units of 2^-24 per MMA
   if (!atmem) P.diag &= (1 | 8 | 16);
   if (P.diag & 32) P.diag |= 1;  // free-running MMA issuer: timing only
   if ((P.diag & 4) && P.nb_max > 64) P.diag &= ~4;

@@ -17,18 +17,21 @@ for case in ("c32x32_n1_noise", "c64x96_n3", "c256x256_n1"):
     gold = dict(np.load(os.path.join(ROOT, "tests/golden", case + ".npz")))
     x = synth.make_frames(cfg["h"], cfg["w"], 0, cfg["batch"], cfg["smooth"]).to(dev)
     t = torch.tensor(cfg["t"]).reshape(-1, 1).to(dev)
-    for kind, flush, mh in (("ffma", 0, 0), ("tc", 0, 0), ("tc", 4, 0), ("tc", 2, 0), ("tc", 1, 0), ("tc", 0, 1), ("tc", 4, 1), ("tc", 2, 1), ("tc", 1, 1)):
+    for kind, flush, mh, comp in (("ffma", 0, 1, 0), ("tc", 0, 1, 0), ("tc", 2, 1, 0), ("tc", 0, 1, 270), ("tc", 16, 1, 270), ("tc", 8, 1, 270),
+                                  ("tc", 4, 1, 270), ("tc", 2, 1, 270), ("tc", 2, 1, 300), ("tc", 1, 1, 300), ("tc", 8, 1, 240)):
         A.set_option("tc_flush", flush)
         A.set_option("tc_mask_hi", mh)
+        A.set_option("tc_comp_milli", comp)
         eng = Engine(sd, cfg["batch"], cfg["h"], cfg["w"], dev, conv_kind=kind)
         got = O.flatten_outputs(eng.forward(x, t, cfg["n"]))
         torch.cuda.synchronize()
         errs = {k: float((got[k].cpu() - torch.from_numpy(g)).abs().max()) for k, g in gold.items() if k in got}
         fr = {k: float(((got[k].cpu() - torch.from_numpy(g)).abs() > 5e-4).float().mean()) for k, g in gold.items() if k in got}
-        print(json.dumps({"case": case, "kind": kind, "flush": flush, "rn_split": mh, "worst": max(errs.values()),
+        print(json.dumps({"case": case, "kind": kind, "flush": flush, "rn_split": mh, "comp": comp, "worst": max(errs.values()),
                           "worst_S": max(v for k, v in errs.items() if k.startswith("S")),
                           "worst_flow": max(v for k, v in errs.items() if k.startswith("flow")),
                           "frac_gt_5e-4": max(fr.values())}), flush=True)
         del eng
-A.set_option("tc_flush", 2)
-A.set_option("tc_mask_hi", 0)
+A.set_option("tc_flush", 8)
+A.set_option("tc_mask_hi", 1)
+A.set_option("tc_comp_milli", 270)
