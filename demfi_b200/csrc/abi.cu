@@ -21,7 +21,7 @@ void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_r
 
 static std::atomic<int> g_opt_mask_hi{1};
 static std::atomic<int> g_opt_split{3};
-static std::atomic<int> g_opt_flush{8};
+static std::atomic<int> g_opt_flush{10};
 static std::atomic<int> g_opt_atmem{1};   // A operand through tensor memory (1) or shared memory (0)
 static std::atomic<int> g_opt_diag{0};
 static std::atomic<int> g_opt_comp{270};

@@ -378,131 +378,127 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       }
     }
   } else if (warp == 8) {
-    // ===== TMA producer =====
+    // ===== TMA producer (one elected lane).  Per-stage work is kept minimal: no divisions, incremental pointers. =====
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      const bool do_a = !(P.diag & 8), do_b = !(P.diag & 16);  // timing diagnostics only (results are garbage)
+      const size_t w_step = 2 * (size_t)c.cout_pad * TC_KC;   // floats per (chunk, tap) in the packed weights
       for (int tile = blockIdx.x; tile < P.ntiles && !(P.diag & 32); tile += gridDim.x) {
         int t = tile;
         const int nb = t % P.n_blocks;
         t /= P.n_blocks;
-        const int tx0 = (t % P.tiles_x) * TC_TW;
+        const int tx0 = (t % P.tiles_x) * TC_TW - c.pad_w;
         t /= P.tiles_x;
-        const int ty0 = (t % P.tiles_y) * TC_TH;
+        const int ty0 = (t % P.tiles_y) * TC_TH - c.pad_h;
         const int n = t / P.tiles_y;
-        const int N = n_of(nb), n0 = nb * P.nb_max;
+        const int N = n_of(nb);
         const uint32_t b_bytes = (uint32_t)N * 128u;
-        int chunk = 0;
-        for (int s = 0; s < c.nsrc; ++s)
-          for (int c0 = 0; c0 < c.src[s].C; c0 += TC_KC, ++chunk)
-            for (int tap = 0; tap < taps; ++tap) {
-              const int ky = tap / c.KW, kx = tap - ky * c.KW;
-              mbar_wait(bar_empty(stage), phase ^ 1);
-              const bool do_a = !(P.diag & 8), do_b = !(P.diag & 16);  // timing diagnostics only (results are garbage)
-              mbar_arrive_expect_tx(bar_full(stage), (do_a ? (uint32_t)TC_A_BYTES : 0u) + (do_b ? 2u * b_bytes : 0u));
-              const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
-              if (do_a) tma_load_4d(sa, &P.tmap[s], bar_full(stage), c0, tx0 + kx - c.pad_w, ty0 + ky - c.pad_h, n);
-              // [Bhi rows n0..n0+N | Blo rows n0..n0+N] land contiguously: one 2N-row K-major tile
-              const float* wsrc = c.wpack + ((size_t)chunk * taps + tap) * 2 * (size_t)c.cout_pad * TC_KC + (size_t)n0 * TC_KC;
-              if (do_b) {
-                bulk_load(sa + A_SLOTS * TC_A_BYTES, wsrc, b_bytes, bar_full(stage));
-                bulk_load(sa + A_SLOTS * TC_A_BYTES + b_bytes, wsrc + (size_t)c.cout_pad * TC_KC, b_bytes, bar_full(stage));
+        const uint32_t tx_bytes = (do_a ? (uint32_t)TC_A_BYTES : 0u) + (do_b ? 2u * b_bytes : 0u);
+        const float* wsrc = c.wpack + (size_t)(nb * P.nb_max) * TC_KC;
+        const size_t lo_off = (size_t)c.cout_pad * TC_KC;
+        for (int s = 0; s < c.nsrc; ++s) {
+          const CUtensorMap* map = &P.tmap[s];
+          const int Cs = c.src[s].C;
+          for (int c0 = 0; c0 < Cs; c0 += TC_KC)
+            for (int ky = 0; ky < c.KH; ++ky)
+              for (int kx = 0; kx < c.KW; ++kx) {
+                mbar_wait(bar_empty(stage), phase ^ 1);
+                const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
+                const uint32_t fb = bar_full(stage);
+                mbar_arrive_expect_tx(fb, tx_bytes);
+                if (do_a) tma_load_4d(sa, map, fb, c0, tx0 + kx, ty0 + ky, n);
+                if (do_b) {  // [Bhi rows | Blo rows] land contiguously: one 2N-row K-major tile
+                  bulk_load(sa + A_SLOTS * TC_A_BYTES, wsrc, b_bytes, fb);
+                  bulk_load(sa + A_SLOTS * TC_A_BYTES + b_bytes, wsrc + lo_off, b_bytes, fb);
+                }
+                wsrc += w_step;
+                if (++stage == S) { stage = 0; phase ^= 1; }
               }
-              if (++stage == S) { stage = 0; phase ^= 1; }
-            }
+        }
       }
     }
   } else {
-    // ===== MMA issuer (warp 9: the whole warp walks the loop, one elected lane issues) =====
-    {
-      // instruction descriptor: D=f32 (1<<4), A=B=tf32 (2<<7, 2<<10), both K-major, N>>3 at 17, M>>4 at 24
-      const uint32_t idesc0 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BM >> 4) << 24);
-      int stage = 0, acc = 0, sa_ = 0;
-      uint32_t phase = 0, acc_phase = 0, aphase = 0;
-      for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
-        const int N = n_of(tile % P.n_blocks);
-        const uint32_t idesc_n = idesc0 | ((uint32_t)(N >> 3) << 17);         // N columns
-        const uint32_t idesc_2n = idesc0 | ((uint32_t)((2 * N) >> 3) << 17);  // [hi;lo] weight tile: 2N columns
-        int in_seg = 0, done = 0;
-        uint32_t d_tmem = 0, accum = 0;
-        for (int s = 0; s < c.nsrc; ++s)
-          for (int c0 = 0; c0 < c.src[s].C; c0 += TC_KC)
-            for (int tap = 0; tap < taps; ++tap) {
-              if (in_seg == 0) {  // new accumulation segment: fresh accumulator pair
-                mbar_wait(bar_tempty(acc), acc_phase ^ 1);
-                d_tmem = tmem_base + (uint32_t)(acc * P.buf_stride);  // main [0,N), correction [N,2N)
-                accum = 0;
-              }
-              const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
-              const uint64_t b_hi = make_desc_sw128(sa + A_SLOTS * TC_A_BYTES);
-              if constexpr (ATMEM) {
-                if (!(P.diag & 32)) {
-                  mbar_wait(bar_aready(sa_), aphase);
-                  mbar_wait(bar_full(stage), phase);  // already complete (the splitter waited on it): orders the B tile
-                  tc_fence_after();
-                }
-                const uint32_t ta = tmem_base + (uint32_t)(P.a_base + sa_ * 64);
-                const uint32_t d_lohi = d_tmem + (uint32_t)((P.diag & 4) ? 2 * N : N);
-                const uint32_t acc_lohi = (P.diag & 4) ? accum : 1u;
-                if (elect_one()) {
-                if (P.split == 3 && !(P.diag & 2)) {
-#pragma unroll
-                  for (int k = 0; k < TC_KC / 8; ++k)
-                    umma_tf32_ts(d_tmem, ta + (uint32_t)(k * 8), b_hi + (uint64_t)(k * 2), idesc_2n, k == 0 ? accum : 1u);
-#pragma unroll
-                  for (int k = 0; k < TC_KC / 8; ++k)
-                    umma_tf32_ts(d_lohi, ta + 32u + (uint32_t)(k * 8), b_hi + (uint64_t)(k * 2), idesc_n, k == 0 ? acc_lohi : 1u);
-                } else {
-                  uint32_t ac = accum;
-#pragma unroll
-                  for (int k = 0; k < TC_KC / 8; ++k) {
-                    const uint64_t kk = (uint64_t)(k * 2);
-                    if (P.split == 3) {
-                      umma_tf32_ts(d_tmem, ta + (uint32_t)(k * 8), b_hi + kk, idesc_2n, ac);  // hi*hi | hi*lo
-                      umma_tf32_ts(d_lohi, ta + 32u + (uint32_t)(k * 8), b_hi + kk, idesc_n, k == 0 ? acc_lohi : 1u);  // lo*hi
-                    } else {
-                      umma_tf32_ts(d_tmem, ta + (uint32_t)(k * 8), b_hi + kk, idesc_n, ac);
-                    }
-                    ac = 1;
-                  }
-                }
-                if (!(P.diag & 32) || (P.diag & 64)) umma_commit(bar_aempty(sa_));  // 64: keep the per-stage commits
-                }
-                __syncwarp();
-                accum = 1;
-                if (++sa_ == P.a_stages) { sa_ = 0; aphase ^= 1; }
-              } else {
-                mbar_wait(bar_split(stage), phase);
-                tc_fence_after();
-                const uint64_t a_hi = make_desc_sw128(sa), a_lo = make_desc_sw128(sa + TC_A_BYTES);
-                if (elect_one()) {
-                  uint32_t ac = accum;
-#pragma unroll
-                  for (int k = 0; k < TC_KC / 8; ++k) {
-                    const uint64_t kk = (uint64_t)(k * 2);  // 32 bytes >> 4 per k-step of 8 tf32
-                    if (P.split == 3) {
-                      umma_tf32(d_tmem, a_hi + kk, b_hi + kk, idesc_2n, ac);               // hi*hi | hi*lo
-                      umma_tf32(d_tmem + (uint32_t)N, a_lo + kk, b_hi + kk, idesc_n, 1);   // lo*hi -> correction
-                    } else {
-                      umma_tf32(d_tmem, a_hi + kk, b_hi + kk, idesc_n, ac);
-                    }
-                    ac = 1;
-                  }
-                }
-                __syncwarp();
-                accum = 1;
-              }
-              if ((!(P.diag & 32) || (P.diag & 64)) && elect_one()) umma_commit(bar_empty(stage));
-              __syncwarp();
-              if (++stage == S) { stage = 0; phase ^= 1; }
-              ++done;
-              if (++in_seg == P.flush || done == P.stages_per_tile) {
-                if (elect_one()) umma_commit(bar_tfull(acc));
-                __syncwarp();
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-                in_seg = 0;
-              }
+    // ===== MMA issuer (warp 9: the whole warp walks the flattened stage loop, one elected lane issues).
+    // The issuing warp's own instruction stream was the bottleneck (ncu + free-running experiments), so the
+    // per-stage code is a barrier probe, a handful of uniform adds and the tcgen05 instructions. =====
+    const uint32_t idesc0 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BM >> 4) << 24);  // D=f32, A=B=tf32, K-major, M=128
+    const uint64_t bdesc0 = make_desc_sw128(smem_base + A_SLOTS * TC_A_BYTES);  // B tile of stage 0
+    const uint64_t adesc0 = make_desc_sw128(smem_base);                         // SS: raw/hi A tile of stage 0
+    const uint64_t dstep = (uint64_t)(stage_bytes >> 4);                        // descriptor start-address step per stage
+    const bool free_run = (P.diag & 32) != 0, keep_commits = (P.diag & 64) != 0;
+    uint32_t stage = 0, phase = 0, sa_ = 0, aphase = 0, acc = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+      const int N = n_of(tile % P.n_blocks);
+      const uint32_t idesc_n = idesc0 | ((uint32_t)(N >> 3) << 17);         // N columns
+      const uint32_t idesc_2n = idesc0 | ((uint32_t)((2 * N) >> 3) << 17);  // [hi;lo] weight tile: 2N columns
+      for (int done = 0; done < P.stages_per_tile; done += P.flush) {
+        const int seg_len = min(P.flush, P.stages_per_tile - done);
+        mbar_wait(bar_tempty(acc), acc_phase ^ 1);  // fresh accumulator pair for this segment
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * (uint32_t)P.buf_stride;  // main [0,N), correction [N,2N)
+        const uint32_t d_lohi = d_tmem + (uint32_t)((P.diag & 4) ? 2 * N : N);
+        for (int i = 0; i < seg_len; ++i) {
+          const uint64_t b_hi = bdesc0 + dstep * stage;
+          const uint32_t first = (i == 0) ? 0u : 1u;
+          if constexpr (ATMEM) {
+            if (!free_run) {
+              mbar_wait(bar_aready(sa_), aphase);  // splitter stored A (it waited on full[stage]: B has landed too)
+              tc_fence_after();
             }
+            const uint32_t ta = tmem_base + (uint32_t)P.a_base + sa_ * 64u;
+            if (elect_one()) {
+              if (P.split == 3 && !(P.diag & 2)) {  // grouped: 4x (Ahi x [Bhi;Blo]) then 4x (Alo x Bhi)
+#pragma unroll
+                for (int k = 0; k < TC_KC / 8; ++k)
+                  umma_tf32_ts(d_tmem, ta + (uint32_t)(k * 8), b_hi + (uint64_t)(k * 2), idesc_2n, k == 0 ? first : 1u);
+#pragma unroll
+                for (int k = 0; k < TC_KC / 8; ++k)
+                  umma_tf32_ts(d_lohi, ta + 32u + (uint32_t)(k * 8), b_hi + (uint64_t)(k * 2), idesc_n,
+                               (k == 0 && (P.diag & 4)) ? first : 1u);
+              } else {
+#pragma unroll
+                for (int k = 0; k < TC_KC / 8; ++k) {
+                  const uint64_t kk = (uint64_t)(k * 2);
+                  if (P.split == 3) {
+                    umma_tf32_ts(d_tmem, ta + (uint32_t)(k * 8), b_hi + kk, idesc_2n, k == 0 ? first : 1u);
+                    umma_tf32_ts(d_lohi, ta + 32u + (uint32_t)(k * 8), b_hi + kk, idesc_n, (k == 0 && (P.diag & 4)) ? first : 1u);
+                  } else {
+                    umma_tf32_ts(d_tmem, ta + (uint32_t)(k * 8), b_hi + kk, idesc_n, k == 0 ? first : 1u);
+                  }
+                }
+              }
+              if (!free_run || keep_commits) {
+                umma_commit(bar_aempty(sa_));
+                umma_commit(bar_empty(stage));
+              }
+              if (i == seg_len - 1) umma_commit(bar_tfull(acc));
+            }
+            __syncwarp();
+            if (++sa_ == (uint32_t)P.a_stages) { sa_ = 0; aphase ^= 1; }
+          } else {
+            mbar_wait(bar_split(stage), phase);
+            tc_fence_after();
+            const uint64_t a_hi = adesc0 + dstep * stage, a_lo = a_hi + (uint64_t)(TC_A_BYTES >> 4);
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < TC_KC / 8; ++k) {
+                const uint64_t kk = (uint64_t)(k * 2);  // 32 bytes >> 4 per k-step of 8 tf32
+                if (P.split == 3) {
+                  umma_tf32(d_tmem, a_hi + kk, b_hi + kk, idesc_2n, k == 0 ? first : 1u);  // hi*hi | hi*lo
+                  umma_tf32(d_tmem + (uint32_t)N, a_lo + kk, b_hi + kk, idesc_n, 1);       // lo*hi -> correction
+                } else {
+                  umma_tf32(d_tmem, a_hi + kk, b_hi + kk, idesc_n, k == 0 ? first : 1u);
+                }
+              }
+              umma_commit(bar_empty(stage));
+              if (i == seg_len - 1) umma_commit(bar_tfull(acc));
+            }
+            __syncwarp();
+          }
+          if (++stage == (uint32_t)S) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   }
@@ -608,6 +604,10 @@ int launch_conv_tc(const demfi_conv_t& c, cudaStream_t st) {
   for (int s = 0; s < c.nsrc; ++s) P.stages_per_tile += ((c.src[s].C + TC_KC - 1) / TC_KC) * c.KH * c.KW;
   P.flush = get_option("tc_flush");
   if (P.flush <= 0 || P.flush > P.stages_per_tile) P.flush = P.stages_per_tile;
+  {  // balanced segments: e.g. 18 stages with tc_flush = 8..10 -> 2 x 9 instead of 8 + 8 + 2 (one drain fewer)
+    const int nseg = (P.stages_per_tile + P.flush - 1) / P.flush;
+    P.flush = (P.stages_per_tile + nseg - 1) / nseg;
+  }
   const int smem = stages * stage_bytes + 8 * (3 * stages + 8) + 16 + 1024;
   static bool attr_set = false;
   if (!attr_set) {

@@ -166,7 +166,7 @@ uint64_t demfi_launch_count(void);
  * fp32 tile is fed and the tensor core's own truncation is relied on -- measured identical operand
  * behaviour on B200, slightly more biased residual), "tc_split" (3: 3xTF32, fp32-parity mode, default; 1: single-pass TF32, NOT parity
  * grade, for measurement only), "tc_flush" (K stages of 32 channels accumulated inside the tensor core
- * before the partial sum is drained and added in fp32 round-to-nearest; default 8, 0 = whole K), "tc_comp_milli" (gain correction of the truncating tensor-core accumulation in
+ * before the partial sum is drained and added in fp32 round-to-nearest; default 10 (segments are balanced: 18 stages -> 2 x 9), 0 = whole K), "tc_comp_milli" (gain correction of the truncating tensor-core accumulation in
  * units of 1e-3 * 2^-24 per chained MMA; default 270 = the measured -0.27*2^-24 bias per MMA on B200),
  * "tc_a_tmem" (1: activation operand through tensor memory, 0: through shared memory), "tc_stages" /
  * "tc_grid" (caps on pipeline depth / persistent CTAs, 0 = auto), "tc_diag" (timing diagnostics bitmask).

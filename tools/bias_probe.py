@@ -36,4 +36,4 @@ for relu_in in (False, True):
         print(json.dumps({"conv": name, "relu_in": relu_in, "flush": flush, "comp_milli": comp, "mmas_per_chain": nm, "slope": slope,
                           "slope_per_mma_in_2^-24": slope / nm * 2 ** 24, "max_abs": float(err.abs().max()),
                           "rms_after_removing_slope": float((err - slope * wv).pow(2).mean().sqrt())}), flush=True)
-A.set_option("tc_flush", 8); A.set_option("tc_comp_milli", 270)
+A.set_option("tc_flush", 10); A.set_option("tc_comp_milli", 270)

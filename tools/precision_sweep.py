@@ -32,6 +32,6 @@ for case in ("c32x32_n1_noise", "c64x96_n3", "c256x256_n1"):
                           "worst_flow": max(v for k, v in errs.items() if k.startswith("flow")),
                           "frac_gt_5e-4": max(fr.values())}), flush=True)
         del eng
-A.set_option("tc_flush", 8)
+A.set_option("tc_flush", 10)
 A.set_option("tc_mask_hi", 1)
 A.set_option("tc_comp_milli", 270)

@@ -9,7 +9,7 @@ H, W = 736, 1280
 shape = dict(n=1, h=H, w=W, srcC=[64], co=64, k=(3, 3))
 d, keep = make_conv(A.CONV_TC, **shape)
 macs = H * W * 64 * 64 * 9
-base = dict(tc_flush=8, tc_stages=0, tc_grid=0, tc_split=3, tc_mask_hi=1, tc_a_tmem=1, tc_diag=0, tc_comp_milli=270)
+base = dict(tc_flush=10, tc_stages=0, tc_grid=0, tc_split=3, tc_mask_hi=1, tc_a_tmem=1, tc_diag=0, tc_comp_milli=270)
 def run(**kw):
     o = dict(base); o.update(kw)
     for k, v in o.items():
