@@ -55,6 +55,7 @@ SYMBOLS = {
     "demfi_fgac_sample": (i32, [vp, i32, vp, i32, i32, i32, i32, i32, vp, i32, vp]),
     "demfi_fgac_blend": (i32, [vp, i32, vp, i32, vp, i32, C.c_int64, i32, vp, i32, vp]),
     "demfi_copy_channels": (i32, [vp, i32, vp, i32, i32, C.c_int64, i32, vp]),
+    "demfi_upsample2x": (i32, [vp, i32, i32, i32, i32, i32, vp, i32, vp]),
     "demfi_export_nchw": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, vp]),
     "demfi_import_nchw": (i32, [vp, i32, i32, i32, i32, vp, i32, vp]),
     "demfi_launch_count": (C.c_uint64, []),

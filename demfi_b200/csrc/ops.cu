@@ -282,6 +282,22 @@ import_nchw_kernel(const float* __restrict__ src, int B, int H, int W, int C, fl
   dst[(n * plane + p) * dst_ld + c] = __ldg(src + (n * C + c) * plane + p);
 }
 
+// nearest-neighbour x2 up-sampling (nn.UpsamplingNearest2d, DeMFInet.py:573,592,597,601), 128-bit per thread
+__global__ void __launch_bounds__(256)
+upsample2x_kernel(const float* __restrict__ src, int src_ld, int B, int Hs, int Ws, int C4, float* __restrict__ dst,
+                  int dst_ld) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int W = 2 * Ws, H = 2 * Hs;
+  if (i >= (long long)B * H * W * C4) return;
+  const int c4 = (int)(i % C4);
+  const long long pix = i / C4;
+  const int x = (int)(pix % W);
+  const int y = (int)((pix / W) % H);
+  const long long n = pix / ((long long)W * H);
+  const float4 v = __ldg((const float4*)(src + ((n * Hs + (y >> 1)) * Ws + (x >> 1)) * src_ld) + c4);
+  *((float4*)(dst + pix * dst_ld) + c4) = v;
+}
+
 static inline unsigned blocks_for(long long n, int per = 256) { return (unsigned)((n + per - 1) / per); }
 
 }  // namespace demfi
@@ -370,6 +386,16 @@ int demfi_copy_channels(const float* src, int32_t src_ld, float* dst, int32_t ds
   DEMFI_REQUIRE(nch > 0 && npix > 0, "copy_channels: bad shape");
   copy_channels_kernel<<<blocks_for(npix * nch), 256, 0, (cudaStream_t)stream>>>(src, src_ld, dst, dst_ld, nch, npix, act);
   DEMFI_LAUNCH_CHECK("copy_channels");
+  return 0;
+}
+
+int demfi_upsample2x(const float* src, int32_t src_ld, int32_t B, int32_t Hs, int32_t Ws, int32_t C, float* dst,
+                     int32_t dst_ld, void* stream) {
+  if (check_device()) return 3;
+  DEMFI_REQUIRE(B > 0 && Hs > 0 && Ws > 0 && C > 0 && C % 4 == 0 && src_ld % 4 == 0 && dst_ld % 4 == 0 &&
+                    ((uintptr_t)src % 16) == 0 && ((uintptr_t)dst % 16) == 0, "upsample2x: bad arguments");
+  upsample2x_kernel<<<blocks_for((long long)B * Hs * Ws * C), 256, 0, (cudaStream_t)stream>>>(src, src_ld, B, Hs, Ws, C / 4, dst, dst_ld);
+  DEMFI_LAUNCH_CHECK("upsample2x");
   return 0;
 }
 

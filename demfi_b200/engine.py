@@ -115,6 +115,9 @@ class Engine:
         v["DE0"] = self._buf("DE0", B, h // 4, w // 4, 256)
         v["DE1"] = self._buf("DE1", B, h // 2, w // 2, 128)
         v["DE2"] = self._buf("DE2", B, h, w, 64)
+        v["UP0"] = self._buf("UP0", B, h // 2, w // 2, 256)  # nearest x2 of the UNet decoder outputs
+        v["UP1"] = self._buf("UP1", B, h, w, 128)
+        v["UP2"] = self._buf("UP2", B, H, W, 64)
         v["DECIN"] = self._buf("DECIN", 3 * B, H, W, 64)
         v["SP"] = self._buf("SP", 3 * B, H, W, 4)
         v["DL0"] = self._buf("DL0", B, H, W, 8)
@@ -299,11 +302,15 @@ class Engine:
         ops.append(self.conv(p + "enc2", [v["EN1"]], (h // 2, w // 2), B, [full(v["EN2"], 128, relu)], k=(4, 4), stride=2, pad=(1, 1)))
         ops.append(self.conv(p + "enc3", [v["EN2"]], (h // 4, w // 4), B, [full(v["EN3"], 256, relu)], k=(4, 4), stride=2, pad=(1, 1)))
         ops.append(self.conv(p + "dec0", [v["EN3"]], (h // 4, w // 4), B, [full(v["DE0"], 256, relu)]))
-        ops.append(self.conv(p + "dec1", [(v["DE0"], 1), (v["EN2"], 0)], (h // 2, w // 2), B, [full(v["DE1"], 128, relu)]))
-        ops.append(self.conv(p + "dec2", [(v["DE1"], 1), (v["EN1"], 0)], (h, w), B, [full(v["DE2"], 64, relu)]))
+        # decoder inputs are materialised at the finer resolution so that dec1-3 run on the tensor-core kernel
+        ops.append(("upsample", v["DE0"], v["UP0"]))
+        ops.append(self.conv(p + "dec1", [v["UP0"], v["EN2"]], (h // 2, w // 2), B, [full(v["DE1"], 128, relu)]))
+        ops.append(("upsample", v["DE1"], v["UP1"]))
+        ops.append(self.conv(p + "dec2", [v["UP1"], v["EN1"]], (h, w), B, [full(v["DE2"], 64, relu)]))
+        ops.append(("upsample", v["DE2"], v["UP2"]))
         DECIN, DL0 = v["DECIN"], v["DL0"]
         dec3_out = [5 + c for c in range(64)] + [69 + c for c in range(64)] + [0, 1, 2, 3, 4] + [-1] * 11
-        ops.append(self.conv(p + "dec3", [(v["DE2"], 1)], (H, W), B,
+        ops.append(self.conv(p + "dec3", [v["UP2"]], (H, W), B,
                              [full(DECIN.frames(0, B), 64, tanh, AGG1.ch(0, 64), ch0=0),
                               full(DECIN.frames(B, B), 64, tanh, AGG1.ch(64, 64), ch0=64),
                               full(DL0, 8, none, AGG1.ch(192, 8), ch0=128)], out_map=dec3_out))
@@ -427,6 +434,9 @@ class Engine:
                 A.check(lib.demfi_copy_channels(s.ptr, s.ld, d.ptr, d.ld, s.C, s.npix(), act, st), "copy_channels")
             elif k == "zero":
                 op[1].t.zero_()
+            elif k == "upsample":
+                sv, dv = op[1], op[2]
+                A.check(lib.demfi_upsample2x(sv.ptr, sv.ld, sv.N, sv.H, sv.W, sv.C, dv.ptr, dv.ld, st), "upsample2x")
             elif k == "cfr_splat":
                 A.check(lib.demfi_cfr_splat(op[1].ptr, op[1].ld, self.t_dev.data_ptr(), B, H, W, op[2].ptr, st), "cfr_splat")
             elif k == "cfr_finalize":

@@ -151,6 +151,10 @@ int demfi_fgac_blend(const float* w, int32_t w_ld, const float* src, int32_t src
  * Replaces the small torch.cat assemblies (DeMFInet.py:117-123, 151-155). act: NONE or SIGMOID. */
 int demfi_copy_channels(const float* src, int32_t src_ld, float* dst, int32_t dst_ld, int32_t nch, int64_t npix,
                         int32_t act, void* stream);
+/* nn.UpsamplingNearest2d(scale_factor=2) (DeMFInet.py:573): src [B,Hs,Ws,C of src_ld] -> dst [B,2Hs,2Ws,C of dst_ld].
+ * Materialises the UNet decoder inputs so that dec1-3 run on the tensor-core conv. */
+int demfi_upsample2x(const float* src, int32_t src_ld, int32_t B, int32_t Hs, int32_t Ws, int32_t C, float* dst,
+                     int32_t dst_ld, void* stream);
 /* NHWC slice -> NCHW tensor [B,C,H,W] (the tensors DeMFInet.forward returns, DeMFInet.py:170-179). */
 int demfi_export_nchw(const float* src, int32_t src_ld, int32_t B, int32_t H, int32_t W, int32_t C, int32_t act,
                       float* dst, void* stream);

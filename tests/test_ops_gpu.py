@@ -145,3 +145,15 @@ def test_errors_are_loud():
     assert rc != 0 and b"even" in lib.demfi_last_error()
     with pytest.raises(A.DemfiError):
         A.set_option("no_such_option", 1)
+
+
+def test_upsample2x():
+    n, h, w, C = 2, 6, 10, 128
+    src = rnd(n, C, h, w, seed=13)
+    sb, _ = nhwc(src, 132)
+    dst = torch.zeros(n, 2 * h, 2 * w, 160, device=DEV)
+    A.check(A.lib().demfi_upsample2x(sb.data_ptr(), 132, n, h, w, C, dst.data_ptr() + 4 * 16, 160, stream()), "upsample2x")
+    torch.cuda.synchronize()
+    want = src.repeat_interleave(2, 2).repeat_interleave(2, 3)
+    assert torch.equal(dst[..., 16:16 + C].permute(0, 3, 1, 2).cpu(), want)
+    assert float(dst[..., :16].abs().max()) == 0 and float(dst[..., 16 + C:].abs().max()) == 0
