@@ -158,6 +158,25 @@ def measure_tf32_peak(dev):
         torch.cuda.empty_cache()
 
 
+def conv_groups(prof, K):
+    """ms per step of every conv launch, grouped by the reference module it belongs to"""
+    groups = {}
+    for fam in ("conv_tc", "conv_ffma"):
+        for label, v in prof.get(fam, {}).get("by_label", {}).items():
+            g = label.split(".")[0]
+            if g.startswith("Dec") or g == "Ch_Reducer":
+                g = "D1" if not label.split(".")[0].endswith("_2") and "res_2" not in label else "D2"
+                if label.startswith("Ch_Reducer"):
+                    g = "Ch_Reducer"
+            d = groups.setdefault(g, {"ms": 0.0, "tflops": 0.0, "macs": 0, "ffma_ms": 0.0})
+            d["ms"] += v["ms"] / K
+            d["macs"] += v["macs"] / K
+            if fam == "conv_ffma":
+                d["ffma_ms"] += v["ms"] / K
+    return {g: {"ms": round(d["ms"], 2), "TFLOP/s": round(2 * d["macs"] / (d["ms"] / 1e3) / 1e12, 1), "of_which_cuda_core_ms": round(d["ffma_ms"], 2)}
+            for g, d in sorted(groups.items(), key=lambda kv: -kv[1]["ms"])}
+
+
 def run_ours(args):
     import torch.distributed as dist
     from demfi_b200 import _abi as A
@@ -281,6 +300,7 @@ def run_ours(args):
         "top_shapes": [{"conv": k, "launches_per_step": v["launches"] // K, "ms_per_launch": round(v["ms"] / v["launches"], 3),
                         "TFLOP/s": round(2 * v["macs"] / (v["ms"] / 1e3) / 1e12, 1)} for k, v in top],
         "other_kernels_ms_per_step": {k: round(v["ms"] / K, 3) for k, v in prof.items() if k != "conv_tc"},
+        "conv_ms_per_step_by_layer_group": conv_groups(prof, K),
     }
     cpu_fps, _, cores, sample = cpu_reference_sample(1, 1)
     hp = (H0 + 31) // 32 * 32

@@ -18,8 +18,8 @@
 //                the tensor core accumulates with truncation, so keeping the small terms out of the main
 //                chain cuts its length 3x (measured: error grows linearly with the chain length).
 // Persistent CTAs (one per SM) walk the tile list; warp roles:
-//   warps 0-3 split A | warps 4-7 epilogue (TMEM -> regs -> fused epilogue -> HBM)
-//   warp 8 TMA producer | warp 9 TMEM allocator + single-thread tcgen05.mma issuer
+//   warps 0-3 split A | warps 4-7 and 10-13 epilogue (TMEM -> regs -> fused epilogue -> HBM)
+//   warp 8 TMA producer | warp 9 TMEM allocator + tcgen05.mma issuer (one elected lane)
 // The accumulator pair is double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
 // cout_pad > 128 is processed as N blocks of <= 128 channels (a tile = pixel tile x N block).
 #include <cuda.h>
@@ -33,7 +33,7 @@ namespace demfi {
 
 constexpr int TC_TH = 8, TC_TW = 16, TC_BM = 128, TC_KC = 32;
 constexpr int TC_A_BYTES = TC_BM * TC_KC * 4;  // 16 KiB
-constexpr int TC_THREADS = 320;
+constexpr int TC_THREADS = 448;  // 14 warps: 0-3 split, 4-7 + 10-13 epilogue, 8 TMA, 9 MMA
 constexpr int TC_MAX_STAGES = 6;
 constexpr int TC_SMEM_BUDGET = 200 * 1024;
 
@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull(a), 1);
-      mbar_init(bar_tempty(a), 128);
+      mbar_init(bar_tempty(a), 256);
     }
     for (int a = 0; a < 4; ++a) mbar_init(bar_aempty(a), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -310,10 +310,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           }
     }
     }
-  } else if (warp < 8) {
-    // ===== epilogue: TMEM lane = pixel row of the tile; warp w owns lanes 32*(w%4).. =====
+  } else if (warp < 8 || warp >= 10) {
+    // ===== epilogue: 8 warps.  TMEM lane = pixel row of the tile; a warp can only touch lanes 32*(warp%4)...
+    // Group 0 (warps 4-7) takes the accumulator columns [0, csplit), group 1 (warps 10-13) takes [csplit, N):
+    // the epilogue was the critical role in the ncu source profile (95 % busy), so its work is halved per warp,
+    // TMEM loads are issued in batches (one wait per batch) and the ReLU / linear NHWC case is inlined. =====
+    const int grp = warp >= 10 ? 1 : 0;
     const int wq = warp & 3;
     const int m = wq * 32 + lane;
+    constexpr int HMAX = (NMAX / 2 + 15) / 16 * 16;  // columns one group can own
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
@@ -325,36 +330,44 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const int ty0 = (t % P.tiles_y) * TC_TH;
       const int n = t / P.tiles_y;
       const int N = n_of(nb), n0 = nb * P.nb_max;
+      const int csplit = ((N / 2 + 15) / 16) * 16;
+      const int cbeg = grp ? csplit : 0, cnum = grp ? N - csplit : csplit;  // this group's columns
       const int oy = ty0 + (m >> 4), ox = tx0 + (m & 15);
       const bool valid = (oy < c.H) && (ox < c.W);
       // The tensor core accumulates with truncation (a biased error that compounds over ~100 layers), so
       // the K loop is cut into segments of P.flush stages: each segment's partial sum is drained from
       // TMEM and added here in fp32 round-to-nearest while the MMAs of the next segment run.
-      float sum[NMAX];
+      float sum[HMAX];
       bool first = true;
       for (int done = 0; done < P.stages_per_tile; done += P.flush) {
         const float gain = 1.0f + P.comp * (float)(4 * min(P.flush, P.stages_per_tile - done));
         mbar_wait(bar_tfull(acc), acc_phase);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * P.buf_stride);
+        const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * P.buf_stride) + (uint32_t)cbeg;
+        uint32_t r[HMAX];
 #pragma unroll
-        for (int col = 0; col < NMAX; col += 16) {
-          if (col < N) {
-            uint32_t r[16], rc[16];
-            tmem_ld16_nowait(taddr + (uint32_t)col, r);
-            if (P.split == 3) tmem_ld16_nowait(taddr + (uint32_t)(N + col), rc);
+        for (int col = 0; col < HMAX; col += 16)
+          if (col < cnum) tmem_ld16_nowait(taddr + (uint32_t)col, r + col);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < HMAX; ++j) {
+          const float v = __uint_as_float(r[j]) * gain;
+          sum[j] = first ? v : sum[j] + v;
+        }
+        if (P.split == 3) {
+#pragma unroll
+          for (int col = 0; col < HMAX; col += 16)
+            if (col < cnum) tmem_ld16_nowait(taddr + (uint32_t)(N + col), r + col);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < HMAX; ++j) sum[j] += __uint_as_float(r[j]);
+          if (P.diag & 4) {
+#pragma unroll
+            for (int col = 0; col < HMAX; col += 16)
+              if (col < cnum) tmem_ld16_nowait(taddr + (uint32_t)(2 * N + col), r + col);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float v = __uint_as_float(r[j]) * gain;
-              if (P.split == 3) v += __uint_as_float(rc[j]);
-              sum[col + j] = first ? v : sum[col + j] + v;
-            }
-            if (P.split == 3 && (P.diag & 4)) {
-              tmem_ld16(taddr + (uint32_t)(2 * N + col), rc);
-#pragma unroll
-              for (int j = 0; j < 16; ++j) sum[col + j] += __uint_as_float(rc[j]);
-            }
+            for (int j = 0; j < HMAX; ++j) sum[j] += __uint_as_float(r[j]);
           }
         }
         tc_fence_before();
@@ -363,15 +376,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         first = false;
       }
       if (valid && !(P.diag & 1)) {
+        const int ch_lo = n0 + cbeg, ch_hi = ch_lo + cnum;  // absolute accumulator channels held in sum[]
 #pragma unroll 1
         for (int sgi = 0; sgi < c.nseg; ++sgi) {
-          if (c.seg[sgi].ch0 >= n0 + N || c.seg[sgi].ch0 + c.seg[sgi].nch <= n0) continue;
-          const SegCursor cur = seg_cursor(c, c.seg[sgi], n, oy, ox);
+          const demfi_seg_t& sg = c.seg[sgi];
+          if (sg.ch0 >= ch_hi || sg.ch0 + sg.nch <= ch_lo) continue;
+          const SegCursor cur = seg_cursor(c, sg, n, oy, ox);
+          if (sg.store == DEMFI_STORE_NHWC && (sg.act == DEMFI_ACT_RELU || sg.act == DEMFI_ACT_NONE)) {
+            // fast path (ResBlocks, RDB, Mixer ...): bias (+ residual) (+ ReLU), 128-bit store, no call
+            const float lo_clamp = sg.act == DEMFI_ACT_RELU ? 0.0f : -INFINITY;
 #pragma unroll
-          for (int col = 0; col < NMAX; col += 4) {
-            if (col < N) {
-              const float4 b = ld4(c.bias + n0 + col);
-              seg_emit4(cur, n0 + col, make_float4(sum[col] + b.x, sum[col + 1] + b.y, sum[col + 2] + b.z, sum[col + 3] + b.w));
+            for (int col = 0; col < HMAX; col += 4) {
+              const int co = ch_lo + col;
+              if (col < cnum && co >= cur.lo && co < cur.hi) {
+                const float4 b = ld4(c.bias + co);
+                float4 v = make_float4(sum[col] + b.x, sum[col + 1] + b.y, sum[col + 2] + b.z, sum[col + 3] + b.w);
+                if (cur.res != nullptr) {
+                  const float4 rr = ld4(cur.res + (co - cur.lo));
+                  v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
+                }
+                v.x = fmaxf(v.x, lo_clamp); v.y = fmaxf(v.y, lo_clamp); v.z = fmaxf(v.z, lo_clamp); v.w = fmaxf(v.w, lo_clamp);
+                st4(cur.dst + (co - cur.lo), v);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int col = 0; col < HMAX; col += 4) {
+              if (col < cnum) {
+                const float4 b = ld4(c.bias + ch_lo + col);
+                seg_emit4(cur, ch_lo + col, make_float4(sum[col] + b.x, sum[col + 1] + b.y, sum[col + 2] + b.z, sum[col + 3] + b.w));
+              }
             }
           }
         }
