@@ -301,6 +301,10 @@ def run_ours(args):
                         "TFLOP/s": round(2 * v["macs"] / (v["ms"] / 1e3) / 1e12, 1)} for k, v in top],
         "other_kernels_ms_per_step": {k: round(v["ms"] / K, 3) for k, v in prof.items() if k != "conv_tc"},
         "conv_ms_per_step_by_layer_group": conv_groups(prof, K),
+        "hbm_bound_kernels": {k: {"launches_per_step": v["launches"] // K, "ms_per_launch": round(v["ms"] / v["launches"], 4),
+                                  "GB/s": round(v["bytes"] / (v["ms"] / 1e3) / 1e9, 1),
+                                  "frac_of_measured_hbm": round(v["bytes"] / (v["ms"] / 1e3) / 1e9 / peaks.get("hbm_gbs", 6437.3), 3)}
+                              for k, v in prof.items() if v.get("bytes", 0) > 0 and v["ms"] > 0},
     }
     cpu_fps, _, cores, sample = cpu_reference_sample(1, 1)
     hp = (H0 + 31) // 32 * 32

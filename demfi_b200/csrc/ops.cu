@@ -66,48 +66,69 @@ __device__ __forceinline__ float gather1(const float* img, int ld, int n, int H,
 
 // ------------------------------------------------------------------------------------------
 // bwarp + Eq.(2).  LPP lanes cooperate on one pixel, each lane owning 4 channels per pass.
+// LPP = 16 (feature maps): a CTA walks an 8-row x 16-column pixel tile row by row, so the bilinear corners shared
+// with the previous row (and with x-neighbours) are L1 hits instead of L2 round trips.
+// LPP = 1 (3-channel pixel warp): one thread per pixel, scalar path.
 template <int LPP>
 __global__ void __launch_bounds__(256)
 bwarp_blend_kernel(const float* __restrict__ a, int a_ld, const float* __restrict__ b, int b_ld,
                    const float* __restrict__ flow, int flow_ld, const float* __restrict__ occ, int occ_ld,
                    const float* __restrict__ tv, int B, int H, int W, int C, float* __restrict__ out, int out_ld,
-                   float* __restrict__ occ_out, int occ_out_ld) {
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long pix = gid / LPP;
-  const int lane = (int)(gid % LPP);
-  const long long npix = (long long)B * H * W;
-  if (pix >= npix) return;
-  const int x = (int)(pix % W);
-  const int y = (int)((pix / W) % H);
-  const int n = (int)(pix / ((long long)W * H));
-  const float4 f = __ldg((const float4*)(flow + pix * flow_ld));
-  const float o0 = sigmoid_f(__ldg(occ + pix * occ_ld));
-  const float o1 = 1.0f - o0;
-  const float t = __ldg(tv + n);
-  const Corners ca = make_corners(bwarp_coord(x, f.x, W), bwarp_coord(y, f.y, H), H, W);
-  const Corners cb = make_corners(bwarp_coord(x, f.z, W), bwarp_coord(y, f.w, H), H, W);
-  // bwarp's validity mask: warped ones < 0.999 -> 0 (DeMFInet.py:758-766)
-  const float ma = ca.wsum < 0.999f ? 0.0f : 1.0f;
-  const float mb = cb.wsum < 0.999f ? 0.0f : 1.0f;
-  const float ka = (1.0f - t) * o0, kb = t * o1;
-  const float den = ka + kb;
-  if (lane == 0 && occ_out != nullptr) occ_out[pix * occ_out_ld] = o0;
-  if (C % 4 == 0) {
-    for (int ch = lane * 4; ch < C; ch += LPP * 4) {
-      const float4 va = gather4(a, a_ld, n, H, W, ca, ch);
-      const float4 vb = gather4(b, b_ld, n, H, W, cb, ch);
-      float4 r;
-      r.x = (ka * (va.x * ma) + kb * (vb.x * mb)) / den;
-      r.y = (ka * (va.y * ma) + kb * (vb.y * mb)) / den;
-      r.z = (ka * (va.z * ma) + kb * (vb.z * mb)) / den;
-      r.w = (ka * (va.w * ma) + kb * (vb.w * mb)) / den;
-      st4(out + pix * out_ld + ch, r);
-    }
+                   float* __restrict__ occ_out, int occ_out_ld, int tiles_x, int tiles_y) {
+  constexpr int ROWS = LPP == 16 ? 8 : 1;
+  int n, x, y0, lane;
+  if constexpr (LPP == 16) {
+    int t = blockIdx.x;
+    const int tx = t % tiles_x;
+    t /= tiles_x;
+    const int ty = t % tiles_y;
+    n = t / tiles_y;
+    x = tx * 16 + (threadIdx.x >> 4);
+    y0 = ty * 8;
+    lane = threadIdx.x & 15;
+    if (x >= W) return;
   } else {
-    for (int ch = lane; ch < C; ch += LPP) {
-      const float va = gather1(a, a_ld, n, H, W, ca, ch);
-      const float vb = gather1(b, b_ld, n, H, W, cb, ch);
-      out[pix * out_ld + ch] = (ka * (va * ma) + kb * (vb * mb)) / den;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)B * H * W) return;
+    x = (int)(gid % W);
+    y0 = (int)((gid / W) % H);
+    n = (int)(gid / ((long long)W * H));
+    lane = 0;
+  }
+  const float t = __ldg(tv + n);
+#pragma unroll 1
+  for (int r = 0; r < ROWS; ++r) {
+    const int y = y0 + r;
+    if (y >= H) break;
+    const long long pix = ((long long)n * H + y) * W + x;
+    const float4 f = __ldg((const float4*)(flow + pix * flow_ld));
+    const float o0 = sigmoid_f(__ldg(occ + pix * occ_ld));
+    const float o1 = 1.0f - o0;
+    const Corners ca = make_corners(bwarp_coord(x, f.x, W), bwarp_coord(y, f.y, H), H, W);
+    const Corners cb = make_corners(bwarp_coord(x, f.z, W), bwarp_coord(y, f.w, H), H, W);
+    // bwarp's validity mask: warped ones < 0.999 -> 0 (DeMFInet.py:758-766)
+    const float ma = ca.wsum < 0.999f ? 0.0f : 1.0f;
+    const float mb = cb.wsum < 0.999f ? 0.0f : 1.0f;
+    const float ka = (1.0f - t) * o0, kb = t * o1;
+    const float den = ka + kb;
+    if (lane == 0 && occ_out != nullptr) occ_out[pix * occ_out_ld] = o0;
+    if (C % 4 == 0) {
+      for (int ch = lane * 4; ch < C; ch += LPP * 4) {
+        const float4 va = gather4(a, a_ld, n, H, W, ca, ch);
+        const float4 vb = gather4(b, b_ld, n, H, W, cb, ch);
+        float4 r4;
+        r4.x = (ka * (va.x * ma) + kb * (vb.x * mb)) / den;
+        r4.y = (ka * (va.y * ma) + kb * (vb.y * mb)) / den;
+        r4.z = (ka * (va.z * ma) + kb * (vb.z * mb)) / den;
+        r4.w = (ka * (va.w * ma) + kb * (vb.w * mb)) / den;
+        st4(out + pix * out_ld + ch, r4);
+      }
+    } else {
+      for (int ch = lane; ch < C; ch += LPP) {
+        const float va = gather1(a, a_ld, n, H, W, ca, ch);
+        const float vb = gather1(b, b_ld, n, H, W, cb, ch);
+        out[pix * out_ld + ch] = (ka * (va * ma) + kb * (vb * mb)) / den;
+      }
     }
   }
 }
@@ -318,12 +339,14 @@ int demfi_bwarp_blend(const float* a, int32_t a_ld, const float* b, int32_t b_ld
                   "bwarp_blend: vector path needs 16-byte aligned slices");
   const long long npix = (long long)B * H * W;
   cudaStream_t st = (cudaStream_t)stream;
-  if (C >= 64)
-    bwarp_blend_kernel<16><<<blocks_for(npix * 16), 256, 0, st>>>(a, a_ld, b, b_ld, flow, flow_ld, occ, occ_ld, t, B, H,
-                                                                  W, C, out, out_ld, occ_out, occ_out_ld);
-  else
+  if (C >= 64 && C % 4 == 0) {
+    const int tiles_x = (W + 15) / 16, tiles_y = (H + 7) / 8;
+    bwarp_blend_kernel<16><<<(unsigned)((long long)tiles_x * tiles_y * B), 256, 0, st>>>(
+        a, a_ld, b, b_ld, flow, flow_ld, occ, occ_ld, t, B, H, W, C, out, out_ld, occ_out, occ_out_ld, tiles_x, tiles_y);
+  } else {
     bwarp_blend_kernel<1><<<blocks_for(npix), 256, 0, st>>>(a, a_ld, b, b_ld, flow, flow_ld, occ, occ_ld, t, B, H, W, C,
-                                                            out, out_ld, occ_out, occ_out_ld);
+                                                            out, out_ld, occ_out, occ_out_ld, 0, 0);
+  }
   DEMFI_LAUNCH_CHECK("bwarp_blend");
   return 0;
 }

@@ -503,6 +503,29 @@ class Engine:
                 sharps_final.append(None)
         return sharps_dec1, sharps_final, flow_predictions, occ0_predictions, two_blurry
 
+    @staticmethod
+    def _op_bytes(op) -> int:
+        """algorithmic HBM bytes (fp32, every operand once) of the memory-bound operators"""
+        k = op[0]
+        if k == "bwarp_blend":
+            a, out, oo = op[1], op[5], op[6]
+            return a.npix() * 4 * (2 * a.C + 4 + 1 + a.C + (1 if oo is not None else 0))
+        if k == "fgac_sample":
+            return op[1].npix() * 4 * (2 * op[1].C + 2)
+        if k == "fgac_blend":
+            return op[2].npix() * 4 * (1 + 3 * op[2].C)
+        if k == "cfr_splat":
+            return op[1].npix() * 4 * (4 + 12)
+        if k == "cfr_finalize":
+            return op[1].npix() * 4 * (8 + 4)
+        if k == "copy":
+            return op[1].npix() * 4 * 2 * op[1].C
+        if k == "upsample":
+            return op[2].npix() * 4 * op[2].C * 5 // 4
+        if k == "zero":
+            return op[1].npix() * 4 * op[1].ld
+        return 0
+
     def profile_summary(self) -> Dict[str, dict]:
         """Aggregate self.profile (CUDA-event durations on the launch stream) per kernel family."""
         out: Dict[str, dict] = {}
@@ -513,10 +536,13 @@ class Engine:
                 macs = op[4]
             else:
                 fam, macs = op[0], 0
-            d = out.setdefault(fam, {"launches": 0, "ms": 0.0, "macs": 0, "by_label": {}})
+                if fam == "bwarp_blend":
+                    fam = "bwarp_blend_c%d" % op[1].C
+            d = out.setdefault(fam, {"launches": 0, "ms": 0.0, "macs": 0, "bytes": 0, "by_label": {}})
             d["launches"] += 1
             d["ms"] += ms
             d["macs"] += macs
+            d["bytes"] += self._op_bytes(op)
             if op[0] == "conv":
                 b = d["by_label"].setdefault(op[2].split(".")[-1] if False else op[2], {"launches": 0, "ms": 0.0, "macs": 0})
                 b["launches"] += 1
