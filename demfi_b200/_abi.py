@@ -16,7 +16,7 @@ MAX_SRC = 4
 MAX_SEG = 4
 ACT_NONE, ACT_RELU, ACT_TANH, ACT_SIGMOID, ACT_SIGMOID_MUL, ACT_GRU = range(6)
 STORE_NHWC, STORE_PIXEL_SHUFFLE2 = 0, 1
-CONV_FFMA, CONV_TC = 0, 1
+CONV_FFMA, CONV_TC, CONV_TC16 = 0, 1, 2
 
 i32 = C.c_int32
 vp = C.c_void_p
@@ -61,6 +61,7 @@ SYMBOLS = {
     "demfi_launch_count": (C.c_uint64, []),
     "demfi_set_option": (i32, [C.c_char_p, i32]),
     "demfi_get_option": (i32, [C.c_char_p, C.POINTER(i32)]),
+    "demfi_tc_debug_read": (i32, [C.POINTER(C.c_int64), i32]),
 }
 
 _lib = None

@@ -111,6 +111,7 @@ int demfi_get_option(const char* name, int32_t* value) {
 size_t demfi_packed_weight_floats(int32_t kind, int32_t KH, int32_t KW, const int32_t* src_C, int32_t nsrc,
                                   int32_t cout_pad) {
   if (kind == DEMFI_CONV_TC) return tc_packed_floats(KH, KW, src_C, nsrc, cout_pad);
+  if (kind == DEMFI_CONV_TC16) return h3_packed_floats(KH, KW, src_C, nsrc, cout_pad);
   int k_total = 0;
   for (int s = 0; s < nsrc; ++s) k_total += src_C[s];
   return (size_t)KH * KW * k_total * cout_pad;
@@ -127,6 +128,7 @@ int demfi_pack_weights(int32_t kind, const float* w, int32_t Co, int32_t Ci, int
   for (int k = 0; k < k_total; ++k) DEMFI_REQUIRE(in_map[k] >= -1 && in_map[k] < Ci, "pack_weights: in_map[%d] out of range", k);
   for (int n = 0; n < cout_pad; ++n) DEMFI_REQUIRE(out_map[n] >= -1 && out_map[n] < Co, "pack_weights: out_map[%d] out of range", n);
   if (kind == DEMFI_CONV_TC) return tc_pack_weights(w, Co, Ci, KH, KW, in_map, src_C, nsrc, out_map, cout_pad, out);
+  if (kind == DEMFI_CONV_TC16) return h3_pack_weights(w, Co, Ci, KH, KW, in_map, src_C, nsrc, out_map, cout_pad, out);
   // FFMA layout: [tap][k][cout_pad]
   const int taps = KH * KW;
   for (int tap = 0; tap < taps; ++tap)
@@ -139,6 +141,11 @@ int demfi_pack_weights(int32_t kind, const float* w, int32_t Co, int32_t Ci, int
       }
     }
   return 0;
+}
+
+int demfi_tc_debug_read(int64_t* host, int32_t ctas) {
+  DEMFI_REQUIRE(host != nullptr, "tc_debug_read: null buffer");
+  return tc_debug_read(reinterpret_cast<long long*>(host), ctas);
 }
 
 int demfi_conv2d(const demfi_conv_t* c, void* stream) {
@@ -170,6 +177,8 @@ int demfi_conv2d(const demfi_conv_t* c, void* stream) {
   }
   DEMFI_REQUIRE(c->wpack && c->bias, "conv2d: null weights");
   if (c->kind == DEMFI_CONV_TC) return launch_conv_tc(*c, (cudaStream_t)stream);
+  if (c->kind == DEMFI_CONV_TC16) return launch_conv_h3(*c, (cudaStream_t)stream);
+  DEMFI_REQUIRE(c->kind == DEMFI_CONV_FFMA, "conv2d: unknown kind %d", c->kind);
   return launch_conv_ffma(*c, (cudaStream_t)stream);
 }
 

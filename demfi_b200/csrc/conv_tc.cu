@@ -50,6 +50,7 @@ struct TcParams {
                          // 4 separate lo*hi accumulator, 8/16 skip A/B loads, 32 free-running issuer (timing only)
   float comp;            // per-MMA gain correction of the truncating tensor-core accumulation (0 = off)
   int a_stages, a_base;  // A-in-TMEM variant: ring of a_stages x 64 TMEM columns (hi 32 | lo 32) starting at a_base
+  long long* dbg;        // tc_diag & 128: per-CTA role timers [gridDim.x][16] (cycles), see demfi_tc_debug_read
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------
@@ -88,6 +89,13 @@ static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
+}
+// mbarrier wait that adds the cycles it took to *acc when role timers are on (tc_diag & 128)
+__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, bool on, long long& acc) {
+  if (!on) { mbar_wait(bar, parity); return; }
+  const long long t = clock64();
+  mbar_wait(bar, parity);
+  acc += clock64() - t;
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
                                             int c3) {
@@ -245,9 +253,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32) << 16);
       int stage = 0, sa = 0;
       uint32_t phase = 0, aphase = 0;
+      const bool dbg = P.dbg != nullptr;
+      long long w_full = 0, w_aempty = 0, w_st = 0;
+      const long long t_begin = dbg ? clock64() : 0;
       for (int tile = blockIdx.x; tile < P.ntiles && !(P.diag & 32); tile += gridDim.x) {
         for (int st_ = 0; st_ < P.stages_per_tile; ++st_) {
-          mbar_wait(bar_full(stage), phase);
+          mbar_wait_t(bar_full(stage), phase, dbg, w_full);
           const uint32_t row = smem_base + (uint32_t)stage * stage_bytes + (uint32_t)m * 128u;
           uint32_t hi[32], lo[32];
 #pragma unroll
@@ -264,17 +275,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               hi[j] = h;
             }
           }
-          mbar_wait(bar_aempty(sa), aphase ^ 1);
+          mbar_wait_t(bar_aempty(sa), aphase ^ 1, dbg, w_aempty);
           tc_fence_after();
           const uint32_t ta = tmem_base + lane_addr + (uint32_t)(P.a_base + sa * 64);
+          const long long t_st = dbg ? clock64() : 0;
           tmem_st32(ta, hi);
           if (P.split == 3) tmem_st32(ta + 32u, lo);
           tmem_st_wait();
           tc_fence_before();
           mbar_arrive(bar_aready(sa));
+          if (dbg) w_st += clock64() - t_st;
           if (++stage == S) { stage = 0; phase ^= 1; }
           if (++sa == P.a_stages) { sa = 0; aphase ^= 1; }
         }
+      }
+      if (dbg && threadIdx.x == 0) {
+        long long* d = P.dbg + (size_t)blockIdx.x * 16;
+        d[0] = clock64() - t_begin; d[1] = w_full; d[2] = w_aempty; d[3] = w_st;
       }
     } else {
     int stage = 0;
@@ -321,6 +338,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     constexpr int HMAX = (NMAX / 2 + 15) / 16 * 16;  // columns one group can own
     int acc = 0;
     uint32_t acc_phase = 0;
+    const bool dbg = P.dbg != nullptr;
+    long long w_tfull = 0, w_store = 0;
+    const long long t_begin = dbg ? clock64() : 0;
     for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
       int t = tile;
       const int nb = t % P.n_blocks;
@@ -341,7 +361,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       bool first = true;
       for (int done = 0; done < P.stages_per_tile; done += P.flush) {
         const float gain = 1.0f + P.comp * (float)(4 * min(P.flush, P.stages_per_tile - done));
-        mbar_wait(bar_tfull(acc), acc_phase);
+        mbar_wait_t(bar_tfull(acc), acc_phase, dbg, w_tfull);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * P.buf_stride) + (uint32_t)cbeg;
         uint32_t r[HMAX];
@@ -375,6 +395,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         first = false;
       }
+      const long long t_store = dbg ? clock64() : 0;
       if (valid && !(P.diag & 1)) {
         const int ch_lo = n0 + cbeg, ch_hi = ch_lo + cnum;  // absolute accumulator channels held in sum[]
 #pragma unroll 1
@@ -410,6 +431,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           }
         }
       }
+      if (dbg) w_store += clock64() - t_store;
+    }
+    if (dbg && warp == 4 && lane == 0) {
+      long long* d = P.dbg + (size_t)blockIdx.x * 16;
+      d[4] = clock64() - t_begin; d[5] = w_tfull; d[6] = w_store;
     }
   } else if (warp == 8) {
     // ===== TMA producer (one elected lane).  Per-stage work is kept minimal: no divisions, incremental pointers. =====
@@ -418,6 +444,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       uint32_t phase = 0;
       const bool do_a = !(P.diag & 8), do_b = !(P.diag & 16);  // timing diagnostics only (results are garbage)
       const size_t w_step = 2 * (size_t)c.cout_pad * TC_KC;   // floats per (chunk, tap) in the packed weights
+      const bool dbg = P.dbg != nullptr;
+      long long w_empty = 0;
+      const long long t_begin = dbg ? clock64() : 0;
       for (int tile = blockIdx.x; tile < P.ntiles && !(P.diag & 32); tile += gridDim.x) {
         int t = tile;
         const int nb = t % P.n_blocks;
@@ -437,7 +466,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           for (int c0 = 0; c0 < Cs; c0 += TC_KC)
             for (int ky = 0; ky < c.KH; ++ky)
               for (int kx = 0; kx < c.KW; ++kx) {
-                mbar_wait(bar_empty(stage), phase ^ 1);
+                mbar_wait_t(bar_empty(stage), phase ^ 1, dbg, w_empty);
                 const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
                 const uint32_t fb = bar_full(stage);
                 mbar_arrive_expect_tx(fb, tx_bytes);
@@ -451,6 +480,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               }
         }
       }
+      if (dbg) {
+        long long* d = P.dbg + (size_t)blockIdx.x * 16;
+        d[8] = clock64() - t_begin; d[9] = w_empty;
+      }
     }
   } else {
     // ===== MMA issuer (warp 9: the whole warp walks the flattened stage loop, one elected lane issues).
@@ -462,13 +495,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const uint64_t dstep = (uint64_t)(stage_bytes >> 4);                        // descriptor start-address step per stage
     const bool free_run = (P.diag & 32) != 0, keep_commits = (P.diag & 64) != 0;
     uint32_t stage = 0, phase = 0, sa_ = 0, aphase = 0, acc = 0, acc_phase = 0;
+    const bool dbg = P.dbg != nullptr;
+    long long w_tempty = 0, w_aready = 0;
+    const long long t_begin = dbg ? clock64() : 0;
     for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
       const int N = n_of(tile % P.n_blocks);
       const uint32_t idesc_n = idesc0 | ((uint32_t)(N >> 3) << 17);         // N columns
       const uint32_t idesc_2n = idesc0 | ((uint32_t)((2 * N) >> 3) << 17);  // [hi;lo] weight tile: 2N columns
       for (int done = 0; done < P.stages_per_tile; done += P.flush) {
         const int seg_len = min(P.flush, P.stages_per_tile - done);
-        mbar_wait(bar_tempty(acc), acc_phase ^ 1);  // fresh accumulator pair for this segment
+        mbar_wait_t(bar_tempty(acc), acc_phase ^ 1, dbg, w_tempty);  // fresh accumulator pair for this segment
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * (uint32_t)P.buf_stride;  // main [0,N), correction [N,2N)
         const uint32_t d_lohi = d_tmem + (uint32_t)((P.diag & 4) ? 2 * N : N);
@@ -477,7 +513,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           const uint32_t first = (i == 0) ? 0u : 1u;
           if constexpr (ATMEM) {
             if (!free_run) {
-              mbar_wait(bar_aready(sa_), aphase);  // splitter stored A (it waited on full[stage]: B has landed too)
+              mbar_wait_t(bar_aready(sa_), aphase, dbg, w_aready);  // splitter stored A (it waited on full[stage]: B has landed too)
               tc_fence_after();
             }
             const uint32_t ta = tmem_base + (uint32_t)P.a_base + sa_ * 64u;
@@ -535,6 +571,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
+    if (dbg && lane == 0) {
+      long long* d = P.dbg + (size_t)blockIdx.x * 16;
+      d[12] = clock64() - t_begin; d[13] = w_tempty; d[14] = w_aready;
+    }
   }
 
   tc_fence_before();
@@ -563,6 +603,24 @@ static EncodeTiledFn get_encode_fn() {
       fn = reinterpret_cast<EncodeTiledFn>(p);
   }
   return fn;
+}
+
+constexpr int TC_DBG_CTAS = 256;
+static long long* g_tc_dbg = nullptr;
+// role timers of the last conv_tc launch made with tc_diag & 128: [ctas][16] cycles
+//   0 splitter total, 1 wait full, 2 wait A slot free, 3 tcgen05.st + arrive | 4 epilogue total, 5 wait accumulator, 6 store phase
+//   8 producer total, 9 wait stage free | 12 issuer total, 13 wait accumulator free, 14 wait A ready
+int tc_debug_read(long long* host, int ctas) {
+  DEMFI_REQUIRE(g_tc_dbg != nullptr, "tc_debug_read: no launch was made with tc_diag & 128");
+  DEMFI_REQUIRE(ctas > 0 && ctas <= TC_DBG_CTAS, "tc_debug_read: ctas out of range");
+  DEMFI_REQUIRE(cudaMemcpy(host, g_tc_dbg, (size_t)ctas * 16 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess, "tc_debug_read: copy failed");
+  return 0;
+}
+
+long long* tc_debug_buffer(cudaStream_t st) {
+  if (g_tc_dbg == nullptr && cudaMalloc(&g_tc_dbg, TC_DBG_CTAS * 16 * sizeof(long long)) != cudaSuccess) return nullptr;
+  cudaMemsetAsync(g_tc_dbg, 0, TC_DBG_CTAS * 16 * sizeof(long long), st);
+  return g_tc_dbg;
 }
 
 static int num_sms() {
@@ -616,6 +674,10 @@ int launch_conv_tc(const demfi_conv_t& c, cudaStream_t st) {
   P.stages = stages;
   if (atmem && P.a_stages > stages) P.a_stages = stages;  // the aready[] barriers reuse the split[] slots
   P.diag = get_option("tc_diag");
+  if (P.diag & 128) {
+    P.dbg = tc_debug_buffer(st);
+    DEMFI_REQUIRE(P.dbg != nullptr, "conv_tc: cannot allocate the role-timer buffer");
+  }
   P.comp = (float)get_option("tc_comp_milli") * 1e-3f * 5.9604645e-8f;  // milli-units of 2^-24 per MMA
   if (!atmem) P.diag &= (1 | 8 | 16);
   if (P.diag & 32) P.diag |= 1;  // free-running MMA issuer: timing only

@@ -71,7 +71,7 @@ class Engine:
         if not dry:
             A.check(self.lib.demfi_device_check(device.index or 0), "demfi_device_check")
         self.conv_kind = (conv_kind or os.environ.get("DEMFI_CONV_KIND", "auto")).lower()
-        assert self.conv_kind in ("auto", "ffma", "tc")
+        assert self.conv_kind in ("auto", "ffma", "tc", "tc16")
         self._keep: list = []  # weights, ctypes structs
         self.bufs: Dict[str, torch.Tensor] = {}
         self.views: Dict[str, View] = {}
@@ -152,16 +152,17 @@ class Engine:
         return (np.ascontiguousarray(torch.cat(ws, 0).numpy()), np.ascontiguousarray(torch.cat(bs, 0).numpy()))
 
     def _pick_kind(self, KH, KW, stride, pad, srcs, cout_pad):
-        eligible = (stride == 1 and all(u == 0 for _, u in srcs) and pad == (KH // 2, KW // 2)
-                    and KH % 2 == 1 and KW % 2 == 1 and cout_pad % 16 == 0 and cout_pad <= 256)
-        if self.conv_kind == "ffma" or not eligible:
+        """auto: every convolution the 3xFP16 tcgen05 kernel supports (stride 1 or 2, no up-sampled source) runs on
+        it; the rest on the CUDA-core kernel.  tc = first-generation 3xTF32 kernel where eligible (comparison)."""
+        no_up = all(u == 0 for _, u in srcs)
+        tc16_ok = stride in (1, 2) and no_up and cout_pad % 16 == 0 and cout_pad <= 256
+        tc_ok = (stride == 1 and no_up and pad == (KH // 2, KW // 2) and KH % 2 == 1 and KW % 2 == 1
+                 and cout_pad % 16 == 0 and cout_pad <= 256 and min(vw.C for vw, _ in srcs) >= 16)
+        if self.conv_kind == "ffma":
             return A.CONV_FFMA
         if self.conv_kind == "tc":
-            return A.CONV_TC
-        # auto: the tensor-core kernel pads every source to 32-channel chunks; tiny-K convs stay on CUDA cores
-        if min(vw.C for vw, _ in srcs) < 16:
-            return A.CONV_FFMA
-        return A.CONV_TC
+            return A.CONV_TC if tc_ok else A.CONV_FFMA
+        return A.CONV_TC16 if tc16_ok else A.CONV_FFMA
 
     def conv(self, names, srcs, out_hw, N, segs, k=(3, 3), stride=1, pad=None, in_map=None, out_map=None,
              cout=None, in_hw=None, label=None):
@@ -532,7 +533,7 @@ class Engine:
         for op, e0, e1 in self.profile or []:
             ms = e0.elapsed_time(e1)
             if op[0] == "conv":
-                fam = "conv_tc" if op[3] == A.CONV_TC else "conv_ffma"
+                fam = "conv_ffma" if op[3] == A.CONV_FFMA else "conv_tc"
                 macs = op[4]
             else:
                 fam, macs = op[0], 0

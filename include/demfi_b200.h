@@ -45,7 +45,11 @@ enum {
   DEMFI_STORE_PIXEL_SHUFFLE2 = 1 /* nn.PixelShuffle(2), DeMFInet.py:229: accumulator channel
                                     q*(nch/4)+c of pixel (y,x) -> dst pixel (2y+q/2, 2x+q%2), channel c */
 };
-enum { DEMFI_CONV_FFMA = 0, DEMFI_CONV_TC = 1 };
+enum {
+  DEMFI_CONV_FFMA = 0, /* CUDA-core fp32 implicit GEMM (exact fp32)                                   */
+  DEMFI_CONV_TC = 1,   /* tcgen05 kind::tf32, 3xTF32 split (first-generation tensor-core kernel)       */
+  DEMFI_CONV_TC16 = 2  /* tcgen05 kind::f16, 3xFP16 split + halo-tile activation staging; stride 1|2  */
+};
 
 /* one input of a (virtually concatenated) convolution */
 typedef struct {
@@ -77,7 +81,7 @@ typedef struct {
   int32_t KH, KW, stride, pad_h, pad_w;
   int32_t nsrc, nseg;
   int32_t cout_pad;  /* accumulator channels (padded Cout, multiple of 16)             */
-  int32_t kind;      /* DEMFI_CONV_FFMA | DEMFI_CONV_TC                               */
+  int32_t kind;      /* DEMFI_CONV_FFMA | DEMFI_CONV_TC | DEMFI_CONV_TC16                */
   demfi_src_t src[DEMFI_MAX_SRC];
   demfi_seg_t seg[DEMFI_MAX_SEG];
   const float* wpack; /* device, produced by demfi_pack_weights for the same `kind`    */
@@ -101,7 +105,9 @@ size_t demfi_packed_weight_floats(int32_t kind, int32_t KH, int32_t KW, const in
  * channel that internal channel k carries, or -1 for padding; out_map[n] (n < cout_pad) likewise
  * for output channels.  kind FFMA: [tap][k][cout_pad] fp32.  kind TC: per (32-channel chunk, tap) a
  * [cout_pad x 32] K-major tile, 128-byte-swizzled, stored twice: tf32 "hi" part and fp32
- * residual "lo" part (3xTF32 split). */
+ * residual "lo" part (3xTF32 split).  kind TC16: per (N block, 32-channel chunk, tap) a
+ * [2*N x 32] fp16 K-major tile, 64-byte-swizzled: rows 0..N-1 hold h = fp16(w), rows N..2N-1 hold
+ * l = fp16((w - h) * 2048) (3xFP16 split; the returned count is in floats, two fp16 per float). */
 int demfi_pack_weights(int32_t kind, const float* w_oihw_host, int32_t Co, int32_t Ci, int32_t KH, int32_t KW,
                        const int32_t* in_map, const int32_t* src_C, int32_t nsrc, const int32_t* out_map,
                        int32_t cout_pad, float* out_host);
@@ -177,6 +183,12 @@ uint64_t demfi_launch_count(void);
  * Returns non-zero for an unknown option. */
 int demfi_set_option(const char* name, int32_t value);
 int demfi_get_option(const char* name, int32_t* value);
+/* Role timers of the last tensor-core conv launched with "tc_diag" & 128 (measurement only): host[ctas][16]
+ * cycle counts per persistent CTA -- 0 splitter total, 1 its wait for the TMA stage, 2 its wait for a free A slot,
+ * 3 tcgen05.st + arrive; 4 epilogue total, 5 its wait for an accumulator, 6 store phase; 8 producer total,
+ * 9 its wait for a free stage; 12 MMA issuer total, 13 its wait for a drained accumulator, 14 its wait for A.
+ * Synchronises the device. */
+int demfi_tc_debug_read(int64_t* host, int32_t ctas);
 
 #ifdef __cplusplus
 }

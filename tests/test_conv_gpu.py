@@ -12,7 +12,7 @@ from demfi_b200 import _abi as A
 from gpu_util import DEV, from_nhwc, nhwc, run_conv
 
 pytestmark = pytest.mark.gpu
-KINDS = [pytest.param(A.CONV_FFMA, id="ffma"), pytest.param(A.CONV_TC, id="tc")]
+KINDS = [pytest.param(A.CONV_FFMA, id="ffma"), pytest.param(A.CONV_TC, id="tc"), pytest.param(A.CONV_TC16, id="tc16")]
 TOL = 2e-5  # max-abs relative to max(1, max|ref|): fp32 conv noise level (ref self-noise 2-3e-5)
 
 
@@ -205,14 +205,17 @@ def test_two_sources_permuted_padded(kind):
     check(from_nhwc(out, 64), F.relu(ref_conv(xin, w, b)), "agg3 conv")
 
 
-def test_ffma_stride2_4x4():
-    n, h, w_ = 1, 32, 48
-    x = rnd(n, 204, h, w_, seed=60)
-    w, b = wb(64, 204, 4, 4)
+@pytest.mark.parametrize("kind", [pytest.param(A.CONV_FFMA, id="ffma"), pytest.param(A.CONV_TC16, id="tc16")])
+@pytest.mark.parametrize("h,w_,ci,co", [(32, 48, 204, 64), (24, 40, 64, 128), (40, 72, 128, 256)])
+def test_stride2_4x4(kind, h, w_, ci, co):
+    """UNet encoders (DeMFInet.py:575-577): 4x4, stride 2, pad 1; ragged tiles (12 = 1.5*8, 20 = 1.25*16, 36 = 2.25*16)"""
+    n = 1
+    x = rnd(n, ci, h, w_, seed=60)
+    w, b = wb(co, ci, 4, 4)
     xb, _ = nhwc(x)
-    out = torch.zeros(n, h // 2, w_ // 2, 64, device=DEV)
-    run_conv(w, b, [(xb, 204, 0)], (h // 2, w_ // 2), A.CONV_FFMA, [dict(ch0=0, nch=64, dst=out, act=A.ACT_RELU)], stride=2, pad=(1, 1))
-    check(from_nhwc(out, 64), F.relu(ref_conv(x, w, b, 2, (1, 1))), "enc1 4x4 s2")
+    out = torch.zeros(n, h // 2, w_ // 2, co, device=DEV)
+    run_conv(w, b, [(xb, ci, 0)], (h // 2, w_ // 2), kind, [dict(ch0=0, nch=co, dst=out, act=A.ACT_RELU)], stride=2, pad=(1, 1))
+    check(from_nhwc(out, co), F.relu(ref_conv(x, w, b, 2, (1, 1))), f"enc 4x4 s2 {ci}->{co}")
 
 
 def test_ffma_upsample_concat():
@@ -226,14 +229,32 @@ def test_ffma_upsample_concat():
     check(from_nhwc(out, 64), F.relu(ref_conv(torch.cat([up, sk], 1), w, b)), "dec2 up+cat")
 
 
-def test_ffma_tiny_cin_7x7():
+@pytest.mark.parametrize("kind", [pytest.param(A.CONV_FFMA, id="ffma"), pytest.param(A.CONV_TC16, id="tc16")])
+def test_tiny_cin_7x7(kind):
     n, h, w_ = 1, 24, 24
     x = rnd(n, 5, h, w_, seed=63)
     w, b = wb(32, 5, 7, 7)
     xb, _ = nhwc(x, 8)
     out = torch.zeros(n, h, w_, 32, device=DEV)
-    run_conv(w, b, [(xb, 8, 0)], (h, w_), A.CONV_FFMA, [dict(ch0=0, nch=32, dst=out, act=A.ACT_RELU)])
+    run_conv(w, b, [(xb, 8, 0)], (h, w_), kind, [dict(ch0=0, nch=32, dst=out, act=A.ACT_RELU)])
     check(from_nhwc(out, 32), F.relu(ref_conv(x, w, b)), "conv_delta1")
+
+
+def test_tc16_operand_range():
+    """3xFP16 split (conv_h3.cu): values far below the fp16 normal range (6e-5) and up to a few thousand keep
+    fp32-level accuracy -- the low half is taken from the exact fp32 residual and scaled by 2048."""
+    n, h, w_ = 1, 16, 32
+    w, b = wb(64, 64, 3, 3)
+    for scale in (1e-6, 1e-4, 1.0, 3e3):
+        x = rnd(n, 64, h, w_, seed=72) * scale
+        xb, _ = nhwc(x)
+        out = torch.zeros(n, h, w_, 64, device=DEV)
+        run_conv(w, torch.zeros(64), [(xb, 64, 0)], (h, w_), A.CONV_TC16, [dict(ch0=0, nch=64, dst=out)])
+        want = ref_conv(x, w, torch.zeros(64))
+        err = float((from_nhwc(out, 64).double() - want).abs().max())
+        ref32 = float((F.conv2d(x, w, None, padding=1).double() - want).abs().max())
+        print(f"scale {scale:g}: tc16 err {err:.3e}, torch fp32 conv err {ref32:.3e}, max|ref| {float(want.abs().max()):.3e}")
+        assert err <= max(4.0 * ref32, 2e-5 * float(want.abs().max())), (scale, err, ref32)
 
 
 def test_tc_single_pass_is_not_parity_grade():

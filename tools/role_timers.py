@@ -1,0 +1,38 @@
+"""Per-role cycle breakdown of one tcgen05 conv launch (tc_diag & 128): where each warp role waits."""
+import ctypes as C, json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+from demfi_b200 import _abi as A
+from tools.bench_conv import make_conv, time_conv
+
+NAMES = {0: "split.total", 1: "split.wait_full", 2: "split.wait_aslot", 3: "split.st+arrive", 4: "epi.total", 5: "epi.wait_acc",
+         6: "epi.store", 7: "split.convert", 8: "prod.total", 9: "prod.wait_empty", 12: "mma.total", 13: "mma.wait_acc_free", 14: "mma.wait_A"}
+
+
+def run(shape, kind=A.CONV_TC16, **opts):
+    base = dict(tc_flush=10, tc_stages=0, tc_grid=0, tc_split=3, tc_mask_hi=1, tc_a_tmem=1, tc_diag=0, tc_comp_milli=270)
+    base.update(opts)
+    base["tc_diag"] |= 128
+    for k, v in base.items():
+        A.set_option(k, v)
+    d, keep = make_conv(kind, **shape)
+    ms = time_conv(d)
+    buf = np.zeros((148, 16), dtype=np.int64)
+    A.check(A.lib().demfi_tc_debug_read(buf.ctypes.data_as(C.POINTER(C.c_int64)), 148), "debug_read")
+    med = np.median(buf, axis=0)
+    print(json.dumps({"kind": kind, "shape": {k: v for k, v in shape.items()}, **opts, "ms": round(ms, 3),
+                      "kclk": {NAMES[i]: round(float(med[i]) / 1e3, 1) for i in NAMES}}), flush=True)
+    A.set_option("tc_diag", 0)
+
+
+if __name__ == "__main__":
+    s64 = dict(n=1, h=736, w=1280, srcC=[64], co=64, k=(3, 3))
+    rdb = dict(n=1, h=368, w=640, srcC=[192], co=32, k=(3, 3))
+    chr_ = dict(n=1, h=736, w=1280, srcC=[64, 64, 64], co=64, k=(7, 7))
+    run(s64, kind=A.CONV_TC)
+    run(s64)
+    run(s64, tc_flush=0)
+    run(s64, tc_diag=1)
+    run(rdb)
+    run(chr_)
