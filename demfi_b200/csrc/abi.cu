@@ -27,6 +27,7 @@ static std::atomic<int> g_opt_diag{0};
 static std::atomic<int> g_opt_comp{270};
 static std::atomic<int> g_opt_stages{0};  // diagnostics: cap on pipeline stages (0 = as many as fit)
 static std::atomic<int> g_opt_grid{0};    // diagnostics: cap on persistent CTAs (0 = one per SM)
+static std::atomic<int> g_opt_gen{3};     // DEMFI_CONV_TC16 kernel generation: 3 = conv_s3 where supported, 2 = conv_h3 only
 int get_option(const char* name) {
   if (!strcmp(name, "tc_mask_hi")) return g_opt_mask_hi.load();
   if (!strcmp(name, "tc_split")) return g_opt_split.load();
@@ -36,6 +37,7 @@ int get_option(const char* name) {
   if (!strcmp(name, "tc_comp_milli")) return g_opt_comp.load();
   if (!strcmp(name, "tc_a_tmem")) return g_opt_atmem.load();
   if (!strcmp(name, "tc_grid")) return g_opt_grid.load();
+  if (!strcmp(name, "tc_gen")) return g_opt_gen.load();
   return -1;
 }
 
@@ -97,6 +99,11 @@ int demfi_set_option(const char* name, int32_t value) {
   if (!strcmp(name, "tc_comp_milli")) { g_opt_comp.store(value); return 0; }
   if (!strcmp(name, "tc_a_tmem")) { g_opt_atmem.store(value ? 1 : 0); return 0; }
   if (!strcmp(name, "tc_grid")) { g_opt_grid.store(value < 0 ? 0 : value); return 0; }
+  if (!strcmp(name, "tc_gen")) {
+    DEMFI_REQUIRE(value == 2 || value == 3, "set_option: tc_gen must be 2 or 3");
+    g_opt_gen.store(value);
+    return 0;
+  }
   set_error("set_option: unknown option '%s'", name);
   return 1;
 }
@@ -177,7 +184,10 @@ int demfi_conv2d(const demfi_conv_t* c, void* stream) {
   }
   DEMFI_REQUIRE(c->wpack && c->bias, "conv2d: null weights");
   if (c->kind == DEMFI_CONV_TC) return launch_conv_tc(*c, (cudaStream_t)stream);
-  if (c->kind == DEMFI_CONV_TC16) return launch_conv_h3(*c, (cudaStream_t)stream);
+  if (c->kind == DEMFI_CONV_TC16) {
+    if (g_opt_gen.load() == 3 && s3_supports(*c)) return launch_conv_s3(*c, (cudaStream_t)stream);
+    return launch_conv_h3(*c, (cudaStream_t)stream);
+  }
   DEMFI_REQUIRE(c->kind == DEMFI_CONV_FFMA, "conv2d: unknown kind %d", c->kind);
   return launch_conv_ffma(*c, (cudaStream_t)stream);
 }

@@ -1,0 +1,739 @@
+// tcgen05 implicit-GEMM convolution, third generation ("s3"): the 3xFP16 scheme of conv_h3.cu
+//
+//   D_main += Ah * Bh            D_corr += Ah * Bl + Al * Bh          out = D_main + D_corr / 2048
+//
+// with BOTH operands read by the tensor core from shared memory (SS-form tcgen05.mma): no per-tap register
+// traffic at all.  ncu on conv_h3 (profiles/r1_conv_h3_profile.md) showed the L1/shared-memory data pipe at
+// ~80 % and the MMA issuer waiting for its A operand 53 % of the time: every tap of every chunk went
+// shared memory -> registers -> tensor memory through eight splitter warps, and the epilogue's per-thread
+// 16-byte global stores (one 32-byte sector each) were another 23 % of the pipe's wavefronts.
+//
+// Data flow per persistent CTA (one per SM), tile = 16 rows x 8 output pixels (M = 128), N block <= 96:
+//   * activations: ONE TMA box per 32-channel chunk covering the tile plus its halo {32 ch, 8+KW-1, 16+KH-1}
+//     (fp32, 128-byte rows = pixels).  Six converter warps split it ONCE, in place, into fp16 hi / lo and lay it
+//     out as the tensor core's un-swizzled K-major canonical layout: eight planes (4 x hi, 4 x lo) of
+//     [halo pixel][8 channels = 16 bytes].  In that layout a core matrix is 8 consecutive pixels x 16 bytes
+//     (128 contiguous bytes) and the 8-pixel groups of the M dimension are one halo row apart, so the A
+//     operand of tap (ky, kx) is the SAME buffer behind a descriptor whose start address is moved by
+//     (ky * halo_w + kx) * 16 bytes, with SBO = halo_w * 16 (next tile row) and LBO = one plane (next 8 channels).
+//     The tile is 8 pixels wide precisely so that every core matrix is one contiguous run of halo pixels.
+//   * weights: the pre-packed [Bh rows ; Bl rows] x 32 fp16 tiles of conv_h3 (64-byte swizzle).  When the whole
+//     filter bank of the N block fits beside the activation buffers (e.g. 64 -> 64 3x3: 144 KB) it is loaded once per
+//     CTA and stays resident; otherwise it streams through a ring, one (chunk, tap) stage at a time.
+//   * MMAs per (tap, 16 channels): Ah x [Bh;Bl] (N' = 2N: main | corr) and Al x Bh (-> corr), issued by one thread.
+//   * the K loop is cut into segments whose partial sums are drained from tensor memory (double-buffered) and
+//     added in fp32 RN by eight epilogue warps, with the gain compensation of the truncating tensor-core
+//     accumulation.
+//   * epilogue: for plain destinations (NHWC, pure activation, optional residual, all segments alike) the tile is
+//     staged in shared memory in the TMA 128-byte-swizzle box layout and written with cp.async.bulk.tensor
+//     stores (residual tiles are TMA-loaded into the same staging buffer first): whole 128-byte lines instead
+//     of one sector per thread.  Everything else (multi-activation heads, pixel shuffle, GRU) keeps the generic
+//     per-thread epilogue of common.cuh.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include <cstring>
+
+#include "common.cuh"
+
+namespace demfi {
+
+constexpr int S3_TH = 16, S3_TW = 8, S3_BM = 128, S3_KC = 32;
+constexpr int S3_CV_WARPS = 6, S3_EPI_WARPS = 8;
+constexpr int S3_CV_THREADS = S3_CV_WARPS * 32;
+constexpr int S3_EPI_THREADS = S3_EPI_WARPS * 32;
+constexpr int S3_THREADS = (S3_CV_WARPS + S3_EPI_WARPS + 2) * 32;  // 512: 0-5 convert, 6-13 epilogue, 14 TMA, 15 MMA
+constexpr int S3_MAX_NA = 3;   // halo-tile buffers
+constexpr int S3_MAX_NS = 8;   // weight ring
+constexpr int S3_MAX_PX = 2;   // halo pixels per converter thread (halo <= 384 pixels)
+constexpr int S3_BOX_BYTES = S3_BM * 128;  // one 32-channel staging box
+constexpr int S3_NBARS = 3 * S3_MAX_NA + 4 + 2 + 2 * S3_MAX_NS;
+constexpr float S3_LO_SCALE = 2048.0f;
+
+struct S3Params {
+  CUtensorMap tmap[DEMFI_MAX_SRC];  // activation sources
+  CUtensorMap omap[DEMFI_MAX_SEG];  // TMA epilogue: destination of each segment
+  CUtensorMap rmap;                 // TMA epilogue: residual operand (shared by all segments)
+  demfi_conv_t c;
+  int tiles_x, tiles_y, ntiles, n_blocks, nb_max;
+  int hw, hh, halo_px;
+  int a_bytes, na;
+  int b_bytes, ns, resident;
+  int b_off, stg_off, bar_off;  // byte offsets in (1024-aligned) shared memory
+  int acc_stride;
+  int taps, stages_per_tile, flush;
+  int tma_epi, tma_res;
+  float comp;
+  int diag;
+  long long* dbg;
+};
+
+namespace s3 {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// non-blocking probe (try_wait may suspend the thread for a system-dependent time: wrong tool for polling two queues)
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug becomes a trapped launch (reported error), never a hung GPU.
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 8000000000ll) {
+      printf("demfi conv_s3: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", (int)blockIdx.x,
+             (int)threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
+}
+__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, bool on, long long& acc) {
+  if (!on) { mbar_wait(bar, parity); return; }
+  const long long t = clock64();
+  mbar_wait(bar, parity);
+  acc += clock64() - t;
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// both operands from shared memory
+__device__ __forceinline__ void umma_f16_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// K-major shared-memory matrix descriptors.  Bits: start >> 4 in [0,14), LBO >> 4 in [16,30), SBO >> 4 in [32,46),
+// version 1 in [46,48), layout in [61,64).
+// B (weights): rows of 32 fp16 = 64 bytes, 64-byte swizzle (layout 4), SBO = 512 B between 8-row groups.
+__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
+}
+// A (activations): rows of 128 bytes = one halo pixel (Ah | Al), 128-byte swizzle (layout 2): the 16-byte chunks of the
+// row at byte address a are XOR-ed with bits [7,10) of a -- the pattern TMA wrote and the converter kept.  SBO =
+// distance between 8-row groups = one halo row.
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+// a = h + l / 2048 for two values: returns the packed fp16 pairs (low half = first value)
+__device__ __forceinline__ void split2(float a0, float a1, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a0, a1);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn((a0 - hf.x) * S3_LO_SCALE, (a1 - hf.y) * S3_LO_SCALE);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ float act_pure(int act, float v) {
+  if (act == DEMFI_ACT_RELU) return fmaxf(v, 0.0f);
+  if (act == DEMFI_ACT_TANH) return tanhf(v);
+  if (act == DEMFI_ACT_SIGMOID) return sigmoid_f(v);
+  return v;
+}
+}  // namespace s3
+using namespace s3;
+
+template <int NMAX>
+__global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_constant__ S3Params P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const demfi_conv_t& c = P.c;
+  const int NS = P.ns, NA = P.na;
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t b_base = smem_base + (uint32_t)P.b_off;
+  const uint32_t bars = smem_base + (uint32_t)P.bar_off;
+  auto bar_rawfull = [&](int a) { return bars + 8u * (uint32_t)a; };
+  auto bar_cvfull = [&](int a) { return bars + 8u * (uint32_t)(S3_MAX_NA + a); };
+  auto bar_aempty = [&](int a) { return bars + 8u * (uint32_t)(2 * S3_MAX_NA + a); };
+  auto bar_tfull = [&](int a) { return bars + 8u * (uint32_t)(3 * S3_MAX_NA + a); };
+  auto bar_tempty = [&](int a) { return bars + 8u * (uint32_t)(3 * S3_MAX_NA + 2 + a); };
+  const uint32_t bar_wfull = bars + 8u * (uint32_t)(3 * S3_MAX_NA + 4);
+  const uint32_t bar_resfull = bars + 8u * (uint32_t)(3 * S3_MAX_NA + 5);
+  auto bar_bfull = [&](int s) { return bars + 8u * (uint32_t)(3 * S3_MAX_NA + 6 + s); };
+  auto bar_bfree = [&](int s) { return bars + 8u * (uint32_t)(3 * S3_MAX_NA + 6 + S3_MAX_NS + s); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (size_t)P.bar_off + 8 * S3_NBARS);
+  auto n_of = [&](int nb) { return min(P.nb_max, c.cout_pad - nb * P.nb_max); };
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const bool dbg = P.dbg != nullptr;
+  const int chunks_per_tile = P.stages_per_tile / P.taps;
+
+  if (threadIdx.x == 0) {
+    for (int a = 0; a < S3_MAX_NA; ++a) {
+      mbar_init(bar_rawfull(a), 1);
+      mbar_init(bar_cvfull(a), S3_CV_WARPS);
+      mbar_init(bar_aempty(a), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull(a), 1);
+      mbar_init(bar_tempty(a), S3_EPI_WARPS);
+    }
+    mbar_init(bar_wfull, 1);
+    mbar_init(bar_resfull, 1);
+    for (int s = 0; s < S3_MAX_NS; ++s) {
+      mbar_init(bar_bfull(s), 1);
+      mbar_init(bar_bfree(s), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == S3_CV_WARPS + S3_EPI_WARPS + 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < S3_CV_WARPS) {
+    // ===== converter: fp32 halo tile -> fp16 hi / lo planes, in place =====
+    const int tid = (int)threadIdx.x;
+    long long w_raw = 0, w_cv = 0;
+    const long long t_begin = dbg ? clock64() : 0;
+    int abuf = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+      for (int ch = 0; ch < chunks_per_tile; ++ch) {
+        mbar_wait_t(bar_rawfull(abuf), aphase, dbg, w_raw);
+        const long long t_cv = dbg ? clock64() : 0;
+        const uint32_t a_addr = smem_base + (uint32_t)(abuf * P.a_bytes);
+#pragma unroll 1
+        for (int p = tid; p < P.halo_px; p += S3_CV_THREADS) {
+          // row = pixel: 32 fp32 -> [Ah 32 x fp16 | Al 32 x fp16], same 128 bytes, same 16-byte-chunk swizzle (chunk ^ (p & 7))
+          const uint32_t row = a_addr + (uint32_t)p * 128u;
+          const uint32_t sw = (uint32_t)p & 7u;
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint4 v = lds128(row + ((((uint32_t)j) ^ sw) << 4));
+            split2(__uint_as_float(v.x), __uint_as_float(v.y), hi[2 * j], lo[2 * j]);
+            split2(__uint_as_float(v.z), __uint_as_float(v.w), hi[2 * j + 1], lo[2 * j + 1]);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            sts128(row + ((((uint32_t)j) ^ sw) << 4), make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]));
+            sts128(row + ((((uint32_t)(j + 4)) ^ sw) << 4), make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]));
+          }
+        }
+        fence_async_smem();  // generic-proxy writes -> visible to the tensor core / TMA (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_cvfull(abuf));
+        if (dbg) w_cv += clock64() - t_cv;
+        if (++abuf == NA) { abuf = 0; aphase ^= 1u; }
+      }
+    }
+    if (dbg && threadIdx.x == 0) {
+      long long* d = P.dbg + (size_t)blockIdx.x * 16;
+      d[0] = clock64() - t_begin; d[1] = w_raw; d[7] = w_cv;
+    }
+  } else if (warp < S3_CV_WARPS + S3_EPI_WARPS) {
+    // ===== epilogue: TMEM lane = pixel row; a warp can only touch lanes 32*(warp%4)...  Group 0 takes accumulator
+    // columns [0, csplit), group 1 takes [csplit, N). =====
+    const int e_tid = (int)threadIdx.x - S3_CV_THREADS;
+    const int grp = (warp - S3_CV_WARPS) >> 2;
+    const int wq = warp & 3;
+    const int m = wq * 32 + lane;
+    constexpr int HMAX = (NMAX / 2 + 15) / 16 * 16;
+    int acc = 0;
+    uint32_t acc_phase = 0, res_phase = 0;
+    long long w_tfull = 0, w_store = 0;
+    const long long t_begin = dbg ? clock64() : 0;
+    const uint32_t stg = smem_base + (uint32_t)P.stg_off;
+    bool store_pending = false;
+    for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+      int t = tile;
+      const int nb = t % P.n_blocks;
+      t /= P.n_blocks;
+      const int tx0 = (t % P.tiles_x) * S3_TW;
+      t /= P.tiles_x;
+      const int ty0 = (t % P.tiles_y) * S3_TH;
+      const int n = t / P.tiles_y;
+      const int N = n_of(nb), n0 = nb * P.nb_max;
+      const int csplit = ((N / 2 + 15) / 16) * 16;
+      const int cbeg = grp ? csplit : 0, cnum = grp ? N - csplit : csplit;
+      const int oy = ty0 + (m >> 3), ox = tx0 + (m & 7);
+      const bool valid = (oy < c.H) && (ox < c.W);
+      const int nboxes = (N + 31) >> 5;
+      if (P.tma_epi) {
+        // the staging buffer is free once the previous tile's stores have read it; then fetch the residual tile
+        if (e_tid == 0) {
+          if (store_pending) bulk_wait_read0();
+          if (P.tma_res) {
+            mbar_arrive_expect_tx(bar_resfull, (uint32_t)(nboxes * S3_BOX_BYTES));
+            for (int b = 0; b < nboxes; ++b)
+              tma_load_4d(stg + (uint32_t)(b * S3_BOX_BYTES), &P.rmap, bar_resfull, n0 + 32 * b - c.seg[0].ch0, tx0, ty0, n);
+          }
+        }
+        store_pending = true;
+      }
+      float sum[HMAX];
+      bool first = true;
+      for (int done = 0; done < P.stages_per_tile; done += P.flush) {
+        const float gain = 1.0f + P.comp * (float)(2 * min(P.flush, P.stages_per_tile - done));
+        mbar_wait_t(bar_tfull(acc), acc_phase, dbg, w_tfull);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * P.acc_stride) + (uint32_t)cbeg;
+        uint32_t r[HMAX];
+#pragma unroll
+        for (int col = 0; col < HMAX; col += 16)
+          if (col < cnum) tmem_ld16_nowait(taddr + (uint32_t)col, r + col);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < HMAX; ++j) {
+          const float v = __uint_as_float(r[j]) * gain;
+          sum[j] = first ? v : sum[j] + v;
+        }
+#pragma unroll
+        for (int col = 0; col < HMAX; col += 16)
+          if (col < cnum) tmem_ld16_nowait(taddr + (uint32_t)(N + col), r + col);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < HMAX; ++j) sum[j] = fmaf(__uint_as_float(r[j]), 1.0f / S3_LO_SCALE, sum[j]);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        first = false;
+      }
+      const long long t_store = dbg ? clock64() : 0;
+      if (P.tma_epi) {
+        // ---- staged epilogue: bias (+ residual) + activation -> swizzled box layout -> TMA store ----
+        const int act = c.seg[0].act;
+        if (P.tma_res) {
+          mbar_wait(bar_resfull, res_phase);
+          res_phase ^= 1u;
+        } else {
+          asm volatile("bar.sync 2, %0;" ::"n"(S3_EPI_THREADS) : "memory");  // staging buffer released (thread 0 waited)
+        }
+        const uint32_t row = stg + (uint32_t)m * 128u;
+        const uint32_t sw = (uint32_t)m & 7u;
+#pragma unroll
+        for (int col = 0; col < HMAX; col += 4) {
+          if (col < cnum) {
+            const int chn = cbeg + col;  // channel within the N block
+            const uint32_t addr = row + (uint32_t)((chn >> 5) * S3_BOX_BYTES) + (((uint32_t)((chn & 31) >> 2) ^ sw) << 4);
+            const float4 b = ld4(c.bias + n0 + chn);
+            float4 v = make_float4(sum[col] + b.x, sum[col + 1] + b.y, sum[col + 2] + b.z, sum[col + 3] + b.w);
+            if (P.tma_res) {
+              const uint4 rr = lds128(addr);
+              v.x += __uint_as_float(rr.x); v.y += __uint_as_float(rr.y); v.z += __uint_as_float(rr.z); v.w += __uint_as_float(rr.w);
+            }
+            v.x = act_pure(act, v.x); v.y = act_pure(act, v.y); v.z = act_pure(act, v.z); v.w = act_pure(act, v.w);
+            sts128(addr, make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)));
+          }
+        }
+        fence_async_smem();
+        asm volatile("bar.sync 3, %0;" ::"n"(S3_EPI_THREADS) : "memory");
+        if (e_tid == 0 && !(P.diag & 1)) {
+          for (int sgi = 0; sgi < c.nseg; ++sgi) {
+            const demfi_seg_t& sg = c.seg[sgi];
+            for (int b = 0; b < nboxes; ++b) {
+              const int c_lo = n0 + 32 * b - sg.ch0;  // destination channel of the box's first channel
+              if (c_lo + 32 <= 0 || c_lo >= sg.nch) continue;
+              tma_store_4d(&P.omap[sgi], stg + (uint32_t)(b * S3_BOX_BYTES), c_lo, tx0, ty0, n);
+            }
+          }
+          bulk_commit();
+        }
+      } else if (valid && !(P.diag & 1)) {
+        const int ch_lo = n0 + cbeg, ch_hi = ch_lo + cnum;
+#pragma unroll 1
+        for (int sgi = 0; sgi < c.nseg; ++sgi) {
+          const demfi_seg_t& sg = c.seg[sgi];
+          if (sg.ch0 >= ch_hi || sg.ch0 + sg.nch <= ch_lo) continue;
+          const SegCursor cur = seg_cursor(c, sg, n, oy, ox);
+#pragma unroll
+          for (int col = 0; col < HMAX; col += 4) {
+            if (col < cnum) {
+              const float4 b = ld4(c.bias + ch_lo + col);
+              seg_emit4(cur, ch_lo + col, make_float4(sum[col] + b.x, sum[col + 1] + b.y, sum[col + 2] + b.z, sum[col + 3] + b.w));
+            }
+          }
+        }
+      }
+      if (dbg) w_store += clock64() - t_store;
+    }
+    if (P.tma_epi && e_tid == 0 && store_pending) bulk_wait0();  // stores complete before the CTA exits
+    if (dbg && e_tid == 0) {
+      long long* d = P.dbg + (size_t)blockIdx.x * 16;
+      d[4] = clock64() - t_begin; d[5] = w_tfull; d[6] = w_store;
+    }
+  } else if (warp == S3_CV_WARPS + S3_EPI_WARPS) {
+    // ===== TMA producer (one thread): halo tiles and, unless resident, the weight ring.  The two sequences are
+    // advanced by polling so that a full weight ring never delays the next halo tile. =====
+    if (elect_one()) {
+      const long long t_begin = dbg ? clock64() : 0;
+      const uint32_t a_tx = (uint32_t)(P.halo_px * 128);
+      if (P.resident) {
+        const uint32_t b_tx = (uint32_t)n_of(0) * 128u;
+        mbar_arrive_expect_tx(bar_wfull, b_tx * (uint32_t)P.stages_per_tile);
+        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(c.wpack);
+        for (int s = 0; s < P.stages_per_tile; ++s)
+          bulk_load(b_base + (uint32_t)(s * P.b_bytes), wsrc + (size_t)s * b_tx, b_tx, bar_wfull);
+      }
+      // A sequence state
+      int a_tile = blockIdx.x, a_src = 0, a_c0 = 0, abuf = 0;
+      uint32_t aphase = 0;
+      // B sequence state
+      int b_tile = P.resident ? P.ntiles : (int)blockIdx.x, b_stage = 0, slot = 0;
+      uint32_t sphase = 0;
+      while (a_tile < P.ntiles || b_tile < P.ntiles) {
+        if (a_tile < P.ntiles && mbar_test_wait(bar_aempty(abuf), aphase ^ 1u)) {
+          int t = a_tile / P.n_blocks;
+          const int tx0 = (t % P.tiles_x) * S3_TW - c.pad_w;
+          t /= P.tiles_x;
+          const int ty0 = (t % P.tiles_y) * S3_TH - c.pad_h;
+          const int n = t / P.tiles_y;
+          mbar_arrive_expect_tx(bar_rawfull(abuf), a_tx);
+          tma_load_4d(smem_base + (uint32_t)(abuf * P.a_bytes), &P.tmap[a_src], bar_rawfull(abuf), a_c0, tx0, ty0, n);
+          if (++abuf == NA) { abuf = 0; aphase ^= 1u; }
+          a_c0 += S3_KC;
+          if (a_c0 >= c.src[a_src].C) {
+            a_c0 = 0;
+            if (++a_src == c.nsrc) { a_src = 0; a_tile += gridDim.x; }
+          }
+        }
+        if (b_tile < P.ntiles && mbar_test_wait(bar_bfree(slot), sphase ^ 1u)) {
+          const int nb = b_tile % P.n_blocks;
+          const uint32_t b_tx = (uint32_t)n_of(nb) * 128u;  // 2N rows x 64 bytes
+          // packed weights: [n block][chunk][tap][2*N_block rows][32 fp16]; full blocks hold nb_max channels
+          const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(c.wpack) +
+                                (size_t)nb * (size_t)P.stages_per_tile * (size_t)P.nb_max * 128u + (size_t)b_stage * b_tx;
+          mbar_arrive_expect_tx(bar_bfull(slot), b_tx);
+          bulk_load(b_base + (uint32_t)(slot * P.b_bytes), wsrc, b_tx, bar_bfull(slot));
+          if (++slot == NS) { slot = 0; sphase ^= 1u; }
+          if (++b_stage == P.stages_per_tile) { b_stage = 0; b_tile += gridDim.x; }
+        }
+      }
+      if (dbg) {
+        long long* d = P.dbg + (size_t)blockIdx.x * 16;
+        d[8] = clock64() - t_begin;
+      }
+    }
+  } else {
+    // ===== MMA issuer: ONE thread runs the whole persistent loop =====
+    if (elect_one()) {
+      const uint32_t idesc0 = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(S3_BM >> 4) << 24);  // D=f32, A=B=f16, K-major, M=128
+      const uint64_t bdesc0 = make_desc_sw64(b_base);
+      const uint32_t bstep = (uint32_t)(P.b_bytes >> 4);
+      const uint64_t adesc0 = make_desc_sw128(smem_base, (uint32_t)P.hw * 128u);
+      const uint32_t astep = (uint32_t)(P.a_bytes >> 4);
+      const bool use_base_offset = (P.diag & 8) != 0;
+      long long w_tempty = 0, w_ready = 0;
+      const long long t_begin = dbg ? clock64() : 0;
+      uint32_t slot = 0, sphase = 0, acc = 0, acc_phase = 0, abuf = 0, aphase = 0;
+      if (P.resident) {
+        mbar_wait(bar_wfull, 0);
+        tc_fence_after();
+      }
+      for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+        const int N = n_of(tile % P.n_blocks);
+        const uint32_t idesc_n = idesc0 | ((uint32_t)(N >> 3) << 17);
+        const uint32_t idesc_2n = idesc0 | ((uint32_t)((2 * N) >> 3) << 17);
+        int done = 0, i = 0, seg_len = min(P.flush, P.stages_per_tile);
+        uint32_t d_main = 0, d_corr = 0;
+        uint32_t stage = 0;
+        for (int ch = 0; ch < chunks_per_tile; ++ch) {
+          mbar_wait_t(bar_cvfull(abuf), aphase, dbg, w_ready);
+          tc_fence_after();
+          const uint64_t a_chunk = adesc0 + (uint64_t)(astep * abuf);
+          int ky = 0, kx = 0;
+          for (int tap = 0; tap < P.taps; ++tap, ++stage) {
+            if (i == 0) {
+              mbar_wait_t(bar_tempty(acc), acc_phase ^ 1u, dbg, w_tempty);
+              tc_fence_after();
+              d_main = tmem_base + acc * (uint32_t)P.acc_stride;
+              d_corr = d_main + (uint32_t)N;
+            }
+            uint64_t bd;
+            if (P.resident) {
+              bd = bdesc0 + (uint64_t)(bstep * stage);
+            } else {
+              mbar_wait_t(bar_bfull(slot), sphase, dbg, w_ready);
+              tc_fence_after();
+              bd = bdesc0 + (uint64_t)(bstep * slot);
+            }
+            // A of this tap: the halo tile seen from pixel (ky, kx): rows (pixels) 128 bytes apart, bytes 0-63 Ah, 64-127 Al
+            uint64_t ah = a_chunk + (uint64_t)((uint32_t)(ky * P.hw + kx) << 3);
+            if (use_base_offset) ah |= (uint64_t)(((uint32_t)ah >> 3) & 7u) << 49;
+            umma_f16_ss(d_main, ah, bd, idesc_2n, i == 0 ? 0u : 1u);  // Ah x [Bh;Bl]  k 0..15
+            umma_f16_ss(d_main, ah + 2u, bd + 2u, idesc_2n, 1u);      //               k 16..31
+            umma_f16_ss(d_corr, ah + 4u, bd, idesc_n, 1u);            // Al x Bh
+            umma_f16_ss(d_corr, ah + 6u, bd + 2u, idesc_n, 1u);
+            if (!P.resident) {
+              umma_commit(bar_bfree(slot));
+              if (++slot == (uint32_t)NS) { slot = 0; sphase ^= 1u; }
+            }
+            if (++i == seg_len) {
+              umma_commit(bar_tfull(acc));
+              acc ^= 1u;
+              if (acc == 0) acc_phase ^= 1u;
+              done += seg_len;
+              seg_len = min(P.flush, P.stages_per_tile - done);
+              i = 0;
+            }
+            if (++kx == c.KW) { kx = 0; ++ky; }
+          }
+          umma_commit(bar_aempty(abuf));
+          if (++abuf == (uint32_t)NA) { abuf = 0; aphase ^= 1u; }
+        }
+      }
+      if (dbg) {
+        long long* d = P.dbg + (size_t)blockIdx.x * 16;
+        d[12] = clock64() - t_begin; d[13] = w_tempty; d[14] = w_ready;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == S3_CV_WARPS + S3_EPI_WARPS + 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// ---- host --------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn s3_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+static int s3_num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+static int s3_nb_max(int cout_pad) { return cout_pad <= 96 ? cout_pad : 64; }  // same N blocking as conv_h3 (shared weight layout)
+constexpr int S3_SMEM_MAX = 227 * 1024;
+
+// all segments plain and alike: NHWC store, a pure activation, the same channel range and the same (optional) residual
+static bool s3_uniform_segments(const demfi_conv_t& c) {
+  const demfi_seg_t& a = c.seg[0];
+  for (int s = 0; s < c.nseg; ++s) {
+    const demfi_seg_t& g = c.seg[s];
+    if (g.store != DEMFI_STORE_NHWC || g.act > DEMFI_ACT_SIGMOID) return false;
+    if (g.act != a.act || g.ch0 != a.ch0 || g.nch != a.nch || g.res != a.res || g.res_ld != a.res_ld) return false;
+  }
+  return true;
+}
+
+bool s3_supports(const demfi_conv_t& c) {
+  if (c.stride != 1) return false;
+  if (c.cout_pad % 16 != 0 || c.cout_pad < 16 || c.cout_pad > 256) return false;
+  for (int s = 0; s < c.nsrc; ++s)
+    if (c.src[s].up != 0) return false;
+  const int hw = S3_TW + c.KW - 1, hh = S3_TH + c.KH - 1;
+  if (hw > 256 || hh > 256 || hw * hh > S3_MAX_PX * S3_CV_THREADS) return false;
+  const int a_bytes = (hw * hh * 128 + 1023) / 1024 * 1024;
+  const int nbm = s3_nb_max(c.cout_pad);
+  const int b_bytes = 2 * nbm * 64;
+  const int stg = ((nbm + 31) / 32) * S3_BOX_BYTES;
+  return 2 * a_bytes + 4 * b_bytes + stg + 2048 <= S3_SMEM_MAX;
+}
+
+static int s3_encode(EncodeTiledFn enc, CUtensorMap* map, const float* ptr, int C_, int ld, int W, int H, int N, int bw, int bh,
+                     const char* what) {
+  cuuint64_t dims[4] = {(cuuint64_t)C_, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 4, (cuuint64_t)ld * 4 * W, (cuuint64_t)ld * 4 * W * H};
+  cuuint32_t box[4] = {S3_KC, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DEMFI_REQUIRE(r == CUDA_SUCCESS, "conv_s3: cuTensorMapEncodeTiled failed for %s (CUresult %d)", what, (int)r);
+  return 0;
+}
+
+int launch_conv_s3(const demfi_conv_t& c, cudaStream_t st) {
+  DEMFI_REQUIRE(s3_supports(c), "conv_s3: unsupported convolution (stride %d, cout_pad %d, %dx%d)", c.stride, c.cout_pad, c.KH, c.KW);
+  DEMFI_REQUIRE(c.Hi + 2 * c.pad_h - c.KH + 1 == c.H && c.Wi + 2 * c.pad_w - c.KW + 1 == c.W, "conv_s3: inconsistent sizes");
+  EncodeTiledFn enc = s3_encode_fn();
+  DEMFI_REQUIRE(enc != nullptr, "conv_s3: cuTensorMapEncodeTiled not available from the driver");
+  static thread_local S3Params P;  // CUtensorMap needs 64-byte alignment; thread_local storage gives it
+  memset(&P, 0, sizeof(P));
+  P.c = c;
+  P.hw = S3_TW + c.KW - 1;
+  P.hh = S3_TH + c.KH - 1;
+  P.halo_px = P.hw * P.hh;
+  for (int s = 0; s < c.nsrc; ++s)
+    if (s3_encode(enc, &P.tmap[s], c.src[s].ptr, c.src[s].C, c.src[s].ld, c.Wi, c.Hi, c.N, P.hw, P.hh, "a source")) return 1;
+  P.tiles_x = (c.W + S3_TW - 1) / S3_TW;
+  P.tiles_y = (c.H + S3_TH - 1) / S3_TH;
+  const long long nt = (long long)P.tiles_x * P.tiles_y * c.N;
+  P.nb_max = s3_nb_max(c.cout_pad);
+  P.n_blocks = (c.cout_pad + P.nb_max - 1) / P.nb_max;
+  DEMFI_REQUIRE(nt > 0 && nt * P.n_blocks < (1ll << 31), "conv_s3: bad tile count");
+  P.ntiles = (int)nt * P.n_blocks;
+  P.a_bytes = (P.halo_px * 128 + 1023) / 1024 * 1024;
+  P.b_bytes = 2 * P.nb_max * 64;
+  P.acc_stride = 2 * P.nb_max;
+  P.taps = c.KH * c.KW;
+  int chunks = 0;
+  for (int s = 0; s < c.nsrc; ++s) chunks += (c.src[s].C + S3_KC - 1) / S3_KC;
+  P.stages_per_tile = chunks * P.taps;
+
+  // epilogue mode
+  P.tma_epi = (s3_uniform_segments(c) && !(get_option("tc_diag") & 2)) ? 1 : 0;
+  P.tma_res = (P.tma_epi && c.seg[0].res != nullptr) ? 1 : 0;
+  const int stg_bytes = P.tma_epi ? ((P.nb_max + 31) / 32) * S3_BOX_BYTES : 0;
+  if (P.tma_epi) {
+    for (int s = 0; s < c.nseg; ++s)
+      if (s3_encode(enc, &P.omap[s], c.seg[s].dst, c.seg[s].nch, c.seg[s].dst_ld, c.W, c.H, c.N, S3_TW, S3_TH, "a destination")) return 1;
+    if (P.tma_res)
+      if (s3_encode(enc, &P.rmap, c.seg[0].res, c.seg[0].nch, c.seg[0].res_ld, c.W, c.H, c.N, S3_TW, S3_TH, "the residual")) return 1;
+  }
+
+  // shared-memory plan: [A buffers][weights: resident bank or ring][staging][barriers]
+  const int fixed = stg_bytes + 8 * S3_NBARS + 16 + 1024;
+  const int bank = P.stages_per_tile * P.b_bytes;
+  P.resident = (P.n_blocks == 1 && 2 * P.a_bytes + bank + fixed <= S3_SMEM_MAX && !(get_option("tc_diag") & 4)) ? 1 : 0;
+  if (P.resident) {
+    P.ns = 0;
+    P.na = (3 * P.a_bytes + bank + fixed <= S3_SMEM_MAX) ? 3 : 2;
+  } else {
+    P.na = 3;
+    int ns = S3_MAX_NS;
+    while (ns > 2 && P.na * P.a_bytes + ns * P.b_bytes + fixed > S3_SMEM_MAX) --ns;
+    if (P.na * P.a_bytes + ns * P.b_bytes + fixed > S3_SMEM_MAX) P.na = 2;
+    {
+      const int cap = get_option("tc_stages");
+      if (cap >= 2 && cap < ns) ns = cap;
+    }
+    DEMFI_REQUIRE(P.na * P.a_bytes + ns * P.b_bytes + fixed <= S3_SMEM_MAX, "conv_s3: shared-memory plan does not fit");
+    P.ns = ns;
+  }
+  P.b_off = P.na * P.a_bytes;
+  P.stg_off = P.b_off + (P.resident ? bank : P.ns * P.b_bytes);
+  P.stg_off = (P.stg_off + 1023) & ~1023;
+  P.bar_off = P.stg_off + stg_bytes;
+  const int smem = P.bar_off + 8 * S3_NBARS + 16 + 1024;
+  DEMFI_REQUIRE(smem <= S3_SMEM_MAX + 1024, "conv_s3: shared-memory plan (%d bytes) does not fit", smem);
+
+  P.flush = get_option("tc_flush");
+  if (P.flush <= 0 || P.flush > P.stages_per_tile) P.flush = P.stages_per_tile;
+  {  // balanced segments
+    const int nseg = (P.stages_per_tile + P.flush - 1) / P.flush;
+    P.flush = (P.stages_per_tile + nseg - 1) / nseg;
+  }
+  P.comp = (float)get_option("tc_comp_milli") * 1e-3f * 5.9604645e-8f;
+  P.diag = get_option("tc_diag") & (1 | 8 | 128);
+  if (P.diag & 128) {
+    long long* buf = tc_debug_buffer(st);
+    DEMFI_REQUIRE(buf != nullptr, "conv_s3: cannot allocate the role-timer buffer");
+    P.dbg = buf;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    const void* fns[] = {(const void*)conv_s3_kernel<32>, (const void*)conv_s3_kernel<64>, (const void*)conv_s3_kernel<96>};
+    for (const void* f : fns) {
+      cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, S3_SMEM_MAX);
+      DEMFI_REQUIRE(e == cudaSuccess, "conv_s3: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
+    }
+    attr_set = true;
+  }
+  int grid = P.ntiles < s3_num_sms() ? P.ntiles : s3_num_sms();
+  if (get_option("tc_grid") > 0 && get_option("tc_grid") < grid) grid = get_option("tc_grid");
+  if (P.nb_max <= 32) conv_s3_kernel<32><<<grid, S3_THREADS, smem, st>>>(P);
+  else if (P.nb_max <= 64) conv_s3_kernel<64><<<grid, S3_THREADS, smem, st>>>(P);
+  else conv_s3_kernel<96><<<grid, S3_THREADS, smem, st>>>(P);
+  DEMFI_LAUNCH_CHECK("conv_s3");
+  return 0;
+}
+
+}  // namespace demfi

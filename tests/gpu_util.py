@@ -7,6 +7,7 @@ import torch
 from demfi_b200 import _abi as A
 
 DEV = torch.device("cuda:0")
+CONV_TC16_H3 = 102  # test-only pseudo kind: DEMFI_CONV_TC16 forced onto the second-generation kernel (tc_gen = 2)
 
 
 def nhwc(t_nchw, ld=None):
@@ -31,6 +32,9 @@ def run_conv(w, b, srcs, out_hw, kind, segs_spec, stride=1, pad=None, in_map=Non
     segs_spec: [dict(ch0, nch, dst=buffer [N,Ho',Wo',ld], act, res=buffer, res2=buffer, store)].
     Returns nothing (dst buffers are written)."""
     lib = A.lib()
+    A.set_option("tc_gen", 2 if kind == CONV_TC16_H3 else 3)
+    if kind == CONV_TC16_H3:
+        kind = A.CONV_TC16
     Co, Ci, KH, KW = w.shape
     if pad is None:
         pad = (KH // 2, KW // 2)
@@ -70,6 +74,9 @@ def run_conv(w, b, srcs, out_hw, kind, segs_spec, stride=1, pad=None, in_map=Non
         if sg.get("res2") is not None:
             s.res2, s.res2_ld = sg["res2"].data_ptr(), sg["res2"].shape[3]
     d.wpack, d.bias = wdev.data_ptr(), bdev.data_ptr()
-    A.check(lib.demfi_conv2d(C.byref(d), stream()), "conv2d")
-    torch.cuda.synchronize()
+    try:
+        A.check(lib.demfi_conv2d(C.byref(d), stream()), "conv2d")
+        torch.cuda.synchronize()
+    finally:
+        A.set_option("tc_gen", 3)
     return wdev, bdev

@@ -9,10 +9,11 @@ import torch
 import torch.nn.functional as F
 
 from demfi_b200 import _abi as A
-from gpu_util import DEV, from_nhwc, nhwc, run_conv
+from gpu_util import CONV_TC16_H3, DEV, from_nhwc, nhwc, run_conv
 
 pytestmark = pytest.mark.gpu
-KINDS = [pytest.param(A.CONV_FFMA, id="ffma"), pytest.param(A.CONV_TC, id="tc"), pytest.param(A.CONV_TC16, id="tc16")]
+KINDS = [pytest.param(A.CONV_FFMA, id="ffma"), pytest.param(A.CONV_TC, id="tc"), pytest.param(CONV_TC16_H3, id="tc16-h3"),
+         pytest.param(A.CONV_TC16, id="tc16-s3")]
 TOL = 2e-5  # max-abs relative to max(1, max|ref|): fp32 conv noise level (ref self-noise 2-3e-5)
 
 
@@ -229,7 +230,8 @@ def test_ffma_upsample_concat():
     check(from_nhwc(out, 64), F.relu(ref_conv(torch.cat([up, sk], 1), w, b)), "dec2 up+cat")
 
 
-@pytest.mark.parametrize("kind", [pytest.param(A.CONV_FFMA, id="ffma"), pytest.param(A.CONV_TC16, id="tc16")])
+@pytest.mark.parametrize("kind", [pytest.param(A.CONV_FFMA, id="ffma"), pytest.param(CONV_TC16_H3, id="tc16-h3"),
+                                  pytest.param(A.CONV_TC16, id="tc16-s3")])
 def test_tiny_cin_7x7(kind):
     n, h, w_ = 1, 24, 24
     x = rnd(n, 5, h, w_, seed=63)

@@ -11,7 +11,7 @@ NAMES = {0: "split.total", 1: "split.wait_full", 2: "split.wait_aslot", 3: "spli
 
 
 def run(shape, kind=A.CONV_TC16, **opts):
-    base = dict(tc_flush=10, tc_stages=0, tc_grid=0, tc_split=3, tc_mask_hi=1, tc_a_tmem=1, tc_diag=0, tc_comp_milli=270)
+    base = dict(tc_flush=10, tc_stages=0, tc_grid=0, tc_split=3, tc_mask_hi=1, tc_a_tmem=1, tc_diag=0, tc_comp_milli=270, tc_gen=3)
     base.update(opts)
     base["tc_diag"] |= 128
     for k, v in base.items():
@@ -30,9 +30,13 @@ if __name__ == "__main__":
     s64 = dict(n=1, h=736, w=1280, srcC=[64], co=64, k=(3, 3))
     rdb = dict(n=1, h=368, w=640, srcC=[192], co=32, k=(3, 3))
     chr_ = dict(n=1, h=736, w=1280, srcC=[64, 64, 64], co=64, k=(7, 7))
-    run(s64, kind=A.CONV_TC)
+    gru = dict(n=1, h=736, w=1280, srcC=[64, 64], co=128, k=(1, 5))
+    run(s64, tc_gen=2)
     run(s64)
+    run(s64, tc_diag=4)   # weights streamed instead of resident
+    run(s64, tc_diag=2)   # generic per-thread epilogue instead of the TMA store
+    run(s64, tc_diag=1)   # no stores
     run(s64, tc_flush=0)
-    run(s64, tc_diag=1)
     run(rdb)
     run(chr_)
+    run(gru)
