@@ -59,6 +59,7 @@ struct S3Params {
   int hw, hh, halo_px;
   int a_bytes, na;
   int b_bytes, ns, resident;
+  int gtaps;  // weight ring: (chunk, tap) stages per ring slot, fetched with ONE bulk copy and ONE barrier round trip
   int b_off, stg_off, bar_off;  // byte offsets in (1024-aligned) shared memory
   int acc_stride;
   int taps, stages_per_tile, flush;
@@ -160,6 +161,18 @@ __device__ __forceinline__ void umma_f16_ss(uint32_t d_tmem, uint64_t adesc, uin
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// descriptors passed as (low, high) 32-bit halves: only the low word (start address) ever changes
+__device__ __forceinline__ void umma_f16_ss2(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                             uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accum)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -278,7 +291,7 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
         const long long t_cv = dbg ? clock64() : 0;
         const uint32_t a_addr = smem_base + (uint32_t)(abuf * P.a_bytes);
 #pragma unroll 1
-        for (int p = tid; p < P.halo_px; p += S3_CV_THREADS) {
+        for (int p = (P.diag & 16) ? P.halo_px : tid; p < P.halo_px; p += S3_CV_THREADS) {
           // row = pixel: 32 fp32 -> [Ah 32 x fp16 | Al 32 x fp16], same 128 bytes, same 16-byte-chunk swizzle (chunk ^ (p & 7))
           const uint32_t row = a_addr + (uint32_t)p * 128u;
           const uint32_t sw = (uint32_t)p & 7u;
@@ -389,7 +402,7 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
         const uint32_t sw = (uint32_t)m & 7u;
 #pragma unroll
         for (int col = 0; col < HMAX; col += 4) {
-          if (col < cnum) {
+          if (col < cnum && !(P.diag & 32)) {
             const int chn = cbeg + col;  // channel within the N block
             const uint32_t addr = row + (uint32_t)((chn >> 5) * S3_BOX_BYTES) + (((uint32_t)((chn & 31) >> 2) ^ sw) << 4);
             const float4 b = ld4(c.bias + n0 + chn);
@@ -404,7 +417,7 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
         }
         fence_async_smem();
         asm volatile("bar.sync 3, %0;" ::"n"(S3_EPI_THREADS) : "memory");
-        if (e_tid == 0 && !(P.diag & 1)) {
+        if (e_tid == 0 && !(P.diag & (1 | 32))) {
           for (int sgi = 0; sgi < c.nseg; ++sgi) {
             const demfi_seg_t& sg = c.seg[sgi];
             for (int b = 0; b < nboxes; ++b) {
@@ -475,14 +488,17 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
         }
         if (b_tile < P.ntiles && mbar_test_wait(bar_bfree(slot), sphase ^ 1u)) {
           const int nb = b_tile % P.n_blocks;
-          const uint32_t b_tx = (uint32_t)n_of(nb) * 128u;  // 2N rows x 64 bytes
-          // packed weights: [n block][chunk][tap][2*N_block rows][32 fp16]; full blocks hold nb_max channels
+          const uint32_t b_tx = (uint32_t)n_of(nb) * 128u;  // one stage: 2N rows x 64 bytes
+          const int len = min(P.gtaps, P.stages_per_tile - b_stage);
+          // packed weights: [n block][chunk][tap][2*N_block rows][32 fp16]; full blocks hold nb_max channels.  The stages of a
+          // group are consecutive in that order, so the group is one contiguous copy.
           const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(c.wpack) +
                                 (size_t)nb * (size_t)P.stages_per_tile * (size_t)P.nb_max * 128u + (size_t)b_stage * b_tx;
-          mbar_arrive_expect_tx(bar_bfull(slot), b_tx);
-          bulk_load(b_base + (uint32_t)(slot * P.b_bytes), wsrc, b_tx, bar_bfull(slot));
+          mbar_arrive_expect_tx(bar_bfull(slot), b_tx * (uint32_t)len);
+          bulk_load(b_base + (uint32_t)(slot * P.gtaps * P.b_bytes), wsrc, b_tx * (uint32_t)len, bar_bfull(slot));
           if (++slot == NS) { slot = 0; sphase ^= 1u; }
-          if (++b_stage == P.stages_per_tile) { b_stage = 0; b_tile += gridDim.x; }
+          b_stage += len;
+          if (b_stage == P.stages_per_tile) { b_stage = 0; b_tile += gridDim.x; }
         }
       }
       if (dbg) {
@@ -491,18 +507,26 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
       }
     }
   } else {
-    // ===== MMA issuer: ONE thread runs the whole persistent loop =====
+    // ===== MMA issuer: ONE thread runs the whole persistent loop.
+    // Measured (tools/mma_probe.cu and this kernel): the tensor pipe runs only 1-2 MMAs ahead of the issuing thread, so
+    // every instruction between two tcgen05.mma is serial with the math (a first version with ~75 instructions of
+    // bookkeeping per stage ran at 411 clk/stage against 224 clk of MMA work).  Hence: all bookkeeping (accumulator
+    // hand-over, segment ends, chunk ends) sits OUTSIDE the innermost loop, which issues a run of consecutive taps with
+    // nothing but 32-bit adds on the low descriptor words (the high words -- SBO, version, swizzle -- never change). =====
     if (elect_one()) {
       const uint32_t idesc0 = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(S3_BM >> 4) << 24);  // D=f32, A=B=f16, K-major, M=128
-      const uint64_t bdesc0 = make_desc_sw64(b_base);
-      const uint32_t bstep = (uint32_t)(P.b_bytes >> 4);
-      const uint64_t adesc0 = make_desc_sw128(smem_base, (uint32_t)P.hw * 128u);
-      const uint32_t astep = (uint32_t)(P.a_bytes >> 4);
-      const bool use_base_offset = (P.diag & 8) != 0;
+      const uint32_t a_hi = (uint32_t)(make_desc_sw128(0u, (uint32_t)P.hw * 128u) >> 32);
+      const uint32_t b_hi = (uint32_t)(make_desc_sw64(0u) >> 32);
+      const uint32_t a_lo0 = ((smem_base >> 4) & 0x3FFFu) | (1u << 16);
+      const uint32_t b_lo0 = (b_base >> 4) & 0x3FFFu;
+      const uint32_t astep = (uint32_t)(P.a_bytes >> 4), gstep = (uint32_t)((P.gtaps * P.b_bytes) >> 4);
+      const uint32_t row_skip = (uint32_t)(P.hw - c.KW) << 3;  // extra step from the last tap of a kernel row to the next row
+      const int KW = c.KW, taps = P.taps;
+      const bool resident = P.resident != 0;
       long long w_tempty = 0, w_ready = 0;
       const long long t_begin = dbg ? clock64() : 0;
       uint32_t slot = 0, sphase = 0, acc = 0, acc_phase = 0, abuf = 0, aphase = 0;
-      if (P.resident) {
+      if (resident) {
         mbar_wait(bar_wfull, 0);
         tc_fence_after();
       }
@@ -510,49 +534,61 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
         const int N = n_of(tile % P.n_blocks);
         const uint32_t idesc_n = idesc0 | ((uint32_t)(N >> 3) << 17);
         const uint32_t idesc_2n = idesc0 | ((uint32_t)((2 * N) >> 3) << 17);
-        int done = 0, i = 0, seg_len = min(P.flush, P.stages_per_tile);
+        const uint32_t bstep = (uint32_t)N << 3;  // one stage = 2N rows x 64 bytes, in 16-byte units
+        int done = 0, fill = 0, seg_len = min(P.flush, P.stages_per_tile);
+        int issued = 0, gleft = resident ? P.stages_per_tile : 0;
         uint32_t d_main = 0, d_corr = 0;
-        uint32_t stage = 0;
+        uint32_t b = b_lo0;  // resident bank: stage after stage
+#pragma unroll 1
         for (int ch = 0; ch < chunks_per_tile; ++ch) {
           mbar_wait_t(bar_cvfull(abuf), aphase, dbg, w_ready);
           tc_fence_after();
-          const uint64_t a_chunk = adesc0 + (uint64_t)(astep * abuf);
-          int ky = 0, kx = 0;
-          for (int tap = 0; tap < P.taps; ++tap, ++stage) {
-            if (i == 0) {
+          uint32_t a = a_lo0 + astep * abuf;
+          int kx = 0, tap = 0;
+#pragma unroll 1
+          while (tap < taps) {
+            uint32_t accum = 1u;
+            if (fill == 0) {
               mbar_wait_t(bar_tempty(acc), acc_phase ^ 1u, dbg, w_tempty);
               tc_fence_after();
               d_main = tmem_base + acc * (uint32_t)P.acc_stride;
               d_corr = d_main + (uint32_t)N;
+              accum = 0u;
             }
-            uint64_t bd;
-            if (P.resident) {
-              bd = bdesc0 + (uint64_t)(bstep * stage);
-            } else {
+            if (gleft == 0) {  // next group of the weight ring
               mbar_wait_t(bar_bfull(slot), sphase, dbg, w_ready);
               tc_fence_after();
-              bd = bdesc0 + (uint64_t)(bstep * slot);
+              gleft = min(P.gtaps, P.stages_per_tile - issued);
+              b = b_lo0 + gstep * slot;
             }
-            // A of this tap: the halo tile seen from pixel (ky, kx): rows (pixels) 128 bytes apart, bytes 0-63 Ah, 64-127 Al
-            uint64_t ah = a_chunk + (uint64_t)((uint32_t)(ky * P.hw + kx) << 3);
-            if (use_base_offset) ah |= (uint64_t)(((uint32_t)ah >> 3) & 7u) << 49;
-            umma_f16_ss(d_main, ah, bd, idesc_2n, i == 0 ? 0u : 1u);  // Ah x [Bh;Bl]  k 0..15
-            umma_f16_ss(d_main, ah + 2u, bd + 2u, idesc_2n, 1u);      //               k 16..31
-            umma_f16_ss(d_corr, ah + 4u, bd, idesc_n, 1u);            // Al x Bh
-            umma_f16_ss(d_corr, ah + 6u, bd + 2u, idesc_n, 1u);
-            if (!P.resident) {
+            const int run = min(min(taps - tap, seg_len - fill), gleft);
+#pragma unroll 1
+            for (int t = 0; t < run; ++t) {
+              umma_f16_ss2(d_main, a, a_hi, b, b_hi, idesc_2n, accum);         // Ah x [Bh;Bl]  k 0..15
+              umma_f16_ss2(d_main, a + 2u, a_hi, b + 2u, b_hi, idesc_2n, 1u);  //               k 16..31
+              umma_f16_ss2(d_corr, a + 4u, a_hi, b, b_hi, idesc_n, 1u);        // Al x Bh
+              umma_f16_ss2(d_corr, a + 6u, a_hi, b + 2u, b_hi, idesc_n, 1u);
+              accum = 1u;
+              b += bstep;
+              a += 8u;
+              if (++kx == KW) { kx = 0; a += row_skip; }
+            }
+            tap += run;
+            fill += run;
+            issued += run;
+            gleft -= run;
+            if (!resident && gleft == 0) {
               umma_commit(bar_bfree(slot));
               if (++slot == (uint32_t)NS) { slot = 0; sphase ^= 1u; }
             }
-            if (++i == seg_len) {
+            if (fill == seg_len) {
               umma_commit(bar_tfull(acc));
               acc ^= 1u;
               if (acc == 0) acc_phase ^= 1u;
               done += seg_len;
               seg_len = min(P.flush, P.stages_per_tile - done);
-              i = 0;
+              fill = 0;
             }
-            if (++kx == c.KW) { kx = 0; ++ky; }
           }
           umma_commit(bar_aempty(abuf));
           if (++abuf == (uint32_t)NA) { abuf = 0; aphase ^= 1u; }
@@ -685,21 +721,34 @@ int launch_conv_s3(const demfi_conv_t& c, cudaStream_t st) {
   P.resident = (P.n_blocks == 1 && 2 * P.a_bytes + bank + fixed <= S3_SMEM_MAX && !(get_option("tc_diag") & 4)) ? 1 : 0;
   if (P.resident) {
     P.ns = 0;
+    P.gtaps = P.stages_per_tile;
     P.na = (3 * P.a_bytes + bank + fixed <= S3_SMEM_MAX) ? 3 : 2;
   } else {
+    // ring of `ns` slots, each a group of `gtaps` consecutive stages (target <= 24 KB per slot, >= 3 slots)
     P.na = 3;
-    int ns = S3_MAX_NS;
-    while (ns > 2 && P.na * P.a_bytes + ns * P.b_bytes + fixed > S3_SMEM_MAX) --ns;
-    if (P.na * P.a_bytes + ns * P.b_bytes + fixed > S3_SMEM_MAX) P.na = 2;
+    int g = 24576 / P.b_bytes;
+    if (g < 1) g = 1;
+    if (g > P.stages_per_tile) g = P.stages_per_tile;
     {
-      const int cap = get_option("tc_stages");
-      if (cap >= 2 && cap < ns) ns = cap;
+      const int cap = get_option("tc_stages");  // diagnostics: stages per ring slot
+      if (cap >= 1 && cap < g) g = cap;
     }
-    DEMFI_REQUIRE(P.na * P.a_bytes + ns * P.b_bytes + fixed <= S3_SMEM_MAX, "conv_s3: shared-memory plan does not fit");
+    int ns = 4;
+    auto fits = [&](int na_, int ns_, int g_) { return na_ * P.a_bytes + ns_ * g_ * P.b_bytes + fixed <= S3_SMEM_MAX; };
+    while (!fits(P.na, ns, g)) {
+      if (ns > 3) --ns;
+      else if (g > 2) --g;
+      else if (P.na > 2) --P.na;
+      else if (ns > 2) --ns;
+      else if (g > 1) --g;
+      else break;
+    }
+    DEMFI_REQUIRE(fits(P.na, ns, g), "conv_s3: shared-memory plan does not fit");
     P.ns = ns;
+    P.gtaps = g;
   }
   P.b_off = P.na * P.a_bytes;
-  P.stg_off = P.b_off + (P.resident ? bank : P.ns * P.b_bytes);
+  P.stg_off = P.b_off + (P.resident ? bank : P.ns * P.gtaps * P.b_bytes);
   P.stg_off = (P.stg_off + 1023) & ~1023;
   P.bar_off = P.stg_off + stg_bytes;
   const int smem = P.bar_off + 8 * S3_NBARS + 16 + 1024;
@@ -712,7 +761,7 @@ int launch_conv_s3(const demfi_conv_t& c, cudaStream_t st) {
     P.flush = (P.stages_per_tile + nseg - 1) / nseg;
   }
   P.comp = (float)get_option("tc_comp_milli") * 1e-3f * 5.9604645e-8f;
-  P.diag = get_option("tc_diag") & (1 | 8 | 128);
+  P.diag = get_option("tc_diag") & (1 | 16 | 32 | 128);
   if (P.diag & 128) {
     long long* buf = tc_debug_buffer(st);
     DEMFI_REQUIRE(buf != nullptr, "conv_s3: cannot allocate the role-timer buffer");

@@ -97,6 +97,9 @@ __global__ void __launch_bounds__(128 + 256, 1) probe(int N1, int N2, int iters,
           uint32_t ta = tmem + 448u + buf * 32u, d1 = tmem, d2 = tmem + 256u;
           if (mode & 1) { d1 = tmem + (uint32_t)((i / 9) & 1) * 128u; d2 = d1 + (uint32_t)N2; ta = tmem + 256u + (uint32_t)(i & 3) * 64u; }
           if (mode & 2) bd = make_desc_sw128(sb + (uint32_t)(i % 6) * 32768u + 16384u);
+          // conv_s3-like operands: A = shifted window into a halo tile (start not 1024-aligned, SBO = 10 rows), B = 64-byte swizzle
+          if (mode & 32) ad = (uint64_t)(((sb + buf * A_BYTES + (uint32_t)(i % 9) * 384u) >> 4) & 0x3FFF) | ((uint64_t)(1280 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+          if (mode & 64) bd = (uint64_t)(((sb + NBUF * A_BYTES + buf * B_BYTES) >> 4) & 0x3FFF) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
           const uint32_t ta2 = (mode & 1) ? ta + 32u : ta;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
@@ -204,6 +207,11 @@ int main(int argc, char**) {
   long long* dcyc;
   cudaMalloc(&dcyc, sms * sizeof(long long));
   const int cfg[][2] = {{64, 0}, {128, 0}, {256, 0}, {32, 0}, {128, 64}, {64, 32}, {192, 96}, {256, 128}, {64, 64}, {96, 96}};
+  if (argc > 2) {  // conv_s3-like SS operands: 32 shifted-window A, 64 SW64 B
+    for (int mode : {0, 32, 64, 96}) run<1, false>(128, 64, sms, dcyc, mode);
+    for (int mode : {0, 32, 64, 96}) run<1, false>(256, 128, sms, dcyc, mode);
+    return 0;
+  }
   if (argc > 1) {  // interference modes: 1 kernel-like TMEM layout, 2 six rotating B buffers, 4 kernel-like issue pattern,
                    // 8 concurrent tcgen05.ld warps, 16 two commits per stage
     for (int mode : {0, 1, 2, 4, 8, 16, 3, 31 - 4, 31}) run<0, true>(128, 64, sms, dcyc, mode);
