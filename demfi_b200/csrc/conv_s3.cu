@@ -52,8 +52,16 @@ constexpr float S3_LO_SCALE = 2048.0f;
 
 struct S3Params {
   CUtensorMap tmap[DEMFI_MAX_SRC];  // activation sources
-  CUtensorMap omap[DEMFI_MAX_SEG];  // TMA epilogue: destination of each segment
-  CUtensorMap rmap;                 // TMA epilogue: residual operand (shared by all segments)
+  // TMA epilogue, planned per N block (S3_MAX_BLK blocks): every block is covered by segments that are all alike
+  // (multi-destination convs such as LFF), so a tile has ONE activation, ONE optional residual pair, 1-2 destinations.
+  CUtensorMap omap[DEMFI_MAX_SEG];  // destinations; block nb uses omap[b_o0[nb] .. b_o0[nb] + b_on[nb])
+  CUtensorMap rmap[DEMFI_MAX_SEG];  // first operand (residual / GRU h) of block nb
+  CUtensorMap r2map[DEMFI_MAX_SEG]; // second operand (GRU z) of block nb
+  int b_seg[DEMFI_MAX_SEG];         // representative segment of the block (-1: nothing to store)
+  int b_o0[DEMFI_MAX_SEG], b_on[DEMFI_MAX_SEG];
+  int b_nres[DEMFI_MAX_SEG];        // operands to fetch (0, 1, 2)
+  int o_c0[DEMFI_MAX_SEG];          // destination channel of the block's first channel, per destination
+  int r_c0[DEMFI_MAX_SEG];          // same for the operands
   demfi_conv_t c;
   int tiles_x, tiles_y, ntiles, n_blocks, nb_max;
   int hw, hh, halo_px;
@@ -63,7 +71,7 @@ struct S3Params {
   int b_off, stg_off, bar_off;  // byte offsets in (1024-aligned) shared memory
   int acc_stride;
   int taps, stages_per_tile, flush;
-  int tma_epi, tma_res;
+  int tma_epi, stg2_off;
   float comp;
   int diag;
   long long* dbg;
@@ -347,14 +355,19 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
       const int oy = ty0 + (m >> 3), ox = tx0 + (m & 7);
       const bool valid = (oy < c.H) && (ox < c.W);
       const int nboxes = (N + 31) >> 5;
+      const int sidx = P.tma_epi ? P.b_seg[nb] : -1;
+      const int nres = P.tma_epi ? P.b_nres[nb] : 0;
       if (P.tma_epi) {
-        // the staging buffer is free once the previous tile's stores have read it; then fetch the residual tile
+        // the staging buffers are free once the previous tile's stores have read them; then fetch the operand tiles
         if (e_tid == 0) {
           if (store_pending) bulk_wait_read0();
-          if (P.tma_res) {
-            mbar_arrive_expect_tx(bar_resfull, (uint32_t)(nboxes * S3_BOX_BYTES));
-            for (int b = 0; b < nboxes; ++b)
-              tma_load_4d(stg + (uint32_t)(b * S3_BOX_BYTES), &P.rmap, bar_resfull, n0 + 32 * b - c.seg[0].ch0, tx0, ty0, n);
+          if (nres > 0) {
+            mbar_arrive_expect_tx(bar_resfull, (uint32_t)(nres * nboxes * S3_BOX_BYTES));
+            for (int b = 0; b < nboxes; ++b) {
+              tma_load_4d(stg + (uint32_t)(b * S3_BOX_BYTES), &P.rmap[nb], bar_resfull, P.r_c0[nb] + 32 * b, tx0, ty0, n);
+              if (nres > 1)
+                tma_load_4d(stg + (uint32_t)(P.stg2_off + b * S3_BOX_BYTES), &P.r2map[nb], bar_resfull, P.r_c0[nb] + 32 * b, tx0, ty0, n);
+            }
           }
         }
         store_pending = true;
@@ -390,9 +403,9 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
       }
       const long long t_store = dbg ? clock64() : 0;
       if (P.tma_epi) {
-        // ---- staged epilogue: bias (+ residual) + activation -> swizzled box layout -> TMA store ----
-        const int act = c.seg[0].act;
-        if (P.tma_res) {
+        // ---- staged epilogue: bias, operands, activation -> swizzled box layout -> TMA store ----
+        const int act = sidx >= 0 ? c.seg[sidx].act : DEMFI_ACT_NONE;
+        if (nres > 0) {
           mbar_wait(bar_resfull, res_phase);
           res_phase ^= 1u;
         } else {
@@ -407,25 +420,34 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
             const uint32_t addr = row + (uint32_t)((chn >> 5) * S3_BOX_BYTES) + (((uint32_t)((chn & 31) >> 2) ^ sw) << 4);
             const float4 b = ld4(c.bias + n0 + chn);
             float4 v = make_float4(sum[col] + b.x, sum[col + 1] + b.y, sum[col + 2] + b.z, sum[col + 3] + b.w);
-            if (P.tma_res) {
-              const uint4 rr = lds128(addr);
-              v.x += __uint_as_float(rr.x); v.y += __uint_as_float(rr.y); v.z += __uint_as_float(rr.z); v.w += __uint_as_float(rr.w);
+            if (act <= DEMFI_ACT_SIGMOID) {
+              if (nres > 0) {
+                const uint4 rr = lds128(addr);
+                v.x += __uint_as_float(rr.x); v.y += __uint_as_float(rr.y); v.z += __uint_as_float(rr.z); v.w += __uint_as_float(rr.w);
+              }
+              v.x = act_pure(act, v.x); v.y = act_pure(act, v.y); v.z = act_pure(act, v.z); v.w = act_pure(act, v.w);
+            } else {
+              const uint4 hh = lds128(addr);
+              const float h0 = __uint_as_float(hh.x), h1 = __uint_as_float(hh.y), h2 = __uint_as_float(hh.z), h3 = __uint_as_float(hh.w);
+              if (act == DEMFI_ACT_SIGMOID_MUL) {  // r * h (DeMFInet.py:846-847)
+                v.x = sigmoid_f(v.x) * h0; v.y = sigmoid_f(v.y) * h1; v.z = sigmoid_f(v.z) * h2; v.w = sigmoid_f(v.w) * h3;
+              } else {  // GRU update (1 - z) h + z tanh(q) (DeMFInet.py:847-848)
+                const uint4 zz = lds128(addr + (uint32_t)P.stg2_off);
+                const float z0 = __uint_as_float(zz.x), z1 = __uint_as_float(zz.y), z2 = __uint_as_float(zz.z), z3 = __uint_as_float(zz.w);
+                v.x = (1.0f - z0) * h0 + z0 * tanhf(v.x);
+                v.y = (1.0f - z1) * h1 + z1 * tanhf(v.y);
+                v.z = (1.0f - z2) * h2 + z2 * tanhf(v.z);
+                v.w = (1.0f - z3) * h3 + z3 * tanhf(v.w);
+              }
             }
-            v.x = act_pure(act, v.x); v.y = act_pure(act, v.y); v.z = act_pure(act, v.z); v.w = act_pure(act, v.w);
             sts128(addr, make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)));
           }
         }
         fence_async_smem();
         asm volatile("bar.sync 3, %0;" ::"n"(S3_EPI_THREADS) : "memory");
-        if (e_tid == 0 && !(P.diag & (1 | 32))) {
-          for (int sgi = 0; sgi < c.nseg; ++sgi) {
-            const demfi_seg_t& sg = c.seg[sgi];
-            for (int b = 0; b < nboxes; ++b) {
-              const int c_lo = n0 + 32 * b - sg.ch0;  // destination channel of the box's first channel
-              if (c_lo + 32 <= 0 || c_lo >= sg.nch) continue;
-              tma_store_4d(&P.omap[sgi], stg + (uint32_t)(b * S3_BOX_BYTES), c_lo, tx0, ty0, n);
-            }
-          }
+        if (e_tid == 0 && sidx >= 0 && !(P.diag & (1 | 32))) {
+          for (int j = P.b_o0[nb]; j < P.b_o0[nb] + P.b_on[nb]; ++j)
+            for (int b = 0; b < nboxes; ++b) tma_store_4d(&P.omap[j], stg + (uint32_t)(b * S3_BOX_BYTES), P.o_c0[j] + 32 * b, tx0, ty0, n);
           bulk_commit();
         }
       } else if (valid && !(P.diag & 1)) {
@@ -638,13 +660,49 @@ static int s3_num_sms() {
 static int s3_nb_max(int cout_pad) { return cout_pad <= 96 ? cout_pad : 64; }  // same N blocking as conv_h3 (shared weight layout)
 constexpr int S3_SMEM_MAX = 227 * 1024;
 
-// all segments plain and alike: NHWC store, a pure activation, the same channel range and the same (optional) residual
-static bool s3_uniform_segments(const demfi_conv_t& c) {
-  const demfi_seg_t& a = c.seg[0];
-  for (int s = 0; s < c.nseg; ++s) {
-    const demfi_seg_t& g = c.seg[s];
-    if (g.store != DEMFI_STORE_NHWC || g.act > DEMFI_ACT_SIGMOID) return false;
-    if (g.act != a.act || g.ch0 != a.ch0 || g.nch != a.nch || g.res != a.res || g.res_ld != a.res_ld) return false;
+// TMA epilogue plan: per N block, the segments that intersect it must all be alike (same channel range, activation,
+// operands, store mode -- i.e. one result written to one or more destinations); at most DEMFI_MAX_SEG destinations in total.
+// Pixel-shuffle segments need one N block per quadrant (nch / 4 == block width).
+struct S3EpiPlan {
+  int b_seg[DEMFI_MAX_SEG], b_o0[DEMFI_MAX_SEG], b_on[DEMFI_MAX_SEG], b_nres[DEMFI_MAX_SEG];
+  int o_seg[DEMFI_MAX_SEG], o_blk[DEMFI_MAX_SEG];
+  int n_out;
+  bool any_res2;
+};
+static bool s3_plan_epilogue(const demfi_conv_t& c, int nb_max, int n_blocks, S3EpiPlan& E) {
+  if (n_blocks > DEMFI_MAX_SEG) return false;
+  E.n_out = 0;
+  E.any_res2 = false;
+  for (int nb = 0; nb < n_blocks; ++nb) {
+    const int n0 = nb * nb_max, n1 = n0 + (c.cout_pad - n0 < nb_max ? c.cout_pad - n0 : nb_max);
+    E.b_seg[nb] = -1;
+    E.b_o0[nb] = E.n_out;
+    E.b_on[nb] = 0;
+    E.b_nres[nb] = 0;
+    for (int s = 0; s < c.nseg; ++s) {
+      const demfi_seg_t& g = c.seg[s];
+      if (g.ch0 >= n1 || g.ch0 + g.nch <= n0) continue;
+      if (E.b_seg[nb] < 0) {
+        E.b_seg[nb] = s;
+        E.b_nres[nb] = g.act == DEMFI_ACT_GRU ? 2 : (g.res != nullptr ? 1 : 0);
+        if (g.act == DEMFI_ACT_GRU) E.any_res2 = true;
+      } else {
+        const demfi_seg_t& a = c.seg[E.b_seg[nb]];
+        if (g.ch0 != a.ch0 || g.nch != a.nch || g.act != a.act || g.store != a.store || g.res != a.res || g.res_ld != a.res_ld ||
+            g.res2 != a.res2 || g.res2_ld != a.res2_ld)
+          return false;
+      }
+      if (g.store == DEMFI_STORE_PIXEL_SHUFFLE2) {
+        const int cq = g.nch / 4;
+        if (cq < 1 || (n0 - g.ch0) / cq != (n1 - 1 - g.ch0) / cq || n0 < g.ch0) return false;  // block inside one quadrant
+        if (g.res != nullptr) return false;
+      }
+      if (E.n_out == DEMFI_MAX_SEG) return false;
+      E.o_seg[E.n_out] = s;
+      E.o_blk[E.n_out] = nb;
+      ++E.n_out;
+      ++E.b_on[nb];
+    }
   }
   return true;
 }
@@ -705,14 +763,48 @@ int launch_conv_s3(const demfi_conv_t& c, cudaStream_t st) {
   P.stages_per_tile = chunks * P.taps;
 
   // epilogue mode
-  P.tma_epi = (s3_uniform_segments(c) && !(get_option("tc_diag") & 2)) ? 1 : 0;
-  P.tma_res = (P.tma_epi && c.seg[0].res != nullptr) ? 1 : 0;
-  const int stg_bytes = P.tma_epi ? ((P.nb_max + 31) / 32) * S3_BOX_BYTES : 0;
+  S3EpiPlan E;
+  P.tma_epi = (s3_plan_epilogue(c, P.nb_max, P.n_blocks, E) && !(get_option("tc_diag") & 2)) ? 1 : 0;
+  const int box_bytes_all = ((P.nb_max + 31) / 32) * S3_BOX_BYTES;
+  const int stg_bytes = P.tma_epi ? box_bytes_all * (E.any_res2 ? 2 : 1) : 0;
+  P.stg2_off = box_bytes_all;  // second operand tile, relative to the staging tile
   if (P.tma_epi) {
-    for (int s = 0; s < c.nseg; ++s)
-      if (s3_encode(enc, &P.omap[s], c.seg[s].dst, c.seg[s].nch, c.seg[s].dst_ld, c.W, c.H, c.N, S3_TW, S3_TH, "a destination")) return 1;
-    if (P.tma_res)
-      if (s3_encode(enc, &P.rmap, c.seg[0].res, c.seg[0].nch, c.seg[0].res_ld, c.W, c.H, c.N, S3_TW, S3_TH, "the residual")) return 1;
+    for (int nb = 0; nb < P.n_blocks; ++nb) {
+      P.b_seg[nb] = E.b_seg[nb];
+      P.b_o0[nb] = E.b_o0[nb];
+      P.b_on[nb] = E.b_on[nb];
+      P.b_nres[nb] = E.b_nres[nb];
+      if (E.b_seg[nb] < 0) continue;
+      const demfi_seg_t& g = c.seg[E.b_seg[nb]];
+      const int n0 = nb * P.nb_max;
+      P.r_c0[nb] = n0 - g.ch0;
+      if (E.b_nres[nb] >= 1)
+        if (s3_encode(enc, &P.rmap[nb], g.res, g.nch, g.res_ld, c.W, c.H, c.N, S3_TW, S3_TH, "an epilogue operand")) return 1;
+      if (E.b_nres[nb] >= 2)
+        if (s3_encode(enc, &P.r2map[nb], g.res2, g.nch, g.res2_ld, c.W, c.H, c.N, S3_TW, S3_TH, "the second epilogue operand")) return 1;
+    }
+    for (int j = 0; j < E.n_out; ++j) {
+      const demfi_seg_t& g = c.seg[E.o_seg[j]];
+      const int n0 = E.o_blk[j] * P.nb_max;
+      if (g.store == DEMFI_STORE_PIXEL_SHUFFLE2) {
+        // nn.PixelShuffle(2): accumulator channel q*cq + ch of pixel (y, x) -> pixel (2y + q/2, 2x + q%2), channel ch: the
+        // quadrant is a tensor of its own with doubled pixel strides
+        const int cq = g.nch / 4, q = (n0 - g.ch0) / cq;
+        P.o_c0[j] = n0 - g.ch0 - q * cq;
+        const float* base = g.dst + ((size_t)(q >> 1) * (size_t)(2 * c.W) + (size_t)(q & 1)) * (size_t)g.dst_ld;
+        cuuint64_t dims[4] = {(cuuint64_t)cq, (cuuint64_t)c.W, (cuuint64_t)c.H, (cuuint64_t)c.N};
+        cuuint64_t strides[3] = {(cuuint64_t)g.dst_ld * 8, (cuuint64_t)g.dst_ld * 16 * c.W, (cuuint64_t)g.dst_ld * 16 * c.W * c.H};
+        cuuint32_t box[4] = {S3_KC, S3_TW, S3_TH, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&P.omap[j], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        DEMFI_REQUIRE(r == CUDA_SUCCESS, "conv_s3: cuTensorMapEncodeTiled failed for a pixel-shuffle destination (CUresult %d)", (int)r);
+      } else {
+        P.o_c0[j] = n0 - g.ch0;
+        if (s3_encode(enc, &P.omap[j], g.dst, g.nch, g.dst_ld, c.W, c.H, c.N, S3_TW, S3_TH, "a destination")) return 1;
+      }
+    }
   }
 
   // shared-memory plan: [A buffers][weights: resident bank or ring][staging][barriers]
