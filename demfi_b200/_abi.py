@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdemfi_b200.so")
+LIB_PATH = os.environ.get("DEMFI_LIB") or os.path.join(_HERE, "libdemfi_b200.so")  # DEMFI_LIB: A/B measurement of two builds
 
 MAX_SRC = 4
 MAX_SEG = 4

@@ -68,7 +68,7 @@ struct S3Params {
   int a_bytes, na;
   int b_bytes, ns, resident;
   int gtaps;  // weight ring: (chunk, tap) stages per ring slot, fetched with ONE bulk copy and ONE barrier round trip
-  int b_off, stg_off, bar_off;  // byte offsets in (1024-aligned) shared memory
+  int b_off, stg_off, bar_off, bias_off;  // byte offsets in (1024-aligned) shared memory
   int acc_stride;
   int taps, stages_per_tile, flush;
   int tma_epi, stg2_off;
@@ -224,16 +224,40 @@ __device__ __forceinline__ void split2(float a0, float a1, uint32_t& hi, uint32_
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
-__device__ __forceinline__ float act_pure(int act, float v) {
-  if (act == DEMFI_ACT_RELU) return fmaxf(v, 0.0f);
-  if (act == DEMFI_ACT_TANH) return tanhf(v);
-  if (act == DEMFI_ACT_SIGMOID) return sigmoid_f(v);
+// Transcendental epilogues (tanh / sigmoid heads, GRU gates), out of line: ONE copy of the expf / tanhf / division
+// expansions instead of one per unrolled call site -- inlined they were a quarter of the kernel's 7 K instructions and the
+// instruction-cache pressure slowed the MMA issuer's loop by 10 % (A/B on one GPU).  Operands come from the staging tiles.
+static __device__ __noinline__ float4 finish4(int act, float4 v, uint32_t addr, int nres, uint32_t stg2_off) {
+  float4 h = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  if (nres > 0) {
+    const uint4 hh = lds128(addr);
+    h = make_float4(__uint_as_float(hh.x), __uint_as_float(hh.y), __uint_as_float(hh.z), __uint_as_float(hh.w));
+  }
+  if (act == DEMFI_ACT_SIGMOID_MUL) {  // r * h (DeMFInet.py:846-847)
+    v.x = sigmoid_f(v.x) * h.x; v.y = sigmoid_f(v.y) * h.y; v.z = sigmoid_f(v.z) * h.z; v.w = sigmoid_f(v.w) * h.w;
+  } else if (act == DEMFI_ACT_GRU) {  // (1 - z) h + z tanh(q) (DeMFInet.py:847-848)
+    const uint4 zz = lds128(addr + stg2_off);
+    const float z0 = __uint_as_float(zz.x), z1 = __uint_as_float(zz.y), z2 = __uint_as_float(zz.z), z3 = __uint_as_float(zz.w);
+    v.x = (1.0f - z0) * h.x + z0 * tanhf(v.x);
+    v.y = (1.0f - z1) * h.y + z1 * tanhf(v.y);
+    v.z = (1.0f - z2) * h.z + z2 * tanhf(v.z);
+    v.w = (1.0f - z3) * h.w + z3 * tanhf(v.w);
+  } else {
+    v.x += h.x; v.y += h.y; v.z += h.z; v.w += h.w;
+    if (act == DEMFI_ACT_TANH) {
+      v.x = tanhf(v.x); v.y = tanhf(v.y); v.z = tanhf(v.z); v.w = tanhf(v.w);
+    } else if (act == DEMFI_ACT_SIGMOID) {
+      v.x = sigmoid_f(v.x); v.y = sigmoid_f(v.y); v.z = sigmoid_f(v.z); v.w = sigmoid_f(v.w);
+    }
+  }
   return v;
 }
 }  // namespace s3
 using namespace s3;
 
-template <int NMAX>
+// DBG: per-role cycle counters (tc_diag & 128).  A template parameter, not a run-time flag: the timed variants of every
+// wait would otherwise sit between the hot instructions of all roles (instruction-cache footprint).
+template <int NMAX, bool DBG>
 __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_constant__ S3Params P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -256,7 +280,7 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
-  const bool dbg = P.dbg != nullptr;
+  constexpr bool dbg = DBG;
   const int chunks_per_tile = P.stages_per_tile / P.taps;
 
   if (threadIdx.x == 0) {
@@ -341,6 +365,14 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
     const long long t_begin = dbg ? clock64() : 0;
     const uint32_t stg = smem_base + (uint32_t)P.stg_off;
     bool store_pending = false;
+    // bias -> shared memory once per CTA: the per-tile global loads (L2 latency on a cold L1 line) stalled every warp of the
+    // store phase (ncu: long-scoreboard stalls on the bias FADDs)
+    const uint32_t bias_s = smem_base + (uint32_t)P.bias_off;
+    for (int i = e_tid * 4; i < c.cout_pad; i += S3_EPI_THREADS * 4) {
+      const float4 b = ld4(c.bias + i);
+      sts128(bias_s + (uint32_t)i * 4u, make_uint4(__float_as_uint(b.x), __float_as_uint(b.y), __float_as_uint(b.z), __float_as_uint(b.w)));
+    }
+    asm volatile("bar.sync 2, %0;" ::"n"(S3_EPI_THREADS) : "memory");
     for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
       int t = tile;
       const int nb = t % P.n_blocks;
@@ -418,27 +450,19 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
           if (col < cnum && !(P.diag & 32)) {
             const int chn = cbeg + col;  // channel within the N block
             const uint32_t addr = row + (uint32_t)((chn >> 5) * S3_BOX_BYTES) + (((uint32_t)((chn & 31) >> 2) ^ sw) << 4);
-            const float4 b = ld4(c.bias + n0 + chn);
-            float4 v = make_float4(sum[col] + b.x, sum[col + 1] + b.y, sum[col + 2] + b.z, sum[col + 3] + b.w);
-            if (act <= DEMFI_ACT_SIGMOID) {
+            const uint4 bu = lds128(bias_s + (uint32_t)(n0 + chn) * 4u);
+            float4 v = make_float4(sum[col] + __uint_as_float(bu.x), sum[col + 1] + __uint_as_float(bu.y),
+                                   sum[col + 2] + __uint_as_float(bu.z), sum[col + 3] + __uint_as_float(bu.w));
+            if (act == DEMFI_ACT_NONE || act == DEMFI_ACT_RELU) {  // the common case stays inline (a few FADD / FMNMX)
               if (nres > 0) {
                 const uint4 rr = lds128(addr);
                 v.x += __uint_as_float(rr.x); v.y += __uint_as_float(rr.y); v.z += __uint_as_float(rr.z); v.w += __uint_as_float(rr.w);
               }
-              v.x = act_pure(act, v.x); v.y = act_pure(act, v.y); v.z = act_pure(act, v.z); v.w = act_pure(act, v.w);
-            } else {
-              const uint4 hh = lds128(addr);
-              const float h0 = __uint_as_float(hh.x), h1 = __uint_as_float(hh.y), h2 = __uint_as_float(hh.z), h3 = __uint_as_float(hh.w);
-              if (act == DEMFI_ACT_SIGMOID_MUL) {  // r * h (DeMFInet.py:846-847)
-                v.x = sigmoid_f(v.x) * h0; v.y = sigmoid_f(v.y) * h1; v.z = sigmoid_f(v.z) * h2; v.w = sigmoid_f(v.w) * h3;
-              } else {  // GRU update (1 - z) h + z tanh(q) (DeMFInet.py:847-848)
-                const uint4 zz = lds128(addr + (uint32_t)P.stg2_off);
-                const float z0 = __uint_as_float(zz.x), z1 = __uint_as_float(zz.y), z2 = __uint_as_float(zz.z), z3 = __uint_as_float(zz.w);
-                v.x = (1.0f - z0) * h0 + z0 * tanhf(v.x);
-                v.y = (1.0f - z1) * h1 + z1 * tanhf(v.y);
-                v.z = (1.0f - z2) * h2 + z2 * tanhf(v.z);
-                v.w = (1.0f - z3) * h3 + z3 * tanhf(v.w);
+              if (act == DEMFI_ACT_RELU) {
+                v.x = fmaxf(v.x, 0.0f); v.y = fmaxf(v.y, 0.0f); v.z = fmaxf(v.z, 0.0f); v.w = fmaxf(v.w, 0.0f);
               }
+            } else {
+              v = finish4(act, v, addr, nres, (uint32_t)P.stg2_off);
             }
             sts128(addr, make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)));
           }
@@ -808,7 +832,7 @@ int launch_conv_s3(const demfi_conv_t& c, cudaStream_t st) {
   }
 
   // shared-memory plan: [A buffers][weights: resident bank or ring][staging][barriers]
-  const int fixed = stg_bytes + 8 * S3_NBARS + 16 + 1024;
+  const int fixed = stg_bytes + 8 * S3_NBARS + 16 + 1024 + 1024;  // + barriers, tensor-memory slot, bias, alignment slack
   const int bank = P.stages_per_tile * P.b_bytes;
   P.resident = (P.n_blocks == 1 && 2 * P.a_bytes + bank + fixed <= S3_SMEM_MAX && !(get_option("tc_diag") & 4)) ? 1 : 0;
   if (P.resident) {
@@ -843,7 +867,8 @@ int launch_conv_s3(const demfi_conv_t& c, cudaStream_t st) {
   P.stg_off = P.b_off + (P.resident ? bank : P.ns * P.gtaps * P.b_bytes);
   P.stg_off = (P.stg_off + 1023) & ~1023;
   P.bar_off = P.stg_off + stg_bytes;
-  const int smem = P.bar_off + 8 * S3_NBARS + 16 + 1024;
+  P.bias_off = (P.bar_off + 8 * S3_NBARS + 16 + 15) & ~15;
+  const int smem = P.bias_off + 1024 + 1024;
   DEMFI_REQUIRE(smem <= S3_SMEM_MAX + 1024, "conv_s3: shared-memory plan (%d bytes) does not fit", smem);
 
   P.flush = get_option("tc_flush");
@@ -861,7 +886,8 @@ int launch_conv_s3(const demfi_conv_t& c, cudaStream_t st) {
   }
   static bool attr_set = false;
   if (!attr_set) {
-    const void* fns[] = {(const void*)conv_s3_kernel<32>, (const void*)conv_s3_kernel<64>, (const void*)conv_s3_kernel<96>};
+    const void* fns[] = {(const void*)conv_s3_kernel<32, false>, (const void*)conv_s3_kernel<64, false>, (const void*)conv_s3_kernel<96, false>,
+                         (const void*)conv_s3_kernel<32, true>,  (const void*)conv_s3_kernel<64, true>,  (const void*)conv_s3_kernel<96, true>};
     for (const void* f : fns) {
       cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, S3_SMEM_MAX);
       DEMFI_REQUIRE(e == cudaSuccess, "conv_s3: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
@@ -870,9 +896,15 @@ int launch_conv_s3(const demfi_conv_t& c, cudaStream_t st) {
   }
   int grid = P.ntiles < s3_num_sms() ? P.ntiles : s3_num_sms();
   if (get_option("tc_grid") > 0 && get_option("tc_grid") < grid) grid = get_option("tc_grid");
-  if (P.nb_max <= 32) conv_s3_kernel<32><<<grid, S3_THREADS, smem, st>>>(P);
-  else if (P.nb_max <= 64) conv_s3_kernel<64><<<grid, S3_THREADS, smem, st>>>(P);
-  else conv_s3_kernel<96><<<grid, S3_THREADS, smem, st>>>(P);
+  if (P.dbg != nullptr) {
+    if (P.nb_max <= 32) conv_s3_kernel<32, true><<<grid, S3_THREADS, smem, st>>>(P);
+    else if (P.nb_max <= 64) conv_s3_kernel<64, true><<<grid, S3_THREADS, smem, st>>>(P);
+    else conv_s3_kernel<96, true><<<grid, S3_THREADS, smem, st>>>(P);
+  } else {
+    if (P.nb_max <= 32) conv_s3_kernel<32, false><<<grid, S3_THREADS, smem, st>>>(P);
+    else if (P.nb_max <= 64) conv_s3_kernel<64, false><<<grid, S3_THREADS, smem, st>>>(P);
+    else conv_s3_kernel<96, false><<<grid, S3_THREADS, smem, st>>>(P);
+  }
   DEMFI_LAUNCH_CHECK("conv_s3");
   return 0;
 }

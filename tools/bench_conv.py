@@ -15,7 +15,7 @@ from demfi_b200 import _abi as A
 DEV = torch.device("cuda:0")
 
 
-def make_conv(kind, n, h, w, srcC, co, k, act=A.ACT_RELU, seed=0):
+def make_conv(kind, n, h, w, srcC, co, k, act=A.ACT_RELU, seed=0, res=False):
     lib = A.lib()
     g = torch.Generator().manual_seed(seed)
     ci = sum(srcC)
@@ -41,6 +41,10 @@ def make_conv(kind, n, h, w, srcC, co, k, act=A.ACT_RELU, seed=0):
     out = torch.zeros(n, h, w, ld, device=DEV)
     keep.append(out)
     d.seg[0].dst, d.seg[0].dst_ld, d.seg[0].ch0, d.seg[0].nch, d.seg[0].act = out.data_ptr(), ld, 0, ld, act
+    if res:
+        rb = torch.randn(n, h, w, ld, device=DEV)
+        keep.append(rb)
+        d.seg[0].res, d.seg[0].res_ld = rb.data_ptr(), ld
     d.wpack, d.bias = keep[0].data_ptr(), keep[1].data_ptr()
     return d, keep
 
@@ -62,6 +66,13 @@ def time_conv(d, iters=5, warm=2):
 SHAPES = [  # name, batch, res divisor, srcC, cout, k
     ("resblock 64->64 3x3 (x1 frame)", 1, 1, [64], 64, (3, 3)),
     ("resblock 64->64 3x3 (x3 frames, D1)", 3, 1, [64], 64, (3, 3)),
+    ("resblock conv2 64->64 3x3 +res (x3 frames)", 3, 1, [64], 64, (3, 3)),
+    ("conv_delta1 8->32 7x7", 1, 1, [8], 32, (7, 7)),
+    ("blend2 32->64 3x3", 1, 1, [32], 64, (3, 3)),
+    ("blend1 64->32 3x3", 1, 1, [64], 32, (3, 3)),
+    ("delta2 32->32 3x3", 1, 1, [32], 32, (3, 3)),
+    ("RDB conv 96->32 3x3 @1/2", 1, 2, [96], 32, (3, 3)),
+    ("SFENet1 48->96 5x5 @1/2", 1, 2, [48], 96, (5, 5)),
     ("Ch_Reducer 192->64 7x7", 1, 1, [64, 64, 64], 64, (7, 7)),
     ("GRU zr 128->128 1x5", 1, 1, [64, 64], 128, (1, 5)),
     ("GRU q 128->64 5x1", 1, 1, [64, 64], 64, (5, 1)),
@@ -95,7 +106,7 @@ if __name__ == "__main__":
         for kind_name in a.kinds.split(","):
             kind = {"tc": A.CONV_TC, "tc16": A.CONV_TC16, "tc16h3": A.CONV_TC16, "ffma": A.CONV_FFMA}[kind_name]
             A.set_option("tc_gen", 2 if kind_name == "tc16h3" else 3)
-            d, keep = make_conv(kind, n, h, w, srcC, co, k)
+            d, keep = make_conv(kind, n, h, w, srcC, co, k, res="+res" in name, act=A.ACT_NONE if "+res" in name else A.ACT_RELU)
             ms = time_conv(d)
             row[kind_name + "_ms"] = round(ms, 3)
             row[kind_name + "_TFLOPs"] = round(2 * macs / ms / 1e9, 1)
