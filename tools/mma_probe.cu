@@ -89,7 +89,23 @@ __global__ void __launch_bounds__(128 + 256, 1) probe(int N1, int N2, int iters,
     const uint32_t id1 = idesc0 | ((uint32_t)(N1 >> 3) << 17), id2 = idesc0 | ((uint32_t)(N2 >> 3) << 17);
     const uint32_t sb = smem_u32(smem);
     long long t0 = clock64();
-    if (!(mode & 4)) {
+    if (mode & 128) {
+      uint32_t junk = threadIdx.x;
+      if (elect_one()) {
+        for (int i = 0; i < iters; ++i) {
+          for (int j = 0; j < ((mode >> 9) & 127); ++j) asm volatile("mad.lo.u32 %0, %0, 1664525, 1013904223;" : "+r"(junk));
+          const uint32_t buf = (uint32_t)(i & 1) ^ (junk == 0x12345u ? 1u : 0u);
+          uint64_t ad = make_desc_sw128(sb + buf * A_BYTES), bd = make_desc_sw128(sb + NBUF * A_BYTES + buf * B_BYTES);
+          mma_ss<KIND>(tmem, ad, bd, id1, i ? 1u : 0u);
+          mma_ss<KIND>(tmem, ad + 2u, bd + 2u, id1, 1u);
+          if (!(mode & 256)) {
+            mma_ss<KIND>(tmem + 256u, ad + 4u, bd, id2, i ? 1u : 0u);
+            mma_ss<KIND>(tmem + 256u, ad + 6u, bd + 2u, id2, 1u);
+          }
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+      }
+    } else if (!(mode & 4)) {
       if (elect_one()) {
         for (int i = 0; i < iters; ++i) {
           const uint32_t buf = (uint32_t)(i & 1);
@@ -150,6 +166,27 @@ __global__ void __launch_bounds__(128 + 256, 1) probe(int N1, int N2, int iters,
     long long t1 = clock64();
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
     stop_flag = 1;
+  } else if (warp == 1 && (mode & 256)) {
+    // second issuer (mode 256): the lo products Al x Bh into its own accumulator, same per-stage ALU chain as warp 0
+    const uint32_t idesc0 = (1u << 4) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t id2 = idesc0 | ((uint32_t)(N2 >> 3) << 17);
+    const uint32_t sb = smem_u32(smem);
+    uint32_t junk = threadIdx.x;
+    if (elect_one()) {
+      for (int i = 0; i < iters; ++i) {
+        for (int j = 0; j < ((mode >> 9) & 127); ++j) asm volatile("mad.lo.u32 %0, %0, 1664525, 1013904223;" : "+r"(junk));
+        const uint32_t buf = (uint32_t)(i & 1) ^ (junk == 0x12345u ? 1u : 0u);
+        uint64_t ad = make_desc_sw128(sb + buf * A_BYTES), bd = make_desc_sw128(sb + NBUF * A_BYTES + buf * B_BYTES);
+        mma_ss<KIND>(tmem + 256u, ad + 4u, bd, id2, i ? 1u : 0u);
+        mma_ss<KIND>(tmem + 256u, ad + 6u, bd + 2u, id2, 1u);
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar2[0])) : "memory");
+    }
+    __syncwarp();
+    uint32_t ok = 0;
+    while (!ok) {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(&bar2[0])) : "memory");
+    }
   } else if (warp >= 4 && (mode & 8)) {
     // eight extra warps drain an idle accumulator region every ~3000 cycles (what the epilogue warps do)
     uint32_t r[16], sink = 0;
@@ -207,6 +244,11 @@ int main(int argc, char**) {
   long long* dcyc;
   cudaMalloc(&dcyc, sms * sizeof(long long));
   const int cfg[][2] = {{64, 0}, {128, 0}, {256, 0}, {32, 0}, {128, 64}, {64, 32}, {192, 96}, {256, 128}, {64, 64}, {96, 96}};
+  if (argc > 3) {  // conv_s3-like stage (2 x N1 + 2 x N2 per stage) with an ALU chain of c ops per stage; single vs dual issuer
+    for (int c : {0, 8, 16, 24, 32, 48})
+      for (int dual : {0, 256}) run<1, false>(128, 64, sms, dcyc, 128 | dual | (c << 9));
+    return 0;
+  }
   if (argc > 2) {  // conv_s3-like SS operands: 32 shifted-window A, 64 SW64 B
     for (int mode : {0, 32, 64, 96}) run<1, false>(128, 64, sms, dcyc, mode);
     for (int mode : {0, 32, 64, 96}) run<1, false>(256, 128, sms, dcyc, mode);
