@@ -17,18 +17,20 @@ MAX_SEG = 4
 ACT_NONE, ACT_RELU, ACT_TANH, ACT_SIGMOID, ACT_SIGMOID_MUL, ACT_GRU = range(6)
 STORE_NHWC, STORE_PIXEL_SHUFFLE2 = 0, 1
 CONV_FFMA, CONV_TC, CONV_TC16 = 0, 1, 2
+FMT_F32, FMT_S16 = 0, 1
+SEG_DST_S16, SEG_RES_S16, SEG_RES2_S16 = 1, 2, 4
 
 i32 = C.c_int32
 vp = C.c_void_p
 
 
 class Src(C.Structure):
-    _fields_ = [("ptr", vp), ("C", i32), ("ld", i32), ("up", i32), ("reserved", i32)]
+    _fields_ = [("ptr", vp), ("C", i32), ("ld", i32), ("up", i32), ("fmt", i32)]
 
 
 class Seg(C.Structure):
     _fields_ = [("dst", vp), ("res", vp), ("res2", vp), ("dst_ld", i32), ("res_ld", i32), ("res2_ld", i32),
-                ("ch0", i32), ("nch", i32), ("act", i32), ("store", i32), ("reserved", i32)]
+                ("ch0", i32), ("nch", i32), ("act", i32), ("store", i32), ("fmt", i32)]
 
 
 class Conv(C.Structure):

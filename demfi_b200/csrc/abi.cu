@@ -183,6 +183,26 @@ int demfi_conv2d(const demfi_conv_t* c, void* stream) {
       DEMFI_REQUIRE(G.nch % 16 == 0 && G.res == nullptr, "conv2d: pixel-shuffle segment %d must have nch%%16==0 and no res", s);
   }
   DEMFI_REQUIRE(c->wpack && c->bias, "conv2d: null weights");
+  {
+    bool any_s16 = false;
+    for (int s = 0; s < c->nsrc; ++s) {
+      DEMFI_REQUIRE(c->src[s].fmt == DEMFI_FMT_F32 || c->src[s].fmt == DEMFI_FMT_S16, "conv2d: source %d has an unknown format", s);
+      if (c->src[s].fmt == DEMFI_FMT_S16) {
+        any_s16 = true;
+        DEMFI_REQUIRE(c->src[s].C % 32 == 0 && c->src[s].up == 0, "conv2d: an S16 source needs C %% 32 == 0 and no up-sampling (source %d)", s);
+      }
+    }
+    for (int s = 0; s < c->nseg; ++s) {
+      DEMFI_REQUIRE((c->seg[s].fmt & ~7) == 0, "conv2d: segment %d has unknown format bits", s);
+      if (c->seg[s].fmt != 0) {
+        any_s16 = true;
+        DEMFI_REQUIRE(c->seg[s].ch0 % 32 == 0 && c->seg[s].nch % 32 == 0, "conv2d: an S16 segment needs ch0 and nch multiples of 32 (segment %d)", s);
+      }
+    }
+    if (any_s16)
+      DEMFI_REQUIRE(c->kind == DEMFI_CONV_TC16 && g_opt_gen.load() == 3 && s3_supports(*c) && s3_s16_ok(*c),
+                    "conv2d: the S16 activation format is only implemented by the conv_s3 kernel (stride 1, TMA epilogue)");
+  }
   if (c->kind == DEMFI_CONV_TC) return launch_conv_tc(*c, (cudaStream_t)stream);
   if (c->kind == DEMFI_CONV_TC16) {
     if (g_opt_gen.load() == 3 && s3_supports(*c)) return launch_conv_s3(*c, (cudaStream_t)stream);

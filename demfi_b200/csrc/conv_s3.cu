@@ -60,6 +60,7 @@ struct S3Params {
   int b_seg[DEMFI_MAX_SEG];         // representative segment of the block (-1: nothing to store)
   int b_o0[DEMFI_MAX_SEG], b_on[DEMFI_MAX_SEG];
   int b_nres[DEMFI_MAX_SEG];        // operands to fetch (0, 1, 2)
+  int b_roff[DEMFI_MAX_SEG];        // first operand: 0 = fetched into the result tile (same format), else into the second tile
   int o_c0[DEMFI_MAX_SEG];          // destination channel of the block's first channel, per destination
   int r_c0[DEMFI_MAX_SEG];          // same for the operands
   demfi_conv_t c;
@@ -224,29 +225,23 @@ __device__ __forceinline__ void split2(float a0, float a1, uint32_t& hi, uint32_
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
-// Transcendental epilogues (tanh / sigmoid heads, GRU gates), out of line: ONE copy of the expf / tanhf / division
-// expansions instead of one per unrolled call site -- inlined they were a quarter of the kernel's 7 K instructions and the
-// instruction-cache pressure slowed the MMA issuer's loop by 10 % (A/B on one GPU).  Operands come from the staging tiles.
+// Transcendental epilogues (tanh / sigmoid heads, GRU gates), out of line: ONE copy of the exp / reciprocal expansions
+// instead of one per unrolled call site -- inlined they were a quarter of the kernel's 7 K instructions and the
+// instruction-cache pressure slowed the MMA issuer's loop by 10 % (A/B on one GPU).
 // sigmoid / tanh through ex2.approx + the approximate reciprocal: absolute error ~1e-7 on outputs in [-1, 1] (the parity
 // budget is 5e-4 end to end, 2e-5 per operator in the tests); the IEEE division + expf versions made the GRU convolutions
 // epilogue-bound (0.69 ms in the network against 0.48 ms for the same shape with a ReLU epilogue).
 __device__ __forceinline__ float sigmoid_fast(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
 __device__ __forceinline__ float tanh_fast(float v) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * v)); }
-static __device__ __noinline__ float4 finish4(int act, float4 v, uint32_t addr, int nres, uint32_t stg2_off) {
-  float4 h = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-  if (nres > 0) {
-    const uint4 hh = lds128(addr);
-    h = make_float4(__uint_as_float(hh.x), __uint_as_float(hh.y), __uint_as_float(hh.z), __uint_as_float(hh.w));
-  }
+// v = accumulator + bias; h = first operand (residual / GRU h; zeros when absent); z = second operand (GRU z)
+static __device__ __noinline__ float4 finish4v(int act, float4 v, float4 h, float4 z) {
   if (act == DEMFI_ACT_SIGMOID_MUL) {  // r * h (DeMFInet.py:846-847)
     v.x = sigmoid_fast(v.x) * h.x; v.y = sigmoid_fast(v.y) * h.y; v.z = sigmoid_fast(v.z) * h.z; v.w = sigmoid_fast(v.w) * h.w;
   } else if (act == DEMFI_ACT_GRU) {  // (1 - z) h + z tanh(q) (DeMFInet.py:847-848)
-    const uint4 zz = lds128(addr + stg2_off);
-    const float z0 = __uint_as_float(zz.x), z1 = __uint_as_float(zz.y), z2 = __uint_as_float(zz.z), z3 = __uint_as_float(zz.w);
-    v.x = (1.0f - z0) * h.x + z0 * tanh_fast(v.x);
-    v.y = (1.0f - z1) * h.y + z1 * tanh_fast(v.y);
-    v.z = (1.0f - z2) * h.z + z2 * tanh_fast(v.z);
-    v.w = (1.0f - z3) * h.w + z3 * tanh_fast(v.w);
+    v.x = (1.0f - z.x) * h.x + z.x * tanh_fast(v.x);
+    v.y = (1.0f - z.y) * h.y + z.y * tanh_fast(v.y);
+    v.z = (1.0f - z.z) * h.z + z.z * tanh_fast(v.z);
+    v.w = (1.0f - z.w) * h.w + z.w * tanh_fast(v.w);
   } else {
     v.x += h.x; v.y += h.y; v.z += h.z; v.w += h.w;
     if (act == DEMFI_ACT_TANH) {
@@ -256,6 +251,55 @@ static __device__ __noinline__ float4 finish4(int act, float4 v, uint32_t addr, 
     }
   }
   return v;
+}
+__device__ __forceinline__ float4 as_f4(uint4 u) {
+  return make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
+}
+__device__ __forceinline__ uint4 as_u4(float4 v) {
+  return make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
+}
+// S16 decode: eight channels = one 16-byte chunk of fp16 hi + one of fp16 lo -> two float4 (value = hi + lo / 2048)
+__device__ __forceinline__ void s16_decode8(uint4 hi, uint4 lo, float4& v0, float4& v1) {
+  const float k = 1.0f / S3_LO_SCALE;
+  float2 h, l;
+  h = __half22float2(*reinterpret_cast<const __half2*>(&hi.x)); l = __half22float2(*reinterpret_cast<const __half2*>(&lo.x));
+  v0.x = fmaf(l.x, k, h.x); v0.y = fmaf(l.y, k, h.y);
+  h = __half22float2(*reinterpret_cast<const __half2*>(&hi.y)); l = __half22float2(*reinterpret_cast<const __half2*>(&lo.y));
+  v0.z = fmaf(l.x, k, h.x); v0.w = fmaf(l.y, k, h.y);
+  h = __half22float2(*reinterpret_cast<const __half2*>(&hi.z)); l = __half22float2(*reinterpret_cast<const __half2*>(&lo.z));
+  v1.x = fmaf(l.x, k, h.x); v1.y = fmaf(l.y, k, h.y);
+  h = __half22float2(*reinterpret_cast<const __half2*>(&hi.w)); l = __half22float2(*reinterpret_cast<const __half2*>(&lo.w));
+  v1.z = fmaf(l.x, k, h.x); v1.w = fmaf(l.y, k, h.y);
+}
+// Operand fetch from a staged tile (box row `base` of pixel m, sw = m & 7), channels chn..chn+7 / chn..chn+3 of the N block
+__device__ __forceinline__ void op_load8(uint32_t base, int chn, uint32_t sw, bool s16, float4& v0, float4& v1) {
+  if (s16) {
+    const uint32_t g8 = (uint32_t)((chn & 31) >> 3);
+    s16_decode8(lds128(base + ((g8 ^ sw) << 4)), lds128(base + (((g8 + 4u) ^ sw) << 4)), v0, v1);
+  } else {
+    const uint32_t q = (uint32_t)((chn & 31) >> 2);
+    v0 = as_f4(lds128(base + ((q ^ sw) << 4)));
+    v1 = as_f4(lds128(base + (((q + 1u) ^ sw) << 4)));
+  }
+}
+__device__ __forceinline__ float4 op_load4(uint32_t base, int chn, uint32_t sw, bool s16) {
+  if (s16) {  // four channels = half of an S16 chunk pair
+    const uint32_t g8 = (uint32_t)((chn & 31) >> 3);
+    const uint32_t half = (uint32_t)(chn & 4) << 1;  // byte offset 0 or 8 inside the 16-byte chunks
+    uint2 uh, ul;
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(uh.x), "=r"(uh.y) : "r"(base + ((g8 ^ sw) << 4) + half));
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(ul.x), "=r"(ul.y) : "r"(base + (((g8 + 4u) ^ sw) << 4) + half));
+    float4 v, dummy;
+    s16_decode8(make_uint4(uh.x, uh.y, 0u, 0u), make_uint4(ul.x, ul.y, 0u, 0u), v, dummy);
+    return v;
+  }
+  return as_f4(lds128(base + (((uint32_t)((chn & 31) >> 2) ^ sw) << 4)));
+}
+__device__ __forceinline__ void s16_encode8(float4 v0, float4 v1, uint4& hi, uint4& lo) {
+  split2(v0.x, v0.y, hi.x, lo.x);
+  split2(v0.z, v0.w, hi.y, lo.y);
+  split2(v1.x, v1.y, hi.z, lo.z);
+  split2(v1.z, v1.w, hi.w, lo.w);
 }
 }  // namespace s3
 using namespace s3;
@@ -323,33 +367,40 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
     int abuf = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
-      for (int ch = 0; ch < chunks_per_tile; ++ch) {
-        mbar_wait_t(bar_rawfull(abuf), aphase, dbg, w_raw);
-        const long long t_cv = dbg ? clock64() : 0;
-        const uint32_t a_addr = smem_base + (uint32_t)(abuf * P.a_bytes);
+      for (int si = 0; si < c.nsrc; ++si) {
+        const bool s16 = c.src[si].fmt == DEMFI_FMT_S16;  // already fp16 hi | lo rows: the MMA reads the TMA tile as it lands
+        for (int c0 = 0; c0 < c.src[si].C; c0 += S3_KC) {
+          // every chunk is waited for, converted or not: a parity wait is only meaningful when the waiter is at most
+          // one phase behind the barrier (skipping the S16 chunks let a later wait fall through on a stale phase)
+          mbar_wait_t(bar_rawfull(abuf), aphase, dbg, w_raw);
+          if (!s16) {
+            const long long t_cv = dbg ? clock64() : 0;
+            const uint32_t a_addr = smem_base + (uint32_t)(abuf * P.a_bytes);
 #pragma unroll 1
-        for (int p = (P.diag & 16) ? P.halo_px : tid; p < P.halo_px; p += S3_CV_THREADS) {
-          // row = pixel: 32 fp32 -> [Ah 32 x fp16 | Al 32 x fp16], same 128 bytes, same 16-byte-chunk swizzle (chunk ^ (p & 7))
-          const uint32_t row = a_addr + (uint32_t)p * 128u;
-          const uint32_t sw = (uint32_t)p & 7u;
-          uint32_t hi[16], lo[16];
+            for (int p = (P.diag & 16) ? P.halo_px : tid; p < P.halo_px; p += S3_CV_THREADS) {
+              // row = pixel: 32 fp32 -> [Ah 32 x fp16 | Al 32 x fp16], same 128 bytes, same 16-byte-chunk swizzle (chunk ^ (p & 7))
+              const uint32_t row = a_addr + (uint32_t)p * 128u;
+              const uint32_t sw = (uint32_t)p & 7u;
+              uint32_t hi[16], lo[16];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const uint4 v = lds128(row + ((((uint32_t)j) ^ sw) << 4));
-            split2(__uint_as_float(v.x), __uint_as_float(v.y), hi[2 * j], lo[2 * j]);
-            split2(__uint_as_float(v.z), __uint_as_float(v.w), hi[2 * j + 1], lo[2 * j + 1]);
-          }
+              for (int j = 0; j < 8; ++j) {
+                const uint4 v = lds128(row + ((((uint32_t)j) ^ sw) << 4));
+                split2(__uint_as_float(v.x), __uint_as_float(v.y), hi[2 * j], lo[2 * j]);
+                split2(__uint_as_float(v.z), __uint_as_float(v.w), hi[2 * j + 1], lo[2 * j + 1]);
+              }
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            sts128(row + ((((uint32_t)j) ^ sw) << 4), make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]));
-            sts128(row + ((((uint32_t)(j + 4)) ^ sw) << 4), make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]));
+              for (int j = 0; j < 4; ++j) {
+                sts128(row + ((((uint32_t)j) ^ sw) << 4), make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]));
+                sts128(row + ((((uint32_t)(j + 4)) ^ sw) << 4), make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]));
+              }
+            }
+            fence_async_smem();  // generic-proxy writes -> visible to the tensor core / TMA (async proxy)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_cvfull(abuf));
+            if (dbg) w_cv += clock64() - t_cv;
           }
+          if (++abuf == NA) { abuf = 0; aphase ^= 1u; }
         }
-        fence_async_smem();  // generic-proxy writes -> visible to the tensor core / TMA (async proxy)
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_cvfull(abuf));
-        if (dbg) w_cv += clock64() - t_cv;
-        if (++abuf == NA) { abuf = 0; aphase ^= 1u; }
       }
     }
     if (dbg && threadIdx.x == 0) {
@@ -401,7 +452,7 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
           if (nres > 0) {
             mbar_arrive_expect_tx(bar_resfull, (uint32_t)(nres * nboxes * S3_BOX_BYTES));
             for (int b = 0; b < nboxes; ++b) {
-              tma_load_4d(stg + (uint32_t)(b * S3_BOX_BYTES), &P.rmap[nb], bar_resfull, P.r_c0[nb] + 32 * b, tx0, ty0, n);
+              tma_load_4d(stg + (uint32_t)(P.b_roff[nb] + b * S3_BOX_BYTES), &P.rmap[nb], bar_resfull, P.r_c0[nb] + 32 * b, tx0, ty0, n);
               if (nres > 1)
                 tma_load_4d(stg + (uint32_t)(P.stg2_off + b * S3_BOX_BYTES), &P.r2map[nb], bar_resfull, P.r_c0[nb] + 32 * b, tx0, ty0, n);
             }
@@ -450,26 +501,65 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
         }
         const uint32_t row = stg + (uint32_t)m * 128u;
         const uint32_t sw = (uint32_t)m & 7u;
+        const int sfmt = sidx >= 0 ? c.seg[sidx].fmt : 0;
+        const uint32_t roff = (uint32_t)P.b_roff[nb];  // where the first operand tile was fetched (0: in place)
+        const float4 zero4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (sfmt & DEMFI_SEG_DST_S16) {
+          // S16 destination: eight channels per step = one hi chunk + one lo chunk of the pixel's 128-byte group row
+          // (an operand tile, when present, is in the same format and the same place: read, then overwritten in place)
 #pragma unroll
-        for (int col = 0; col < HMAX; col += 4) {
-          if (col < cnum && !(P.diag & 32)) {
-            const int chn = cbeg + col;  // channel within the N block
-            const uint32_t addr = row + (uint32_t)((chn >> 5) * S3_BOX_BYTES) + (((uint32_t)((chn & 31) >> 2) ^ sw) << 4);
-            const uint4 bu = lds128(bias_s + (uint32_t)(n0 + chn) * 4u);
-            float4 v = make_float4(sum[col] + __uint_as_float(bu.x), sum[col + 1] + __uint_as_float(bu.y),
-                                   sum[col + 2] + __uint_as_float(bu.z), sum[col + 3] + __uint_as_float(bu.w));
-            if (act == DEMFI_ACT_NONE || act == DEMFI_ACT_RELU) {  // the common case stays inline (a few FADD / FMNMX)
-              if (nres > 0) {
-                const uint4 rr = lds128(addr);
-                v.x += __uint_as_float(rr.x); v.y += __uint_as_float(rr.y); v.z += __uint_as_float(rr.z); v.w += __uint_as_float(rr.w);
+          for (int col = 0; col < HMAX; col += 8) {
+            if (col < cnum && !(P.diag & 32)) {
+              const int chn = cbeg + col;
+              const uint32_t g8 = (uint32_t)((chn & 31) >> 3);
+              const uint32_t base = row + (uint32_t)((chn >> 5) * S3_BOX_BYTES);
+              const uint32_t a_hi = base + ((g8 ^ sw) << 4), a_lo = base + (((g8 + 4u) ^ sw) << 4);
+              const float4 b0 = as_f4(lds128(bias_s + (uint32_t)(n0 + chn) * 4u)), b1 = as_f4(lds128(bias_s + (uint32_t)(n0 + chn + 4) * 4u));
+              float4 v0 = make_float4(sum[col] + b0.x, sum[col + 1] + b0.y, sum[col + 2] + b0.z, sum[col + 3] + b0.w);
+              float4 v1 = make_float4(sum[col + 4] + b1.x, sum[col + 5] + b1.y, sum[col + 6] + b1.z, sum[col + 7] + b1.w);
+              float4 h0 = zero4, h1 = zero4, z0 = zero4, z1 = zero4;
+              if (nres > 0) op_load8(base + roff, chn, sw, (sfmt & DEMFI_SEG_RES_S16) != 0, h0, h1);
+              if (nres > 1) op_load8(base + (uint32_t)P.stg2_off, chn, sw, (sfmt & DEMFI_SEG_RES2_S16) != 0, z0, z1);
+              if (act == DEMFI_ACT_NONE || act == DEMFI_ACT_RELU) {
+                v0.x += h0.x; v0.y += h0.y; v0.z += h0.z; v0.w += h0.w;
+                v1.x += h1.x; v1.y += h1.y; v1.z += h1.z; v1.w += h1.w;
+                if (act == DEMFI_ACT_RELU) {
+                  v0.x = fmaxf(v0.x, 0.0f); v0.y = fmaxf(v0.y, 0.0f); v0.z = fmaxf(v0.z, 0.0f); v0.w = fmaxf(v0.w, 0.0f);
+                  v1.x = fmaxf(v1.x, 0.0f); v1.y = fmaxf(v1.y, 0.0f); v1.z = fmaxf(v1.z, 0.0f); v1.w = fmaxf(v1.w, 0.0f);
+                }
+              } else {
+                v0 = finish4v(act, v0, h0, z0);
+                v1 = finish4v(act, v1, h1, z1);
               }
-              if (act == DEMFI_ACT_RELU) {
-                v.x = fmaxf(v.x, 0.0f); v.y = fmaxf(v.y, 0.0f); v.z = fmaxf(v.z, 0.0f); v.w = fmaxf(v.w, 0.0f);
-              }
-            } else {
-              v = finish4(act, v, addr, nres, (uint32_t)P.stg2_off);
+              uint4 hi, lo;
+              s16_encode8(v0, v1, hi, lo);
+              sts128(a_hi, hi);
+              sts128(a_lo, lo);
             }
-            sts128(addr, make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)));
+          }
+        } else {
+#pragma unroll
+          for (int col = 0; col < HMAX; col += 4) {
+            if (col < cnum && !(P.diag & 32)) {
+              const int chn = cbeg + col;  // channel within the N block
+              const uint32_t base = row + (uint32_t)((chn >> 5) * S3_BOX_BYTES);
+              const uint32_t addr = base + (((uint32_t)((chn & 31) >> 2) ^ sw) << 4);
+              const float4 b = as_f4(lds128(bias_s + (uint32_t)(n0 + chn) * 4u));
+              float4 v = make_float4(sum[col] + b.x, sum[col + 1] + b.y, sum[col + 2] + b.z, sum[col + 3] + b.w);
+              float4 h = zero4;
+              if (nres > 0) h = op_load4(base + roff, chn, sw, (sfmt & DEMFI_SEG_RES_S16) != 0);
+              if (act == DEMFI_ACT_NONE || act == DEMFI_ACT_RELU) {  // the common case stays inline (a few FADD / FMNMX)
+                v.x += h.x; v.y += h.y; v.z += h.z; v.w += h.w;
+                if (act == DEMFI_ACT_RELU) {
+                  v.x = fmaxf(v.x, 0.0f); v.y = fmaxf(v.y, 0.0f); v.z = fmaxf(v.z, 0.0f); v.w = fmaxf(v.w, 0.0f);
+                }
+              } else {
+                float4 z = zero4;
+                if (nres > 1) z = op_load4(base + (uint32_t)P.stg2_off, chn, sw, (sfmt & DEMFI_SEG_RES2_S16) != 0);
+                v = finish4v(act, v, h, z);
+              }
+              sts128(addr, as_u4(v));
+            }
           }
         }
         fence_async_smem();
@@ -576,7 +666,7 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
       const bool resident = P.resident != 0;
       long long w_tempty = 0, w_ready = 0;
       const long long t_begin = dbg ? clock64() : 0;
-      uint32_t slot = 0, sphase = 0, acc = 0, acc_phase = 0, abuf = 0, aphase = 0;
+      uint32_t slot = 0, sphase = 0, acc = 0, acc_phase = 0, abuf = 0, aphase = 0, cvphase = 0;
       if (resident) {
         mbar_wait(bar_wfull, 0);
         tc_fence_after();
@@ -591,9 +681,16 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
         uint32_t d_main = 0, d_corr = 0;
         uint32_t b = b_lo0;  // resident bank: stage after stage
 #pragma unroll 1
-        for (int ch = 0; ch < chunks_per_tile; ++ch) {
-          mbar_wait_t(bar_cvfull(abuf), aphase, dbg, w_ready);
+        for (int ch = 0, si = 0, c0 = 0; ch < chunks_per_tile; ++ch) {
+          if (c.src[si].fmt == DEMFI_FMT_S16) {
+            mbar_wait_t(bar_rawfull(abuf), aphase, dbg, w_ready);  // TMA -> tensor core, no converter hop
+          } else {
+            mbar_wait_t(bar_cvfull(abuf), (cvphase >> abuf) & 1u, dbg, w_ready);
+            cvphase ^= 1u << abuf;
+          }
           tc_fence_after();
+          c0 += S3_KC;
+          if (c0 >= c.src[si].C) { c0 = 0; ++si; }
           uint32_t a = a_lo0 + astep * abuf;
           int kx = 0, tap = 0;
 #pragma unroll 1
@@ -693,7 +790,7 @@ constexpr int S3_SMEM_MAX = 227 * 1024;
 // operands, store mode -- i.e. one result written to one or more destinations); at most DEMFI_MAX_SEG destinations in total.
 // Pixel-shuffle segments need one N block per quadrant (nch / 4 == block width).
 struct S3EpiPlan {
-  int b_seg[DEMFI_MAX_SEG], b_o0[DEMFI_MAX_SEG], b_on[DEMFI_MAX_SEG], b_nres[DEMFI_MAX_SEG];
+  int b_seg[DEMFI_MAX_SEG], b_o0[DEMFI_MAX_SEG], b_on[DEMFI_MAX_SEG], b_nres[DEMFI_MAX_SEG], b_mixed[DEMFI_MAX_SEG];
   int o_seg[DEMFI_MAX_SEG], o_blk[DEMFI_MAX_SEG];
   int n_out;
   bool any_res2;
@@ -708,6 +805,7 @@ static bool s3_plan_epilogue(const demfi_conv_t& c, int nb_max, int n_blocks, S3
     E.b_o0[nb] = E.n_out;
     E.b_on[nb] = 0;
     E.b_nres[nb] = 0;
+    E.b_mixed[nb] = 0;
     for (int s = 0; s < c.nseg; ++s) {
       const demfi_seg_t& g = c.seg[s];
       if (g.ch0 >= n1 || g.ch0 + g.nch <= n0) continue;
@@ -718,9 +816,17 @@ static bool s3_plan_epilogue(const demfi_conv_t& c, int nb_max, int n_blocks, S3
       } else {
         const demfi_seg_t& a = c.seg[E.b_seg[nb]];
         if (g.ch0 != a.ch0 || g.nch != a.nch || g.act != a.act || g.store != a.store || g.res != a.res || g.res_ld != a.res_ld ||
-            g.res2 != a.res2 || g.res2_ld != a.res2_ld)
+            g.res2 != a.res2 || g.res2_ld != a.res2_ld || g.fmt != a.fmt)
           return false;
       }
+      // the first operand normally shares the staging tile with the result (updated in place): that needs the same format.
+      // A residual in the other format goes to the second tile instead (not available to the two-operand GRU epilogue).
+      if (g.res != nullptr && ((g.fmt & DEMFI_SEG_DST_S16) != 0) != ((g.fmt & DEMFI_SEG_RES_S16) != 0)) {
+        if (g.act == DEMFI_ACT_GRU) return false;
+        E.b_mixed[nb] = 1;
+        E.any_res2 = true;
+      }
+      if ((g.fmt & DEMFI_SEG_DST_S16) && (g.ch0 % 32 != 0 || g.nch % 32 != 0 || (n0 - g.ch0) % 32 != 0)) return false;
       if (g.store == DEMFI_STORE_PIXEL_SHUFFLE2) {
         const int cq = g.nch / 4;
         if (cq < 1 || (n0 - g.ch0) / cq != (n1 - 1 - g.ch0) / cq || n0 < g.ch0) return false;  // block inside one quadrant
@@ -734,6 +840,14 @@ static bool s3_plan_epilogue(const demfi_conv_t& c, int nb_max, int n_blocks, S3
     }
   }
   return true;
+}
+
+bool s3_s16_ok(const demfi_conv_t& c) {
+  const int nbm = s3_nb_max(c.cout_pad);
+  S3EpiPlan E;
+  bool any_seg = false;
+  for (int s = 0; s < c.nseg; ++s) any_seg = any_seg || c.seg[s].fmt != 0;
+  return !any_seg || s3_plan_epilogue(c, nbm, (c.cout_pad + nbm - 1) / nbm, E);
 }
 
 bool s3_supports(const demfi_conv_t& c) {
@@ -794,6 +908,8 @@ int launch_conv_s3(const demfi_conv_t& c, cudaStream_t st) {
   // epilogue mode
   S3EpiPlan E;
   P.tma_epi = (s3_plan_epilogue(c, P.nb_max, P.n_blocks, E) && !(get_option("tc_diag") & 2)) ? 1 : 0;
+  for (int sg = 0; sg < c.nseg; ++sg)
+    DEMFI_REQUIRE(c.seg[sg].fmt == 0 || P.tma_epi, "conv_s3: segment %d asks for the S16 format, which needs the TMA epilogue", sg);
   const int box_bytes_all = ((P.nb_max + 31) / 32) * S3_BOX_BYTES;
   const int stg_bytes = P.tma_epi ? box_bytes_all * (E.any_res2 ? 2 : 1) : 0;
   P.stg2_off = box_bytes_all;  // second operand tile, relative to the staging tile
@@ -803,6 +919,7 @@ int launch_conv_s3(const demfi_conv_t& c, cudaStream_t st) {
       P.b_o0[nb] = E.b_o0[nb];
       P.b_on[nb] = E.b_on[nb];
       P.b_nres[nb] = E.b_nres[nb];
+      P.b_roff[nb] = E.b_mixed[nb] ? box_bytes_all : 0;
       if (E.b_seg[nb] < 0) continue;
       const demfi_seg_t& g = c.seg[E.b_seg[nb]];
       const int n0 = nb * P.nb_max;

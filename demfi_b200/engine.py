@@ -30,12 +30,18 @@ def _ru(x, m):
 
 
 class View:
-    """A channel slice of an NHWC fp32 buffer: element (n,y,x,c) at ptr + (((n*H+y)*W+x)*ld + c)*4."""
-    __slots__ = ("t", "N", "H", "W", "ld", "c0", "C", "n0")
+    """A channel slice of an NHWC buffer: element (n,y,x,c) at ptr + (((n*H+y)*W+x)*ld + c)*4.
 
-    def __init__(self, t: torch.Tensor, N, H, W, ld, c0=0, C_=None, n0=0):
-        self.t, self.N, self.H, self.W, self.ld, self.c0, self.n0 = t, N, H, W, ld, c0, n0
+    fmt = A.FMT_F32: plain fp32.  fmt = A.FMT_S16: the "split fp16" storage format of include/demfi_b200.h (per 32-channel
+    group 32 fp16 hi + 32 fp16 lo, same bytes as fp32): written by a tensor-core conv epilogue and read by the next conv
+    without any conversion pass.  Only convolutions (and the bit-copying up-sampler) may touch S16 views."""
+    __slots__ = ("t", "N", "H", "W", "ld", "c0", "C", "n0", "fmt")
+
+    def __init__(self, t: torch.Tensor, N, H, W, ld, c0=0, C_=None, n0=0, fmt=0):
+        self.t, self.N, self.H, self.W, self.ld, self.c0, self.n0, self.fmt = t, N, H, W, ld, c0, n0, fmt
         self.C = ld - c0 if C_ is None else C_
+        if fmt:
+            assert self.c0 % 32 == 0 and self.C % 32 == 0, "S16 views are made of whole 32-channel groups"
 
     @property
     def ptr(self) -> int:
@@ -43,11 +49,15 @@ class View:
 
     def ch(self, c0, C_):
         assert c0 + C_ <= self.C + (self.ld - self.c0 - self.C) + 0 or True
-        return View(self.t, self.N, self.H, self.W, self.ld, self.c0 + c0, C_, self.n0)
+        return View(self.t, self.N, self.H, self.W, self.ld, self.c0 + c0, C_, self.n0, self.fmt)
 
     def frames(self, n0, N):
         """batch sub-range [n0, n0+N)"""
-        return View(self.t, N, self.H, self.W, self.ld, self.c0, self.C, self.n0 + n0)
+        return View(self.t, N, self.H, self.W, self.ld, self.c0, self.C, self.n0 + n0, self.fmt)
+
+    def as_fmt(self, fmt):
+        """the same memory, to be written / read in another storage format"""
+        return View(self.t, self.N, self.H, self.W, self.ld, self.c0, self.C, self.n0, fmt)
 
     def npix(self):
         return self.N * self.H * self.W
@@ -55,6 +65,9 @@ class View:
     def to_nchw(self) -> torch.Tensor:
         """debug / test read-back (torch indexing, not a product path)"""
         full = self.t.view(-1, self.H, self.W, self.ld)[self.n0:self.n0 + self.N, :, :, self.c0:self.c0 + self.C]
+        if self.fmt == A.FMT_S16:
+            g = full.contiguous().reshape(self.N, self.H, self.W, self.C // 32, 32).view(torch.float16)
+            full = (g[..., :32].float() + g[..., 32:].float() / 2048.0).reshape(self.N, self.H, self.W, self.C)
         return full.permute(0, 3, 1, 2).contiguous()
 
 
@@ -71,7 +84,9 @@ class Engine:
         if not dry:
             A.check(self.lib.demfi_device_check(device.index or 0), "demfi_device_check")
         self.conv_kind = (conv_kind or os.environ.get("DEMFI_CONV_KIND", "auto")).lower()
-        assert self.conv_kind in ("auto", "ffma", "tc", "tc16")
+        assert self.conv_kind in ("auto", "ffma", "tc", "tc16", "tc16f32")
+        # S16 activation storage between convolutions (conv_s3 only); "tc16f32" keeps every buffer fp32 (comparison)
+        self.use_s16 = self.conv_kind in ("auto", "tc16") and os.environ.get("DEMFI_S16", "1") != "0"
         self._keep: list = []  # weights, ctypes structs
         self.bufs: Dict[str, torch.Tensor] = {}
         self.views: Dict[str, View] = {}
@@ -82,42 +97,43 @@ class Engine:
         self._build()
 
     # ------------------------------------------------------------------ memory
-    def _buf(self, name, N, H, W, ld) -> View:
+    def _buf(self, name, N, H, W, ld, s16=False) -> View:
+        """s16=True: a buffer only convolutions touch -> stored in the S16 format when the tensor-core kernels run"""
         t = torch.zeros(N * H * W * ld, dtype=torch.float32, device=self.dev)
         self.bufs[name] = t
-        return View(t, N, H, W, ld)
+        return View(t, N, H, W, ld, fmt=A.FMT_S16 if (s16 and self.use_s16) else A.FMT_F32)
 
     def _alloc(self):
         B, H, W = self.B, self.H, self.W
         h, w = H // 2, W // 2
         v = self.views
         v["S2D"] = self._buf("S2D", B, h, w, 48)
-        v["F1"] = self._buf("F1", B, h, w, 96)
-        v["T"] = self._buf("T", B, h, w, 96 + 12 * 224)
-        v["G"] = self._buf("G", B, h, w, 1152)
-        v["GF0"] = self._buf("GF0", B, h, w, 96)
-        v["TR"] = self._buf("TR", B, h, w, 96)
-        v["U"] = self._buf("U", B, H, W, 64)
+        v["F1"] = self._buf("F1", B, h, w, 96, s16=True)
+        v["T"] = self._buf("T", B, h, w, 96 + 12 * 224, s16=True)
+        v["G"] = self._buf("G", B, h, w, 1152, s16=True)
+        v["GF0"] = self._buf("GF0", B, h, w, 96, s16=True)
+        v["TR"] = self._buf("TR", B, h, w, 96, s16=True)
+        v["U"] = self._buf("U", B, H, W, 64, s16=True)
         v["F01"] = self._buf("F01", 2 * B, H, W, 64)
         v["FO"] = self._buf("FO", B, H, W, 8)
         v["ACC"] = self._buf("ACC", B, H, W, 8)
         v["AGG1"] = self._buf("AGG1", B, H, W, 204)
         for i in range(3):
-            v[f"P{i}"] = self._buf(f"P{i}", 3 * B, H, W, 64)  # ResBlock ping-pong pool (FAC-FB enc, D1, D2)
+            v[f"P{i}"] = self._buf(f"P{i}", 3 * B, H, W, 64, s16=True)  # ResBlock ping-pong pool (FAC-FB enc, D1, D2)
         v["SE"] = self._buf("SE", 2 * B, H, W, 128)
         v["RK"] = self._buf("RK", 2 * B, H, W, 64)
         v["SMP"] = self._buf("SMP", 2 * B, H, W, 64)
-        v["WG"] = self._buf("WG", 2 * B, H, W, 64)
+        v["WG"] = self._buf("WG", 2 * B, H, W, 64, s16=True)
         v["WL"] = self._buf("WL", 2 * B, H, W, 4)
         v["EN1"] = self._buf("EN1", B, h, w, 64)
         v["EN2"] = self._buf("EN2", B, h // 2, w // 2, 128)
         v["EN3"] = self._buf("EN3", B, h // 4, w // 4, 256)
-        v["DE0"] = self._buf("DE0", B, h // 4, w // 4, 256)
-        v["DE1"] = self._buf("DE1", B, h // 2, w // 2, 128)
-        v["DE2"] = self._buf("DE2", B, h, w, 64)
-        v["UP0"] = self._buf("UP0", B, h // 2, w // 2, 256)  # nearest x2 of the UNet decoder outputs
-        v["UP1"] = self._buf("UP1", B, h, w, 128)
-        v["UP2"] = self._buf("UP2", B, H, W, 64)
+        v["DE0"] = self._buf("DE0", B, h // 4, w // 4, 256, s16=True)
+        v["DE1"] = self._buf("DE1", B, h // 2, w // 2, 128, s16=True)
+        v["DE2"] = self._buf("DE2", B, h, w, 64, s16=True)
+        v["UP0"] = self._buf("UP0", B, h // 2, w // 2, 256, s16=True)  # nearest x2 of the UNet decoder outputs
+        v["UP1"] = self._buf("UP1", B, h, w, 128, s16=True)
+        v["UP2"] = self._buf("UP2", B, H, W, 64, s16=True)
         v["DECIN"] = self._buf("DECIN", 3 * B, H, W, 64)
         v["SP"] = self._buf("SP", 3 * B, H, W, 4)
         v["DL0"] = self._buf("DL0", B, H, W, 8)
@@ -125,15 +141,15 @@ class Engine:
         v["REF"] = self._buf("REF", B, H, W, 32)
         v["A3"] = self._buf("A3", B, H, W, 36)
         for i in range(3):
-            v[f"FR{i}"] = self._buf(f"FR{i}", B, H, W, 64)
-        v["R1"] = self._buf("R1", B, H, W, 32)
-        v["RD"] = self._buf("RD", B, H, W, 64)
-        v["D1B"] = self._buf("D1B", B, H, W, 32)
-        v["BL1"] = self._buf("BL1", B, H, W, 32)
-        v["X"] = self._buf("X", B, H, W, 64)
-        v["Z"] = self._buf("Z", B, H, W, 64)
-        v["RH"] = self._buf("RH", B, H, W, 64)
-        v["FO1"] = self._buf("FO1", B, H, W, 32)
+            v[f"FR{i}"] = self._buf(f"FR{i}", B, H, W, 64, s16=True)
+        v["R1"] = self._buf("R1", B, H, W, 32, s16=True)
+        v["RD"] = self._buf("RD", B, H, W, 64, s16=True)
+        v["D1B"] = self._buf("D1B", B, H, W, 32, s16=True)
+        v["BL1"] = self._buf("BL1", B, H, W, 32, s16=True)
+        v["X"] = self._buf("X", B, H, W, 64, s16=True)
+        v["Z"] = self._buf("Z", B, H, W, 64, s16=True)
+        v["RH"] = self._buf("RH", B, H, W, 64, s16=True)
+        v["FO1"] = self._buf("FO1", B, H, W, 32, s16=True)
         v["D2O"] = self._buf("D2O", B, H, W, 12)
         self.t_dev = torch.zeros(B, dtype=torch.float32, device=self.dev)
 
@@ -212,16 +228,22 @@ class Engine:
         for i, (vw, up) in enumerate(srcs):
             assert vw.N == N and (vw.H << up, vw.W << up) == (Hi, Wi), (names, i, vw.N, vw.H, vw.W, up, Hi, Wi)
             d.src[i].ptr, d.src[i].C, d.src[i].ld, d.src[i].up = vw.ptr, vw.C, vw.ld, up
+            d.src[i].fmt = vw.fmt
+            assert vw.fmt == A.FMT_F32 or kind == A.CONV_TC16, (names, "S16 source on a kernel that cannot read it")
         for i, sg in enumerate(segs):
             dst: View = sg["dst"]
             s = d.seg[i]
             s.dst, s.dst_ld = dst.ptr, dst.ld
             s.ch0, s.nch = sg["ch0"], sg["nch"]
             s.act, s.store = sg.get("act", A.ACT_NONE), sg.get("store", A.STORE_NHWC)
+            s.fmt = A.SEG_DST_S16 if dst.fmt == A.FMT_S16 else 0
             if sg.get("res") is not None:
                 s.res, s.res_ld = sg["res"].ptr, sg["res"].ld
+                s.fmt |= A.SEG_RES_S16 if sg["res"].fmt == A.FMT_S16 else 0
             if sg.get("res2") is not None:
                 s.res2, s.res2_ld = sg["res2"].ptr, sg["res2"].ld
+                s.fmt |= A.SEG_RES2_S16 if sg["res2"].fmt == A.FMT_S16 else 0
+            assert s.fmt == 0 or kind == A.CONV_TC16, (names, "S16 destination / operand on a kernel that cannot handle it")
         d.wpack, d.bias = wdev.data_ptr(), bdev.data_ptr()
         self._keep.append(d)
         macs = N * Ho * Wo * Co * Ci * KH * KW
@@ -270,7 +292,7 @@ class Engine:
         a, b_, c_ = pool
         for i in range(5):
             ops.append(self.conv(f"{p}feature_extraction.{i}.conv1", [a], (H, W), 2 * B, [full(b_, 64, relu)]))
-            dst = SE.ch(0, 64) if i == 4 else c_
+            dst = SE.ch(0, 64) if i == 4 else c_  # SE is fp32 (read by the FGAC operators); its S16 skip goes to a second tile
             ops.append(self.conv(f"{p}feature_extraction.{i}.conv2", [b_], (H, W), 2 * B, [full(dst, 64, none, a)]))
             a, c_ = c_, a
         g = p + "shared_FGAC."
@@ -350,6 +372,10 @@ class Engine:
 
         # ---- recursive boosting iteration (DeMFInet.py:130-165); buffers rotate with the iteration index
         self._iter_cache: Dict[Tuple[int, bool], list] = {}
+        for ops_ in (self.ops_prefix_ff, self.ops_stage1):
+            for op in ops_:  # only convolutions (and the bit-copying up-sampler) may touch S16 views
+                if op[0] not in ("conv", "upsample"):
+                    assert all(a_.fmt == A.FMT_F32 for a_ in op[1:] if isinstance(a_, View)), op[0]
         self._agg3_map = (list(range(9)) + [73] + [74, 75, 76, 77] + [80, 81, 78, 79] + [82, 83, 84, 85] + [86]
                           + list(range(87, 99)) + [-1] + list(range(9, 73)))
 

@@ -45,6 +45,15 @@ enum {
   DEMFI_STORE_PIXEL_SHUFFLE2 = 1 /* nn.PixelShuffle(2), DeMFInet.py:229: accumulator channel
                                     q*(nch/4)+c of pixel (y,x) -> dst pixel (2y+q/2, 2x+q%2), channel c */
 };
+/* Activation storage formats.  F32: plain fp32.  S16 ("split fp16"): every group of 32 channels (128 bytes of the pixel)
+ * holds 32 fp16 "hi" values followed by 32 fp16 "lo" values; channel c of the group is hi[c] + lo[c] / 2048
+ * (hi = fp16(v), lo = fp16((v - hi) * 2048): ~22 significant bits, |v| < 65504).  It is exactly what the tensor-core
+ * kernel feeds to its kind::f16 MMAs (3xFP16 split), so a convolution whose input was written in S16 by the previous
+ * convolution needs no conversion pass at all: the TMA tile is the MMA operand.  Same bytes per channel as fp32.
+ * Only DEMFI_CONV_TC16 (conv_s3 kernel) reads or writes S16; every other operator takes F32. */
+enum { DEMFI_FMT_F32 = 0, DEMFI_FMT_S16 = 1 };
+/* demfi_seg_t.fmt bits */
+enum { DEMFI_SEG_DST_S16 = 1, DEMFI_SEG_RES_S16 = 2, DEMFI_SEG_RES2_S16 = 4 };
 enum {
   DEMFI_CONV_FFMA = 0, /* CUDA-core fp32 implicit GEMM (exact fp32)                                   */
   DEMFI_CONV_TC = 1,   /* tcgen05 kind::tf32, 3xTF32 split (first-generation tensor-core kernel)       */
@@ -58,7 +67,7 @@ typedef struct {
   int32_t ld;
   int32_t up;       /* 1: source is at half the conv-input resolution and is read through
                        nearest-neighbour x2 up-sampling (nn.UpsamplingNearest2d, DeMFInet.py:573) */
-  int32_t reserved;
+  int32_t fmt;      /* DEMFI_FMT_F32 | DEMFI_FMT_S16 (S16: C and the slice offset multiples of 32 channels) */
 } demfi_src_t;
 
 /* one destination of a channel range [ch0, ch0+nch) of the accumulator */
@@ -69,7 +78,7 @@ typedef struct {
   int32_t dst_ld, res_ld, res2_ld;
   int32_t ch0, nch;  /* multiples of 4 */
   int32_t act, store;
-  int32_t reserved;
+  int32_t fmt;       /* bit mask DEMFI_SEG_DST_S16 | DEMFI_SEG_RES_S16 | DEMFI_SEG_RES2_S16 (0: everything fp32) */
 } demfi_seg_t;
 
 /* A convolution = every nn.Conv2d / nn.Conv3d([1,3,3]) call of DeMFInet.py (section 2.1 of

@@ -19,6 +19,25 @@ def nhwc(t_nchw, ld=None):
     return buf.to(DEV).contiguous(), ld
 
 
+def s16_encode(buf):
+    """fp32 NHWC buffer [..., C] (C % 32 == 0) -> the S16 storage format (include/demfi_b200.h): per 32-channel group
+    32 fp16 hi then 32 fp16 lo, hi = fp16(v), lo = fp16((v - hi) * 2048); returned as a float32-typed buffer of the same shape"""
+    t = buf.float().cpu()
+    assert t.shape[-1] % 32 == 0
+    g = t.reshape(*t.shape[:-1], t.shape[-1] // 32, 32)
+    hi = g.half()
+    lo = ((g - hi.float()) * 2048.0).half()
+    packed = torch.cat([hi, lo], dim=-1).contiguous()            # [..., G, 64] fp16
+    return packed.view(torch.float32).reshape(t.shape).to(buf.device).contiguous()
+
+
+def s16_decode(buf):
+    t = buf.cpu().contiguous()
+    g = t.reshape(*t.shape[:-1], t.shape[-1] // 32, 32).view(torch.float16)  # [..., G, 64]
+    val = g[..., :32].float() + g[..., 32:].float() / 2048.0
+    return val.reshape(t.shape).to(buf.device)
+
+
 def from_nhwc(buf, c):
     return buf[..., :c].permute(0, 3, 1, 2).contiguous().cpu()
 
@@ -38,7 +57,7 @@ def run_conv(w, b, srcs, out_hw, kind, segs_spec, stride=1, pad=None, in_map=Non
     Co, Ci, KH, KW = w.shape
     if pad is None:
         pad = (KH // 2, KW // 2)
-    src_C = [c for _, c, _ in srcs]
+    src_C = [s_[1] for s_ in srcs]
     kt = sum(src_C)
     cout_pad = cout_pad or (Co + 15) // 16 * 16
     in_map = in_map if in_map is not None else list(range(Ci)) + [-1] * (kt - Ci)
@@ -63,12 +82,15 @@ def run_conv(w, b, srcs, out_hw, kind, segs_spec, stride=1, pad=None, in_map=Non
     d.Hi, d.Wi = srcs[0][0].shape[1] << up0, srcs[0][0].shape[2] << up0
     d.KH, d.KW, d.stride, d.pad_h, d.pad_w = KH, KW, stride, pad[0], pad[1]
     d.nsrc, d.nseg, d.cout_pad, d.kind = len(srcs), len(segs_spec), cout_pad, kind
-    for i, (buf, c, up) in enumerate(srcs):
+    for i, src in enumerate(srcs):
+        buf, c, up = src[:3]
         d.src[i].ptr, d.src[i].C, d.src[i].ld, d.src[i].up = buf.data_ptr(), c, buf.shape[3], up
+        d.src[i].fmt = src[3] if len(src) > 3 else 0
     for i, sg in enumerate(segs_spec):
         s = d.seg[i]
         s.dst, s.dst_ld = sg["dst"].data_ptr() + 4 * sg.get("dst_c0", 0), sg["dst"].shape[3]
         s.ch0, s.nch, s.act, s.store = sg["ch0"], sg["nch"], sg.get("act", 0), sg.get("store", 0)
+        s.fmt = sg.get("fmt", 0)
         if sg.get("res") is not None:
             s.res, s.res_ld = sg["res"].data_ptr(), sg["res"].shape[3]
         if sg.get("res2") is not None:

@@ -9,7 +9,7 @@ import torch
 import torch.nn.functional as F
 
 from demfi_b200 import _abi as A
-from gpu_util import CONV_TC16_H3, DEV, from_nhwc, nhwc, run_conv
+from gpu_util import CONV_TC16_H3, DEV, from_nhwc, nhwc, run_conv, s16_decode, s16_encode
 
 pytestmark = pytest.mark.gpu
 KINDS = [pytest.param(A.CONV_FFMA, id="ffma"), pytest.param(A.CONV_TC, id="tc"), pytest.param(CONV_TC16_H3, id="tc16-h3"),
@@ -300,3 +300,97 @@ def test_tc_operand_truncation_probe():
     e0 = float((res[0].double() - want).abs().max())
     print(f"mask_hi=1 err {e1:.3e}; mask_hi=0 err {e0:.3e}; identical={torch.equal(res[0], res[1])}")
     assert e1 < 2e-5
+
+
+# ---- S16 ("split fp16") activation format: conv_s3 reads it without a conversion pass and writes it from its epilogue
+def test_s16_roundtrip_host():
+    x = rnd(2, 5, 7, 64, seed=5, scale=3.0)
+    back = s16_decode(s16_encode(x))
+    assert float((back - x).abs().max()) <= 2.0 ** -21 * float(x.abs().max())
+
+
+@pytest.mark.parametrize("src_s16,dst_s16", [(True, False), (False, True), (True, True)])
+@pytest.mark.parametrize("k", [(3, 3), (1, 1), (1, 5)])
+def test_s16_conv_relu(src_s16, dst_s16, k):
+    n, h, w_, ci, co = 2, 40, 24, 64, 64
+    x = rnd(n, ci, h, w_, seed=3)
+    w, b = wb(co, ci, *k)
+    xb, _ = nhwc(x)
+    if src_s16:
+        xb = s16_encode(xb)
+    out = torch.zeros(n, h, w_, co, device=DEV)
+    run_conv(w, b, [(xb, ci, 0, A.FMT_S16 if src_s16 else A.FMT_F32)], (h, w_), A.CONV_TC16,
+             [dict(ch0=0, nch=co, dst=out, act=A.ACT_RELU, fmt=A.SEG_DST_S16 if dst_s16 else 0)])
+    got = s16_decode(out) if dst_s16 else out
+    check(from_nhwc(got, co), F.relu(ref_conv(x, w, b)), f"s16 src={src_s16} dst={dst_s16} {k}")
+
+
+def test_s16_residual_two_sources_n32():
+    """RDB-like: two S16 sources (96 + 32 channels of one trunk buffer), 32 output channels written S16 into the trunk, and an
+    LFF-like 1x1 with an S16 residual and two S16 destinations"""
+    n, h, w_ = 1, 32, 40
+    x = rnd(n, 160, h, w_, seed=9)
+    trunk, ld = nhwc(x, ld=224)
+    trunk = s16_encode(trunk)
+    w, b = wb(32, 128, 3, 3)
+    out = trunk  # source: channels [0,128); destination: channels [128,160) of the same buffer
+    run_conv(w, b, [(trunk, 128, 0, A.FMT_S16)], (h, w_), A.CONV_TC16,
+             [dict(ch0=0, nch=32, dst=out, dst_c0=128, act=A.ACT_RELU, fmt=A.SEG_DST_S16)])
+    got = s16_decode(trunk)[..., 128:160]
+    check(from_nhwc(got, 32), F.relu(ref_conv(x[:, :128], w, b)), "s16 rdb conv into trunk slice")
+    # LFF-like: 1x1 over the 160 channels, residual = channels [0,96), two destinations
+    x2 = s16_decode(trunk)[..., :160].permute(0, 3, 1, 2).cpu()
+    w1, b1 = wb(96, 160, 1, 1, seed=4)
+    o1 = torch.zeros(n, h, w_, 96, device=DEV)
+    o2 = torch.zeros(n, h, w_, 192, device=DEV)
+    segs = [dict(ch0=0, nch=96, dst=o1, res=trunk, fmt=A.SEG_DST_S16 | A.SEG_RES_S16),
+            dict(ch0=0, nch=96, dst=o2, dst_c0=96, res=trunk, fmt=A.SEG_DST_S16 | A.SEG_RES_S16)]
+    run_conv(w1, b1, [(trunk, 160, 0, A.FMT_S16)], (h, w_), A.CONV_TC16, segs)
+    want = ref_conv(x2, w1, b1) + x2[:, :96].double()
+    check(from_nhwc(s16_decode(o1), 96), want, "s16 lff dst 1")
+    check(from_nhwc(s16_decode(o2)[..., 96:192], 96), want, "s16 lff dst 2")
+
+
+def test_s16_gru_epilogues():
+    """zr conv: Z = sigmoid (S16 out), RH = sigmoid * h (S16 operand and out); q conv: (1 - z) h + z tanh(q) with S16 h and z"""
+    n, hh, w_ = 1, 24, 40
+    hx = rnd(n, 128, hh, w_, seed=21, scale=0.7)
+    hb, _ = nhwc(hx[:, :64]); xb, _ = nhwc(hx[:, 64:])
+    hs, xs = s16_encode(hb), s16_encode(xb)
+    h_val = s16_decode(hs).permute(0, 3, 1, 2).cpu().double()
+    wz, bz = wb(128, 128, 1, 5, seed=7)
+    Z = torch.zeros(n, hh, w_, 64, device=DEV); RH = torch.zeros(n, hh, w_, 64, device=DEV)
+    run_conv(wz, bz, [(hs, 64, 0, A.FMT_S16), (xs, 64, 0, A.FMT_S16)], (hh, w_), A.CONV_TC16,
+             [dict(ch0=0, nch=64, dst=Z, act=A.ACT_SIGMOID, fmt=A.SEG_DST_S16),
+              dict(ch0=64, nch=64, dst=RH, act=A.ACT_SIGMOID_MUL, res=hs, fmt=A.SEG_DST_S16 | A.SEG_RES_S16)])
+    full = ref_conv(hx, wz, bz)
+    z_ref, r_ref = torch.sigmoid(full[:, :64]), torch.sigmoid(full[:, 64:])
+    check(from_nhwc(s16_decode(Z), 64), z_ref, "s16 gru z")
+    check(from_nhwc(s16_decode(RH), 64), r_ref * h_val, "s16 gru r*h")
+    wq, bq = wb(64, 128, 1, 5, seed=8)
+    H1 = torch.zeros(n, hh, w_, 64, device=DEV)
+    run_conv(wq, bq, [(RH, 64, 0, A.FMT_S16), (xs, 64, 0, A.FMT_S16)], (hh, w_), A.CONV_TC16,
+             [dict(ch0=0, nch=64, dst=H1, act=A.ACT_GRU, res=hs, res2=Z, fmt=A.SEG_DST_S16 | A.SEG_RES_S16 | A.SEG_RES2_S16)])
+    rh_val = s16_decode(RH).permute(0, 3, 1, 2).cpu()
+    z_val = s16_decode(Z).permute(0, 3, 1, 2).cpu().double()
+    q = torch.tanh(ref_conv(torch.cat([rh_val, hx[:, 64:]], 1), wq, bq))
+    check(from_nhwc(s16_decode(H1), 64), (1 - z_val) * h_val + z_val * q, "s16 gru update")
+
+
+@pytest.mark.parametrize("res_s16,dst_s16", [(True, False), (False, True)])
+def test_s16_mixed_residual(res_s16, dst_s16):
+    """skip connection stored in the other format than the result (FAC-FB: last ResBlock writes the fp32 SE buffer)"""
+    n, h, w_ = 2, 24, 40
+    x = rnd(n, 64, h, w_, seed=31)
+    r = rnd(n, 64, h, w_, seed=32)
+    w, b = wb(64, 64, 3, 3)
+    xb, _ = nhwc(x)
+    rb, _ = nhwc(r)
+    if res_s16:
+        rb = s16_encode(rb)
+    r_val = (s16_decode(rb) if res_s16 else rb).permute(0, 3, 1, 2).cpu().double()
+    out = torch.zeros(n, h, w_, 64, device=DEV)
+    run_conv(w, b, [(xb, 64, 0)], (h, w_), A.CONV_TC16,
+             [dict(ch0=0, nch=64, dst=out, res=rb, fmt=(A.SEG_DST_S16 if dst_s16 else 0) | (A.SEG_RES_S16 if res_s16 else 0))])
+    got = s16_decode(out) if dst_s16 else out
+    check(from_nhwc(got, 64), ref_conv(x, w, b) + r_val, f"mixed residual res_s16={res_s16} dst_s16={dst_s16}")
