@@ -689,6 +689,7 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
             cvphase ^= 1u << abuf;
           }
           tc_fence_after();
+          const bool k2 = c.src[si].C - c0 > 16;  // channels 16..31 of the chunk exist (else they are TMA zero fill: skip their MMAs)
           c0 += S3_KC;
           if (c0 >= c.src[si].C) { c0 = 0; ++si; }
           uint32_t a = a_lo0 + astep * abuf;
@@ -710,16 +711,28 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
               b = b_lo0 + gstep * slot;
             }
             const int run = min(min(taps - tap, seg_len - fill), gleft);
+            if (k2) {
 #pragma unroll 1
-            for (int t = 0; t < run; ++t) {
-              umma_f16_ss2(d_main, a, a_hi, b, b_hi, idesc_2n, accum);         // Ah x [Bh;Bl]  k 0..15
-              umma_f16_ss2(d_main, a + 2u, a_hi, b + 2u, b_hi, idesc_2n, 1u);  //               k 16..31
-              umma_f16_ss2(d_corr, a + 4u, a_hi, b, b_hi, idesc_n, 1u);        // Al x Bh
-              umma_f16_ss2(d_corr, a + 6u, a_hi, b + 2u, b_hi, idesc_n, 1u);
-              accum = 1u;
-              b += bstep;
-              a += 8u;
-              if (++kx == KW) { kx = 0; a += row_skip; }
+              for (int t = 0; t < run; ++t) {
+                umma_f16_ss2(d_main, a, a_hi, b, b_hi, idesc_2n, accum);         // Ah x [Bh;Bl]  k 0..15
+                umma_f16_ss2(d_main, a + 2u, a_hi, b + 2u, b_hi, idesc_2n, 1u);  //               k 16..31
+                umma_f16_ss2(d_corr, a + 4u, a_hi, b, b_hi, idesc_n, 1u);        // Al x Bh
+                umma_f16_ss2(d_corr, a + 6u, a_hi, b + 2u, b_hi, idesc_n, 1u);
+                accum = 1u;
+                b += bstep;
+                a += 8u;
+                if (++kx == KW) { kx = 0; a += row_skip; }
+              }
+            } else {  // a chunk of <= 16 channels (tiny Cin, ragged last chunk): one k-step per product
+#pragma unroll 1
+              for (int t = 0; t < run; ++t) {
+                umma_f16_ss2(d_main, a, a_hi, b, b_hi, idesc_2n, accum);
+                umma_f16_ss2(d_corr, a + 4u, a_hi, b, b_hi, idesc_n, 1u);
+                accum = 1u;
+                b += bstep;
+                a += 8u;
+                if (++kx == KW) { kx = 0; a += row_skip; }
+              }
             }
             tap += run;
             fill += run;

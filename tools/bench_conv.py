@@ -15,7 +15,7 @@ from demfi_b200 import _abi as A
 DEV = torch.device("cuda:0")
 
 
-def make_conv(kind, n, h, w, srcC, co, k, act=A.ACT_RELU, seed=0, res=False):
+def make_conv(kind, n, h, w, srcC, co, k, act=A.ACT_RELU, seed=0, res=False, s16=False):
     lib = A.lib()
     g = torch.Generator().manual_seed(seed)
     ci = sum(srcC)
@@ -37,14 +37,22 @@ def make_conv(kind, n, h, w, srcC, co, k, act=A.ACT_RELU, seed=0, res=False):
         buf = torch.randn(n, h, w, c, device=DEV)
         keep.append(buf)
         d.src[i].ptr, d.src[i].C, d.src[i].ld, d.src[i].up = buf.data_ptr(), c, c, 0
+        if s16 and c % 32 == 0:
+            buf.copy_(torch.randn(n, h, w, c * 2, device=DEV).half().view(torch.float32))  # valid fp16 bit patterns
+            d.src[i].fmt = A.FMT_S16
     ld = (co + 3) // 4 * 4
     out = torch.zeros(n, h, w, ld, device=DEV)
     keep.append(out)
     d.seg[0].dst, d.seg[0].dst_ld, d.seg[0].ch0, d.seg[0].nch, d.seg[0].act = out.data_ptr(), ld, 0, ld, act
+    if s16 and co % 32 == 0:
+        d.seg[0].fmt = A.SEG_DST_S16
     if res:
         rb = torch.randn(n, h, w, ld, device=DEV)
         keep.append(rb)
         d.seg[0].res, d.seg[0].res_ld = rb.data_ptr(), ld
+        if s16 and co % 32 == 0:
+            rb.copy_(torch.randn(n, h, w, ld * 2, device=DEV).half().view(torch.float32))
+            d.seg[0].fmt |= A.SEG_RES_S16
     d.wpack, d.bias = keep[0].data_ptr(), keep[1].data_ptr()
     return d, keep
 
@@ -92,6 +100,7 @@ if __name__ == "__main__":
     ap.add_argument("--kinds", default="tc,ffma")
     ap.add_argument("--opts", default="")  # e.g. tc_mask_hi=0,tc_split=1
     ap.add_argument("--only", default="")
+    ap.add_argument("--s16", action="store_true", help="sources / destination / residual in the S16 storage format where channel counts allow")
     a = ap.parse_args()
     for kv in filter(None, a.opts.split(",")):
         k, v = kv.split("=")
@@ -106,7 +115,7 @@ if __name__ == "__main__":
         for kind_name in a.kinds.split(","):
             kind = {"tc": A.CONV_TC, "tc16": A.CONV_TC16, "tc16h3": A.CONV_TC16, "ffma": A.CONV_FFMA}[kind_name]
             A.set_option("tc_gen", 2 if kind_name == "tc16h3" else 3)
-            d, keep = make_conv(kind, n, h, w, srcC, co, k, res="+res" in name, act=A.ACT_NONE if "+res" in name else A.ACT_RELU)
+            d, keep = make_conv(kind, n, h, w, srcC, co, k, res="+res" in name, act=A.ACT_NONE if "+res" in name else A.ACT_RELU, s16=a.s16)
             ms = time_conv(d)
             row[kind_name + "_ms"] = round(ms, 3)
             row[kind_name + "_TFLOPs"] = round(2 * macs / ms / 1e9, 1)

@@ -10,18 +10,18 @@ NAMES = {0: "split.total", 1: "split.wait_full", 2: "split.wait_aslot", 3: "spli
          6: "epi.store", 7: "split.convert", 8: "prod.total", 9: "prod.wait_empty", 12: "mma.total", 13: "mma.wait_acc_free", 14: "mma.wait_A"}
 
 
-def run(shape, kind=A.CONV_TC16, **opts):
+def run(shape, kind=A.CONV_TC16, s16=False, **opts):
     base = dict(tc_flush=10, tc_stages=0, tc_grid=0, tc_split=3, tc_mask_hi=1, tc_a_tmem=1, tc_diag=0, tc_comp_milli=270, tc_gen=3)
     base.update(opts)
     base["tc_diag"] |= 128
     for k, v in base.items():
         A.set_option(k, v)
-    d, keep = make_conv(kind, **shape)
+    d, keep = make_conv(kind, s16=s16, **shape)
     ms = time_conv(d)
     buf = np.zeros((148, 16), dtype=np.int64)
     A.check(A.lib().demfi_tc_debug_read(buf.ctypes.data_as(C.POINTER(C.c_int64)), 148), "debug_read")
     med = np.median(buf, axis=0)
-    print(json.dumps({"kind": kind, "shape": {k: v for k, v in shape.items()}, **opts, "ms": round(ms, 3),
+    print(json.dumps({"kind": kind, "s16": s16, "shape": {k: v for k, v in shape.items()}, **opts, "ms": round(ms, 3),
                       "kclk": {NAMES[i]: round(float(med[i]) / 1e3, 1) for i in NAMES}}), flush=True)
     A.set_option("tc_diag", 0)
 
@@ -33,10 +33,11 @@ if __name__ == "__main__":
     gru = dict(n=1, h=736, w=1280, srcC=[64, 64], co=128, k=(1, 5))
     run(s64, tc_gen=2)
     run(s64)
-    run(s64, tc_diag=4)   # weights streamed instead of resident
-    run(s64, tc_diag=2)   # generic per-thread epilogue instead of the TMA store
-    run(s64, tc_diag=1)   # no stores
-    run(s64, tc_flush=0)
+    run(s64, s16=True)
+    run(s64, s16=True, tc_diag=4)   # weights streamed instead of resident
+    run(s64, s16=True, tc_diag=1)   # no stores
     run(rdb)
+    run(rdb, s16=True)
     run(chr_)
     run(gru)
+    run(gru, s16=True)
