@@ -79,75 +79,101 @@ __device__ __forceinline__ float gather1(const float* img, int ld, int n, int H,
 // LPP = 16 (feature maps): a CTA walks an 8-row x 16-column pixel tile row by row, so the bilinear corners shared
 // with the previous row (and with x-neighbours) are L1 hits instead of L2 round trips.
 // LPP = 1 (3-channel pixel warp): one thread per pixel, scalar path.
-// LPP = 16: the tile's flows and occlusion logits are staged in shared memory first (one coalesced load per pixel), so a
-// row iteration is corner arithmetic -> eight independent 16-byte gathers per lane -> blend -> store, with nothing but the
-// gathers on the global-memory critical path.  ncu on the first version (flow loaded inside the row loop, 80 registers,
-// 36 % occupancy): DRAM traffic already ideal (511 MB read vs 501 MB algorithmic) but only 2.0 TB/s -- latency-bound.
+// LPP = 16: ONE thread per pixel of the 16 x 8 tile first loads the flows / occlusion logit (coalesced) and does all the
+// per-pixel arithmetic -- the two coordinate round trips, floor, corner weights, validity masks, sigmoid, blend factors --
+// and leaves it in shared memory; the row loop is then: read 17 words (broadcast), eight independent 16-byte gathers per
+// lane, blend, store.  ncu on the first version (everything inside the row loop, recomputed by each of the 16 lanes of a
+// pixel, 80 registers, 36 % occupancy): DRAM traffic already ideal (511 MB read vs 501 MB algorithmic) but 2.0 TB/s --
+// latency- and issue-bound (~300 instructions per lane per row).
+struct PixelPlan {
+  int ax0, ay0, bx0, by0;
+  float aw[4], bw[4];
+  float ma, mb, ka, kb, den;
+};
+
 template <int LPP>
-__global__ void __launch_bounds__(256, LPP == 16 ? 4 : 1)
+__global__ void __launch_bounds__(256, 4)
 bwarp_blend_kernel(const float* __restrict__ a, int a_ld, const float* __restrict__ b, int b_ld,
                    const float* __restrict__ flow, int flow_ld, const float* __restrict__ occ, int occ_ld,
                    const float* __restrict__ tv, int B, int H, int W, int C, float* __restrict__ out, int out_ld,
                    float* __restrict__ occ_out, int occ_out_ld, int tiles_x, int tiles_y) {
-  constexpr int ROWS = LPP == 16 ? 8 : 1;
-  __shared__ float4 s_flow[LPP == 16 ? 128 : 1];
-  __shared__ float s_occ[LPP == 16 ? 128 : 1];
-  int n, x, y0, lane;
   if constexpr (LPP == 16) {
-    int t = blockIdx.x;
-    const int tx = t % tiles_x;
-    t /= tiles_x;
-    const int ty = t % tiles_y;
-    n = t / tiles_y;
-    y0 = ty * 8;
+    __shared__ PixelPlan plan[128];
+    int t_ = blockIdx.x;
+    const int tx = t_ % tiles_x;
+    t_ /= tiles_x;
+    const int ty = t_ % tiles_y;
+    const int n = t_ / tiles_y;
+    const int y0 = ty * 8;
+    const float t = __ldg(tv + n);
     if (threadIdx.x < 128) {  // pixel (row threadIdx.x >> 4, column threadIdx.x & 15) of the tile
       const int py = y0 + ((int)threadIdx.x >> 4), px = tx * 16 + ((int)threadIdx.x & 15);
       if (py < H && px < W) {
         const long long pix = ((long long)n * H + py) * W + px;
-        s_flow[threadIdx.x] = __ldg((const float4*)(flow + pix * flow_ld));
-        const float o = sigmoid_f(__ldg(occ + pix * occ_ld));
-        s_occ[threadIdx.x] = o;
-        if (occ_out != nullptr) occ_out[pix * occ_out_ld] = o;
+        const float4 f = __ldg((const float4*)(flow + pix * flow_ld));
+        const float o0 = sigmoid_f(__ldg(occ + pix * occ_ld));
+        if (occ_out != nullptr) occ_out[pix * occ_out_ld] = o0;
+        const float o1 = 1.0f - o0;
+        const Corners ca = make_corners(bwarp_coord(px, f.x, W), bwarp_coord(py, f.y, H), H, W);
+        const Corners cb = make_corners(bwarp_coord(px, f.z, W), bwarp_coord(py, f.w, H), H, W);
+        PixelPlan& P = plan[threadIdx.x];
+        P.ax0 = ca.x0; P.ay0 = ca.y0; P.bx0 = cb.x0; P.by0 = cb.y0;
+        P.aw[0] = ca.w00; P.aw[1] = ca.w01; P.aw[2] = ca.w10; P.aw[3] = ca.w11;
+        P.bw[0] = cb.w00; P.bw[1] = cb.w01; P.bw[2] = cb.w10; P.bw[3] = cb.w11;
+        // bwarp's validity mask: warped ones < 0.999 -> 0 (DeMFInet.py:758-766)
+        P.ma = ca.wsum < 0.999f ? 0.0f : 1.0f;
+        P.mb = cb.wsum < 0.999f ? 0.0f : 1.0f;
+        P.ka = (1.0f - t) * o0;
+        P.kb = t * o1;
+        P.den = P.ka + P.kb;
       }
     }
     __syncthreads();
-    x = tx * 16 + (threadIdx.x >> 4);
-    lane = threadIdx.x & 15;
+    const int col = (int)threadIdx.x >> 4, lane = (int)threadIdx.x & 15;
+    const int x = tx * 16 + col;
     if (x >= W) return;
+#pragma unroll 1
+    for (int r = 0; r < 8; ++r) {
+      const int y = y0 + r;
+      if (y >= H) break;
+      const PixelPlan& P = plan[r * 16 + col];
+      Corners ca, cb;
+      ca.x0 = P.ax0; ca.y0 = P.ay0; ca.w00 = P.aw[0]; ca.w01 = P.aw[1]; ca.w10 = P.aw[2]; ca.w11 = P.aw[3];
+      cb.x0 = P.bx0; cb.y0 = P.by0; cb.w00 = P.bw[0]; cb.w01 = P.bw[1]; cb.w10 = P.bw[2]; cb.w11 = P.bw[3];
+      const float ma = P.ma, mb = P.mb, ka = P.ka, kb = P.kb, den = P.den;
+      const long long pix = ((long long)n * H + y) * W + x;
+      for (int ch = lane * 4; ch < C; ch += 64) {
+        const float4 va = gather4(a, a_ld, n, H, W, ca, ch);
+        const float4 vb = gather4(b, b_ld, n, H, W, cb, ch);
+        float4 r4;
+        r4.x = (ka * (va.x * ma) + kb * (vb.x * mb)) / den;
+        r4.y = (ka * (va.y * ma) + kb * (vb.y * mb)) / den;
+        r4.z = (ka * (va.z * ma) + kb * (vb.z * mb)) / den;
+        r4.w = (ka * (va.w * ma) + kb * (vb.w * mb)) / den;
+        st4(out + pix * out_ld + ch, r4);
+      }
+    }
   } else {
+    // LPP = 1 (3-channel pixel warp of the boosting loop): one thread per pixel, scalar channels
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (long long)B * H * W) return;
-    x = (int)(gid % W);
-    y0 = (int)((gid / W) % H);
-    n = (int)(gid / ((long long)W * H));
-    lane = 0;
-  }
-  const float t = __ldg(tv + n);
-#pragma unroll 1
-  for (int r = 0; r < ROWS; ++r) {
-    const int y = y0 + r;
-    if (y >= H) break;
-    const long long pix = ((long long)n * H + y) * W + x;
-    float4 f;
-    float o0;
-    if constexpr (LPP == 16) {
-      f = s_flow[r * 16 + ((int)threadIdx.x >> 4)];
-      o0 = s_occ[r * 16 + ((int)threadIdx.x >> 4)];
-    } else {
-      f = __ldg((const float4*)(flow + pix * flow_ld));
-      o0 = sigmoid_f(__ldg(occ + pix * occ_ld));
-      if (occ_out != nullptr) occ_out[pix * occ_out_ld] = o0;
-    }
+    const int x = (int)(gid % W);
+    const int y = (int)((gid / W) % H);
+    const int n = (int)(gid / ((long long)W * H));
+    const float t = __ldg(tv + n);
+    const long long pix = gid;
+    const float4 f = __ldg((const float4*)(flow + pix * flow_ld));
+    const float o0 = sigmoid_f(__ldg(occ + pix * occ_ld));
+    if (occ_out != nullptr) occ_out[pix * occ_out_ld] = o0;
     const float o1 = 1.0f - o0;
     const Corners ca = make_corners(bwarp_coord(x, f.x, W), bwarp_coord(y, f.y, H), H, W);
     const Corners cb = make_corners(bwarp_coord(x, f.z, W), bwarp_coord(y, f.w, H), H, W);
-    // bwarp's validity mask: warped ones < 0.999 -> 0 (DeMFInet.py:758-766)
     const float ma = ca.wsum < 0.999f ? 0.0f : 1.0f;
     const float mb = cb.wsum < 0.999f ? 0.0f : 1.0f;
     const float ka = (1.0f - t) * o0, kb = t * o1;
     const float den = ka + kb;
     if (C % 4 == 0) {
-      for (int ch = lane * 4; ch < C; ch += LPP * 4) {
+      for (int ch = 0; ch < C; ch += 4) {
         const float4 va = gather4(a, a_ld, n, H, W, ca, ch);
         const float4 vb = gather4(b, b_ld, n, H, W, cb, ch);
         float4 r4;
@@ -158,7 +184,7 @@ bwarp_blend_kernel(const float* __restrict__ a, int a_ld, const float* __restric
         st4(out + pix * out_ld + ch, r4);
       }
     } else {
-      for (int ch = lane; ch < C; ch += LPP) {
+      for (int ch = 0; ch < C; ++ch) {
         const float va = gather1(a, a_ld, n, H, W, ca, ch);
         const float vb = gather1(b, b_ld, n, H, W, cb, ch);
         out[pix * out_ld + ch] = (ka * (va * ma) + kb * (vb * mb)) / den;
@@ -177,32 +203,60 @@ fgac_sample_kernel(const float* __restrict__ refk, int refk_ld, const float* __r
   const long long pix = gid / LPP;
   const int lane = (int)(gid % LPP);
   const long long npix = (long long)B * H * W;
-  if (pix >= npix) return;
+  const bool live = pix < npix;  // no early return: every lane of the warp takes part in the shuffles below
   const int n = (int)(pix / ((long long)W * H));
-  const float2 f = __ldg((const float2*)(flow + pix * flow_ld));
-  // bilinear_sampler: g = 2*f/(W-1) - 1; grid_sample: ((g+1)/2)*(W-1)
-  const float gx = 2.0f * f.x / (float)(W - 1) - 1.0f;
-  const float gy = 2.0f * f.y / (float)(H - 1) - 1.0f;
-  const Corners c = make_corners(((gx + 1.0f) / 2.0f) * (float)(W - 1), ((gy + 1.0f) / 2.0f) * (float)(H - 1), H, W);
+  // one lane per pixel does the coordinate arithmetic, the others receive the corners by shuffle (blocks are whole
+  // groups of LPP lanes: npix * LPP threads are launched in blocks of 256)
+  Corners c = {};
+  if (lane == 0 && live) {
+    const float2 f = __ldg((const float2*)(flow + pix * flow_ld));
+    // bilinear_sampler: g = 2*f/(W-1) - 1; grid_sample: ((g+1)/2)*(W-1)
+    const float gx = 2.0f * f.x / (float)(W - 1) - 1.0f;
+    const float gy = 2.0f * f.y / (float)(H - 1) - 1.0f;
+    c = make_corners(((gx + 1.0f) / 2.0f) * (float)(W - 1), ((gy + 1.0f) / 2.0f) * (float)(H - 1), H, W);
+  }
+  c.x0 = __shfl_sync(0xffffffffu, c.x0, 0, LPP);
+  c.y0 = __shfl_sync(0xffffffffu, c.y0, 0, LPP);
+  c.w00 = __shfl_sync(0xffffffffu, c.w00, 0, LPP);
+  c.w01 = __shfl_sync(0xffffffffu, c.w01, 0, LPP);
+  c.w10 = __shfl_sync(0xffffffffu, c.w10, 0, LPP);
+  c.w11 = __shfl_sync(0xffffffffu, c.w11, 0, LPP);
+  if (!live) return;
   for (int ch = lane * 4; ch < C; ch += LPP * 4) st4(out + pix * out_ld + ch, gather4(refk, refk_ld, n, H, W, c, ch));
 }
 
+// Pure streaming (3 reads + 1 write per element): four pixels per lane group, all loads issued before the first use
+// (64 bytes of loads in flight per thread instead of 32)
 template <int LPP>
 __global__ void __launch_bounds__(256)
 fgac_blend_kernel(const float* __restrict__ w, int w_ld, const float* __restrict__ src, int src_ld,
                   const float* __restrict__ e, int e_ld, long long npix, int C, float* __restrict__ out, int out_ld) {
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long pix = gid / LPP;
-  const int lane = (int)(gid % LPP);
-  if (pix >= npix) return;
-  const float ww = __ldg(w + pix * w_ld);
+  constexpr int PPT = 4;  // pixels per thread, strided by the number of pixels one block covers per step
+  const int lane = (int)(threadIdx.x % LPP);
+  const long long ppb = blockDim.x / LPP;
+  const long long p0 = (long long)blockIdx.x * ppb * PPT + threadIdx.x / LPP;
   for (int ch = lane * 4; ch < C; ch += LPP * 4) {
-    const float4 s = __ldg((const float4*)(src + pix * src_ld + ch));
-    const float4 v = __ldg((const float4*)(e + pix * e_ld + ch));
-    float4 r;
-    r.x = ww * s.x + (1.0f - ww) * v.x; r.y = ww * s.y + (1.0f - ww) * v.y;
-    r.z = ww * s.z + (1.0f - ww) * v.z; r.w = ww * s.w + (1.0f - ww) * v.w;
-    st4(out + pix * out_ld + ch, r);
+    float ww[PPT];
+    float4 s[PPT], v[PPT];
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+      const long long pix = p0 + k * ppb;
+      if (pix < npix) {
+        ww[k] = __ldg(w + pix * w_ld);
+        s[k] = __ldg((const float4*)(src + pix * src_ld + ch));
+        v[k] = __ldg((const float4*)(e + pix * e_ld + ch));
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+      const long long pix = p0 + k * ppb;
+      if (pix < npix) {
+        float4 r;
+        r.x = ww[k] * s[k].x + (1.0f - ww[k]) * v[k].x; r.y = ww[k] * s[k].y + (1.0f - ww[k]) * v[k].y;
+        r.z = ww[k] * s[k].z + (1.0f - ww[k]) * v[k].z; r.w = ww[k] * s[k].w + (1.0f - ww[k]) * v[k].w;
+        st4(out + pix * out_ld + ch, r);
+      }
+    }
   }
 }
 
@@ -403,7 +457,7 @@ int demfi_fgac_blend(const float* w, int32_t w_ld, const float* src, int32_t src
   if (check_device()) return 3;
   DEMFI_REQUIRE(npix > 0 && C > 0 && C % 4 == 0 && src_ld % 4 == 0 && e_ld % 4 == 0 && out_ld % 4 == 0,
                 "fgac_blend: bad shape");
-  fgac_blend_kernel<16><<<blocks_for(npix * 16), 256, 0, (cudaStream_t)stream>>>(w, w_ld, src, src_ld, e, e_ld, npix, C,
+  fgac_blend_kernel<16><<<blocks_for(npix * 16, 256 * 4), 256, 0, (cudaStream_t)stream>>>(w, w_ld, src, src_ld, e, e_ld, npix, C,
                                                                                   out, out_ld);
   DEMFI_LAUNCH_CHECK("fgac_blend");
   return 0;
