@@ -247,7 +247,9 @@ class Engine:
         d.wpack, d.bias = wdev.data_ptr(), bdev.data_ptr()
         self._keep.append(d)
         macs = N * Ho * Wo * Co * Ci * KH * KW
-        op = ("conv", d, label or names[0], kind, macs)
+        views = {"src": [vw for vw, _ in srcs], "dst": [sg["dst"] for sg in segs],
+                 "res": [sg[k_] for sg in segs for k_ in ("res", "res2") if sg.get(k_) is not None]}
+        op = ("conv", d, label or names[0], kind, macs, views)
         return op
 
     # ------------------------------------------------------------------ plan
@@ -433,6 +435,57 @@ class Engine:
         ops.append(self.conv("Dec_last1_2", [a], (H, W), B, [full(b_, 64, relu)]))
         ops.append(self.conv("Dec_last2_2", [b_], (H, W), B, [full(v["D2O"], 12, none, A3.ch(0, 12))]))
         return ops
+
+    # ------------------------------------------------------------------ static checks
+    def check_formats(self, num_update: int = 3) -> int:
+        """Replay the op lists symbolically and check the storage formats: every 32-channel group a convolution reads as S16
+        must have been written as S16 by a convolution (or copied bit-wise by the up-sampler), and no fp32 reader may see a
+        group last written as S16.  Returns the number of (reader, group) pairs checked.  Host-only: runs on a dry engine."""
+        state: Dict[Tuple[int, int, int], int] = {}  # (buffer id, frame, 32-channel group) -> format last written
+        checked = 0
+
+        def groups(vw: View):
+            for n in range(vw.n0, vw.n0 + vw.N):
+                for g in range(vw.c0 // 32, (vw.c0 + vw.C + 31) // 32):
+                    yield (id(vw.t), n, g)
+
+        def write(vw: View, fmt=None):
+            for k in groups(vw):
+                state[k] = vw.fmt if fmt is None else fmt
+
+        def read(vw: View, who):
+            nonlocal checked
+            for k in groups(vw):
+                have = state.get(k, A.FMT_F32)  # never-written buffers are zero-filled fp32
+                assert have == vw.fmt, f"{who}: reads a {'S16' if vw.fmt else 'fp32'} view of data written as {'S16' if have else 'fp32'}"
+                checked += 1
+
+        seqs = [self.ops_prefix_ff, self.ops_stage1] + [self._iter_ops(i, True) for i in range(num_update)]
+        for ops in seqs:
+            for op in ops:
+                if op[0] == "conv":
+                    _, d, label, kind, _macs, views = op
+                    for vw in views["src"] + views["res"]:
+                        read(vw, label)
+                    for vw in views["dst"]:
+                        write(vw)
+                elif op[0] == "upsample":
+                    read(op[1], "upsample")
+                    write(op[2], op[1].fmt)
+                    assert op[2].fmt == op[1].fmt, "upsample copies bits: source and destination formats must agree"
+                elif op[0] == "zero":
+                    write(op[1], A.FMT_F32)
+                else:
+                    vs = [a_ for a_ in op[1:] if isinstance(a_, View)]
+                    first_out = {"copy": 1, "cfr_splat": 1, "cfr_finalize": 1, "bwarp_blend": 4, "fgac_sample": 2, "fgac_blend": 3}[op[0]]
+                    outs = vs[first_out:]
+                    for vw in vs:
+                        assert vw.fmt == A.FMT_F32, f"{op[0]} only handles fp32 views"
+                        if not any(vw is o for o in outs):
+                            read(vw, op[0])
+                    for vw in outs:
+                        write(vw)
+        return checked
 
     # ------------------------------------------------------------------ execution
     def _run(self, ops, st):

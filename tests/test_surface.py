@@ -75,6 +75,26 @@ def test_plan_builds_on_host_and_accounts_for_every_conv(state_dict):
         e.forward(torch.zeros(1, 3, 4, 64, 96), torch.tensor([[0.5]]), 1)
 
 
+def test_storage_formats_are_consistent_along_the_plan(state_dict):
+    """S16 (split-fp16) buffers are only written and read by convolutions, producer and consumer agree on the format of
+    every 32-channel group, and fp32 operators never see S16 data -- checked by replaying the plan symbolically"""
+    from demfi_b200 import _abi as A
+    e = Engine(state_dict, 1, 64, 96, torch.device("cpu"), dry=True)
+    assert e.use_s16
+    assert e.check_formats(3) > 500
+    n_s16 = sum(1 for v in e.views.values() if v.fmt == A.FMT_S16)
+    assert n_s16 >= 20, n_s16
+    # every S16 source / destination sits on the tensor-core kernel that implements the format
+    for ops in (e.ops_prefix_ff, e.ops_stage1, e._iter_ops(0, True)):
+        for op in ops:
+            if op[0] == "conv" and any(v.fmt for vs in op[5].values() for v in vs):
+                assert op[3] == A.CONV_TC16, op[2]
+    # the all-fp32 plan (comparison mode) passes the same replay trivially
+    f = Engine(state_dict, 1, 64, 96, torch.device("cpu"), conv_kind="tc16f32", dry=True)
+    assert not f.use_s16 and all(v.fmt == A.FMT_F32 for v in f.views.values())
+    f.check_formats(2)
+
+
 def test_shape_constraints():
     with pytest.raises(ValueError):
         Engine(synth.make_state_dict(0), 1, 36, 64, torch.device("cpu"), dry=True)
