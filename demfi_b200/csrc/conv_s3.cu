@@ -358,6 +358,10 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: let the next kernel of the stream start its own prologue (barrier init, TMEM allocation,
+  // resident-weight load) on SMs as they drain; everything here that reads or writes activations waits for the previous
+  // kernel to have completed (griddepcontrol.wait), the loads of weights and bias (constants) do not.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp < S3_CV_WARPS) {
     // ===== converter: fp32 halo tile -> fp16 hi / lo planes, in place =====
@@ -429,6 +433,7 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
       sts128(bias_s + (uint32_t)i * 4u, make_uint4(__float_as_uint(b.x), __float_as_uint(b.y), __float_as_uint(b.z), __float_as_uint(b.w)));
     }
     asm volatile("bar.sync 2, %0;" ::"n"(S3_EPI_THREADS) : "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // operand tiles and destinations belong to earlier kernels
     for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
       int t = tile;
       const int nb = t % P.n_blocks;
@@ -605,6 +610,7 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
         for (int s = 0; s < P.stages_per_tile; ++s)
           bulk_load(b_base + (uint32_t)(s * P.b_bytes), wsrc + (size_t)s * b_tx, b_tx, bar_wfull);
       }
+      asm volatile("griddepcontrol.wait;" ::: "memory");  // activations are the previous kernels' outputs
       // A sequence state
       int a_tile = blockIdx.x, a_src = 0, a_c0 = 0, abuf = 0;
       uint32_t aphase = 0;
@@ -1031,14 +1037,22 @@ int launch_conv_s3(const demfi_conv_t& c, cudaStream_t st) {
   }
   int grid = P.ntiles < s3_num_sms() ? P.ntiles : s3_num_sms();
   if (get_option("tc_grid") > 0 && get_option("tc_grid") < grid) grid = get_option("tc_grid");
-  if (P.dbg != nullptr) {
-    if (P.nb_max <= 32) conv_s3_kernel<32, true><<<grid, S3_THREADS, smem, st>>>(P);
-    else if (P.nb_max <= 64) conv_s3_kernel<64, true><<<grid, S3_THREADS, smem, st>>>(P);
-    else conv_s3_kernel<96, true><<<grid, S3_THREADS, smem, st>>>(P);
-  } else {
-    if (P.nb_max <= 32) conv_s3_kernel<32, false><<<grid, S3_THREADS, smem, st>>>(P);
-    else if (P.nb_max <= 64) conv_s3_kernel<64, false><<<grid, S3_THREADS, smem, st>>>(P);
-    else conv_s3_kernel<96, false><<<grid, S3_THREADS, smem, st>>>(P);
+  {
+    void (*fn)(S3Params) = nullptr;
+    if (P.dbg != nullptr) fn = P.nb_max <= 32 ? conv_s3_kernel<32, true> : P.nb_max <= 64 ? conv_s3_kernel<64, true> : conv_s3_kernel<96, true>;
+    else fn = P.nb_max <= 32 ? conv_s3_kernel<32, false> : P.nb_max <= 64 ? conv_s3_kernel<64, false> : conv_s3_kernel<96, false>;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(S3_THREADS);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = get_option("tc_pdl") ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, fn, P);
+    DEMFI_REQUIRE(e == cudaSuccess, "conv_s3 launch failed: %s", cudaGetErrorString(e));
   }
   DEMFI_LAUNCH_CHECK("conv_s3");
   return 0;

@@ -188,7 +188,9 @@ uint64_t demfi_launch_count(void);
  * before the partial sum is drained and added in fp32 round-to-nearest; default 10 (segments are balanced: 18 stages -> 2 x 9), 0 = whole K), "tc_comp_milli" (gain correction of the truncating tensor-core accumulation in
  * units of 1e-3 * 2^-24 per chained MMA; default 270 = the measured -0.27*2^-24 bias per MMA on B200),
  * "tc_a_tmem" (1: activation operand through tensor memory, 0: through shared memory), "tc_stages" /
- * "tc_grid" (caps on pipeline depth / persistent CTAs, 0 = auto), "tc_diag" (timing diagnostics bitmask).
+ * "tc_grid" (caps on pipeline depth / persistent CTAs, 0 = auto), "tc_diag" (timing diagnostics bitmask),
+ * "tc_gen" (DEMFI_CONV_TC16 kernel: 3 = conv_s3 where it applies (default), 2 = conv_h3 only), "tc_pdl" (1: programmatic
+ * dependent launch between consecutive conv_s3 kernels; default 0 -- measured slightly slower on the full forward).
  * Returns non-zero for an unknown option. */
 int demfi_set_option(const char* name, int32_t value);
 int demfi_get_option(const char* name, int32_t* value);
