@@ -51,3 +51,150 @@ def run_clip(model_net, frames: torch.Tensor, multiple: int, num_update: int, ra
                 sink(idx, t, out)
             done += 1
     return done
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Folder runner: the `--phase test_custom` path of the reference (Custom_Test + make_2D_dataset_Custom_Test,
+# utils.py:522-593; test_custom, main.py:1109-1196) with the I/O taken off the critical path.
+#
+#   <custom_path>/<scene>/*.png   ->   <custom_path>/<scene>_sharply_interpolated_x<M>/
+#        <frame idx>.png, <frame idx+1>.png             deblurred S0_final / S1_final of the pair (written at its first t)
+#        <frame idx stem>_<suffix:03d>.png               St_final for t = (suffix + 1) / M
+#
+# The reference decodes four PNGs, runs the model and encodes up to three PNGs synchronously on the main thread for
+# every (pair, t).  Here: every frame is decoded ONCE (thread pool, cv2 releases the GIL), normalised on the GPU,
+# kept in a small device cache (a frame serves four pairs); the t-independent prefix of the network is reused across
+# the M-1 time indices of a pair; results are converted to uint8 on the GPU exactly as the reference does on the host
+# (float64 denorm255_np, truncating astype(uint8)), copied back into pinned buffers and encoded by the pool while the
+# next forward runs.
+import glob
+import os
+from collections import OrderedDict
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+
+def enumerate_custom(custom_path: str, multiple: int):
+    """[(scene, idx, [B0, B1, Bm1, B2] paths, [(t, St name)], S0 name, S1 name)] in the reference's order
+    (make_2D_dataset_Custom_Test, utils.py:558-593: pairs idx = 1 .. F-3, t = linspace(1/M, 1-1/M, M-1))."""
+    out = []
+    ts = np.linspace(1 / multiple, 1 - 1 / multiple, multiple - 1)
+    for scene_folder in sorted(glob.glob(os.path.join(custom_path, "*", ""))):
+        frames = sorted(glob.glob(scene_folder + "*.png"))
+        scene = scene_folder.split(os.path.join(custom_path, ""))[-1].split(os.sep)[0]
+        for idx in range(1, len(frames)):
+            if idx == len(frames) - 2:
+                break
+            stem = os.path.basename(frames[idx]).split(".")[0]
+            st = [(float(ts[m]), f"{stem}_{str(m).zfill(3)}.png") for m in range(multiple - 1)]
+            out.append((scene, idx, [frames[idx], frames[idx + 1], frames[idx - 1], frames[idx + 2]], st,
+                        os.path.basename(frames[idx]), os.path.basename(frames[idx + 1])))
+    return out
+
+
+_NORM_LUT = ((torch.arange(256, dtype=torch.float32) / 255.0 - 0.5) * 2)  # CPU fp32 arithmetic, as the reference's loader does
+
+
+def normalize_bgr_u8(img_u8: torch.Tensor) -> torch.Tensor:
+    """[H,W,3] uint8 (cv2 BGR) -> [3,H,W] fp32 in [-1,1]: RGBframes_np2Tensor (utils.py:224-238).  The reference computes
+    (x / 255.0 - 0.5) * 2 on a CPU fp32 tensor; a 256-entry table built with exactly that arithmetic gives the same bits on
+    any device (CUDA's tensor / scalar is a multiplication by the reciprocal and differs in the last place)."""
+    return _NORM_LUT.to(img_u8.device)[img_u8.permute(2, 0, 1).long()]
+
+
+def denorm255_u8(x: torch.Tensor) -> torch.Tensor:
+    """[.., 3, H, W] in [-1,1] -> [.., H, W, 3] uint8: denorm255_np (utils.py:718-721) on the float64 copy the caller makes
+    (utils.py:1415), then the truncating astype(np.uint8) of main.py:1165-1178."""
+    y = ((x.to(torch.float64) + 1) / 2).clamp(0, 1) * 255
+    return y.to(torch.uint8).movedim(-3, -1).contiguous()
+
+
+class FolderRunner:
+    def __init__(self, model_net, multiple: int, num_update: int, patch_boundary: int = 32, io_threads: int = 8,
+                 rank: int = 0, world: int = 1, cache_frames: int = 8):
+        self.net, self.M, self.N, self.pb = model_net, multiple, num_update, patch_boundary
+        self.rank, self.world = rank, world
+        self.pool = ThreadPoolExecutor(max_workers=io_threads)
+        self.cache: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+        self.cache_frames = cache_frames
+        self.dev = next(model_net.parameters()).device if hasattr(model_net, "parameters") else torch.device("cpu")
+        self.cuda = self.dev.type == "cuda"
+        self.copy_stream = torch.cuda.Stream(self.dev) if self.cuda else None
+
+    # -- input side
+    def _decode(self, path):
+        import cv2
+        img = cv2.imread(path)
+        if img is None:
+            raise FileNotFoundError(path)
+        t = torch.from_numpy(img)
+        return t.pin_memory() if self.cuda else t
+
+    def _prefetch(self, paths, pending):
+        for p in paths:
+            if p not in self.cache and p not in pending:
+                pending[p] = self.pool.submit(self._decode, p)
+
+    def _frame(self, path, pending):
+        if path in self.cache:
+            self.cache.move_to_end(path)
+            return self.cache[path]
+        host = pending.pop(path).result() if path in pending else self._decode(path)
+        if self.cuda:
+            with torch.cuda.stream(self.copy_stream):
+                f = normalize_bgr_u8(host.to(self.dev, non_blocking=True))
+            torch.cuda.current_stream(self.dev).wait_stream(self.copy_stream)
+        else:
+            f = normalize_bgr_u8(host)
+        self.cache[path] = f
+        while len(self.cache) > self.cache_frames:
+            self.cache.popitem(last=False)
+        return f
+
+    # -- output side
+    @staticmethod
+    def _write(path, img_hwc_u8: torch.Tensor, ready_event):
+        import cv2
+        if ready_event is not None:
+            ready_event.synchronize()
+        cv2.imwrite(path, img_hwc_u8.numpy())
+        return path
+
+    def _save(self, path, img_chw: torch.Tensor, futures):
+        u8 = denorm255_u8(img_chw)
+        if self.cuda:
+            host = torch.empty(u8.shape, dtype=torch.uint8).pin_memory()
+            host.copy_(u8, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+        else:
+            host, ev = u8, None
+        futures.append(self.pool.submit(self._write, path, host, ev))
+
+    @torch.no_grad()
+    def run(self, custom_path: str) -> dict:
+        """Returns {"pairs", "interpolated", "deblurred", "files"} for this rank's share of the work."""
+        work = enumerate_custom(custom_path, self.M)
+        mine = [w for i, w in enumerate(work) if i % self.world == self.rank]
+        pending, futures = {}, []
+        stats = {"pairs": 0, "interpolated": 0, "deblurred": 0, "files": []}
+        for k, (scene, idx, paths, st, s0_name, s1_name) in enumerate(mine):
+            self._prefetch(paths, pending)
+            if k + 1 < len(mine):
+                self._prefetch(mine[k + 1][2], pending)  # decode the next pair's frames while this one computes
+            x = torch.stack([self._frame(p, pending) for p in paths], dim=1).unsqueeze(0)  # [1,3,4,H,W]: B0, B1, B-1, B2
+            out_dir = os.path.join(custom_path, f"{scene}_sharply_interpolated_x{self.M}")
+            os.makedirs(out_dir, exist_ok=True)
+            for j, (t, st_name) in enumerate(st):
+                tt = torch.tensor([[t]], dtype=torch.float32, device=x.device)
+                s0, s1, stf = interpolate(self.net, x, tt, self.N, self.pb, reuse_prefix=j > 0)
+                if j == 0:  # main.py:1160-1169: the deblurred pair is written at the first time index only
+                    self._save(os.path.join(out_dir, s0_name), s0[0], futures)
+                    self._save(os.path.join(out_dir, s1_name), s1[0], futures)
+                    stats["deblurred"] += 2
+                self._save(os.path.join(out_dir, st_name), stf[0], futures)
+                stats["interpolated"] += 1
+            stats["pairs"] += 1
+        stats["files"] = [f.result() for f in futures]
+        return stats

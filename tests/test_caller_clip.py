@@ -121,3 +121,75 @@ def test_two_rank_sharding_gloo(state_dict, tmp_path):
     for part in gathered:
         for idx, arr in part.items():
             assert np.abs(arr - single[idx]).max() < 1e-4  # worker uses 2 CPU threads, this process all of them
+
+
+# ---- folder runner: mirrors Custom_Test / test_custom (utils.py:522-593, main.py:1109-1196)
+def _write_scene(root, scene, n, h, w, seed):
+    import cv2
+    os.makedirs(os.path.join(root, scene), exist_ok=True)
+    g = np.random.Generator(np.random.PCG64(seed))
+    base = g.integers(0, 256, size=(h + 8, w + 8, 3), dtype=np.uint8)
+    base = cv2.blur(base, (5, 5))
+    for i in range(n):
+        cv2.imwrite(os.path.join(root, scene, f"{i:05d}.png"), base[i % 4:i % 4 + h, (2 * i) % 7:(2 * i) % 7 + w])
+
+
+def test_enumerate_custom_matches_reference_naming(tmp_path):
+    from demfi_b200.clip import enumerate_custom
+    _write_scene(str(tmp_path), "sceneA", 6, 24, 40, 1)
+    _write_scene(str(tmp_path), "sceneB", 5, 24, 40, 2)
+    work = enumerate_custom(str(tmp_path), 8)
+    # F frames -> F-3 pairs (idx = 1 .. F-3), 7 time indices each, named <B0 stem>_<suffix:03d>.png
+    assert [(w[0], w[1]) for w in work] == [("sceneA", 1), ("sceneA", 2), ("sceneA", 3), ("sceneB", 1), ("sceneB", 2)]
+    scene, idx, paths, st, s0, s1 = work[1]
+    assert [os.path.basename(p) for p in paths] == ["00002.png", "00003.png", "00001.png", "00004.png"]  # B0, B1, B-1, B2
+    assert [n for _, n in st] == [f"00002_{m:03d}.png" for m in range(7)]
+    assert np.allclose([t for t, _ in st], np.linspace(1 / 8, 7 / 8, 7)) and (s0, s1) == ("00002.png", "00003.png")
+
+
+class BlendModel:
+    """deterministic stand-in with the model's call signature and return structure: S0 = B0 * 0.9, S1 = B1 * 0.9 + 0.05,
+    St = (1 - t) B0 + t B1 (bit-reproducible, unlike a multi-threaded conv stack)"""
+
+    def __init__(self):
+        self.calls = []
+
+    def __call__(self, x, t, n, is_training=None, reuse_prefix=False):
+        self.calls.append((tuple(x.shape), float(t.reshape(-1)[0]), reuse_prefix))
+        b0, b1 = x[:, :, 0], x[:, :, 1]
+        tt = t.reshape(-1, 1, 1, 1)
+        fin = [b0 * 0.9, b1 * 0.9 + 0.05, (1 - tt) * b0 + tt * b1]
+        return [b0, b1, b0], [fin] * n, [None] * (n + 1), [None] * (n + 1), (b0 + b1) / 2
+
+
+def test_folder_runner_writes_what_the_reference_loop_writes(tmp_path):
+    """End to end on CPU: frames decoded once, prefix reuse inside a pair, and byte-identical PNGs to a literal restatement of
+    test_custom's save path (float64 denorm255_np, truncating uint8)."""
+    import cv2
+    from demfi_b200.clip import FolderRunner
+    root = str(tmp_path)
+    _write_scene(root, "clip", 5, 24, 40, 3)  # 2 pairs
+    m = BlendModel()
+    stats = FolderRunner(m, multiple=4, num_update=1, io_threads=2).run(root)
+    assert stats["pairs"] == 2 and stats["interpolated"] == 6 and stats["deblurred"] == 4 and len(stats["files"]) == 10
+    assert [c[2] for c in m.calls] == [False, True, True, False, True, True]  # prefix recomputed once per pair
+    assert all(c[0] == (1, 3, 4, 32, 64) for c in m.calls)  # reflect-padded to x32
+    out_dir = os.path.join(root, "clip_sharply_interpolated_x4")
+    assert sorted(os.listdir(out_dir)) == sorted(["00001.png", "00002.png", "00003.png"] +
+                                                 [f"0000{i}_{k:03d}.png" for i in (1, 2) for k in range(3)])
+    # literal reference path (utils.py:224-238, 1339-1477; main.py:1150-1178) for pair idx = 1
+    frames = np.stack([cv2.imread(os.path.join(root, "clip", f"{i:05d}.png")) for i in (1, 2, 0, 3)], axis=0)
+    x = torch.Tensor(frames.transpose(3, 0, 1, 2).astype(float)).mul_(1.0)
+    x = ((x / 255.0 - 0.5) * 2).unsqueeze(0)  # RGBframes_np2Tensor
+    xp, oh, ow = pad_to_multiple(x, 32)
+    ref = BlendModel()
+    for k, t in enumerate((0.25, 0.5, 0.75)):
+        res = ref(xp, torch.tensor([[t]], dtype=torch.float32), 1)
+        st = np.squeeze(res[1][-1][2].numpy()).astype(np.float64)[..., :oh, :ow]
+        img = (((np.transpose(st, [1, 2, 0])[:, :, ::-1] + 1) / 2).clip(0, 1) * 255).astype(np.uint8)[:, :, ::-1]
+        assert np.array_equal(cv2.imread(os.path.join(out_dir, f"00001_{k:03d}.png")), img), k
+    # the deblurred pair is written at the FIRST time index of the pair only (main.py:1160-1169)
+    res0 = ref(xp, torch.tensor([[0.25]]), 1)
+    s0 = np.squeeze(res0[1][-1][0].numpy()).astype(np.float64)[..., :oh, :ow]
+    img0 = np.transpose(((s0 + 1) / 2).clip(0, 1) * 255, [1, 2, 0]).astype(np.uint8)
+    assert np.array_equal(cv2.imread(os.path.join(out_dir, "00001.png")), img0)
