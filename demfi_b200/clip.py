@@ -81,6 +81,8 @@ def enumerate_custom(custom_path: str, multiple: int):
     out = []
     ts = np.linspace(1 / multiple, 1 - 1 / multiple, multiple - 1)
     for scene_folder in sorted(glob.glob(os.path.join(custom_path, "*", ""))):
+        if "_sharply_interpolated_x" in os.path.basename(os.path.dirname(scene_folder)):
+            continue  # an output folder of an earlier run (the reference would re-process it as a scene)
         frames = sorted(glob.glob(scene_folder + "*.png"))
         scene = scene_folder.split(os.path.join(custom_path, ""))[-1].split(os.sep)[0]
         for idx in range(1, len(frames)):
