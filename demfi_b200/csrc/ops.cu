@@ -40,40 +40,6 @@ __device__ __forceinline__ float bwarp_coord(int i, float f, int size) {
   return ((g + 1.0f) / 2.0f) * (float)(size - 1);
 }
 
-// All four corner loads are issued unconditionally (coordinates clamped into the image, out-of-image corners already
-// carry weight 0) so that they are in flight together: with a branch per corner the first FMA of each block waited for
-// its load and the four round trips were serialised.
-__device__ __forceinline__ float4 gather4(const float* img, int ld, int n, int H, int W, const Corners& c, int ch) {
-  const float* base = img + (size_t)n * H * W * ld + ch;
-  const int x0 = min(max(c.x0, 0), W - 1), x1 = min(max(c.x0 + 1, 0), W - 1);
-  const int y0 = min(max(c.y0, 0), H - 1), y1 = min(max(c.y0 + 1, 0), H - 1);
-  const float4 v00 = __ldg((const float4*)(base + ((size_t)y0 * W + x0) * ld));
-  const float4 v01 = __ldg((const float4*)(base + ((size_t)y0 * W + x1) * ld));
-  const float4 v10 = __ldg((const float4*)(base + ((size_t)y1 * W + x0) * ld));
-  const float4 v11 = __ldg((const float4*)(base + ((size_t)y1 * W + x1) * ld));
-  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-  // same accumulation order as before: nw, ne, sw, se (ATen grid_sampler_2d)
-  r.x += v00.x * c.w00; r.y += v00.y * c.w00; r.z += v00.z * c.w00; r.w += v00.w * c.w00;
-  r.x += v01.x * c.w01; r.y += v01.y * c.w01; r.z += v01.z * c.w01; r.w += v01.w * c.w01;
-  r.x += v10.x * c.w10; r.y += v10.y * c.w10; r.z += v10.z * c.w10; r.w += v10.w * c.w10;
-  r.x += v11.x * c.w11; r.y += v11.y * c.w11; r.z += v11.z * c.w11; r.w += v11.w * c.w11;
-  return r;
-}
-
-__device__ __forceinline__ float gather1(const float* img, int ld, int n, int H, int W, const Corners& c, int ch) {
-  const float* base = img + (size_t)n * H * W * ld + ch;
-  const int x0 = min(max(c.x0, 0), W - 1), x1 = min(max(c.x0 + 1, 0), W - 1);
-  const int y0 = min(max(c.y0, 0), H - 1), y1 = min(max(c.y0 + 1, 0), H - 1);
-  const float v00 = __ldg(base + ((size_t)y0 * W + x0) * ld), v01 = __ldg(base + ((size_t)y0 * W + x1) * ld);
-  const float v10 = __ldg(base + ((size_t)y1 * W + x0) * ld), v11 = __ldg(base + ((size_t)y1 * W + x1) * ld);
-  float r = 0.f;
-  r += v00 * c.w00;
-  r += v01 * c.w01;
-  r += v10 * c.w10;
-  r += v11 * c.w11;
-  return r;
-}
-
 // ------------------------------------------------------------------------------------------
 // bwarp + Eq.(2).  LPP lanes cooperate on one pixel, each lane owning 4 channels per pass.
 // LPP = 16 (feature maps): a CTA walks an 8-row x 16-column pixel tile row by row, so the bilinear corners shared
@@ -86,10 +52,32 @@ __device__ __forceinline__ float gather1(const float* img, int ld, int n, int H,
 // pixel, 80 registers, 36 % occupancy): DRAM traffic already ideal (511 MB read vs 501 MB algorithmic) but 2.0 TB/s --
 // latency- and issue-bound (~300 instructions per lane per row).
 struct PixelPlan {
-  int ax0, ay0, bx0, by0;
-  float aw[4], bw[4];
-  float ma, mb, ka, kb, den;
+  int ia[4], ib[4];   // clamped corner pixel indices (y * W + x) of the two warps: nw, ne, sw, se
+  float aw[4], bw[4]; // corner weights, zero for out-of-image corners
+  float ma, mb, ka, kb, rden;
 };
+
+__device__ __forceinline__ void plan_corners(const Corners& c, int H, int W, int* idx, float* w) {
+  const int x0 = min(max(c.x0, 0), W - 1), x1 = min(max(c.x0 + 1, 0), W - 1);
+  const int y0 = min(max(c.y0, 0), H - 1), y1 = min(max(c.y0 + 1, 0), H - 1);
+  idx[0] = y0 * W + x0; idx[1] = y0 * W + x1; idx[2] = y1 * W + x0; idx[3] = y1 * W + x1;
+  w[0] = c.w00; w[1] = c.w01; w[2] = c.w10; w[3] = c.w11;
+}
+
+// four corner loads (all in flight together), then the ATen accumulation order nw, ne, sw, se
+__device__ __forceinline__ float4 gather4_planned(const float* base, unsigned ld, int i0, int i1, int i2, int i3, float w0, float w1,
+                                                  float w2, float w3) {
+  const float4 v0 = __ldg((const float4*)(base + (size_t)(unsigned)i0 * ld));
+  const float4 v1 = __ldg((const float4*)(base + (size_t)(unsigned)i1 * ld));
+  const float4 v2 = __ldg((const float4*)(base + (size_t)(unsigned)i2 * ld));
+  const float4 v3 = __ldg((const float4*)(base + (size_t)(unsigned)i3 * ld));
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+  r.x += v0.x * w0; r.y += v0.y * w0; r.z += v0.z * w0; r.w += v0.w * w0;
+  r.x += v1.x * w1; r.y += v1.y * w1; r.z += v1.z * w1; r.w += v1.w * w1;
+  r.x += v2.x * w2; r.y += v2.y * w2; r.z += v2.z * w2; r.w += v2.w * w2;
+  r.x += v3.x * w3; r.y += v3.y * w3; r.z += v3.z * w3; r.w += v3.w * w3;
+  return r;
+}
 
 template <int LPP>
 __global__ void __launch_bounds__(256, 4)
@@ -117,41 +105,42 @@ bwarp_blend_kernel(const float* __restrict__ a, int a_ld, const float* __restric
         const Corners ca = make_corners(bwarp_coord(px, f.x, W), bwarp_coord(py, f.y, H), H, W);
         const Corners cb = make_corners(bwarp_coord(px, f.z, W), bwarp_coord(py, f.w, H), H, W);
         PixelPlan& P = plan[threadIdx.x];
-        P.ax0 = ca.x0; P.ay0 = ca.y0; P.bx0 = cb.x0; P.by0 = cb.y0;
-        P.aw[0] = ca.w00; P.aw[1] = ca.w01; P.aw[2] = ca.w10; P.aw[3] = ca.w11;
-        P.bw[0] = cb.w00; P.bw[1] = cb.w01; P.bw[2] = cb.w10; P.bw[3] = cb.w11;
+        plan_corners(ca, H, W, P.ia, P.aw);
+        plan_corners(cb, H, W, P.ib, P.bw);
         // bwarp's validity mask: warped ones < 0.999 -> 0 (DeMFInet.py:758-766)
         P.ma = ca.wsum < 0.999f ? 0.0f : 1.0f;
         P.mb = cb.wsum < 0.999f ? 0.0f : 1.0f;
         P.ka = (1.0f - t) * o0;
         P.kb = t * o1;
-        P.den = P.ka + P.kb;
+        P.rden = 1.0f / (P.ka + P.kb);  // one IEEE division per pixel; the blend multiplies by it (<= 1 ulp from x / den)
       }
     }
     __syncthreads();
     const int col = (int)threadIdx.x >> 4, lane = (int)threadIdx.x & 15;
     const int x = tx * 16 + col;
     if (x >= W) return;
+    const size_t img = (size_t)n * H * W;
+    const float* pa = a + img * a_ld + lane * 4;
+    const float* pb = b + img * b_ld + lane * 4;
+    float* po = out + (img + (size_t)y0 * W + x) * out_ld + lane * 4;
 #pragma unroll 1
     for (int r = 0; r < 8; ++r) {
-      const int y = y0 + r;
-      if (y >= H) break;
+      if (y0 + r >= H) break;
       const PixelPlan& P = plan[r * 16 + col];
-      Corners ca, cb;
-      ca.x0 = P.ax0; ca.y0 = P.ay0; ca.w00 = P.aw[0]; ca.w01 = P.aw[1]; ca.w10 = P.aw[2]; ca.w11 = P.aw[3];
-      cb.x0 = P.bx0; cb.y0 = P.by0; cb.w00 = P.bw[0]; cb.w01 = P.bw[1]; cb.w10 = P.bw[2]; cb.w11 = P.bw[3];
-      const float ma = P.ma, mb = P.mb, ka = P.ka, kb = P.kb, den = P.den;
-      const long long pix = ((long long)n * H + y) * W + x;
-      for (int ch = lane * 4; ch < C; ch += 64) {
-        const float4 va = gather4(a, a_ld, n, H, W, ca, ch);
-        const float4 vb = gather4(b, b_ld, n, H, W, cb, ch);
-        float4 r4;
-        r4.x = (ka * (va.x * ma) + kb * (vb.x * mb)) / den;
-        r4.y = (ka * (va.y * ma) + kb * (vb.y * mb)) / den;
-        r4.z = (ka * (va.z * ma) + kb * (vb.z * mb)) / den;
-        r4.w = (ka * (va.w * ma) + kb * (vb.w * mb)) / den;
-        st4(out + pix * out_ld + ch, r4);
+      const float ma = P.ma, mb = P.mb, ka = P.ka, kb = P.kb, rden = P.rden;
+      for (int ch = 0; ch < C; ch += 64) {
+        if (ch + lane * 4 < C) {
+          const float4 va = gather4_planned(pa + ch, (unsigned)a_ld, P.ia[0], P.ia[1], P.ia[2], P.ia[3], P.aw[0], P.aw[1], P.aw[2], P.aw[3]);
+          const float4 vb = gather4_planned(pb + ch, (unsigned)b_ld, P.ib[0], P.ib[1], P.ib[2], P.ib[3], P.bw[0], P.bw[1], P.bw[2], P.bw[3]);
+          float4 r4;
+          r4.x = (ka * (va.x * ma) + kb * (vb.x * mb)) * rden;
+          r4.y = (ka * (va.y * ma) + kb * (vb.y * mb)) * rden;
+          r4.z = (ka * (va.z * ma) + kb * (vb.z * mb)) * rden;
+          r4.w = (ka * (va.w * ma) + kb * (vb.w * mb)) * rden;
+          st4(po + ch, r4);
+        }
       }
+      po += (size_t)W * out_ld;
     }
   } else {
     // LPP = 1 (3-channel pixel warp of the boosting loop): one thread per pixel, scalar channels
@@ -171,23 +160,42 @@ bwarp_blend_kernel(const float* __restrict__ a, int a_ld, const float* __restric
     const float ma = ca.wsum < 0.999f ? 0.0f : 1.0f;
     const float mb = cb.wsum < 0.999f ? 0.0f : 1.0f;
     const float ka = (1.0f - t) * o0, kb = t * o1;
-    const float den = ka + kb;
+    const float rden = 1.0f / (ka + kb);
+    int ia[4], ib[4];
+    float wa[4], wb[4];
+    plan_corners(ca, H, W, ia, wa);
+    plan_corners(cb, H, W, ib, wb);
+    const size_t img = (size_t)n * H * W;
+    const float* pa = a + img * a_ld;
+    const float* pb = b + img * b_ld;
     if (C % 4 == 0) {
       for (int ch = 0; ch < C; ch += 4) {
-        const float4 va = gather4(a, a_ld, n, H, W, ca, ch);
-        const float4 vb = gather4(b, b_ld, n, H, W, cb, ch);
+        const float4 va = gather4_planned(pa + ch, (unsigned)a_ld, ia[0], ia[1], ia[2], ia[3], wa[0], wa[1], wa[2], wa[3]);
+        const float4 vb = gather4_planned(pb + ch, (unsigned)b_ld, ib[0], ib[1], ib[2], ib[3], wb[0], wb[1], wb[2], wb[3]);
         float4 r4;
-        r4.x = (ka * (va.x * ma) + kb * (vb.x * mb)) / den;
-        r4.y = (ka * (va.y * ma) + kb * (vb.y * mb)) / den;
-        r4.z = (ka * (va.z * ma) + kb * (vb.z * mb)) / den;
-        r4.w = (ka * (va.w * ma) + kb * (vb.w * mb)) / den;
+        r4.x = (ka * (va.x * ma) + kb * (vb.x * mb)) * rden;
+        r4.y = (ka * (va.y * ma) + kb * (vb.y * mb)) * rden;
+        r4.z = (ka * (va.z * ma) + kb * (vb.z * mb)) * rden;
+        r4.w = (ka * (va.w * ma) + kb * (vb.w * mb)) * rden;
         st4(out + pix * out_ld + ch, r4);
       }
     } else {
+      // scalar channels (C = 3): all 8 x C corner loads are independent; addresses computed once per corner
+      const float* qa[4];
+      const float* qb[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        qa[k] = pa + (size_t)(unsigned)ia[k] * (unsigned)a_ld;
+        qb[k] = pb + (size_t)(unsigned)ib[k] * (unsigned)b_ld;
+      }
       for (int ch = 0; ch < C; ++ch) {
-        const float va = gather1(a, a_ld, n, H, W, ca, ch);
-        const float vb = gather1(b, b_ld, n, H, W, cb, ch);
-        out[pix * out_ld + ch] = (ka * (va * ma) + kb * (vb * mb)) / den;
+        float va = 0.f, vb = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          va += __ldg(qa[k] + ch) * wa[k];
+          vb += __ldg(qb[k] + ch) * wb[k];
+        }
+        out[pix * out_ld + ch] = (ka * (va * ma) + kb * (vb * mb)) * rden;
       }
     }
   }
@@ -195,34 +203,51 @@ bwarp_blend_kernel(const float* __restrict__ a, int a_ld, const float* __restric
 
 // ------------------------------------------------------------------------------------------
 // FGAC sampling: absolute coordinates = flow values (DeMFInet.py:413-419, 499-508).
+// A group of LPP lanes handles PPT pixels: lane k of the group does the coordinate arithmetic of pixel k (one flow load
+// each, in parallel), the corner indices / weights are broadcast by shuffle, then all PPT x 4 corner gathers of a lane are
+// issued before the first use (256 bytes of loads in flight per thread).
 template <int LPP>
 __global__ void __launch_bounds__(256)
 fgac_sample_kernel(const float* __restrict__ refk, int refk_ld, const float* __restrict__ flow, int flow_ld, int B,
                    int H, int W, int C, float* __restrict__ out, int out_ld) {
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long pix = gid / LPP;
-  const int lane = (int)(gid % LPP);
+  constexpr int PPT = 4;
+  const int lane = (int)(threadIdx.x % LPP);
+  const long long ppb = blockDim.x / LPP;  // pixels one block covers per step
+  const long long p0 = (long long)blockIdx.x * ppb * PPT + threadIdx.x / LPP;
   const long long npix = (long long)B * H * W;
-  const bool live = pix < npix;  // no early return: every lane of the warp takes part in the shuffles below
-  const int n = (int)(pix / ((long long)W * H));
-  // one lane per pixel does the coordinate arithmetic, the others receive the corners by shuffle (blocks are whole
-  // groups of LPP lanes: npix * LPP threads are launched in blocks of 256)
-  Corners c = {};
-  if (lane == 0 && live) {
-    const float2 f = __ldg((const float2*)(flow + pix * flow_ld));
-    // bilinear_sampler: g = 2*f/(W-1) - 1; grid_sample: ((g+1)/2)*(W-1)
-    const float gx = 2.0f * f.x / (float)(W - 1) - 1.0f;
-    const float gy = 2.0f * f.y / (float)(H - 1) - 1.0f;
-    c = make_corners(((gx + 1.0f) / 2.0f) * (float)(W - 1), ((gy + 1.0f) / 2.0f) * (float)(H - 1), H, W);
+  const long long plane = (long long)W * H;
+  int idx[4] = {0, 0, 0, 0};
+  float wgt[4] = {0.f, 0.f, 0.f, 0.f};
+  if (lane < PPT) {
+    const long long pix = p0 + lane * ppb;
+    if (pix < npix) {
+      const float2 f = __ldg((const float2*)(flow + pix * flow_ld));
+      // bilinear_sampler: g = 2*f/(W-1) - 1; grid_sample: ((g+1)/2)*(W-1)
+      const float gx = 2.0f * f.x / (float)(W - 1) - 1.0f;
+      const float gy = 2.0f * f.y / (float)(H - 1) - 1.0f;
+      const Corners c = make_corners(((gx + 1.0f) / 2.0f) * (float)(W - 1), ((gy + 1.0f) / 2.0f) * (float)(H - 1), H, W);
+      plan_corners(c, H, W, idx, wgt);
+    }
   }
-  c.x0 = __shfl_sync(0xffffffffu, c.x0, 0, LPP);
-  c.y0 = __shfl_sync(0xffffffffu, c.y0, 0, LPP);
-  c.w00 = __shfl_sync(0xffffffffu, c.w00, 0, LPP);
-  c.w01 = __shfl_sync(0xffffffffu, c.w01, 0, LPP);
-  c.w10 = __shfl_sync(0xffffffffu, c.w10, 0, LPP);
-  c.w11 = __shfl_sync(0xffffffffu, c.w11, 0, LPP);
-  if (!live) return;
-  for (int ch = lane * 4; ch < C; ch += LPP * 4) st4(out + pix * out_ld + ch, gather4(refk, refk_ld, n, H, W, c, ch));
+  for (int ch = lane * 4; ch < C; ch += LPP * 4) {
+    float4 r[PPT];
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+      // every lane of the warp takes part in the shuffles (no early exit above)
+      const int i0 = __shfl_sync(0xffffffffu, idx[0], k, LPP), i1 = __shfl_sync(0xffffffffu, idx[1], k, LPP);
+      const int i2 = __shfl_sync(0xffffffffu, idx[2], k, LPP), i3 = __shfl_sync(0xffffffffu, idx[3], k, LPP);
+      const float w0 = __shfl_sync(0xffffffffu, wgt[0], k, LPP), w1 = __shfl_sync(0xffffffffu, wgt[1], k, LPP);
+      const float w2 = __shfl_sync(0xffffffffu, wgt[2], k, LPP), w3 = __shfl_sync(0xffffffffu, wgt[3], k, LPP);
+      const long long pix = p0 + k * ppb;
+      const long long n = pix < npix ? pix / plane : 0;
+      r[k] = gather4_planned(refk + (size_t)n * plane * refk_ld + ch, (unsigned)refk_ld, i0, i1, i2, i3, w0, w1, w2, w3);
+    }
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+      const long long pix = p0 + k * ppb;
+      if (pix < npix) st4(out + pix * out_ld + ch, r[k]);
+    }
+  }
 }
 
 // Pure streaming (3 reads + 1 write per element): four pixels per lane group, all loads issued before the first use
@@ -446,7 +471,7 @@ int demfi_fgac_sample(const float* refk, int32_t refk_ld, const float* flow, int
   DEMFI_REQUIRE(refk_ld % 4 == 0 && out_ld % 4 == 0 && flow_ld % 2 == 0 && ((uintptr_t)flow % 8) == 0 &&
                     ((uintptr_t)refk % 16) == 0 && ((uintptr_t)out % 16) == 0, "fgac_sample: misaligned slices");
   const long long npix = (long long)B * H * W;
-  fgac_sample_kernel<16><<<blocks_for(npix * 16), 256, 0, (cudaStream_t)stream>>>(refk, refk_ld, flow, flow_ld, B, H, W,
+  fgac_sample_kernel<16><<<blocks_for(npix * 16, 256 * 4), 256, 0, (cudaStream_t)stream>>>(refk, refk_ld, flow, flow_ld, B, H, W,
                                                                                    C, out, out_ld);
   DEMFI_LAUNCH_CHECK("fgac_sample");
   return 0;
