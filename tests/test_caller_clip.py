@@ -193,3 +193,23 @@ def test_folder_runner_writes_what_the_reference_loop_writes(tmp_path):
     s0 = np.squeeze(res0[1][-1][0].numpy()).astype(np.float64)[..., :oh, :ow]
     img0 = np.transpose(((s0 + 1) / 2).clip(0, 1) * 255, [1, 2, 0]).astype(np.uint8)
     assert np.array_equal(cv2.imread(os.path.join(out_dir, "00001.png")), img0)
+
+
+def test_folder_runner_shards_pairs_across_ranks(tmp_path):
+    """world_size 2: the two ranks split the frame pairs (all t of a pair stay on one rank), together they write every file
+    exactly as one rank does"""
+    from demfi_b200.clip import FolderRunner
+    roots = []
+    for world in (1, 2):
+        root = str(tmp_path / f"w{world}")
+        _write_scene(root, "s", 7, 24, 40, 9)  # 4 pairs
+        counts = [FolderRunner(BlendModel(), multiple=2, num_update=1, io_threads=2, rank=r, world=world).run(root) for r in range(world)]
+        assert sum(c["pairs"] for c in counts) == 4 and sum(c["interpolated"] for c in counts) == 4
+        if world == 2:
+            assert [c["pairs"] for c in counts] == [2, 2]
+        roots.append(os.path.join(root, "s_sharply_interpolated_x2"))
+    import cv2
+    assert sorted(os.listdir(roots[0])) == sorted(os.listdir(roots[1]))
+    for name in os.listdir(roots[0]):
+        if "_" in name:  # interpolated frames: one writer each (deblurred frames are written by two neighbouring pairs)
+            assert np.array_equal(cv2.imread(os.path.join(roots[0], name)), cv2.imread(os.path.join(roots[1], name))), name
