@@ -394,3 +394,39 @@ def test_s16_mixed_residual(res_s16, dst_s16):
              [dict(ch0=0, nch=64, dst=out, res=rb, fmt=(A.SEG_DST_S16 if dst_s16 else 0) | (A.SEG_RES_S16 if res_s16 else 0))])
     got = s16_decode(out) if dst_s16 else out
     check(from_nhwc(got, 64), ref_conv(x, w, b) + r_val, f"mixed residual res_s16={res_s16} dst_s16={dst_s16}")
+
+
+@pytest.mark.parametrize("case", ["resident_res_s16", "ring_7x7_f32", "gru_s16"])
+def test_s3_repeated_launches_are_bitwise_identical(case):
+    """race hunt: persistent tile loop (800 tiles on 148 CTAs), staging-tile reuse behind asynchronous TMA stores, in-place
+    conversion, weight ring -- the kernel has a fixed accumulation order, so every launch must reproduce the first bit for bit"""
+    import ctypes as C
+    lib = A.lib()
+    n, h, w_ = 2, 156, 312
+    if case == "resident_res_s16":
+        x, r = rnd(n, 64, h, w_, seed=50), rnd(n, 64, h, w_, seed=51)
+        xb, rb = s16_encode(nhwc(x)[0]), s16_encode(nhwc(r)[0])
+        w, b = wb(64, 64, 3, 3)
+        out = torch.zeros(n, h, w_, 64, device=DEV)
+        args = (w, b, [(xb, 64, 0, A.FMT_S16)], (h, w_), A.CONV_TC16,
+                [dict(ch0=0, nch=64, dst=out, res=rb, fmt=A.SEG_DST_S16 | A.SEG_RES_S16)])
+    elif case == "ring_7x7_f32":
+        x = rnd(n, 96, h, w_, seed=52)
+        xb = nhwc(x)[0]
+        w, b = wb(64, 96, 7, 7)
+        out = torch.zeros(n, h, w_, 64, device=DEV)
+        args = (w, b, [(xb, 96, 0)], (h, w_), A.CONV_TC16, [dict(ch0=0, nch=64, dst=out, act=A.ACT_TANH)])
+    else:
+        hx = rnd(n, 128, h, w_, seed=53, scale=0.7)
+        hs, xs = s16_encode(nhwc(hx[:, :64])[0]), s16_encode(nhwc(hx[:, 64:])[0])
+        w, b = wb(128, 128, 1, 5)
+        out = torch.zeros(n, h, w_, 128, device=DEV)
+        args = (w, b, [(hs, 64, 0, A.FMT_S16), (xs, 64, 0, A.FMT_S16)], (h, w_), A.CONV_TC16,
+                [dict(ch0=0, nch=64, dst=out, act=A.ACT_SIGMOID, fmt=A.SEG_DST_S16),
+                 dict(ch0=64, nch=64, dst=out, dst_c0=64, act=A.ACT_SIGMOID_MUL, res=hs, fmt=A.SEG_DST_S16 | A.SEG_RES_S16)])
+    run_conv(*args)
+    ref = out.clone()
+    for it in range(12):
+        out.zero_()
+        run_conv(*args)
+        assert torch.equal(out.view(torch.int32), ref.view(torch.int32)), f"{case}: launch {it} differs from the first"
