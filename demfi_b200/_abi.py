@@ -33,6 +33,13 @@ class Seg(C.Structure):
                 ("ch0", i32), ("nch", i32), ("act", i32), ("store", i32), ("fmt", i32)]
 
 
+class Part(C.Structure):
+    _fields_ = [("src", vp), ("src_ld", i32), ("nch", i32), ("dst_c0", i32), ("reserved", i32)]
+
+
+MAX_PARTS = 8
+
+
 class Conv(C.Structure):
     _fields_ = [("N", i32), ("H", i32), ("W", i32), ("Hi", i32), ("Wi", i32),
                 ("KH", i32), ("KW", i32), ("stride", i32), ("pad_h", i32), ("pad_w", i32),
@@ -57,6 +64,7 @@ SYMBOLS = {
     "demfi_fgac_sample": (i32, [vp, i32, vp, i32, i32, i32, i32, i32, vp, i32, vp]),
     "demfi_fgac_blend": (i32, [vp, i32, vp, i32, vp, i32, C.c_int64, i32, vp, i32, vp]),
     "demfi_copy_channels": (i32, [vp, i32, vp, i32, i32, C.c_int64, i32, vp]),
+    "demfi_gather_channels": (i32, [C.POINTER(Part), i32, vp, i32, C.c_int64, vp]),
     "demfi_upsample2x": (i32, [vp, i32, i32, i32, i32, i32, vp, i32, vp]),
     "demfi_export_nchw": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, vp]),
     "demfi_import_nchw": (i32, [vp, i32, i32, i32, i32, vp, i32, vp]),

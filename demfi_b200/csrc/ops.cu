@@ -393,6 +393,32 @@ copy_channels_kernel(const float* __restrict__ src, int src_ld, float* __restric
   dst[pix * dst_ld + c] = act_scalar(act, __ldg(src + pix * src_ld + c));
 }
 
+struct GatherParams {
+  demfi_part_t part[DEMFI_MAX_PARTS];
+  int nparts;
+};
+
+// one thread per (pixel, part): the parts of a pixel are copied by neighbouring threads, so the loads of all parts are in flight
+// together and the destination row is completed by one warp
+__global__ void __launch_bounds__(256)
+gather_channels_kernel(const __grid_constant__ GatherParams G, float* __restrict__ dst, int dst_ld, long long npix) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long pix = gid / G.nparts;
+  const int k = (int)(gid - pix * G.nparts);
+  if (pix >= npix) return;
+  const demfi_part_t& P = G.part[k];
+  const float* s = P.src + pix * P.src_ld;
+  float* d = dst + pix * dst_ld + P.dst_c0;
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (j < P.nch) v[j] = __ldg(s + j);
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (j < P.nch) d[j] = v[j];
+  for (int j = 8; j < P.nch; ++j) d[j] = __ldg(s + j);
+}
+
 __global__ void __launch_bounds__(256)
 export_nchw_kernel(const float* __restrict__ src, int src_ld, int B, int H, int W, int C, int act,
                    float* __restrict__ dst) {
@@ -522,6 +548,21 @@ int demfi_copy_channels(const float* src, int32_t src_ld, float* dst, int32_t ds
   DEMFI_REQUIRE(nch > 0 && npix > 0, "copy_channels: bad shape");
   copy_channels_kernel<<<blocks_for(npix * nch), 256, 0, (cudaStream_t)stream>>>(src, src_ld, dst, dst_ld, nch, npix, act);
   DEMFI_LAUNCH_CHECK("copy_channels");
+  return 0;
+}
+
+int demfi_gather_channels(const demfi_part_t* parts, int32_t nparts, float* dst, int32_t dst_ld, int64_t npix, void* stream) {
+  if (check_device()) return 3;
+  DEMFI_REQUIRE(parts && dst && nparts >= 1 && nparts <= DEMFI_MAX_PARTS && npix > 0, "gather_channels: bad arguments");
+  GatherParams G;
+  G.nparts = nparts;
+  for (int k = 0; k < nparts; ++k) {
+    DEMFI_REQUIRE(parts[k].src && parts[k].nch > 0 && parts[k].dst_c0 >= 0 && parts[k].dst_c0 + parts[k].nch <= dst_ld,
+                  "gather_channels: part %d does not fit the destination row", k);
+    G.part[k] = parts[k];
+  }
+  gather_channels_kernel<<<blocks_for(npix * nparts), 256, 0, (cudaStream_t)stream>>>(G, dst, dst_ld, npix);
+  DEMFI_LAUNCH_CHECK("gather_channels");
   return 0;
 }
 

@@ -354,14 +354,11 @@ class Engine:
         SP = v["SP"]
         ops.append(self.conv("Dec_last2", [b_], (H, W), 3 * B, [full(SP, 4)]))
         REF = v["REF"]
-        for f in range(3):
-            ops.append(("copy", SP.frames(f * B, B).ch(0, 3), REF.ch(3 * f, 3), none))
-            if f < 2:
-                ops.append(("copy", SP.frames(f * B, B).ch(0, 3), A3.ch(3 * f, 3), none))
-        ops.append(("copy", FO.ch(0, 4), REF.ch(21, 4), none))
-        ops.append(("copy", DL0.ch(0, 5), REF.ch(25, 5), none))
-        ops.append(("copy", DL0.ch(0, 4), A3.ch(10, 4), none))
-        ops.append(("copy", FO.ch(0, 4), A3.ch(14, 4), none))
+        # ref_list (DeMFInet.py:117-120) and the static part of Agg3 (:151-155): each destination row is assembled in one pass
+        ops.append(("gather", REF, [(SP.frames(f * B, B).ch(0, 3), 3 * f) for f in range(3)] +
+                    [(FO.ch(0, 4), 21), (DL0.ch(0, 5), 25)]))
+        ops.append(("gather", A3, [(SP.frames(f * B, B).ch(0, 3), 3 * f) for f in range(2)] +
+                    [(DL0.ch(0, 4), 10), (FO.ch(0, 4), 14)]))
         # Ch_Reducer (DeMFInet.py:114) over cat(rF0, rF1, rFt)
         FR = [v["FR0"], v["FR1"], v["FR2"]]
         ops.append(self.conv("Ch_Reducer", [DECIN.frames(0, B), DECIN.frames(B, B), DECIN.frames(2 * B, B)], (H, W), B,
@@ -376,7 +373,9 @@ class Engine:
         self._iter_cache: Dict[Tuple[int, bool], list] = {}
         for ops_ in (self.ops_prefix_ff, self.ops_stage1):
             for op in ops_:  # only convolutions (and the bit-copying up-sampler) may touch S16 views
-                if op[0] not in ("conv", "upsample"):
+                if op[0] == "gather":
+                    assert op[1].fmt == A.FMT_F32 and all(sv.fmt == A.FMT_F32 for sv, _ in op[2])
+                elif op[0] not in ("conv", "upsample"):
                     assert all(a_.fmt == A.FMT_F32 for a_ in op[1:] if isinstance(a_, View)), op[0]
         self._agg3_map = (list(range(9)) + [73] + [74, 75, 76, 77] + [80, 81, 78, 79] + [82, 83, 84, 85] + [86]
                           + list(range(87, 99)) + [-1] + list(range(9, 73)))
@@ -475,6 +474,12 @@ class Engine:
                     assert op[2].fmt == op[1].fmt, "upsample copies bits: source and destination formats must agree"
                 elif op[0] == "zero":
                     write(op[1], A.FMT_F32)
+                elif op[0] == "gather":
+                    assert op[1].fmt == A.FMT_F32, "gather only handles fp32 views"
+                    for sv, c0 in op[2]:
+                        assert sv.fmt == A.FMT_F32, "gather only handles fp32 views"
+                        read(sv, "gather")
+                        write(op[1].ch(c0, sv.C))
                 else:
                     vs = [a_ for a_ in op[1:] if isinstance(a_, View)]
                     first_out = {"copy": 1, "cfr_splat": 1, "cfr_finalize": 1, "bwarp_blend": 4, "fgac_sample": 2, "fgac_blend": 3}[op[0]]
@@ -512,6 +517,13 @@ class Engine:
             elif k == "copy":
                 s, d, act = op[1], op[2], op[3]
                 A.check(lib.demfi_copy_channels(s.ptr, s.ld, d.ptr, d.ld, s.C, s.npix(), act, st), "copy_channels")
+            elif k == "gather":
+                dst, parts = op[1], op[2]
+                arr = (A.Part * len(parts))()
+                for i, (sv, c0) in enumerate(parts):
+                    arr[i].src, arr[i].src_ld, arr[i].nch, arr[i].dst_c0 = sv.ptr, sv.ld, sv.C, dst.c0 + c0
+                A.check(lib.demfi_gather_channels(arr, len(parts), dst.t.data_ptr() + 4 * dst.n0 * dst.H * dst.W * dst.ld, dst.ld,
+                                                  dst.npix(), st), "gather_channels")
             elif k == "zero":
                 op[1].t.zero_()
             elif k == "upsample":
@@ -600,6 +612,8 @@ class Engine:
             return op[1].npix() * 4 * (8 + 4)
         if k == "copy":
             return op[1].npix() * 4 * 2 * op[1].C
+        if k == "gather":
+            return op[1].npix() * 4 * 2 * sum(sv.C for sv, _ in op[2])
         if k == "upsample":
             return op[2].npix() * 4 * op[2].C * 5 // 4
         if k == "zero":

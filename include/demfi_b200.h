@@ -166,6 +166,15 @@ int demfi_fgac_blend(const float* w, int32_t w_ld, const float* src, int32_t src
  * Replaces the small torch.cat assemblies (DeMFInet.py:117-123, 151-155). act: NONE or SIGMOID. */
 int demfi_copy_channels(const float* src, int32_t src_ld, float* dst, int32_t dst_ld, int32_t nch, int64_t npix,
                         int32_t act, void* stream);
+/* Several channel-slice copies into ONE destination buffer in one pass over its pixels (the torch.cat assemblies of
+ * ref_list / Agg3, DeMFInet.py:117-123, 151-155): for every part k, dst[p*dst_ld + dst_c0[k] + j] = src[k][p*src_ld[k] + j],
+ * j < nch[k].  At most DEMFI_MAX_PARTS parts; all parts index the same npix pixels. */
+#define DEMFI_MAX_PARTS 8
+typedef struct {
+  const float* src;
+  int32_t src_ld, nch, dst_c0, reserved;
+} demfi_part_t;
+int demfi_gather_channels(const demfi_part_t* parts, int32_t nparts, float* dst, int32_t dst_ld, int64_t npix, void* stream);
 /* nn.UpsamplingNearest2d(scale_factor=2) (DeMFInet.py:573): src [B,Hs,Ws,C of src_ld] -> dst [B,2Hs,2Ws,C of dst_ld].
  * Materialises the UNet decoder inputs so that dec1-3 run on the tensor-core conv. */
 int demfi_upsample2x(const float* src, int32_t src_ld, int32_t B, int32_t Hs, int32_t Ws, int32_t C, float* dst,

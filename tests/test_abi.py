@@ -34,14 +34,15 @@ def test_every_declared_symbol_is_exported_and_bound():
 
 def test_ctypes_struct_layout_matches_c(tmp_path):
     prog = tmp_path / "sz.c"
-    prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "demfi_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n",'
+    prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "demfi_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                     'sizeof(demfi_src_t),sizeof(demfi_seg_t),sizeof(demfi_conv_t),offsetof(demfi_conv_t,src),'
-                    'offsetof(demfi_conv_t,seg),offsetof(demfi_conv_t,wpack),offsetof(demfi_seg_t,ch0));return 0;}\n')
+                    'offsetof(demfi_conv_t,seg),offsetof(demfi_conv_t,wpack),offsetof(demfi_seg_t,ch0),sizeof(demfi_part_t),'
+                    'offsetof(demfi_part_t,dst_c0));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)], check=True)
     got = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
     want = [C.sizeof(A.Src), C.sizeof(A.Seg), C.sizeof(A.Conv), A.Conv.src.offset, A.Conv.seg.offset, A.Conv.wpack.offset,
-            A.Seg.ch0.offset]
+            A.Seg.ch0.offset, C.sizeof(A.Part), A.Part.dst_c0.offset]
     assert got == want, (got, want)
 
 

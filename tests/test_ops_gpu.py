@@ -157,3 +157,22 @@ def test_upsample2x():
     want = src.repeat_interleave(2, 2).repeat_interleave(2, 3)
     assert torch.equal(dst[..., 16:16 + C].permute(0, 3, 1, 2).cpu(), want)
     assert float(dst[..., :16].abs().max()) == 0 and float(dst[..., 16 + C:].abs().max()) == 0
+
+
+def test_gather_channels_assembles_a_row_in_one_pass():
+    """ref_list / Agg3 assembly (DeMFInet.py:117-123, 151-155): five slices of four buffers into one 32-channel row"""
+    import ctypes as C
+    n, h, w = 2, 20, 28
+    g = torch.Generator().manual_seed(3)
+    srcs = [torch.randn(n, h, w, ld, generator=g).to(DEV) for ld in (4, 4, 8, 8)]
+    dst = torch.full((n, h, w, 32), -7.0, device=DEV)
+    spec = [(0, 0, 3, 0), (1, 0, 3, 3), (2, 0, 4, 21), (3, 0, 5, 25), (2, 4, 1, 30)]  # (buffer, src channel 0, nch, dst channel 0)
+    arr = (A.Part * len(spec))()
+    for i, (b, c0, nch, d0) in enumerate(spec):
+        arr[i].src, arr[i].src_ld, arr[i].nch, arr[i].dst_c0 = srcs[b].data_ptr() + 4 * c0, srcs[b].shape[3], nch, d0
+    A.check(A.lib().demfi_gather_channels(arr, len(spec), dst.data_ptr(), 32, n * h * w, stream()), "gather")
+    torch.cuda.synchronize()
+    want = torch.full((n, h, w, 32), -7.0, device=DEV)
+    for b, c0, nch, d0 in spec:
+        want[..., d0:d0 + nch] = srcs[b][..., c0:c0 + nch]
+    assert torch.equal(dst, want)
