@@ -73,6 +73,7 @@ struct S3Params {
   int acc_stride;
   int taps, stages_per_tile, flush;
   int tma_epi, stg2_off;
+  int all_full_chunks;  // every source has C % 32 == 0 (no ragged chunk)
   float comp;
   int diag;
   long long* dbg;
@@ -670,6 +671,8 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
       const uint32_t row_skip = (uint32_t)(P.hw - c.KW) << 3;  // extra step from the last tap of a kernel row to the next row
       const int KW = c.KW, taps = P.taps;
       const bool resident = P.resident != 0;
+      const bool fast33 = resident && c.KH == 3 && c.KW == 3 && P.nb_max == 64 && c.cout_pad == 64 && P.flush == 9 &&
+                          P.acc_stride == 128 && !(P.diag & 64) && P.all_full_chunks;
       long long w_tempty = 0, w_ready = 0;
       const long long t_begin = dbg ? clock64() : 0;
       uint32_t slot = 0, sphase = 0, acc = 0, acc_phase = 0, abuf = 0, aphase = 0, cvphase = 0;
@@ -700,6 +703,26 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
           if (c0 >= c.src[si].C) { c0 = 0; ++si; }
           uint32_t a = a_lo0 + astep * abuf;
           int kx = 0, tap = 0;
+          if (fast33) {
+            // the dominant shape (64 -> 64 3x3, resident weights, one accumulation segment per chunk): the 36 MMAs of a chunk
+            // straight-line, every operand = one of two bases + an immediate (halo row = 10 pixels, stage = 512 x 16 bytes)
+            mbar_wait_t(bar_tempty(acc), acc_phase ^ 1u, dbg, w_tempty);
+            tc_fence_after();
+            const uint32_t dm = tmem_base + acc * 128u, dc = dm + 64u;
+            const uint32_t bb = b_lo0 + (uint32_t)ch * (9u * 512u);
+#pragma unroll
+            for (int tp = 0; tp < 9; ++tp) {
+              const uint32_t ao = (uint32_t)((tp / 3) * 80 + (tp % 3) * 8), bo = (uint32_t)tp * 512u;
+              umma_f16_ss2(dm, a + ao, a_hi, bb + bo, b_hi, idesc_2n, tp == 0 ? 0u : 1u);
+              umma_f16_ss2(dm, a + ao + 2u, a_hi, bb + bo + 2u, b_hi, idesc_2n, 1u);
+              umma_f16_ss2(dc, a + ao + 4u, a_hi, bb + bo, b_hi, idesc_n, 1u);
+              umma_f16_ss2(dc, a + ao + 6u, a_hi, bb + bo + 2u, b_hi, idesc_n, 1u);
+            }
+            umma_commit(bar_tfull(acc));
+            acc ^= 1u;
+            if (acc == 0) acc_phase ^= 1u;
+            tap = taps;
+          }
 #pragma unroll 1
           while (tap < taps) {
             uint32_t accum = 1u;
@@ -1012,6 +1035,9 @@ int launch_conv_s3(const demfi_conv_t& c, cudaStream_t st) {
   const int smem = P.bias_off + 1024 + 1024;
   DEMFI_REQUIRE(smem <= S3_SMEM_MAX + 1024, "conv_s3: shared-memory plan (%d bytes) does not fit", smem);
 
+  P.all_full_chunks = 1;
+  for (int s_ = 0; s_ < c.nsrc; ++s_)
+    if (c.src[s_].C % S3_KC != 0) P.all_full_chunks = 0;
   P.flush = get_option("tc_flush");
   if (P.flush <= 0 || P.flush > P.stages_per_tile) P.flush = P.stages_per_tile;
   {  // balanced segments
@@ -1019,7 +1045,7 @@ int launch_conv_s3(const demfi_conv_t& c, cudaStream_t st) {
     P.flush = (P.stages_per_tile + nseg - 1) / nseg;
   }
   P.comp = (float)get_option("tc_comp_milli") * 1e-3f * 5.9604645e-8f;
-  P.diag = get_option("tc_diag") & (1 | 16 | 32 | 128);
+  P.diag = get_option("tc_diag") & (1 | 16 | 32 | 64 | 128);
   if (P.diag & 128) {
     long long* buf = tc_debug_buffer(st);
     DEMFI_REQUIRE(buf != nullptr, "conv_s3: cannot allocate the role-timer buffer");
