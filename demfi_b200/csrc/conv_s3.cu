@@ -3,32 +3,35 @@
 //   D_main += Ah * Bh            D_corr += Ah * Bl + Al * Bh          out = D_main + D_corr / 2048
 //
 // with BOTH operands read by the tensor core from shared memory (SS-form tcgen05.mma): no per-tap register
-// traffic at all.  ncu on conv_h3 (profiles/r1_conv_h3_profile.md) showed the L1/shared-memory data pipe at
+// traffic at all.  ncu on conv_h3 (profiles/r1_conv_s3_profile.md) showed the L1/shared-memory data pipe at
 // ~80 % and the MMA issuer waiting for its A operand 53 % of the time: every tap of every chunk went
 // shared memory -> registers -> tensor memory through eight splitter warps, and the epilogue's per-thread
 // 16-byte global stores (one 32-byte sector each) were another 23 % of the pipe's wavefronts.
 //
 // Data flow per persistent CTA (one per SM), tile = 16 rows x 8 output pixels (M = 128), N block <= 96:
-//   * activations: ONE TMA box per 32-channel chunk covering the tile plus its halo {32 ch, 8+KW-1, 16+KH-1}
-//     (fp32, 128-byte rows = pixels).  Six converter warps split it ONCE, in place, into fp16 hi / lo and lay it
-//     out as the tensor core's un-swizzled K-major canonical layout: eight planes (4 x hi, 4 x lo) of
-//     [halo pixel][8 channels = 16 bytes].  In that layout a core matrix is 8 consecutive pixels x 16 bytes
-//     (128 contiguous bytes) and the 8-pixel groups of the M dimension are one halo row apart, so the A
-//     operand of tap (ky, kx) is the SAME buffer behind a descriptor whose start address is moved by
-//     (ky * halo_w + kx) * 16 bytes, with SBO = halo_w * 16 (next tile row) and LBO = one plane (next 8 channels).
-//     The tile is 8 pixels wide precisely so that every core matrix is one contiguous run of halo pixels.
+//   * activations: ONE TMA box per 32-channel chunk covering the tile plus its halo {32 ch, 8+KW-1, 16+KH-1},
+//     128-byte rows = pixels, 128-byte swizzle.  A source in the S16 storage format (include/demfi_b200.h) already
+//     holds [32 x fp16 hi | 32 x fp16 lo] per row: the TMA tile IS the MMA operand.  An fp32 source is split ONCE per
+//     halo pixel, in place, by six converter warps into the same row format (same 128 bytes, same swizzle).
+//     The A operand of tap (ky, kx) is the SAME buffer behind a shifted-window descriptor: start address moved by
+//     (ky * halo_w + kx) * 128 bytes, SBO = halo_w * 128 (next tile row), k-step + 32 bytes, lo half + 64 bytes.  The
+//     128-byte swizzle is a function of the absolute shared-memory address bits, so unaligned window starts need no
+//     base offset (verified against float64 conv2d).  The tile is 8 pixels wide precisely so that every 8-row
+//     core-matrix group of the M dimension is one contiguous run of halo pixels.
 //   * weights: the pre-packed [Bh rows ; Bl rows] x 32 fp16 tiles of conv_h3 (64-byte swizzle).  When the whole
 //     filter bank of the N block fits beside the activation buffers (e.g. 64 -> 64 3x3: 144 KB) it is loaded once per
-//     CTA and stays resident; otherwise it streams through a ring, one (chunk, tap) stage at a time.
-//   * MMAs per (tap, 16 channels): Ah x [Bh;Bl] (N' = 2N: main | corr) and Al x Bh (-> corr), issued by one thread.
+//     CTA and stays resident; otherwise it streams through a ring whose slots hold groups of consecutive (chunk, tap)
+//     stages (one bulk copy and one barrier round trip per group).
+//   * MMAs per (tap, 16 channels): Ah x [Bh;Bl] (N' = 2N: main | corr) and Al x Bh (-> corr), issued by one thread
+//     whose inner loop is 4 MMAs + 32-bit adds (every instruction there is serial with the tensor pipe).
 //   * the K loop is cut into segments whose partial sums are drained from tensor memory (double-buffered) and
 //     added in fp32 RN by eight epilogue warps, with the gain compensation of the truncating tensor-core
 //     accumulation.
-//   * epilogue: for plain destinations (NHWC, pure activation, optional residual, all segments alike) the tile is
-//     staged in shared memory in the TMA 128-byte-swizzle box layout and written with cp.async.bulk.tensor
-//     stores (residual tiles are TMA-loaded into the same staging buffer first): whole 128-byte lines instead
-//     of one sector per thread.  Everything else (multi-activation heads, pixel shuffle, GRU) keeps the generic
-//     per-thread epilogue of common.cuh.
+//   * epilogue, planned per N block on the host: bias, operand tiles (residual, GRU h / z) TMA-loaded into the staging
+//     tile, activation, result staged in the TMA 128-byte-swizzle box layout as fp32 or S16 and written with
+//     cp.async.bulk.tensor stores (1-2 destinations, pixel shuffle as a strided tensor map): whole 128-byte lines
+//     instead of one sector per thread.  What the planner cannot express keeps the generic per-thread epilogue of
+//     common.cuh.
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -45,7 +48,6 @@ constexpr int S3_EPI_THREADS = S3_EPI_WARPS * 32;
 constexpr int S3_THREADS = (S3_CV_WARPS + S3_EPI_WARPS + 2) * 32;  // 512: 0-5 convert, 6-13 epilogue, 14 TMA, 15 MMA
 constexpr int S3_MAX_NA = 3;   // halo-tile buffers
 constexpr int S3_MAX_NS = 8;   // weight ring
-constexpr int S3_MAX_PX = 2;   // halo pixels per converter thread (halo <= 384 pixels)
 constexpr int S3_BOX_BYTES = S3_BM * 128;  // one 32-channel staging box
 constexpr int S3_NBARS = 3 * S3_MAX_NA + 4 + 2 + 2 * S3_MAX_NS;
 constexpr float S3_LO_SCALE = 2048.0f;
@@ -898,7 +900,7 @@ bool s3_supports(const demfi_conv_t& c) {
   for (int s = 0; s < c.nsrc; ++s)
     if (c.src[s].up != 0) return false;
   const int hw = S3_TW + c.KW - 1, hh = S3_TH + c.KH - 1;
-  if (hw > 256 || hh > 256 || hw * hh > S3_MAX_PX * S3_CV_THREADS) return false;
+  if (hw > 256 || hh > 256) return false;
   const int a_bytes = (hw * hh * 128 + 1023) / 1024 * 1024;
   const int nbm = s3_nb_max(c.cout_pad);
   const int b_bytes = 2 * nbm * 64;
