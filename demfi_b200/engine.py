@@ -94,6 +94,10 @@ class Engine:
         self._sd = {k: v.detach().to("cpu", torch.float32).contiguous() for k, v in state_dict.items()}
         self._wcache: Dict[tuple, tuple] = {}
         self.profile: Optional[list] = None  # when a list: (op, start_event, end_event) per launched op
+        self.use_graph = os.environ.get("DEMFI_GRAPH", "0") == "1"
+        self._graphs: Dict[tuple, tuple] = {}
+        self._gx: Optional[torch.Tensor] = None
+        self._tb: Optional[torch.Tensor] = None
         self._build()
 
     # ------------------------------------------------------------------ memory
@@ -554,28 +558,51 @@ class Engine:
 
     @torch.no_grad()
     def forward(self, x: torch.Tensor, t_value: torch.Tensor, num_update: int, reuse_prefix: bool = False,
-                final_only: bool = False):
+                final_only: bool = False, graph: Optional[bool] = None):
         """One `DeMFInet.forward` (eval 5-tuple).  reuse_prefix=True skips the t-independent FF_RDB +
         FAC_FB stage and reuses what the previous call on the same frames left in HBM
         (SURVEY.md 3.2); final_only=True decodes D2 only for the last boosting iteration (the earlier
-        entries of Sharps_final are then None)."""
+        entries of Sharps_final are then None).  graph=True (or DEMFI_GRAPH=1) replays the ~240 launches of the call as one
+        CUDA graph: the launch-bound regime of small frames (256x256: the host cannot issue launches as fast as the GPU retires
+        them); at 1280x720 the GPU is the bottleneck and eager launches cost nothing."""
         B, H, W = self.B, self.H, self.W
         if self.dry:
             raise RuntimeError("a dry (host-only) engine cannot run: demfi_b200 has no CPU path")
         assert tuple(x.shape) == (B, 3, 4, H, W), (tuple(x.shape), (B, 3, 4, H, W))
         x = x.to(self.dev, torch.float32).contiguous()
         self.t_dev.copy_(t_value.reshape(B).to(torch.float32), non_blocking=True)
+        if graph is None:
+            graph = self.use_graph
+        if not graph or self.profile is not None:
+            return self._forward_body(x, num_update, reuse_prefix, final_only)
+        key = (int(num_update), bool(reuse_prefix), bool(final_only))
+        if self._gx is None:
+            self._gx = torch.empty_like(x)
+        self._gx.copy_(x)
+        if key not in self._graphs:
+            self._forward_body(self._gx, num_update, reuse_prefix, final_only)  # warm: lazy op lists, function attributes
+            torch.cuda.synchronize(self.dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = self._forward_body(self._gx, num_update, reuse_prefix, final_only)
+            self._graphs[key] = (g, out)
+        g, out = self._graphs[key]
+        g.replay()
+        clone = lambda o: (None if o is None else o.clone() if isinstance(o, torch.Tensor) else type(o)(clone(e) for e in o))
+        return clone(out)  # the caller owns what it gets (the reference appends results to lists across calls)
+
+    def _forward_body(self, x: torch.Tensor, num_update: int, reuse_prefix: bool, final_only: bool):
+        B, H, W = self.B, self.H, self.W
         st = torch.cuda.current_stream(self.dev).cuda_stream
         v = self.views
         lib = self.lib
-        two_blurry = torch.empty((B, 3, H, W), dtype=torch.float32, device=self.dev)
+        if self._tb is None:  # mean(B0, B1) of the current frames: a persistent buffer, so that prefix reuse (and graphs) see it
+            self._tb = torch.empty((B, 3, H, W), dtype=torch.float32, device=self.dev)
         if not reuse_prefix:
             A.check(lib.demfi_pack_input(x.data_ptr(), B, H, W, v["S2D"].ptr, v["REF"].ch(9, 12).ptr, 32,
-                                         v["A3"].ch(23, 12).ptr, 36, two_blurry.data_ptr(), st), "pack_input")
+                                         v["A3"].ch(23, 12).ptr, 36, self._tb.data_ptr(), st), "pack_input")
             self._run(self.ops_prefix_ff, st)
-            self._two_blurry = two_blurry
-        else:
-            two_blurry = self._two_blurry.clone()
+        two_blurry = self._tb.clone()
         self._run(self.ops_stage1, st)
         SP, A3, DL0 = v["SP"], v["A3"], v["DL0"]
         sharps_dec1 = [self._export(SP.frames(f * B, B), 3, st) for f in range(3)]

@@ -205,3 +205,31 @@ def test_full_size_forward_is_bitwise_repeatable_and_batch_invariant(state_dict)
     a = eng.views["SE"].to_nchw().clone()
     eng.forward(x, t, 1)
     assert torch.equal(a, eng.views["SE"].to_nchw()), "full-size conv stack is not bitwise repeatable"
+
+
+def test_cuda_graph_replay_matches_eager_bitwise(state_dict):
+    """graph=True replays the whole call (~240 launches) as one CUDA graph: same kernels, same order -> same bits up to the
+    atomics of the splat; meant for the launch-bound regime of small frames"""
+    import time
+    from demfi_b200.engine import Engine
+    h, w = 128, 160
+    eng = Engine(state_dict, 1, h, w, DEV)
+    xs = [synth.make_frames(h, w, seed=s).to(DEV) for s in (31, 32)]
+    ts = [torch.tensor([[tv]], device=DEV) for tv in (0.25, 0.75)]
+    for x in xs:
+        eager = [eng.forward(x, ts[0], 2), eng.forward(x, ts[1], 2, reuse_prefix=True)]
+        graph = [eng.forward(x, ts[0], 2, graph=True), eng.forward(x, ts[1], 2, reuse_prefix=True, graph=True)]
+        for e, g in zip(eager, graph):
+            fe, fg = O.flatten_outputs(e), O.flatten_outputs(g)
+            assert fe.keys() == fg.keys()
+            worst = max(float((fe[k] - fg[k]).abs().max()) for k in fe)
+            assert worst <= 2e-4, worst  # the splat's fp32 atomics land in a different order (as between two eager runs)
+            assert torch.equal(fe["two_blurry"], fg["two_blurry"])
+    def run(graph, n=20):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(n):
+            eng.forward(xs[i % 2], ts[0], 2, graph=graph)
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / n * 1e3
+    print(f"{h}x{w} N=2: eager {run(False):.2f} ms, CUDA graph {run(True):.2f} ms per forward")
