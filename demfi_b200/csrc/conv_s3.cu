@@ -46,7 +46,7 @@ constexpr int S3_CV_WARPS = 6, S3_EPI_WARPS = 8;
 constexpr int S3_CV_THREADS = S3_CV_WARPS * 32;
 constexpr int S3_EPI_THREADS = S3_EPI_WARPS * 32;
 constexpr int S3_THREADS = (S3_CV_WARPS + S3_EPI_WARPS + 2) * 32;  // 512: 0-5 convert, 6-13 epilogue, 14 TMA, 15 MMA
-constexpr int S3_MAX_NA = 3;   // halo-tile buffers
+constexpr int S3_MAX_NA = 6;   // halo-tile buffers (3 in general; up to 6 for 1x1 / few-tap kernels, which are HBM-latency bound)
 constexpr int S3_MAX_NS = 8;   // weight ring
 constexpr int S3_BOX_BYTES = S3_BM * 128;  // one 32-channel staging box
 constexpr int S3_NBARS = 3 * S3_MAX_NA + 4 + 2 + 2 * S3_MAX_NS;
@@ -908,6 +908,15 @@ bool s3_supports(const demfi_conv_t& c) {
   return 2 * a_bytes + 4 * b_bytes + stg + 2048 <= S3_SMEM_MAX;
 }
 
+// Halo-tile buffers wanted.  A 1x1 kernel consumes a chunk in ~400 cycles, so the loads in flight -- not the math -- set its
+// pace when the source streams from HBM: measured (tools/layer_table.py) GFF.0 (36 chunks per tile, 1.08 GB) 0.32 -> 0.28 ms and
+// the FGAC 1x1s (fp32 sources) 0.31 -> 0.28 ms with 6 buffers; no gain on the LFFs (7 chunks, L2-warm S16 trunk) or the
+// 1x5 / 5x1 GRU convolutions, which keep 3 (and their shared memory for the weight ring).
+static int s3_want_buffers(int taps, int chunks_per_tile) {
+  if (taps == 1 && (chunks_per_tile >= 16 || chunks_per_tile <= 2)) return S3_MAX_NA;
+  return 3;
+}
+
 static int s3_encode(EncodeTiledFn enc, CUtensorMap* map, const float* ptr, int C_, int ld, int W, int H, int N, int bw, int bh,
                      const char* what) {
   cuuint64_t dims[4] = {(cuuint64_t)C_, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
@@ -1005,6 +1014,8 @@ int launch_conv_s3(const demfi_conv_t& c, cudaStream_t st) {
     P.ns = 0;
     P.gtaps = P.stages_per_tile;
     P.na = (3 * P.a_bytes + bank + fixed <= S3_SMEM_MAX) ? 3 : 2;
+    const int want = s3_want_buffers(P.taps, chunks);
+    while (P.na < want && (P.na + 1) * P.a_bytes + bank + fixed <= S3_SMEM_MAX) ++P.na;
   } else {
     // ring of `ns` slots, each a group of `gtaps` consecutive stages (target <= 24 KB per slot, >= 3 slots)
     P.na = 3;
@@ -1026,6 +1037,8 @@ int launch_conv_s3(const demfi_conv_t& c, cudaStream_t st) {
       else break;
     }
     DEMFI_REQUIRE(fits(P.na, ns, g), "conv_s3: shared-memory plan does not fit");
+    const int want = s3_want_buffers(P.taps, chunks);
+    while (P.na < want && fits(P.na + 1, ns, g)) ++P.na;
     P.ns = ns;
     P.gtaps = g;
   }
