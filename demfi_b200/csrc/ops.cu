@@ -301,10 +301,11 @@ __device__ __forceinline__ void splat_one(float* acc, int n, int H, int W, int r
       const float wgt = expf(-((dy - cy) * (dy - cy) + (dx - cx) * (dx - cx)));
       const int tr = r + iy + oy, tc = c + ix + ox;
       if (tr >= 0 && tr < H && tc >= 0 && tc < W) {
+        // one 128-bit vector reduction per target (sm_90+) instead of three scalar ones: the splat is bound by L2 atomic
+        // throughput (ncu: 105 us for 22.6 M scalar reductions, DRAM 7 % busy)
         float* d = acc + (((size_t)n * H + tr) * W + tc) * 8 + slot;
-        atomicAdd(d + 0, vx * wgt);
-        atomicAdd(d + 1, vy * wgt);
-        atomicAdd(d + 2, wgt);
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(vx * wgt), "f"(vy * wgt), "f"(wgt), "f"(0.0f)
+                     : "memory");
       }
     }
 }
