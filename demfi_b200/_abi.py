@@ -57,6 +57,7 @@ SYMBOLS = {
     "demfi_pack_weights": (i32, [i32, vp, i32, i32, i32, i32, C.POINTER(i32), C.POINTER(i32), i32,
                                  C.POINTER(i32), i32, vp]),
     "demfi_conv2d": (i32, [C.POINTER(Conv), vp]),
+    "demfi_conv_describe": (i32, [C.POINTER(Conv), C.POINTER(i32)]),
     "demfi_pack_input": (i32, [vp, i32, i32, i32, vp, vp, i32, vp, i32, vp, vp]),
     "demfi_cfr_splat": (i32, [vp, i32, vp, i32, i32, i32, vp, vp]),
     "demfi_cfr_finalize": (i32, [vp, vp, i32, i32, i32, vp, i32, vp]),

@@ -158,6 +158,20 @@ int demfi_tc_debug_read(int64_t* host, int32_t ctas) {
   return tc_debug_read(reinterpret_cast<long long*>(host), ctas);
 }
 
+int demfi_conv_describe(const demfi_conv_t* c, int32_t* info) {
+  DEMFI_REQUIRE(c != nullptr && info != nullptr, "conv_describe: null argument");
+  for (int i = 0; i < 16; ++i) info[i] = 0;
+  if (c->kind == DEMFI_CONV_FFMA) return 0;
+  if (c->kind == DEMFI_CONV_TC) { info[0] = 1; return 0; }
+  DEMFI_REQUIRE(c->kind == DEMFI_CONV_TC16, "conv_describe: unknown kind %d", c->kind);
+  if (g_opt_gen.load() == 3 && s3_supports(*c)) {
+    info[0] = 3;
+    return s3_describe(*c, info);
+  }
+  info[0] = 2;
+  return 0;
+}
+
 int demfi_conv2d(const demfi_conv_t* c, void* stream) {
   if (check_device()) return 3;
   DEMFI_REQUIRE(c != nullptr, "conv2d: null descriptor");

@@ -930,19 +930,16 @@ static int s3_encode(EncodeTiledFn enc, CUtensorMap* map, const float* ptr, int 
   return 0;
 }
 
-int launch_conv_s3(const demfi_conv_t& c, cudaStream_t st) {
+// Everything of a launch that is pure host arithmetic (tiling, N blocking, epilogue plan, shared-memory plan, accumulation
+// segments): no CUDA call, so that demfi_conv_describe() can report it on a machine without a GPU.  Returns the dynamic
+// shared-memory size through *smem_out.
+static int s3_plan(const demfi_conv_t& c, S3Params& P, S3EpiPlan& E, int* smem_out) {
   DEMFI_REQUIRE(s3_supports(c), "conv_s3: unsupported convolution (stride %d, cout_pad %d, %dx%d)", c.stride, c.cout_pad, c.KH, c.KW);
   DEMFI_REQUIRE(c.Hi + 2 * c.pad_h - c.KH + 1 == c.H && c.Wi + 2 * c.pad_w - c.KW + 1 == c.W, "conv_s3: inconsistent sizes");
-  EncodeTiledFn enc = s3_encode_fn();
-  DEMFI_REQUIRE(enc != nullptr, "conv_s3: cuTensorMapEncodeTiled not available from the driver");
-  static thread_local S3Params P;  // CUtensorMap needs 64-byte alignment; thread_local storage gives it
-  memset(&P, 0, sizeof(P));
   P.c = c;
   P.hw = S3_TW + c.KW - 1;
   P.hh = S3_TH + c.KH - 1;
   P.halo_px = P.hw * P.hh;
-  for (int s = 0; s < c.nsrc; ++s)
-    if (s3_encode(enc, &P.tmap[s], c.src[s].ptr, c.src[s].C, c.src[s].ld, c.Wi, c.Hi, c.N, P.hw, P.hh, "a source")) return 1;
   P.tiles_x = (c.W + S3_TW - 1) / S3_TW;
   P.tiles_y = (c.H + S3_TH - 1) / S3_TH;
   const long long nt = (long long)P.tiles_x * P.tiles_y * c.N;
@@ -959,7 +956,6 @@ int launch_conv_s3(const demfi_conv_t& c, cudaStream_t st) {
   P.stages_per_tile = chunks * P.taps;
 
   // epilogue mode
-  S3EpiPlan E;
   P.tma_epi = (s3_plan_epilogue(c, P.nb_max, P.n_blocks, E) && !(get_option("tc_diag") & 2)) ? 1 : 0;
   for (int sg = 0; sg < c.nseg; ++sg)
     DEMFI_REQUIRE(c.seg[sg].fmt == 0 || P.tma_epi, "conv_s3: segment %d asks for the S16 format, which needs the TMA epilogue", sg);
@@ -973,36 +969,13 @@ int launch_conv_s3(const demfi_conv_t& c, cudaStream_t st) {
       P.b_on[nb] = E.b_on[nb];
       P.b_nres[nb] = E.b_nres[nb];
       P.b_roff[nb] = E.b_mixed[nb] ? box_bytes_all : 0;
-      if (E.b_seg[nb] < 0) continue;
-      const demfi_seg_t& g = c.seg[E.b_seg[nb]];
-      const int n0 = nb * P.nb_max;
-      P.r_c0[nb] = n0 - g.ch0;
-      if (E.b_nres[nb] >= 1)
-        if (s3_encode(enc, &P.rmap[nb], g.res, g.nch, g.res_ld, c.W, c.H, c.N, S3_TW, S3_TH, "an epilogue operand")) return 1;
-      if (E.b_nres[nb] >= 2)
-        if (s3_encode(enc, &P.r2map[nb], g.res2, g.nch, g.res2_ld, c.W, c.H, c.N, S3_TW, S3_TH, "the second epilogue operand")) return 1;
+      if (E.b_seg[nb] >= 0) P.r_c0[nb] = nb * P.nb_max - c.seg[E.b_seg[nb]].ch0;
     }
     for (int j = 0; j < E.n_out; ++j) {
       const demfi_seg_t& g = c.seg[E.o_seg[j]];
       const int n0 = E.o_blk[j] * P.nb_max;
-      if (g.store == DEMFI_STORE_PIXEL_SHUFFLE2) {
-        // nn.PixelShuffle(2): accumulator channel q*cq + ch of pixel (y, x) -> pixel (2y + q/2, 2x + q%2), channel ch: the
-        // quadrant is a tensor of its own with doubled pixel strides
-        const int cq = g.nch / 4, q = (n0 - g.ch0) / cq;
-        P.o_c0[j] = n0 - g.ch0 - q * cq;
-        const float* base = g.dst + ((size_t)(q >> 1) * (size_t)(2 * c.W) + (size_t)(q & 1)) * (size_t)g.dst_ld;
-        cuuint64_t dims[4] = {(cuuint64_t)cq, (cuuint64_t)c.W, (cuuint64_t)c.H, (cuuint64_t)c.N};
-        cuuint64_t strides[3] = {(cuuint64_t)g.dst_ld * 8, (cuuint64_t)g.dst_ld * 16 * c.W, (cuuint64_t)g.dst_ld * 16 * c.W * c.H};
-        cuuint32_t box[4] = {S3_KC, S3_TW, S3_TH, 1};
-        cuuint32_t estr[4] = {1, 1, 1, 1};
-        CUresult r = enc(&P.omap[j], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        DEMFI_REQUIRE(r == CUDA_SUCCESS, "conv_s3: cuTensorMapEncodeTiled failed for a pixel-shuffle destination (CUresult %d)", (int)r);
-      } else {
-        P.o_c0[j] = n0 - g.ch0;
-        if (s3_encode(enc, &P.omap[j], g.dst, g.nch, g.dst_ld, c.W, c.H, c.N, S3_TW, S3_TH, "a destination")) return 1;
-      }
+      P.o_c0[j] = n0 - g.ch0;
+      if (g.store == DEMFI_STORE_PIXEL_SHUFFLE2) P.o_c0[j] -= ((n0 - g.ch0) / (g.nch / 4)) * (g.nch / 4);  // channel inside the quadrant
     }
   }
 
@@ -1049,6 +1022,7 @@ int launch_conv_s3(const demfi_conv_t& c, cudaStream_t st) {
   P.bias_off = (P.bar_off + 8 * S3_NBARS + 16 + 15) & ~15;
   const int smem = P.bias_off + 1024 + 1024;
   DEMFI_REQUIRE(smem <= S3_SMEM_MAX + 1024, "conv_s3: shared-memory plan (%d bytes) does not fit", smem);
+  *smem_out = smem;
 
   P.all_full_chunks = 1;
   for (int s_ = 0; s_ < c.nsrc; ++s_)
@@ -1061,6 +1035,68 @@ int launch_conv_s3(const demfi_conv_t& c, cudaStream_t st) {
   }
   P.comp = (float)get_option("tc_comp_milli") * 1e-3f * 5.9604645e-8f;
   P.diag = get_option("tc_diag") & (1 | 16 | 32 | 64 | 128);
+  return 0;
+}
+
+// host-only description of what a DEMFI_CONV_TC16 launch on conv_s3 would do (demfi_conv_describe)
+int s3_describe(const demfi_conv_t& c, int32_t* info) {
+  static thread_local S3Params P;
+  memset(&P, 0, sizeof(P));
+  S3EpiPlan E;
+  int smem = 0;
+  if (s3_plan(c, P, E, &smem)) return 1;
+  info[1] = P.tma_epi;
+  info[2] = P.resident;
+  info[3] = P.na;
+  info[4] = P.ns;
+  info[5] = P.gtaps;
+  info[6] = P.n_blocks;
+  info[7] = smem;
+  info[8] = P.flush;
+  info[9] = P.stages_per_tile;
+  return 0;
+}
+
+int launch_conv_s3(const demfi_conv_t& c, cudaStream_t st) {
+  EncodeTiledFn enc = s3_encode_fn();
+  DEMFI_REQUIRE(enc != nullptr, "conv_s3: cuTensorMapEncodeTiled not available from the driver");
+  static thread_local S3Params P;  // CUtensorMap needs 64-byte alignment; thread_local storage gives it
+  memset(&P, 0, sizeof(P));
+  S3EpiPlan E;
+  int smem = 0;
+  if (s3_plan(c, P, E, &smem)) return 1;
+  for (int s = 0; s < c.nsrc; ++s)
+    if (s3_encode(enc, &P.tmap[s], c.src[s].ptr, c.src[s].C, c.src[s].ld, c.Wi, c.Hi, c.N, P.hw, P.hh, "a source")) return 1;
+  if (P.tma_epi) {
+    for (int nb = 0; nb < P.n_blocks; ++nb) {
+      if (E.b_seg[nb] < 0) continue;
+      const demfi_seg_t& g = c.seg[E.b_seg[nb]];
+      if (E.b_nres[nb] >= 1)
+        if (s3_encode(enc, &P.rmap[nb], g.res, g.nch, g.res_ld, c.W, c.H, c.N, S3_TW, S3_TH, "an epilogue operand")) return 1;
+      if (E.b_nres[nb] >= 2)
+        if (s3_encode(enc, &P.r2map[nb], g.res2, g.nch, g.res2_ld, c.W, c.H, c.N, S3_TW, S3_TH, "the second epilogue operand")) return 1;
+    }
+    for (int j = 0; j < E.n_out; ++j) {
+      const demfi_seg_t& g = c.seg[E.o_seg[j]];
+      const int n0 = E.o_blk[j] * P.nb_max;
+      if (g.store == DEMFI_STORE_PIXEL_SHUFFLE2) {
+        // nn.PixelShuffle(2): accumulator channel q*cq + ch of pixel (y, x) -> pixel (2y + q/2, 2x + q%2), channel ch: the
+        // quadrant is a tensor of its own with doubled pixel strides
+        const int cq = g.nch / 4, q = (n0 - g.ch0) / cq;
+        const float* base = g.dst + ((size_t)(q >> 1) * (size_t)(2 * c.W) + (size_t)(q & 1)) * (size_t)g.dst_ld;
+        cuuint64_t dims[4] = {(cuuint64_t)cq, (cuuint64_t)c.W, (cuuint64_t)c.H, (cuuint64_t)c.N};
+        cuuint64_t strides[3] = {(cuuint64_t)g.dst_ld * 8, (cuuint64_t)g.dst_ld * 16 * c.W, (cuuint64_t)g.dst_ld * 16 * c.W * c.H};
+        cuuint32_t box[4] = {S3_KC, S3_TW, S3_TH, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&P.omap[j], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        DEMFI_REQUIRE(r == CUDA_SUCCESS, "conv_s3: cuTensorMapEncodeTiled failed for a pixel-shuffle destination (CUresult %d)", (int)r);
+      } else {
+        if (s3_encode(enc, &P.omap[j], g.dst, g.nch, g.dst_ld, c.W, c.H, c.N, S3_TW, S3_TH, "a destination")) return 1;
+      }
+    }
+  }
   if (P.diag & 128) {
     long long* buf = tc_debug_buffer(st);
     DEMFI_REQUIRE(buf != nullptr, "conv_s3: cannot allocate the role-timer buffer");

@@ -124,6 +124,13 @@ int demfi_pack_weights(int32_t kind, const float* w_oihw_host, int32_t Co, int32
 /* ---- convolution (DeMFInet.py: every nn.Conv call; see demfi_conv_t) -------------------- */
 int demfi_conv2d(const demfi_conv_t* conv, void* stream);
 
+/* Host-only (no GPU needed): what demfi_conv2d would do with this descriptor.  info[0] = kernel (0 conv_ffma, 1 conv_tc,
+ * 2 conv_h3, 3 conv_s3); for conv_s3 also info[1] = TMA-store epilogue (else the generic per-thread one), [2] = weights
+ * resident in shared memory, [3] = halo-tile buffers, [4] = weight-ring slots, [5] = (chunk, tap) stages per slot,
+ * [6] = N blocks, [7] = dynamic shared memory in bytes, [8] = stages per accumulation segment, [9] = stages per tile.
+ * Lets a plan be checked for silent fall-backs to slower paths without launching anything. */
+int demfi_conv_describe(const demfi_conv_t* conv, int32_t info[16]);
+
 /* ---- memory-bound operators ------------------------------------------------------------ */
 /* Input unpack.  x is the caller's [B,3,4,H,W] NCHW-T tensor (DeMFInet.py:51-55).  Writes
  *  - s2d:   [B,H/2,W/2,48] pixel_reshuffle(cat(B0,B1,B-1,B2), 2)   (DeMFInet.py:234-235,290-316)

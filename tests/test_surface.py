@@ -95,6 +95,36 @@ def test_storage_formats_are_consistent_along_the_plan(state_dict):
     f.check_formats(2)
 
 
+def test_no_convolution_of_the_plan_falls_back_to_a_slower_path(state_dict):
+    """demfi_conv_describe (host only): at the north-star size every stride-1 convolution runs conv_s3 with the TMA-store
+    epilogue, the 64 -> 64 3x3 ResBlock convolutions keep their weights resident in shared memory, every plan fits 227 KB"""
+    import ctypes as C
+    from demfi_b200 import _abi as A
+    e = Engine(state_dict, 1, 736, 1280, torch.device("cpu"), dry=True)
+    lib = A.lib()
+    rows = []
+    for ops in (e.ops_prefix_ff, e.ops_stage1, e._iter_ops(0, True)):
+        for op in ops:
+            if op[0] != "conv":
+                continue
+            info = (A.i32 * 16)()
+            A.check(lib.demfi_conv_describe(C.byref(op[1]), info), "describe")
+            rows.append((op[2], op[1].stride, list(info)))
+    assert len(rows) == 104 + 23
+    for label, stride, info in rows:
+        if stride == 2:
+            assert info[0] == 2, label                      # the three UNet encoders: conv_h3
+        else:
+            assert info[0] == 3 and info[1] == 1, (label, info[:3])   # conv_s3 with the TMA epilogue
+            assert 0 < info[7] <= 227 * 1024 + 1024 and info[3] >= 2, (label, info)
+    resident = [l for l, s_, i in rows if i[0] == 3 and i[2] == 1]
+    for name in ("Decoder_res.0.conv1", "Decoder_res_2.4.conv2", "FAC_FB_Module.feature_extraction.2.conv1", "Dec_last1"):
+        assert name in resident, name
+    assert len(resident) >= 60, len(resident)
+    deep = {l: i[3] for l, s_, i in rows if i[0] == 3 and i[3] > 3}  # the HBM-streaming 1x1s get more halo-tile buffers
+    assert deep.get("FF_RDB_Module.GFF.0", 0) >= 4 and deep.get("FAC_FB_Module.shared_FGAC.conv_ref_k", 0) == 6, deep
+
+
 def test_shape_constraints():
     with pytest.raises(ValueError):
         Engine(synth.make_state_dict(0), 1, 36, 64, torch.device("cpu"), dry=True)
