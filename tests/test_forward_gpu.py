@@ -144,6 +144,14 @@ def test_return_structure(net):
         assert r[4].shape == (1, 3, 32, 32)
         r7 = net(x, t, 2, is_training=True)
         assert len(r7) == 7 and len(r7[5]) == 4 and r7[5][0].shape == (1, 1, 32, 32) and len(r7[6][0]) == 2
+        # the two extra items of the training tuple (DeMFInet.py:170-172) against the oracle: FGAC difference maps
+        # (min-max normalised, :456-462) and the refined flows of Stage I
+        want = O.forward(net.state_dict_cpu() if hasattr(net, "state_dict_cpu") else {k: v.cpu() for k, v in net.state_dict().items()},
+                         x.cpu(), t.cpu(), 2, is_training=True)
+        for got_m, want_m in zip(r7[5], want[5]):
+            assert float((got_m.cpu() - want_m).abs().max()) < 2e-3
+        for got_f, want_f in zip(r7[6][0], want[6][0]):
+            assert float((got_f.cpu() - want_f).abs().max()) < TOL
     with pytest.raises(NotImplementedError):
         net(x, t, 1, is_training=True)
     with pytest.raises(ValueError):
