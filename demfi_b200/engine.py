@@ -48,7 +48,7 @@ class View:
         return self.t.data_ptr() + 4 * (self.n0 * self.H * self.W * self.ld + self.c0)
 
     def ch(self, c0, C_):
-        assert c0 + C_ <= self.C + (self.ld - self.c0 - self.C) + 0 or True
+        assert 0 <= c0 and self.c0 + c0 + C_ <= self.ld, ("channel slice outside the buffer row", self.c0, c0, C_, self.ld)
         return View(self.t, self.N, self.H, self.W, self.ld, self.c0 + c0, C_, self.n0, self.fmt)
 
     def frames(self, n0, N):
@@ -514,42 +514,41 @@ class Engine:
 
     def _run_one(self, op, st):
         lib, B, H, W = self.lib, self.B, self.H, self.W
-        if True:
-            k = op[0]
-            if k == "conv":
-                A.check(lib.demfi_conv2d(C.byref(op[1]), st), f"conv2d[{op[2]}]")
-            elif k == "copy":
-                s, d, act = op[1], op[2], op[3]
-                A.check(lib.demfi_copy_channels(s.ptr, s.ld, d.ptr, d.ld, s.C, s.npix(), act, st), "copy_channels")
-            elif k == "gather":
-                dst, parts = op[1], op[2]
-                arr = (A.Part * len(parts))()
-                for i, (sv, c0) in enumerate(parts):
-                    arr[i].src, arr[i].src_ld, arr[i].nch, arr[i].dst_c0 = sv.ptr, sv.ld, sv.C, dst.c0 + c0
-                A.check(lib.demfi_gather_channels(arr, len(parts), dst.t.data_ptr() + 4 * dst.n0 * dst.H * dst.W * dst.ld, dst.ld,
-                                                  dst.npix(), st), "gather_channels")
-            elif k == "zero":
-                op[1].t.zero_()
-            elif k == "upsample":
-                sv, dv = op[1], op[2]
-                A.check(lib.demfi_upsample2x(sv.ptr, sv.ld, sv.N, sv.H, sv.W, sv.C, dv.ptr, dv.ld, st), "upsample2x")
-            elif k == "cfr_splat":
-                A.check(lib.demfi_cfr_splat(op[1].ptr, op[1].ld, self.t_dev.data_ptr(), B, H, W, op[2].ptr, st), "cfr_splat")
-            elif k == "cfr_finalize":
-                A.check(lib.demfi_cfr_finalize(op[1].ptr, self.t_dev.data_ptr(), B, H, W, op[2].ptr, op[2].ld, st), "cfr_finalize")
-            elif k == "bwarp_blend":
-                a, b, fl, oc, out, oo = op[1:]
-                A.check(lib.demfi_bwarp_blend(a.ptr, a.ld, b.ptr, b.ld, fl.ptr, fl.ld, oc.ptr, oc.ld, self.t_dev.data_ptr(),
-                                              B, H, W, a.C, out.ptr, out.ld, oo.ptr if oo is not None else None,
-                                              oo.ld if oo is not None else 0, st), "bwarp_blend")
-            elif k == "fgac_sample":
-                r, fl, out = op[1:]
-                A.check(lib.demfi_fgac_sample(r.ptr, r.ld, fl.ptr, fl.ld, r.N, H, W, r.C, out.ptr, out.ld, st), "fgac_sample")
-            elif k == "fgac_blend":
-                wv, s, e, out = op[1:]
-                A.check(lib.demfi_fgac_blend(wv.ptr, wv.ld, s.ptr, s.ld, e.ptr, e.ld, s.npix(), s.C, out.ptr, out.ld, st), "fgac_blend")
-            else:
-                raise AssertionError(k)
+        k = op[0]
+        if k == "conv":
+            A.check(lib.demfi_conv2d(C.byref(op[1]), st), f"conv2d[{op[2]}]")
+        elif k == "copy":
+            s, d, act = op[1], op[2], op[3]
+            A.check(lib.demfi_copy_channels(s.ptr, s.ld, d.ptr, d.ld, s.C, s.npix(), act, st), "copy_channels")
+        elif k == "gather":
+            dst, parts = op[1], op[2]
+            arr = (A.Part * len(parts))()
+            for i, (sv, c0) in enumerate(parts):
+                arr[i].src, arr[i].src_ld, arr[i].nch, arr[i].dst_c0 = sv.ptr, sv.ld, sv.C, dst.c0 + c0
+            A.check(lib.demfi_gather_channels(arr, len(parts), dst.t.data_ptr() + 4 * dst.n0 * dst.H * dst.W * dst.ld, dst.ld,
+                                              dst.npix(), st), "gather_channels")
+        elif k == "zero":
+            op[1].t.zero_()
+        elif k == "upsample":
+            sv, dv = op[1], op[2]
+            A.check(lib.demfi_upsample2x(sv.ptr, sv.ld, sv.N, sv.H, sv.W, sv.C, dv.ptr, dv.ld, st), "upsample2x")
+        elif k == "cfr_splat":
+            A.check(lib.demfi_cfr_splat(op[1].ptr, op[1].ld, self.t_dev.data_ptr(), B, H, W, op[2].ptr, st), "cfr_splat")
+        elif k == "cfr_finalize":
+            A.check(lib.demfi_cfr_finalize(op[1].ptr, self.t_dev.data_ptr(), B, H, W, op[2].ptr, op[2].ld, st), "cfr_finalize")
+        elif k == "bwarp_blend":
+            a, b, fl, oc, out, oo = op[1:]
+            A.check(lib.demfi_bwarp_blend(a.ptr, a.ld, b.ptr, b.ld, fl.ptr, fl.ld, oc.ptr, oc.ld, self.t_dev.data_ptr(),
+                                          B, H, W, a.C, out.ptr, out.ld, oo.ptr if oo is not None else None,
+                                          oo.ld if oo is not None else 0, st), "bwarp_blend")
+        elif k == "fgac_sample":
+            r, fl, out = op[1:]
+            A.check(lib.demfi_fgac_sample(r.ptr, r.ld, fl.ptr, fl.ld, r.N, H, W, r.C, out.ptr, out.ld, st), "fgac_sample")
+        elif k == "fgac_blend":
+            wv, s, e, out = op[1:]
+            A.check(lib.demfi_fgac_blend(wv.ptr, wv.ld, s.ptr, s.ld, e.ptr, e.ld, s.npix(), s.C, out.ptr, out.ld, st), "fgac_blend")
+        else:
+            raise AssertionError(k)
 
     def _export(self, view: View, C_, st, act=A.ACT_NONE) -> torch.Tensor:
         out = torch.empty((view.N, C_, view.H, view.W), dtype=torch.float32, device=self.dev)
