@@ -98,6 +98,43 @@ def test_pack_weights_tc_layout_hi_lo_swizzle():
                     assert abs(float(hi) + float(p[ci, tap, 1, n, col]) - float(v)) == 0.0  # exact split
 
 
+def test_pack_weights_tc16_layout_fp16_hi_lo_swizzle64():
+    """the layout conv_h3 / conv_s3 stream: per (N block, 32-channel chunk, tap) a [2N x 32] fp16 K-major tile, 64-byte swizzle
+    (16-byte group g of row r stored at g ^ ((r >> 1) & 3)); rows 0..N-1 = fp16(w), rows N..2N-1 = fp16((w - hi) * 2048)"""
+    rng = np.random.default_rng(2)
+    w = (rng.standard_normal((70, 44, 3, 1)) * 0.3).astype(np.float32)
+    src_C = [36, 8]                      # chunks: (src 0: 0..31), (src 0: 32..35 + pad), (src 1: 0..7 + pad)
+    in_map = list(range(36)) + list(range(36, 44))
+    cout_pad = 112                       # > 96 -> N blocks of 64 and 48
+    out_map = list(range(70)) + [-1] * 42
+    p = _pack(A.CONV_TC16, w, src_C, in_map, out_map, cout_pad)
+    halves = p.view(np.float16)
+    chunks = [(0, 0), (0, 32), (1, 0)]
+    kbase = [0, 36]
+    taps = 3
+    base = 0
+    for nb, N in ((0, 64), (1, 48)):
+        for ci, (s_, c0) in enumerate(chunks):
+            for tap in range(taps):
+                tile = halves[base + (ci * taps + tap) * 2 * N * 32: base + (ci * taps + tap + 1) * 2 * N * 32].reshape(2 * N, 32)
+                for n in range(N):
+                    co = out_map[nb * 64 + n]
+                    for k in range(32):
+                        c = c0 + k
+                        v = np.float32(0.0)
+                        if c < src_C[s_] and co >= 0:
+                            v = w[co, in_map[kbase[s_] + c], tap, 0]
+                        hi = np.float16(v)
+                        lo = np.float16((np.float32(v) - np.float32(hi)) * np.float32(2048.0))
+                        for row, want in ((n, hi), (N + n, lo)):
+                            col = (((k >> 3) ^ ((row >> 1) & 3)) << 3) + (k & 7)
+                            assert tile[row, col] == want, (nb, ci, tap, n, k)
+                        # the pair reconstructs the weight to ~2^-22 relative
+                        assert abs(float(hi) + float(lo) / 2048.0 - float(v)) <= 2.0 ** -21 * max(abs(float(v)), 2.0 ** -14)
+        base += len(chunks) * taps * 2 * N * 32
+    assert base == halves.size
+
+
 def test_pack_weights_rejects_bad_maps():
     w = np.zeros((4, 4, 1, 1), dtype=np.float32)
     with pytest.raises(A.DemfiError):
