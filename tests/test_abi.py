@@ -147,3 +147,40 @@ def test_no_gpu_means_loud_failure():
         pytest.skip("GPU present")
     rc = A.lib().demfi_copy_channels(None, 4, None, 4, 1, 1, 0, None)
     assert rc != 0 and b"no CPU path" in A.lib().demfi_last_error() or rc != 0
+
+
+def _describe(cout_pad, segs, k=(3, 3), srcC=(64,), stride=1, kind=A.CONV_TC16, hw=(64, 96)):
+    d = A.Conv()
+    d.N, d.H, d.W = 1, hw[0], hw[1]
+    d.Hi, d.Wi = hw[0] * stride, hw[1] * stride
+    d.KH, d.KW, d.stride = k[0], k[1], stride
+    d.pad_h, d.pad_w = (k[0] // 2, k[1] // 2) if stride == 1 else (1, 1)
+    d.nsrc, d.nseg, d.cout_pad, d.kind = len(srcC), len(segs), cout_pad, kind
+    for i, c in enumerate(srcC):
+        d.src[i].ptr, d.src[i].C, d.src[i].ld = 0x1000, c, c
+    for i, (ch0, nch, act, res, fmt) in enumerate(segs):
+        sg = d.seg[i]
+        sg.dst, sg.dst_ld, sg.ch0, sg.nch, sg.act, sg.fmt = 0x2000 + 0x100000 * i, 256, ch0, nch, act, fmt
+        if res:
+            sg.res, sg.res_ld = 0x9000000, 256
+    info = (A.i32 * 16)()
+    A.check(A.lib().demfi_conv_describe(C.byref(d), info), "describe")
+    return list(info)
+
+
+def test_conv_describe_reports_kernel_and_epilogue_plan():
+    """host-only planning (no GPU): which kernel, TMA or generic epilogue, resident weights"""
+    plain = _describe(64, [(0, 64, A.ACT_RELU, False, 0)])
+    assert plain[0] == 3 and plain[1] == 1 and plain[2] == 1 and plain[9] == 18 and plain[8] == 9  # 64->64 3x3: resident, 2 segments of 9
+    heads = _describe(144, [(0, 64, A.ACT_TANH, True, 0), (64, 64, A.ACT_TANH, True, 0), (128, 8, A.ACT_NONE, True, 0)])
+    assert heads[0] == 3 and heads[1] == 1 and heads[6] == 3          # three heads = three N blocks, each alike -> TMA epilogue
+    lff = _describe(96, [(0, 96, A.ACT_NONE, True, A.SEG_DST_S16 | A.SEG_RES_S16)] * 2, k=(1, 1), srcC=(224,))
+    assert lff[1] == 1 and lff[6] == 1                                  # one result, two destinations
+    mixed = _describe(64, [(0, 32, A.ACT_RELU, False, 0), (32, 32, A.ACT_TANH, False, 0)])
+    assert mixed[0] == 3 and mixed[1] == 0                              # two different segments inside one N block: generic epilogue
+    big = _describe(64, [(0, 64, A.ACT_TANH, False, 0)], k=(7, 7), srcC=(64, 64, 64))
+    assert big[2] == 0 and big[4] >= 2 and big[5] >= 2                  # 2.4 MB of weights: ring of multi-stage groups
+    enc = _describe(64, [(0, 64, A.ACT_RELU, False, 0)], k=(4, 4), srcC=(204,), stride=2)
+    assert enc[0] == 2                                                  # stride 2 -> conv_h3
+    assert _describe(64, [(0, 64, A.ACT_RELU, False, 0)], kind=A.CONV_FFMA)[0] == 0
+    assert _describe(64, [(0, 64, A.ACT_RELU, False, 0)], kind=A.CONV_TC)[0] == 1
