@@ -69,6 +69,8 @@ SYMBOLS = {
     "demfi_upsample2x": (i32, [vp, i32, i32, i32, i32, i32, vp, i32, vp]),
     "demfi_export_nchw": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, vp]),
     "demfi_import_nchw": (i32, [vp, i32, i32, i32, i32, vp, i32, vp]),
+    "demfi_frame_metrics_workspace": (C.c_int64, [i32, i32, i32, i32]),
+    "demfi_frame_metrics": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, C.c_int64, vp, vp]),
     "demfi_launch_count": (C.c_uint64, []),
     "demfi_set_option": (i32, [C.c_char_p, i32]),
     "demfi_get_option": (i32, [C.c_char_p, C.POINTER(i32)]),

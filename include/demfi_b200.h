@@ -193,6 +193,20 @@ int demfi_export_nchw(const float* src, int32_t src_ld, int32_t B, int32_t H, in
 int demfi_import_nchw(const float* src, int32_t B, int32_t H, int32_t W, int32_t C, float* dst, int32_t dst_ld,
                       void* stream);
 
+/* ---- evaluation metrics (the consumer right after the hot path) ------------------------- */
+/* PSNR / SSIM sums of predicted frames against their targets as the reference's evaluation loop computes them
+ * (main.py:763-771 with utils.py:652-705, 718-721): pred, target are NCHW [B,C,H,W] fp32 in [-1,1] on the device (what
+ * DeMFInet.forward returns / the ground-truth batch).  Both are scaled to 0..255 inside the kernel: the prediction in fp64 and
+ * rounded half-to-even (np.around of the float64 array), the target in fp32 arithmetic and NOT rounded when target_mode = 0
+ * (a ground truth, main.py:765-766) or exactly like the prediction when target_mode = 1 (a second network output, the
+ * "PSNR(ours, reference)" parity figure).  out (device, 2*B doubles): out[2b] = sum of squared errors over the C*H*W elements
+ * of image b, out[2b+1] = sum of the SSIM map over the C*(H-10)*(W-10) window positions; the host divides and takes the log
+ * (demfi_b200/metrics.py).  fp64 arithmetic, fixed summation order (bit-reproducible).  H, W >= 11.  workspace: device memory
+ * of at least demfi_frame_metrics_workspace(B, C, H, W) bytes (returns -1 for an invalid shape). */
+int64_t demfi_frame_metrics_workspace(int32_t B, int32_t C, int32_t H, int32_t W);
+int demfi_frame_metrics(const float* pred, const float* target, int32_t B, int32_t C, int32_t H, int32_t W, int32_t target_mode,
+                        void* workspace, int64_t workspace_bytes, double* out, void* stream);
+
 /* ---- introspection ---------------------------------------------------------------------- */
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 uint64_t demfi_launch_count(void);
