@@ -32,10 +32,11 @@ import torch  # noqa: E402
 
 H0, W0 = 720, 1280      # BASELINE.json config[1]; the caller reflect-pads to 736x1280 (utils.py:1351-1365)
 N_TST, MFI = 3, 8
-# reference arm / cpu_baseline sample: a (H/d x W/d) crop of the padded frame; d = 2 (1/4 of the pixels) for short
-# runs, d = 4 (1/16) when K + W > 12 so that the whole CPU run still ends within a few minutes
+# reference arm / cpu_baseline sample: the whole padded frame when K + W <= 4 (16 s per forward on the B200 box's 16 host
+# cores), else a (H/d x W/d) crop: d = 2 (1/4 of the pixels) up to K + W = 12, d = 4 (1/16) beyond, so that the whole CPU
+# run still ends within a few minutes
 def ref_sample_div(steps, warmup):
-    return 2 if steps + warmup <= 12 else 4
+    return 1 if steps + warmup <= 4 else 2 if steps + warmup <= 12 else 4
 
 
 def env_int(name, default):
@@ -93,8 +94,9 @@ class ClockSampler:
 def cpu_reference_sample(steps: int, warmup: int):
     """The reference's CPU implementation of the path on this box's host cores.  The reference is Python and is
     not present on the GPU box, so this is the oracle PORT (oracle/demfi_oracle.py, pinned to the reference by
-    tests/test_oracle.py) with all host threads.  Each step = one forward on a 1/16-area crop of the padded
-    frame; the conv work is proportional to pixels, so frames/s = 1 / (16 * seconds per crop forward)."""
+    tests/test_oracle.py) with all host threads.  Each step = one forward on the padded frame, or on a 1/4- or 1/16-area
+    crop of it for longer runs (ref_sample_div); the conv work is proportional to pixels, so frames/s = 1 / (area ratio *
+    seconds per crop forward)."""
     from demfi_b200 import synth
     from oracle import demfi_oracle as O
     cores = os.cpu_count() or 1
@@ -113,8 +115,12 @@ def cpu_reference_sample(steps: int, warmup: int):
     dt = (time.perf_counter() - t0) / max(steps, 1)
     area = (hp * wp) / (hs * ws)
     fps = 1.0 / (dt * area)
-    sample = (f"oracle port (torch CPU fp32, {cores} threads), {steps} forward(s) on a {hs}x{ws} crop = 1/{area:.0f} of the "
-              f"{hp}x{wp} padded frame, N_tst={N_TST}; scaled by pixel count ({dt:.2f} s per crop forward)")
+    if div == 1:
+        sample = (f"oracle port (torch CPU fp32, {cores} threads), {steps} forward(s) on the whole {hp}x{wp} padded frame, "
+                  f"N_tst={N_TST} ({dt:.2f} s per forward)")
+    else:
+        sample = (f"oracle port (torch CPU fp32, {cores} threads), {steps} forward(s) on a {hs}x{ws} crop = 1/{area:.0f} of the "
+                  f"{hp}x{wp} padded frame, N_tst={N_TST}; scaled by pixel count ({dt:.2f} s per crop forward)")
     return fps, dt * area * 1000.0, cores, sample
 
 
@@ -126,7 +132,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "interpolated_frames_per_sec", "value": fps, "unit": "frames/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{W0}x{H0} x{MFI} MFI, N_tst={N_TST}, 1 interpolated frame per step (CPU sample, scaled)"},
+            "config": {"workload": f"{W0}x{H0} x{MFI} MFI, N_tst={N_TST}, 1 interpolated frame per step (CPU sample: see cpu_baseline.sample)"},
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)

@@ -185,22 +185,12 @@ class DeMFInet(nn.Module):
         sharps_dec1, sharps_final, flows, occs, two_blurry = res
         if not (is_training or self.args.visualization_flag):
             return sharps_dec1, sharps_final, flows, occs, two_blurry
-        # surface parity for the training / visualisation tuples (not on the inference hot path)
-        v = eng.views
-        diffs = []
-        weights = []
-        for d in range(2):
-            src = v["SE"].frames(d * B, B).ch(0, 64).to_nchw()
-            out = v["AGG1"].ch(64 * d, 64).to_nchw()
-            diff = torch.mean(torch.abs(out - src), 1, keepdim=True).view(B, -1)
-            diff = diff - diff.min(1, keepdim=True)[0]
-            diff = diff / diff.max(1, keepdim=True)[0]
-            diffs.append(diff.view(B, 1, H, W))
-            weights.append(v["WL"].frames(d * B, B).ch(0, 1).to_nchw())
+        # the training / visualisation tuples (DeMFInet.py:167-176): FGAC side outputs, not on the inference hot path
+        diffs, maps = eng.fgac_maps(visualization=bool(self.args.visualization_flag) and not is_training)
         difference_maps = [diffs[0], diffs[1], diffs[0], diffs[1]]
         if is_training:
             return (sharps_dec1, sharps_final, flows, occs, two_blurry, difference_maps,
                     [[flows[0][:, 0:2], flows[0][:, 2:4]]])
-        if self.args.visualization_flag:
-            raise NotImplementedError("visualization_flag maps (utils.py:1480-1754) are out of scope (SURVEY.md 2, row 11)")
-        return sharps_dec1, sharps_final, flows, occs, two_blurry
+        v = eng.views
+        blending_weights = [maps[0], maps[1], maps[0], maps[1], [v["FO"].ch(0, 2).to_nchw(), v["FO"].ch(2, 2).to_nchw()]]
+        return sharps_dec1, sharps_final, flows, occs, two_blurry, blending_weights, difference_maps

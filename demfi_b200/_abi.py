@@ -66,6 +66,7 @@ SYMBOLS = {
     "demfi_fgac_blend": (i32, [vp, i32, vp, i32, vp, i32, C.c_int64, i32, vp, i32, vp]),
     "demfi_copy_channels": (i32, [vp, i32, vp, i32, i32, C.c_int64, i32, vp]),
     "demfi_gather_channels": (i32, [C.POINTER(Part), i32, vp, i32, C.c_int64, vp]),
+    "demfi_channel_absmean": (i32, [vp, i32, vp, i32, C.c_int64, i32, vp, vp]),
     "demfi_upsample2x": (i32, [vp, i32, i32, i32, i32, i32, vp, i32, vp]),
     "demfi_export_nchw": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, vp]),
     "demfi_import_nchw": (i32, [vp, i32, i32, i32, i32, vp, i32, vp]),

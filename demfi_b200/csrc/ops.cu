@@ -461,6 +461,27 @@ upsample2x_kernel(const float* __restrict__ src, int src_ld, int B, int Hs, int 
 
 static inline unsigned blocks_for(long long n, int per = 256) { return (unsigned)((n + per - 1) / per); }
 
+// Channel mean of |a| or |a - b| per pixel (the FGAC difference / visualisation maps, DeMFInet.py:456-491): 16 lanes per
+// pixel, one float4 per lane and pass, shuffle tree.  out[p] = mean_c |a[p,c] - b[p,c]|.
+__global__ void __launch_bounds__(256) channel_absmean_kernel(const float* __restrict__ a, int a_ld, const float* __restrict__ b,
+                                                               int b_ld, long long npix, int C4, float inv_c, float* __restrict__ out) {
+  const long long p = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+  const int l = threadIdx.x & 15;
+  float s = 0.0f;
+  if (p < npix) {
+    for (int q = l; q < C4; q += 16) {
+      float4 v = ld4(a + p * a_ld + 4 * q);
+      if (b != nullptr) {
+        const float4 w = ld4(b + p * b_ld + 4 * q);
+        v.x -= w.x; v.y -= w.y; v.z -= w.z; v.w -= w.w;
+      }
+      s += (fabsf(v.x) + fabsf(v.y)) + (fabsf(v.z) + fabsf(v.w));
+    }
+  }
+  for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (p < npix && l == 0) out[p] = s * inv_c;
+}
+
 }  // namespace demfi
 
 using namespace demfi;
@@ -564,6 +585,16 @@ int demfi_gather_channels(const demfi_part_t* parts, int32_t nparts, float* dst,
   }
   gather_channels_kernel<<<blocks_for(npix * nparts), 256, 0, (cudaStream_t)stream>>>(G, dst, dst_ld, npix);
   DEMFI_LAUNCH_CHECK("gather_channels");
+  return 0;
+}
+
+int demfi_channel_absmean(const float* a, int32_t a_ld, const float* b, int32_t b_ld, int64_t npix, int32_t C, float* out,
+                          void* stream) {
+  if (check_device()) return 3;
+  DEMFI_REQUIRE(a && out && npix > 0 && C > 0 && C % 4 == 0 && a_ld % 4 == 0 && ((uintptr_t)a % 16) == 0 &&
+                    (b == nullptr || (b_ld % 4 == 0 && ((uintptr_t)b % 16) == 0)), "channel_absmean: bad arguments");
+  channel_absmean_kernel<<<blocks_for(npix * 16), 256, 0, (cudaStream_t)stream>>>(a, a_ld, b, b_ld, npix, C / 4, 1.0f / (float)C, out);
+  DEMFI_LAUNCH_CHECK("channel_absmean");
   return 0;
 }
 

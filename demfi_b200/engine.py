@@ -440,6 +440,39 @@ class Engine:
         return ops
 
     # ------------------------------------------------------------------ static checks
+    def fgac_maps(self, visualization: bool):
+        """The FGAC side outputs of the training / visualisation tuples (FGAC.forward, DeMFInet.py:454-495), from the buffers
+        the last forward left in place: per direction d (0: F1 -> F0, 1: F0 -> F1) the min-max normalised difference map and,
+        for visualisation, [w, 1 - w, source, key conv of the reference frame, E_s, result] (the last four as normalised
+        channel means).  Channel means come from `demfi_channel_absmean`; the per-sample normalisation is three small torch
+        ops on [B, H*W] maps."""
+        B, H, W, v = self.B, self.H, self.W, self.views
+        st = torch.cuda.current_stream(self.dev).cuda_stream
+
+        def absmean(a: View, b: Optional[View] = None) -> torch.Tensor:
+            assert a.fmt == A.FMT_F32 and (b is None or b.fmt == A.FMT_F32)
+            out = torch.empty(a.N, H * W, dtype=torch.float32, device=self.dev)
+            A.check(A.lib().demfi_channel_absmean(a.ptr, a.ld, b.ptr if b is not None else None, b.ld if b is not None else 0,
+                                                  a.npix(), a.C, out.data_ptr(), st), "demfi_channel_absmean")
+            return out
+
+        def norm(m: torch.Tensor) -> torch.Tensor:
+            m = m - m.min(1, keepdim=True)[0]
+            m = m / m.max(1, keepdim=True)[0]
+            return m.view(B, 1, H, W)
+
+        diffs, maps = [], []
+        for d in range(2):
+            src = v["SE"].frames(d * B, B).ch(0, 64)       # source_v = encoder features of frame d
+            e_s = v["SE"].frames(d * B, B).ch(64, 64)      # fusion output
+            res = v["AGG1"].ch(64 * d, 64)                 # Eq.(4) result
+            ref_k = v["RK"].frames((1 - d) * B, B)         # conv_ref_k of the OTHER frame, before sampling
+            diffs.append(norm(absmean(res, src)))
+            if visualization:
+                w = v["WL"].frames(d * B, B).ch(0, 1).to_nchw()
+                maps.append([w, 1 - w, norm(absmean(src)), norm(absmean(ref_k)), norm(absmean(e_s)), norm(absmean(res))])
+        return diffs, maps
+
     def check_formats(self, num_update: int = 3) -> int:
         """Replay the op lists symbolically and check the storage formats: every 32-channel group a convolution reads as S16
         must have been written as S16 by a convolution (or copied bit-wise by the up-sampler), and no fp32 reader may see a

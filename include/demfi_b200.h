@@ -182,6 +182,11 @@ typedef struct {
   int32_t src_ld, nch, dst_c0, reserved;
 } demfi_part_t;
 int demfi_gather_channels(const demfi_part_t* parts, int32_t nparts, float* dst, int32_t dst_ld, int64_t npix, void* stream);
+/* Channel mean of absolute values per pixel: out[p] = mean_{c<C} |a[p*a_ld + c] - (b ? b[p*b_ld + c] : 0)|, out a dense
+ * [npix] map.  The reduction half of the FGAC difference map (DeMFInet.py:456-462) and of the four visualisation maps
+ * (:465-491); the per-sample min-max normalisation that follows is done by the host mirror.  C % 4 == 0. */
+int demfi_channel_absmean(const float* a, int32_t a_ld, const float* b, int32_t b_ld, int64_t npix, int32_t C, float* out,
+                          void* stream);
 /* nn.UpsamplingNearest2d(scale_factor=2) (DeMFInet.py:573): src [B,Hs,Ws,C of src_ld] -> dst [B,2Hs,2Ws,C of dst_ld].
  * Materialises the UNet decoder inputs so that dec1-3 run on the tensor-core conv. */
 int demfi_upsample2x(const float* src, int32_t src_ld, int32_t B, int32_t Hs, int32_t Ws, int32_t C, float* dst,

@@ -179,7 +179,17 @@ def _resblocks(x, sd, prefix, n=5):
     return x
 
 
-def fgac(sd, ref, src, flow_s2r, out=None, tag=""):
+def _minmax_map(x):
+    """channel mean of |x|, min-max normalised per sample (`DeMFInet.py:465-491`, the same five lines four times)"""
+    m = torch.mean(torch.abs(x), 1, keepdim=True)
+    b = m.shape[0]
+    f = m.reshape(b, -1)
+    f = f - f.min(1, keepdim=True)[0]
+    f = f / f.max(1, keepdim=True)[0]
+    return f.reshape(m.shape)
+
+
+def fgac(sd, ref, src, flow_s2r, out=None, tag="", visualization=False):
     """`FGAC.forward` with rr = sr = 0, `DeMFInet.py:386-452`: the key conv of `ref` is
     bilinearly sampled at ABSOLUTE position (x, y) = flow value (no base grid is added,
     `:413-419`, `bilinear_sampler` `:499-514`); the correlation softmax runs over one
@@ -203,10 +213,12 @@ def fgac(sd, ref, src, flow_s2r, out=None, tag=""):
     if out is not None:
         out["fgac_sampled" + tag] = sampled
         out["fgac_w" + tag] = w_sr
+    if visualization:  # `DeMFInet.py:464-493`: [w, 1-w, source, key conv of ref (before sampling), E_s, result]
+        return res, [w_sr, 1 - w_sr, _minmax_map(src), _minmax_map(ref_k), _minmax_map(e_s), _minmax_map(res)], d.reshape(diff.shape)
     return res, w_sr, d.reshape(diff.shape)
 
 
-def fac_fb(sd, F0, F1, flow_10, flow_01, out):
+def fac_fb(sd, F0, F1, flow_10, flow_01, out, visualization=False):
     """`FAC_FB.forward`, `DeMFInet.py:335-358` (shared FGAC)."""
     p = "FAC_FB_Module."
     B = F0.shape[0]
@@ -214,8 +226,8 @@ def fac_fb(sd, F0, F1, flow_10, flow_01, out):
     e = _resblocks(F.relu(_conv(x, sd, p + "conv_first")), sd, p + "feature_extraction")
     e0, e1 = e[:B], e[B:]
     out["enc0"], out["enc1"] = e0, e1
-    a0, w0, d10 = fgac(sd, e1, e0, flow_01, out, "0")
-    a1, w1, d01 = fgac(sd, e0, e1, flow_10, out, "1")
+    a0, w0, d10 = fgac(sd, e1, e0, flow_01, out, "0", visualization)
+    a1, w1, d01 = fgac(sd, e0, e1, flow_10, out, "1", visualization)
     return a0, a1, [w0, w1, w0, w1], [d10, d01, d10, d01]
 
 
@@ -254,9 +266,10 @@ def booster(sd, f_rec, ref30, delta5, out=None, tag=""):
 # ----------------------------------------------------------------------------- forward
 @torch.no_grad()
 def forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, t_value: torch.Tensor,
-            num_update: Optional[int] = None, is_training=None, intermediates: Optional[dict] = None):
-    """`DeMFInet.forward`, `DeMFInet.py:46-179`.  Returns the eval 5-tuple (7-tuple when
-    is_training).  `intermediates`, when a dict, receives named tensors (NCHW)."""
+            num_update: Optional[int] = None, is_training=None, intermediates: Optional[dict] = None,
+            visualization_flag: bool = False):
+    """`DeMFInet.forward`, `DeMFInet.py:46-179`.  Returns the eval 5-tuple, the training 7-tuple when is_training, or the
+    visualisation 7-tuple (`args.visualization_flag`, eval only).  `intermediates`, when a dict, receives named tensors (NCHW)."""
     out = intermediates if intermediates is not None else {}
     B = x.shape[0]
     B0, B1, Bm1, B2 = x[:, :, 0], x[:, :, 1], x[:, :, 2], x[:, :, 3]
@@ -270,7 +283,7 @@ def forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, t_value: torch.Tensor,
     Ft = eq2_blend(F0, flow_t0, F1, flow_t1, occ_logit, t)
     out["Ft"] = Ft
 
-    aF0, aF1, blending_weights, difference_maps = fac_fb(sd, F0, F1, flow_10, flow_01, out)
+    aF0, aF1, blending_weights, difference_maps = fac_fb(sd, F0, F1, flow_10, flow_01, out, visualization_flag)
     out.update(aF0=aF0, aF1=aF1)
 
     agg1 = torch.cat([aF0, aF1, Ft, flow_t0, flow_t1, flow_01, flow_10, occ_logit], 1)
@@ -318,6 +331,9 @@ def forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, t_value: torch.Tensor,
     if is_training:
         return (sharps_dec1, sharps_final, flow_predictions, occ0_predictions, two_blurry,
                 difference_maps, [[rflow_t0, rflow_t1]])
+    if visualization_flag:  # `DeMFInet.py:167-168, 174-176`
+        return (sharps_dec1, sharps_final, flow_predictions, occ0_predictions, two_blurry,
+                blending_weights + [[flow_01, flow_10]], difference_maps)
     return sharps_dec1, sharps_final, flow_predictions, occ0_predictions, two_blurry
 
 

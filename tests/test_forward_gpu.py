@@ -159,6 +159,37 @@ def test_return_structure(net):
             net(synth.make_frames(20, 24), t, 1)
 
 
+def test_visualisation_tuple_matches_reference_golden(state_dict):
+    """eval + args.visualization_flag: the 7-tuple of DeMFInet.py:174-176 against the reference's own output
+    (tests/golden/c48x64_vis_b2.npz).  Measured 1-5e-6 on every map; the bound is the north-star 5e-4."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "c48x64_vis_b2.npz"))
+    m = DeMFInet(synth.default_args(visualization_flag=True)).to(DEV).eval()
+    m.load_state_dict(state_dict, strict=True)
+    x = synth.make_frames(48, 64, seed=0, batch=2).to(DEV)
+    t = torch.tensor([[0.25], [0.625]], device=DEV)
+    with torch.no_grad():
+        res = m(x, t, 1)
+    assert len(res) == 7 and len(res[5]) == 5 and len(res[6]) == 4 and res[5][2] is res[5][0] and res[5][3] is res[5][1]
+    assert res[6][2] is res[6][0] and len(res[5][0]) == 6 and len(res[5][4]) == 2
+    worst = 0.0
+    for i in range(2):
+        for j in range(6):
+            assert res[5][i][j].shape == (2, 1, 48, 64)
+            d = float((res[5][i][j].cpu() - torch.from_numpy(g[f"bw{i}_{j}"])).abs().max())
+            print(f"visualisation map {i}.{j}: max-abs {d:.2e}")
+            assert d < TOL, (i, j, d)
+            worst = max(worst, d)
+        assert float((res[6][i].cpu() - torch.from_numpy(g[f"diff{i}"])).abs().max()) < TOL
+    assert float((res[5][4][0].cpu() - torch.from_numpy(g["flow_01"])).abs().max()) < TOL
+    assert float((res[5][4][1].cpu() - torch.from_numpy(g["flow_10"])).abs().max()) < TOL
+    assert float((res[1][0][2].cpu() - torch.from_numpy(g["St_final0"])).abs().max()) < TOL
+    # is_training wins over the flag (DeMFInet.py:170-173)
+    with torch.no_grad():
+        r7 = m(x, t, 1, is_training=True)
+    assert len(r7) == 7 and len(r7[6]) == 1 and len(r7[6][0]) == 2
+
+
 # ---- BASELINE.json's full size (1280x720 padded to 1280x736, N_tst=3): size-independent properties
 FULL_H, FULL_W = 736, 1280
 

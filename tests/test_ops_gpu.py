@@ -176,3 +176,23 @@ def test_gather_channels_assembles_a_row_in_one_pass():
     for b, c0, nch, d0 in spec:
         want[..., d0:d0 + nch] = srcs[b][..., c0:c0 + nch]
     assert torch.equal(dst, want)
+
+
+def test_channel_absmean():
+    """mean_c |a - b| per pixel (FGAC difference / visualisation maps, DeMFInet.py:456-491): channel slices of wider rows,
+    with and without the second operand, a ragged pixel count"""
+    n, h, w = 2, 7, 13
+    a = rnd(n, 64, h, w, seed=31)
+    b = rnd(n, 64, h, w, seed=32)
+    ab, _ = nhwc(a, 132)
+    bb, _ = nhwc(b, 68)
+    for second in (True, False):
+        out = torch.full((n * h * w + 5,), -3.0, device=DEV)
+        A.check(A.lib().demfi_channel_absmean(ab.data_ptr(), 132, bb.data_ptr() if second else None, 68 if second else 0,
+                                              n * h * w, 64, out.data_ptr(), stream()), "channel_absmean")
+        torch.cuda.synchronize()
+        want = ((a.double() - b.double()) if second else a.double()).abs().mean(1).reshape(-1)
+        assert float((out[:n * h * w].cpu().double() - want).abs().max()) < 1e-6
+        assert float((out[n * h * w:] + 3.0).abs().max()) == 0   # nothing written past npix
+    A.lib().demfi_channel_absmean(ab.data_ptr(), 132, None, 0, 10, 6, out.data_ptr(), stream())  # C % 4 != 0
+    assert b"channel_absmean" in A.lib().demfi_last_error()

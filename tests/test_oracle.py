@@ -1,6 +1,8 @@
 """CPU: pins oracle/demfi_oracle.py to the golden vectors generated from the unmodified reference
 (oracle/gen_golden.py) and its closed-form primitives to the torch library ops the reference calls."""
 import numpy as np
+import os
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -28,6 +30,24 @@ def test_oracle_matches_reference_golden(state_dict, golden_meta, case):
         d = float((got[k] - torch.from_numpy(g)).abs().max())
         assert d < ORACLE_TOL, f"{case}:{k} max-abs {d}"
     assert len(res[1]) == cfg["n"] and len(res[2]) == cfg["n"] + 1
+
+
+def test_oracle_visualisation_tuple_matches_reference_golden(state_dict):
+    """eval + args.visualization_flag (DeMFInet.py:167-176, FGAC maps :464-493): reference output in
+    tests/golden/c48x64_vis_b2.npz (oracle/gen_golden_vis.py)"""
+    import numpy as np
+    from demfi_b200 import synth
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "c48x64_vis_b2.npz"))
+    x = synth.make_frames(48, 64, seed=0, batch=2)
+    t = torch.tensor([[0.25], [0.625]])
+    res = O.forward(state_dict, x, t, 1, visualization_flag=True)
+    assert len(res) == 7 and len(res[5]) == 5 and len(res[6]) == 4 and res[5][2] is res[5][0] and res[6][3] is res[6][1]
+    for i in range(2):
+        for j in range(6):
+            assert float((res[5][i][j] - torch.from_numpy(g[f"bw{i}_{j}"])).abs().max()) < ORACLE_TOL, (i, j)
+        assert float((res[6][i] - torch.from_numpy(g[f"diff{i}"])).abs().max()) < ORACLE_TOL
+    assert float((res[5][4][0] - torch.from_numpy(g["flow_01"])).abs().max()) < ORACLE_TOL
+    assert float((res[5][4][1] - torch.from_numpy(g["flow_10"])).abs().max()) < ORACLE_TOL
 
 
 def test_bilinear_gather_is_grid_sample_align_corners_true():
