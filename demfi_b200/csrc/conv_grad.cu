@@ -1,0 +1,136 @@
+// Backward pieces of a stride-1 convolution layer y = act(conv(x, W) + b) -- first correct CUDA path of the training row
+// (the reference gets these from autograd through nn.Conv2d, main.py:443):
+//   * dz = dy * act'(y)                       act_backward_kernel (ReLU / tanh / sigmoid from the stored output)
+//   * dx = conv(dz, W rotated 180, Cin<->Cout) runs on the FORWARD tensor-core kernel (demfi_conv2d) with weights re-packed by
+//                                             the host (demfi_b200/grad.py), so it needs nothing here
+//   * dW[co,ci,ky,kx] = sum_p dz[p,co] * x[p + (ky,kx) - pad, ci],  db[co] = sum_p dz[p,co]      conv_wgrad_kernel
+// conv_wgrad_kernel is the CUDA-core version (fp32 FFMA, 64 x 64 output tile per CTA and tap, pixels as the reduction
+// dimension, one fp32 atomic add per output and pixel chunk): the same role conv_ffma plays for the forward -- correct first,
+// and later the independent implementation the tensor-core wgrad is tested against.  Algorithmic work = the forward's MACs.
+#include "common.cuh"
+
+namespace demfi {
+
+constexpr int WG_T = 64;     // output tile: WG_T output channels x WG_T input channels
+constexpr int WG_KP = 16;    // pixels per shared-memory stage
+constexpr int WG_CHUNK = 2048;  // pixels reduced by one CTA before its atomic adds
+
+struct WgradParams {
+  const float* x; const float* dz; float* dw; float* db;
+  int x_ld, dz_ld, Cin, Cout, N, H, W, KH, KW, pad_h, pad_w;
+  int co_blocks, ci_blocks;
+  long long npix;
+};
+
+__global__ void __launch_bounds__(256) conv_wgrad_kernel(const WgradParams P) {
+  __shared__ __align__(16) float zs[WG_KP][WG_T];
+  __shared__ __align__(16) float xs[WG_KP][WG_T];
+  const int tap = blockIdx.y, ky = tap / P.KW, kx = tap % P.KW;
+  const int cb = blockIdx.z / P.ci_blocks, ib = blockIdx.z % P.ci_blocks;
+  const int co0 = cb * WG_T, ci0 = ib * WG_T;
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  const bool do_bias = (P.db != nullptr && tap == 0 && ib == 0);
+  float acc[4][4] = {};
+  float bsum[4] = {};
+  const long long p0 = (long long)blockIdx.x * WG_CHUNK;
+  const long long p1 = min(p0 + (long long)WG_CHUNK, P.npix);
+  const int lc = threadIdx.x & 63, lr0 = threadIdx.x >> 6;  // loader: channel lc of rows lr0, lr0 + 4, ...
+  for (long long pb = p0; pb < p1; pb += WG_KP) {
+#pragma unroll
+    for (int r = lr0; r < WG_KP; r += 4) {
+      const long long p = pb + r;
+      float zv = 0.0f, xv = 0.0f;
+      if (p < p1) {
+        if (co0 + lc < P.Cout) zv = P.dz[p * P.dz_ld + co0 + lc];
+        const int xw = (int)(p % P.W), yh = (int)((p / P.W) % P.H);
+        const int sy = yh + ky - P.pad_h, sx = xw + kx - P.pad_w;
+        if (ci0 + lc < P.Cin && sy >= 0 && sy < P.H && sx >= 0 && sx < P.W)
+          xv = P.x[(p + (long long)(sy - yh) * P.W + (sx - xw)) * P.x_ld + ci0 + lc];
+      }
+      zs[r][lc] = zv;
+      xs[r][lc] = xv;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < WG_KP; ++r) {
+      const float4 a = *reinterpret_cast<const float4*>(&zs[r][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&xs[r][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        bsum[i] += av[i];
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int co = co0 + ty * 4 + i;
+    if (co >= P.Cout) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int ci = ci0 + tx * 4 + j;
+      if (ci < P.Cin) atomicAdd(&P.dw[(((size_t)co * P.Cin + ci) * P.KH + ky) * P.KW + kx], acc[i][j]);
+    }
+    if (do_bias && tx == 0) atomicAdd(&P.db[co], bsum[i]);
+  }
+}
+
+// dz = dy * act'(y), y the layer's stored OUTPUT (ReLU: y > 0; tanh: 1 - y^2; sigmoid: y (1 - y)); C channels of NHWC rows
+__global__ void __launch_bounds__(256) act_backward_kernel(const float* __restrict__ dy, int dy_ld, const float* __restrict__ y, int y_ld,
+                                                           long long npix, int C, int act, float* __restrict__ out, int out_ld) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix * C) return;
+  const long long p = i / C;
+  const int c = (int)(i % C);
+  const float g = dy[p * dy_ld + c];
+  float d = 1.0f;
+  if (act != DEMFI_ACT_NONE) {
+    const float v = y[p * y_ld + c];
+    d = act == DEMFI_ACT_RELU ? (v > 0.0f ? 1.0f : 0.0f) : act == DEMFI_ACT_TANH ? 1.0f - v * v : v * (1.0f - v);
+  }
+  out[p * out_ld + c] = g * d;
+}
+
+}  // namespace demfi
+
+using namespace demfi;
+
+extern "C" {
+
+int demfi_conv2d_wgrad(const float* x, int32_t x_ld, int32_t Cin, const float* dz, int32_t dz_ld, int32_t Cout, int32_t N,
+                       int32_t H, int32_t W, int32_t KH, int32_t KW, int32_t pad_h, int32_t pad_w, float* dw, float* dbias,
+                       void* stream) {
+  if (check_device()) return 3;
+  DEMFI_REQUIRE(x && dz && dw, "conv2d_wgrad: null pointer");
+  DEMFI_REQUIRE(N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && KH > 0 && KW > 0 && KH * KW <= 65535 && x_ld >= Cin && dz_ld >= Cout &&
+                    pad_h >= 0 && pad_w >= 0, "conv2d_wgrad: bad shape");
+  DEMFI_REQUIRE(H + 2 * pad_h - KH + 1 == H && W + 2 * pad_w - KW + 1 == W, "conv2d_wgrad: only stride-1 'same' convolutions");
+  WgradParams P;
+  P.x = x; P.dz = dz; P.dw = dw; P.db = dbias;
+  P.x_ld = x_ld; P.dz_ld = dz_ld; P.Cin = Cin; P.Cout = Cout; P.N = N; P.H = H; P.W = W; P.KH = KH; P.KW = KW;
+  P.pad_h = pad_h; P.pad_w = pad_w;
+  P.co_blocks = (Cout + WG_T - 1) / WG_T;
+  P.ci_blocks = (Cin + WG_T - 1) / WG_T;
+  P.npix = (long long)N * H * W;
+  DEMFI_REQUIRE(P.co_blocks * P.ci_blocks <= 65535, "conv2d_wgrad: too many channel blocks");
+  dim3 grid((unsigned)((P.npix + WG_CHUNK - 1) / WG_CHUNK), KH * KW, P.co_blocks * P.ci_blocks);
+  conv_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P);
+  DEMFI_LAUNCH_CHECK("conv_wgrad");
+  return 0;
+}
+
+int demfi_act_backward(const float* dy, int32_t dy_ld, const float* y, int32_t y_ld, int64_t npix, int32_t C, int32_t act,
+                       float* out, int32_t out_ld, void* stream) {
+  if (check_device()) return 3;
+  DEMFI_REQUIRE(dy && out && npix > 0 && C > 0 && dy_ld >= C && out_ld >= C, "act_backward: bad arguments");
+  DEMFI_REQUIRE(act == DEMFI_ACT_NONE || ((act == DEMFI_ACT_RELU || act == DEMFI_ACT_TANH || act == DEMFI_ACT_SIGMOID) && y && y_ld >= C),
+                "act_backward: activation %d has no backward here (or y is missing)", act);
+  act_backward_kernel<<<(unsigned)((npix * C + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dy, dy_ld, y, y_ld, npix, C, act, out, out_ld);
+  DEMFI_LAUNCH_CHECK("act_backward");
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,134 @@
+"""Differentiable convolution layer through the C ABI -- the first slice of the training row.
+
+`conv2d(x, weight, bias, act)` computes `act(F.conv2d(x, weight, bias, padding='same'))` for the stride-1 layers of DeMFI-Net
+(every nn.Conv2d / nn.Conv3d[1,k,k] of `DeMFInet.py` except the three stride-2 UNet encoders) and is differentiable:
+
+  forward   demfi_conv2d            tcgen05 kernel, 3xFP16 split (fp32 parity), fused bias + activation
+  dz        demfi_act_backward      dy * act'(y) from the stored output
+  dx        demfi_conv2d            the SAME forward kernel on the weights rotated by 180 degrees with Cin/Cout exchanged
+  dW, db    demfi_conv2d_wgrad      CUDA-core fp32 kernel (first correct path; accumulates with fp32 atomics)
+
+What the reference gets from autograd through `nn.Conv2d` (main.py:443).  NCHW tensors at the boundary (imported / exported
+with the ABI's layout kernels), NHWC inside.  No CPU or ATen fallback: CPU tensors raise.  Not yet wired into `DeMFInet.forward`
+(whose `is_training` + grad mode still raises): the warps, the splat and the fused epilogues need their own backward first.
+"""
+from __future__ import annotations
+
+from typing import Dict, Tuple
+
+import numpy as np
+import torch
+
+from . import _abi as A
+
+ACTS = {"none": A.ACT_NONE, "relu": A.ACT_RELU, "tanh": A.ACT_TANH, "sigmoid": A.ACT_SIGMOID}
+_ru = lambda v, m: (v + m - 1) // m * m
+_PACKED: Dict[Tuple, Tuple[torch.Tensor, torch.Tensor, object]] = {}
+
+
+def _stream(dev):
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _pack(w: np.ndarray, b: np.ndarray, src_c: int, dev) -> Tuple[torch.Tensor, torch.Tensor, int]:
+    """OIHW fp32 -> the tensor-core kernel's packed hi/lo layout for ONE source of `src_c` (>= Cin, zero-weight padding) channels"""
+    lib = A.lib()
+    Co, Ci, KH, KW = w.shape
+    cout_pad = _ru(Co, 16)
+    sC = (A.i32 * 1)(src_c)
+    in_map = (A.i32 * src_c)(*(list(range(Ci)) + [-1] * (src_c - Ci)))
+    out_map = (A.i32 * cout_pad)(*(list(range(Co)) + [-1] * (cout_pad - Co)))
+    n = lib.demfi_packed_weight_floats(A.CONV_TC16, KH, KW, sC, 1, cout_pad)
+    packed = np.empty(n, dtype=np.float32)
+    w = np.ascontiguousarray(w, dtype=np.float32)
+    A.check(lib.demfi_pack_weights(A.CONV_TC16, w.ctypes.data, Co, Ci, KH, KW, in_map, sC, 1, out_map, cout_pad,
+                                   packed.ctypes.data), "demfi_pack_weights")
+    bias = np.zeros(cout_pad, dtype=np.float32)
+    bias[:Co] = b
+    return torch.from_numpy(packed).to(dev), torch.from_numpy(bias).to(dev), cout_pad
+
+
+def _conv_nhwc(x: torch.Tensor, C_: int, wdev: torch.Tensor, bdev: torch.Tensor, cout_pad: int, k: Tuple[int, int], act: int):
+    """x: [N,H,W,ld] fp32 NHWC of which the first C_ channels are read; returns [N,H,W,cout_pad]"""
+    N, H, W, ld = x.shape
+    y = torch.empty(N, H, W, cout_pad, dtype=torch.float32, device=x.device)
+    d = A.Conv()
+    d.N, d.H, d.W, d.Hi, d.Wi = N, H, W, H, W
+    d.KH, d.KW, d.stride, d.pad_h, d.pad_w = k[0], k[1], 1, k[0] // 2, k[1] // 2
+    d.nsrc, d.nseg, d.cout_pad, d.kind = 1, 1, cout_pad, A.CONV_TC16
+    d.src[0].ptr, d.src[0].C, d.src[0].ld = x.data_ptr(), C_, ld
+    s = d.seg[0]
+    s.dst, s.dst_ld, s.ch0, s.nch, s.act, s.store = y.data_ptr(), cout_pad, 0, cout_pad, act, A.STORE_NHWC
+    d.wpack, d.bias = wdev.data_ptr(), bdev.data_ptr()
+    A.check(A.lib().demfi_conv2d(d, _stream(x.device)), "demfi_conv2d")
+    return y
+
+
+def _to_nhwc(t: torch.Tensor, ld: int) -> torch.Tensor:
+    N, C_, H, W = t.shape
+    out = torch.zeros(N, H, W, ld, dtype=torch.float32, device=t.device) if ld != C_ else \
+        torch.empty(N, H, W, ld, dtype=torch.float32, device=t.device)
+    A.check(A.lib().demfi_import_nchw(t.contiguous().data_ptr(), N, H, W, C_, out.data_ptr(), ld, _stream(t.device)), "import_nchw")
+    return out
+
+
+def _to_nchw(buf: torch.Tensor, C_: int) -> torch.Tensor:
+    N, H, W, ld = buf.shape
+    out = torch.empty(N, C_, H, W, dtype=torch.float32, device=buf.device)
+    A.check(A.lib().demfi_export_nchw(buf.data_ptr(), ld, N, H, W, C_, A.ACT_NONE, out.data_ptr(), _stream(buf.device)), "export_nchw")
+    return out
+
+
+class _Conv2d(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, act: int):
+        if not x.is_cuda:
+            raise A.DemfiError("demfi_b200.grad.conv2d runs on the GPU only (no CPU fallback)")
+        Co, Ci, KH, KW = weight.shape
+        if KH % 2 == 0 or KW % 2 == 0 or x.shape[1] != Ci:
+            raise ValueError("conv2d: odd 'same' kernels with matching channel counts only (the stride-1 layers of DeMFI-Net)")
+        dev = x.device
+        with torch.cuda.device(dev):
+            cin_pad = _ru(Ci, 8)
+            xb = _to_nhwc(x.detach().float(), cin_pad)
+            b = bias.detach() if bias is not None else torch.zeros(Co, device=dev)
+            wdev, bdev, cout_pad = _pack(weight.detach().cpu().numpy(), b.cpu().numpy(), cin_pad, dev)
+            yb = _conv_nhwc(xb, cin_pad, wdev, bdev, cout_pad, (KH, KW), act)
+            y = _to_nchw(yb, Co)
+        ctx.save_for_backward(weight)
+        ctx.xb, ctx.yb, ctx.act, ctx.has_bias, ctx.shape = xb, yb, act, bias is not None, tuple(x.shape)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (weight,) = ctx.saved_tensors
+        xb, yb, act = ctx.xb, ctx.yb, ctx.act
+        Co, Ci, KH, KW = weight.shape
+        N, _, H, W = ctx.shape
+        dev = dy.device
+        lib = A.lib()
+        with torch.cuda.device(dev):
+            st = _stream(dev)
+            co_pad = _ru(Co, 8)
+            dyb = _to_nhwc(dy.detach().float(), co_pad)
+            dz = torch.zeros_like(dyb)
+            A.check(lib.demfi_act_backward(dyb.data_ptr(), co_pad, yb.data_ptr(), yb.shape[3], N * H * W, Co, act, dz.data_ptr(),
+                                           co_pad, st), "demfi_act_backward")
+            dx = dw = db = None
+            if ctx.needs_input_grad[0]:
+                # dx = conv(dz, W^T rotated): w_t[ci, co, ky, kx] = W[co, ci, KH-1-ky, KW-1-kx]
+                w_t = weight.detach().flip(2, 3).transpose(0, 1).contiguous().cpu().numpy()
+                wdev, bdev, ci_pad = _pack(w_t, np.zeros(Ci, dtype=np.float32), co_pad, dev)
+                dx = _to_nchw(_conv_nhwc(dz, co_pad, wdev, bdev, ci_pad, (KH, KW), A.ACT_NONE), Ci)
+            if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+                dw = torch.zeros(Co, Ci, KH, KW, dtype=torch.float32, device=dev)
+                db = torch.zeros(Co, dtype=torch.float32, device=dev) if ctx.has_bias else None
+                A.check(lib.demfi_conv2d_wgrad(xb.data_ptr(), xb.shape[3], Ci, dz.data_ptr(), co_pad, Co, N, H, W, KH, KW,
+                                               KH // 2, KW // 2, dw.data_ptr(), db.data_ptr() if db is not None else None, st),
+                        "demfi_conv2d_wgrad")
+        return dx, dw, db, None
+
+
+def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor = None, act: str = "none") -> torch.Tensor:
+    """act(conv2d(x, weight, bias, stride 1, 'same' padding)); x [N,Cin,H,W], weight [Cout,Cin,KH,KW] (odd KH, KW) on a B200."""
+    return _Conv2d.apply(x, weight, bias, ACTS[act])

@@ -198,6 +198,19 @@ int demfi_export_nchw(const float* src, int32_t src_ld, int32_t B, int32_t H, in
 int demfi_import_nchw(const float* src, int32_t B, int32_t H, int32_t W, int32_t C, float* dst, int32_t dst_ld,
                       void* stream);
 
+/* ---- backward of a convolution layer (training row; first correct path) ------------------------ */
+/* The reference obtains these from autograd through nn.Conv2d (main.py:443).  For y = act(conv(x, W) + b), stride 1, 'same':
+ *   dz = dy * act'(y)                    demfi_act_backward (act: NONE / RELU / TANH / SIGMOID, from the stored output y)
+ *   dx = conv(dz, W rotated by 180 degrees with Cin and Cout exchanged): the forward kernel, demfi_conv2d, on re-packed weights
+ *   dW, db                               demfi_conv2d_wgrad: dw[co][ci][ky][kx] += sum_p dz[p][co] * x[p + (ky,kx) - pad][ci]
+ *                                        (OIHW fp32, the layout of the parameter), dbias[co] += sum_p dz[p][co] (may be NULL).
+ * x, dz: NHWC with row strides x_ld / dz_ld.  Both gradients are ACCUMULATED (+=) with fp32 atomics: zero them first. */
+int demfi_conv2d_wgrad(const float* x, int32_t x_ld, int32_t Cin, const float* dz, int32_t dz_ld, int32_t Cout, int32_t N,
+                       int32_t H, int32_t W, int32_t KH, int32_t KW, int32_t pad_h, int32_t pad_w, float* dw, float* dbias,
+                       void* stream);
+int demfi_act_backward(const float* dy, int32_t dy_ld, const float* y, int32_t y_ld, int64_t npix, int32_t C, int32_t act,
+                       float* out, int32_t out_ld, void* stream);
+
 /* ---- evaluation metrics (the consumer right after the hot path) ------------------------- */
 /* PSNR / SSIM sums of predicted frames against their targets as the reference's evaluation loop computes them
  * (main.py:763-771 with utils.py:652-705, 718-721): pred, target are NCHW [B,C,H,W] fp32 in [-1,1] on the device (what

@@ -1,0 +1,65 @@
+"""Backward of a convolution layer through the C ABI (training row f-2, first slice): demfi_b200.grad.conv2d against torch
+autograd on the same layer in float64.  Forward and dx run on the tcgen05 kernel (fp32 parity), dW / db on the CUDA-core
+wgrad kernel (fp32 atomics): tolerances relative to the gradient's own scale."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from demfi_b200 import grad
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+ACT = {"none": lambda v: v, "relu": torch.relu, "tanh": torch.tanh, "sigmoid": torch.sigmoid}
+
+
+@pytest.mark.parametrize("ci,co,k,act,n,h,w", [
+    (64, 64, (3, 3), "relu", 2, 40, 56),       # ResBlock conv
+    (5, 32, (7, 7), "relu", 1, 32, 48),        # Mixer.conv_delta1: ragged Cin
+    (64, 3, (3, 3), "none", 3, 24, 40),        # Dec_last2: ragged Cout
+    (128, 64, (1, 5), "tanh", 1, 32, 64),      # GRU q-like, asymmetric kernel
+    (96, 133, (3, 3), "none", 1, 24, 24),      # more output channels than one 64-wide block, ragged
+    (224, 96, (1, 1), "sigmoid", 1, 20, 36),   # 1x1 (LFF-like)
+])
+def test_conv2d_layer_gradients(ci, co, k, act, n, h, w):
+    g = torch.Generator().manual_seed(ci * 1000 + co)
+    x = torch.randn(n, ci, h, w, generator=g)
+    wt = torch.randn(co, ci, *k, generator=g) / (ci * k[0] * k[1]) ** 0.5
+    b = torch.randn(co, generator=g) * 0.1
+    gy = torch.randn(n, co, h, w, generator=g)
+    # float64 reference
+    xr, wr, br = (t.double().requires_grad_(True) for t in (x, wt, b))
+    yr = ACT[act](F.conv2d(xr, wr, br, padding=(k[0] // 2, k[1] // 2)))
+    yr.backward(gy.double())
+    # ours
+    xd, wd, bd = (t.to(DEV).requires_grad_(True) for t in (x, wt, b))
+    y = grad.conv2d(xd, wd, bd, act)
+    y.backward(gy.to(DEV))
+    torch.cuda.synchronize()
+
+    def rel(a, r):
+        return float((a.double().cpu() - r).abs().max() / r.abs().max())
+    print(f"{ci}->{co} {k} {act}: y {rel(y.detach(), yr.detach()):.2e} dx {rel(xd.grad, xr.grad):.2e} "
+          f"dW {rel(wd.grad, wr.grad):.2e} db {rel(bd.grad, br.grad):.2e}")
+    assert rel(y.detach(), yr.detach()) < 1e-5
+    assert rel(xd.grad, xr.grad) < 1e-5
+    assert rel(wd.grad, wr.grad) < 2e-5
+    assert rel(bd.grad, br.grad) < 2e-5
+
+
+def test_conv2d_without_bias_and_partial_grads():
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(1, 32, 16, 24, generator=g).to(DEV)
+    wt = (torch.randn(32, 32, 3, 3, generator=g) / 17.0).to(DEV).requires_grad_(True)
+    y = grad.conv2d(x, wt, None, "relu")          # x does not require grad: no dx conv is run
+    y.sum().backward()
+    ref_w = wt.detach().double().cpu().requires_grad_(True)
+    torch.relu(F.conv2d(x.double().cpu(), ref_w, None, padding=1)).sum().backward()
+    assert float((wt.grad.double().cpu() - ref_w.grad).abs().max() / ref_w.grad.abs().max()) < 2e-5
+
+
+def test_conv2d_refuses_cpu_and_even_kernels():
+    from demfi_b200._abi import DemfiError
+    with pytest.raises(DemfiError):
+        grad.conv2d(torch.zeros(1, 8, 8, 8), torch.zeros(8, 8, 3, 3))
+    with pytest.raises(ValueError):
+        grad.conv2d(torch.zeros(1, 8, 8, 8, device=DEV), torch.zeros(8, 8, 4, 4, device=DEV))
