@@ -211,6 +211,19 @@ int demfi_conv2d_wgrad(const float* x, int32_t x_ld, int32_t Cin, const float* d
 int demfi_act_backward(const float* dy, int32_t dy_ld, const float* y, int32_t y_ld, int64_t npix, int32_t C, int32_t act,
                        float* out, int32_t out_ld, void* stream);
 
+/* Backward of demfi_bwarp_blend (same a, b, flow, occ, t as the forward call; dout = gradient of its output): da, db are
+ * ACCUMULATED with fp32 atomics at the four bilinear corners (zero them first; either may be NULL), dflow (4 channels:
+ * d/d flow of the a-warp x, y, then of the b-warp) and docc (1 channel, gradient of the occlusion LOGIT) are written.  The
+ * validity mask of bwarp is piecewise constant and only gates the gradients (autograd through DeMFInet.py:757-766). */
+int demfi_bwarp_blend_backward(const float* a, int32_t a_ld, const float* b, int32_t b_ld, const float* flow, int32_t flow_ld,
+                               const float* occ, int32_t occ_ld, const float* t, const float* dout, int32_t dout_ld, int32_t B,
+                               int32_t H, int32_t W, int32_t C, float* da, int32_t da_ld, float* db, int32_t db_ld, float* dflow,
+                               int32_t dflow_ld, float* docc, int32_t docc_ld, void* stream);
+/* Backward of demfi_fgac_sample: drefk accumulated (atomics, may be NULL), dflow (2 channels) written. */
+int demfi_fgac_sample_backward(const float* refk, int32_t refk_ld, const float* flow, int32_t flow_ld, const float* dout,
+                               int32_t dout_ld, int32_t B, int32_t H, int32_t W, int32_t C, float* drefk, int32_t drefk_ld,
+                               float* dflow, int32_t dflow_ld, void* stream);
+
 /* ---- evaluation metrics (the consumer right after the hot path) ------------------------- */
 /* PSNR / SSIM sums of predicted frames against their targets as the reference's evaluation loop computes them
  * (main.py:763-771 with utils.py:652-705, 718-721): pred, target are NCHW [B,C,H,W] fp32 in [-1,1] on the device (what

@@ -63,3 +63,72 @@ def test_conv2d_refuses_cpu_and_even_kernels():
         grad.conv2d(torch.zeros(1, 8, 8, 8), torch.zeros(8, 8, 3, 3))
     with pytest.raises(ValueError):
         grad.conv2d(torch.zeros(1, 8, 8, 8, device=DEV), torch.zeros(8, 8, 4, 4, device=DEV))
+
+
+# ---------------------------------------------------------------------------------------------- warps
+import os
+
+import numpy as np
+
+from demfi_b200 import _abi as A
+from gpu_util import from_nhwc, nhwc, stream
+
+WARP_GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "warp_grads.npz"))
+
+
+def _close(got, want, what, tol=5e-6):
+    d = float((got - want).abs().max())
+    scale = max(1.0, float(want.abs().max()))
+    print(f"{what}: max-abs {d:.2e} (scale {scale:.1f})")
+    assert d < tol * scale, (what, d)
+
+
+@pytest.mark.parametrize("tag,C,ld", [("c64", 64, 64), ("c64", 64, 72), ("c3", 3, 4), ("c3", 3, 36)])
+def test_bwarp_blend_backward_matches_reference_autograd(tag, C, ld):
+    """gradients of bwarp + Eq.(2) w.r.t. both sources, the four flow channels and the occlusion logit against autograd
+    through the reference's own functions (tests/golden/warp_grads.npz): integer displacements, out-of-image targets and the
+    0.999 validity band included; vector (C % 4 == 0) and scalar (3-channel pixel warp) paths, dense and strided rows"""
+    T = lambda k: torch.from_numpy(WARP_GOLD[f"blend_{tag}_{k}"])
+    a, b, fl, occ, gy = T("a"), T("b"), T("flow"), T("occ"), T("gy")
+    n, _, h, w = a.shape
+    ab, _ = nhwc(a, ld)
+    bb, _ = nhwc(b, ld)
+    gb, _ = nhwc(gy, ld)
+    fb, _ = nhwc(fl, 8)
+    ob, _ = nhwc(occ, 4)
+    da = torch.zeros(n, h, w, ld, device=DEV)
+    db = torch.zeros(n, h, w, ld, device=DEV)
+    dfl = torch.full((n, h, w, 4), 7.0, device=DEV)
+    doc = torch.full((n, h, w, 4), 7.0, device=DEV)
+    tv = T("t").reshape(-1).to(DEV)
+    A.check(A.lib().demfi_bwarp_blend_backward(ab.data_ptr(), ld, bb.data_ptr(), ld, fb.data_ptr(), 8, ob.data_ptr(), 4, tv.data_ptr(),
+                                               gb.data_ptr(), ld, n, h, w, C, da.data_ptr(), ld, db.data_ptr(), ld, dfl.data_ptr(), 4,
+                                               doc.data_ptr(), 4, stream()), "bwarp_blend_backward")
+    torch.cuda.synchronize()
+    _close(from_nhwc(da, C), T("da"), "da")
+    _close(from_nhwc(db, C), T("db"), "db")
+    _close(from_nhwc(dfl, 4), T("dflow"), "dflow", 1e-5)
+    _close(from_nhwc(doc, 1), T("docc"), "docc", 1e-5)
+    assert float(da[..., C:].abs().max() if ld > C else 0.0) == 0.0      # nothing scattered into the padding channels
+    assert float((doc[..., 1:] - 7.0).abs().max()) == 0.0
+
+
+def test_fgac_sample_backward_matches_reference_autograd():
+    T = lambda k: torch.from_numpy(WARP_GOLD[f"sample_{k}"])
+    refk, fl, gy = T("refk"), T("flow"), T("gy")
+    n, C, h, w = refk.shape
+    rb, _ = nhwc(refk)
+    gb, _ = nhwc(gy)
+    fb, _ = nhwc(fl, 8)
+    dr = torch.zeros(n, h, w, C, device=DEV)
+    dfl = torch.zeros(n, h, w, 2, device=DEV)
+    A.check(A.lib().demfi_fgac_sample_backward(rb.data_ptr(), C, fb.data_ptr(), 8, gb.data_ptr(), C, n, h, w, C, dr.data_ptr(), C,
+                                               dfl.data_ptr(), 2, stream()), "fgac_sample_backward")
+    torch.cuda.synchronize()
+    _close(from_nhwc(dr, C), T("drefk"), "drefk")
+    _close(from_nhwc(dfl, 2), T("dflow"), "dflow", 1e-5)
+    # value gradients only (no flow gradient requested), accumulated on top of what is there
+    A.check(A.lib().demfi_fgac_sample_backward(rb.data_ptr(), C, fb.data_ptr(), 8, gb.data_ptr(), C, n, h, w, C, dr.data_ptr(), C,
+                                               None, 0, stream()), "fgac_sample_backward")
+    torch.cuda.synchronize()
+    _close(from_nhwc(dr, C), 2 * T("drefk"), "drefk accumulated", 1e-5)

@@ -50,6 +50,32 @@ def test_oracle_visualisation_tuple_matches_reference_golden(state_dict):
     assert float((res[5][4][1] - torch.from_numpy(g["flow_10"])).abs().max()) < ORACLE_TOL
 
 
+def test_oracle_autograd_matches_reference_autograd_on_the_warps():
+    """Gradients through the oracle's bwarp + Eq.(2) blend and bilinear gather equal autograd through the reference's own
+    `bwarp` / `bilinear_sampler` (tests/golden/warp_grads.npz, oracle/gen_golden_grads.py): this is what the CUDA backward
+    operators are checked against."""
+    import numpy as np
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "warp_grads.npz"))
+    for tag in ("c64", "c3"):
+        T = lambda k, rg=False: torch.tensor(g[f"blend_{tag}_{k}"], requires_grad=rg)
+        a, b, fl, occ = T("a", True), T("b", True), T("flow", True), T("occ", True)
+        out = O.eq2_blend(a, fl[:, 0:2], b, fl[:, 2:4], occ, T("t").view(-1, 1, 1, 1))
+        (out * T("gy")).sum().backward()
+        assert float((out - T("out")).abs().max()) < 2e-6
+        for name, got in (("da", a.grad), ("db", b.grad), ("dflow", fl.grad), ("docc", occ.grad)):
+            want = T(name)
+            assert float((got - want).abs().max()) < 2e-6 * max(1.0, float(want.abs().max())), (tag, name)
+    T = lambda k, rg=False: torch.tensor(g[f"sample_{k}"], requires_grad=rg)
+    refk, fl = T("refk", True), T("flow", True)
+    H, W = refk.shape[-2:]
+    px = ((2 * fl[:, 0] / (W - 1) - 1) + 1.0) / 2.0 * (W - 1)
+    py = ((2 * fl[:, 1] / (H - 1) - 1) + 1.0) / 2.0 * (H - 1)
+    out, _ = O.bilinear_gather(refk, px, py)
+    (out * T("gy")).sum().backward()
+    assert float((refk.grad - T("drefk")).abs().max()) < 2e-6
+    assert float((fl.grad - T("dflow")).abs().max()) < 2e-6 * float(T("dflow").abs().max())
+
+
 def test_bilinear_gather_is_grid_sample_align_corners_true():
     g = torch.Generator().manual_seed(0)
     img = torch.randn(2, 5, 9, 13, generator=g)
