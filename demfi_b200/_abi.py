@@ -75,6 +75,7 @@ SYMBOLS = {
     "demfi_bwarp_blend_backward": (i32, [vp, i32, vp, i32, vp, i32, vp, i32, vp, vp, i32, i32, i32, i32, i32, vp, i32, vp, i32,
                                          vp, i32, vp, i32, vp]),
     "demfi_fgac_sample_backward": (i32, [vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, vp, i32, vp, i32, vp]),
+    "demfi_cfr_backward": (i32, [vp, i32, vp, vp, vp, i32, i32, i32, i32, vp, vp, i32, vp]),
     "demfi_frame_metrics_workspace": (C.c_int64, [i32, i32, i32, i32]),
     "demfi_frame_metrics": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, C.c_int64, vp, vp]),
     "demfi_launch_count": (C.c_uint64, []),

@@ -1,6 +1,7 @@
 // Backward of the bilinear-sampling operators of the hot path (training row; first correct path):
 //   * bwarp + Eq.(2) blend   (forward: ops.cu bwarp_blend_kernel; reference: bwarp DeMFInet.py:732-766, blend :66-71/:90-93/:146-149)
 //   * FGAC sampling          (forward: ops.cu fgac_sample_kernel; reference: bilinear_sampler DeMFInet.py:499-514)
+//   * complementary flow reversal (Gaussian forward splat), further down
 // What the reference gets from autograd through F.grid_sample(bilinear, zeros, align_corners=True):
 //   value gradient   d src[corner k] += g * w_k                    (scatter, fp32 red.global.add; zero the buffers first)
 //   coordinate grad  dS/dpx = wy0 (v_ne - v_nw) + wy1 (v_se - v_sw), dS/dpy = wx0 (v_sw - v_nw) + wx1 (v_se - v_ne),
@@ -182,6 +183,84 @@ fgac_sample_bwd_kernel(const float* __restrict__ refk, int refk_ld, const float*
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Backward of the complementary flow reversal (forward: ops.cu cfr_splat_kernel + cfr_finalize_kernel; reference:
+// CFR_flow_t_align + fwarp + sample_one, DeMFInet.py:606-729).  The forward SCATTERS v * w_k and w_k to four targets, so the
+// backward GATHERS -- no atomics:
+//   1. per target pixel (cfr_finalize_bwd): from g = d/d(flow_t0, flow_t1), the forward accumulators and t, the gradients of
+//      the accumulators {dA01.x, dA01.y, dn0, -, dA10.x, dA10.y, dn1, -} (same layout as acc).  With u = the combination
+//      before the division and n = (1-t) n0 + t n1 > 0: du = g / n, dn = -(g . u) / n^2 (the mask of :615 is detached).
+//   2. per source pixel (cfr_splat_bwd): for its four targets k (floor() taken exactly as in the forward, in-image only):
+//      d/dv += w_k dA[k];  d/dw_k = v . dA[k] + dn[k];  w_k = exp(-((dy-cy_k)^2 + (dx-cx_k)^2)) => d w_k/d dx = -2 (dx-cx_k) w_k;
+//      the displacement is s * v (s = t or 1-t), so d/dv += s * d/d(dx, dy).
+__global__ void __launch_bounds__(256)
+cfr_finalize_bwd_kernel(const float* __restrict__ acc, const float* __restrict__ tv, const float* __restrict__ gout, int gout_ld,
+                        int B, int H, int W, float* __restrict__ gacc) {
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= (long long)B * H * W) return;
+  const int n = (int)(pix / ((long long)W * H));
+  const float t = __ldg(tv + n);
+  const float4 a = __ldg((const float4*)(acc + pix * 8));
+  const float4 b = __ldg((const float4*)(acc + pix * 8 + 4));
+  const float* gp = gout + pix * gout_ld;
+  float4 g = make_float4(__ldg(gp), __ldg(gp + 1), __ldg(gp + 2), __ldg(gp + 3));
+  const float k00 = -(1.0f - t) * t, k01 = t * t, k10 = (1.0f - t) * (1.0f - t), k11 = t * (1.0f - t);
+  const float ux = k00 * a.x + k01 * b.x, uy = k00 * a.y + k01 * b.y, uz = k10 * a.x - k11 * b.x, uw = k10 * a.y - k11 * b.y;
+  const float norm = (1.0f - t) * a.z + t * b.z;
+  float dn = 0.0f;
+  if (norm > 0.0f) {
+    const float rn = 1.0f / norm;
+    dn = -(g.x * ux + g.y * uy + g.z * uz + g.w * uw) * rn * rn;
+    g.x *= rn; g.y *= rn; g.z *= rn; g.w *= rn;
+  }
+  st4(gacc + pix * 8, make_float4(k00 * g.x + k10 * g.z, k00 * g.y + k10 * g.w, (1.0f - t) * dn, 0.0f));
+  st4(gacc + pix * 8 + 4, make_float4(k01 * g.x - k11 * g.z, k01 * g.y - k11 * g.w, t * dn, 0.0f));
+}
+
+__device__ __forceinline__ void splat_one_bwd(const float* __restrict__ gacc, int n, int H, int W, int r, int c, float vx, float vy,
+                                              float s, int slot, float& dvx, float& dvy) {
+  const float dx = s * vx, dy = s * vy;
+  const float fy = floorf(dy), fx = floorf(dx);
+  const int iy = (int)fminf(fmaxf(fy, -(float)H - 2.f), (float)H + 2.f);
+  const int ix = (int)fminf(fmaxf(fx, -(float)W - 2.f), (float)W + 2.f);
+  float gvx = 0.f, gvy = 0.f, gdx = 0.f, gdy = 0.f;
+#pragma unroll
+  for (int oy = 0; oy < 2; ++oy)
+#pragma unroll
+    for (int ox = 0; ox < 2; ++ox) {
+      const float cy = fy + (float)oy, cx = fx + (float)ox;
+      const float wgt = expf(-((dy - cy) * (dy - cy) + (dx - cx) * (dx - cx)));
+      const int tr = r + iy + oy, tc = c + ix + ox;
+      if (tr >= 0 && tr < H && tc >= 0 && tc < W) {
+        const float4 G = __ldg((const float4*)(gacc + (((size_t)n * H + tr) * W + tc) * 8 + slot));
+        gvx += wgt * G.x;
+        gvy += wgt * G.y;
+        const float gw = (vx * G.x + vy * G.y + G.z) * wgt;
+        gdx += gw * (-2.0f * (dx - cx));
+        gdy += gw * (-2.0f * (dy - cy));
+      }
+    }
+  dvx = gvx + s * gdx;
+  dvy = gvy + s * gdy;
+}
+
+__global__ void __launch_bounds__(256)
+cfr_splat_bwd_kernel(const float* __restrict__ fo, int fo_ld, const float* __restrict__ tv, const float* __restrict__ gacc, int B,
+                     int H, int W, float* __restrict__ dfo, int dfo_ld) {
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= (long long)B * H * W) return;
+  const int c = (int)(pix % W);
+  const int r = (int)((pix / W) % H);
+  const int n = (int)(pix / ((long long)W * H));
+  const float t = __ldg(tv + n);
+  const float4 f = __ldg((const float4*)(fo + pix * fo_ld));
+  float4 d;
+  splat_one_bwd(gacc, n, H, W, r, c, f.x, f.y, t, 0, d.x, d.y);
+  splat_one_bwd(gacc, n, H, W, r, c, f.z, f.w, 1.0f - t, 4, d.z, d.w);
+  float* o = dfo + pix * dfo_ld;
+  o[0] = d.x; o[1] = d.y; o[2] = d.z; o[3] = d.w;
+}
+
 static inline bool vec_ok(int C, std::initializer_list<int> lds, std::initializer_list<const void*> ptrs) {
   if (C % 4 != 0) return false;
   for (int ld : lds)
@@ -231,6 +310,20 @@ int demfi_fgac_sample_backward(const float* refk, int32_t refk_ld, const float* 
         refk, refk_ld, flow, flow_ld, dout, dout_ld, B, H, W, C, drefk, drefk_ld, dflow, dflow_ld);
   }
   DEMFI_LAUNCH_CHECK("fgac_sample_backward");
+  return 0;
+}
+
+int demfi_cfr_backward(const float* fo, int32_t fo_ld, const float* t, const float* acc, const float* gout, int32_t gout_ld,
+                       int32_t B, int32_t H, int32_t W, float* gacc, float* dfo, int32_t dfo_ld, void* stream) {
+  if (check_device()) return 3;
+  DEMFI_REQUIRE(fo && t && acc && gout && gacc && dfo, "cfr_backward: null pointer");
+  DEMFI_REQUIRE(B > 0 && H > 0 && W > 0 && fo_ld >= 4 && fo_ld % 4 == 0 && ((uintptr_t)fo % 16) == 0 && gout_ld >= 4 && dfo_ld >= 4 &&
+                    ((uintptr_t)acc % 16) == 0 && ((uintptr_t)gacc % 16) == 0, "cfr_backward: bad shape or alignment");
+  const long long npix = (long long)B * H * W;
+  cfr_finalize_bwd_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, (cudaStream_t)stream>>>(acc, t, gout, gout_ld, B, H, W, gacc);
+  DEMFI_LAUNCH_CHECK("cfr_finalize_backward");
+  cfr_splat_bwd_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, (cudaStream_t)stream>>>(fo, fo_ld, t, gacc, B, H, W, dfo, dfo_ld);
+  DEMFI_LAUNCH_CHECK("cfr_splat_backward");
   return 0;
 }
 

@@ -224,6 +224,13 @@ int demfi_fgac_sample_backward(const float* refk, int32_t refk_ld, const float* 
                                int32_t dout_ld, int32_t B, int32_t H, int32_t W, int32_t C, float* drefk, int32_t drefk_ld,
                                float* dflow, int32_t dflow_ld, void* stream);
 
+/* Backward of demfi_cfr_splat + demfi_cfr_finalize: fo, t as in the forward; acc = the accumulators the forward splat left
+ * ([B,H,W,8], unchanged by finalize); gout = gradient of finalize's 4-channel output (flow_t0, flow_t1); gacc = scratch
+ * [B,H,W,8] (written); dfo = gradient w.r.t. the 4 channels (flow_01, flow_10) of fo (written).  Gathers only, no atomics;
+ * floor() is taken exactly as in the forward and has no gradient (autograd through DeMFInet.py:606-729). */
+int demfi_cfr_backward(const float* fo, int32_t fo_ld, const float* t, const float* acc, const float* gout, int32_t gout_ld,
+                       int32_t B, int32_t H, int32_t W, float* gacc, float* dfo, int32_t dfo_ld, void* stream);
+
 /* ---- evaluation metrics (the consumer right after the hot path) ------------------------- */
 /* PSNR / SSIM sums of predicted frames against their targets as the reference's evaluation loop computes them
  * (main.py:763-771 with utils.py:652-705, 718-721): pred, target are NCHW [B,C,H,W] fp32 in [-1,1] on the device (what

@@ -2,7 +2,7 @@
 
 Gradient goldens for the bilinear-sampling operators of the hot path, from torch autograd through the UNMODIFIED reference
 functions `bwarp` (DeMFInet.py:732-766) + the Eq.(2) expression of `DeMFInet.forward` (:64-71) and `bilinear_sampler`
-(:499-514), on seeded inputs that include integer displacements, out-of-image targets and the 0.999 validity band.
+(:499-514) and `CFR_flow_t_align` (:606-729), on seeded inputs that include integer displacements, out-of-image targets and the 0.999 validity band.
 Writes tests/golden/warp_grads.npz (inputs, upstream gradient, and the gradients w.r.t. every input).
 
     python oracle/gen_golden_grads.py
@@ -61,6 +61,21 @@ def main():
     (smp * gy).sum().backward()
     for k, v in dict(refk=refk, flow=fl, gy=gy, out=smp, drefk=refk.grad, dflow=fl.grad).items():
         out[f"sample_{k}"] = v.detach().numpy()
+    # complementary flow reversal (Gaussian forward splat), DeMFInet.py:606-729
+    n, h, w = 2, 12, 16
+    f01 = (rng.standard_normal((n, 2, h, w)) * 2.5).astype(np.float32)
+    f10 = (rng.standard_normal((n, 2, h, w)) * 2.5).astype(np.float32)
+    f01[:, :, 0:2, :] = np.round(f01[:, :, 0:2, :]) * 8.0 / 3.0    # t * f lands on integers for t = 0.375: the floor() edge
+    f10[:, :, 2, :] = 0.0
+    f01[:, :, 3, 0:3] = 300.0                                        # splats outside the image
+    f01, f10 = torch.tensor(f01, requires_grad=True), torch.tensor(f10, requires_grad=True)
+    t = torch.tensor([[0.375], [0.75]])
+    g0 = torch.tensor(rng.standard_normal((n, 2, h, w)).astype(np.float32))
+    g1 = torch.tensor(rng.standard_normal((n, 2, h, w)).astype(np.float32))
+    ft0, ft1 = ref.CFR_flow_t_align(dev, f01, f10, t[:, :, None, None])
+    ((ft0 * g0).sum() + (ft1 * g1).sum()).backward()
+    for k, v in dict(f01=f01, f10=f10, t=t, g0=g0, g1=g1, ft0=ft0, ft1=ft1, df01=f01.grad, df10=f10.grad).items():
+        out[f"cfr_{k}"] = v.detach().numpy()
     np.savez_compressed(os.path.join(GOLD, "warp_grads.npz"), **out)
     for k, v in out.items():
         print(k, v.shape, float(np.abs(v).max()))

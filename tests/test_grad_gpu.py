@@ -132,3 +132,28 @@ def test_fgac_sample_backward_matches_reference_autograd():
                                                None, 0, stream()), "fgac_sample_backward")
     torch.cuda.synchronize()
     _close(from_nhwc(dr, C), 2 * T("drefk"), "drefk accumulated", 1e-5)
+
+
+def test_cfr_backward_matches_reference_autograd():
+    """gradient of the complementary flow reversal w.r.t. flow_01 / flow_10 against autograd through the reference's
+    CFR_flow_t_align (put_ with accumulate, floor without gradient): displacements landing exactly on integers, splats leaving
+    the image, two different t in the batch"""
+    T = lambda k: torch.from_numpy(WARP_GOLD[f"cfr_{k}"])
+    f01, f10 = T("f01"), T("f10")
+    n, _, h, w = f01.shape
+    fo, _ = nhwc(torch.cat([f01, f10], 1), 8)
+    gb, _ = nhwc(torch.cat([T("g0"), T("g1")], 1), 4)
+    tv = T("t").reshape(-1).to(DEV)
+    acc = torch.zeros(n, h, w, 8, device=DEV)
+    out = torch.zeros(n, h, w, 4, device=DEV)
+    lib = A.lib()
+    A.check(lib.demfi_cfr_splat(fo.data_ptr(), 8, tv.data_ptr(), n, h, w, acc.data_ptr(), stream()), "splat")
+    A.check(lib.demfi_cfr_finalize(acc.data_ptr(), tv.data_ptr(), n, h, w, out.data_ptr(), 4, stream()), "finalize")
+    gacc = torch.empty(n, h, w, 8, device=DEV)
+    dfo = torch.full((n, h, w, 8), 7.0, device=DEV)
+    A.check(lib.demfi_cfr_backward(fo.data_ptr(), 8, tv.data_ptr(), acc.data_ptr(), gb.data_ptr(), 4, n, h, w, gacc.data_ptr(),
+                                   dfo.data_ptr(), 8, stream()), "cfr_backward")
+    torch.cuda.synchronize()
+    _close(from_nhwc(out, 4), torch.cat([T("ft0"), T("ft1")], 1), "forward flow_t0|flow_t1", 2e-6)
+    _close(from_nhwc(dfo, 4), torch.cat([T("df01"), T("df10")], 1), "d flow_01|flow_10", 5e-6)
+    assert float((dfo[..., 4:] - 7.0).abs().max()) == 0.0
