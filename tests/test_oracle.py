@@ -74,6 +74,13 @@ def test_oracle_autograd_matches_reference_autograd_on_the_warps():
     (out * T("gy")).sum().backward()
     assert float((refk.grad - T("drefk")).abs().max()) < 2e-6
     assert float((fl.grad - T("dflow")).abs().max()) < 2e-6 * float(T("dflow").abs().max())
+    # complementary flow reversal: put_(accumulate=True) splat, floor() without gradient, detached norm mask
+    T = lambda k, rg=False: torch.tensor(g[f"cfr_{k}"], requires_grad=rg)
+    f01, f10 = T("f01", True), T("f10", True)
+    ft0, ft1 = O.cfr_flow_t_align(f01, f10, T("t").view(-1, 1, 1, 1))
+    ((ft0 * T("g0")).sum() + (ft1 * T("g1")).sum()).backward()
+    assert float((ft0 - T("ft0")).abs().max()) < 2e-6 and float((ft1 - T("ft1")).abs().max()) < 2e-6
+    assert float((f01.grad - T("df01")).abs().max()) < 5e-6 and float((f10.grad - T("df10")).abs().max()) < 5e-6
 
 
 def test_bilinear_gather_is_grid_sample_align_corners_true():
