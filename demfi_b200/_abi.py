@@ -76,6 +76,11 @@ SYMBOLS = {
                                          vp, i32, vp, i32, vp]),
     "demfi_fgac_sample_backward": (i32, [vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, vp, i32, vp, i32, vp]),
     "demfi_cfr_backward": (i32, [vp, i32, vp, vp, vp, i32, i32, i32, i32, vp, vp, i32, vp]),
+    "demfi_fgac_blend_backward": (i32, [vp, i32, vp, i32, vp, i32, vp, i32, C.c_int64, i32, vp, i32, vp, i32, vp, i32, vp]),
+    "demfi_upsample2x_backward": (i32, [vp, i32, i32, i32, i32, i32, vp, i32, vp]),
+    "demfi_l1_sum_workspace": (C.c_int64, [C.c_int64]),
+    "demfi_l1_sum": (i32, [vp, vp, C.c_int64, C.c_float, vp, vp, C.c_int64, vp, vp]),
+    "demfi_adam_step": (i32, [vp, vp, vp, vp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, i32, vp]),
     "demfi_frame_metrics_workspace": (C.c_int64, [i32, i32, i32, i32]),
     "demfi_frame_metrics": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, C.c_int64, vp, vp]),
     "demfi_launch_count": (C.c_uint64, []),

@@ -1,0 +1,130 @@
+"""Host side of the training step around the model (first slice): the pieces of `main.py:367-512`
+that are not the network itself, over the C ABI.
+
+  * `rec_losses`            the L1 reconstruction losses Eq.(9)-(10) of main.py:404-440 (same names: total, rec_D1, rec_D2)
+                            and, fused into the same pass, the gradients w.r.t. every predicted frame
+  * `Adam`                  torch.optim.Adam(params, lr, betas=(0.9, 0.999), weight_decay) of main.py:179-180: same state
+                            (`exp_avg`, `exp_avg_sq`, `step`), same update, one `demfi_adam_step` launch per parameter tensor
+  * `allreduce_gradients`   the one exchange step of data-parallel training: the 260 gradient tensors
+                            (29.6 MB) flattened into one bucket, summed over ranks with `torch.distributed.all_reduce` (NCCL over
+                            NVLink on the GPUs; gloo in the CPU test) and averaged
+
+No CPU fallback for the kernels: `rec_losses` and `Adam.step` raise on CPU tensors.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Sequence
+
+import torch
+
+from . import _abi as A
+
+_WS: Dict[int, torch.Tensor] = {}
+
+
+def _ws(dev, nbytes):
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    t = _WS.get(key)
+    if t is None or t.numel() * 8 < nbytes:
+        t = torch.empty((nbytes + 7) // 8, dtype=torch.float64, device=dev)
+        _WS[key] = t
+    return t
+
+
+def _l1_term(pred: torch.Tensor, target: torch.Tensor, grad_scale: float, want_grad: bool, out: torch.Tensor):
+    if not (pred.is_cuda and target.is_cuda):
+        raise A.DemfiError("demfi_b200.train.rec_losses runs on the GPU only (no CPU fallback)")
+    if pred.shape != target.shape:
+        raise ValueError("prediction and ground truth must have the same shape")
+    pred, target = pred.detach().contiguous().float(), target.detach().contiguous().float()
+    n = pred.numel()
+    lib = A.lib()
+    need = lib.demfi_l1_sum_workspace(n)
+    ws = _ws(pred.device, need)
+    grad = torch.empty_like(pred) if want_grad else None
+    with torch.cuda.device(pred.device):
+        A.check(lib.demfi_l1_sum(pred.data_ptr(), target.data_ptr(), n, grad_scale / n, grad.data_ptr() if want_grad else None,
+                                 ws.data_ptr(), ws.numel() * 8, out.data_ptr(), torch.cuda.current_stream().cuda_stream), "demfi_l1_sum")
+    return grad
+
+
+def rec_losses(sharps_prime: Sequence[torch.Tensor], sharps_final: Sequence[Sequence[torch.Tensor]], S0_GT, S1_GT, St_GT,
+               rec_D1_lambda: float = 1.0, rec_D2_lambda: float = 1.0, with_grads: bool = False):
+    """(total_loss, rec_D1_loss, rec_D2_loss) as Python floats -- `main.py:404-440` -- and, with_grads, also
+    (grads_prime[3], grads_final[N][3]) = d total / d each predicted frame."""
+    gts = [S0_GT, S1_GT, St_GT]
+    dev = sharps_prime[0].device
+    n_terms = 3 * (1 + len(sharps_final))
+    sums = torch.zeros(n_terms, dtype=torch.float64, device=dev)
+    g_prime: List[torch.Tensor] = []
+    g_final: List[List[torch.Tensor]] = []
+    k = 0
+    for idx in range(3):
+        g_prime.append(_l1_term(sharps_prime[idx], gts[idx], rec_D1_lambda / 3.0, with_grads, sums[k:k + 1]))
+        k += 1
+    for tri in sharps_final:
+        g_final.append([])
+        for idx in range(3):
+            g_final[-1].append(_l1_term(tri[idx], gts[idx], rec_D2_lambda / 3.0, with_grads, sums[k:k + 1]))
+            k += 1
+    s = sums.cpu().tolist()                       # one read-back for all terms
+    numel = [t.numel() for t in gts]
+    means = [s[i] / numel[i % 3] for i in range(n_terms)]
+    rec_D1 = rec_D1_lambda * (means[0] + means[1] + means[2]) / 3.0
+    rec_D2 = sum(rec_D2_lambda * (means[3 + 3 * i] + means[4 + 3 * i] + means[5 + 3 * i]) / 3.0 for i in range(len(sharps_final)))
+    if with_grads:
+        return rec_D1 + rec_D2, rec_D1, rec_D2, g_prime, g_final
+    return rec_D1 + rec_D2, rec_D1, rec_D2
+
+
+class Adam:
+    """torch.optim.Adam for fp32 CUDA parameters through `demfi_adam_step` (no amsgrad, no foreach grouping)."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        self.params = [p for p in params]
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.state: Dict[int, dict] = {}
+        self.param_groups = [{"params": self.params, "lr": lr}]    # `optimizer.param_groups[0]['lr']`, main.py:385
+
+    def zero_grad(self):
+        for p in self.params:
+            p.grad = None
+
+    @torch.no_grad()
+    def step(self):
+        lib = A.lib()
+        lr = self.param_groups[0]["lr"]
+        for i, p in enumerate(self.params):
+            if p.grad is None:
+                continue
+            if not p.is_cuda:
+                raise A.DemfiError("demfi_b200.train.Adam updates CUDA parameters only (no CPU fallback)")
+            st = self.state.setdefault(i, {"step": 0, "exp_avg": torch.zeros_like(p), "exp_avg_sq": torch.zeros_like(p)})
+            st["step"] += 1
+            g = p.grad.contiguous()
+            assert p.is_contiguous() and p.dtype == torch.float32 and g.dtype == torch.float32
+            with torch.cuda.device(p.device):
+                A.check(lib.demfi_adam_step(p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel(),
+                                            lr, self.betas[0], self.betas[1], self.eps, self.weight_decay, st["step"],
+                                            torch.cuda.current_stream().cuda_stream), "demfi_adam_step")
+
+
+def allreduce_gradients(params, world_size: int = None, group=None) -> int:
+    """Average the gradients over the ranks of the job: one flat fp32 bucket, one `all_reduce(SUM)`, scaled by 1/world and
+    copied back.  Returns the number of bytes exchanged per rank (the bucket size).  A no-op without torch.distributed."""
+    import torch.distributed as dist
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return 0
+    if not (dist.is_available() and dist.is_initialized()):
+        return 0
+    world = world_size or dist.get_world_size(group)
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat.mul_(1.0 / world)
+    o = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[o:o + n].view_as(g))
+        o += n
+    return flat.numel() * 4

@@ -231,6 +231,26 @@ int demfi_fgac_sample_backward(const float* refk, int32_t refk_ld, const float* 
 int demfi_cfr_backward(const float* fo, int32_t fo_ld, const float* t, const float* acc, const float* gout, int32_t gout_ld,
                        int32_t B, int32_t H, int32_t W, float* gacc, float* dfo, int32_t dfo_ld, void* stream);
 
+/* Eq.(4) backward (forward: demfi_fgac_blend, out = w*src + (1-w)*e): dw[p] = sum_c gout*(src - e) (written, 1 channel),
+ * dsrc = gout*w, de = gout*(1-w) (written; any of the three may be NULL). */
+int demfi_fgac_blend_backward(const float* w, int32_t w_ld, const float* src, int32_t src_ld, const float* e, int32_t e_ld,
+                              const float* gout, int32_t gout_ld, int64_t npix, int32_t C, float* dw, int32_t dw_ld, float* dsrc,
+                              int32_t dsrc_ld, float* de, int32_t de_ld, void* stream);
+/* nn.UpsamplingNearest2d(2) backward: gsrc[n,y,x,:] = sum of gdst over the 2x2 children (written). */
+int demfi_upsample2x_backward(const float* gdst, int32_t gdst_ld, int32_t B, int32_t Hs, int32_t Ws, int32_t C, float* gsrc,
+                              int32_t gsrc_ld, void* stream);
+/* One term of the reconstruction losses (nn.L1Loss, main.py:404-440): out[0] (device double) = sum_i |pred[i] - target[i]|
+ * over n contiguous elements, fixed summation order; when grad != NULL also grad[i] = grad_scale * sign(pred[i] - target[i])
+ * (what autograd sends back for  grad_scale * n * mean|.|;  the caller folds lambda / 3 / n into grad_scale).
+ * workspace: at least demfi_l1_sum_workspace(n) bytes of device memory. */
+int64_t demfi_l1_sum_workspace(int64_t n);
+int demfi_l1_sum(const float* pred, const float* target, int64_t n, float grad_scale, float* grad, void* workspace,
+                 int64_t workspace_bytes, double* out, void* stream);
+/* torch.optim.Adam (main.py:179-180), one parameter tensor, in place: g' = grad + weight_decay*param; exp_avg, exp_avg_sq
+ * updated; param -= lr / (1 - beta1^step) * exp_avg / (sqrt(exp_avg_sq) / sqrt(1 - beta2^step) + eps).  step counts from 1. */
+int demfi_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2,
+                    float eps, float weight_decay, int32_t step, void* stream);
+
 /* ---- evaluation metrics (the consumer right after the hot path) ------------------------- */
 /* PSNR / SSIM sums of predicted frames against their targets as the reference's evaluation loop computes them
  * (main.py:763-771 with utils.py:652-705, 718-721): pred, target are NCHW [B,C,H,W] fp32 in [-1,1] on the device (what

@@ -213,3 +213,39 @@ def test_folder_runner_shards_pairs_across_ranks(tmp_path):
     for name in os.listdir(roots[0]):
         if "_" in name:  # interpolated frames: one writer each (deblurred frames are written by two neighbouring pairs)
             assert np.array_equal(cv2.imread(os.path.join(roots[0], name)), cv2.imread(os.path.join(roots[1], name))), name
+
+
+def _allreduce_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from demfi_b200.train import allreduce_gradients
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        params = [torch.nn.Parameter(torch.zeros(4, 3)), torch.nn.Parameter(torch.zeros(5)), torch.nn.Parameter(torch.zeros(2))]
+        params[0].grad = torch.full((4, 3), float(rank + 1))
+        params[1].grad = torch.arange(5, dtype=torch.float32) * (rank + 1)
+        nbytes = allreduce_gradients(params)            # params[2] has no gradient: skipped
+        q.put((rank, nbytes, params[0].grad.clone(), params[1].grad.clone(), params[2].grad))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_allreduce_two_ranks_gloo():
+    """the one exchange step of data-parallel training, world_size 2 over gloo on CPU: the flat bucket
+    is summed over ranks and averaged, tensors without a gradient stay out of the bucket"""
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_allreduce_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, nbytes, g0, g1, g2 in res:
+        assert nbytes == (12 + 5) * 4 and g2 is None
+        assert torch.equal(g0, torch.full((4, 3), 1.5)) and torch.equal(g1, torch.arange(5, dtype=torch.float32) * 1.5)

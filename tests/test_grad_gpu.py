@@ -157,3 +157,87 @@ def test_cfr_backward_matches_reference_autograd():
     _close(from_nhwc(out, 4), torch.cat([T("ft0"), T("ft1")], 1), "forward flow_t0|flow_t1", 2e-6)
     _close(from_nhwc(dfo, 4), torch.cat([T("df01"), T("df10")], 1), "d flow_01|flow_10", 5e-6)
     assert float((dfo[..., 4:] - 7.0).abs().max()) == 0.0
+
+
+# ---------------------------------------------------------------------------------------------- losses, optimiser, small ops
+def test_rec_losses_and_their_gradients():
+    """Eq.(9)-(10) of main.py:404-440 against the oracle restatement (torch L1Loss) and its autograd"""
+    from demfi_b200 import train
+    from oracle import train_oracle as TO
+    g = torch.Generator().manual_seed(11)
+    B, H, W, N = 2, 24, 40, 3
+    gts = [torch.randn(B, 3, H, W, generator=g) for _ in range(3)]
+    prime = [(gt + 0.1 * torch.randn(B, 3, H, W, generator=g)).requires_grad_(True) for gt in gts]
+    final = [[(gt + 0.05 * torch.randn(B, 3, H, W, generator=g)).requires_grad_(True) for gt in gts] for _ in range(N)]
+    final[1][2].data[0, 0, 0, :5] = gts[2][0, 0, 0, :5]          # exact zeros of the difference: sign(0) = 0
+    want = TO.rec_losses(prime, final, *gts, rec_D1_lambda=1.0, rec_D2_lambda=0.5)
+    want[0].backward()
+    d = lambda t: t.detach().to(DEV)
+    got = train.rec_losses([d(t) for t in prime], [[d(t) for t in tri] for tri in final], *[d(t) for t in gts],
+                           rec_D1_lambda=1.0, rec_D2_lambda=0.5, with_grads=True)
+    for a, b in zip(got[:3], want):
+        assert abs(a - float(b.detach())) < 1e-6 * max(1.0, abs(float(b.detach()))), (a, float(b.detach()))
+    for i in range(3):
+        assert float((got[3][i].cpu() - prime[i].grad).abs().max()) < 1e-9
+        for j in range(N):
+            assert float((got[4][j][i].cpu() - final[j][i].grad).abs().max()) < 1e-9
+    # bit-reproducible sums
+    again = train.rec_losses([d(t) for t in prime], [[d(t) for t in tri] for tri in final], *[d(t) for t in gts], 1.0, 0.5)
+    assert again[0] == got[0]
+    with pytest.raises(A.DemfiError):
+        train.rec_losses(prime, final, *gts)
+
+
+@pytest.mark.parametrize("wd", [0.0, 1e-2])
+def test_adam_matches_torch_optim(wd):
+    from demfi_b200 import train
+    g = torch.Generator().manual_seed(5)
+    shapes = [(64, 64, 3, 3), (64,), (3, 64, 1, 3, 3), (1000, 7)]
+    ref = [torch.randn(*s, generator=g).to(DEV).requires_grad_(True) for s in shapes]
+    mine = [r.detach().clone().requires_grad_(True) for r in ref]
+    opt_ref = torch.optim.Adam(ref, lr=1e-2, betas=(0.9, 0.999), weight_decay=wd)
+    opt = train.Adam(mine, lr=1e-2, betas=(0.9, 0.999), weight_decay=wd)
+    for step in range(4):
+        for r, m in zip(ref, mine):
+            gr = torch.randn(r.shape, generator=g).to(DEV) * (0.1 + step)
+            r.grad, m.grad = gr.clone(), gr.clone()
+        opt_ref.step()
+        opt.step()
+    torch.cuda.synchronize()
+    for r, m in zip(ref, mine):
+        assert float((r - m).abs().max()) < 2e-6, float((r - m).abs().max())
+    assert opt.state[0]["step"] == 4 and opt.param_groups[0]["lr"] == 1e-2
+    opt.zero_grad()
+    assert all(p.grad is None for p in mine)
+
+
+def test_fgac_blend_and_upsample_backward():
+    g = torch.Generator().manual_seed(9)
+    n, C, h, w = 2, 64, 12, 20
+    wgt = torch.sigmoid(torch.randn(n, 1, h, w, generator=g)).double().requires_grad_(True)
+    src = torch.randn(n, C, h, w, generator=g).double().requires_grad_(True)
+    e = torch.randn(n, C, h, w, generator=g).double().requires_grad_(True)
+    gy = torch.randn(n, C, h, w, generator=g)
+    ((wgt * src + (1 - wgt) * e) * gy.double()).sum().backward()
+    wb, _ = nhwc(wgt.detach().float(), 4)
+    sb, _ = nhwc(src.detach().float(), 128)
+    eb, _ = nhwc(e.detach().float(), 64)
+    gb, _ = nhwc(gy, 64)
+    dw = torch.zeros(n, h, w, 4, device=DEV)
+    ds = torch.zeros(n, h, w, 64, device=DEV)
+    de = torch.zeros(n, h, w, 72, device=DEV)
+    A.check(A.lib().demfi_fgac_blend_backward(wb.data_ptr(), 4, sb.data_ptr(), 128, eb.data_ptr(), 64, gb.data_ptr(), 64, n * h * w, C,
+                                              dw.data_ptr(), 4, ds.data_ptr(), 64, de.data_ptr(), 72, stream()), "fgac_blend_backward")
+    torch.cuda.synchronize()
+    _close(from_nhwc(dw, 1).double(), wgt.grad, "dw", 2e-6)
+    _close(from_nhwc(ds, C).double(), src.grad, "dsrc", 1e-6)
+    _close(from_nhwc(de, C).double(), e.grad, "de", 1e-6)
+    # nearest x2 up-sampling
+    x = torch.randn(n, C, 5, 7, generator=g).double().requires_grad_(True)
+    gu = torch.randn(n, C, 10, 14, generator=g)
+    (torch.nn.functional.interpolate(x, scale_factor=2, mode="nearest") * gu.double()).sum().backward()
+    gub, _ = nhwc(gu, 68)
+    gx = torch.zeros(n, 5, 7, 64, device=DEV)
+    A.check(A.lib().demfi_upsample2x_backward(gub.data_ptr(), 68, n, 5, 7, C, gx.data_ptr(), 64, stream()), "upsample2x_backward")
+    torch.cuda.synchronize()
+    _close(from_nhwc(gx, C).double(), x.grad, "upsample2x backward", 1e-6)
