@@ -132,3 +132,19 @@ class _Conv2d(torch.autograd.Function):
 def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor = None, act: str = "none") -> torch.Tensor:
     """act(conv2d(x, weight, bias, stride 1, 'same' padding)); x [N,Cin,H,W], weight [Cout,Cin,KH,KW] (odd KH, KW) on a B200."""
     return _Conv2d.apply(x, weight, bias, ACTS[act])
+
+
+# ---------------------------------------------------------------------------------------------- a first differentiable stack
+def decoder_d1(model, feats: torch.Tensor) -> torch.Tensor:
+    """D1 of DeMFI-Net (`DeMFInet.py:95-102`: Dec_first -> 5 x ResidualBlock_noBN_3D -> Dec_last1 -> Dec_last2, all
+    Conv3d[1,3,3], i.e. the same 2-D stack applied to every frame) as a differentiable function of its input and of the
+    module's OWN parameters, every convolution through `conv2d` above.  feats: [F*B, 64, H, W] (the frames batched).
+    The first multi-layer slice of the training row: forward + backward + `train.Adam` reproduce torch autograd on the same
+    stack (tests/test_grad_gpu.py)."""
+    w2 = lambda conv: conv.weight.squeeze(2)                      # [Co,Ci,1,3,3] -> [Co,Ci,3,3] (a view: gradients flow back)
+    x = conv2d(feats, w2(model.Dec_first), model.Dec_first.bias, "relu")
+    for blk in model.Decoder_res:
+        y = conv2d(x, w2(blk.conv1), blk.conv1.bias, "relu")
+        x = x + conv2d(y, w2(blk.conv2), blk.conv2.bias, "none")  # ResidualBlock_noBN_3D, DeMFInet.py:517-540
+    x = conv2d(x, w2(model.Dec_last1), model.Dec_last1.bias, "relu")
+    return conv2d(x, w2(model.Dec_last2), model.Dec_last2.bias, "none")

@@ -205,7 +205,7 @@ def test_adam_matches_torch_optim(wd):
         opt.step()
     torch.cuda.synchronize()
     for r, m in zip(ref, mine):
-        assert float((r - m).abs().max()) < 2e-6, float((r - m).abs().max())
+        assert float((r.detach() - m.detach()).abs().max()) < 2e-6
     assert opt.state[0]["step"] == 4 and opt.param_groups[0]["lr"] == 1e-2
     opt.zero_grad()
     assert all(p.grad is None for p in mine)
@@ -241,3 +241,61 @@ def test_fgac_blend_and_upsample_backward():
     A.check(A.lib().demfi_upsample2x_backward(gub.data_ptr(), 68, n, 5, 7, C, gx.data_ptr(), 64, stream()), "upsample2x_backward")
     torch.cuda.synchronize()
     _close(from_nhwc(gx, C).double(), x.grad, "upsample2x backward", 1e-6)
+
+
+# ---------------------------------------------------------------------------------------------- a multi-layer training slice
+def test_three_training_steps_of_the_d1_decoder_follow_torch():
+    """forward (13 tcgen05 convs with residual adds) -> L1 losses with fused gradients -> backward (dx on the tcgen05 kernel,
+    dW/db on the wgrad kernel) -> demfi Adam, three steps on the module's own D1 parameters, against the same loop written
+    with F.conv2d / autograd / torch.optim.Adam in float64: per-step loss and first-step gradients"""
+    import copy
+    from demfi_b200 import synth, train
+    from demfi_b200.DeMFInet import DeMFInet
+    torch.backends.cudnn.allow_tf32 = False
+    model = DeMFInet(synth.default_args()).to(DEV)
+    model.load_state_dict(synth.make_state_dict(0))
+    names = ["Dec_first", "Dec_last1", "Dec_last2"] + [f"Decoder_res.{i}.conv{j}" for i in range(5) for j in (1, 2)]
+    mods = {n: model.get_submodule(n) for n in names}
+    ref = {n: (copy.deepcopy(m.weight.detach()).double().cpu().squeeze(2).requires_grad_(True),
+               copy.deepcopy(m.bias.detach()).double().cpu().requires_grad_(True)) for n, m in mods.items()}
+    g = torch.Generator().manual_seed(3)
+    B, H, W = 1, 24, 40
+    feats = torch.tanh(torch.randn(3 * B, 64, H, W, generator=g))
+    gts = [torch.randn(B, 3, H, W, generator=g) * 0.5 for _ in range(3)]
+
+    def ref_forward(x):
+        c = lambda n, t: torch.nn.functional.conv2d(t, ref[n][0], ref[n][1], padding=1)
+        x = torch.relu(c("Dec_first", x))
+        for i in range(5):
+            x = x + c(f"Decoder_res.{i}.conv2", torch.relu(c(f"Decoder_res.{i}.conv1", x)))
+        return c("Dec_last2", torch.relu(c("Dec_last1", x)))
+
+    params = [p for m in mods.values() for p in (m.weight, m.bias)]
+    opt = train.Adam(params, lr=1e-4)
+    opt_ref = torch.optim.Adam([t for pair in ref.values() for t in pair], lr=1e-4)
+    fd, gd = feats.to(DEV), [t.to(DEV) for t in gts]
+    for step in range(3):
+        # ours
+        opt.zero_grad()
+        out = grad.decoder_d1(model, fd)
+        sharps = [out[0:B], out[B:2 * B], out[2 * B:3 * B]]
+        total, d1, _, g_prime, _ = train.rec_losses(sharps, [], *gd, with_grads=True)
+        torch.autograd.backward(sharps, g_prime)
+        # reference
+        opt_ref.zero_grad()
+        o = ref_forward(feats.double())
+        loss = sum(torch.nn.functional.l1_loss(gts[i].double(), o[i * B:(i + 1) * B]) for i in range(3)) / 3
+        loss.backward()
+        print(f"step {step}: loss ours {total:.8f} torch {float(loss.detach()):.8f}")
+        assert abs(total - float(loss.detach())) < 5e-6 * max(1.0, abs(float(loss.detach())))
+        if step == 0:
+            for n, m in mods.items():
+                gw, gr = m.weight.grad.squeeze(2).double().cpu(), ref[n][0].grad
+                assert float((gw - gr).abs().max()) < 5e-5 * float(gr.abs().max()), n
+                assert float((m.bias.grad.double().cpu() - ref[n][1].grad).abs().max()) < 5e-5 * float(ref[n][1].grad.abs().max()), n
+        opt.step()
+        opt_ref.step()
+    torch.cuda.synchronize()
+    for n, m in mods.items():   # Adam normalises by |g|: parameters whose gradient is ~0 may step differently, so compare in bulk
+        d = (m.weight.detach().squeeze(2).double().cpu() - ref[n][0].detach()).abs()
+        assert float(d.mean()) < 2e-6, (n, float(d.mean()))
