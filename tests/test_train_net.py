@@ -1,0 +1,87 @@
+"""Wiring of the differentiable training forward (demfi_b200/train_net.py) checked WITHOUT a GPU: the four kernel-backed
+operator families are replaced by torch implementations (below, from the oracle's closed forms, themselves pinned to autograd
+through the reference's functions in tests/test_oracle.py) and the whole graph -- 260 parameters, N_trn = 2, two samples with
+different t -- is compared with `total_loss.backward()` through the UNMODIFIED reference module (tests/golden/train_grads.npz,
+oracle/gen_golden_train.py).  On a B200 the same graph runs with `KernelOps`, whose operators are checked one by one in
+tests/test_grad_gpu.py."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from demfi_b200 import synth, train_net
+from demfi_b200.DeMFInet import DeMFInet
+from oracle import demfi_oracle as O
+from oracle import train_oracle as TO
+from oracle.gen_golden_train import CFG, FULL, case_tensors, summarise
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "train_grads.npz"))
+ACT = {"none": lambda v: v, "relu": torch.relu, "tanh": torch.tanh, "sigmoid": torch.sigmoid}
+
+
+class TorchOps:
+    """test-only stand-ins for the kernel-backed operators (never importable from the package)"""
+
+    @staticmethod
+    def conv2d(x, w, b, act="none", stride=1):
+        pad = (w.shape[2] // 2, w.shape[3] // 2) if stride == 1 else (1, 1)
+        return ACT[act](F.conv2d(x, w, b, stride=stride, padding=pad))
+
+    @staticmethod
+    def bwarp_blend(a, b, flow, occ_logit, t):
+        return O.eq2_blend(a, flow[:, 0:2], b, flow[:, 2:4], occ_logit, t.view(-1, 1, 1, 1))
+
+    @staticmethod
+    def cfr(flow_01, flow_10, t):
+        return O.cfr_flow_t_align(flow_01, flow_10, t.view(-1, 1, 1, 1))
+
+    @staticmethod
+    def fgac_sample(refk, flow):
+        H, W = refk.shape[-2:]
+        px = ((2 * flow[:, 0] / (W - 1) - 1) + 1.0) / 2.0 * (W - 1)
+        py = ((2 * flow[:, 1] / (H - 1) - 1) + 1.0) / 2.0 * (H - 1)
+        return O.bilinear_gather(refk, px, py)[0]
+
+
+def test_training_forward_and_gradients_match_the_reference():
+    model = DeMFInet(synth.default_args())
+    model.load_state_dict(synth.make_state_dict(0))
+    x, t, gts = case_tensors()
+    res = train_net.forward_train(model, x, t, CFG["n"], ops=TorchOps)
+    assert len(res) == 7 and len(res[1]) == CFG["n"] and len(res[2]) == CFG["n"] + 1 and len(res[5]) == 4 and len(res[6][0]) == 2
+    assert float((res[1][-1][2].detach() - torch.from_numpy(GOLD["St_final_last"])).abs().max()) < 5e-5
+    assert float((res[2][-1].detach() - torch.from_numpy(GOLD["flow_last"])).abs().max()) < 5e-5
+    total, d1, d2 = TO.rec_losses(res[0], res[1], *gts)
+    assert np.allclose([float(total.detach()), float(d1.detach()), float(d2.detach())], GOLD["losses"], rtol=2e-6)
+    total.backward()
+    names = [n for n, _ in model.named_parameters()]
+    assert names == list(GOLD["names"])
+    grads = [(n, p.grad if p.grad is not None else torch.zeros(1)) for n, p in model.named_parameters()]
+    # the only parameters without a gradient: conv_source_k, dead for rr = sr = 0 (the reference gives them exact zeros)
+    assert [n for n, p in model.named_parameters() if p.grad is None] == [
+        "FAC_FB_Module.shared_FGAC.conv_source_k.weight", "FAC_FB_Module.shared_FGAC.conv_source_k.bias"]
+    got, want = summarise(grads), GOLD["summary"]
+    numel = np.asarray([p.numel() for p in model.parameters()], dtype=np.float64)
+    # each statistic against its natural scale: the gradient's own L2 norm (norm, projection on a unit direction) and
+    # sqrt(numel) * norm for the plain sum (|sum| <= ||g||_1 <= sqrt(n) ||g||_2; correlated 1e-5-level differences add up in it)
+    scale = np.maximum(want[:, 0:1], 1e-6) * np.stack([np.ones_like(numel), np.sqrt(numel), np.ones_like(numel)], 1)
+    err = np.abs(got - want) / scale
+    worst = int(err.max(1).argmax())
+    print(f"worst parameter {names[worst]}: relative error {err[worst].max():.2e}; median {np.median(err.max(1)):.2e}")
+    assert err.max() < 2e-4, (names[worst], err[worst])
+    for n in FULL:
+        g = dict(grads)[n]
+        w = torch.from_numpy(GOLD["full:" + n])
+        assert float((g - w).abs().max()) < 2e-3 * float(w.abs().max()) + 1e-7, n
+
+
+def test_kernel_ops_refuse_cpu_tensors_and_stride2_backward_is_announced():
+    from demfi_b200._abi import DemfiError
+    with pytest.raises(DemfiError):
+        train_net.KernelOps.cfr(torch.zeros(1, 2, 8, 8), torch.zeros(1, 2, 8, 8), torch.tensor([0.5]))
+    with pytest.raises(DemfiError):
+        train_net.KernelOps.fgac_sample(torch.zeros(1, 64, 8, 8), torch.zeros(1, 2, 8, 8))
+    with pytest.raises(NotImplementedError):
+        train_net.KernelOps.conv2d(torch.zeros(1, 8, 8, 8), torch.zeros(8, 8, 4, 4), None, "relu", stride=2)
