@@ -173,8 +173,9 @@ class DeMFInet(nn.Module):
         if not torch.cuda.is_available():
             raise RuntimeError("demfi_b200.DeMFInet needs a B200 (sm_100a) GPU: there is no CPU fallback")
         if is_training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("backward through the sm_100a kernels is not implemented yet (SURVEY.md 8f-2); "
-                                      "wrap the call in torch.no_grad()")
+            raise NotImplementedError("the fused inference engine keeps nothing for a backward pass: wrap the call in torch.no_grad(), "
+                                      "or use demfi_b200.train_net.forward_train(model, x, t, N_trn) for the differentiable forward "
+                                      "(SURVEY.md 8f-2)")
         dev = x.device if x.is_cuda else self.device
         B, C, T, H, W = x.size()
         if num_update is None:  # `summary()` dry run, DeMFInet.py:126-128

@@ -70,7 +70,8 @@ SYMBOLS = {
     "demfi_upsample2x": (i32, [vp, i32, i32, i32, i32, i32, vp, i32, vp]),
     "demfi_export_nchw": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, vp]),
     "demfi_import_nchw": (i32, [vp, i32, i32, i32, i32, vp, i32, vp]),
-    "demfi_conv2d_wgrad": (i32, [vp, i32, i32, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp]),
+    "demfi_conv2d_wgrad": (i32, [vp, i32, i32, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp]),
+    "demfi_conv2d_dgrad_strided": (i32, [vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp]),
     "demfi_act_backward": (i32, [vp, i32, vp, i32, C.c_int64, i32, i32, vp, i32, vp]),
     "demfi_bwarp_blend_backward": (i32, [vp, i32, vp, i32, vp, i32, vp, i32, vp, vp, i32, i32, i32, i32, i32, vp, i32, vp, i32,
                                          vp, i32, vp, i32, vp]),

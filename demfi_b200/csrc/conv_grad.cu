@@ -17,7 +17,7 @@ constexpr int WG_CHUNK = 2048;  // pixels reduced by one CTA before its atomic a
 
 struct WgradParams {
   const float* x; const float* dz; float* dw; float* db;
-  int x_ld, dz_ld, Cin, Cout, N, H, W, KH, KW, pad_h, pad_w;
+  int x_ld, dz_ld, Cin, Cout, N, H, W, Hi, Wi, stride, KH, KW, pad_h, pad_w;  // H, W: output (dz) plane; Hi, Wi: input (x) plane
   int co_blocks, ci_blocks;
   long long npix;
 };
@@ -43,9 +43,10 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const WgradParams P) {
       if (p < p1) {
         if (co0 + lc < P.Cout) zv = P.dz[p * P.dz_ld + co0 + lc];
         const int xw = (int)(p % P.W), yh = (int)((p / P.W) % P.H);
-        const int sy = yh + ky - P.pad_h, sx = xw + kx - P.pad_w;
-        if (ci0 + lc < P.Cin && sy >= 0 && sy < P.H && sx >= 0 && sx < P.W)
-          xv = P.x[(p + (long long)(sy - yh) * P.W + (sx - xw)) * P.x_ld + ci0 + lc];
+        const long long n = p / ((long long)P.W * P.H);
+        const int sy = yh * P.stride + ky - P.pad_h, sx = xw * P.stride + kx - P.pad_w;
+        if (ci0 + lc < P.Cin && sy >= 0 && sy < P.Hi && sx >= 0 && sx < P.Wi)
+          xv = P.x[((n * P.Hi + sy) * P.Wi + sx) * P.x_ld + ci0 + lc];
       }
       zs[r][lc] = zv;
       xs[r][lc] = xv;
@@ -78,6 +79,34 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const WgradParams P) {
   }
 }
 
+// dx of a STRIDED convolution (the three 4x4 stride-2 UNet encoders, DeMFInet.py:566-571), gather form on CUDA cores:
+// dx[n, yi, xi, ci] = sum over taps (ky, kx) with (yi + pad - ky) and (xi + pad - kx) divisible by the stride, and over co, of
+// dz[n, (yi + pad - ky) / s, (xi + pad - kx) / s, co] * W[co, ci, ky, kx].  One thread per (input pixel, input channel); the 32
+// lanes of a warp share the pixel, so the dz reads are broadcasts.  Three small layers: correct first.
+__global__ void __launch_bounds__(256)
+conv_dgrad_strided_kernel(const float* __restrict__ dz, int dz_ld, const float* __restrict__ w, int Cin, int Cout, int N, int H, int W,
+                          int Hi, int Wi, int KH, int KW, int pad_h, int pad_w, int stride, float* __restrict__ dx, int dx_ld) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)N * Hi * Wi * Cin) return;
+  const int ci = (int)(i % Cin);
+  const long long p = i / Cin;
+  const int xi = (int)(p % Wi), yi = (int)((p / Wi) % Hi);
+  const long long n = p / ((long long)Wi * Hi);
+  float acc = 0.0f;
+  for (int ky = 0; ky < KH; ++ky) {
+    const int ty = yi + pad_h - ky;
+    if (ty < 0 || ty % stride != 0 || ty / stride >= H) continue;
+    for (int kx = 0; kx < KW; ++kx) {
+      const int tx = xi + pad_w - kx;
+      if (tx < 0 || tx % stride != 0 || tx / stride >= W) continue;
+      const float* z = dz + ((n * H + ty / stride) * W + tx / stride) * dz_ld;
+      const float* wp = w + ((size_t)ci * KH + ky) * KW + kx;
+      for (int co = 0; co < Cout; ++co) acc = fmaf(__ldg(z + co), __ldg(wp + (size_t)co * Cin * KH * KW), acc);
+    }
+  }
+  dx[p * dx_ld + ci] = acc;
+}
+
 // dz = dy * act'(y), y the layer's stored OUTPUT (ReLU: y > 0; tanh: 1 - y^2; sigmoid: y (1 - y)); C channels of NHWC rows
 __global__ void __launch_bounds__(256) act_backward_kernel(const float* __restrict__ dy, int dy_ld, const float* __restrict__ y, int y_ld,
                                                            long long npix, int C, int act, float* __restrict__ out, int out_ld) {
@@ -101,17 +130,21 @@ using namespace demfi;
 extern "C" {
 
 int demfi_conv2d_wgrad(const float* x, int32_t x_ld, int32_t Cin, const float* dz, int32_t dz_ld, int32_t Cout, int32_t N,
-                       int32_t H, int32_t W, int32_t KH, int32_t KW, int32_t pad_h, int32_t pad_w, float* dw, float* dbias,
-                       void* stream) {
+                       int32_t H, int32_t W, int32_t KH, int32_t KW, int32_t pad_h, int32_t pad_w, int32_t stride, float* dw,
+                       float* dbias, void* stream) {
   if (check_device()) return 3;
   DEMFI_REQUIRE(x && dz && dw, "conv2d_wgrad: null pointer");
   DEMFI_REQUIRE(N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && KH > 0 && KW > 0 && KH * KW <= 65535 && x_ld >= Cin && dz_ld >= Cout &&
                     pad_h >= 0 && pad_w >= 0, "conv2d_wgrad: bad shape");
-  DEMFI_REQUIRE(H + 2 * pad_h - KH + 1 == H && W + 2 * pad_w - KW + 1 == W, "conv2d_wgrad: only stride-1 'same' convolutions");
+  DEMFI_REQUIRE(stride == 1 || stride == 2, "conv2d_wgrad: stride 1 or 2");
+  // the input plane is the one DeMFI-Net's layers see: 'same' for stride 1, exactly stride x the output for the stride-2 encoders
+  const int Hi = H * stride, Wi = W * stride;
+  DEMFI_REQUIRE((Hi + 2 * pad_h - KH) / stride + 1 == H && (Wi + 2 * pad_w - KW) / stride + 1 == W,
+                "conv2d_wgrad: kernel / padding / stride do not map a %d x %d input to the %d x %d output", Hi, Wi, H, W);
   WgradParams P;
   P.x = x; P.dz = dz; P.dw = dw; P.db = dbias;
   P.x_ld = x_ld; P.dz_ld = dz_ld; P.Cin = Cin; P.Cout = Cout; P.N = N; P.H = H; P.W = W; P.KH = KH; P.KW = KW;
-  P.pad_h = pad_h; P.pad_w = pad_w;
+  P.pad_h = pad_h; P.pad_w = pad_w; P.Hi = Hi; P.Wi = Wi; P.stride = stride;
   P.co_blocks = (Cout + WG_T - 1) / WG_T;
   P.ci_blocks = (Cin + WG_T - 1) / WG_T;
   P.npix = (long long)N * H * W;
@@ -119,6 +152,22 @@ int demfi_conv2d_wgrad(const float* x, int32_t x_ld, int32_t Cin, const float* d
   dim3 grid((unsigned)((P.npix + WG_CHUNK - 1) / WG_CHUNK), KH * KW, P.co_blocks * P.ci_blocks);
   conv_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P);
   DEMFI_LAUNCH_CHECK("conv_wgrad");
+  return 0;
+}
+
+int demfi_conv2d_dgrad_strided(const float* dz, int32_t dz_ld, const float* w_oihw, int32_t Cin, int32_t Cout, int32_t N, int32_t H,
+                               int32_t W, int32_t KH, int32_t KW, int32_t pad_h, int32_t pad_w, int32_t stride, float* dx,
+                               int32_t dx_ld, void* stream) {
+  if (check_device()) return 3;
+  DEMFI_REQUIRE(dz && w_oihw && dx && N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && KH > 0 && KW > 0 && stride >= 1 && dz_ld >= Cout &&
+                    dx_ld >= Cin, "conv2d_dgrad_strided: bad arguments");
+  const int Hi = H * stride, Wi = W * stride;
+  DEMFI_REQUIRE((Hi + 2 * pad_h - KH) / stride + 1 == H && (Wi + 2 * pad_w - KW) / stride + 1 == W,
+                "conv2d_dgrad_strided: kernel / padding / stride do not map a %d x %d input to the %d x %d output", Hi, Wi, H, W);
+  const long long n = (long long)N * Hi * Wi * Cin;
+  conv_dgrad_strided_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dz, dz_ld, w_oihw, Cin, Cout, N, H, W, Hi, Wi, KH, KW,
+                                                                                           pad_h, pad_w, stride, dx, dx_ld);
+  DEMFI_LAUNCH_CHECK("conv_dgrad_strided");
   return 0;
 }
 

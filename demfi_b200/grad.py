@@ -1,7 +1,8 @@
 """Differentiable convolution layer through the C ABI -- the first slice of the training row.
 
-`conv2d(x, weight, bias, act)` computes `act(F.conv2d(x, weight, bias, padding='same'))` for the stride-1 layers of DeMFI-Net
-(every nn.Conv2d / nn.Conv3d[1,k,k] of `DeMFInet.py` except the three stride-2 UNet encoders) and is differentiable:
+`conv2d(x, weight, bias, act, stride)` computes `act(F.conv2d(x, weight, bias, ...))` for the layer shapes of DeMFI-Net (stride 1
+with 'same' padding: every nn.Conv2d / nn.Conv3d[1,k,k] of `DeMFInet.py`; stride 2, 4x4, padding 1: the three UNet encoders,
+whose dx runs on the CUDA-core `demfi_conv2d_dgrad_strided`) and is differentiable:
 
   forward   demfi_conv2d            tcgen05 kernel, 3xFP16 split (fp32 parity), fused bias + activation
   dz        demfi_act_backward      dy * act'(y) from the stored output
@@ -23,7 +24,7 @@ from . import _abi as A
 
 ACTS = {"none": A.ACT_NONE, "relu": A.ACT_RELU, "tanh": A.ACT_TANH, "sigmoid": A.ACT_SIGMOID}
 _ru = lambda v, m: (v + m - 1) // m * m
-_PACKED: Dict[Tuple, Tuple[torch.Tensor, torch.Tensor, object]] = {}
+_MAX_COUT = 256    # demfi_conv2d: cout_pad <= 256
 
 
 def _stream(dev):
@@ -48,13 +49,17 @@ def _pack(w: np.ndarray, b: np.ndarray, src_c: int, dev) -> Tuple[torch.Tensor, 
     return torch.from_numpy(packed).to(dev), torch.from_numpy(bias).to(dev), cout_pad
 
 
-def _conv_nhwc(x: torch.Tensor, C_: int, wdev: torch.Tensor, bdev: torch.Tensor, cout_pad: int, k: Tuple[int, int], act: int):
-    """x: [N,H,W,ld] fp32 NHWC of which the first C_ channels are read; returns [N,H,W,cout_pad]"""
-    N, H, W, ld = x.shape
+def _conv_nhwc(x: torch.Tensor, C_: int, wdev: torch.Tensor, bdev: torch.Tensor, cout_pad: int, k: Tuple[int, int], act: int,
+               stride: int = 1):
+    """x: [N,Hi,Wi,ld] fp32 NHWC of which the first C_ channels are read; returns [N,Hi/stride,Wi/stride,cout_pad].
+    stride 1: 'same' padding; stride 2: the 4x4 / pad 1 encoders of the UNet."""
+    N, Hi, Wi, ld = x.shape
+    H, W = Hi // stride, Wi // stride
+    pad = (k[0] // 2, k[1] // 2) if stride == 1 else (1, 1)
     y = torch.empty(N, H, W, cout_pad, dtype=torch.float32, device=x.device)
     d = A.Conv()
-    d.N, d.H, d.W, d.Hi, d.Wi = N, H, W, H, W
-    d.KH, d.KW, d.stride, d.pad_h, d.pad_w = k[0], k[1], 1, k[0] // 2, k[1] // 2
+    d.N, d.H, d.W, d.Hi, d.Wi = N, H, W, Hi, Wi
+    d.KH, d.KW, d.stride, d.pad_h, d.pad_w = k[0], k[1], stride, pad[0], pad[1]
     d.nsrc, d.nseg, d.cout_pad, d.kind = 1, 1, cout_pad, A.CONV_TC16
     d.src[0].ptr, d.src[0].C, d.src[0].ld = x.data_ptr(), C_, ld
     s = d.seg[0]
@@ -81,22 +86,24 @@ def _to_nchw(buf: torch.Tensor, C_: int) -> torch.Tensor:
 
 class _Conv2d(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, act: int):
+    def forward(ctx, x, weight, bias, act: int, stride: int = 1):
         if not x.is_cuda:
             raise A.DemfiError("demfi_b200.grad.conv2d runs on the GPU only (no CPU fallback)")
         Co, Ci, KH, KW = weight.shape
-        if KH % 2 == 0 or KW % 2 == 0 or x.shape[1] != Ci:
-            raise ValueError("conv2d: odd 'same' kernels with matching channel counts only (the stride-1 layers of DeMFI-Net)")
+        if x.shape[1] != Ci or (stride == 1 and (KH % 2 == 0 or KW % 2 == 0)) or \
+                (stride == 2 and ((KH, KW) != (4, 4) or x.shape[2] % 2 or x.shape[3] % 2)) or stride not in (1, 2):
+            raise ValueError("conv2d: the layer shapes of DeMFI-Net only -- stride 1 with an odd 'same' kernel, or the UNet "
+                             "encoders (4x4, stride 2, padding 1, even input size)")
         dev = x.device
         with torch.cuda.device(dev):
             cin_pad = _ru(Ci, 8)
             xb = _to_nhwc(x.detach().float(), cin_pad)
             b = bias.detach() if bias is not None else torch.zeros(Co, device=dev)
             wdev, bdev, cout_pad = _pack(weight.detach().cpu().numpy(), b.cpu().numpy(), cin_pad, dev)
-            yb = _conv_nhwc(xb, cin_pad, wdev, bdev, cout_pad, (KH, KW), act)
+            yb = _conv_nhwc(xb, cin_pad, wdev, bdev, cout_pad, (KH, KW), act, stride)
             y = _to_nchw(yb, Co)
         ctx.save_for_backward(weight)
-        ctx.xb, ctx.yb, ctx.act, ctx.has_bias, ctx.shape = xb, yb, act, bias is not None, tuple(x.shape)
+        ctx.xb, ctx.yb, ctx.act, ctx.has_bias, ctx.shape, ctx.stride = xb, yb, act, bias is not None, tuple(x.shape), stride
         return y
 
     @staticmethod
@@ -104,7 +111,10 @@ class _Conv2d(torch.autograd.Function):
         (weight,) = ctx.saved_tensors
         xb, yb, act = ctx.xb, ctx.yb, ctx.act
         Co, Ci, KH, KW = weight.shape
-        N, _, H, W = ctx.shape
+        N, _, Hi, Wi = ctx.shape
+        stride = ctx.stride
+        H, W = Hi // stride, Wi // stride                     # the output plane: that of dy, y and dz
+        pad = (KH // 2, KW // 2) if stride == 1 else (1, 1)
         dev = dy.device
         lib = A.lib()
         with torch.cuda.device(dev):
@@ -115,23 +125,35 @@ class _Conv2d(torch.autograd.Function):
             A.check(lib.demfi_act_backward(dyb.data_ptr(), co_pad, yb.data_ptr(), yb.shape[3], N * H * W, Co, act, dz.data_ptr(),
                                            co_pad, st), "demfi_act_backward")
             dx = dw = db = None
-            if ctx.needs_input_grad[0]:
-                # dx = conv(dz, W^T rotated): w_t[ci, co, ky, kx] = W[co, ci, KH-1-ky, KW-1-kx]
-                w_t = weight.detach().flip(2, 3).transpose(0, 1).contiguous().cpu().numpy()
-                wdev, bdev, ci_pad = _pack(w_t, np.zeros(Ci, dtype=np.float32), co_pad, dev)
-                dx = _to_nchw(_conv_nhwc(dz, co_pad, wdev, bdev, ci_pad, (KH, KW), A.ACT_NONE), Ci)
+            if ctx.needs_input_grad[0] and stride != 1:
+                dxb = torch.empty(N, Hi, Wi, _ru(Ci, 4), dtype=torch.float32, device=dev)
+                wc = weight.detach().float().contiguous()
+                A.check(lib.demfi_conv2d_dgrad_strided(dz.data_ptr(), co_pad, wc.data_ptr(), Ci, Co, N, H, W, KH, KW, pad[0], pad[1],
+                                                       stride, dxb.data_ptr(), dxb.shape[3], st), "demfi_conv2d_dgrad_strided")
+                dx = _to_nchw(dxb, Ci)
+            elif ctx.needs_input_grad[0]:
+                # dx = conv(dz, W^T rotated): w_t[ci, co, ky, kx] = W[co, ci, KH-1-ky, KW-1-kx]; the forward kernel produces at
+                # most 256 output channels per launch, so wide inputs (GFF.0: 1152, UNet dec1: 384) go in slices of Cin
+                w_rot = weight.detach().flip(2, 3).transpose(0, 1).cpu()
+                parts = []
+                for c0 in range(0, Ci, _MAX_COUT):
+                    c1 = min(Ci, c0 + _MAX_COUT)
+                    wdev, bdev, ci_pad = _pack(w_rot[c0:c1].contiguous().numpy(), np.zeros(c1 - c0, dtype=np.float32), co_pad, dev)
+                    parts.append(_to_nchw(_conv_nhwc(dz, co_pad, wdev, bdev, ci_pad, (KH, KW), A.ACT_NONE), c1 - c0))
+                dx = parts[0] if len(parts) == 1 else torch.cat(parts, 1)
             if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
                 dw = torch.zeros(Co, Ci, KH, KW, dtype=torch.float32, device=dev)
                 db = torch.zeros(Co, dtype=torch.float32, device=dev) if ctx.has_bias else None
                 A.check(lib.demfi_conv2d_wgrad(xb.data_ptr(), xb.shape[3], Ci, dz.data_ptr(), co_pad, Co, N, H, W, KH, KW,
-                                               KH // 2, KW // 2, dw.data_ptr(), db.data_ptr() if db is not None else None, st),
+                                               pad[0], pad[1], stride, dw.data_ptr(), db.data_ptr() if db is not None else None, st),
                         "demfi_conv2d_wgrad")
-        return dx, dw, db, None
+        return dx, dw, db, None, None
 
 
-def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor = None, act: str = "none") -> torch.Tensor:
-    """act(conv2d(x, weight, bias, stride 1, 'same' padding)); x [N,Cin,H,W], weight [Cout,Cin,KH,KW] (odd KH, KW) on a B200."""
-    return _Conv2d.apply(x, weight, bias, ACTS[act])
+def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor = None, act: str = "none", stride: int = 1) -> torch.Tensor:
+    """act(conv2d(x, weight, bias)): stride 1 with 'same' padding (odd KH, KW), or stride 2 with a 4x4 kernel and padding 1 (the
+    UNet encoders); x [N,Cin,H,W], weight [Cout,Cin,KH,KW] on a B200."""
+    return _Conv2d.apply(x, weight, bias, ACTS[act], stride)
 
 
 # ---------------------------------------------------------------------------------------------- a first differentiable stack

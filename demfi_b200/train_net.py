@@ -135,10 +135,7 @@ class KernelOps:
 
     @staticmethod
     def conv2d(x, w, b, act="none", stride=1):
-        if stride != 1:
-            raise NotImplementedError("backward of the three stride-2 UNet encoders (Refine_Module.enc1-3) is not built yet "
-                                      "(SURVEY.md 8f-2); the differentiable forward stops here")
-        return G.conv2d(x, w, b, act)
+        return G.conv2d(x, w, b, act, stride)
 
     @staticmethod
     def bwarp_blend(a, b, flow, occ_logit, t):

@@ -204,10 +204,17 @@ int demfi_import_nchw(const float* src, int32_t B, int32_t H, int32_t W, int32_t
  *   dx = conv(dz, W rotated by 180 degrees with Cin and Cout exchanged): the forward kernel, demfi_conv2d, on re-packed weights
  *   dW, db                               demfi_conv2d_wgrad: dw[co][ci][ky][kx] += sum_p dz[p][co] * x[p + (ky,kx) - pad][ci]
  *                                        (OIHW fp32, the layout of the parameter), dbias[co] += sum_p dz[p][co] (may be NULL).
+ * H, W are the OUTPUT plane (that of dz); x is [N, H*stride, W*stride, x_ld] (stride 1: 'same'; stride 2: the UNet encoders).
  * x, dz: NHWC with row strides x_ld / dz_ld.  Both gradients are ACCUMULATED (+=) with fp32 atomics: zero them first. */
 int demfi_conv2d_wgrad(const float* x, int32_t x_ld, int32_t Cin, const float* dz, int32_t dz_ld, int32_t Cout, int32_t N,
-                       int32_t H, int32_t W, int32_t KH, int32_t KW, int32_t pad_h, int32_t pad_w, float* dw, float* dbias,
-                       void* stream);
+                       int32_t H, int32_t W, int32_t KH, int32_t KW, int32_t pad_h, int32_t pad_w, int32_t stride, float* dw,
+                       float* dbias, void* stream);
+/* dx of the stride-2 encoders (Refine_Module.enc1-3, 4x4 / stride 2 / pad 1), CUDA cores, gather form: dz [N,H,W,dz_ld] is the
+ * gradient at the conv's pre-activation output, w_oihw the parameter itself ([Cout,Cin,KH,KW] fp32 on the device), dx
+ * [N, H*stride, W*stride, dx_ld] is written. */
+int demfi_conv2d_dgrad_strided(const float* dz, int32_t dz_ld, const float* w_oihw, int32_t Cin, int32_t Cout, int32_t N, int32_t H,
+                               int32_t W, int32_t KH, int32_t KW, int32_t pad_h, int32_t pad_w, int32_t stride, float* dx,
+                               int32_t dx_ld, void* stream);
 int demfi_act_backward(const float* dy, int32_t dy_ld, const float* y, int32_t y_ld, int64_t npix, int32_t C, int32_t act,
                        float* out, int32_t out_ld, void* stream);
 

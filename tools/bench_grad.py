@@ -31,7 +31,7 @@ def main():
         dw = torch.zeros(co, ci, *k, device=DEV)
         db = torch.zeros(co, device=DEV)
         ms = timed(lambda: A.check(lib.demfi_conv2d_wgrad(x.data_ptr(), ci, ci, dz.data_ptr(), co, co, N, H, W, k[0], k[1], k[0] // 2,
-                                                          k[1] // 2, dw.data_ptr(), db.data_ptr(), st), "wgrad"))
+                                                          k[1] // 2, 1, dw.data_ptr(), db.data_ptr(), st), "wgrad"))
         flop = 2.0 * N * H * W * ci * co * k[0] * k[1]
         # dx through the forward tensor-core kernel
         wt = torch.randn(ci, co, *k) / (co * k[0] * k[1]) ** 0.5           # already "transposed": maps co -> ci
