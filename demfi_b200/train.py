@@ -107,6 +107,9 @@ class Adam:
                 A.check(lib.demfi_adam_step(p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel(),
                                             lr, self.betas[0], self.betas[1], self.eps, self.weight_decay, st["step"],
                                             torch.cuda.current_stream().cuda_stream), "demfi_adam_step")
+            # the kernel wrote through the raw pointer: tell torch (autograd's saved-tensor checks, and DeMFInet's own
+            # "weights changed -> repack" test, which reads p._version)
+            torch.autograd.graph.increment_version(p)
 
 
 def allreduce_gradients(params, world_size: int = None, group=None) -> int:

@@ -207,6 +207,7 @@ def test_adam_matches_torch_optim(wd):
     for r, m in zip(ref, mine):
         assert float((r.detach() - m.detach()).abs().max()) < 2e-6
     assert opt.state[0]["step"] == 4 and opt.param_groups[0]["lr"] == 1e-2
+    assert all(m._version >= 4 for m in mine)     # in-place updates are visible to torch (the inference engine repacks on it)
     opt.zero_grad()
     assert all(p.grad is None for p in mine)
 
