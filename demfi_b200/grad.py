@@ -15,7 +15,7 @@ with the ABI's layout kernels), NHWC inside.  No CPU or ATen fallback: CPU tenso
 """
 from __future__ import annotations
 
-from typing import Dict, Tuple
+from typing import Tuple
 
 import numpy as np
 import torch
