@@ -73,7 +73,8 @@ def _to_nhwc(t: torch.Tensor, ld: int) -> torch.Tensor:
     N, C_, H, W = t.shape
     out = torch.zeros(N, H, W, ld, dtype=torch.float32, device=t.device) if ld != C_ else \
         torch.empty(N, H, W, ld, dtype=torch.float32, device=t.device)
-    A.check(A.lib().demfi_import_nchw(t.contiguous().data_ptr(), N, H, W, C_, out.data_ptr(), ld, _stream(t.device)), "import_nchw")
+    src = t.contiguous()      # held until the launch below has been issued (a temporary would go back to the allocator first)
+    A.check(A.lib().demfi_import_nchw(src.data_ptr(), N, H, W, C_, out.data_ptr(), ld, _stream(t.device)), "import_nchw")
     return out
 
 
