@@ -61,7 +61,7 @@ def test_oracle_autograd_matches_reference_autograd_on_the_warps():
         a, b, fl, occ = T("a", True), T("b", True), T("flow", True), T("occ", True)
         out = O.eq2_blend(a, fl[:, 0:2], b, fl[:, 2:4], occ, T("t").view(-1, 1, 1, 1))
         (out * T("gy")).sum().backward()
-        assert float((out - T("out")).abs().max()) < 2e-6
+        assert float((out.detach() - T("out")).abs().max()) < 2e-6
         for name, got in (("da", a.grad), ("db", b.grad), ("dflow", fl.grad), ("docc", occ.grad)):
             want = T(name)
             assert float((got - want).abs().max()) < 2e-6 * max(1.0, float(want.abs().max())), (tag, name)
@@ -79,7 +79,7 @@ def test_oracle_autograd_matches_reference_autograd_on_the_warps():
     f01, f10 = T("f01", True), T("f10", True)
     ft0, ft1 = O.cfr_flow_t_align(f01, f10, T("t").view(-1, 1, 1, 1))
     ((ft0 * T("g0")).sum() + (ft1 * T("g1")).sum()).backward()
-    assert float((ft0 - T("ft0")).abs().max()) < 2e-6 and float((ft1 - T("ft1")).abs().max()) < 2e-6
+    assert float((ft0.detach() - T("ft0")).abs().max()) < 2e-6 and float((ft1.detach() - T("ft1")).abs().max()) < 2e-6
     assert float((f01.grad - T("df01")).abs().max()) < 5e-6 and float((f10.grad - T("df10")).abs().max()) < 5e-6
 
 
