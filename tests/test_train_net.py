@@ -85,3 +85,55 @@ def test_kernel_ops_refuse_cpu_tensors():
         train_net.KernelOps.fgac_sample(torch.zeros(1, 64, 8, 8), torch.zeros(1, 2, 8, 8))
     with pytest.raises(DemfiError):
         train_net.KernelOps.conv2d(torch.zeros(1, 8, 8, 8), torch.zeros(8, 8, 4, 4), None, "relu", stride=2)
+
+
+# ------------------------------------------------------------------------------- data parallel: two ranks over gloo, on CPU
+def _dp_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from demfi_b200.train import allreduce_gradients
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        model = DeMFInet(synth.default_args())
+        model.load_state_dict(synth.make_state_dict(0))
+        x, t, gts = case_tensors()
+        sl = slice(rank, rank + 1)                                     # one sample of the golden batch per rank
+        res = train_net.forward_train(model, x[sl], t[sl], CFG["n"], ops=TorchOps)
+        total, _, _ = TO.rec_losses(res[0], res[1], *[g[sl] for g in gts])
+        total.backward()
+        live = [p for p in model.parameters() if p.grad is not None]
+        nbytes = allreduce_gradients(live)
+        grads = [(n, p.grad if p.grad is not None else torch.zeros(1)) for n, p in model.named_parameters()]
+        q.put((rank, nbytes, float(total.detach()), summarise(grads)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_data_parallel_step_equals_the_batched_reference_gradient():
+    """SURVEY.md section 8(e), training: each rank runs the differentiable forward on its own sample, the gradients go through
+    `train.allreduce_gradients` (one flat bucket, SUM / world) -- and every rank ends up with the gradient the unmodified
+    reference computes for the batch of both samples (the L1 means make the batch loss the average of the per-sample losses)."""
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in procs], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = GOLD["summary"]
+    model = DeMFInet(synth.default_args())
+    numel = np.asarray([p.numel() for p in model.parameters()], dtype=np.float64)
+    scale = np.maximum(want[:, 0:1], 1e-6) * np.stack([np.ones_like(numel), np.sqrt(numel), np.ones_like(numel)], 1)
+    assert abs(0.5 * (res[0][2] + res[1][2]) - GOLD["losses"][0]) < 2e-6 * GOLD["losses"][0]
+    for rank, nbytes, _, got in res:
+        assert nbytes == 4 * int(numel.sum() - 64 * 64 - 64)      # all parameters but the dead conv_source_k (4096 + 64 values)
+        err = np.abs(got - want) / scale
+        assert err.max() < 2e-4, (rank, err.max())
+    assert np.array_equal(res[0][3], res[1][3])                    # both ranks hold the same averaged gradient
