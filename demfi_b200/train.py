@@ -131,3 +131,55 @@ def allreduce_gradients(params, world_size: int = None, group=None) -> int:
         g.copy_(flat[o:o + n].view_as(g))
         o += n
     return flat.numel() * 4
+
+
+class MultiStepLR:
+    """`optim.lr_scheduler.MultiStepLR(optimizer, milestones, gamma)` of main.py:186 / :511 for `train.Adam` (whose
+    `param_groups[0]['lr']` it scales): after the e-th `step()` the rate is lr0 * gamma ** (number of milestones <= e)."""
+
+    def __init__(self, optimizer, milestones, gamma=0.1):
+        self.optimizer, self.milestones, self.gamma = optimizer, sorted(milestones), gamma
+        self.base_lr = optimizer.param_groups[0]["lr"]
+        self.last_epoch = 0
+
+    def step(self):
+        self.last_epoch += 1
+        k = sum(1 for m in self.milestones if m <= self.last_epoch)
+        self.optimizer.param_groups[0]["lr"] = self.base_lr * self.gamma ** k
+
+    def get_last_lr(self):
+        return [self.optimizer.param_groups[0]["lr"]]
+
+
+def split_training_batch(frames: torch.Tensor):
+    """main.py:387-390: a training sample is [B, C, 9, H, W] = the four blurry inputs (B0, B1, B-1, B2), the sharp frame at t, and
+    the sharp frames at 0, 1, -1, 2 -> (input_frames [B,C,4,H,W], S0_GT, S1_GT, frameT)."""
+    input_frames = frames[:, :, :4]
+    frameT = frames[:, :, 4]
+    input_frames_GT = frames[:, :, -4:]
+    return input_frames, input_frames_GT[:, :, 0], input_frames_GT[:, :, 1], frameT
+
+
+def train_step(model, frames: torch.Tensor, t_value: torch.Tensor, optimizer, N_trn: int, rec_D1_lambda: float = 1.0,
+               rec_D2_lambda: float = 1.0, ops=None, loss_fn=None):
+    """One iteration of the loop body of `train()` (main.py:386-448): zero_grad, differentiable forward, Eq.(9)-(10) losses,
+    backward, gradient all-reduce over the ranks (a no-op in a single process), optimizer step.  Returns (total, rec_D1, rec_D2)
+    as floats, like the `.item()` calls of main.py:451-453.
+
+    ops / loss_fn: the operator set of `train_net.forward_train` and the loss implementation; the defaults are this repository's
+    kernels (`train_net.KernelOps`, `rec_losses`).  Tests pass torch stand-ins to check this host logic without a GPU."""
+    from . import train_net
+    input_frames, S0_GT, S1_GT, frameT = split_training_batch(frames)
+    optimizer.zero_grad()
+    res = train_net.forward_train(model, input_frames, t_value, N_trn, ops=ops or train_net.KernelOps)
+    outs = list(res[0]) + [s for tri in res[1] for s in tri]
+    if loss_fn is None:
+        total, d1, d2, g_prime, g_final = rec_losses(res[0], res[1], S0_GT, S1_GT, frameT, rec_D1_lambda, rec_D2_lambda, with_grads=True)
+        torch.autograd.backward(outs, list(g_prime) + [g for tri in g_final for g in tri])
+    else:
+        total_t, d1_t, d2_t = loss_fn(res[0], res[1], S0_GT, S1_GT, frameT, rec_D1_lambda, rec_D2_lambda)
+        total_t.backward()
+        total, d1, d2 = float(total_t.detach()), float(d1_t.detach()), float(d2_t.detach())
+    allreduce_gradients([p for p in model.parameters() if p.grad is not None])
+    optimizer.step()
+    return total, d1, d2

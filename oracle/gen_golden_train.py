@@ -33,6 +33,13 @@ def case_tensors():
     return x, t, [gt[:, :, 0].contiguous(), gt[:, :, 1].contiguous(), gt[:, :, 2].contiguous()]
 
 
+def training_frames():
+    """the [B, C, 9, H, W] sample of main.py:387-390 built from case_tensors(): 4 blurry inputs, frameT, then sharp 0, 1, -1, 2
+    (only the first two of the last four are read by the loss)"""
+    x, t, gts = case_tensors()
+    return torch.cat([x, gts[2][:, :, None], gts[0][:, :, None], gts[1][:, :, None], x[:, :, 2:4]], 2), t
+
+
 def summarise(named_grads):
     rows = []
     for i, (_, g) in enumerate(named_grads):
@@ -59,6 +66,23 @@ def main():
     for n, g in named:
         if n in FULL:
             out["full:" + n] = g.numpy()
+    # two full iterations of the loop body of train() (main.py:386-448) with the reference's optimizer settings (main.py:179-180)
+    net2 = ref_mod.DeMFInet(synth.default_args()).train()
+    net2.load_state_dict(synth.make_state_dict(seed=0), strict=True)
+    opt = torch.optim.Adam(net2.parameters(), lr=1e-4, betas=(0.9, 0.999), weight_decay=0)
+    frames, t = training_frames()
+    step_losses = []
+    for _ in range(2):
+        input_frames, frameT, input_frames_GT = frames[:, :, :4], frames[:, :, 4], frames[:, :, -4:]
+        opt.zero_grad()
+        r = net2(input_frames, t, CFG["n"], is_training=True)
+        tot, a, b = TO.rec_losses(r[0], r[1], input_frames_GT[:, :, 0], input_frames_GT[:, :, 1], frameT)
+        tot.backward()
+        opt.step()
+        step_losses.append([float(tot), float(a), float(b)])
+    out["step_losses"] = np.asarray(step_losses)
+    out["params_after_2_steps"] = summarise([(n, p) for n, p in net2.named_parameters()])
+    out["params_before"] = summarise([(n, p) for n, p in net.named_parameters()])
     np.savez_compressed(os.path.join(GOLD, "train_grads.npz"), **out)
     print("losses", out["losses"], "params", len(named), "grad norm range", out["summary"][:, 0].min(), out["summary"][:, 0].max())
     print("no-grad params:", [n for n, g in named if g is None])

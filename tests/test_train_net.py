@@ -137,3 +137,40 @@ def test_two_rank_data_parallel_step_equals_the_batched_reference_gradient():
         err = np.abs(got - want) / scale
         assert err.max() < 2e-4, (rank, err.max())
     assert np.array_equal(res[0][3], res[1][3])                    # both ranks hold the same averaged gradient
+
+
+def test_two_iterations_of_the_training_loop_follow_the_reference():
+    """`train.train_step` = the loop body of train() (main.py:386-448): batch split, forward, losses, backward, exchange, Adam.
+    Two iterations with torch stand-ins for the kernels (and torch.optim.Adam, since train.Adam is GPU-only) against two
+    iterations of the same loop on the unmodified reference module: the losses of both steps, and where the parameters end up."""
+    from demfi_b200 import train
+    from oracle.gen_golden_train import training_frames
+    model = DeMFInet(synth.default_args())
+    model.load_state_dict(synth.make_state_dict(0))
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, betas=(0.9, 0.999), weight_decay=0)
+    sched = train.MultiStepLR(opt, milestones=[1, 3], gamma=0.5)
+    frames, t = training_frames()
+    got = [train.train_step(model, frames, t, opt, CFG["n"], ops=TorchOps, loss_fn=TO.rec_losses) for _ in range(2)]
+    want = GOLD["step_losses"]
+    assert np.allclose(got[0], want[0], rtol=2e-6), (got[0], want[0])
+    assert np.allclose(got[1], want[1], rtol=2e-4), (got[1], want[1])      # after one Adam step of every parameter
+    after = summarise([(n, p) for n, p in model.named_parameters()])
+    numel = np.asarray([p.numel() for p in model.parameters()], dtype=np.float64)
+    moved = 2e-4 * np.sqrt(numel)                                           # two Adam steps of at most lr per element
+    d_norm = np.abs(after[:, 0] - GOLD["params_after_2_steps"][:, 0]) / moved
+    d_proj = np.abs(after[:, 2] - GOLD["params_after_2_steps"][:, 2]) / moved
+    print(f"parameters after two steps: norm off by {d_norm.max():.3f}, projection off by {d_proj.max():.3f} of the distance moved")
+    assert d_norm.max() < 0.05 and d_proj.max() < 0.05
+    # the scheduler mirror (main.py:186, :511)
+    sched.step()
+    assert opt.param_groups[0]["lr"] == 0.5e-4 and sched.get_last_lr() == [0.5e-4]
+    sched.step(); sched.step()
+    assert opt.param_groups[0]["lr"] == 0.25e-4
+
+
+def test_split_training_batch_follows_main_py():
+    from demfi_b200.train import split_training_batch
+    f = torch.arange(2 * 3 * 9 * 4 * 4, dtype=torch.float32).reshape(2, 3, 9, 4, 4)
+    inp, s0, s1, ft = split_training_batch(f)
+    assert inp.shape == (2, 3, 4, 4, 4) and torch.equal(inp, f[:, :, :4]) and torch.equal(ft, f[:, :, 4])
+    assert torch.equal(s0, f[:, :, 5]) and torch.equal(s1, f[:, :, 6])
