@@ -112,6 +112,39 @@ class Adam:
             torch.autograd.graph.increment_version(p)
 
 
+def _adam_state_dict(self):
+    """`optimizer.state_dict()` in torch.optim.Adam's layout (main.py:270 saves it, :214 loads it): a checkpoint written by the
+    reference loads here and the other way round.  `step` is a float32 scalar tensor as in torch >= 1.12 (a plain int from the
+    pinned torch 1.7.1 is accepted on load)."""
+    state = {i: {"step": torch.tensor(float(st["step"])), "exp_avg": st["exp_avg"], "exp_avg_sq": st["exp_avg_sq"]}
+             for i, st in self.state.items()}
+    group = {"lr": self.param_groups[0]["lr"], "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.weight_decay,
+             "amsgrad": False, "params": list(range(len(self.params)))}
+    return {"state": state, "param_groups": [group]}
+
+
+def _adam_load_state_dict(self, sd):
+    g = sd["param_groups"][0]
+    if g.get("amsgrad", False):
+        raise NotImplementedError("amsgrad state is not supported (main.py:179 does not use it)")
+    if len(g["params"]) != len(self.params):
+        raise ValueError("loaded state dict has a different number of parameters")
+    self.param_groups[0]["lr"] = g["lr"]
+    self.betas, self.eps, self.weight_decay = tuple(g["betas"]), g["eps"], g["weight_decay"]
+    self.state = {}
+    for k, st in sd["state"].items():
+        p = self.params[int(k)]
+        if tuple(st["exp_avg"].shape) != tuple(p.shape):
+            raise ValueError(f"optimizer state {k} has shape {tuple(st['exp_avg'].shape)}, the parameter {tuple(p.shape)}")
+        self.state[int(k)] = {"step": int(float(st["step"])),
+                              "exp_avg": st["exp_avg"].detach().to(p.device, torch.float32).clone(),
+                              "exp_avg_sq": st["exp_avg_sq"].detach().to(p.device, torch.float32).clone()}
+
+
+Adam.state_dict = _adam_state_dict
+Adam.load_state_dict = _adam_load_state_dict
+
+
 def allreduce_gradients(params, world_size: int = None, group=None) -> int:
     """Average the gradients over the ranks of the job: one flat fp32 bucket, one `all_reduce(SUM)`, scaled by 1/world and
     copied back.  Returns the number of bytes exchanged per rank (the bucket size).  A no-op without torch.distributed."""
@@ -149,6 +182,16 @@ class MultiStepLR:
 
     def get_last_lr(self):
         return [self.optimizer.param_groups[0]["lr"]]
+
+    def state_dict(self):
+        """the keys main.py:215-217 touches: last_epoch, milestones (a Counter in torch), gamma, base_lrs"""
+        from collections import Counter
+        return {"last_epoch": self.last_epoch, "milestones": Counter(self.milestones), "gamma": self.gamma, "base_lrs": [self.base_lr]}
+
+    def load_state_dict(self, sd):
+        self.last_epoch, self.gamma = sd["last_epoch"], sd["gamma"]
+        self.milestones = sorted(sd["milestones"].elements()) if hasattr(sd["milestones"], "elements") else sorted(sd["milestones"])
+        self.base_lr = sd.get("base_lrs", [self.base_lr])[0]
 
 
 def split_training_batch(frames: torch.Tensor):

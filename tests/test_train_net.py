@@ -174,3 +174,39 @@ def test_split_training_batch_follows_main_py():
     inp, s0, s1, ft = split_training_batch(f)
     assert inp.shape == (2, 3, 4, 4, 4) and torch.equal(inp, f[:, :, :4]) and torch.equal(ft, f[:, :, 4])
     assert torch.equal(s0, f[:, :, 5]) and torch.equal(s1, f[:, :, 6])
+
+
+def test_optimizer_and_scheduler_checkpoints_are_interchangeable_with_torch():
+    """main.py:270-271 saves `optimizer.state_dict()` / `scheduler.state_dict()`, :214-217 loads them: a checkpoint written by
+    torch.optim.Adam + MultiStepLR loads into train.Adam + train.MultiStepLR and the other way round (host logic only)."""
+    from demfi_b200 import train
+    g = torch.Generator().manual_seed(2)
+    ps = [torch.nn.Parameter(torch.randn(3, 2, generator=g)), torch.nn.Parameter(torch.randn(5, generator=g))]
+    ref = torch.optim.Adam(ps, lr=1e-4, betas=(0.9, 0.999), weight_decay=0)
+    rs = torch.optim.lr_scheduler.MultiStepLR(ref, milestones=[2, 5], gamma=0.5)
+    for _ in range(3):
+        for p in ps:
+            p.grad = torch.randn(p.shape, generator=g)
+        ref.step()
+        rs.step()
+    mine = train.Adam(ps, lr=123.0)
+    ms = train.MultiStepLR(mine, milestones=[9], gamma=0.1)
+    mine.load_state_dict(ref.state_dict())
+    ms.load_state_dict(rs.state_dict())
+    assert mine.param_groups[0]["lr"] == ref.param_groups[0]["lr"] == 0.5e-4 and mine.state[1]["step"] == 3
+    assert torch.equal(mine.state[0]["exp_avg_sq"], ref.state[ps[0]]["exp_avg_sq"])
+    assert ms.last_epoch == 3 and ms.milestones == [2, 5] and ms.gamma == 0.5 and ms.base_lr == 1e-4
+    for _ in range(2):
+        ms.step()
+        rs.step()
+    assert mine.param_groups[0]["lr"] == ref.param_groups[0]["lr"] == 0.25e-4
+    # and back: torch accepts what train.Adam / MultiStepLR write
+    ref2 = torch.optim.Adam(ps, lr=1.0)
+    ref2.load_state_dict(mine.state_dict())
+    assert ref2.param_groups[0]["lr"] == 0.25e-4 and float(ref2.state[ps[1]]["step"]) == 3.0
+    assert torch.equal(ref2.state[ps[0]]["exp_avg"], ref.state[ps[0]]["exp_avg"])
+    rs2 = torch.optim.lr_scheduler.MultiStepLR(ref2, milestones=[100], gamma=0.9)
+    rs2.load_state_dict(ms.state_dict())
+    assert rs2.last_epoch == 5 and rs2.gamma == 0.5 and sorted(rs2.milestones.elements()) == [2, 5]
+    with pytest.raises(ValueError):
+        train.Adam(ps[:1]).load_state_dict(ref.state_dict())
