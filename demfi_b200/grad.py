@@ -10,11 +10,13 @@ whose dx runs on the CUDA-core `demfi_conv2d_dgrad_strided`) and is differentiab
   dW, db    demfi_conv2d_wgrad      CUDA-core fp32 kernel (first correct path; accumulates with fp32 atomics)
 
 What the reference gets from autograd through `nn.Conv2d` (main.py:443).  NCHW tensors at the boundary (imported / exported
-with the ABI's layout kernels), NHWC inside.  No CPU or ATen fallback: CPU tensors raise.  Not yet wired into `DeMFInet.forward`
-(whose `is_training` + grad mode still raises): the warps, the splat and the fused epilogues need their own backward first.
+with the ABI's layout kernels), NHWC inside.  No CPU or ATen fallback: CPU tensors raise.  `train_net.forward_train` builds the
+whole network's training graph from this function.  Weights are packed on the host at every call (first version);
+DEMFI_GRAD_PACK_CACHE=1 keeps the packed tensors until the parameter's version counter moves.
 """
 from __future__ import annotations
 
+import os
 from typing import Tuple
 
 import numpy as np
@@ -47,6 +49,49 @@ def _pack(w: np.ndarray, b: np.ndarray, src_c: int, dev) -> Tuple[torch.Tensor, 
     bias = np.zeros(cout_pad, dtype=np.float32)
     bias[:Co] = b
     return torch.from_numpy(packed).to(dev), torch.from_numpy(bias).to(dev), cout_pad
+
+
+_PACK_CACHE: dict = {}
+_PACK_CACHE_MAX = 4096
+
+
+def _cache_on() -> bool:
+    return os.environ.get("DEMFI_GRAD_PACK_CACHE", "0") == "1"
+
+
+def _key(t):
+    return None if t is None else (t.data_ptr(), t._version, tuple(t.shape))
+
+
+def _pack_forward(weight: torch.Tensor, bias, src_c: int, dev):
+    """packed forward weights of a layer.  With DEMFI_GRAD_PACK_CACHE=1 they are kept until the parameter's version counter
+    moves (load_state_dict, torch optimizers and train.Adam all bump it), i.e. packed once per optimizer step instead of at
+    every call; off by default until that mode has been through the GPU tests."""
+    key = ("f", _key(weight), _key(bias), src_c, str(dev)) if _cache_on() else None
+    if key is not None and key in _PACK_CACHE:
+        return _PACK_CACHE[key]
+    Co = weight.shape[0]
+    b = bias.detach().cpu().numpy() if bias is not None else np.zeros(Co, dtype=np.float32)
+    out = _pack(weight.detach().cpu().numpy(), b, src_c, dev)
+    if key is not None:
+        if len(_PACK_CACHE) >= _PACK_CACHE_MAX:
+            _PACK_CACHE.clear()
+        _PACK_CACHE[key] = out
+    return out
+
+
+def _pack_rotated(weight: torch.Tensor, c0: int, c1: int, src_c: int, dev):
+    """packed weights of the dx convolution for input channels [c0, c1): w_t[ci, co, ky, kx] = W[co, ci, KH-1-ky, KW-1-kx]"""
+    key = ("r", _key(weight), c0, c1, src_c, str(dev)) if _cache_on() else None
+    if key is not None and key in _PACK_CACHE:
+        return _PACK_CACHE[key]
+    w_rot = weight.detach().flip(2, 3).transpose(0, 1)[c0:c1].contiguous().cpu().numpy()
+    out = _pack(w_rot, np.zeros(c1 - c0, dtype=np.float32), src_c, dev)
+    if key is not None:
+        if len(_PACK_CACHE) >= _PACK_CACHE_MAX:
+            _PACK_CACHE.clear()
+        _PACK_CACHE[key] = out
+    return out
 
 
 def _conv_nhwc(x: torch.Tensor, C_: int, wdev: torch.Tensor, bdev: torch.Tensor, cout_pad: int, k: Tuple[int, int], act: int,
@@ -99,8 +144,7 @@ class _Conv2d(torch.autograd.Function):
         with torch.cuda.device(dev):
             cin_pad = _ru(Ci, 8)
             xb = _to_nhwc(x.detach().float(), cin_pad)
-            b = bias.detach() if bias is not None else torch.zeros(Co, device=dev)
-            wdev, bdev, cout_pad = _pack(weight.detach().cpu().numpy(), b.cpu().numpy(), cin_pad, dev)
+            wdev, bdev, cout_pad = _pack_forward(weight, bias, cin_pad, dev)
             yb = _conv_nhwc(xb, cin_pad, wdev, bdev, cout_pad, (KH, KW), act, stride)
             y = _to_nchw(yb, Co)
         ctx.save_for_backward(weight)
@@ -135,11 +179,10 @@ class _Conv2d(torch.autograd.Function):
             elif ctx.needs_input_grad[0]:
                 # dx = conv(dz, W^T rotated): w_t[ci, co, ky, kx] = W[co, ci, KH-1-ky, KW-1-kx]; the forward kernel produces at
                 # most 256 output channels per launch, so wide inputs (GFF.0: 1152, UNet dec1: 384) go in slices of Cin
-                w_rot = weight.detach().flip(2, 3).transpose(0, 1).cpu()
                 parts = []
                 for c0 in range(0, Ci, _MAX_COUT):
                     c1 = min(Ci, c0 + _MAX_COUT)
-                    wdev, bdev, ci_pad = _pack(w_rot[c0:c1].contiguous().numpy(), np.zeros(c1 - c0, dtype=np.float32), co_pad, dev)
+                    wdev, bdev, ci_pad = _pack_rotated(weight, c0, c1, co_pad, dev)
                     parts.append(_to_nchw(_conv_nhwc(dz, co_pad, wdev, bdev, ci_pad, (KH, KW), A.ACT_NONE), c1 - c0))
                 dx = parts[0] if len(parts) == 1 else torch.cat(parts, 1)
             if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):

@@ -4,6 +4,7 @@
 was spent): first thing to run in round 2, together with DEMFI_TRAIN_E2E=1 pytest tests/test_train_net_gpu.py.
 
     python tools/bench_train.py [--size 256] [--batch 2] [--n-trn 5] [--steps 3]
+    DEMFI_GRAD_PACK_CACHE=1 python tools/bench_train.py        # weights packed once per optimizer step instead of per call
     python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tools/bench_train.py
 """
 import argparse, json, os, sys
