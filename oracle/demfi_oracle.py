@@ -63,8 +63,8 @@ def bilinear_gather(img, px, py):
     wx0 = 1.0 - wx1
     wy0 = 1.0 - wy1
     flat = img.reshape(B, C, H * W)
-    out = torch.zeros((B, C) + tuple(px.shape[1:]), dtype=img.dtype)
-    wsum = torch.zeros((B, 1) + tuple(px.shape[1:]), dtype=img.dtype)
+    out = torch.zeros((B, C) + tuple(px.shape[1:]), dtype=img.dtype, device=img.device)
+    wsum = torch.zeros((B, 1) + tuple(px.shape[1:]), dtype=img.dtype, device=img.device)
     for dy, wy in ((0, wy0), (1, wy1)):
         for dx, wx in ((0, wx0), (1, wx1)):
             xi = x0 + dx
@@ -82,8 +82,8 @@ def _unnormalised_grid(flo):
     """The coordinate `bwarp` hands to grid_sample, including its fp32 normalise ->
     un-normalise round trip (`DeMFInet.py:750-757` then align_corners=True)."""
     B, _, H, W = flo.shape
-    xx = torch.arange(W, dtype=torch.float32).view(1, 1, W).expand(B, H, W)
-    yy = torch.arange(H, dtype=torch.float32).view(1, H, 1).expand(B, H, W)
+    xx = torch.arange(W, dtype=torch.float32, device=flo.device).view(1, 1, W).expand(B, H, W)
+    yy = torch.arange(H, dtype=torch.float32, device=flo.device).view(1, H, 1).expand(B, H, W)
     gx = 2.0 * (xx + flo[:, 0]) / max(W - 1, 1) - 1.0
     gy = 2.0 * (yy + flo[:, 1]) / max(H - 1, 1) - 1.0
     px = ((gx + 1.0) / 2.0) * (W - 1)
@@ -118,10 +118,10 @@ def gaussian_splat(img, flo):
     dy = flo[:, 1:2]
     fy = torch.floor(dy)
     fx = torch.floor(dx)
-    rows = torch.arange(H).view(1, 1, H, 1)
-    cols = torch.arange(W).view(1, 1, 1, W)
-    acc = torch.zeros(B, C, H * W, dtype=img.dtype)
-    nrm = torch.zeros(B, 1, H * W, dtype=img.dtype)
+    rows = torch.arange(H, device=img.device).view(1, 1, H, 1)
+    cols = torch.arange(W, device=img.device).view(1, 1, 1, W)
+    acc = torch.zeros(B, C, H * W, dtype=img.dtype, device=img.device)
+    nrm = torch.zeros(B, 1, H * W, dtype=img.dtype, device=img.device)
     for oy in (0.0, 1.0):
         for ox in (0.0, 1.0):
             cy = fy + oy
