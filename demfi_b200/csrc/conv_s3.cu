@@ -36,6 +36,9 @@
 #include <cuda_fp16.h>
 
 #include <cstring>
+#include <mutex>
+#include <set>
+#include <utility>
 
 #include "common.cuh"
 
@@ -74,6 +77,8 @@ struct S3Params {
   int b_off, stg_off, bar_off, bias_off;  // byte offsets in (1024-aligned) shared memory
   int acc_stride;
   int taps, stages_per_tile, flush;
+  int seg_units, nseg, seg_last, grp_units, ngrp, grp_last;  // per tile: accumulation segments / weight-ring groups, in issue units
+  int unit, ustep;  // MMA issue unit: taps per unit (kernel row / column / single tap), tap-to-tap step of the A descriptor (16-byte units)
   int tma_epi, stg2_off;
   int all_full_chunks;  // every source has C % 32 == 0 (no ragged chunk)
   float comp;
@@ -128,6 +133,15 @@ static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
+}
+// Same bound, no call: a function call in the MMA issuer's loop makes ptxas keep the loop state in vector registers across
+// the call site, and every tcgen05.mma then needs its operands moved into uniform registers (R2UR) -- see s3_issue.
+__device__ __forceinline__ void mbar_wait_nocall(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 8000000000ll) __trap();
+  }
 }
 __device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, bool on, long long& acc) {
   if (!on) { mbar_wait(bar, parity); return; }
@@ -307,9 +321,175 @@ __device__ __forceinline__ void s16_encode8(float4 v0, float4 v1, uint4& hi, uin
 }  // namespace s3
 using namespace s3;
 
+// One unit of issue = U consecutive taps (a kernel row; a kernel column for Nx1 kernels; one tap for U = 1), straight-line.
+// a / b: low descriptor words of the unit's first tap; ustep / bstep: their steps from tap to tap.
+template <int U, bool K2>
+__device__ __forceinline__ void s3_issue_unit(uint32_t d_main, uint32_t d_corr, uint32_t a, uint32_t a_hi, uint32_t ustep, uint32_t b,
+                                              uint32_t b_hi, uint32_t bstep, uint32_t idesc_2n, uint32_t idesc_n, uint32_t accum) {
+#pragma unroll
+  for (int t = 0; t < U; ++t) {
+    const uint32_t at = a + (uint32_t)t * ustep, bt = b + (uint32_t)t * bstep;
+    umma_f16_ss2(d_main, at, a_hi, bt, b_hi, idesc_2n, t == 0 ? accum : 1u);  // Ah x [Bh;Bl]  k 0..15
+    if (K2) umma_f16_ss2(d_main, at + 2u, a_hi, bt + 2u, b_hi, idesc_2n, 1u);  //               k 16..31
+    umma_f16_ss2(d_corr, at + 4u, a_hi, bt, b_hi, idesc_n, 1u);               // Al x Bh
+    if (K2) umma_f16_ss2(d_corr, at + 6u, a_hi, bt + 2u, b_hi, idesc_n, 1u);
+  }
+}
+
+template <bool DBG>
+__device__ __forceinline__ void mbar_wait_i(uint32_t bar, uint32_t parity, bool skip, long long& acc) {
+  if (skip) return;  // diagnostics (tc_diag & 1024): the bare issue loop
+  if (!DBG) { mbar_wait_nocall(bar, parity); return; }
+  const long long t = clock64();
+  mbar_wait_nocall(bar, parity);
+  acc += clock64() - t;
+}
+
+// The persistent issue loop of one CTA (single thread).  Units are numbered through the tiles of the CTA; segment (accumulator
+// hand-over), weight-ring group and chunk boundaries all fall on unit boundaries (s3_plan).  Barrier layout as in the kernel.
+// Written for ptxas' uniform datapath: no calls, no min / max (vector-only instructions), counters that count down to a
+// reload value chosen by a select -- the SASS of the loop is UTCHMMA / UTCBAR / U* instructions plus the barrier waits.
+template <int U, bool DBG>
+__device__ __forceinline__ void s3_issue(const S3Params& P, uint32_t smem_base, uint32_t tmem_base, uint32_t bars, long long& w_tempty,
+                                         long long& w_ready) {
+  const demfi_conv_t& c = P.c;
+  auto bar_rawfull = [&](uint32_t a) { return bars + 8u * a; };
+  auto bar_cvfull = [&](uint32_t a) { return bars + 8u * ((uint32_t)S3_MAX_NA + a); };
+  auto bar_aempty = [&](uint32_t a) { return bars + 8u * ((uint32_t)(2 * S3_MAX_NA) + a); };
+  auto bar_tfull = [&](uint32_t a) { return bars + 8u * ((uint32_t)(3 * S3_MAX_NA) + a); };
+  auto bar_tempty = [&](uint32_t a) { return bars + 8u * ((uint32_t)(3 * S3_MAX_NA + 2) + a); };
+  const uint32_t bar_wfull = bars + 8u * (uint32_t)(3 * S3_MAX_NA + 4);
+  auto bar_bfull = [&](uint32_t sl) { return bars + 8u * ((uint32_t)(3 * S3_MAX_NA + 6) + sl); };
+  auto bar_bfree = [&](uint32_t sl) { return bars + 8u * ((uint32_t)(3 * S3_MAX_NA + 6 + S3_MAX_NS) + sl); };
+  const bool bare = (P.diag & 1024) != 0;
+  const uint32_t NA = (uint32_t)P.na, NS = (uint32_t)P.ns;
+  const uint32_t idesc0 = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(S3_BM >> 4) << 24);  // D=f32, A=B=f16, K-major, M=128
+  const uint32_t a_hi = (uint32_t)(make_desc_sw128(0u, (uint32_t)P.hw * 128u) >> 32);
+  const uint32_t b_hi = (uint32_t)(make_desc_sw64(0u) >> 32);
+  const uint32_t a_lo0 = ((smem_base >> 4) & 0x3FFFu) | (1u << 16);
+  const uint32_t b_lo0 = ((smem_base + (uint32_t)P.b_off) >> 4) & 0x3FFFu;
+  const uint32_t astep = (uint32_t)(P.a_bytes >> 4), gstep = (uint32_t)((P.gtaps * P.b_bytes) >> 4);
+  const uint32_t ustep = (uint32_t)P.ustep;        // tap to tap inside a unit
+  const uint32_t rstep = (uint32_t)P.hw << 3;      // unit to unit inside a chunk (next kernel row); U = 1: handled by kx
+  const int KW = c.KW;
+  const bool resident = P.resident != 0;
+  const int upc = P.taps / U;                       // units per chunk
+  const int chunks_per_tile = P.stages_per_tile / P.taps;
+  if ((int)blockIdx.x >= P.ntiles) return;
+
+  uint32_t slot = 0, sphase = 0, acc = 0, acc_phase = 0, abuf = 0, aphase = 0, cvphase = 0;
+  // an activation chunk is ready: straight from TMA (S16 source) or after the converter warps (fp32 source; the converter
+  // barrier of a buffer only counts the fp32 chunks that went through it, hence its own phase bit per buffer)
+  auto wait_chunk = [&](uint32_t buf, uint32_t phase, int si) {
+    if (c.src[si].fmt == DEMFI_FMT_S16) {
+      mbar_wait_i<DBG>(bar_rawfull(buf), phase, bare, w_ready);
+    } else {
+      mbar_wait_i<DBG>(bar_cvfull(buf), (cvphase >> buf) & 1u, bare, w_ready);
+      cvphase ^= 1u << buf;
+    }
+  };
+  if (resident && !bare) mbar_wait_nocall(bar_wfull, 0);
+  // the first unit's waits
+  wait_chunk(0u, 0u, 0);
+  mbar_wait_i<DBG>(bar_tempty(acc), acc_phase ^ 1u, bare, w_tempty);
+  if (!resident) mbar_wait_i<DBG>(bar_bfull(slot), sphase, bare, w_ready);
+  tc_fence_after();
+
+  // Structure (measured in tools/probe_s3*: the same MMAs cost 292 clk per stage with boundary checks after every unit and
+  // 235 clk with none; the floor is 224): a RUN of units up to the next boundary is issued by an inner loop that contains
+  // nothing but the units and two adds; the boundaries -- chunk (activation buffer hand-over), accumulation segment
+  // (accumulator hand-over), weight-ring group -- are handled between runs: commits, bookkeeping, then the waits the next run
+  // needs.  With resident weights and one segment per chunk (the 64 -> 64 3x3 ResBlock convolutions) a run is a whole chunk.
+  for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+    const bool last_tile = tile + (int)gridDim.x >= P.ntiles;
+    const int nb = tile % P.n_blocks;
+    const int N = nb == P.n_blocks - 1 ? c.cout_pad - nb * P.nb_max : P.nb_max;
+    const uint32_t idesc_n = idesc0 | ((uint32_t)(N >> 3) << 17);
+    const uint32_t idesc_2n = idesc0 | ((uint32_t)((2 * N) >> 3) << 17);
+    const uint32_t bstep = (uint32_t)N << 3;  // one stage = 2N rows x 64 bytes, in 16-byte units
+    const uint32_t bunit = bstep * (uint32_t)U;
+    // countdowns (in units): to the end of the chunk / the accumulation segment / the weight-ring group
+    int chunk_left = upc, chunks_left = chunks_per_tile;
+    int seg_left = P.nseg == 1 ? P.seg_last : P.seg_units, segs_left = P.nseg;
+    int grp_left = resident ? 0x40000000 : (P.ngrp == 1 ? P.grp_last : P.grp_units), grps_left = P.ngrp;
+    int si = 0, c0 = 0;
+    bool k2 = c.src[0].C > 16;  // channels 16..31 of the chunk exist (else they are TMA zero fill: skip their MMAs)
+    uint32_t accum = 0u;
+    uint32_t a = a_lo0 + astep * abuf;
+    uint32_t b = resident ? b_lo0 : b_lo0 + gstep * slot;
+    uint32_t d_main = tmem_base + acc * (uint32_t)P.acc_stride;
+    int kx = 0;
+#pragma unroll 1
+    while (chunks_left > 0) {
+      int run = chunk_left;
+      if (seg_left < run) run = seg_left;
+      if (grp_left < run) run = grp_left;
+      const uint32_t d_corr = d_main + (uint32_t)N;
+      // ---- the run: MMAs and two adds per unit ----
+      if (k2) {
+#pragma unroll 1
+        for (int r = 0; r < run; ++r) {
+          s3_issue_unit<U, true>(d_main, d_corr, a, a_hi, ustep, b, b_hi, bstep, idesc_2n, idesc_n, accum);
+          accum = 1u;
+          b += bunit;
+          if (U == 1) { a += 8u; if (++kx == KW) { kx = 0; a += rstep - ((uint32_t)KW << 3); } }
+          else a += rstep;
+        }
+      } else {
+#pragma unroll 1
+        for (int r = 0; r < run; ++r) {
+          s3_issue_unit<U, false>(d_main, d_corr, a, a_hi, ustep, b, b_hi, bstep, idesc_2n, idesc_n, accum);
+          accum = 1u;
+          b += bunit;
+          if (U == 1) { a += 8u; if (++kx == KW) { kx = 0; a += rstep - ((uint32_t)KW << 3); } }
+          else a += rstep;
+        }
+      }
+      // ---- boundaries: commits, bookkeeping, then the waits the next run needs.  (Waiting earlier -- before the last unit
+      // of the run -- was measured and is slower: with two activation buffers the next chunk is still in flight then.) ----
+      chunk_left -= run; seg_left -= run; grp_left -= run;
+      const bool end_chunk = chunk_left == 0, end_seg = seg_left == 0, end_group = grp_left == 0;
+      const bool more = !(end_chunk && chunks_left == 1 && last_tile);  // another unit follows in this CTA
+      if (end_group) {
+        if (!bare) umma_commit(bar_bfree(slot));
+        if (++slot == NS) { slot = 0; sphase ^= 1u; }
+        if (--grps_left == 0) grps_left = P.ngrp;  // (next tile)
+        grp_left = grps_left == 1 ? P.grp_last : P.grp_units;
+        b = b_lo0 + gstep * slot;
+      }
+      if (end_seg) {
+        if (!bare) umma_commit(bar_tfull(acc));
+        acc ^= 1u;
+        if (acc == 0) acc_phase ^= 1u;
+        if (--segs_left == 0) segs_left = P.nseg;  // (next tile)
+        seg_left = segs_left == 1 ? P.seg_last : P.seg_units;
+        d_main = tmem_base + acc * (uint32_t)P.acc_stride;
+        accum = 0u;
+      }
+      if (end_chunk) {
+        if (!bare) umma_commit(bar_aempty(abuf));
+        if (++abuf == NA) { abuf = 0; aphase ^= 1u; }
+        --chunks_left;
+        chunk_left = upc;
+        c0 += S3_KC;
+        if (c0 >= c.src[si].C) { c0 = 0; if (++si == c.nsrc) si = 0; }  // (wraps into the next tile)
+        k2 = c.src[si].C - c0 > 16;
+        a = a_lo0 + astep * abuf;
+        kx = 0;
+      }
+      if (more) {
+        if (end_chunk) wait_chunk(abuf, aphase, si);
+        if (end_seg) mbar_wait_i<DBG>(bar_tempty(acc), acc_phase ^ 1u, bare, w_tempty);
+        if (end_group) mbar_wait_i<DBG>(bar_bfull(slot), sphase, bare, w_ready);
+        tc_fence_after();
+      }
+    }
+  }
+}
+
 // DBG: per-role cycle counters (tc_diag & 128).  A template parameter, not a run-time flag: the timed variants of every
 // wait would otherwise sit between the hot instructions of all roles (instruction-cache footprint).
-template <int NMAX, bool DBG>
+template <int NMAX, bool DBG, int U>
 __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_constant__ S3Params P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -353,20 +533,56 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == S3_CV_WARPS + S3_EPI_WARPS + 1) {
+  if (warp == S3_CV_WARPS + S3_EPI_WARPS) {  // the producer warp owns the tensor-memory allocation (the MMA warp leaves early)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (P.diag & 1024) {  // diagnostics (bare issue loop): operands = ordinary fp16 values (operand VALUES change the MMA timing)
+    for (int i = threadIdx.x; i < P.stg_off / 4; i += S3_THREADS) {
+      uint32_t h = (uint32_t)i * 2654435761u + blockIdx.x * 97u;
+      h ^= h >> 15;
+      reinterpret_cast<uint32_t*>(smem)[i] = (0x3800u | (h & 0x3ffu) | ((h >> 3) & 0x8000u)) | ((0x3800u | ((h >> 10) & 0x3ffu)) << 16);
+    }
+    fence_async_smem();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);  // warp-uniform for ptxas (uniform registers)
   // Programmatic dependent launch: let the next kernel of the stream start its own prologue (barrier init, TMEM allocation,
   // resident-weight load) on SMs as they drain; everything here that reads or writes activations waits for the previous
   // kernel to have completed (griddepcontrol.wait), the loads of weights and bias (constants) do not.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
-  if (warp < S3_CV_WARPS) {
+  if (warp == S3_CV_WARPS + S3_EPI_WARPS + 1) {
+    // ===== MMA issuer: ONE elected thread runs the whole persistent loop, and its warp takes part in nothing afterwards.
+    // What sets its pace (round-2 measurements: tools/diag_timers.py, tools/mma_probe_pair.cu, ncu source page): with the
+    // activation loads, the tcgen05.ld drains and the whole epilogue switched off, the thread still needed ~300 clk per
+    // (tap, 32-channel) stage against 224 clk for the same MMAs in the probe.  The tensor core runs only ~100 clk ahead of
+    // the issuing thread, and every instruction that goes through the memory-I/O queue (R2UR, mbarrier waits, commits) is
+    // ordered behind the UTCHMMAs already issued, so the instructions after one of them are exposed.  ptxas kept the whole
+    // loop state in vector registers -- 5-9 R2UR per tap -- for two reasons found by bisection on the SASS: (1) a call in
+    // the loop (the out-of-line bounded wait), (2) the elected thread re-joining its warp for the block-wide barrier at the
+    // end of the kernel.  With neither, the state lives in uniform registers and a unit of issue (a kernel row of taps,
+    // straight-line) is UTCHMMA + uniform-datapath adds only. =====
+    if (elect_one()) {
+      const long long t_begin = dbg ? clock64() : 0;
+      long long w_tempty = 0, w_ready = 0;
+      s3_issue<U, DBG>(P, smem_base, tmem_base, bars, w_tempty, w_ready);
+      if (P.diag & 1024) {  // bare issue loop: everything has completed when this commit arrives
+        umma_commit(bar_resfull);
+        mbar_wait_nocall(bar_resfull, 0);
+      }
+      if (dbg) {
+        long long* d = P.dbg + (size_t)blockIdx.x * 16;
+        d[12] = clock64() - t_begin; d[13] = w_tempty; d[14] = w_ready;
+      }
+    }
+    return;  // no barrier below involves this warp: the remaining 15 warps meet at named barrier 1
+  }
+  if (P.diag & 1024) {
+    // diagnostics: nothing but the MMA issue loop runs
+  } else if (warp < S3_CV_WARPS) {
     // ===== converter: fp32 halo tile -> fp16 hi / lo planes, in place =====
     const int tid = (int)threadIdx.x;
     long long w_raw = 0, w_cv = 0;
@@ -478,7 +694,7 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
         uint32_t r[HMAX];
 #pragma unroll
         for (int col = 0; col < HMAX; col += 16)
-          if (col < cnum) tmem_ld16_nowait(taddr + (uint32_t)col, r + col);
+          if (col < cnum && !(P.diag & 512)) tmem_ld16_nowait(taddr + (uint32_t)col, r + col);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < HMAX; ++j) {
@@ -487,7 +703,7 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
         }
 #pragma unroll
         for (int col = 0; col < HMAX; col += 16)
-          if (col < cnum) tmem_ld16_nowait(taddr + (uint32_t)(N + col), r + col);
+          if (col < cnum && !(P.diag & 512)) tmem_ld16_nowait(taddr + (uint32_t)(N + col), r + col);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < HMAX; ++j) sum[j] = fmaf(__uint_as_float(r[j]), 1.0f / S3_LO_SCALE, sum[j]);
@@ -627,8 +843,12 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
           t /= P.tiles_x;
           const int ty0 = (t % P.tiles_y) * S3_TH - c.pad_h;
           const int n = t / P.tiles_y;
-          mbar_arrive_expect_tx(bar_rawfull(abuf), a_tx);
-          tma_load_4d(smem_base + (uint32_t)(abuf * P.a_bytes), &P.tmap[a_src], bar_rawfull(abuf), a_c0, tx0, ty0, n);
+          if ((P.diag & 256) && a_tile != (int)blockIdx.x) {
+            mbar_arrive(bar_rawfull(abuf));  // diagnostics: no activation traffic after the first tile (stale operands)
+          } else {
+            mbar_arrive_expect_tx(bar_rawfull(abuf), a_tx);
+            tma_load_4d(smem_base + (uint32_t)(abuf * P.a_bytes), &P.tmap[a_src], bar_rawfull(abuf), a_c0, tx0, ty0, n);
+          }
           if (++abuf == NA) { abuf = 0; aphase ^= 1u; }
           a_c0 += S3_KC;
           if (a_c0 >= c.src[a_src].C) {
@@ -656,146 +876,12 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
         d[8] = clock64() - t_begin;
       }
     }
-  } else {
-    // ===== MMA issuer: ONE thread runs the whole persistent loop.
-    // Measured (tools/mma_probe.cu and this kernel): the tensor pipe runs only 1-2 MMAs ahead of the issuing thread, so
-    // every instruction between two tcgen05.mma is serial with the math (a first version with ~75 instructions of
-    // bookkeeping per stage ran at 411 clk/stage against 224 clk of MMA work).  Hence: all bookkeeping (accumulator
-    // hand-over, segment ends, chunk ends) sits OUTSIDE the innermost loop, which issues a run of consecutive taps with
-    // nothing but 32-bit adds on the low descriptor words (the high words -- SBO, version, swizzle -- never change). =====
-    if (elect_one()) {
-      const uint32_t idesc0 = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(S3_BM >> 4) << 24);  // D=f32, A=B=f16, K-major, M=128
-      const uint32_t a_hi = (uint32_t)(make_desc_sw128(0u, (uint32_t)P.hw * 128u) >> 32);
-      const uint32_t b_hi = (uint32_t)(make_desc_sw64(0u) >> 32);
-      const uint32_t a_lo0 = ((smem_base >> 4) & 0x3FFFu) | (1u << 16);
-      const uint32_t b_lo0 = (b_base >> 4) & 0x3FFFu;
-      const uint32_t astep = (uint32_t)(P.a_bytes >> 4), gstep = (uint32_t)((P.gtaps * P.b_bytes) >> 4);
-      const uint32_t row_skip = (uint32_t)(P.hw - c.KW) << 3;  // extra step from the last tap of a kernel row to the next row
-      const int KW = c.KW, taps = P.taps;
-      const bool resident = P.resident != 0;
-      const bool fast33 = resident && c.KH == 3 && c.KW == 3 && P.nb_max == 64 && c.cout_pad == 64 && P.flush == 9 &&
-                          P.acc_stride == 128 && !(P.diag & 64) && P.all_full_chunks;
-      long long w_tempty = 0, w_ready = 0;
-      const long long t_begin = dbg ? clock64() : 0;
-      uint32_t slot = 0, sphase = 0, acc = 0, acc_phase = 0, abuf = 0, aphase = 0, cvphase = 0;
-      if (resident) {
-        mbar_wait(bar_wfull, 0);
-        tc_fence_after();
-      }
-      for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
-        const int N = n_of(tile % P.n_blocks);
-        const uint32_t idesc_n = idesc0 | ((uint32_t)(N >> 3) << 17);
-        const uint32_t idesc_2n = idesc0 | ((uint32_t)((2 * N) >> 3) << 17);
-        const uint32_t bstep = (uint32_t)N << 3;  // one stage = 2N rows x 64 bytes, in 16-byte units
-        int done = 0, fill = 0, seg_len = min(P.flush, P.stages_per_tile);
-        int issued = 0, gleft = resident ? P.stages_per_tile : 0;
-        uint32_t d_main = 0, d_corr = 0;
-        uint32_t b = b_lo0;  // resident bank: stage after stage
-#pragma unroll 1
-        for (int ch = 0, si = 0, c0 = 0; ch < chunks_per_tile; ++ch) {
-          if (c.src[si].fmt == DEMFI_FMT_S16) {
-            mbar_wait_t(bar_rawfull(abuf), aphase, dbg, w_ready);  // TMA -> tensor core, no converter hop
-          } else {
-            mbar_wait_t(bar_cvfull(abuf), (cvphase >> abuf) & 1u, dbg, w_ready);
-            cvphase ^= 1u << abuf;
-          }
-          tc_fence_after();
-          const bool k2 = c.src[si].C - c0 > 16;  // channels 16..31 of the chunk exist (else they are TMA zero fill: skip their MMAs)
-          c0 += S3_KC;
-          if (c0 >= c.src[si].C) { c0 = 0; ++si; }
-          uint32_t a = a_lo0 + astep * abuf;
-          int kx = 0, tap = 0;
-          if (fast33) {
-            // the dominant shape (64 -> 64 3x3, resident weights, one accumulation segment per chunk): the 36 MMAs of a chunk
-            // straight-line, every operand = one of two bases + an immediate (halo row = 10 pixels, stage = 512 x 16 bytes)
-            mbar_wait_t(bar_tempty(acc), acc_phase ^ 1u, dbg, w_tempty);
-            tc_fence_after();
-            const uint32_t dm = tmem_base + acc * 128u, dc = dm + 64u;
-            const uint32_t bb = b_lo0 + (uint32_t)ch * (9u * 512u);
-#pragma unroll
-            for (int tp = 0; tp < 9; ++tp) {
-              const uint32_t ao = (uint32_t)((tp / 3) * 80 + (tp % 3) * 8), bo = (uint32_t)tp * 512u;
-              umma_f16_ss2(dm, a + ao, a_hi, bb + bo, b_hi, idesc_2n, tp == 0 ? 0u : 1u);
-              umma_f16_ss2(dm, a + ao + 2u, a_hi, bb + bo + 2u, b_hi, idesc_2n, 1u);
-              umma_f16_ss2(dc, a + ao + 4u, a_hi, bb + bo, b_hi, idesc_n, 1u);
-              umma_f16_ss2(dc, a + ao + 6u, a_hi, bb + bo + 2u, b_hi, idesc_n, 1u);
-            }
-            umma_commit(bar_tfull(acc));
-            acc ^= 1u;
-            if (acc == 0) acc_phase ^= 1u;
-            tap = taps;
-          }
-#pragma unroll 1
-          while (tap < taps) {
-            uint32_t accum = 1u;
-            if (fill == 0) {
-              mbar_wait_t(bar_tempty(acc), acc_phase ^ 1u, dbg, w_tempty);
-              tc_fence_after();
-              d_main = tmem_base + acc * (uint32_t)P.acc_stride;
-              d_corr = d_main + (uint32_t)N;
-              accum = 0u;
-            }
-            if (gleft == 0) {  // next group of the weight ring
-              mbar_wait_t(bar_bfull(slot), sphase, dbg, w_ready);
-              tc_fence_after();
-              gleft = min(P.gtaps, P.stages_per_tile - issued);
-              b = b_lo0 + gstep * slot;
-            }
-            const int run = min(min(taps - tap, seg_len - fill), gleft);
-            if (k2) {
-#pragma unroll 1
-              for (int t = 0; t < run; ++t) {
-                umma_f16_ss2(d_main, a, a_hi, b, b_hi, idesc_2n, accum);         // Ah x [Bh;Bl]  k 0..15
-                umma_f16_ss2(d_main, a + 2u, a_hi, b + 2u, b_hi, idesc_2n, 1u);  //               k 16..31
-                umma_f16_ss2(d_corr, a + 4u, a_hi, b, b_hi, idesc_n, 1u);        // Al x Bh
-                umma_f16_ss2(d_corr, a + 6u, a_hi, b + 2u, b_hi, idesc_n, 1u);
-                accum = 1u;
-                b += bstep;
-                a += 8u;
-                if (++kx == KW) { kx = 0; a += row_skip; }
-              }
-            } else {  // a chunk of <= 16 channels (tiny Cin, ragged last chunk): one k-step per product
-#pragma unroll 1
-              for (int t = 0; t < run; ++t) {
-                umma_f16_ss2(d_main, a, a_hi, b, b_hi, idesc_2n, accum);
-                umma_f16_ss2(d_corr, a + 4u, a_hi, b, b_hi, idesc_n, 1u);
-                accum = 1u;
-                b += bstep;
-                a += 8u;
-                if (++kx == KW) { kx = 0; a += row_skip; }
-              }
-            }
-            tap += run;
-            fill += run;
-            issued += run;
-            gleft -= run;
-            if (!resident && gleft == 0) {
-              umma_commit(bar_bfree(slot));
-              if (++slot == (uint32_t)NS) { slot = 0; sphase ^= 1u; }
-            }
-            if (fill == seg_len) {
-              umma_commit(bar_tfull(acc));
-              acc ^= 1u;
-              if (acc == 0) acc_phase ^= 1u;
-              done += seg_len;
-              seg_len = min(P.flush, P.stages_per_tile - done);
-              fill = 0;
-            }
-          }
-          umma_commit(bar_aempty(abuf));
-          if (++abuf == (uint32_t)NA) { abuf = 0; aphase ^= 1u; }
-        }
-      }
-      if (dbg) {
-        long long* d = P.dbg + (size_t)blockIdx.x * 16;
-        d[12] = clock64() - t_begin; d[13] = w_tempty; d[14] = w_ready;
-      }
-    }
   }
 
+  // the epilogue warps have drained the last accumulator (hence every MMA has completed) when they arrive here
   tc_fence_before();
-  __syncthreads();
-  if (warp == S3_CV_WARPS + S3_EPI_WARPS + 1) {
+  asm volatile("bar.sync 1, %0;" ::"n"(S3_THREADS - 32) : "memory");
+  if (warp == S3_CV_WARPS + S3_EPI_WARPS) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
   }
@@ -951,6 +1037,10 @@ static int s3_plan(const demfi_conv_t& c, S3Params& P, S3EpiPlan& E, int* smem_o
   P.b_bytes = 2 * P.nb_max * 64;
   P.acc_stride = 2 * P.nb_max;
   P.taps = c.KH * c.KW;
+  // MMA issue unit: a kernel row (KW > 1), a kernel column (N x 1 kernels) or a single tap; straight-line code exists for 3, 5, 7
+  P.unit = c.KW > 1 ? c.KW : c.KH;
+  P.ustep = c.KW > 1 ? 8 : P.hw * 8;
+  if (P.unit != 3 && P.unit != 5 && P.unit != 7) { P.unit = 1; P.ustep = 8; }
   int chunks = 0;
   for (int s = 0; s < c.nsrc; ++s) chunks += (c.src[s].C + S3_KC - 1) / S3_KC;
   P.stages_per_tile = chunks * P.taps;
@@ -990,23 +1080,26 @@ static int s3_plan(const demfi_conv_t& c, S3Params& P, S3EpiPlan& E, int* smem_o
     const int want = s3_want_buffers(P.taps, chunks);
     while (P.na < want && (P.na + 1) * P.a_bytes + bank + fixed <= S3_SMEM_MAX) ++P.na;
   } else {
-    // ring of `ns` slots, each a group of `gtaps` consecutive stages (target <= 24 KB per slot, >= 3 slots)
+    // ring of `ns` slots, each a group of `gtaps` consecutive stages (target <= 24 KB per slot, >= 3 slots); groups are whole
+    // issue units.  A unit that would need more than 32 KB per slot falls back to tap-by-tap issue.
     P.na = 3;
-    int g = 24576 / P.b_bytes;
-    if (g < 1) g = 1;
+    if (P.unit * P.b_bytes > 32768) { P.unit = 1; P.ustep = 8; }
+    const int U = P.unit;
+    int g = 24576 / P.b_bytes / U * U;
+    if (g < U) g = U;
     if (g > P.stages_per_tile) g = P.stages_per_tile;
     {
       const int cap = get_option("tc_stages");  // diagnostics: stages per ring slot
-      if (cap >= 1 && cap < g) g = cap;
+      if (cap >= 1 && cap < g) g = (cap + U - 1) / U * U;
     }
     int ns = 4;
     auto fits = [&](int na_, int ns_, int g_) { return na_ * P.a_bytes + ns_ * g_ * P.b_bytes + fixed <= S3_SMEM_MAX; };
     while (!fits(P.na, ns, g)) {
       if (ns > 3) --ns;
-      else if (g > 2) --g;
+      else if (g > 2 * U) g -= U;
       else if (P.na > 2) --P.na;
       else if (ns > 2) --ns;
-      else if (g > 1) --g;
+      else if (g > U) g -= U;
       else break;
     }
     DEMFI_REQUIRE(fits(P.na, ns, g), "conv_s3: shared-memory plan does not fit");
@@ -1027,14 +1120,22 @@ static int s3_plan(const demfi_conv_t& c, S3Params& P, S3EpiPlan& E, int* smem_o
   P.all_full_chunks = 1;
   for (int s_ = 0; s_ < c.nsrc; ++s_)
     if (c.src[s_].C % S3_KC != 0) P.all_full_chunks = 0;
-  P.flush = get_option("tc_flush");
-  if (P.flush <= 0 || P.flush > P.stages_per_tile) P.flush = P.stages_per_tile;
-  {  // balanced segments
-    const int nseg = (P.stages_per_tile + P.flush - 1) / P.flush;
-    P.flush = (P.stages_per_tile + nseg - 1) / nseg;
+  {  // accumulation segments: whole issue units, balanced over the tile
+    const int units = P.stages_per_tile / P.unit;
+    int fu = get_option("tc_flush") / P.unit;
+    if (fu < 1) fu = 1;
+    if (get_option("tc_flush") <= 0 || fu > units) fu = units;
+    const int nseg = (units + fu - 1) / fu;
+    P.seg_units = (units + nseg - 1) / nseg;
+    P.nseg = (units + P.seg_units - 1) / P.seg_units;
+    P.seg_last = units - (P.nseg - 1) * P.seg_units;
+    P.flush = P.seg_units * P.unit;
+    P.grp_units = P.gtaps / P.unit;
+    P.ngrp = (units + P.grp_units - 1) / P.grp_units;
+    P.grp_last = units - (P.ngrp - 1) * P.grp_units;
   }
   P.comp = (float)get_option("tc_comp_milli") * 1e-3f * 5.9604645e-8f;
-  P.diag = get_option("tc_diag") & (1 | 16 | 32 | 64 | 128);
+  P.diag = get_option("tc_diag") & (1 | 16 | 32 | 64 | 128 | 256 | 512 | 1024);
   return 0;
 }
 
@@ -1102,22 +1203,33 @@ int launch_conv_s3(const demfi_conv_t& c, cudaStream_t st) {
     DEMFI_REQUIRE(buf != nullptr, "conv_s3: cannot allocate the role-timer buffer");
     P.dbg = buf;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    const void* fns[] = {(const void*)conv_s3_kernel<32, false>, (const void*)conv_s3_kernel<64, false>, (const void*)conv_s3_kernel<96, false>,
-                         (const void*)conv_s3_kernel<32, true>,  (const void*)conv_s3_kernel<64, true>,  (const void*)conv_s3_kernel<96, true>};
-    for (const void* f : fns) {
-      cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, S3_SMEM_MAX);
+  // one kernel per (N block width, issue unit): a single instantiation of the issue loop per kernel keeps its state in
+  // uniform registers (a switch over four inlined copies did not)
+  typedef void (*KernelFn)(S3Params);
+  static const KernelFn table[2][3][4] = {
+      {{conv_s3_kernel<32, false, 1>, conv_s3_kernel<32, false, 3>, conv_s3_kernel<32, false, 5>, conv_s3_kernel<32, false, 7>},
+       {conv_s3_kernel<64, false, 1>, conv_s3_kernel<64, false, 3>, conv_s3_kernel<64, false, 5>, conv_s3_kernel<64, false, 7>},
+       {conv_s3_kernel<96, false, 1>, conv_s3_kernel<96, false, 3>, conv_s3_kernel<96, false, 5>, conv_s3_kernel<96, false, 7>}},
+      {{conv_s3_kernel<32, true, 1>, conv_s3_kernel<32, true, 3>, conv_s3_kernel<32, true, 5>, conv_s3_kernel<32, true, 7>},
+       {conv_s3_kernel<64, true, 1>, conv_s3_kernel<64, true, 3>, conv_s3_kernel<64, true, 5>, conv_s3_kernel<64, true, 7>},
+       {conv_s3_kernel<96, true, 1>, conv_s3_kernel<96, true, 3>, conv_s3_kernel<96, true, 5>, conv_s3_kernel<96, true, 7>}}};
+  const KernelFn fn = table[P.dbg != nullptr ? 1 : 0][P.nb_max <= 32 ? 0 : P.nb_max <= 64 ? 1 : 2][P.unit >> 1];
+  {
+    // cudaFuncSetAttribute applies per device: remember which devices have seen which kernel
+    static std::mutex mu;
+    static std::set<std::pair<int, const void*>> done;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(mu);
+    if (!done.count({dev, (const void*)fn})) {
+      cudaError_t e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, S3_SMEM_MAX);
       DEMFI_REQUIRE(e == cudaSuccess, "conv_s3: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
+      done.insert({dev, (const void*)fn});
     }
-    attr_set = true;
   }
   int grid = P.ntiles < s3_num_sms() ? P.ntiles : s3_num_sms();
   if (get_option("tc_grid") > 0 && get_option("tc_grid") < grid) grid = get_option("tc_grid");
   {
-    void (*fn)(S3Params) = nullptr;
-    if (P.dbg != nullptr) fn = P.nb_max <= 32 ? conv_s3_kernel<32, true> : P.nb_max <= 64 ? conv_s3_kernel<64, true> : conv_s3_kernel<96, true>;
-    else fn = P.nb_max <= 32 ? conv_s3_kernel<32, false> : P.nb_max <= 64 ? conv_s3_kernel<64, false> : conv_s3_kernel<96, false>;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(S3_THREADS);
