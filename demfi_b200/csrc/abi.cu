@@ -28,6 +28,8 @@ static std::atomic<int> g_opt_comp{270};
 static std::atomic<int> g_opt_stages{0};  // diagnostics: cap on pipeline stages (0 = as many as fit)
 static std::atomic<int> g_opt_grid{0};    // diagnostics: cap on persistent CTAs (0 = one per SM)
 static std::atomic<int> g_opt_pdl{0};     // programmatic dependent launch between consecutive conv_s3 kernels (measured: 47.6 vs 46.6 ms per forward, off)
+static std::atomic<int> g_opt_prefetch{2};  // conv_s3: halo-tile chunks prefetched into L2 beyond the TMA loads in flight
+static std::atomic<int> g_opt_nwide{1};     // conv_s3: Cout 97..128 as ONE N block (N' = 256 MMAs) instead of blocks of 64
 static std::atomic<int> g_opt_gen{3};     // DEMFI_CONV_TC16 kernel generation: 3 = conv_s3 where supported, 2 = conv_h3 only
 int get_option(const char* name) {
   if (!strcmp(name, "tc_mask_hi")) return g_opt_mask_hi.load();
@@ -40,6 +42,8 @@ int get_option(const char* name) {
   if (!strcmp(name, "tc_grid")) return g_opt_grid.load();
   if (!strcmp(name, "tc_gen")) return g_opt_gen.load();
   if (!strcmp(name, "tc_pdl")) return g_opt_pdl.load();
+  if (!strcmp(name, "tc_prefetch")) return g_opt_prefetch.load();
+  if (!strcmp(name, "tc_nwide")) return g_opt_nwide.load();
   return -1;
 }
 
@@ -102,6 +106,8 @@ int demfi_set_option(const char* name, int32_t value) {
   if (!strcmp(name, "tc_a_tmem")) { g_opt_atmem.store(value ? 1 : 0); return 0; }
   if (!strcmp(name, "tc_grid")) { g_opt_grid.store(value < 0 ? 0 : value); return 0; }
   if (!strcmp(name, "tc_pdl")) { g_opt_pdl.store(value ? 1 : 0); return 0; }
+  if (!strcmp(name, "tc_prefetch")) { g_opt_prefetch.store(value < 0 ? 0 : value); return 0; }
+  if (!strcmp(name, "tc_nwide")) { g_opt_nwide.store(value ? 1 : 0); return 0; }
   if (!strcmp(name, "tc_gen")) {
     DEMFI_REQUIRE(value == 2 || value == 3, "set_option: tc_gen must be 2 or 3");
     g_opt_gen.store(value);
@@ -121,7 +127,7 @@ int demfi_get_option(const char* name, int32_t* value) {
 size_t demfi_packed_weight_floats(int32_t kind, int32_t KH, int32_t KW, const int32_t* src_C, int32_t nsrc,
                                   int32_t cout_pad) {
   if (kind == DEMFI_CONV_TC) return tc_packed_floats(KH, KW, src_C, nsrc, cout_pad);
-  if (kind == DEMFI_CONV_TC16) return h3_packed_floats(KH, KW, src_C, nsrc, cout_pad);
+  if (kind == DEMFI_CONV_TC16 || kind == DEMFI_CONV_TC16W) return h3_packed_floats(KH, KW, src_C, nsrc, cout_pad);
   int k_total = 0;
   for (int s = 0; s < nsrc; ++s) k_total += src_C[s];
   return (size_t)KH * KW * k_total * cout_pad;
@@ -139,6 +145,8 @@ int demfi_pack_weights(int32_t kind, const float* w, int32_t Co, int32_t Ci, int
   for (int n = 0; n < cout_pad; ++n) DEMFI_REQUIRE(out_map[n] >= -1 && out_map[n] < Co, "pack_weights: out_map[%d] out of range", n);
   if (kind == DEMFI_CONV_TC) return tc_pack_weights(w, Co, Ci, KH, KW, in_map, src_C, nsrc, out_map, cout_pad, out);
   if (kind == DEMFI_CONV_TC16) return h3_pack_weights(w, Co, Ci, KH, KW, in_map, src_C, nsrc, out_map, cout_pad, out);
+  if (kind == DEMFI_CONV_TC16W)
+    return h3_pack_weights(w, Co, Ci, KH, KW, in_map, src_C, nsrc, out_map, cout_pad, out, s3_nb_max(kind, cout_pad));
   // FFMA layout: [tap][k][cout_pad]
   const int taps = KH * KW;
   for (int tap = 0; tap < taps; ++tap)
@@ -163,8 +171,9 @@ int demfi_conv_describe(const demfi_conv_t* c, int32_t* info) {
   for (int i = 0; i < 16; ++i) info[i] = 0;
   if (c->kind == DEMFI_CONV_FFMA) return 0;
   if (c->kind == DEMFI_CONV_TC) { info[0] = 1; return 0; }
-  DEMFI_REQUIRE(c->kind == DEMFI_CONV_TC16, "conv_describe: unknown kind %d", c->kind);
-  if (g_opt_gen.load() == 3 && s3_supports(*c)) {
+  DEMFI_REQUIRE(c->kind == DEMFI_CONV_TC16 || c->kind == DEMFI_CONV_TC16W, "conv_describe: unknown kind %d", c->kind);
+  if (c->kind == DEMFI_CONV_TC16W) DEMFI_REQUIRE(s3_supports(*c), "conv_describe: DEMFI_CONV_TC16W needs a convolution conv_s3 supports");
+  if ((g_opt_gen.load() == 3 || c->kind == DEMFI_CONV_TC16W) && s3_supports(*c)) {
     info[0] = 3;
     return s3_describe(*c, info);
   }
@@ -217,13 +226,17 @@ int demfi_conv2d(const demfi_conv_t* c, void* stream) {
       }
     }
     if (any_s16)
-      DEMFI_REQUIRE(c->kind == DEMFI_CONV_TC16 && g_opt_gen.load() == 3 && s3_supports(*c) && s3_s16_ok(*c),
+      DEMFI_REQUIRE(((c->kind == DEMFI_CONV_TC16 && g_opt_gen.load() == 3) || c->kind == DEMFI_CONV_TC16W) && s3_supports(*c) && s3_s16_ok(*c),
                     "conv2d: the S16 activation format is only implemented by the conv_s3 kernel (stride 1, TMA epilogue)");
   }
   if (c->kind == DEMFI_CONV_TC) return launch_conv_tc(*c, (cudaStream_t)stream);
   if (c->kind == DEMFI_CONV_TC16) {
     if (g_opt_gen.load() == 3 && s3_supports(*c)) return launch_conv_s3(*c, (cudaStream_t)stream);
     return launch_conv_h3(*c, (cudaStream_t)stream);
+  }
+  if (c->kind == DEMFI_CONV_TC16W) {
+    DEMFI_REQUIRE(s3_supports(*c), "conv2d: DEMFI_CONV_TC16W needs a convolution conv_s3 supports (stride 1, no up-sampled source)");
+    return launch_conv_s3(*c, (cudaStream_t)stream);
   }
   DEMFI_REQUIRE(c->kind == DEMFI_CONV_FFMA, "conv2d: unknown kind %d", c->kind);
   return launch_conv_ffma(*c, (cudaStream_t)stream);

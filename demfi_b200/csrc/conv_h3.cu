@@ -630,10 +630,10 @@ size_t h3_packed_floats(int KH, int KW, const int32_t* src_C, int nsrc, int cout
 }
 
 int h3_pack_weights(const float* w, int Co, int Ci, int KH, int KW, const int32_t* in_map, const int32_t* src_C,
-                    int nsrc, const int32_t* out_map, int cout_pad, float* out) {
+                    int nsrc, const int32_t* out_map, int cout_pad, float* out, int nb_max) {
   DEMFI_REQUIRE(cout_pad % 16 == 0 && cout_pad <= 256, "h3_pack_weights: cout_pad must be a multiple of 16 and <= 256");
   const int taps = KH * KW;
-  const int nbm = h3_nb_max(cout_pad);
+  const int nbm = nb_max > 0 ? nb_max : h3_nb_max(cout_pad);  // nb_max > 0: the N blocking of DEMFI_CONV_TC16W (conv_s3)
   const int n_blocks = (cout_pad + nbm - 1) / nbm;
   int chunks = 0;
   for (int s = 0; s < nsrc; ++s) chunks += (src_C[s] + H3_KC - 1) / H3_KC;

@@ -53,21 +53,29 @@ constexpr int S3_MAX_NA = 6;   // halo-tile buffers (3 in general; up to 6 for 1
 constexpr int S3_MAX_NS = 8;   // weight ring
 constexpr int S3_BOX_BYTES = S3_BM * 128;  // one 32-channel staging box
 constexpr int S3_NBARS = 3 * S3_MAX_NA + 4 + 2 + 2 * S3_MAX_NS;
+constexpr int S3_MAX_E = 8;    // epilogue plan entries (N blocks x sub-blocks)
+constexpr int S3_MAX_O = 8;    // destination tensor maps
+constexpr int S3_MAX_OL = 16;  // (entry, destination) pairs
 constexpr float S3_LO_SCALE = 2048.0f;
 
 struct S3Params {
   CUtensorMap tmap[DEMFI_MAX_SRC];  // activation sources
-  // TMA epilogue, planned per N block (S3_MAX_BLK blocks): every block is covered by segments that are all alike
-  // (multi-destination convs such as LFF), so a tile has ONE activation, ONE optional residual pair, 1-2 destinations.
-  CUtensorMap omap[DEMFI_MAX_SEG];  // destinations; block nb uses omap[b_o0[nb] .. b_o0[nb] + b_on[nb])
-  CUtensorMap rmap[DEMFI_MAX_SEG];  // first operand (residual / GRU h) of block nb
-  CUtensorMap r2map[DEMFI_MAX_SEG]; // second operand (GRU z) of block nb
-  int b_seg[DEMFI_MAX_SEG];         // representative segment of the block (-1: nothing to store)
-  int b_o0[DEMFI_MAX_SEG], b_on[DEMFI_MAX_SEG];
-  int b_nres[DEMFI_MAX_SEG];        // operands to fetch (0, 1, 2)
-  int b_roff[DEMFI_MAX_SEG];        // first operand: 0 = fetched into the result tile (same format), else into the second tile
-  int o_c0[DEMFI_MAX_SEG];          // destination channel of the block's first channel, per destination
-  int r_c0[DEMFI_MAX_SEG];          // same for the operands
+  // TMA epilogue, planned on the host per ENTRY = (N block, sub-block).  A sub-block is the whole N block when every segment
+  // that intersects the block is alike (one result, 1-2 destinations: the common case), else 32 channels = one staging box
+  // (multi-head convolutions whose heads differ in activation / format / operands inside one MMA tile: GRU z | r, the
+  // dense-block "push" convolutions).  Entry e = nb * nsb + sb.
+  CUtensorMap omap[S3_MAX_O];         // destinations (one per segment; one per quadrant for a pixel-shuffle segment)
+  CUtensorMap rmap[DEMFI_MAX_SEG];    // first operand (residual / GRU h) of a segment
+  CUtensorMap r2map[DEMFI_MAX_SEG];   // second operand (GRU z) of a segment
+  int sbw, nsb;                       // sub-block width in channels, sub-blocks per full N block
+  signed char e_seg[S3_MAX_E];        // representative segment of the entry (-1: nothing to store)
+  signed char e_nres[S3_MAX_E];       // operands to fetch (0, 1, 2)
+  signed char e_o0[S3_MAX_E], e_on[S3_MAX_E];  // destinations: ol_*[e_o0 .. e_o0 + e_on)
+  int e_roff[S3_MAX_E];               // first operand: 0 = fetched into the result tile (same format), else into the second tile
+  int e_rc0[S3_MAX_E];                // channel of the entry's first channel inside the operand tensors
+  int e_info[S3_MAX_E];               // packed for the store phase: seg.fmt | act << 3 | nres << 6 | (operand in the second tile) << 8
+  signed char ol_map[S3_MAX_OL];      // destination list: tensor map ...
+  int ol_c0[S3_MAX_OL];               // ... and the channel coordinate of the entry's first channel in it
   demfi_conv_t c;
   int tiles_x, tiles_y, ntiles, n_blocks, nb_max;
   int hw, hh, halo_px;
@@ -81,6 +89,7 @@ struct S3Params {
   int unit, ustep;  // MMA issue unit: taps per unit (kernel row / column / single tap), tap-to-tap step of the A descriptor (16-byte units)
   int tma_epi, stg2_off;
   int all_full_chunks;  // every source has C % 32 == 0 (no ragged chunk)
+  int all_s16;          // every source is in the S16 format: the converter warps have nothing to do
   float comp;
   int diag;
   long long* dbg;
@@ -377,20 +386,18 @@ __device__ __forceinline__ void s3_issue(const S3Params& P, uint32_t smem_base, 
   const int chunks_per_tile = P.stages_per_tile / P.taps;
   if ((int)blockIdx.x >= P.ntiles) return;
 
-  uint32_t slot = 0, sphase = 0, acc = 0, acc_phase = 0, abuf = 0, aphase = 0, cvphase = 0;
-  // an activation chunk is ready: straight from TMA (S16 source) or after the converter warps (fp32 source; the converter
-  // barrier of a buffer only counts the fp32 chunks that went through it, hence its own phase bit per buffer)
-  auto wait_chunk = [&](uint32_t buf, uint32_t phase, int si) {
-    if (c.src[si].fmt == DEMFI_FMT_S16) {
-      mbar_wait_i<DBG>(bar_rawfull(buf), phase, bare, w_ready);
-    } else {
-      mbar_wait_i<DBG>(bar_cvfull(buf), (cvphase >> buf) & 1u, bare, w_ready);
-      cvphase ^= 1u << buf;
-    }
+  uint32_t slot = 0, sphase = 0, acc = 0, acc_phase = 0, abuf = 0, aphase = 0;
+  // An activation chunk is ready: straight from TMA when EVERY source is S16 (the converter warps are idle), else after the
+  // converter warps, which then see every chunk -- they convert the fp32 ones and merely pass the S16 ones on.  (Waiting on
+  // the TMA barrier for the S16 chunks of a mixed convolution left the converter warps outside the flow control: lapped by
+  // producer + issuer by two phases of a buffer, their parity wait never returned -- a hang seen at 1280x736 only.)
+  const bool all_s16 = P.all_s16 != 0;
+  auto wait_chunk = [&](uint32_t buf, uint32_t phase) {
+    mbar_wait_i<DBG>(all_s16 ? bar_rawfull(buf) : bar_cvfull(buf), phase, bare, w_ready);
   };
   if (resident && !bare) mbar_wait_nocall(bar_wfull, 0);
   // the first unit's waits
-  wait_chunk(0u, 0u, 0);
+  wait_chunk(0u, 0u);
   mbar_wait_i<DBG>(bar_tempty(acc), acc_phase ^ 1u, bare, w_tempty);
   if (!resident) mbar_wait_i<DBG>(bar_bfull(slot), sphase, bare, w_ready);
   tc_fence_after();
@@ -478,7 +485,7 @@ __device__ __forceinline__ void s3_issue(const S3Params& P, uint32_t smem_base, 
         kx = 0;
       }
       if (more) {
-        if (end_chunk) wait_chunk(abuf, aphase, si);
+        if (end_chunk) wait_chunk(abuf, aphase);
         if (end_seg) mbar_wait_i<DBG>(bar_tempty(acc), acc_phase ^ 1u, bare, w_tempty);
         if (end_group) mbar_wait_i<DBG>(bar_bfull(slot), sphase, bare, w_ready);
         tc_fence_after();
@@ -589,15 +596,14 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
     const long long t_begin = dbg ? clock64() : 0;
     int abuf = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < P.ntiles && !P.all_s16; tile += gridDim.x) {  // (every source S16: nothing to do here)
       for (int si = 0; si < c.nsrc; ++si) {
-        const bool s16 = c.src[si].fmt == DEMFI_FMT_S16;  // already fp16 hi | lo rows: the MMA reads the TMA tile as it lands
+        const bool s16 = c.src[si].fmt == DEMFI_FMT_S16;  // already fp16 hi | lo rows: passed on as it landed
         for (int c0 = 0; c0 < c.src[si].C; c0 += S3_KC) {
-          // every chunk is waited for, converted or not: a parity wait is only meaningful when the waiter is at most
-          // one phase behind the barrier (skipping the S16 chunks let a later wait fall through on a stale phase)
+          // every chunk passes through these warps (see s3_issue): they are part of the buffer hand-over, never lapped
           mbar_wait_t(bar_rawfull(abuf), aphase, dbg, w_raw);
+          const long long t_cv = dbg ? clock64() : 0;
           if (!s16) {
-            const long long t_cv = dbg ? clock64() : 0;
             const uint32_t a_addr = smem_base + (uint32_t)(abuf * P.a_bytes);
 #pragma unroll 1
             for (int p = (P.diag & 16) ? P.halo_px : tid; p < P.halo_px; p += S3_CV_THREADS) {
@@ -618,10 +624,10 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
               }
             }
             fence_async_smem();  // generic-proxy writes -> visible to the tensor core / TMA (async proxy)
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_cvfull(abuf));
-            if (dbg) w_cv += clock64() - t_cv;
           }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_cvfull(abuf));
+          if (dbg) w_cv += clock64() - t_cv;
           if (++abuf == NA) { abuf = 0; aphase ^= 1u; }
         }
       }
@@ -653,6 +659,8 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
     }
     asm volatile("bar.sync 2, %0;" ::"n"(S3_EPI_THREADS) : "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");  // operand tiles and destinations belong to earlier kernels
+    const bool per_box = P.nsb > 1;  // entries are 32-channel boxes (else one entry per N block)
+    const uint32_t emask = per_box ? 0xffffffffu : 0u;
     for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
       int t = tile;
       const int nb = t % P.n_blocks;
@@ -667,18 +675,29 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
       const int oy = ty0 + (m >> 3), ox = tx0 + (m & 7);
       const bool valid = (oy < c.H) && (ox < c.W);
       const int nboxes = (N + 31) >> 5;
-      const int sidx = P.tma_epi ? P.b_seg[nb] : -1;
-      const int nres = P.tma_epi ? P.b_nres[nb] : 0;
+      const int e0 = nb * P.nsb;                                  // first entry of this N block
+      const int ne = per_box ? nboxes : 1;                        // entries of this N block
+      int nres_any = 0;
+      if (P.tma_epi)
+        for (int sb = 0; sb < ne; ++sb) nres_any += P.e_nres[e0 + sb];
       if (P.tma_epi) {
         // the staging buffers are free once the previous tile's stores have read them; then fetch the operand tiles
         if (e_tid == 0) {
           if (store_pending) bulk_wait_read0();
-          if (nres > 0) {
-            mbar_arrive_expect_tx(bar_resfull, (uint32_t)(nres * nboxes * S3_BOX_BYTES));
-            for (int b = 0; b < nboxes; ++b) {
-              tma_load_4d(stg + (uint32_t)(P.b_roff[nb] + b * S3_BOX_BYTES), &P.rmap[nb], bar_resfull, P.r_c0[nb] + 32 * b, tx0, ty0, n);
-              if (nres > 1)
-                tma_load_4d(stg + (uint32_t)(P.stg2_off + b * S3_BOX_BYTES), &P.r2map[nb], bar_resfull, P.r_c0[nb] + 32 * b, tx0, ty0, n);
+          if (nres_any > 0) {
+            uint32_t tx = 0;
+            for (int sb = 0; sb < ne; ++sb) tx += (uint32_t)(P.e_nres[e0 + sb] * (per_box ? 1 : nboxes) * S3_BOX_BYTES);
+            mbar_arrive_expect_tx(bar_resfull, tx);
+            for (int sb = 0; sb < ne; ++sb) {
+              const int e = e0 + sb, nr = P.e_nres[e];
+              if (nr == 0) continue;
+              const int sg = P.e_seg[e];
+              const int b0 = per_box ? sb : 0, b1 = per_box ? sb + 1 : nboxes;
+              for (int b = b0; b < b1; ++b) {
+                tma_load_4d(stg + (uint32_t)(P.e_roff[e] + b * S3_BOX_BYTES), &P.rmap[sg], bar_resfull, P.e_rc0[e] + 32 * (b - b0), tx0, ty0, n);
+                if (nr > 1)
+                  tma_load_4d(stg + (uint32_t)(P.stg2_off + b * S3_BOX_BYTES), &P.r2map[sg], bar_resfull, P.e_rc0[e] + 32 * (b - b0), tx0, ty0, n);
+              }
             }
           }
         }
@@ -691,22 +710,31 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
         mbar_wait_t(bar_tfull(acc), acc_phase, dbg, w_tfull);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * P.acc_stride) + (uint32_t)cbeg;
-        uint32_t r[HMAX];
+        // 32 columns at a time (the wide N = 128 blocks hold 64 columns per thread: the partial sums stay in registers, the
+        // drained values pass through a 32-register window)
 #pragma unroll
-        for (int col = 0; col < HMAX; col += 16)
-          if (col < cnum && !(P.diag & 512)) tmem_ld16_nowait(taddr + (uint32_t)col, r + col);
-        tmem_ld_wait();
+        for (int c32 = 0; c32 < HMAX; c32 += 32) {
+          constexpr int RW = HMAX < 32 ? HMAX : 32;
+          uint32_t r[RW];
 #pragma unroll
-        for (int j = 0; j < HMAX; ++j) {
-          const float v = __uint_as_float(r[j]) * gain;
-          sum[j] = first ? v : sum[j] + v;
+          for (int col = 0; col < RW; col += 16)
+            if (c32 + col < HMAX && c32 + col < cnum && !(P.diag & 512)) tmem_ld16_nowait(taddr + (uint32_t)(c32 + col), r + col);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < RW; ++j) {
+            if (c32 + j < HMAX) {
+              const float v = __uint_as_float(r[j]) * gain;
+              sum[c32 + j] = first ? v : sum[c32 + j] + v;
+            }
+          }
+#pragma unroll
+          for (int col = 0; col < RW; col += 16)
+            if (c32 + col < HMAX && c32 + col < cnum && !(P.diag & 512)) tmem_ld16_nowait(taddr + (uint32_t)(N + c32 + col), r + col);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < RW; ++j)
+            if (c32 + j < HMAX) sum[c32 + j] = fmaf(__uint_as_float(r[j]), 1.0f / S3_LO_SCALE, sum[c32 + j]);
         }
-#pragma unroll
-        for (int col = 0; col < HMAX; col += 16)
-          if (col < cnum && !(P.diag & 512)) tmem_ld16_nowait(taddr + (uint32_t)(N + col), r + col);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < HMAX; ++j) sum[j] = fmaf(__uint_as_float(r[j]), 1.0f / S3_LO_SCALE, sum[j]);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty(acc));
@@ -716,8 +744,7 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
       const long long t_store = dbg ? clock64() : 0;
       if (P.tma_epi) {
         // ---- staged epilogue: bias, operands, activation -> swizzled box layout -> TMA store ----
-        const int act = sidx >= 0 ? c.seg[sidx].act : DEMFI_ACT_NONE;
-        if (nres > 0) {
+        if (nres_any > 0) {
           mbar_wait(bar_resfull, res_phase);
           res_phase ^= 1u;
         } else {
@@ -725,72 +752,71 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
         }
         const uint32_t row = stg + (uint32_t)m * 128u;
         const uint32_t sw = (uint32_t)m & 7u;
-        const int sfmt = sidx >= 0 ? c.seg[sidx].fmt : 0;
-        const uint32_t roff = (uint32_t)P.b_roff[nb];  // where the first operand tile was fetched (0: in place)
         const float4 zero4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        if (sfmt & DEMFI_SEG_DST_S16) {
-          // S16 destination: eight channels per step = one hi chunk + one lo chunk of the pixel's 128-byte group row
-          // (an operand tile, when present, is in the same format and the same place: read, then overwritten in place)
+        // Eight columns per step.  The step's entry (the N block, or its 32-channel box) says through ONE packed word --
+        // independent loads, no dependent chain across the unrolled steps -- whether the result is stored S16 (one hi chunk +
+        // one lo chunk of the pixel's 128-byte group row; an operand tile in the same format is in the same place: read, then
+        // overwritten in place) or fp32 (two 4-channel chunks), with which activation and operands.
 #pragma unroll
-          for (int col = 0; col < HMAX; col += 8) {
-            if (col < cnum && !(P.diag & 32)) {
-              const int chn = cbeg + col;
-              const uint32_t g8 = (uint32_t)((chn & 31) >> 3);
-              const uint32_t base = row + (uint32_t)((chn >> 5) * S3_BOX_BYTES);
-              const uint32_t a_hi = base + ((g8 ^ sw) << 4), a_lo = base + (((g8 + 4u) ^ sw) << 4);
-              const float4 b0 = as_f4(lds128(bias_s + (uint32_t)(n0 + chn) * 4u)), b1 = as_f4(lds128(bias_s + (uint32_t)(n0 + chn + 4) * 4u));
-              float4 v0 = make_float4(sum[col] + b0.x, sum[col + 1] + b0.y, sum[col + 2] + b0.z, sum[col + 3] + b0.w);
-              float4 v1 = make_float4(sum[col + 4] + b1.x, sum[col + 5] + b1.y, sum[col + 6] + b1.z, sum[col + 7] + b1.w);
-              float4 h0 = zero4, h1 = zero4, z0 = zero4, z1 = zero4;
+        for (int col = 0; col < HMAX; col += 8) {
+          if (col < cnum && !(P.diag & 32)) {
+            const int chn = cbeg + col;
+            const uint32_t info = (uint32_t)P.e_info[e0 + (int)((uint32_t)(chn >> 5) & emask)];
+            const int sfmt = (int)(info & 7u), act = (int)((info >> 3) & 7u), nres = (int)((info >> 6) & 3u);
+            const uint32_t roff = (info & 256u) ? (uint32_t)P.stg2_off : 0u;
+            const uint32_t base = row + (uint32_t)((chn >> 5) * S3_BOX_BYTES);
+            const float4 b0 = as_f4(lds128(bias_s + (uint32_t)(n0 + chn) * 4u)), b1 = as_f4(lds128(bias_s + (uint32_t)(n0 + chn + 4) * 4u));
+            float4 v0 = make_float4(sum[col] + b0.x, sum[col + 1] + b0.y, sum[col + 2] + b0.z, sum[col + 3] + b0.w);
+            float4 v1 = make_float4(sum[col + 4] + b1.x, sum[col + 5] + b1.y, sum[col + 6] + b1.z, sum[col + 7] + b1.w);
+            float4 h0 = zero4, h1 = zero4, z0 = zero4, z1 = zero4;
+            if (sfmt & DEMFI_SEG_DST_S16) {
               if (nres > 0) op_load8(base + roff, chn, sw, (sfmt & DEMFI_SEG_RES_S16) != 0, h0, h1);
               if (nres > 1) op_load8(base + (uint32_t)P.stg2_off, chn, sw, (sfmt & DEMFI_SEG_RES2_S16) != 0, z0, z1);
-              if (act == DEMFI_ACT_NONE || act == DEMFI_ACT_RELU) {
-                v0.x += h0.x; v0.y += h0.y; v0.z += h0.z; v0.w += h0.w;
-                v1.x += h1.x; v1.y += h1.y; v1.z += h1.z; v1.w += h1.w;
-                if (act == DEMFI_ACT_RELU) {
-                  v0.x = fmaxf(v0.x, 0.0f); v0.y = fmaxf(v0.y, 0.0f); v0.z = fmaxf(v0.z, 0.0f); v0.w = fmaxf(v0.w, 0.0f);
-                  v1.x = fmaxf(v1.x, 0.0f); v1.y = fmaxf(v1.y, 0.0f); v1.z = fmaxf(v1.z, 0.0f); v1.w = fmaxf(v1.w, 0.0f);
-                }
-              } else {
-                v0 = finish4v(act, v0, h0, z0);
-                v1 = finish4v(act, v1, h1, z1);
+            } else {
+              if (nres > 0) {
+                h0 = op_load4(base + roff, chn, sw, (sfmt & DEMFI_SEG_RES_S16) != 0);
+                h1 = op_load4(base + roff, chn + 4, sw, (sfmt & DEMFI_SEG_RES_S16) != 0);
               }
+              if (nres > 1) {
+                z0 = op_load4(base + (uint32_t)P.stg2_off, chn, sw, (sfmt & DEMFI_SEG_RES2_S16) != 0);
+                z1 = op_load4(base + (uint32_t)P.stg2_off, chn + 4, sw, (sfmt & DEMFI_SEG_RES2_S16) != 0);
+              }
+            }
+            if (act == DEMFI_ACT_NONE || act == DEMFI_ACT_RELU) {  // the common case stays inline (a few FADD / FMNMX)
+              v0.x += h0.x; v0.y += h0.y; v0.z += h0.z; v0.w += h0.w;
+              v1.x += h1.x; v1.y += h1.y; v1.z += h1.z; v1.w += h1.w;
+              if (act == DEMFI_ACT_RELU) {
+                v0.x = fmaxf(v0.x, 0.0f); v0.y = fmaxf(v0.y, 0.0f); v0.z = fmaxf(v0.z, 0.0f); v0.w = fmaxf(v0.w, 0.0f);
+                v1.x = fmaxf(v1.x, 0.0f); v1.y = fmaxf(v1.y, 0.0f); v1.z = fmaxf(v1.z, 0.0f); v1.w = fmaxf(v1.w, 0.0f);
+              }
+            } else {
+              v0 = finish4v(act, v0, h0, z0);
+              v1 = finish4v(act, v1, h1, z1);
+            }
+            if (sfmt & DEMFI_SEG_DST_S16) {
+              const uint32_t g8 = (uint32_t)((chn & 31) >> 3);
               uint4 hi, lo;
               s16_encode8(v0, v1, hi, lo);
-              sts128(a_hi, hi);
-              sts128(a_lo, lo);
-            }
-          }
-        } else {
-#pragma unroll
-          for (int col = 0; col < HMAX; col += 4) {
-            if (col < cnum && !(P.diag & 32)) {
-              const int chn = cbeg + col;  // channel within the N block
-              const uint32_t base = row + (uint32_t)((chn >> 5) * S3_BOX_BYTES);
-              const uint32_t addr = base + (((uint32_t)((chn & 31) >> 2) ^ sw) << 4);
-              const float4 b = as_f4(lds128(bias_s + (uint32_t)(n0 + chn) * 4u));
-              float4 v = make_float4(sum[col] + b.x, sum[col + 1] + b.y, sum[col + 2] + b.z, sum[col + 3] + b.w);
-              float4 h = zero4;
-              if (nres > 0) h = op_load4(base + roff, chn, sw, (sfmt & DEMFI_SEG_RES_S16) != 0);
-              if (act == DEMFI_ACT_NONE || act == DEMFI_ACT_RELU) {  // the common case stays inline (a few FADD / FMNMX)
-                v.x += h.x; v.y += h.y; v.z += h.z; v.w += h.w;
-                if (act == DEMFI_ACT_RELU) {
-                  v.x = fmaxf(v.x, 0.0f); v.y = fmaxf(v.y, 0.0f); v.z = fmaxf(v.z, 0.0f); v.w = fmaxf(v.w, 0.0f);
-                }
-              } else {
-                float4 z = zero4;
-                if (nres > 1) z = op_load4(base + (uint32_t)P.stg2_off, chn, sw, (sfmt & DEMFI_SEG_RES2_S16) != 0);
-                v = finish4v(act, v, h, z);
-              }
-              sts128(addr, as_u4(v));
+              sts128(base + ((g8 ^ sw) << 4), hi);
+              sts128(base + (((g8 + 4u) ^ sw) << 4), lo);
+            } else {
+              const uint32_t q = (uint32_t)((chn & 31) >> 2);
+              sts128(base + ((q ^ sw) << 4), as_u4(v0));
+              sts128(base + (((q + 1u) ^ sw) << 4), as_u4(v1));
             }
           }
         }
         fence_async_smem();
         asm volatile("bar.sync 3, %0;" ::"n"(S3_EPI_THREADS) : "memory");
-        if (e_tid == 0 && sidx >= 0 && !(P.diag & (1 | 32))) {
-          for (int j = P.b_o0[nb]; j < P.b_o0[nb] + P.b_on[nb]; ++j)
-            for (int b = 0; b < nboxes; ++b) tma_store_4d(&P.omap[j], stg + (uint32_t)(b * S3_BOX_BYTES), P.o_c0[j] + 32 * b, tx0, ty0, n);
+        if (e_tid == 0 && !(P.diag & (1 | 32))) {
+          for (int sb = 0; sb < ne; ++sb) {
+            const int e = e0 + sb;
+            if (P.e_seg[e] < 0) continue;
+            const int b0 = per_box ? sb : 0, b1 = per_box ? sb + 1 : nboxes;
+            for (int j = P.e_o0[e]; j < P.e_o0[e] + P.e_on[e]; ++j)
+              for (int b = b0; b < b1; ++b)
+                tma_store_4d(&P.omap[P.ol_map[j]], stg + (uint32_t)(b * S3_BOX_BYTES), P.ol_c0[j] + 32 * (b - b0), tx0, ty0, n);
+          }
           bulk_commit();
         }
       } else if (valid && !(P.diag & 1)) {
@@ -887,6 +913,20 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
   }
 }
 
+// Two translation units (compile time): S3_TU == 1 holds only the role-timer (DBG) instantiations of the kernel, S3_TU == 0
+// everything else.  __graft_entry__.build() compiles this file twice.
+#ifndef S3_TU
+#define S3_TU 0
+#endif
+typedef void (*S3KernelFn)(S3Params);
+#define S3_ROW(N_, D_) {conv_s3_kernel<N_, D_, 1>, conv_s3_kernel<N_, D_, 3>, conv_s3_kernel<N_, D_, 5>, conv_s3_kernel<N_, D_, 7>}
+S3KernelFn s3_dbg_kernel(int nidx, int uidx);
+#if S3_TU == 1
+S3KernelFn s3_dbg_kernel(int nidx, int uidx) {
+  static const S3KernelFn table[4][4] = {S3_ROW(32, true), S3_ROW(64, true), S3_ROW(96, true), S3_ROW(128, true)};
+  return table[nidx][uidx];
+}
+#else
 // ---- host --------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -913,68 +953,105 @@ static int s3_num_sms() {
   }
   return n;
 }
-static int s3_nb_max(int cout_pad) { return cout_pad <= 96 ? cout_pad : 64; }  // same N blocking as conv_h3 (shared weight layout)
+// N blocking: the layout of the packed weights (shared with conv_h3 for DEMFI_CONV_TC16).  DEMFI_CONV_TC16W (conv_s3 only):
+// 97..128 output channels stay ONE block -- an (M 128, N' 256) MMA pair per k-step is bound by the tensor pipe (192 clk for 128
+// channels), two (128, 128) pairs by the operand reads from shared memory (2 x 112 clk) -- and the halo tile is fetched once.
+int s3_nb_max(int kind, int cout_pad) {
+  if (kind == DEMFI_CONV_TC16W && cout_pad > 96 && cout_pad <= 128) return cout_pad;
+  return cout_pad <= 96 ? cout_pad : 64;
+}
 constexpr int S3_SMEM_MAX = 227 * 1024;
 
-// TMA epilogue plan: per N block, the segments that intersect it must all be alike (same channel range, activation,
-// operands, store mode -- i.e. one result written to one or more destinations); at most DEMFI_MAX_SEG destinations in total.
-// Pixel-shuffle segments need one N block per quadrant (nch / 4 == block width).
+// TMA epilogue plan.  Per entry (an N block, or a 32-channel box of it) the segments that intersect it must all be alike (same
+// channel range, activation, operands, store mode -- i.e. one result written to one or more destinations).  Pixel-shuffle
+// segments need one N block per quadrant (nch / 4 == block width).
 struct S3EpiPlan {
-  int b_seg[DEMFI_MAX_SEG], b_o0[DEMFI_MAX_SEG], b_on[DEMFI_MAX_SEG], b_nres[DEMFI_MAX_SEG], b_mixed[DEMFI_MAX_SEG];
-  int o_seg[DEMFI_MAX_SEG], o_blk[DEMFI_MAX_SEG];
-  int n_out;
+  int sbw, nsb, n_ent;
+  int e_seg[S3_MAX_E], e_o0[S3_MAX_E], e_on[S3_MAX_E], e_nres[S3_MAX_E], e_mixed[S3_MAX_E], e_c0[S3_MAX_E];
+  int ol_seg[S3_MAX_OL], ol_ent[S3_MAX_OL], ol_map[S3_MAX_OL];
+  int n_ol;
+  int o_seg[S3_MAX_O], o_q[S3_MAX_O];  // destination tensor maps: (segment, pixel-shuffle quadrant or -1)
+  int n_o;
   bool any_res2;
 };
-static bool s3_plan_epilogue(const demfi_conv_t& c, int nb_max, int n_blocks, S3EpiPlan& E) {
-  if (n_blocks > DEMFI_MAX_SEG) return false;
-  E.n_out = 0;
+static bool s3_plan_epilogue_w(const demfi_conv_t& c, int nb_max, int n_blocks, int sbw, S3EpiPlan& E) {
+  const int nsb = (nb_max + sbw - 1) / sbw;
+  if (n_blocks * nsb > S3_MAX_E) return false;
+  E.sbw = sbw;
+  E.nsb = nsb;
+  E.n_ent = n_blocks * nsb;
+  E.n_ol = 0;
+  E.n_o = 0;
   E.any_res2 = false;
-  for (int nb = 0; nb < n_blocks; ++nb) {
-    const int n0 = nb * nb_max, n1 = n0 + (c.cout_pad - n0 < nb_max ? c.cout_pad - n0 : nb_max);
-    E.b_seg[nb] = -1;
-    E.b_o0[nb] = E.n_out;
-    E.b_on[nb] = 0;
-    E.b_nres[nb] = 0;
-    E.b_mixed[nb] = 0;
+  for (int e = 0; e < E.n_ent; ++e) {
+    const int nb = e / nsb, sb = e % nsb;
+    const int nblk1 = nb * nb_max + (c.cout_pad - nb * nb_max < nb_max ? c.cout_pad - nb * nb_max : nb_max);
+    const int n0 = nb * nb_max + sb * sbw;
+    const int n1 = n0 + sbw < nblk1 ? n0 + sbw : nblk1;
+    E.e_seg[e] = -1;
+    E.e_o0[e] = E.n_ol;
+    E.e_on[e] = 0;
+    E.e_nres[e] = 0;
+    E.e_mixed[e] = 0;
+    E.e_c0[e] = n0;
+    if (n0 >= n1) continue;  // (a sub-block beyond the end of a ragged last block)
     for (int s = 0; s < c.nseg; ++s) {
       const demfi_seg_t& g = c.seg[s];
       if (g.ch0 >= n1 || g.ch0 + g.nch <= n0) continue;
-      if (E.b_seg[nb] < 0) {
-        E.b_seg[nb] = s;
-        E.b_nres[nb] = g.act == DEMFI_ACT_GRU ? 2 : (g.res != nullptr ? 1 : 0);
+      if (E.e_seg[e] < 0) {
+        E.e_seg[e] = s;
+        E.e_nres[e] = g.act == DEMFI_ACT_GRU ? 2 : (g.res != nullptr ? 1 : 0);
         if (g.act == DEMFI_ACT_GRU) E.any_res2 = true;
       } else {
-        const demfi_seg_t& a = c.seg[E.b_seg[nb]];
+        const demfi_seg_t& a = c.seg[E.e_seg[e]];
         if (g.ch0 != a.ch0 || g.nch != a.nch || g.act != a.act || g.store != a.store || g.res != a.res || g.res_ld != a.res_ld ||
             g.res2 != a.res2 || g.res2_ld != a.res2_ld || g.fmt != a.fmt)
           return false;
       }
+      // 32-channel entries must be whole boxes of ONE segment
+      if (nsb > 1 && (g.ch0 % 32 != 0 || g.nch % 32 != 0)) return false;
       // the first operand normally shares the staging tile with the result (updated in place): that needs the same format.
       // A residual in the other format goes to the second tile instead (not available to the two-operand GRU epilogue).
       if (g.res != nullptr && ((g.fmt & DEMFI_SEG_DST_S16) != 0) != ((g.fmt & DEMFI_SEG_RES_S16) != 0)) {
         if (g.act == DEMFI_ACT_GRU) return false;
-        E.b_mixed[nb] = 1;
+        E.e_mixed[e] = 1;
         E.any_res2 = true;
       }
       if ((g.fmt & DEMFI_SEG_DST_S16) && (g.ch0 % 32 != 0 || g.nch % 32 != 0 || (n0 - g.ch0) % 32 != 0)) return false;
+      int q = -1;
       if (g.store == DEMFI_STORE_PIXEL_SHUFFLE2) {
         const int cq = g.nch / 4;
-        if (cq < 1 || (n0 - g.ch0) / cq != (n1 - 1 - g.ch0) / cq || n0 < g.ch0) return false;  // block inside one quadrant
+        if (cq < 1 || n0 < g.ch0 || (n0 - g.ch0) / cq != (n1 - 1 - g.ch0) / cq) return false;  // entry inside one quadrant
         if (g.res != nullptr) return false;
+        q = (n0 - g.ch0) / cq;
       }
-      if (E.n_out == DEMFI_MAX_SEG) return false;
-      E.o_seg[E.n_out] = s;
-      E.o_blk[E.n_out] = nb;
-      ++E.n_out;
-      ++E.b_on[nb];
+      int mi = -1;  // destination tensor map of (segment, quadrant)
+      for (int j = 0; j < E.n_o; ++j)
+        if (E.o_seg[j] == s && E.o_q[j] == q) mi = j;
+      if (mi < 0) {
+        if (E.n_o == S3_MAX_O) return false;
+        mi = E.n_o++;
+        E.o_seg[mi] = s;
+        E.o_q[mi] = q;
+      }
+      if (E.n_ol == S3_MAX_OL) return false;
+      E.ol_seg[E.n_ol] = s;
+      E.ol_ent[E.n_ol] = e;
+      E.ol_map[E.n_ol] = mi;
+      ++E.n_ol;
+      ++E.e_on[e];
     }
   }
   return true;
 }
+static bool s3_plan_epilogue(const demfi_conv_t& c, int nb_max, int n_blocks, S3EpiPlan& E) {
+  if (s3_plan_epilogue_w(c, nb_max, n_blocks, nb_max, E)) return true;
+  return nb_max > 32 && s3_plan_epilogue_w(c, nb_max, n_blocks, 32, E);
+}
 
 bool s3_s16_ok(const demfi_conv_t& c) {
-  const int nbm = s3_nb_max(c.cout_pad);
-  S3EpiPlan E;
+  const int nbm = s3_nb_max(c.kind, c.cout_pad);
+  static thread_local S3EpiPlan E;
   bool any_seg = false;
   for (int s = 0; s < c.nseg; ++s) any_seg = any_seg || c.seg[s].fmt != 0;
   return !any_seg || s3_plan_epilogue(c, nbm, (c.cout_pad + nbm - 1) / nbm, E);
@@ -988,10 +1065,10 @@ bool s3_supports(const demfi_conv_t& c) {
   const int hw = S3_TW + c.KW - 1, hh = S3_TH + c.KH - 1;
   if (hw > 256 || hh > 256) return false;
   const int a_bytes = (hw * hh * 128 + 1023) / 1024 * 1024;
-  const int nbm = s3_nb_max(c.cout_pad);
+  const int nbm = s3_nb_max(c.kind, c.cout_pad);
   const int b_bytes = 2 * nbm * 64;
   const int stg = ((nbm + 31) / 32) * S3_BOX_BYTES;
-  return 2 * a_bytes + 4 * b_bytes + stg + 2048 <= S3_SMEM_MAX;
+  return 2 * a_bytes + (nbm > 96 ? 2 : 4) * b_bytes + stg + 2048 <= S3_SMEM_MAX;
 }
 
 // Halo-tile buffers wanted.  A 1x1 kernel consumes a chunk in ~400 cycles, so the loads in flight -- not the math -- set its
@@ -1029,7 +1106,7 @@ static int s3_plan(const demfi_conv_t& c, S3Params& P, S3EpiPlan& E, int* smem_o
   P.tiles_x = (c.W + S3_TW - 1) / S3_TW;
   P.tiles_y = (c.H + S3_TH - 1) / S3_TH;
   const long long nt = (long long)P.tiles_x * P.tiles_y * c.N;
-  P.nb_max = s3_nb_max(c.cout_pad);
+  P.nb_max = s3_nb_max(c.kind, c.cout_pad);
   P.n_blocks = (c.cout_pad + P.nb_max - 1) / P.nb_max;
   DEMFI_REQUIRE(nt > 0 && nt * P.n_blocks < (1ll << 31), "conv_s3: bad tile count");
   P.ntiles = (int)nt * P.n_blocks;
@@ -1050,22 +1127,36 @@ static int s3_plan(const demfi_conv_t& c, S3Params& P, S3EpiPlan& E, int* smem_o
   for (int sg = 0; sg < c.nseg; ++sg)
     DEMFI_REQUIRE(c.seg[sg].fmt == 0 || P.tma_epi, "conv_s3: segment %d asks for the S16 format, which needs the TMA epilogue", sg);
   const int box_bytes_all = ((P.nb_max + 31) / 32) * S3_BOX_BYTES;
-  const int stg_bytes = P.tma_epi ? box_bytes_all * (E.any_res2 ? 2 : 1) : 0;
+  // second staging tile (operands that cannot share the result tile): only as many boxes as its last user needs
+  int stg2_boxes = 0;
+  if (P.tma_epi && E.any_res2)
+    for (int e = 0; e < E.n_ent; ++e)
+      if (E.e_seg[e] >= 0 && (E.e_mixed[e] || E.e_nres[e] == 2)) {
+        const int last = E.nsb > 1 ? e % E.nsb + 1 : (P.nb_max + 31) / 32;
+        if (last > stg2_boxes) stg2_boxes = last;
+      }
+  const int stg_bytes = P.tma_epi ? box_bytes_all + stg2_boxes * S3_BOX_BYTES : 0;
   P.stg2_off = box_bytes_all;  // second operand tile, relative to the staging tile
+  P.sbw = P.nb_max;
+  P.nsb = 1;
   if (P.tma_epi) {
-    for (int nb = 0; nb < P.n_blocks; ++nb) {
-      P.b_seg[nb] = E.b_seg[nb];
-      P.b_o0[nb] = E.b_o0[nb];
-      P.b_on[nb] = E.b_on[nb];
-      P.b_nres[nb] = E.b_nres[nb];
-      P.b_roff[nb] = E.b_mixed[nb] ? box_bytes_all : 0;
-      if (E.b_seg[nb] >= 0) P.r_c0[nb] = nb * P.nb_max - c.seg[E.b_seg[nb]].ch0;
+    P.sbw = E.sbw;
+    P.nsb = E.nsb;
+    for (int e = 0; e < E.n_ent; ++e) {
+      P.e_seg[e] = (signed char)E.e_seg[e];
+      P.e_o0[e] = (signed char)E.e_o0[e];
+      P.e_on[e] = (signed char)E.e_on[e];
+      P.e_nres[e] = (signed char)E.e_nres[e];
+      P.e_roff[e] = E.e_mixed[e] ? box_bytes_all : 0;
+      P.e_info[e] = E.e_seg[e] < 0 ? 0 : (c.seg[E.e_seg[e]].fmt & 7) | (c.seg[E.e_seg[e]].act << 3) | (E.e_nres[e] << 6) | (E.e_mixed[e] ? 256 : 0);
+      if (E.e_seg[e] >= 0) P.e_rc0[e] = E.e_c0[e] - c.seg[E.e_seg[e]].ch0;
     }
-    for (int j = 0; j < E.n_out; ++j) {
-      const demfi_seg_t& g = c.seg[E.o_seg[j]];
-      const int n0 = E.o_blk[j] * P.nb_max;
-      P.o_c0[j] = n0 - g.ch0;
-      if (g.store == DEMFI_STORE_PIXEL_SHUFFLE2) P.o_c0[j] -= ((n0 - g.ch0) / (g.nch / 4)) * (g.nch / 4);  // channel inside the quadrant
+    for (int j = 0; j < E.n_ol; ++j) {
+      const demfi_seg_t& g = c.seg[E.ol_seg[j]];
+      const int n0 = E.e_c0[E.ol_ent[j]];
+      P.ol_map[j] = (signed char)E.ol_map[j];
+      P.ol_c0[j] = n0 - g.ch0;
+      if (g.store == DEMFI_STORE_PIXEL_SHUFFLE2) P.ol_c0[j] -= ((n0 - g.ch0) / (g.nch / 4)) * (g.nch / 4);  // channel inside the quadrant
     }
   }
 
@@ -1118,6 +1209,9 @@ static int s3_plan(const demfi_conv_t& c, S3Params& P, S3EpiPlan& E, int* smem_o
   *smem_out = smem;
 
   P.all_full_chunks = 1;
+  P.all_s16 = 1;
+  for (int s_ = 0; s_ < c.nsrc; ++s_)
+    if (c.src[s_].fmt != DEMFI_FMT_S16) P.all_s16 = 0;
   for (int s_ = 0; s_ < c.nsrc; ++s_)
     if (c.src[s_].C % S3_KC != 0) P.all_full_chunks = 0;
   {  // accumulation segments: whole issue units, balanced over the tile
@@ -1155,6 +1249,8 @@ int s3_describe(const demfi_conv_t& c, int32_t* info) {
   info[7] = smem;
   info[8] = P.flush;
   info[9] = P.stages_per_tile;
+  info[10] = P.nsb;  // epilogue entries per N block (1: the block is one result; else 32-channel boxes planned one by one)
+  info[11] = P.nb_max;
   return 0;
 }
 
@@ -1169,21 +1265,23 @@ int launch_conv_s3(const demfi_conv_t& c, cudaStream_t st) {
   for (int s = 0; s < c.nsrc; ++s)
     if (s3_encode(enc, &P.tmap[s], c.src[s].ptr, c.src[s].C, c.src[s].ld, c.Wi, c.Hi, c.N, P.hw, P.hh, "a source")) return 1;
   if (P.tma_epi) {
-    for (int nb = 0; nb < P.n_blocks; ++nb) {
-      if (E.b_seg[nb] < 0) continue;
-      const demfi_seg_t& g = c.seg[E.b_seg[nb]];
-      if (E.b_nres[nb] >= 1)
-        if (s3_encode(enc, &P.rmap[nb], g.res, g.nch, g.res_ld, c.W, c.H, c.N, S3_TW, S3_TH, "an epilogue operand")) return 1;
-      if (E.b_nres[nb] >= 2)
-        if (s3_encode(enc, &P.r2map[nb], g.res2, g.nch, g.res2_ld, c.W, c.H, c.N, S3_TW, S3_TH, "the second epilogue operand")) return 1;
+    bool rdone[DEMFI_MAX_SEG] = {false, false, false, false};
+    for (int e = 0; e < E.n_ent; ++e) {
+      const int sg = E.e_seg[e];
+      if (sg < 0 || rdone[sg]) continue;
+      rdone[sg] = true;
+      const demfi_seg_t& g = c.seg[sg];
+      if (E.e_nres[e] >= 1)
+        if (s3_encode(enc, &P.rmap[sg], g.res, g.nch, g.res_ld, c.W, c.H, c.N, S3_TW, S3_TH, "an epilogue operand")) return 1;
+      if (E.e_nres[e] >= 2)
+        if (s3_encode(enc, &P.r2map[sg], g.res2, g.nch, g.res2_ld, c.W, c.H, c.N, S3_TW, S3_TH, "the second epilogue operand")) return 1;
     }
-    for (int j = 0; j < E.n_out; ++j) {
+    for (int j = 0; j < E.n_o; ++j) {
       const demfi_seg_t& g = c.seg[E.o_seg[j]];
-      const int n0 = E.o_blk[j] * P.nb_max;
       if (g.store == DEMFI_STORE_PIXEL_SHUFFLE2) {
         // nn.PixelShuffle(2): accumulator channel q*cq + ch of pixel (y, x) -> pixel (2y + q/2, 2x + q%2), channel ch: the
         // quadrant is a tensor of its own with doubled pixel strides
-        const int cq = g.nch / 4, q = (n0 - g.ch0) / cq;
+        const int cq = g.nch / 4, q = E.o_q[j];
         const float* base = g.dst + ((size_t)(q >> 1) * (size_t)(2 * c.W) + (size_t)(q & 1)) * (size_t)g.dst_ld;
         cuuint64_t dims[4] = {(cuuint64_t)cq, (cuuint64_t)c.W, (cuuint64_t)c.H, (cuuint64_t)c.N};
         cuuint64_t strides[3] = {(cuuint64_t)g.dst_ld * 8, (cuuint64_t)g.dst_ld * 16 * c.W, (cuuint64_t)g.dst_ld * 16 * c.W * c.H};
@@ -1205,15 +1303,9 @@ int launch_conv_s3(const demfi_conv_t& c, cudaStream_t st) {
   }
   // one kernel per (N block width, issue unit): a single instantiation of the issue loop per kernel keeps its state in
   // uniform registers (a switch over four inlined copies did not)
-  typedef void (*KernelFn)(S3Params);
-  static const KernelFn table[2][3][4] = {
-      {{conv_s3_kernel<32, false, 1>, conv_s3_kernel<32, false, 3>, conv_s3_kernel<32, false, 5>, conv_s3_kernel<32, false, 7>},
-       {conv_s3_kernel<64, false, 1>, conv_s3_kernel<64, false, 3>, conv_s3_kernel<64, false, 5>, conv_s3_kernel<64, false, 7>},
-       {conv_s3_kernel<96, false, 1>, conv_s3_kernel<96, false, 3>, conv_s3_kernel<96, false, 5>, conv_s3_kernel<96, false, 7>}},
-      {{conv_s3_kernel<32, true, 1>, conv_s3_kernel<32, true, 3>, conv_s3_kernel<32, true, 5>, conv_s3_kernel<32, true, 7>},
-       {conv_s3_kernel<64, true, 1>, conv_s3_kernel<64, true, 3>, conv_s3_kernel<64, true, 5>, conv_s3_kernel<64, true, 7>},
-       {conv_s3_kernel<96, true, 1>, conv_s3_kernel<96, true, 3>, conv_s3_kernel<96, true, 5>, conv_s3_kernel<96, true, 7>}}};
-  const KernelFn fn = table[P.dbg != nullptr ? 1 : 0][P.nb_max <= 32 ? 0 : P.nb_max <= 64 ? 1 : 2][P.unit >> 1];
+  static const S3KernelFn table[4][4] = {S3_ROW(32, false), S3_ROW(64, false), S3_ROW(96, false), S3_ROW(128, false)};
+  const int nidx = P.nb_max <= 32 ? 0 : P.nb_max <= 64 ? 1 : P.nb_max <= 96 ? 2 : 3;
+  const S3KernelFn fn = P.dbg != nullptr ? s3_dbg_kernel(nidx, P.unit >> 1) : table[nidx][P.unit >> 1];
   {
     // cudaFuncSetAttribute applies per device: remember which devices have seen which kernel
     static std::mutex mu;
@@ -1246,5 +1338,6 @@ int launch_conv_s3(const demfi_conv_t& c, cudaStream_t st) {
   DEMFI_LAUNCH_CHECK("conv_s3");
   return 0;
 }
+#endif  // S3_TU
 
 }  // namespace demfi

@@ -87,6 +87,8 @@ class Engine:
         assert self.conv_kind in ("auto", "ffma", "tc", "tc16", "tc16f32")
         # S16 activation storage between convolutions (conv_s3 only); "tc16f32" keeps every buffer fp32 (comparison)
         self.use_s16 = self.conv_kind in ("auto", "tc16") and os.environ.get("DEMFI_S16", "1") != "0"
+        # dense blocks in "push" form (_rdb_push_ops): needs conv_s3's per-box epilogue plans, i.e. the S16 / TMA-store path
+        self.rdb_push = self.use_s16 and os.environ.get("DEMFI_RDB_PUSH", "1") != "0"
         self._keep: list = []  # weights, ctypes structs
         self.bufs: Dict[str, torch.Tensor] = {}
         self.views: Dict[str, View] = {}
@@ -115,6 +117,7 @@ class Engine:
         v["F1"] = self._buf("F1", B, h, w, 96, s16=True)
         v["T"] = self._buf("T", B, h, w, 96 + 12 * 224, s16=True)
         v["G"] = self._buf("G", B, h, w, 1152, s16=True)
+        v["PS"] = self._buf("PS", B, h, w, 96)  # dense-block partial sums P1 | P2 | P3 (fp32), see _rdb_push_ops
         v["GF0"] = self._buf("GF0", B, h, w, 96, s16=True)
         v["TR"] = self._buf("TR", B, h, w, 96, s16=True)
         v["U"] = self._buf("U", B, H, W, 64, s16=True)
@@ -182,14 +185,20 @@ class Engine:
             return A.CONV_FFMA
         if self.conv_kind == "tc":
             return A.CONV_TC if tc_ok else A.CONV_FFMA
-        return A.CONV_TC16 if tc16_ok else A.CONV_FFMA
+        if not tc16_ok:
+            return A.CONV_FFMA
+        # 97..128 output channels as ONE N block (conv_s3 only: stride 1)
+        wide = stride == 1 and 96 < cout_pad <= 128 and os.environ.get("DEMFI_WIDE_N", "1") != "0"
+        return A.CONV_TC16W if wide else A.CONV_TC16
 
     def conv(self, names, srcs, out_hw, N, segs, k=(3, 3), stride=1, pad=None, in_map=None, out_map=None,
-             cout=None, in_hw=None, label=None):
-        """Append one convolution.  srcs: [(View, up)], segs: [dict(ch0, nch, dst=View, act, res=View, res2=View, store)]."""
+             cout=None, in_hw=None, label=None, wb=None):
+        """Append one convolution.  srcs: [(View, up)], segs: [dict(ch0, nch, dst=View, act, res=View, res2=View, store)].
+        wb = (weight [Co,Ci,KH,KW], bias [Co]) numpy arrays: a weight assembled by the caller from several parameters
+        (`names` then only keys the cache and labels the launch)."""
         if isinstance(names, str):
             names = [names]
-        w, b = self._weight(names)
+        w, b = self._weight(names) if wb is None else wb
         Co, Ci, KH, KW = w.shape
         assert (KH, KW) == tuple(k), (names, w.shape, k)
         if pad is None:
@@ -233,7 +242,7 @@ class Engine:
             assert vw.N == N and (vw.H << up, vw.W << up) == (Hi, Wi), (names, i, vw.N, vw.H, vw.W, up, Hi, Wi)
             d.src[i].ptr, d.src[i].C, d.src[i].ld, d.src[i].up = vw.ptr, vw.C, vw.ld, up
             d.src[i].fmt = vw.fmt
-            assert vw.fmt == A.FMT_F32 or kind == A.CONV_TC16, (names, "S16 source on a kernel that cannot read it")
+            assert vw.fmt == A.FMT_F32 or kind in (A.CONV_TC16, A.CONV_TC16W), (names, "S16 source on a kernel that cannot read it")
         for i, sg in enumerate(segs):
             dst: View = sg["dst"]
             s = d.seg[i]
@@ -247,7 +256,7 @@ class Engine:
             if sg.get("res2") is not None:
                 s.res2, s.res2_ld = sg["res2"].ptr, sg["res2"].ld
                 s.fmt |= A.SEG_RES2_S16 if sg["res2"].fmt == A.FMT_S16 else 0
-            assert s.fmt == 0 or kind == A.CONV_TC16, (names, "S16 destination / operand on a kernel that cannot handle it")
+            assert s.fmt == 0 or kind in (A.CONV_TC16, A.CONV_TC16W), (names, "S16 destination / operand on a kernel that cannot handle it")
         d.wpack, d.bias = wdev.data_ptr(), bdev.data_ptr()
         self._keep.append(d)
         macs = N * Ho * Wo * Co * Ci * KH * KW
@@ -255,6 +264,46 @@ class Engine:
                  "res": [sg[k_] for sg in segs for k_ in ("res", "res2") if sg.get(k_) is not None]}
         op = ("conv", d, label or names[0], kind, macs, views)
         return op
+
+    def _rdb_push_ops(self, i: int, T: View, PS: View, o: int, hw) -> list:
+        """One residual dense block (RDB_Conv x 4, DeMFInet.py:256-287) in "push" form.  The reference's layer c convolves
+        [x, g0 .. g_{c-1}] (96 + 32c channels) into 32 growth channels: four N = 32 tensor-core launches that re-read the whole
+        activation operand per 32 outputs (88 clk of operand reads for 48 clk of math per k-step).  Here each SOURCE is convolved
+        once, as soon as it exists, with the weight slices of every later layer that reads it:
+            x  -> [g0 | P1 P2 P3]      (N = 128;  N = 96 + 32 without the wide-N kernel)
+            g0 -> [g1 | P2 P3]         g1 -> [g2 | P3]         g2 -> [g3]
+        where P_c (fp32, buffer PS) carries layer c's pre-activation partial sum and the first 32-channel box of each launch
+        finishes a layer: g_c = relu(acc + P_c + bias_c) -> S16 trunk slice.  Same multiply-adds, same weights; only the fp32
+        summation order differs.  Per-box epilogues (activation / operand / format per 32 channels) are planned by conv_s3."""
+        B = self.B
+        relu, none = A.ACT_RELU, A.ACT_NONE
+        p = f"FF_RDB_Module.RDBs.{i}."
+        Ws = [self._sd[f"{p}convs.{c}.conv.0.weight"].numpy() for c in range(4)]
+        bs = [self._sd[f"{p}convs.{c}.conv.0.bias"].numpy() for c in range(4)]
+        z32 = np.zeros(32, dtype=np.float32)
+        seg = lambda ch0, nch, dst, act=none, res=None: dict(ch0=ch0, nch=nch, dst=dst, act=act, res=res)
+        g = lambda c: T.ch(o + 96 + 32 * c, 32)
+
+        def wcat(layers, k0, k1):
+            return np.ascontiguousarray(np.concatenate([Ws[c][:, k0:k1] for c in layers], 0))
+
+        ops = []
+        wide = self._pick_kind(3, 3, 1, (1, 1), [(T.ch(o, 96), 0)], 128) == A.CONV_TC16W
+        if wide:
+            ops.append(self.conv([p + "push0"], [T.ch(o, 96)], hw, B, [seg(0, 32, g(0), relu), seg(32, 96, PS.ch(0, 96))],
+                                 wb=(wcat((0, 1, 2, 3), 0, 96), np.concatenate([bs[0], z32, z32, z32]))))
+        else:
+            ops.append(self.conv([p + "push0a"], [T.ch(o, 96)], hw, B, [seg(0, 32, g(0), relu), seg(32, 64, PS.ch(0, 64))],
+                                 wb=(wcat((0, 1, 2), 0, 96), np.concatenate([bs[0], z32, z32]))))
+            ops.append(self.conv([p + "push0b"], [T.ch(o, 96)], hw, B, [seg(0, 32, PS.ch(64, 32))], wb=(wcat((3,), 0, 96), z32)))
+        ops.append(self.conv([p + "push1"], [g(0)], hw, B,
+                             [seg(0, 32, g(1), relu, PS.ch(0, 32)), seg(32, 64, PS.ch(32, 64), none, PS.ch(32, 64))],
+                             wb=(wcat((1, 2, 3), 96, 128), np.concatenate([bs[1], z32, z32]))))
+        ops.append(self.conv([p + "push2"], [g(1)], hw, B,
+                             [seg(0, 32, g(2), relu, PS.ch(32, 32)), seg(32, 32, PS.ch(64, 32), none, PS.ch(64, 32))],
+                             wb=(wcat((2, 3), 128, 160), np.concatenate([bs[2], z32]))))
+        ops.append(self.conv([p + "push3"], [g(2)], hw, B, [seg(0, 32, g(3), relu, PS.ch(64, 32))], wb=(wcat((3,), 160, 192), bs[3])))
+        return ops
 
     # ------------------------------------------------------------------ plan
     def _build(self):
@@ -271,11 +320,16 @@ class Engine:
         T = v["T"]
         ops.append(self.conv(p + "SFENet1", [v["S2D"]], (h, w), B, [full(v["F1"], 96)], k=(5, 5)))
         ops.append(self.conv(p + "SFENet2", [v["F1"]], (h, w), B, [full(T.ch(0, 96), 96)]))
+        push = self.rdb_push
+        PS = v["PS"]
         for i in range(12):
             o = 224 * i
-            for c in range(4):
-                ops.append(self.conv(f"{p}RDBs.{i}.convs.{c}.conv.0", [T.ch(o, 96 + 32 * c)], (h, w), B,
-                                     [full(T.ch(o + 96 + 32 * c, 32), 32, relu)]))
+            if not push:
+                for c in range(4):
+                    ops.append(self.conv(f"{p}RDBs.{i}.convs.{c}.conv.0", [T.ch(o, 96 + 32 * c)], (h, w), B,
+                                         [full(T.ch(o + 96 + 32 * c, 32), 32, relu)]))
+            else:
+                ops.extend(self._rdb_push_ops(i, T, PS, o, (h, w)))
             xi = T.ch(o, 96)
             ops.append(self.conv(f"{p}RDBs.{i}.LFF", [T.ch(o, 224)], (h, w), B,
                                  [full(T.ch(o + 224, 96), 96, none, xi), full(v["G"].ch(96 * i, 96), 96, none, xi)], k=(1, 1)))

@@ -57,7 +57,9 @@ enum { DEMFI_SEG_DST_S16 = 1, DEMFI_SEG_RES_S16 = 2, DEMFI_SEG_RES2_S16 = 4 };
 enum {
   DEMFI_CONV_FFMA = 0, /* CUDA-core fp32 implicit GEMM (exact fp32)                                   */
   DEMFI_CONV_TC = 1,   /* tcgen05 kind::tf32, 3xTF32 split (first-generation tensor-core kernel)       */
-  DEMFI_CONV_TC16 = 2  /* tcgen05 kind::f16, 3xFP16 split + halo-tile activation staging; stride 1|2  */
+  DEMFI_CONV_TC16 = 2, /* tcgen05 kind::f16, 3xFP16 split + halo-tile activation staging; stride 1|2  */
+  DEMFI_CONV_TC16W = 3 /* the same arithmetic on the conv_s3 kernel only (stride 1), with 97..128 output channels kept in
+                          ONE N block (an N' = 256 MMA pair per k-step; weights packed for that blocking)              */
 };
 
 /* one input of a (virtually concatenated) convolution */
@@ -90,7 +92,7 @@ typedef struct {
   int32_t KH, KW, stride, pad_h, pad_w;
   int32_t nsrc, nseg;
   int32_t cout_pad;  /* accumulator channels (padded Cout, multiple of 16)             */
-  int32_t kind;      /* DEMFI_CONV_FFMA | DEMFI_CONV_TC | DEMFI_CONV_TC16                */
+  int32_t kind;      /* DEMFI_CONV_FFMA | DEMFI_CONV_TC | DEMFI_CONV_TC16 | DEMFI_CONV_TC16W */
   demfi_src_t src[DEMFI_MAX_SRC];
   demfi_seg_t seg[DEMFI_MAX_SEG];
   const float* wpack; /* device, produced by demfi_pack_weights for the same `kind`    */
@@ -127,7 +129,9 @@ int demfi_conv2d(const demfi_conv_t* conv, void* stream);
 /* Host-only (no GPU needed): what demfi_conv2d would do with this descriptor.  info[0] = kernel (0 conv_ffma, 1 conv_tc,
  * 2 conv_h3, 3 conv_s3); for conv_s3 also info[1] = TMA-store epilogue (else the generic per-thread one), [2] = weights
  * resident in shared memory, [3] = halo-tile buffers, [4] = weight-ring slots, [5] = (chunk, tap) stages per slot,
- * [6] = N blocks, [7] = dynamic shared memory in bytes, [8] = stages per accumulation segment, [9] = stages per tile.
+ * [6] = N blocks, [7] = dynamic shared memory in bytes, [8] = stages per accumulation segment, [9] = stages per tile,
+ * [10] = epilogue entries per N block (1: one result per block; > 1: every 32-channel box has its own activation / operands /
+ * format / destinations), [11] = N block width.
  * Lets a plan be checked for silent fall-backs to slower paths without launching anything. */
 int demfi_conv_describe(const demfi_conv_t* conv, int32_t info[16]);
 

@@ -92,7 +92,7 @@ def run_conv(w, b, srcs, out_hw, kind, segs_spec, stride=1, pad=None, in_map=Non
         s.ch0, s.nch, s.act, s.store = sg["ch0"], sg["nch"], sg.get("act", 0), sg.get("store", 0)
         s.fmt = sg.get("fmt", 0)
         if sg.get("res") is not None:
-            s.res, s.res_ld = sg["res"].data_ptr(), sg["res"].shape[3]
+            s.res, s.res_ld = sg["res"].data_ptr() + 4 * sg.get("res_c0", 0), sg["res"].shape[3]
         if sg.get("res2") is not None:
             s.res2, s.res2_ld = sg["res2"].data_ptr(), sg["res2"].shape[3]
     d.wpack, d.bias = wdev.data_ptr(), bdev.data_ptr()

@@ -177,7 +177,16 @@ def test_conv_describe_reports_kernel_and_epilogue_plan():
     lff = _describe(96, [(0, 96, A.ACT_NONE, True, A.SEG_DST_S16 | A.SEG_RES_S16)] * 2, k=(1, 1), srcC=(224,))
     assert lff[1] == 1 and lff[6] == 1                                  # one result, two destinations
     mixed = _describe(64, [(0, 32, A.ACT_RELU, False, 0), (32, 32, A.ACT_TANH, False, 0)])
-    assert mixed[0] == 3 and mixed[1] == 0                              # two different segments inside one N block: generic epilogue
+    assert mixed[0] == 3 and mixed[1] == 1 and mixed[10] == 2           # two different segments inside one N block: planned per 32-channel box
+    ragged = _describe(64, [(0, 16, A.ACT_RELU, False, 0), (16, 48, A.ACT_TANH, False, 0)])
+    assert ragged[0] == 3 and ragged[1] == 0                            # ... unless they do not fall on box boundaries: generic epilogue
+    push = _describe(96, [(0, 32, A.ACT_RELU, True, A.SEG_DST_S16), (32, 64, A.ACT_NONE, True, 0)], srcC=(32,))
+    assert push[1] == 1 and push[10] == 3 and push[2] == 1              # dense-block push conv: S16 head + fp32 partial sums, weights resident
+    zr = _describe(128, [(0, 64, A.ACT_SIGMOID, False, A.SEG_DST_S16), (64, 64, A.ACT_SIGMOID_MUL, True, A.SEG_DST_S16 | A.SEG_RES_S16)],
+                   k=(1, 5), srcC=(64, 64), kind=A.CONV_TC16W)
+    assert zr[0] == 3 and zr[1] == 1 and zr[6] == 1 and zr[11] == 128 and zr[10] == 4   # GRU z | r: ONE N block of 128, four boxes
+    zr64 = _describe(128, [(0, 64, A.ACT_SIGMOID, False, 0), (64, 64, A.ACT_SIGMOID_MUL, True, 0)], k=(1, 5), srcC=(64, 64))
+    assert zr64[6] == 2 and zr64[11] == 64                              # DEMFI_CONV_TC16 keeps blocks of 64 (layout shared with conv_h3)
     big = _describe(64, [(0, 64, A.ACT_TANH, False, 0)], k=(7, 7), srcC=(64, 64, 64))
     assert big[2] == 0 and big[4] >= 2 and big[5] >= 2                  # 2.4 MB of weights: ring of multi-stage groups
     enc = _describe(64, [(0, 64, A.ACT_RELU, False, 0)], k=(4, 4), srcC=(204,), stride=2)

@@ -33,9 +33,9 @@ def ref_conv(x, w, b, stride=1, pad=None):
     return F.conv2d(x.double(), w.double(), b.double(), stride=stride, padding=pad)
 
 
-def check(got, want, what):
+def check(got, want, what, tol=None):
     err = float((got.double() - want).abs().max())
-    lim = TOL * max(1.0, float(want.abs().max()))
+    lim = (TOL if tol is None else tol) * max(1.0, float(want.abs().max()))
     print(f"{what}: max-abs err {err:.3e} (limit {lim:.3e}, max|ref| {float(want.abs().max()):.3f})")
     assert err <= lim, f"{what}: {err} > {lim}"
 
@@ -351,8 +351,10 @@ def test_s16_residual_two_sources_n32():
     check(from_nhwc(s16_decode(o2)[..., 96:192], 96), want, "s16 lff dst 2")
 
 
-def test_s16_gru_epilogues():
-    """zr conv: Z = sigmoid (S16 out), RH = sigmoid * h (S16 operand and out); q conv: (1 - z) h + z tanh(q) with S16 h and z"""
+@pytest.mark.parametrize("zr_kind", [pytest.param(A.CONV_TC16, id="zr-2x64"), pytest.param(A.CONV_TC16W, id="zr-1x128")])
+def test_s16_gru_epilogues(zr_kind):
+    """zr conv: Z = sigmoid (S16 out), RH = sigmoid * h (S16 operand and out); q conv: (1 - z) h + z tanh(q) with S16 h and z.
+    DEMFI_CONV_TC16W: z | r as ONE N block of 128 channels (N' = 256 MMAs) whose four 32-channel boxes are planned one by one."""
     n, hh, w_ = 1, 24, 40
     hx = rnd(n, 128, hh, w_, seed=21, scale=0.7)
     hb, _ = nhwc(hx[:, :64]); xb, _ = nhwc(hx[:, 64:])
@@ -360,7 +362,7 @@ def test_s16_gru_epilogues():
     h_val = s16_decode(hs).permute(0, 3, 1, 2).cpu().double()
     wz, bz = wb(128, 128, 1, 5, seed=7)
     Z = torch.zeros(n, hh, w_, 64, device=DEV); RH = torch.zeros(n, hh, w_, 64, device=DEV)
-    run_conv(wz, bz, [(hs, 64, 0, A.FMT_S16), (xs, 64, 0, A.FMT_S16)], (hh, w_), A.CONV_TC16,
+    run_conv(wz, bz, [(hs, 64, 0, A.FMT_S16), (xs, 64, 0, A.FMT_S16)], (hh, w_), zr_kind,
              [dict(ch0=0, nch=64, dst=Z, act=A.ACT_SIGMOID, fmt=A.SEG_DST_S16),
               dict(ch0=64, nch=64, dst=RH, act=A.ACT_SIGMOID_MUL, res=hs, fmt=A.SEG_DST_S16 | A.SEG_RES_S16)])
     full = ref_conv(hx, wz, bz)
@@ -375,6 +377,46 @@ def test_s16_gru_epilogues():
     z_val = s16_decode(Z).permute(0, 3, 1, 2).cpu().double()
     q = torch.tanh(ref_conv(torch.cat([rh_val, hx[:, 64:]], 1), wq, bq))
     check(from_nhwc(s16_decode(H1), 64), (1 - z_val) * h_val + z_val * q, "s16 gru update")
+
+
+@pytest.mark.parametrize("hw", [(32, 40), (37, 45)])
+def test_dense_block_push_form_equals_pull_form(hw):
+    """A residual dense block (RDB_Conv x 4, DeMFInet.py:256-287) the way the engine runs it (Engine._rdb_push_ops): every source
+    convolved once with the weight slices of all later layers, fp32 partial sums P1..P3 accumulated in place through the epilogue
+    operand path, the first 32-channel box of each launch finishing a layer (ReLU, S16 into the trunk) -- against the reference
+    formulation (layer c convolves [x, g0..g_{c-1}]) in float64.  Exercises per-box epilogue plans: S16 + ReLU + fp32 operand in
+    one box, fp32 read-modify-write in the others, of one N = 128 / 96 / 64 MMA tile."""
+    n, (h, w_) = 1, hw
+    x = rnd(n, 96, h, w_, seed=41)
+    Ws, bs = zip(*[wb(32, 96 + 32 * c, 3, 3, seed=50 + c) for c in range(4)])
+    trunk, _ = nhwc(torch.cat([x, torch.zeros(n, 128, h, w_)], 1), ld=224)
+    trunk = s16_encode(trunk)
+    xq = s16_decode(trunk)[..., :96].permute(0, 3, 1, 2).cpu()
+    PS = torch.zeros(n, h, w_, 96, device=DEV)
+    z32 = torch.zeros(32)
+    g = lambda c: dict(dst=trunk, dst_c0=96 + 32 * c)
+    cat = lambda layers, k0, k1: torch.cat([Ws[c][:, k0:k1] for c in layers], 0).contiguous()
+    S = A.SEG_DST_S16
+    run_conv(cat((0, 1, 2, 3), 0, 96), torch.cat([bs[0], z32, z32, z32]), [(trunk, 96, 0, A.FMT_S16)], (h, w_), A.CONV_TC16W,
+             [dict(ch0=0, nch=32, act=A.ACT_RELU, fmt=S, **g(0)), dict(ch0=32, nch=96, dst=PS)])
+    def src_of(c):
+        v = trunk.view(-1)[96 + 32 * c:]
+        class V:  # minimal buffer stand-in for run_conv: data_ptr() + the row stride of the trunk
+            shape = trunk.shape
+            def data_ptr(self_):
+                return v.data_ptr()
+        return [(V(), 32, 0, A.FMT_S16)]
+    run_conv(cat((1, 2, 3), 96, 128), torch.cat([bs[1], z32, z32]), src_of(0), (h, w_), A.CONV_TC16,
+             [dict(ch0=0, nch=32, act=A.ACT_RELU, fmt=S, res=PS, **g(1)), dict(ch0=32, nch=64, dst=PS, dst_c0=32, res=PS, res_c0=32)])
+    run_conv(cat((2, 3), 128, 160), torch.cat([bs[2], z32]), src_of(1), (h, w_), A.CONV_TC16,
+             [dict(ch0=0, nch=32, act=A.ACT_RELU, fmt=S, res=PS, res_c0=32, **g(2)), dict(ch0=32, nch=32, dst=PS, dst_c0=64, res=PS, res_c0=64)])
+    run_conv(cat((3,), 160, 192), bs[3], src_of(2), (h, w_), A.CONV_TC16,
+             [dict(ch0=0, nch=32, act=A.ACT_RELU, fmt=S, res=PS, res_c0=64, **g(3))])
+    got = s16_decode(trunk).permute(0, 3, 1, 2).cpu()
+    feats = [xq.double()]
+    for c in range(4):
+        feats.append(F.relu(ref_conv(torch.cat(feats, 1), Ws[c], bs[c])))
+        check(got[:, 96 + 32 * c:128 + 32 * c], feats[-1], f"dense block growth slice {c} (push form)", tol=2e-5 * (c + 1))
 
 
 @pytest.mark.parametrize("res_s16,dst_s16", [(True, False), (False, True)])

@@ -1,19 +1,22 @@
-"""Opt-in (DEMFI_FULL_PARITY=1): the B200 forward against the ORACLE ITSELF at BASELINE.json's full size (1280x720 padded to
-1280x736, N_tst=3) -- one to two minutes of CPU work on the GPU box, so it is not part of the default `-m gpu` run, which shows
-full-size parity through properties (tests/test_forward_gpu.py).  Writes the figures SURVEY.md section 8(d) asks to be
-reported beside throughput (max-abs, p99.99, fraction > 5e-4, PSNR / SSIM(ours, reference) on rounded 0..255 images) to
-gpurun_out/parity_full_size.json; the committed copy is profiles/r1_parity_full_size.json.
+"""Parity at the size BASELINE.json's metric is quoted on (1280x720 reflect-padded to 1280x736, N_tst = 3).
 
-Yardstick: the unmodified reference against itself (1 vs 8 CPU threads, half this size) differs by up to 4.5e-2 on 1.1e-3 of
-the St samples (profiles/r1_reference_self_noise.json) -- isolated flips of the discontinuous operators (floor() in the
-splat, the 0.999 validity threshold of bwarp) that the decoders' receptive fields spread over a neighbourhood.  The report
-also gives, per tensor, max-abs over the pixels farther than r = 32 / 64 / 96 px from any site where the splat's floor() went
-the other way (|flow0 - oracle| > 1e-3; 156 pixels of 942 080): that is where the 5e-4 bound applies, and it holds on every
-returned tensor already at r = 32 (frames <= 9e-5, St_final <= 3e-4, flows 1e-5, occlusion 2e-6).  (The oracle with 4 threads against the oracle
-with all 16 threads was measured bit-identical on the B200 box, so thread-count noise is not the yardstick there.)
-The assertion is on the bulk (p99 < 5e-4;
-measured 3e-5), the flip fraction (< 5e-3; measured 1.1-1.5e-3, the reference's own figure) and PSNR(ours, oracle) > 60 dB
-(measured 78-81 dB), not on max-abs."""
+test_full_size_forward_against_reference_golden (default under -m gpu, no CPU oracle time): the B200 forward against
+tests/golden/full_736x1280_n3.npz -- outputs of the UNMODIFIED reference module run once at this size by
+oracle/gen_golden_full.py: point samples on a stride-4 lattice (exact fp32 values) and 8x8 block sums of the full-resolution
+tensors (every pixel contributes).  The network contains discontinuous operators (floor() in the flow-reversal splat,
+bwarp's 0.999 validity threshold, DeMFInet.py:606-766): a 1e-6 difference upstream flips isolated pixels by 1e-2..1e-1
+downstream, and the decoders' receptive fields spread each flip over a neighbourhood.  The reference does this to ITSELF
+when only its CPU thread count changes; the golden's .json records that yardstick at this very size (1 thread vs all:
+St_final max-abs 0.13, 1.1e-3 of the samples beyond 5e-4, 68 blocks of flow0 moved).  Hence:
+  * reported, not asserted: the literal max-abs per tensor (it equals a flip's size, as in the reference's self-noise);
+  * asserted: away (>= 32 px) from the blocks where the splat took the other floor() branch, max-abs <= 5e-4 -- the north
+    star's tolerance -- on every sampled tensor and block-mean error <= 2e-4 on every block; over ALL samples p99 <= 5e-4,
+    the fraction beyond 5e-4 and the number of flipped blocks no larger than 2x the reference's own; PSNR(ours, reference)
+    >= 60 dB on the frames (the north star asks for 0.01 dB of PSNR against ground truth).
+The figures are written to gpurun_out/parity_full_size_golden.json (committed copy: profiles/r2_parity_full_size.json).
+
+test_full_size_forward_against_oracle: opt-in (DEMFI_FULL_PARITY=1), the same forward against the ORACLE run on the GPU
+box's host cores at full resolution (minutes of CPU) -- every pixel pointwise; report profiles/r1_parity_full_size.json."""
 import json
 import os
 import time
@@ -25,11 +28,77 @@ from demfi_b200 import metrics, synth
 from demfi_b200.DeMFInet import DeMFInet
 from oracle import demfi_oracle as O
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("DEMFI_FULL_PARITY") != "1", reason="opt-in: DEMFI_FULL_PARITY=1 (minutes of CPU)")]
+pytestmark = [pytest.mark.gpu]
 H, W, N, T = 736, 1280, 3, 0.375
 TOL = 5e-4
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
+
+def test_full_size_forward_against_reference_golden(state_dict):
+    import numpy as np
+    dev = torch.device("cuda:0")
+    gold = np.load(os.path.join(GOLD, "full_736x1280_n3.npz"))
+    with open(os.path.join(GOLD, "full_736x1280_n3.json")) as f:
+        meta = json.load(f)
+    assert meta["shape"] == [H, W] and meta["N_tst"] == N and meta["t"] == T
+    noise = meta["self_noise"]
+    net = DeMFInet(synth.default_args()).to(dev).eval()
+    net.load_state_dict(state_dict, strict=True)
+    with torch.no_grad():
+        res = net(synth.make_frames(H, W, seed=0).to(dev), torch.tensor([[T]], device=dev), N)
+    torch.cuda.synchronize()
+    got = O.flatten_outputs(res)
+
+    def blk(v):
+        b, c, h, w = v.shape
+        return v.double().reshape(b, c, h // 8, 8, w // 8, 8).sum(dim=(3, 5))
+
+    def g(name):
+        return torch.from_numpy(gold[name]).to(dev)
+
+    # blocks where the complementary-flow-reversal splat took the other floor() branch than the reference run
+    site = ((blk(got["flow0"]) - g("flow0/blk").double()).abs().amax(dim=1, keepdim=True) > 1e-3).float()   # [1,1,H/8,W/8]
+    near_blk = torch.nn.functional.max_pool2d(site, 9, 1, 4) > 0                                           # within 32 px
+    near_px = near_blk.repeat_interleave(8, dim=2).repeat_interleave(8, dim=3)[..., 1::4, 2::4]
+    report = {"what": "demfi_b200 forward on B200 vs the unmodified reference (tests/golden/full_736x1280_n3.npz)", "shape": [H, W],
+              "N_tst": N, "t": T, "tolerance": TOL, "splat_flip_blocks": int(site.sum()),
+              "reference_self_noise_flip_blocks": noise["splat_flip_blocks"], "masked_fraction_r32": float(near_blk.float().mean()),
+              "tensors": {}}
+    for key in sorted(gold.files):
+        name, kind = key.split("/")
+        ent = report["tensors"].setdefault(name, {})
+        if kind == "pts":
+            e = (got[name][..., 1::4, 2::4] - g(key)).abs()
+            ea = e.amax(dim=1, keepdim=True)
+            ent.update({"pts_max_abs": float(e.max()), "pts_p99": float(torch.quantile(e.flatten()[:4_000_000], 0.99)),
+                        "pts_frac_gt_5e-4": float((e > TOL).float().mean()),
+                        "pts_max_abs_away_from_flips_r32": float(ea[~near_px].max()),
+                        "reference_self_noise": {k: noise["tensors"][name][k] for k in ("pts_max_abs", "pts_frac_gt_5e-4")}})
+            if name.startswith("S"):
+                mse = float((((got[name][..., 1::4, 2::4] - g(key)) * 0.5) ** 2).mean())
+                ent["psnr_ours_vs_ref_db"] = 99.0 if mse == 0 else -10.0 * float(np.log10(mse))
+        else:
+            eb = (blk(got[name]) - g(key).double()).abs().amax(dim=1, keepdim=True) / 64.0
+            ent.update({"blk_mean_max_abs": float(eb.max()), "blk_mean_max_abs_away_from_flips_r32": float(eb[~near_blk].max())})
+    for name, ent in report["tensors"].items():
+        print(name, json.dumps(ent))
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/parity_full_size_golden.json", "w") as f:
+        json.dump(report, f, indent=1)
+    assert report["splat_flip_blocks"] <= 2 * max(noise["splat_flip_blocks"], 1), report["splat_flip_blocks"]
+    assert report["masked_fraction_r32"] < 0.25
+    for name, ent in report["tensors"].items():
+        if "pts_p99" in ent:
+            assert ent["pts_p99"] < TOL, (name, ent)
+            assert ent["pts_max_abs_away_from_flips_r32"] < TOL, (name, ent)
+            assert ent["pts_frac_gt_5e-4"] <= max(2 * ent["reference_self_noise"]["pts_frac_gt_5e-4"], 5e-4), (name, ent)
+        if "blk_mean_max_abs" in ent:
+            assert ent["blk_mean_max_abs_away_from_flips_r32"] < 2e-4, (name, ent)
+        if "psnr_ours_vs_ref_db" in ent:
+            assert ent["psnr_ours_vs_ref_db"] > 60.0, (name, ent)
+
+
+@pytest.mark.skipif(os.environ.get("DEMFI_FULL_PARITY") != "1", reason="opt-in: DEMFI_FULL_PARITY=1 (minutes of CPU)")
 
 def test_full_size_forward_against_oracle(state_dict):
     dev = torch.device("cuda:0")
