@@ -193,5 +193,5 @@ class DeMFInet(nn.Module):
             return (sharps_dec1, sharps_final, flows, occs, two_blurry, difference_maps,
                     [[flows[0][:, 0:2], flows[0][:, 2:4]]])
         v = eng.views
-        blending_weights = [maps[0], maps[1], maps[0], maps[1], [v["FO"].ch(0, 2).to_nchw(), v["FO"].ch(2, 2).to_nchw()]]
+        blending_weights = [maps[0], maps[1], maps[0], maps[1], [v["FO"].ch(4, 2).to_nchw(), v["FO"].ch(6, 2).to_nchw()]]
         return sharps_dec1, sharps_final, flows, occs, two_blurry, blending_weights, difference_maps

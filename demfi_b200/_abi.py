@@ -61,6 +61,7 @@ SYMBOLS = {
     "demfi_pack_input": (i32, [vp, i32, i32, i32, vp, vp, i32, vp, i32, vp, vp]),
     "demfi_cfr_splat": (i32, [vp, i32, vp, i32, i32, i32, vp, vp]),
     "demfi_cfr_finalize": (i32, [vp, vp, i32, i32, i32, vp, i32, vp]),
+    "demfi_pwb": (i32, [vp, i32, vp, i32, vp, i32, i32, i32, vp, i32, vp]),
     "demfi_bwarp_blend": (i32, [vp, i32, vp, i32, vp, i32, vp, i32, vp, i32, i32, i32, i32, vp, i32, vp, i32, vp]),
     "demfi_fgac_sample": (i32, [vp, i32, vp, i32, i32, i32, i32, i32, vp, i32, vp]),
     "demfi_fgac_blend": (i32, [vp, i32, vp, i32, vp, i32, C.c_int64, i32, vp, i32, vp]),

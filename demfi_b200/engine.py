@@ -88,7 +88,9 @@ class Engine:
         # S16 activation storage between convolutions (conv_s3 only); "tc16f32" keeps every buffer fp32 (comparison)
         self.use_s16 = self.conv_kind in ("auto", "tc16") and os.environ.get("DEMFI_S16", "1") != "0"
         # dense blocks in "push" form (_rdb_push_ops): needs conv_s3's per-box epilogue plans, i.e. the S16 / TMA-store path
-        self.rdb_push = self.use_s16 and os.environ.get("DEMFI_RDB_PUSH", "1") != "0"
+        # (measured: 0.43 ms per block against 0.39 ms in the reference's pull form -- the K = 32 launches are bound by their
+        # epilogue (fp32 partial sums read and written per tile), not by the MMAs they save -- so it is opt-in)
+        self.rdb_push = self.use_s16 and os.environ.get("DEMFI_RDB_PUSH", "0") == "1"
         self._keep: list = []  # weights, ctypes structs
         self.bufs: Dict[str, torch.Tensor] = {}
         self.views: Dict[str, View] = {}
@@ -146,7 +148,10 @@ class Engine:
         v["DL0"] = self._buf("DL0", B, H, W, 8)
         v["DL1"] = self._buf("DL1", B, H, W, 8)
         v["REF"] = self._buf("REF", B, H, W, 32)
-        v["A3"] = self._buf("A3", B, H, W, 36)
+        # D2's side inputs (Agg3 without F_rec, DeMFInet.py:151-155), internal order: S0' pad | S1' pad | St_new occ_final |
+        # flow_final (4) | occ_0 pad3 | rflow_t0 rflow_t1 | flow_01 flow_10 | B0 B1 B-1 B2 -- every producer writes whole 16-byte
+        # units and the pixel warp of the boosting loop reads / writes whole 32-byte sectors (demfi_pwb)
+        v["A3"] = self._buf("A3", B, H, W, 40)
         for i in range(3):
             v[f"FR{i}"] = self._buf(f"FR{i}", B, H, W, 64, s16=True)
         v["R1"] = self._buf("R1", B, H, W, 32, s16=True)
@@ -157,7 +162,7 @@ class Engine:
         v["Z"] = self._buf("Z", B, H, W, 64, s16=True)
         v["RH"] = self._buf("RH", B, H, W, 64, s16=True)
         v["FO1"] = self._buf("FO1", B, H, W, 32, s16=True)
-        v["D2O"] = self._buf("D2O", B, H, W, 12)
+        v["D2O"] = self._buf("D2O", B, H, W, 12)  # S0_final pad | S1_final pad | St_final pad
         self.t_dev = torch.zeros(B, dtype=torch.float32, device=self.dev)
 
     def workspace_bytes(self) -> int:
@@ -188,7 +193,9 @@ class Engine:
         if not tc16_ok:
             return A.CONV_FFMA
         # 97..128 output channels as ONE N block (conv_s3 only: stride 1)
-        wide = stride == 1 and 96 < cout_pad <= 128 and os.environ.get("DEMFI_WIDE_N", "1") != "0"
+        # (measured at 1280x736, profiles/r2_conv_notes.md: GRU z|r 1.87 ms as one N = 128 block vs 1.64 ms as two N = 64 blocks -- the
+        # ring then streams its weights at 42.7 B/clk/SM, the L2 ceiling -- so it is opt-in)
+        wide = stride == 1 and 96 < cout_pad <= 128 and os.environ.get("DEMFI_WIDE_N", "0") == "1"
         return A.CONV_TC16W if wide else A.CONV_TC16
 
     def conv(self, names, srcs, out_hw, N, segs, k=(3, 3), stride=1, pad=None, in_map=None, out_map=None,
@@ -340,9 +347,12 @@ class Engine:
                              [full(v["U"], 256, none, store=A.STORE_PIXEL_SHUFFLE2)],
                              out_map=[(n % 64) * 4 + n // 64 for n in range(256)]))
         F01 = v["F01"]
+        # FO = [occ logit, pad3, flow_01, flow_10]: the order of AGG1's channels 196..203 (UNet input), so that the same eight
+        # accumulator channels go to both places from the epilogue (one result, two destinations) -- no copy kernels
+        upnet2_out = list(range(128)) + [132, -1, -1, -1, 128, 129, 130, 131] + [-1] * 8
         ops.append(self.conv(p + "UPNet.2", [v["U"]], (H, W), B,
                              [full(F01.frames(0, B), 64, tanh, ch0=0), full(F01.frames(B, B), 64, tanh, ch0=64),
-                              full(v["FO"], 8, none, ch0=128)]))
+                              full(v["FO"], 8, none, ch0=128), full(v["AGG1"].ch(196, 8), 8, none, ch0=128)], out_map=upnet2_out))
 
         # ---- FAC_FB (DeMFInet.py:335-358) : shared encoder on [F0;F1], then the two FGAC directions
         p = "FAC_FB_Module."
@@ -359,8 +369,8 @@ class Engine:
         ops.append(self.conv(g + "conv_ref_k", [SE.ch(0, 64)], (H, W), 2 * B, [full(v["RK"], 64)], k=(1, 1)))
         FO = v["FO"]
         # direction 0: ref = enc(F1), source = enc(F0), flow_01; direction 1: the converse (DeMFInet.py:346-349)
-        ops.append(("fgac_sample", v["RK"].frames(B, B), FO.ch(0, 2), v["SMP"].frames(0, B)))
-        ops.append(("fgac_sample", v["RK"].frames(0, B), FO.ch(2, 2), v["SMP"].frames(B, B)))
+        ops.append(("fgac_sample", v["RK"].frames(B, B), FO.ch(4, 2), v["SMP"].frames(0, B)))
+        ops.append(("fgac_sample", v["RK"].frames(0, B), FO.ch(6, 2), v["SMP"].frames(B, B)))
         ops.append(self.conv(g + "fusion", [v["SMP"]], (H, W), 2 * B, [full(SE.ch(64, 64), 64)], k=(1, 1)))
         ops.append(self.conv(g + "w_gen", [SE], (H, W), 2 * B, [full(v["WG"], 64, relu)]))
         ops.append(self.conv(g + "w_gen_2", [v["WG"]], (H, W), 2 * B, [full(v["WL"], 4, sig)]))
@@ -368,16 +378,14 @@ class Engine:
         for d_ in range(2):
             ops.append(("fgac_blend", v["WL"].frames(d_ * B, B), SE.frames(d_ * B, B).ch(0, 64),
                         SE.frames(d_ * B, B).ch(64, 64), AGG1.ch(64 * d_, 64)))
-        ops.append(("copy", FO.ch(4, 1), AGG1.ch(196, 1), none))
-        ops.append(("copy", FO.ch(0, 4), AGG1.ch(200, 4), none))
 
         # ---- t-dependent stage I (DeMFInet.py:63-102)
         ops = []
         self.ops_stage1 = ops
         ops.append(("zero", v["ACC"]))
-        ops.append(("cfr_splat", FO, v["ACC"]))
+        ops.append(("cfr_splat", FO.ch(4, 4), v["ACC"]))
         ops.append(("cfr_finalize", v["ACC"], AGG1.ch(192, 4)))
-        ops.append(("bwarp_blend", F01.frames(0, B), F01.frames(B, B), AGG1.ch(192, 4), FO.ch(4, 1), AGG1.ch(128, 64), None))
+        ops.append(("bwarp_blend", F01.frames(0, B), F01.frames(B, B), AGG1.ch(192, 4), FO.ch(0, 1), AGG1.ch(128, 64), None))
         p = "Refine_Module."
         # internal AGG1 order: aF0 aF1 Ft | flow_t0 flow_t1 | occ pad3 | flow_01 flow_10
         agg1_map = list(range(192)) + [192, 193, 194, 195, 200, -1, -1, -1, 196, 197, 198, 199]
@@ -399,7 +407,7 @@ class Engine:
                               full(DL0, 8, none, AGG1.ch(192, 8), ch0=128)], out_map=dec3_out))
         A3 = v["A3"]
         ops.append(("bwarp_blend", DECIN.frames(0, B), DECIN.frames(B, B), DL0.ch(0, 4), DL0.ch(4, 1),
-                    DECIN.frames(2 * B, B), A3.ch(9, 1)))
+                    DECIN.frames(2 * B, B), A3.ch(16, 1)))
         # D1 (DeMFInet.py:95-102): three frames batched
         pool3 = [v["P0"], v["P1"], v["P2"]]
         ops.append(self.conv("Dec_first", [DECIN], (H, W), 3 * B, [full(pool3[0], 64, relu)]))
@@ -414,9 +422,9 @@ class Engine:
         REF = v["REF"]
         # ref_list (DeMFInet.py:117-120) and the static part of Agg3 (:151-155): each destination row is assembled in one pass
         ops.append(("gather", REF, [(SP.frames(f * B, B).ch(0, 3), 3 * f) for f in range(3)] +
-                    [(FO.ch(0, 4), 21), (DL0.ch(0, 5), 25)]))
-        ops.append(("gather", A3, [(SP.frames(f * B, B).ch(0, 3), 3 * f) for f in range(2)] +
-                    [(DL0.ch(0, 4), 10), (FO.ch(0, 4), 14)]))
+                    [(FO.ch(4, 4), 21), (DL0.ch(0, 5), 25)]))
+        ops.append(("gather", A3, [(SP.frames(f * B, B).ch(0, 3), 4 * f) for f in range(2)] +
+                    [(DL0.ch(0, 4), 20), (FO.ch(4, 4), 24)]))
         # Ch_Reducer (DeMFInet.py:114) over cat(rF0, rF1, rFt)
         FR = [v["FR0"], v["FR1"], v["FR2"]]
         ops.append(self.conv("Ch_Reducer", [DECIN.frames(0, B), DECIN.frames(B, B), DECIN.frames(2 * B, B)], (H, W), B,
@@ -435,8 +443,9 @@ class Engine:
                     assert op[1].fmt == A.FMT_F32 and all(sv.fmt == A.FMT_F32 for sv, _ in op[2])
                 elif op[0] not in ("conv", "upsample"):
                     assert all(a_.fmt == A.FMT_F32 for a_ in op[1:] if isinstance(a_, View)), op[0]
-        self._agg3_map = (list(range(9)) + [73] + [74, 75, 76, 77] + [80, 81, 78, 79] + [82, 83, 84, 85] + [86]
-                          + list(range(87, 99)) + [-1] + list(range(9, 73)))
+        # internal A3 channel -> reference Agg3 channel (DeMFInet.py:151-155), then F_rec
+        self._agg3_map = ([0, 1, 2, -1, 3, 4, 5, -1, 6, 7, 8, 86, 82, 83, 84, 85, 73, -1, -1, -1, 74, 75, 76, 77, 80, 81, 78, 79]
+                          + list(range(87, 99)) + list(range(9, 73)))
 
     def _iter_ops(self, itr: int, decode: bool) -> list:
         key = (itr % 6, decode)  # FR rotates with period 3, DL with period 2
@@ -480,8 +489,7 @@ class Engine:
         A3 = v["A3"]
         ops = []
         # PWB (DeMFInet.py:146-149) + D2 (DeMFInet.py:151-165)
-        ops.append(("bwarp_blend", A3.ch(0, 3), A3.ch(3, 3), DLo.ch(0, 4), DLo.ch(4, 1), A3.ch(6, 3), A3.ch(22, 1)))
-        ops.append(("copy", DLo.ch(0, 4), A3.ch(18, 4), none))
+        ops.append(("pwb", A3.ch(0, 8), DLo, A3.ch(8, 8)))
         pool = [v["P0"].frames(0, B), v["P1"].frames(0, B), v["P2"].frames(0, B)]
         ops.append(self.conv("Dec_first_2", [A3, hout], (H, W), B, [full(pool[0], 64, relu)], in_map=self._agg3_map))
         a, b_, c_ = pool
@@ -490,7 +498,9 @@ class Engine:
             ops.append(self.conv(f"Decoder_res_2.{i}.conv2", [b_], (H, W), B, [full(c_, 64, none, a)]))
             a, c_ = c_, a
         ops.append(self.conv("Dec_last1_2", [a], (H, W), B, [full(b_, 64, relu)]))
-        ops.append(self.conv("Dec_last2_2", [b_], (H, W), B, [full(v["D2O"], 12, none, A3.ch(0, 12))]))
+        # out + [S0', S1', St_new] (DeMFInet.py:161-163): the residual is the first 12 channels of A3 as they lie
+        ops.append(self.conv("Dec_last2_2", [b_], (H, W), B, [full(v["D2O"], 12, none, A3.ch(0, 12))], cout=12,
+                             out_map=[0, 1, 2, -1, 3, 4, 5, -1, 6, 7, 8, -1, -1, -1, -1, -1]))
         return ops
 
     # ------------------------------------------------------------------ static checks
@@ -573,7 +583,7 @@ class Engine:
                         write(op[1].ch(c0, sv.C))
                 else:
                     vs = [a_ for a_ in op[1:] if isinstance(a_, View)]
-                    first_out = {"copy": 1, "cfr_splat": 1, "cfr_finalize": 1, "bwarp_blend": 4, "fgac_sample": 2, "fgac_blend": 3}[op[0]]
+                    first_out = {"copy": 1, "cfr_splat": 1, "cfr_finalize": 1, "bwarp_blend": 4, "fgac_sample": 2, "fgac_blend": 3, "pwb": 2}[op[0]]
                     outs = vs[first_out:]
                     for vw in vs:
                         assert vw.fmt == A.FMT_F32, f"{op[0]} only handles fp32 views"
@@ -628,6 +638,9 @@ class Engine:
             A.check(lib.demfi_bwarp_blend(a.ptr, a.ld, b.ptr, b.ld, fl.ptr, fl.ld, oc.ptr, oc.ld, self.t_dev.data_ptr(),
                                           B, H, W, a.C, out.ptr, out.ld, oo.ptr if oo is not None else None,
                                           oo.ld if oo is not None else 0, st), "bwarp_blend")
+        elif k == "pwb":
+            img, fo, out = op[1:]
+            A.check(lib.demfi_pwb(img.ptr, img.ld, fo.ptr, fo.ld, self.t_dev.data_ptr(), B, H, W, out.ptr, out.ld, st), "pwb")
         elif k == "fgac_sample":
             r, fl, out = op[1:]
             A.check(lib.demfi_fgac_sample(r.ptr, r.ld, fl.ptr, fl.ld, r.N, H, W, r.C, out.ptr, out.ld, st), "fgac_sample")
@@ -686,14 +699,14 @@ class Engine:
             self._tb = torch.empty((B, 3, H, W), dtype=torch.float32, device=self.dev)
         if not reuse_prefix:
             A.check(lib.demfi_pack_input(x.data_ptr(), B, H, W, v["S2D"].ptr, v["REF"].ch(9, 12).ptr, 32,
-                                         v["A3"].ch(23, 12).ptr, 36, self._tb.data_ptr(), st), "pack_input")
+                                         v["A3"].ch(28, 12).ptr, 40, self._tb.data_ptr(), st), "pack_input")
             self._run(self.ops_prefix_ff, st)
         two_blurry = self._tb.clone()
         self._run(self.ops_stage1, st)
         SP, A3, DL0 = v["SP"], v["A3"], v["DL0"]
         sharps_dec1 = [self._export(SP.frames(f * B, B), 3, st) for f in range(3)]
         flow_predictions = [self._export(DL0, 4, st)]
-        occ0_predictions = [self._export(A3.ch(9, 1), 1, st)]
+        occ0_predictions = [self._export(A3.ch(16, 1), 1, st)]
         sharps_final = []
         for itr in range(num_update):
             decode = (not final_only) or itr == num_update - 1
@@ -703,7 +716,7 @@ class Engine:
             occ0_predictions.append(self._export(DLo.ch(4, 1), 1, st, A.ACT_SIGMOID))
             if decode:
                 D2O = v["D2O"]
-                sharps_final.append([self._export(D2O.ch(3 * j, 3), 3, st) for j in range(3)])
+                sharps_final.append([self._export(D2O.ch(4 * j, 3), 3, st) for j in range(3)])
             else:
                 sharps_final.append(None)
         return sharps_dec1, sharps_final, flow_predictions, occ0_predictions, two_blurry
@@ -715,8 +728,12 @@ class Engine:
         if k == "bwarp_blend":
             a, out, oo = op[1], op[5], op[6]
             return a.npix() * 4 * (2 * a.C + 4 + 1 + a.C + (1 if oo is not None else 0))
+        if k == "pwb":   # two 3-channel frames + flows and occlusion in, frame + occlusion + flows out
+            return op[1].npix() * 4 * (6 + 5 + 8)
         if k == "fgac_sample":
-            return op[1].npix() * 4 * (2 * op[1].C + 2)
+            # DRAM bytes, not "every operand once": the coordinates are absolute (DeMFInet.py:403-419), so every pixel gathers
+            # around the image origin and the source is never streamed (ncu, r1): flow in, sampled features out
+            return op[1].npix() * 4 * (op[1].C + 2)
         if k == "fgac_blend":
             return op[2].npix() * 4 * (1 + 3 * op[2].C)
         if k == "cfr_splat":

@@ -163,6 +163,13 @@ int demfi_bwarp_blend(const float* a, int32_t a_ld, const float* b, int32_t b_ld
                       const float* occ, int32_t occ_ld, const float* t, int32_t B, int32_t H, int32_t W, int32_t C,
                       float* out, int32_t out_ld, float* occ_out, int32_t occ_out_ld, void* stream);
 
+/* Pixel-wise blending of the boosting loop (PWB, DeMFInet.py:146-149) fused with the concatenations around it
+ * (DeMFInet.py:151-155): img = [S0' (3) pad | S1' (3) pad] (8 channels per pixel), fo = the iteration's refined
+ * [flow_t0 (2), flow_t1 (2), occlusion logit, pad 3]; writes out = [St (3), sigmoid(occ) | flow_t0, flow_t1] (8 channels)
+ * -- the same Eq.(2) arithmetic as demfi_bwarp_blend with C = 3, with every access a whole 16 / 32-byte unit. */
+int demfi_pwb(const float* img, int32_t img_ld, const float* fo, int32_t fo_ld, const float* t, int32_t B, int32_t H, int32_t W,
+              float* out, int32_t out_ld, void* stream);
+
 /* FGAC sampling (FGAC.forward step (i), DeMFInet.py:403-419 + bilinear_sampler :499-514) with
  * rr = sr = 0: out(y,x,:) = bilinear(ref_k, at absolute position (flow.x, flow.y)), zeros
  * outside.  The correlation/softmax that follows in the reference runs over one element and is

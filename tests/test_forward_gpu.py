@@ -69,7 +69,7 @@ def test_intermediates_match_oracle(state_dict, golden_meta):
     v = eng.views
     mine = {
         "F0": v["F01"].frames(0, B), "F1": v["F01"].frames(B, B),
-        "flow_01": v["FO"].ch(0, 2), "flow_10": v["FO"].ch(2, 2), "occ_logit_ff": v["FO"].ch(4, 1),
+        "flow_01": v["FO"].ch(4, 2), "flow_10": v["FO"].ch(6, 2), "occ_logit_ff": v["FO"].ch(0, 1),
         "flow_t0": v["AGG1"].ch(192, 2), "flow_t1": v["AGG1"].ch(194, 2), "Ft": v["AGG1"].ch(128, 64),
         "enc0": v["SE"].frames(0, B).ch(0, 64), "enc1": v["SE"].frames(B, B).ch(0, 64),
         "fgac_sampled0": v["SMP"].frames(0, B), "fgac_sampled1": v["SMP"].frames(B, B),

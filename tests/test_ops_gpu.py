@@ -53,6 +53,28 @@ def test_bwarp_blend(C, n, h, w):
     assert float((from_nhwc(oo, 1) - torch.sigmoid(occ)).abs().max()) < 1e-6
 
 
+@pytest.mark.parametrize("n,h,w", [(1, 24, 40), (2, 16, 16), (1, 33, 51)])
+def test_pwb_fused(n, h, w):
+    """PWB of the boosting loop (DeMFInet.py:146-149) on the padded 8-channel row [S0' pad | S1' pad] -> [St occ | flows],
+    against the oracle's Eq.(2) blend; integer flows, out-of-image targets and the 0.999 band included"""
+    a, b = rnd(n, 3, h, w, seed=1), rnd(n, 3, h, w, seed=2)
+    fl = flows_with_edge_cases(n, h, w, 3)
+    occ = rnd(n, 1, h, w, seed=4)
+    t = torch.tensor([0.375, 0.75][:n])
+    want = O.eq2_blend(a, fl[:, 0:2], b, fl[:, 2:4], occ, t.view(n, 1, 1, 1))
+    z1 = torch.zeros(n, 1, h, w)
+    row, ld = nhwc(torch.cat([a, z1, b, z1, torch.full((n, 8, h, w), 7.0)], 1), 40)   # out slot pre-filled: every channel is written
+    fo, _ = nhwc(torch.cat([fl, occ], 1), 8)
+    img = row.view(-1)
+    A.check(A.lib().demfi_pwb(row.data_ptr(), ld, fo.data_ptr(), 8, t.to(DEV).data_ptr(), n, h, w, row.data_ptr() + 4 * 8, ld, stream()), "pwb")
+    torch.cuda.synchronize()
+    got = from_nhwc(row, 16)
+    assert float((got[:, 8:11] - want).abs().max()) < 1e-5
+    assert float((got[:, 11:12] - torch.sigmoid(occ)).abs().max()) < 1e-6
+    assert torch.equal(got[:, 12:16], fl)                       # the flows are copied bit for bit
+    assert torch.equal(got[:, 0:8], torch.cat([a, z1, b, z1], 1))  # the inputs are untouched
+
+
 @pytest.mark.parametrize("n,h,w", [(1, 24, 40), (2, 16, 24)])
 def test_cfr_splat_finalize(n, h, w):
     fl = flows_with_edge_cases(n, h, w, 5)
