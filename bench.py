@@ -201,6 +201,9 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     K, Wm = args.steps, max(args.warmup, 3)
+    for kv in filter(None, os.environ.get("DEMFI_OPTS", "").split(",")):  # diagnostics: library options for an A/B run, e.g. tc_flush=10
+        k_, v_ = kv.split("=")
+        A.set_option(k_, int(v_))
 
     peaks = {}
     try:

@@ -16,7 +16,7 @@ MAX_SRC = 4
 MAX_SEG = 4
 ACT_NONE, ACT_RELU, ACT_TANH, ACT_SIGMOID, ACT_SIGMOID_MUL, ACT_GRU = range(6)
 STORE_NHWC, STORE_PIXEL_SHUFFLE2 = 0, 1
-CONV_FFMA, CONV_TC, CONV_TC16, CONV_TC16W = 0, 1, 2, 3
+CONV_FFMA, CONV_TC, CONV_TC16, CONV_TC16W, CONV_TC16P = 0, 1, 2, 3, 4
 FMT_F32, FMT_S16 = 0, 1
 SEG_DST_S16, SEG_RES_S16, SEG_RES2_S16 = 1, 2, 4
 

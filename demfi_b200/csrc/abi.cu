@@ -21,7 +21,7 @@ void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_r
 
 static std::atomic<int> g_opt_mask_hi{1};
 static std::atomic<int> g_opt_split{3};
-static std::atomic<int> g_opt_flush{10};
+static std::atomic<int> g_opt_flush{20};  // stages per accumulation segment (tools/flush_sweep.py: error unchanged up to 24)
 static std::atomic<int> g_opt_atmem{1};   // A operand through tensor memory (1) or shared memory (0)
 static std::atomic<int> g_opt_diag{0};
 static std::atomic<int> g_opt_comp{270};
@@ -127,7 +127,7 @@ int demfi_get_option(const char* name, int32_t* value) {
 size_t demfi_packed_weight_floats(int32_t kind, int32_t KH, int32_t KW, const int32_t* src_C, int32_t nsrc,
                                   int32_t cout_pad) {
   if (kind == DEMFI_CONV_TC) return tc_packed_floats(KH, KW, src_C, nsrc, cout_pad);
-  if (kind == DEMFI_CONV_TC16 || kind == DEMFI_CONV_TC16W) return h3_packed_floats(KH, KW, src_C, nsrc, cout_pad);
+  if (kind == DEMFI_CONV_TC16 || kind == DEMFI_CONV_TC16W || kind == DEMFI_CONV_TC16P) return h3_packed_floats(KH, KW, src_C, nsrc, cout_pad);
   int k_total = 0;
   for (int s = 0; s < nsrc; ++s) k_total += src_C[s];
   return (size_t)KH * KW * k_total * cout_pad;
@@ -145,6 +145,7 @@ int demfi_pack_weights(int32_t kind, const float* w, int32_t Co, int32_t Ci, int
   for (int n = 0; n < cout_pad; ++n) DEMFI_REQUIRE(out_map[n] >= -1 && out_map[n] < Co, "pack_weights: out_map[%d] out of range", n);
   if (kind == DEMFI_CONV_TC) return tc_pack_weights(w, Co, Ci, KH, KW, in_map, src_C, nsrc, out_map, cout_pad, out);
   if (kind == DEMFI_CONV_TC16) return h3_pack_weights(w, Co, Ci, KH, KW, in_map, src_C, nsrc, out_map, cout_pad, out);
+  if (kind == DEMFI_CONV_TC16P) return s3_pack_weights_pair(w, Co, Ci, KH, KW, in_map, src_C, nsrc, out_map, cout_pad, out);
   if (kind == DEMFI_CONV_TC16W)
     return h3_pack_weights(w, Co, Ci, KH, KW, in_map, src_C, nsrc, out_map, cout_pad, out, s3_nb_max(kind, cout_pad));
   // FFMA layout: [tap][k][cout_pad]
@@ -171,9 +172,10 @@ int demfi_conv_describe(const demfi_conv_t* c, int32_t* info) {
   for (int i = 0; i < 16; ++i) info[i] = 0;
   if (c->kind == DEMFI_CONV_FFMA) return 0;
   if (c->kind == DEMFI_CONV_TC) { info[0] = 1; return 0; }
-  DEMFI_REQUIRE(c->kind == DEMFI_CONV_TC16 || c->kind == DEMFI_CONV_TC16W, "conv_describe: unknown kind %d", c->kind);
-  if (c->kind == DEMFI_CONV_TC16W) DEMFI_REQUIRE(s3_supports(*c), "conv_describe: DEMFI_CONV_TC16W needs a convolution conv_s3 supports");
-  if ((g_opt_gen.load() == 3 || c->kind == DEMFI_CONV_TC16W) && s3_supports(*c)) {
+  const bool s3_only = c->kind == DEMFI_CONV_TC16W || c->kind == DEMFI_CONV_TC16P;
+  DEMFI_REQUIRE(c->kind == DEMFI_CONV_TC16 || s3_only, "conv_describe: unknown kind %d", c->kind);
+  if (s3_only) DEMFI_REQUIRE(s3_supports(*c), "conv_describe: DEMFI_CONV_TC16W / TC16P need a convolution conv_s3 supports");
+  if ((g_opt_gen.load() == 3 || s3_only) && s3_supports(*c)) {
     info[0] = 3;
     return s3_describe(*c, info);
   }
@@ -226,7 +228,8 @@ int demfi_conv2d(const demfi_conv_t* c, void* stream) {
       }
     }
     if (any_s16)
-      DEMFI_REQUIRE(((c->kind == DEMFI_CONV_TC16 && g_opt_gen.load() == 3) || c->kind == DEMFI_CONV_TC16W) && s3_supports(*c) && s3_s16_ok(*c),
+      DEMFI_REQUIRE(((c->kind == DEMFI_CONV_TC16 && g_opt_gen.load() == 3) || c->kind == DEMFI_CONV_TC16W || c->kind == DEMFI_CONV_TC16P) &&
+                        s3_supports(*c) && s3_s16_ok(*c),
                     "conv2d: the S16 activation format is only implemented by the conv_s3 kernel (stride 1, TMA epilogue)");
   }
   if (c->kind == DEMFI_CONV_TC) return launch_conv_tc(*c, (cudaStream_t)stream);
@@ -234,8 +237,9 @@ int demfi_conv2d(const demfi_conv_t* c, void* stream) {
     if (g_opt_gen.load() == 3 && s3_supports(*c)) return launch_conv_s3(*c, (cudaStream_t)stream);
     return launch_conv_h3(*c, (cudaStream_t)stream);
   }
-  if (c->kind == DEMFI_CONV_TC16W) {
-    DEMFI_REQUIRE(s3_supports(*c), "conv2d: DEMFI_CONV_TC16W needs a convolution conv_s3 supports (stride 1, no up-sampled source)");
+  if (c->kind == DEMFI_CONV_TC16W || c->kind == DEMFI_CONV_TC16P) {
+    DEMFI_REQUIRE(s3_supports(*c), "conv2d: DEMFI_CONV_TC16W / TC16P need a convolution conv_s3 supports (stride 1, no up-sampled source; "
+                                   "TC16P: 32 or 64 output channels)");
     return launch_conv_s3(*c, (cudaStream_t)stream);
   }
   DEMFI_REQUIRE(c->kind == DEMFI_CONV_FFMA, "conv2d: unknown kind %d", c->kind);

@@ -135,6 +135,8 @@ size_t h3_packed_floats(int KH, int KW, const int32_t* src_C, int nsrc, int cout
 int h3_pack_weights(const float* w, int Co, int Ci, int KH, int KW, const int32_t* in_map, const int32_t* src_C,
                     int nsrc, const int32_t* out_map, int cout_pad, float* out, int nb_max = 0);
 int s3_nb_max(int kind, int cout_pad);
+int s3_pack_weights_pair(const float* w, int Co, int Ci, int KH, int KW, const int32_t* in_map, const int32_t* src_C, int nsrc,
+                         const int32_t* out_map, int cout_pad, float* out);
 size_t tc_packed_floats(int KH, int KW, const int32_t* src_C, int nsrc, int cout_pad);
 int tc_pack_weights(const float* w, int Co, int Ci, int KH, int KW, const int32_t* in_map, const int32_t* src_C,
                     int nsrc, const int32_t* out_map, int cout_pad, float* out);

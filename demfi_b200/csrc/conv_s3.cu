@@ -52,7 +52,8 @@ constexpr int S3_THREADS = (S3_CV_WARPS + S3_EPI_WARPS + 2) * 32;  // 512: 0-5 c
 constexpr int S3_MAX_NA = 6;   // halo-tile buffers (3 in general; up to 6 for 1x1 / few-tap kernels, which are HBM-latency bound)
 constexpr int S3_MAX_NS = 8;   // weight ring
 constexpr int S3_BOX_BYTES = S3_BM * 128;  // one 32-channel staging box
-constexpr int S3_NBARS = 3 * S3_MAX_NA + 4 + 2 + 2 * S3_MAX_NS;
+constexpr int S3_BAR_PEER = 3 * S3_MAX_NA + 4 + 2 + 2 * S3_MAX_NS;      // CTA pair: peerA[MAX_NA], peerW, peerB[MAX_NS] (leader's copies)
+constexpr int S3_NBARS = S3_BAR_PEER + S3_MAX_NA + 1 + S3_MAX_NS;
 constexpr int S3_MAX_E = 8;    // epilogue plan entries (N blocks x sub-blocks)
 constexpr int S3_MAX_O = 8;    // destination tensor maps
 constexpr int S3_MAX_OL = 16;  // (entry, destination) pairs
@@ -90,6 +91,7 @@ struct S3Params {
   int tma_epi, stg2_off;
   int all_full_chunks;  // every source has C % 32 == 0 (no ragged chunk)
   int all_s16;          // every source is in the S16 format: the converter warps have nothing to do
+  int pair;             // CTA-pair kernel (DEMFI_CONV_TC16P)
   float comp;
   int diag;
   long long* dbg;
@@ -209,6 +211,46 @@ __device__ __forceinline__ void umma_f16_ss2(uint32_t d_tmem, uint32_t a_lo, uin
       "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
       ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accum)
       : "memory");
+}
+// ---- CTA pair (cta_group::2): one tcgen05.mma covers M = 256 = the 128-pixel tiles of BOTH CTAs of a cluster; every CTA
+// supplies its own A rows and HALF of the B rows from the same shared-memory offsets; issued by the leader CTA only.
+__device__ __forceinline__ void umma_f16_ss2_pair(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                  uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// completion of all earlier MMAs -> the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// Arrive on the barrier at the same offset in CTA `rank` of the cluster.  Default semantics (release at CTA scope), as the
+// CUTLASS 2-SM kernels do: what is handed over is operand data written by TMA and tensor-memory reads ordered by tcgen05
+// fences, not generic-proxy stores.  (.release.cluster compiles to MEMBAR.ALL.GPU + ERRBAR + CCTL.IVALL around the arrive
+// and .acquire.cluster polling to an L1 invalidate per wait: ncu showed 10 % of all warp samples in those, and the hand-over
+// of an accumulator from the peer's epilogue to the leader's issuer took thousands of cycles.)
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(bar), "r"(rank));
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
+// wait for arrivals from the peer CTA: the ordinary CTA-scope wait (see mbar_arrive_remote)
+__device__ __forceinline__ void mbar_wait_cluster_nocall(uint32_t bar, uint32_t parity) { mbar_wait_nocall(bar, parity); }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -332,16 +374,24 @@ using namespace s3;
 
 // One unit of issue = U consecutive taps (a kernel row; a kernel column for Nx1 kernels; one tap for U = 1), straight-line.
 // a / b: low descriptor words of the unit's first tap; ustep / bstep: their steps from tap to tap.
-template <int U, bool K2>
+// PAIR: cta_group::2 MMAs (M = 256 over the CTA pair; the corrections have their own accumulator columns, see the kernel).
+template <int U, bool K2, bool PAIR>
 __device__ __forceinline__ void s3_issue_unit(uint32_t d_main, uint32_t d_corr, uint32_t a, uint32_t a_hi, uint32_t ustep, uint32_t b,
                                               uint32_t b_hi, uint32_t bstep, uint32_t idesc_2n, uint32_t idesc_n, uint32_t accum) {
 #pragma unroll
   for (int t = 0; t < U; ++t) {
     const uint32_t at = a + (uint32_t)t * ustep, bt = b + (uint32_t)t * bstep;
-    umma_f16_ss2(d_main, at, a_hi, bt, b_hi, idesc_2n, t == 0 ? accum : 1u);  // Ah x [Bh;Bl]  k 0..15
-    if (K2) umma_f16_ss2(d_main, at + 2u, a_hi, bt + 2u, b_hi, idesc_2n, 1u);  //               k 16..31
-    umma_f16_ss2(d_corr, at + 4u, a_hi, bt, b_hi, idesc_n, 1u);               // Al x Bh
-    if (K2) umma_f16_ss2(d_corr, at + 6u, a_hi, bt + 2u, b_hi, idesc_n, 1u);
+    if (PAIR) {
+      umma_f16_ss2_pair(d_main, at, a_hi, bt, b_hi, idesc_2n, t == 0 ? accum : 1u);
+      if (K2) umma_f16_ss2_pair(d_main, at + 2u, a_hi, bt + 2u, b_hi, idesc_2n, 1u);
+      umma_f16_ss2_pair(d_corr, at + 4u, a_hi, bt, b_hi, idesc_n, t == 0 ? accum : 1u);  // own columns: first MMA of a segment overwrites
+      if (K2) umma_f16_ss2_pair(d_corr, at + 6u, a_hi, bt + 2u, b_hi, idesc_n, 1u);
+    } else {
+      umma_f16_ss2(d_main, at, a_hi, bt, b_hi, idesc_2n, t == 0 ? accum : 1u);  // Ah x [Bh;Bl]  k 0..15
+      if (K2) umma_f16_ss2(d_main, at + 2u, a_hi, bt + 2u, b_hi, idesc_2n, 1u);  //               k 16..31
+      umma_f16_ss2(d_corr, at + 4u, a_hi, bt, b_hi, idesc_n, 1u);               // Al x Bh
+      if (K2) umma_f16_ss2(d_corr, at + 6u, a_hi, bt + 2u, b_hi, idesc_n, 1u);
+    }
   }
 }
 
@@ -353,14 +403,28 @@ __device__ __forceinline__ void mbar_wait_i(uint32_t bar, uint32_t parity, bool 
   mbar_wait_nocall(bar, parity);
   acc += clock64() - t;
 }
+template <bool DBG>
+__device__ __forceinline__ void mbar_wait_ic(uint32_t bar, uint32_t parity, long long& acc) {  // arrivals from the peer CTA
+  if (!DBG) { mbar_wait_cluster_nocall(bar, parity); return; }
+  const long long t = clock64();
+  mbar_wait_cluster_nocall(bar, parity);
+  acc += clock64() - t;
+}
 
 // The persistent issue loop of one CTA (single thread).  Units are numbered through the tiles of the CTA; segment (accumulator
 // hand-over), weight-ring group and chunk boundaries all fall on unit boundaries (s3_plan).  Barrier layout as in the kernel.
 // Written for ptxas' uniform datapath: no calls, no min / max (vector-only instructions), counters that count down to a
 // reload value chosen by a select -- the SASS of the loop is UTCHMMA / UTCBAR / U* instructions plus the barrier waits.
-template <int U, bool DBG>
+//
+// MODE 0: one CTA.  MODE 1: leader of a CTA pair -- issues cta_group::2 MMAs for both CTAs, so besides its own barriers it
+// waits for the peer's operands (peerA / peerB / peerW, forwarded by the peer's shadow thread) and for both CTAs' epilogues
+// (the leader's tempty counts the warps of both); its commits are multicast to the barriers of both CTAs.  MODE 2: the
+// shadow -- the same thread of the OTHER CTA walks the same sequence of boundaries, issues nothing, and wherever the leader
+// would wait for an operand it waits for the LOCAL copy of that barrier and arrives on the leader's peer barrier.
+template <int U, bool DBG, int MODE>
 __device__ __forceinline__ void s3_issue(const S3Params& P, uint32_t smem_base, uint32_t tmem_base, uint32_t bars, long long& w_tempty,
-                                         long long& w_ready) {
+                                         long long& w_ready, long long& w_peer) {
+  constexpr bool PAIR = MODE != 0, LEAD = MODE == 1, SHADOW = MODE == 2;
   const demfi_conv_t& c = P.c;
   auto bar_rawfull = [&](uint32_t a) { return bars + 8u * a; };
   auto bar_cvfull = [&](uint32_t a) { return bars + 8u * ((uint32_t)S3_MAX_NA + a); };
@@ -370,9 +434,12 @@ __device__ __forceinline__ void s3_issue(const S3Params& P, uint32_t smem_base, 
   const uint32_t bar_wfull = bars + 8u * (uint32_t)(3 * S3_MAX_NA + 4);
   auto bar_bfull = [&](uint32_t sl) { return bars + 8u * ((uint32_t)(3 * S3_MAX_NA + 6) + sl); };
   auto bar_bfree = [&](uint32_t sl) { return bars + 8u * ((uint32_t)(3 * S3_MAX_NA + 6 + S3_MAX_NS) + sl); };
-  const bool bare = (P.diag & 1024) != 0;
+  auto bar_peerA = [&](uint32_t a) { return bars + 8u * ((uint32_t)S3_BAR_PEER + a); };
+  const uint32_t bar_peerW = bars + 8u * (uint32_t)(S3_BAR_PEER + S3_MAX_NA);
+  auto bar_peerB = [&](uint32_t sl) { return bars + 8u * ((uint32_t)(S3_BAR_PEER + S3_MAX_NA + 1) + sl); };
+  const bool bare = !PAIR && (P.diag & 1024) != 0;
   const uint32_t NA = (uint32_t)P.na, NS = (uint32_t)P.ns;
-  const uint32_t idesc0 = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(S3_BM >> 4) << 24);  // D=f32, A=B=f16, K-major, M=128
+  const uint32_t idesc0 = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)((PAIR ? 2 * S3_BM : S3_BM) >> 4) << 24);  // D=f32, A=B=f16, K-major
   const uint32_t a_hi = (uint32_t)(make_desc_sw128(0u, (uint32_t)P.hw * 128u) >> 32);
   const uint32_t b_hi = (uint32_t)(make_desc_sw64(0u) >> 32);
   const uint32_t a_lo0 = ((smem_base >> 4) & 0x3FFFu) | (1u << 16);
@@ -384,7 +451,11 @@ __device__ __forceinline__ void s3_issue(const S3Params& P, uint32_t smem_base, 
   const bool resident = P.resident != 0;
   const int upc = P.taps / U;                       // units per chunk
   const int chunks_per_tile = P.stages_per_tile / P.taps;
-  if ((int)blockIdx.x >= P.ntiles) return;
+  // tiles of this CTA (MODE 0) / tile PAIRS of this cluster (the two CTAs take tiles 2q and 2q + 1)
+  const int first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int count = PAIR ? (P.ntiles + 1) >> 1 : P.ntiles;
+  if (first >= count) return;
 
   uint32_t slot = 0, sphase = 0, acc = 0, acc_phase = 0, abuf = 0, aphase = 0;
   // An activation chunk is ready: straight from TMA when EVERY source is S16 (the converter warps are idle), else after the
@@ -394,12 +465,33 @@ __device__ __forceinline__ void s3_issue(const S3Params& P, uint32_t smem_base, 
   const bool all_s16 = P.all_s16 != 0;
   auto wait_chunk = [&](uint32_t buf, uint32_t phase) {
     mbar_wait_i<DBG>(all_s16 ? bar_rawfull(buf) : bar_cvfull(buf), phase, bare, w_ready);
+    if (LEAD) mbar_wait_ic<DBG>(bar_peerA(buf), phase, w_peer);
+    if (SHADOW) mbar_arrive_remote(bar_peerA(buf), 0u);
   };
-  if (resident && !bare) mbar_wait_nocall(bar_wfull, 0);
+  auto wait_group = [&](uint32_t sl, uint32_t phase) {
+    mbar_wait_i<DBG>(bar_bfull(sl), phase, bare, w_ready);
+    if (LEAD) mbar_wait_ic<DBG>(bar_peerB(sl), phase, w_peer);
+    if (SHADOW) mbar_arrive_remote(bar_peerB(sl), 0u);
+  };
+  auto wait_acc = [&](uint32_t a_, uint32_t phase) {  // both CTAs' epilogue warps arrive on the leader's barrier
+    if (SHADOW) return;
+    if (LEAD) mbar_wait_ic<DBG>(bar_tempty(a_), phase, w_tempty);
+    else mbar_wait_i<DBG>(bar_tempty(a_), phase, bare, w_tempty);
+  };
+  auto commit = [&](uint32_t bar) {
+    if (SHADOW || bare) return;
+    if (LEAD) umma_commit_pair(bar);
+    else umma_commit(bar);
+  };
+  if (resident && !bare) {
+    mbar_wait_nocall(bar_wfull, 0);
+    if (LEAD) mbar_wait_cluster_nocall(bar_peerW, 0);
+    if (SHADOW) mbar_arrive_remote(bar_peerW, 0u);
+  }
   // the first unit's waits
   wait_chunk(0u, 0u);
-  mbar_wait_i<DBG>(bar_tempty(acc), acc_phase ^ 1u, bare, w_tempty);
-  if (!resident) mbar_wait_i<DBG>(bar_bfull(slot), sphase, bare, w_ready);
+  wait_acc(acc, acc_phase ^ 1u);
+  if (!resident) wait_group(slot, sphase);
   tc_fence_after();
 
   // Structure (measured in tools/probe_s3*: the same MMAs cost 292 clk per stage with boundary checks after every unit and
@@ -407,13 +499,14 @@ __device__ __forceinline__ void s3_issue(const S3Params& P, uint32_t smem_base, 
   // nothing but the units and two adds; the boundaries -- chunk (activation buffer hand-over), accumulation segment
   // (accumulator hand-over), weight-ring group -- are handled between runs: commits, bookkeeping, then the waits the next run
   // needs.  With resident weights and one segment per chunk (the 64 -> 64 3x3 ResBlock convolutions) a run is a whole chunk.
-  for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
-    const bool last_tile = tile + (int)gridDim.x >= P.ntiles;
-    const int nb = tile % P.n_blocks;
+  for (int tile = first; tile < count; tile += stride) {
+    const bool last_tile = tile + stride >= count;
+    const int nb = PAIR ? 0 : tile % P.n_blocks;
     const int N = nb == P.n_blocks - 1 ? c.cout_pad - nb * P.nb_max : P.nb_max;
     const uint32_t idesc_n = idesc0 | ((uint32_t)(N >> 3) << 17);
     const uint32_t idesc_2n = idesc0 | ((uint32_t)((2 * N) >> 3) << 17);
-    const uint32_t bstep = (uint32_t)N << 3;  // one stage = 2N rows x 64 bytes, in 16-byte units
+    // one stage of weights in THIS CTA's shared memory, in 16-byte units: 2N rows x 64 bytes; a CTA of a pair holds half
+    const uint32_t bstep = PAIR ? (uint32_t)N << 2 : (uint32_t)N << 3;
     const uint32_t bunit = bstep * (uint32_t)U;
     // countdowns (in units): to the end of the chunk / the accumulation segment / the weight-ring group
     int chunk_left = upc, chunks_left = chunks_per_tile;
@@ -431,25 +524,28 @@ __device__ __forceinline__ void s3_issue(const S3Params& P, uint32_t smem_base, 
       int run = chunk_left;
       if (seg_left < run) run = seg_left;
       if (grp_left < run) run = grp_left;
-      const uint32_t d_corr = d_main + (uint32_t)N;
+      // corrections: accumulated onto the Ah x Bl half of the main tile (one CTA); own columns after the main tile (pair)
+      const uint32_t d_corr = d_main + (PAIR ? 2u * (uint32_t)N : (uint32_t)N);
       // ---- the run: MMAs and two adds per unit ----
-      if (k2) {
+      if (!SHADOW) {
+        if (k2) {
 #pragma unroll 1
-        for (int r = 0; r < run; ++r) {
-          s3_issue_unit<U, true>(d_main, d_corr, a, a_hi, ustep, b, b_hi, bstep, idesc_2n, idesc_n, accum);
-          accum = 1u;
-          b += bunit;
-          if (U == 1) { a += 8u; if (++kx == KW) { kx = 0; a += rstep - ((uint32_t)KW << 3); } }
-          else a += rstep;
-        }
-      } else {
+          for (int r = 0; r < run; ++r) {
+            s3_issue_unit<U, true, PAIR>(d_main, d_corr, a, a_hi, ustep, b, b_hi, bstep, idesc_2n, idesc_n, accum);
+            accum = 1u;
+            b += bunit;
+            if (U == 1) { a += 8u; if (++kx == KW) { kx = 0; a += rstep - ((uint32_t)KW << 3); } }
+            else a += rstep;
+          }
+        } else {
 #pragma unroll 1
-        for (int r = 0; r < run; ++r) {
-          s3_issue_unit<U, false>(d_main, d_corr, a, a_hi, ustep, b, b_hi, bstep, idesc_2n, idesc_n, accum);
-          accum = 1u;
-          b += bunit;
-          if (U == 1) { a += 8u; if (++kx == KW) { kx = 0; a += rstep - ((uint32_t)KW << 3); } }
-          else a += rstep;
+          for (int r = 0; r < run; ++r) {
+            s3_issue_unit<U, false, PAIR>(d_main, d_corr, a, a_hi, ustep, b, b_hi, bstep, idesc_2n, idesc_n, accum);
+            accum = 1u;
+            b += bunit;
+            if (U == 1) { a += 8u; if (++kx == KW) { kx = 0; a += rstep - ((uint32_t)KW << 3); } }
+            else a += rstep;
+          }
         }
       }
       // ---- boundaries: commits, bookkeeping, then the waits the next run needs.  (Waiting earlier -- before the last unit
@@ -458,14 +554,14 @@ __device__ __forceinline__ void s3_issue(const S3Params& P, uint32_t smem_base, 
       const bool end_chunk = chunk_left == 0, end_seg = seg_left == 0, end_group = grp_left == 0;
       const bool more = !(end_chunk && chunks_left == 1 && last_tile);  // another unit follows in this CTA
       if (end_group) {
-        if (!bare) umma_commit(bar_bfree(slot));
+        commit(bar_bfree(slot));
         if (++slot == NS) { slot = 0; sphase ^= 1u; }
         if (--grps_left == 0) grps_left = P.ngrp;  // (next tile)
         grp_left = grps_left == 1 ? P.grp_last : P.grp_units;
         b = b_lo0 + gstep * slot;
       }
       if (end_seg) {
-        if (!bare) umma_commit(bar_tfull(acc));
+        commit(bar_tfull(acc));
         acc ^= 1u;
         if (acc == 0) acc_phase ^= 1u;
         if (--segs_left == 0) segs_left = P.nseg;  // (next tile)
@@ -474,7 +570,7 @@ __device__ __forceinline__ void s3_issue(const S3Params& P, uint32_t smem_base, 
         accum = 0u;
       }
       if (end_chunk) {
-        if (!bare) umma_commit(bar_aempty(abuf));
+        commit(bar_aempty(abuf));
         if (++abuf == NA) { abuf = 0; aphase ^= 1u; }
         --chunks_left;
         chunk_left = upc;
@@ -486,8 +582,8 @@ __device__ __forceinline__ void s3_issue(const S3Params& P, uint32_t smem_base, 
       }
       if (more) {
         if (end_chunk) wait_chunk(abuf, aphase);
-        if (end_seg) mbar_wait_i<DBG>(bar_tempty(acc), acc_phase ^ 1u, bare, w_tempty);
-        if (end_group) mbar_wait_i<DBG>(bar_bfull(slot), sphase, bare, w_ready);
+        if (end_seg) wait_acc(acc, acc_phase ^ 1u);
+        if (end_group) wait_group(slot, sphase);
         tc_fence_after();
       }
     }
@@ -496,7 +592,11 @@ __device__ __forceinline__ void s3_issue(const S3Params& P, uint32_t smem_base, 
 
 // DBG: per-role cycle counters (tc_diag & 128).  A template parameter, not a run-time flag: the timed variants of every
 // wait would otherwise sit between the hot instructions of all roles (instruction-cache footprint).
-template <int NMAX, bool DBG, int U>
+// PAIR: the CTAs of a 2-CTA cluster work on two adjacent pixel tiles with ONE stream of cta_group::2 MMAs (M = 256) issued by
+// the leader; each CTA holds half of the weight rows, so the filter bank of a 64 -> 64 3x3 layer takes 72 KB instead of 144 KB
+// (room for four halo buffers instead of two), the B-operand reads per SM halve (the N = 64 MMA pair becomes bound by the
+// tensor pipe, 192 clk per k-step pair, instead of by shared-memory reads, 224) and a ring streams half the bytes from L2.
+template <int NMAX, bool DBG, int U, bool PAIR>
 __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_constant__ S3Params P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -514,8 +614,15 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
   const uint32_t bar_resfull = bars + 8u * (uint32_t)(3 * S3_MAX_NA + 5);
   auto bar_bfull = [&](int s) { return bars + 8u * (uint32_t)(3 * S3_MAX_NA + 6 + s); };
   auto bar_bfree = [&](int s) { return bars + 8u * (uint32_t)(3 * S3_MAX_NA + 6 + S3_MAX_NS + s); };
+  auto bar_peer = [&](int i) { return bars + 8u * (uint32_t)(S3_BAR_PEER + i); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (size_t)P.bar_off + 8 * S3_NBARS);
   auto n_of = [&](int nb) { return min(P.nb_max, c.cout_pad - nb * P.nb_max); };
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  // this CTA's tile sequence: tile0, tile0 + tstep, ... < tend.  A pair takes tiles (2q, 2q + 1); for an odd tile count the
+  // last tile of rank 1 lies one past the end: its loads are out-of-range boxes (zero fill), its stores are skipped.
+  const int tile0 = PAIR ? 2 * (int)(blockIdx.x >> 1) + (int)rank : (int)blockIdx.x;
+  const int tstep = PAIR ? (int)(gridDim.x & ~1u) : (int)gridDim.x;
+  const int tend = PAIR ? ((P.ntiles + 1) & ~1) : P.ntiles;
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -530,8 +637,10 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull(a), 1);
-      mbar_init(bar_tempty(a), S3_EPI_WARPS);
+      mbar_init(bar_tempty(a), PAIR ? 2 * S3_EPI_WARPS : S3_EPI_WARPS);  // pair: the leader's copy counts both CTAs' warps
     }
+    if (PAIR)
+      for (int i = 0; i < S3_MAX_NA + 1 + S3_MAX_NS; ++i) mbar_init(bar_peer(i), 1);
     mbar_init(bar_wfull, 1);
     mbar_init(bar_resfull, 1);
     for (int s = 0; s < S3_MAX_NS; ++s) {
@@ -541,8 +650,13 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == S3_CV_WARPS + S3_EPI_WARPS) {  // the producer warp owns the tensor-memory allocation (the MMA warp leaves early)
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   if (P.diag & 1024) {  // diagnostics (bare issue loop): operands = ordinary fp16 values (operand VALUES change the MMA timing)
     for (int i = threadIdx.x; i < P.stg_off / 4; i += S3_THREADS) {
@@ -553,7 +667,8 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
     fence_async_smem();
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them from here
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);  // warp-uniform for ptxas (uniform registers)
   // Programmatic dependent launch: let the next kernel of the stream start its own prologue (barrier init, TMEM allocation,
@@ -574,15 +689,17 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
     // straight-line) is UTCHMMA + uniform-datapath adds only. =====
     if (elect_one()) {
       const long long t_begin = dbg ? clock64() : 0;
-      long long w_tempty = 0, w_ready = 0;
-      s3_issue<U, DBG>(P, smem_base, tmem_base, bars, w_tempty, w_ready);
+      long long w_tempty = 0, w_ready = 0, w_peer = 0;
+      if (!PAIR) s3_issue<U, DBG, 0>(P, smem_base, tmem_base, bars, w_tempty, w_ready, w_peer);
+      else if (rank == 0) s3_issue<U, DBG, 1>(P, smem_base, tmem_base, bars, w_tempty, w_ready, w_peer);
+      else s3_issue<U, DBG, 2>(P, smem_base, tmem_base, bars, w_tempty, w_ready, w_peer);
       if (P.diag & 1024) {  // bare issue loop: everything has completed when this commit arrives
         umma_commit(bar_resfull);
         mbar_wait_nocall(bar_resfull, 0);
       }
       if (dbg) {
         long long* d = P.dbg + (size_t)blockIdx.x * 16;
-        d[12] = clock64() - t_begin; d[13] = w_tempty; d[14] = w_ready;
+        d[12] = clock64() - t_begin; d[13] = w_tempty; d[14] = w_ready; d[15] = w_peer;
       }
     }
     return;  // no barrier below involves this warp: the remaining 15 warps meet at named barrier 1
@@ -596,7 +713,7 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
     const long long t_begin = dbg ? clock64() : 0;
     int abuf = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < P.ntiles && !P.all_s16; tile += gridDim.x) {  // (every source S16: nothing to do here)
+    for (int tile = tile0; tile < tend && !P.all_s16; tile += tstep) {  // (every source S16: nothing to do here)
       for (int si = 0; si < c.nsrc; ++si) {
         const bool s16 = c.src[si].fmt == DEMFI_FMT_S16;  // already fp16 hi | lo rows: passed on as it landed
         for (int c0 = 0; c0 < c.src[si].C; c0 += S3_KC) {
@@ -632,7 +749,7 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
         }
       }
     }
-    if (dbg && threadIdx.x == 0) {
+    if (dbg && threadIdx.x == 0 && !P.all_s16) {
       long long* d = P.dbg + (size_t)blockIdx.x * 16;
       d[0] = clock64() - t_begin; d[1] = w_raw; d[7] = w_cv;
     }
@@ -646,7 +763,7 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
     constexpr int HMAX = (NMAX / 2 + 15) / 16 * 16;
     int acc = 0;
     uint32_t acc_phase = 0, res_phase = 0;
-    long long w_tfull = 0, w_store = 0;
+    long long w_tfull = 0, w_store = 0, w_ld = 0, w_arr = 0, w_s1 = 0, w_s2 = 0, w_s3 = 0, w_top = 0;
     const long long t_begin = dbg ? clock64() : 0;
     const uint32_t stg = smem_base + (uint32_t)P.stg_off;
     bool store_pending = false;
@@ -661,7 +778,8 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
     asm volatile("griddepcontrol.wait;" ::: "memory");  // operand tiles and destinations belong to earlier kernels
     const bool per_box = P.nsb > 1;  // entries are 32-channel boxes (else one entry per N block)
     const uint32_t emask = per_box ? 0xffffffffu : 0u;
-    for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+    for (int tile = tile0; tile < tend; tile += tstep) {
+      const bool dummy = PAIR && tile >= P.ntiles;  // (odd tile count: the pair's second tile does not exist)
       int t = tile;
       const int nb = t % P.n_blocks;
       t /= P.n_blocks;
@@ -678,8 +796,9 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
       const int e0 = nb * P.nsb;                                  // first entry of this N block
       const int ne = per_box ? nboxes : 1;                        // entries of this N block
       int nres_any = 0;
-      if (P.tma_epi)
+      if (P.tma_epi && !dummy)
         for (int sb = 0; sb < ne; ++sb) nres_any += P.e_nres[e0 + sb];
+      const long long t_top = dbg ? clock64() : 0;
       if (P.tma_epi) {
         // the staging buffers are free once the previous tile's stores have read them; then fetch the operand tiles
         if (e_tid == 0) {
@@ -703,13 +822,20 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
         }
         store_pending = true;
       }
+      if (dbg) w_top += clock64() - t_top;
       float sum[HMAX];
       bool first = true;
       for (int done = 0; done < P.stages_per_tile; done += P.flush) {
         const float gain = 1.0f + P.comp * (float)(2 * min(P.flush, P.stages_per_tile - done));
         mbar_wait_t(bar_tfull(acc), acc_phase, dbg, w_tfull);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * P.acc_stride) + (uint32_t)cbeg;
+        // accumulator columns of this thread's channels: [main | corrections] (one CTA); a pair's main tile interleaves the
+        // halves held by the two CTAs -- [Ah Bh | Ah Bl] of channels 0..N/2-1, then of N/2..N-1 -- followed by Al Bh for all N
+        const uint32_t tbuf = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * P.acc_stride);
+        const uint32_t taddr = tbuf + (uint32_t)(PAIR ? grp * N : cbeg);
+        const uint32_t tcorr = tbuf + (uint32_t)(PAIR ? grp * N + (N >> 1) : N + cbeg);
+        const uint32_t tcorr2 = tbuf + (uint32_t)(2 * N + cbeg);
+        const long long t_ld0 = dbg ? clock64() : 0;
         // 32 columns at a time (the wide N = 128 blocks hold 64 columns per thread: the partial sums stay in registers, the
         // drained values pass through a 32-register window)
 #pragma unroll
@@ -729,15 +855,29 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
           }
 #pragma unroll
           for (int col = 0; col < RW; col += 16)
-            if (c32 + col < HMAX && c32 + col < cnum && !(P.diag & 512)) tmem_ld16_nowait(taddr + (uint32_t)(N + c32 + col), r + col);
+            if (c32 + col < HMAX && c32 + col < cnum && !(P.diag & 512)) tmem_ld16_nowait(tcorr + (uint32_t)(c32 + col), r + col);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < RW; ++j)
             if (c32 + j < HMAX) sum[c32 + j] = fmaf(__uint_as_float(r[j]), 1.0f / S3_LO_SCALE, sum[c32 + j]);
+          if (PAIR) {
+#pragma unroll
+            for (int col = 0; col < RW; col += 16)
+              if (c32 + col < HMAX && c32 + col < cnum) tmem_ld16_nowait(tcorr2 + (uint32_t)(c32 + col), r + col);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < RW; ++j)
+              if (c32 + j < HMAX) sum[c32 + j] = fmaf(__uint_as_float(r[j]), 1.0f / S3_LO_SCALE, sum[c32 + j]);
+          }
         }
+        const long long t_ld1 = dbg ? clock64() : 0;
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_tempty(acc));
+        if (lane == 0) {
+          if (PAIR && rank != 0) mbar_arrive_remote(bar_tempty(acc), 0u);
+          else mbar_arrive(bar_tempty(acc));
+        }
+        if (dbg) { w_ld += t_ld1 - t_ld0; w_arr += clock64() - t_ld1; }
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         first = false;
       }
@@ -750,6 +890,7 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
         } else {
           asm volatile("bar.sync 2, %0;" ::"n"(S3_EPI_THREADS) : "memory");  // staging buffer released (thread 0 waited)
         }
+        if (dbg) w_s1 += clock64() - t_store;  // waited for the staging tile / the operand tiles
         const uint32_t row = stg + (uint32_t)m * 128u;
         const uint32_t sw = (uint32_t)m & 7u;
         const float4 zero4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -806,9 +947,12 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
             }
           }
         }
+        const long long t_s2 = dbg ? clock64() : 0;
         fence_async_smem();
         asm volatile("bar.sync 3, %0;" ::"n"(S3_EPI_THREADS) : "memory");
-        if (e_tid == 0 && !(P.diag & (1 | 32))) {
+        if (dbg) w_s2 += clock64() - t_s2;
+        const long long t_s3 = dbg ? clock64() : 0;
+        if (e_tid == 0 && !dummy && !(P.diag & (1 | 32))) {
           for (int sb = 0; sb < ne; ++sb) {
             const int e = e0 + sb;
             if (P.e_seg[e] < 0) continue;
@@ -819,6 +963,7 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
           }
           bulk_commit();
         }
+        if (dbg) w_s3 += clock64() - t_s3;
       } else if (valid && !(P.diag & 1)) {
         const int ch_lo = n0 + cbeg, ch_hi = ch_lo + cnum;
 #pragma unroll 1
@@ -840,7 +985,8 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
     if (P.tma_epi && e_tid == 0 && store_pending) bulk_wait0();  // stores complete before the CTA exits
     if (dbg && e_tid == 0) {
       long long* d = P.dbg + (size_t)blockIdx.x * 16;
-      d[4] = clock64() - t_begin; d[5] = w_tfull; d[6] = w_store;
+      d[4] = clock64() - t_begin; d[5] = w_tfull; d[6] = w_store; d[10] = w_ld; d[11] = w_arr; d[2] = w_s1; d[3] = w_s2;
+      if (P.all_s16) { d[1] = w_top; d[7] = w_s3; }
     }
   } else if (warp == S3_CV_WARPS + S3_EPI_WARPS) {
     // ===== TMA producer (one thread): halo tiles and, unless resident, the weight ring.  The two sequences are
@@ -848,28 +994,34 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
     if (elect_one()) {
       const long long t_begin = dbg ? clock64() : 0;
       const uint32_t a_tx = (uint32_t)(P.halo_px * 128);
+      // packed weights of a pair: [rank][chunk][tap][N rows = Bh half ; Bl half][32 fp16] -- this CTA streams its own half
+      const size_t w_rank_off = PAIR ? (size_t)rank * (size_t)P.stages_per_tile * (size_t)P.b_bytes : 0;
       if (P.resident) {
-        const uint32_t b_tx = (uint32_t)n_of(0) * 128u;
+        const uint32_t b_tx = PAIR ? (uint32_t)P.b_bytes : (uint32_t)n_of(0) * 128u;
         mbar_arrive_expect_tx(bar_wfull, b_tx * (uint32_t)P.stages_per_tile);
-        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(c.wpack);
+        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(c.wpack) + w_rank_off;
         for (int s = 0; s < P.stages_per_tile; ++s)
           bulk_load(b_base + (uint32_t)(s * P.b_bytes), wsrc + (size_t)s * b_tx, b_tx, bar_wfull);
       }
       asm volatile("griddepcontrol.wait;" ::: "memory");  // activations are the previous kernels' outputs
       // A sequence state
-      int a_tile = blockIdx.x, a_src = 0, a_c0 = 0, abuf = 0;
+      int a_tile = tile0, a_src = 0, a_c0 = 0, abuf = 0;
       uint32_t aphase = 0;
       // B sequence state
-      int b_tile = P.resident ? P.ntiles : (int)blockIdx.x, b_stage = 0, slot = 0;
+      int b_tile = P.resident ? tend : tile0, b_stage = 0, slot = 0;
       uint32_t sphase = 0;
-      while (a_tile < P.ntiles || b_tile < P.ntiles) {
-        if (a_tile < P.ntiles && mbar_test_wait(bar_aempty(abuf), aphase ^ 1u)) {
+      long long w_idle = 0, t_idle = dbg ? clock64() : 0;
+      while (a_tile < tend || b_tile < tend) {
+        if (dbg) t_idle = clock64();
+        bool issued = false;
+        if (a_tile < tend && mbar_test_wait(bar_aempty(abuf), aphase ^ 1u)) {
+          issued = true;
           int t = a_tile / P.n_blocks;
           const int tx0 = (t % P.tiles_x) * S3_TW - c.pad_w;
           t /= P.tiles_x;
           const int ty0 = (t % P.tiles_y) * S3_TH - c.pad_h;
           const int n = t / P.tiles_y;
-          if ((P.diag & 256) && a_tile != (int)blockIdx.x) {
+          if ((P.diag & 256) && a_tile != tile0) {
             mbar_arrive(bar_rawfull(abuf));  // diagnostics: no activation traffic after the first tile (stale operands)
           } else {
             mbar_arrive_expect_tx(bar_rawfull(abuf), a_tx);
@@ -879,27 +1031,29 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
           a_c0 += S3_KC;
           if (a_c0 >= c.src[a_src].C) {
             a_c0 = 0;
-            if (++a_src == c.nsrc) { a_src = 0; a_tile += gridDim.x; }
+            if (++a_src == c.nsrc) { a_src = 0; a_tile += tstep; }
           }
         }
-        if (b_tile < P.ntiles && mbar_test_wait(bar_bfree(slot), sphase ^ 1u)) {
-          const int nb = b_tile % P.n_blocks;
-          const uint32_t b_tx = (uint32_t)n_of(nb) * 128u;  // one stage: 2N rows x 64 bytes
+        if (b_tile < tend && mbar_test_wait(bar_bfree(slot), sphase ^ 1u)) {
+          issued = true;
+          const int nb = PAIR ? 0 : b_tile % P.n_blocks;
+          const uint32_t b_tx = PAIR ? (uint32_t)P.b_bytes : (uint32_t)n_of(nb) * 128u;  // one stage: 2N rows x 64 bytes (a pair: N rows per CTA)
           const int len = min(P.gtaps, P.stages_per_tile - b_stage);
           // packed weights: [n block][chunk][tap][2*N_block rows][32 fp16]; full blocks hold nb_max channels.  The stages of a
           // group are consecutive in that order, so the group is one contiguous copy.
-          const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(c.wpack) +
+          const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(c.wpack) + w_rank_off +
                                 (size_t)nb * (size_t)P.stages_per_tile * (size_t)P.nb_max * 128u + (size_t)b_stage * b_tx;
           mbar_arrive_expect_tx(bar_bfull(slot), b_tx * (uint32_t)len);
           bulk_load(b_base + (uint32_t)(slot * P.gtaps * P.b_bytes), wsrc, b_tx * (uint32_t)len, bar_bfull(slot));
           if (++slot == NS) { slot = 0; sphase ^= 1u; }
           b_stage += len;
-          if (b_stage == P.stages_per_tile) { b_stage = 0; b_tile += gridDim.x; }
+          if (b_stage == P.stages_per_tile) { b_stage = 0; b_tile += tstep; }
         }
+        if (dbg && !issued) w_idle += clock64() - t_idle;
       }
       if (dbg) {
         long long* d = P.dbg + (size_t)blockIdx.x * 16;
-        d[8] = clock64() - t_begin;
+        d[8] = clock64() - t_begin; d[9] = w_idle;
       }
     }
   }
@@ -907,9 +1061,13 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
   // the epilogue warps have drained the last accumulator (hence every MMA has completed) when they arrive here
   tc_fence_before();
   asm volatile("bar.sync 1, %0;" ::"n"(S3_THREADS - 32) : "memory");
+  // pair: neither CTA may retire while the other can still arrive on its barriers or its MMAs read this shared memory (the
+  // issuer / shadow threads have exited by themselves; the cluster barrier counts the non-exited threads)
+  if (PAIR) cluster_sync_all();
   if (warp == S3_CV_WARPS + S3_EPI_WARPS) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
   }
 }
 
@@ -919,12 +1077,14 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
 #define S3_TU 0
 #endif
 typedef void (*S3KernelFn)(S3Params);
-#define S3_ROW(N_, D_) {conv_s3_kernel<N_, D_, 1>, conv_s3_kernel<N_, D_, 3>, conv_s3_kernel<N_, D_, 5>, conv_s3_kernel<N_, D_, 7>}
-S3KernelFn s3_dbg_kernel(int nidx, int uidx);
+#define S3_ROW(N_, D_, P_) \
+  {conv_s3_kernel<N_, D_, 1, P_>, conv_s3_kernel<N_, D_, 3, P_>, conv_s3_kernel<N_, D_, 5, P_>, conv_s3_kernel<N_, D_, 7, P_>}
+S3KernelFn s3_dbg_kernel(int nidx, int uidx, int pair);
 #if S3_TU == 1
-S3KernelFn s3_dbg_kernel(int nidx, int uidx) {
-  static const S3KernelFn table[4][4] = {S3_ROW(32, true), S3_ROW(64, true), S3_ROW(96, true), S3_ROW(128, true)};
-  return table[nidx][uidx];
+S3KernelFn s3_dbg_kernel(int nidx, int uidx, int pair) {
+  static const S3KernelFn table[4][4] = {S3_ROW(32, true, false), S3_ROW(64, true, false), S3_ROW(96, true, false), S3_ROW(128, true, false)};
+  static const S3KernelFn ptable[2][4] = {S3_ROW(32, true, true), S3_ROW(64, true, true)};
+  return pair ? ptable[nidx][uidx] : table[nidx][uidx];
 }
 #else
 // ---- host --------------------------------------------------------------------------------
@@ -957,6 +1117,7 @@ static int s3_num_sms() {
 // 97..128 output channels stay ONE block -- an (M 128, N' 256) MMA pair per k-step is bound by the tensor pipe (192 clk for 128
 // channels), two (128, 128) pairs by the operand reads from shared memory (2 x 112 clk) -- and the halo tile is fetched once.
 int s3_nb_max(int kind, int cout_pad) {
+  if (kind == DEMFI_CONV_TC16P) return cout_pad;  // (32 or 64: one block, halved between the CTAs of the pair)
   if (kind == DEMFI_CONV_TC16W && cout_pad > 96 && cout_pad <= 128) return cout_pad;
   return cout_pad <= 96 ? cout_pad : 64;
 }
@@ -1057,8 +1218,48 @@ bool s3_s16_ok(const demfi_conv_t& c) {
   return !any_seg || s3_plan_epilogue(c, nbm, (c.cout_pad + nbm - 1) / nbm, E);
 }
 
+// Packed weights of a CTA pair (DEMFI_CONV_TC16P): [rank][chunk][tap][N rows][32 fp16], 64-byte swizzle as in h3_pack_weights;
+// rank r holds output channels r N/2 .. (r+1) N/2 - 1: rows 0..N/2-1 = fp16(w), rows N/2..N-1 = fp16((w - hi) * 2048).  The
+// main MMA (N' = 2N over the pair) reads all N rows of each CTA, the correction MMA (N' = N) the first N/2 (the hi rows).
+int s3_pack_weights_pair(const float* w, int Co, int Ci, int KH, int KW, const int32_t* in_map, const int32_t* src_C, int nsrc,
+                         const int32_t* out_map, int cout_pad, float* out) {
+  DEMFI_REQUIRE(cout_pad == 32 || cout_pad == 64, "pack_weights: DEMFI_CONV_TC16P needs cout_pad 32 or 64 (got %d)", cout_pad);
+  const int taps = KH * KW, N = cout_pad, Nh = N / 2;
+  int chunks = 0;
+  for (int s_ = 0; s_ < nsrc; ++s_) chunks += (src_C[s_] + S3_KC - 1) / S3_KC;
+  __half* o = reinterpret_cast<__half*>(out);
+  for (int rank = 0; rank < 2; ++rank) {
+    int chunk = 0, kbase = 0;
+    for (int s_ = 0; s_ < nsrc; ++s_) {
+      for (int c0 = 0; c0 < src_C[s_]; c0 += S3_KC, ++chunk) {
+        for (int tap = 0; tap < taps; ++tap) {
+          __half* tile = o + (((size_t)rank * chunks + chunk) * taps + tap) * (size_t)(N * S3_KC);
+          for (int n = 0; n < Nh; ++n)
+            for (int k = 0; k < S3_KC; ++k) {
+              float v = 0.0f;
+              const int cc = c0 + k;
+              if (cc < src_C[s_]) {
+                const int ci = in_map[kbase + cc], co = out_map[rank * Nh + n];
+                if (ci >= 0 && co >= 0) v = w[((size_t)co * Ci + ci) * taps + tap];
+              }
+              DEMFI_REQUIRE(v > -65504.0f && v < 65504.0f, "pack_weights: weight %g outside the fp16 range", (double)v);
+              const __half h = __float2half_rn(v);
+              const __half l = __float2half_rn((v - __half2float(h)) * S3_LO_SCALE);
+              const int rh = n, rl = Nh + n;
+              tile[(size_t)rh * S3_KC + (size_t)((((k >> 3) ^ ((rh >> 1) & 3)) << 3) + (k & 7))] = h;
+              tile[(size_t)rl * S3_KC + (size_t)((((k >> 3) ^ ((rl >> 1) & 3)) << 3) + (k & 7))] = l;
+            }
+        }
+      }
+      kbase += src_C[s_];
+    }
+  }
+  return 0;
+}
+
 bool s3_supports(const demfi_conv_t& c) {
   if (c.stride != 1) return false;
+  if (c.kind == DEMFI_CONV_TC16P && c.cout_pad != 32 && c.cout_pad != 64) return false;
   if (c.cout_pad % 16 != 0 || c.cout_pad < 16 || c.cout_pad > 256) return false;
   for (int s = 0; s < c.nsrc; ++s)
     if (c.src[s].up != 0) return false;
@@ -1066,7 +1267,7 @@ bool s3_supports(const demfi_conv_t& c) {
   if (hw > 256 || hh > 256) return false;
   const int a_bytes = (hw * hh * 128 + 1023) / 1024 * 1024;
   const int nbm = s3_nb_max(c.kind, c.cout_pad);
-  const int b_bytes = 2 * nbm * 64;
+  const int b_bytes = (c.kind == DEMFI_CONV_TC16P ? 1 : 2) * nbm * 64;
   const int stg = ((nbm + 31) / 32) * S3_BOX_BYTES;
   return 2 * a_bytes + (nbm > 96 ? 2 : 4) * b_bytes + stg + 2048 <= S3_SMEM_MAX;
 }
@@ -1111,8 +1312,11 @@ static int s3_plan(const demfi_conv_t& c, S3Params& P, S3EpiPlan& E, int* smem_o
   DEMFI_REQUIRE(nt > 0 && nt * P.n_blocks < (1ll << 31), "conv_s3: bad tile count");
   P.ntiles = (int)nt * P.n_blocks;
   P.a_bytes = (P.halo_px * 128 + 1023) / 1024 * 1024;
-  P.b_bytes = 2 * P.nb_max * 64;
-  P.acc_stride = 2 * P.nb_max;
+  P.pair = c.kind == DEMFI_CONV_TC16P ? 1 : 0;
+  // one weight stage in a CTA's shared memory: [Bh ; Bl] = 2N rows of 64 bytes; a CTA of a pair holds half of the rows
+  P.b_bytes = (P.pair ? 1 : 2) * P.nb_max * 64;
+  // accumulator buffer: [main N | corrections N]; a pair keeps Al x Bh in columns of its own: [main 2N | Al Bh N]
+  P.acc_stride = (P.pair ? 3 : 2) * P.nb_max;
   P.taps = c.KH * c.KW;
   // MMA issue unit: a kernel row (KW > 1), a kernel column (N x 1 kernels) or a single tap; straight-line code exists for 3, 5, 7
   P.unit = c.KW > 1 ? c.KW : c.KH;
@@ -1168,7 +1372,7 @@ static int s3_plan(const demfi_conv_t& c, S3Params& P, S3EpiPlan& E, int* smem_o
     P.ns = 0;
     P.gtaps = P.stages_per_tile;
     P.na = (3 * P.a_bytes + bank + fixed <= S3_SMEM_MAX) ? 3 : 2;
-    const int want = s3_want_buffers(P.taps, chunks);
+    const int want = P.pair ? 5 : s3_want_buffers(P.taps, chunks);  // (a pair's halved filter bank leaves room: deeper prefetch)
     while (P.na < want && (P.na + 1) * P.a_bytes + bank + fixed <= S3_SMEM_MAX) ++P.na;
   } else {
     // ring of `ns` slots, each a group of `gtaps` consecutive stages (target <= 24 KB per slot, >= 3 slots); groups are whole
@@ -1194,7 +1398,7 @@ static int s3_plan(const demfi_conv_t& c, S3Params& P, S3EpiPlan& E, int* smem_o
       else break;
     }
     DEMFI_REQUIRE(fits(P.na, ns, g), "conv_s3: shared-memory plan does not fit");
-    const int want = s3_want_buffers(P.taps, chunks);
+    const int want = P.pair ? 4 : s3_want_buffers(P.taps, chunks);
     while (P.na < want && fits(P.na + 1, ns, g)) ++P.na;
     P.ns = ns;
     P.gtaps = g;
@@ -1251,6 +1455,7 @@ int s3_describe(const demfi_conv_t& c, int32_t* info) {
   info[9] = P.stages_per_tile;
   info[10] = P.nsb;  // epilogue entries per N block (1: the block is one result; else 32-channel boxes planned one by one)
   info[11] = P.nb_max;
+  info[12] = P.pair;
   return 0;
 }
 
@@ -1303,9 +1508,10 @@ int launch_conv_s3(const demfi_conv_t& c, cudaStream_t st) {
   }
   // one kernel per (N block width, issue unit): a single instantiation of the issue loop per kernel keeps its state in
   // uniform registers (a switch over four inlined copies did not)
-  static const S3KernelFn table[4][4] = {S3_ROW(32, false), S3_ROW(64, false), S3_ROW(96, false), S3_ROW(128, false)};
+  static const S3KernelFn table[4][4] = {S3_ROW(32, false, false), S3_ROW(64, false, false), S3_ROW(96, false, false), S3_ROW(128, false, false)};
+  static const S3KernelFn ptable[2][4] = {S3_ROW(32, false, true), S3_ROW(64, false, true)};
   const int nidx = P.nb_max <= 32 ? 0 : P.nb_max <= 64 ? 1 : P.nb_max <= 96 ? 2 : 3;
-  const S3KernelFn fn = P.dbg != nullptr ? s3_dbg_kernel(nidx, P.unit >> 1) : table[nidx][P.unit >> 1];
+  const S3KernelFn fn = P.dbg != nullptr ? s3_dbg_kernel(nidx, P.unit >> 1, P.pair) : P.pair ? ptable[nidx][P.unit >> 1] : table[nidx][P.unit >> 1];
   {
     // cudaFuncSetAttribute applies per device: remember which devices have seen which kernel
     static std::mutex mu;
@@ -1321,17 +1527,26 @@ int launch_conv_s3(const demfi_conv_t& c, cudaStream_t st) {
   }
   int grid = P.ntiles < s3_num_sms() ? P.ntiles : s3_num_sms();
   if (get_option("tc_grid") > 0 && get_option("tc_grid") < grid) grid = get_option("tc_grid");
+  if (P.pair) {  // whole clusters of two CTAs
+    const int pairs = (P.ntiles + 1) / 2;
+    grid = 2 * (pairs < s3_num_sms() / 2 ? pairs : s3_num_sms() / 2);
+    if (get_option("tc_grid") > 1 && (get_option("tc_grid") & ~1) < grid) grid = get_option("tc_grid") & ~1;
+  }
   {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(S3_THREADS);
     cfg.dynamicSmemBytes = (size_t)smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = get_option("tc_pdl") ? 1 : 0;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = 2;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = P.pair ? 2 : 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, fn, P);
     DEMFI_REQUIRE(e == cudaSuccess, "conv_s3 launch failed: %s", cudaGetErrorString(e));
   }

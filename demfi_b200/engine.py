@@ -192,6 +192,15 @@ class Engine:
             return A.CONV_TC if tc_ok else A.CONV_FFMA
         if not tc16_ok:
             return A.CONV_FFMA
+        # CTA pairs (cta_group::2, two pixel tiles per MMA, half of the weight rows per CTA) where they were measured faster
+        # than one CTA per tile (profiles/r2_conv_notes.md): 32 output channels (the activation operand is read once for two
+        # tiles: +10..35 %) and long K loops (>= 20 (chunk, tap) stages per tile: halved weight traffic / shared-memory reads,
+        # +17..20 % on Ch_Reducer, w_gen, the GRU q convolutions).  The 18-stage 64 -> 64 3x3 ResBlock convolutions are bound by
+        # their epilogue in both forms (a tie) and stay on one CTA per tile.
+        if stride == 1 and cout_pad in (32, 64) and os.environ.get("DEMFI_PAIR", "1") != "0":
+            stages = sum((vw.C + 31) // 32 for vw, _ in srcs) * KH * KW
+            if cout_pad == 32 or stages >= 20:
+                return A.CONV_TC16P
         # 97..128 output channels as ONE N block (conv_s3 only: stride 1)
         # (measured at 1280x736, profiles/r2_conv_notes.md: GRU z|r 1.87 ms as one N = 128 block vs 1.64 ms as two N = 64 blocks -- the
         # ring then streams its weights at 42.7 B/clk/SM, the L2 ceiling -- so it is opt-in)
@@ -249,7 +258,7 @@ class Engine:
             assert vw.N == N and (vw.H << up, vw.W << up) == (Hi, Wi), (names, i, vw.N, vw.H, vw.W, up, Hi, Wi)
             d.src[i].ptr, d.src[i].C, d.src[i].ld, d.src[i].up = vw.ptr, vw.C, vw.ld, up
             d.src[i].fmt = vw.fmt
-            assert vw.fmt == A.FMT_F32 or kind in (A.CONV_TC16, A.CONV_TC16W), (names, "S16 source on a kernel that cannot read it")
+            assert vw.fmt == A.FMT_F32 or kind in (A.CONV_TC16, A.CONV_TC16W, A.CONV_TC16P), (names, "S16 source on a kernel that cannot read it")
         for i, sg in enumerate(segs):
             dst: View = sg["dst"]
             s = d.seg[i]
@@ -263,7 +272,7 @@ class Engine:
             if sg.get("res2") is not None:
                 s.res2, s.res2_ld = sg["res2"].ptr, sg["res2"].ld
                 s.fmt |= A.SEG_RES2_S16 if sg["res2"].fmt == A.FMT_S16 else 0
-            assert s.fmt == 0 or kind in (A.CONV_TC16, A.CONV_TC16W), (names, "S16 destination / operand on a kernel that cannot handle it")
+            assert s.fmt == 0 or kind in (A.CONV_TC16, A.CONV_TC16W, A.CONV_TC16P), (names, "S16 destination / operand on a kernel that cannot handle it")
         d.wpack, d.bias = wdev.data_ptr(), bdev.data_ptr()
         self._keep.append(d)
         macs = N * Ho * Wo * Co * Ci * KH * KW

@@ -58,8 +58,11 @@ enum {
   DEMFI_CONV_FFMA = 0, /* CUDA-core fp32 implicit GEMM (exact fp32)                                   */
   DEMFI_CONV_TC = 1,   /* tcgen05 kind::tf32, 3xTF32 split (first-generation tensor-core kernel)       */
   DEMFI_CONV_TC16 = 2, /* tcgen05 kind::f16, 3xFP16 split + halo-tile activation staging; stride 1|2  */
-  DEMFI_CONV_TC16W = 3 /* the same arithmetic on the conv_s3 kernel only (stride 1), with 97..128 output channels kept in
+  DEMFI_CONV_TC16W = 3, /* the same arithmetic on the conv_s3 kernel only (stride 1), with 97..128 output channels kept in
                           ONE N block (an N' = 256 MMA pair per k-step; weights packed for that blocking)              */
+  DEMFI_CONV_TC16P = 4  /* the same arithmetic on CTA PAIRS (2-CTA clusters, tcgen05 cta_group::2, M = 256 = two pixel tiles
+                          per MMA): 32 or 64 output channels, stride 1; each CTA holds half of the weight rows (weights
+                          packed per CTA rank)                                                                          */
 };
 
 /* one input of a (virtually concatenated) convolution */
@@ -92,7 +95,7 @@ typedef struct {
   int32_t KH, KW, stride, pad_h, pad_w;
   int32_t nsrc, nseg;
   int32_t cout_pad;  /* accumulator channels (padded Cout, multiple of 16)             */
-  int32_t kind;      /* DEMFI_CONV_FFMA | DEMFI_CONV_TC | DEMFI_CONV_TC16 | DEMFI_CONV_TC16W */
+  int32_t kind;      /* DEMFI_CONV_FFMA | DEMFI_CONV_TC | DEMFI_CONV_TC16 | _TC16W | _TC16P */
   demfi_src_t src[DEMFI_MAX_SRC];
   demfi_seg_t seg[DEMFI_MAX_SEG];
   const float* wpack; /* device, produced by demfi_pack_weights for the same `kind`    */
@@ -131,7 +134,7 @@ int demfi_conv2d(const demfi_conv_t* conv, void* stream);
  * resident in shared memory, [3] = halo-tile buffers, [4] = weight-ring slots, [5] = (chunk, tap) stages per slot,
  * [6] = N blocks, [7] = dynamic shared memory in bytes, [8] = stages per accumulation segment, [9] = stages per tile,
  * [10] = epilogue entries per N block (1: one result per block; > 1: every 32-channel box has its own activation / operands /
- * format / destinations), [11] = N block width.
+ * format / destinations), [11] = N block width, [12] = 1 for the CTA-pair kernel (DEMFI_CONV_TC16P).
  * Lets a plan be checked for silent fall-backs to slower paths without launching anything. */
 int demfi_conv_describe(const demfi_conv_t* conv, int32_t info[16]);
 

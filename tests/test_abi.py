@@ -164,14 +164,18 @@ def _describe(cout_pad, segs, k=(3, 3), srcC=(64,), stride=1, kind=A.CONV_TC16, 
         if res:
             sg.res, sg.res_ld = 0x9000000, 256
     info = (A.i32 * 16)()
-    A.check(A.lib().demfi_conv_describe(C.byref(d), info), "describe")
+    if A.lib().demfi_conv_describe(C.byref(d), info) != 0:
+        return None
     return list(info)
 
 
 def test_conv_describe_reports_kernel_and_epilogue_plan():
     """host-only planning (no GPU): which kernel, TMA or generic epilogue, resident weights"""
     plain = _describe(64, [(0, 64, A.ACT_RELU, False, 0)])
-    assert plain[0] == 3 and plain[1] == 1 and plain[2] == 1 and plain[9] == 18 and plain[8] == 9  # 64->64 3x3: resident, 2 segments of 9
+    assert plain[0] == 3 and plain[1] == 1 and plain[2] == 1 and plain[9] == 18 and plain[8] == 18  # 64->64 3x3: resident, one segment of 18 stages
+    pair = _describe(64, [(0, 64, A.ACT_RELU, False, A.SEG_DST_S16)], kind=A.CONV_TC16P)
+    assert pair[0] == 3 and pair[2] == 1 and pair[3] >= 4 and pair[12] == 1   # CTA pair: half the filter bank per CTA -> 4+ halo buffers
+    assert _describe(96, [(0, 96, A.ACT_RELU, False, 0)], kind=A.CONV_TC16P, srcC=(48,)) is None   # pairs: 32 or 64 output channels only
     heads = _describe(144, [(0, 64, A.ACT_TANH, True, 0), (64, 64, A.ACT_TANH, True, 0), (128, 8, A.ACT_NONE, True, 0)])
     assert heads[0] == 3 and heads[1] == 1 and heads[6] == 3          # three heads = three N blocks, each alike -> TMA epilogue
     lff = _describe(96, [(0, 96, A.ACT_NONE, True, A.SEG_DST_S16 | A.SEG_RES_S16)] * 2, k=(1, 1), srcC=(224,))

@@ -302,6 +302,75 @@ def test_tc_operand_truncation_probe():
     assert e1 < 2e-5
 
 
+# ---- CTA pairs (DEMFI_CONV_TC16P): cta_group::2 MMAs over two pixel tiles, each CTA holding half of the weight rows
+PAIR_CASES = {
+    # name: (n, h, w, srcC list, co, k, src S16, dst S16, residual, act)
+    "resblock_s16_res": (2, 40, 56, [64], 64, (3, 3), True, True, True, A.ACT_NONE),
+    "resblock_f32_relu": (1, 24, 40, [64], 64, (3, 3), False, False, False, A.ACT_RELU),
+    "odd_tile_count": (1, 48, 24, [64], 64, (3, 3), True, True, False, A.ACT_RELU),      # 3 x 3 = 9 tiles: the last pair is half empty
+    "single_tile": (1, 16, 8, [64], 64, (3, 3), True, False, False, A.ACT_RELU),
+    "many_tiles": (2, 156, 312, [64], 64, (3, 3), True, True, True, A.ACT_RELU),         # 800 tiles > 74 pairs, ragged edges
+    "n32_dense": (1, 40, 48, [96, 32], 32, (3, 3), True, True, False, A.ACT_RELU),
+    "ring_7x7_three_sources": (1, 32, 40, [64, 64, 64], 64, (7, 7), False, True, False, A.ACT_TANH),
+    "mixed_formats_1x5": (1, 24, 40, [64, 64], 64, (1, 5), None, True, False, A.ACT_RELU),   # first source S16, second fp32
+    "ragged_cin_5": (1, 24, 40, [8], 32, (7, 7), False, True, False, A.ACT_RELU),
+    "one_by_one": (3, 16, 32, [64], 64, (1, 1), True, False, False, A.ACT_NONE),
+}
+
+
+@pytest.mark.parametrize("case", list(PAIR_CASES))
+def test_cta_pair_kernel(case):
+    n, h, w_, srcC, co, k, s16, d16, res, act = PAIR_CASES[case]
+    ci = sum(srcC)
+    x = rnd(n, ci, h, w_, seed=11)
+    w, b = wb(co, ci, *k, seed=13)
+    srcs, vals, c0 = [], [], 0
+    for i, c in enumerate(srcC):
+        buf, _ = nhwc(x[:, c0:c0 + c])
+        as16 = (s16 is True or (s16 is None and i == 0)) and c % 32 == 0
+        if as16:
+            buf = s16_encode(buf)
+            vals.append(s16_decode(buf)[..., :c].permute(0, 3, 1, 2).cpu())
+        else:
+            vals.append(x[:, c0:c0 + c])
+        srcs.append((buf, c, 0, A.FMT_S16 if as16 else A.FMT_F32))
+        c0 += c
+    if srcC == [8]:   # Mixer.conv_delta1: five real channels in an eight-channel slice
+        w[:, 5:] = 0
+    out = torch.zeros(n, h, w_, co, device=DEV)
+    seg = dict(ch0=0, nch=co, dst=out, act=act, fmt=A.SEG_DST_S16 if d16 else 0)
+    want = ref_conv(torch.cat(vals, 1), w, b)
+    if res:
+        r = rnd(n, co, h, w_, seed=17)
+        rb, _ = nhwc(r)
+        if d16:
+            rb = s16_encode(rb)
+            r = s16_decode(rb).permute(0, 3, 1, 2).cpu()
+            seg["fmt"] |= A.SEG_RES_S16
+        seg["res"] = rb
+        want = want + r.double()
+    want = {A.ACT_NONE: lambda v: v, A.ACT_RELU: F.relu, A.ACT_TANH: torch.tanh}[act](want)
+    run_conv(w, b, srcs, (h, w_), A.CONV_TC16P, [seg])
+    got = s16_decode(out) if d16 else out
+    check(from_nhwc(got, co), want, f"cta pair: {case}")
+
+
+def test_cta_pair_close_to_single_cta():
+    """the pair kernel performs the same MMAs on the same operands and drains the same segments; only the two correction
+    products are accumulated in columns of their own instead of on top of each other: last-bit differences"""
+    n, h, w_ = 2, 72, 104
+    x = rnd(n, 64, h, w_, seed=23)
+    w, b = wb(64, 64, 3, 3, seed=29)
+    xb = s16_encode(nhwc(x)[0])
+    outs = []
+    for kind in (A.CONV_TC16, A.CONV_TC16P):
+        out = torch.zeros(n, h, w_, 64, device=DEV)
+        run_conv(w, b, [(xb, 64, 0, A.FMT_S16)], (h, w_), kind, [dict(ch0=0, nch=64, dst=out, act=A.ACT_RELU, fmt=A.SEG_DST_S16)])
+        outs.append(out.clone())
+    a, b_ = s16_decode(outs[0]), s16_decode(outs[1])
+    assert float((a - b_).abs().max()) <= 2.0 ** -20 * float(a.abs().max())
+
+
 # ---- S16 ("split fp16") activation format: conv_s3 reads it without a conversion pass and writes it from its epilogue
 def test_s16_roundtrip_host():
     x = rnd(2, 5, 7, 64, seed=5, scale=3.0)

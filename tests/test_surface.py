@@ -88,7 +88,7 @@ def test_storage_formats_are_consistent_along_the_plan(state_dict):
     for ops in (e.ops_prefix_ff, e.ops_stage1, e._iter_ops(0, True)):
         for op in ops:
             if op[0] == "conv" and any(v.fmt for vs in op[5].values() for v in vs):
-                assert op[3] in (A.CONV_TC16, A.CONV_TC16W), op[2]
+                assert op[3] in (A.CONV_TC16, A.CONV_TC16W, A.CONV_TC16P), op[2]
     # the all-fp32 plan (comparison mode) passes the same replay trivially
     f = Engine(state_dict, 1, 64, 96, torch.device("cpu"), conv_kind="tc16f32", dry=True)
     assert not f.use_s16 and all(v.fmt == A.FMT_F32 for v in f.views.values())

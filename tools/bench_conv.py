@@ -113,7 +113,9 @@ if __name__ == "__main__":
         macs = n * h * w * sum(srcC) * co * k[0] * k[1]
         row = {"conv": name, "GMAC": round(macs / 1e9, 2)}
         for kind_name in a.kinds.split(","):
-            kind = {"tc": A.CONV_TC, "tc16": A.CONV_TC16, "tc16h3": A.CONV_TC16, "ffma": A.CONV_FFMA}[kind_name]
+            kind = {"tc": A.CONV_TC, "tc16": A.CONV_TC16, "tc16h3": A.CONV_TC16, "ffma": A.CONV_FFMA, "tc16p": A.CONV_TC16P}[kind_name]
+            if kind == A.CONV_TC16P and (co + 15) // 16 * 16 not in (32, 64):
+                continue
             A.set_option("tc_gen", 2 if kind_name == "tc16h3" else 3)
             d, keep = make_conv(kind, n, h, w, srcC, co, k, res="+res" in name, act=A.ACT_NONE if "+res" in name else A.ACT_RELU, s16=a.s16)
             ms = time_conv(d)

@@ -6,8 +6,8 @@ import torch
 from demfi_b200 import _abi as A
 from tools.bench_conv import make_conv, time_conv
 
-NAMES = {0: "split.total", 1: "split.wait_full", 2: "split.wait_aslot", 3: "split.st+arrive", 4: "epi.total", 5: "epi.wait_acc",
-         6: "epi.store", 7: "split.convert", 8: "prod.total", 9: "prod.wait_empty", 12: "mma.total", 13: "mma.wait_acc_free", 14: "mma.wait_A"}
+NAMES = {0: "split.total", 1: "split.wait_full|epi.top(wait_read+operands)", 2: "epi.store.wait_staging", 3: "epi.store.fence+bar", 4: "epi.total", 5: "epi.wait_acc",
+         6: "epi.store", 7: "split.convert|epi.store.tma_issue", 8: "prod.total", 9: "prod.wait_empty", 10: "epi.tmem_ld", 11: "epi.arrive", 12: "mma.total", 13: "mma.wait_acc_free", 14: "mma.wait_A", 15: "mma.wait_peer"}
 
 
 def run(shape, kind=A.CONV_TC16, s16=False, **opts):
@@ -20,7 +20,7 @@ def run(shape, kind=A.CONV_TC16, s16=False, **opts):
     ms = time_conv(d)
     buf = np.zeros((148, 16), dtype=np.int64)
     A.check(A.lib().demfi_tc_debug_read(buf.ctypes.data_as(C.POINTER(C.c_int64)), 148), "debug_read")
-    med = np.median(buf, axis=0)
+    med = np.median(buf[0::2], axis=0) if kind == A.CONV_TC16P else np.median(buf, axis=0)   # pairs: the leaders (even CTAs)
     print(json.dumps({"kind": kind, "s16": s16, "shape": {k: v for k, v in shape.items()}, **opts, "ms": round(ms, 3),
                       "kclk": {NAMES[i]: round(float(med[i]) / 1e3, 1) for i in NAMES}}), flush=True)
     A.set_option("tc_diag", 0)
