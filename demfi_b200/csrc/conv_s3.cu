@@ -92,6 +92,7 @@ struct S3Params {
   int all_full_chunks;  // every source has C % 32 == 0 (no ragged chunk)
   int all_s16;          // every source is in the S16 format: the converter warps have nothing to do
   int pair;             // CTA-pair kernel (DEMFI_CONV_TC16P)
+  int offload;          // the TMA duties of the epilogue (operand fetch, stores) run on a warp of their own (all sources S16)
   float comp;
   int diag;
   long long* dbg;
@@ -676,6 +677,45 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
   // kernel to have completed (griddepcontrol.wait), the loads of weights and bias (constants) do not.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
+  // ---- the TMA side of the epilogue for one tile: operand tiles in, result boxes out.  Run by thread 0 of the epilogue
+  // warps, or -- when every source is S16 and the converter warps have nothing to do -- by lane 0 of converter warp 0
+  // (P.offload): the issue of a bulk tensor store blocks the issuing thread for several hundred cycles and the wait for its
+  // shared-memory reads for as long again, and on an epilogue warp both delay that warp's next accumulator drain, i.e. the
+  // hand-over every MMA of the next tile but one waits for (measured: 1.4-2 kclk per tile on the critical warp).
+  const uint32_t stg_base = smem_base + (uint32_t)P.stg_off;
+  auto epi_fetch = [&](int nb, int tx0, int ty0, int n, int nboxes) {
+    const bool pb = P.nsb > 1;
+    const int e0 = nb * P.nsb, ne = pb ? nboxes : 1;
+    uint32_t tx = 0;
+    for (int sb = 0; sb < ne; ++sb) tx += (uint32_t)(P.e_nres[e0 + sb] * (pb ? 1 : nboxes) * S3_BOX_BYTES);
+    if (tx == 0) return;
+    mbar_arrive_expect_tx(bar_resfull, tx);
+    for (int sb = 0; sb < ne; ++sb) {
+      const int e = e0 + sb, nr = P.e_nres[e];
+      if (nr == 0) continue;
+      const int sg = P.e_seg[e];
+      const int b0 = pb ? sb : 0, b1 = pb ? sb + 1 : nboxes;
+      for (int b = b0; b < b1; ++b) {
+        tma_load_4d(stg_base + (uint32_t)(P.e_roff[e] + b * S3_BOX_BYTES), &P.rmap[sg], bar_resfull, P.e_rc0[e] + 32 * (b - b0), tx0, ty0, n);
+        if (nr > 1)
+          tma_load_4d(stg_base + (uint32_t)(P.stg2_off + b * S3_BOX_BYTES), &P.r2map[sg], bar_resfull, P.e_rc0[e] + 32 * (b - b0), tx0, ty0, n);
+      }
+    }
+  };
+  auto epi_store = [&](int nb, int tx0, int ty0, int n, int nboxes) {
+    const bool pb = P.nsb > 1;
+    const int e0 = nb * P.nsb, ne = pb ? nboxes : 1;
+    for (int sb = 0; sb < ne; ++sb) {
+      const int e = e0 + sb;
+      if (P.e_seg[e] < 0) continue;
+      const int b0 = pb ? sb : 0, b1 = pb ? sb + 1 : nboxes;
+      for (int j = P.e_o0[e]; j < P.e_o0[e] + P.e_on[e]; ++j)
+        for (int b = b0; b < b1; ++b)
+          tma_store_4d(&P.omap[P.ol_map[j]], stg_base + (uint32_t)(b * S3_BOX_BYTES), P.ol_c0[j] + 32 * (b - b0), tx0, ty0, n);
+    }
+    bulk_commit();
+  };
+
   if (warp == S3_CV_WARPS + S3_EPI_WARPS + 1) {
     // ===== MMA issuer: ONE elected thread runs the whole persistent loop, and its warp takes part in nothing afterwards.
     // What sets its pace (round-2 measurements: tools/diag_timers.py, tools/mma_probe_pair.cu, ncu source page): with the
@@ -713,6 +753,36 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
     const long long t_begin = dbg ? clock64() : 0;
     int abuf = 0;
     uint32_t aphase = 0;
+    if (P.offload && warp == 0) {
+      // ===== store warp (every source S16): the TMA side of the epilogue, tile by tile; barrier 2 = "staging tile free and the
+      // operand tiles requested" (this warp arrives, the epilogue threads wait), barrier 3 = "staging tile written" (they
+      // arrive, this warp waits) =====
+      asm volatile("griddepcontrol.wait;" ::: "memory");
+      bool pending = false;
+      for (int tile = tile0; tile < tend; tile += tstep) {
+        int t = tile;
+        const int nb = t % P.n_blocks;
+        t /= P.n_blocks;
+        const int tx0 = (t % P.tiles_x) * S3_TW;
+        t /= P.tiles_x;
+        const int ty0 = (t % P.tiles_y) * S3_TH;
+        const int n = t / P.tiles_y;
+        const int nboxes = (n_of(nb) + 31) >> 5;
+        const bool dummy = PAIR && tile >= P.ntiles;
+        if (lane == 0) {
+          if (pending) bulk_wait_read0();
+          if (!dummy) epi_fetch(nb, tx0, ty0, n, nboxes);
+        }
+        __syncwarp();
+        asm volatile("bar.arrive 2, %0;" ::"n"(S3_EPI_THREADS + 32) : "memory");
+        asm volatile("bar.sync 3, %0;" ::"n"(S3_EPI_THREADS + 32) : "memory");
+        if (lane == 0 && !dummy) {
+          epi_store(nb, tx0, ty0, n, nboxes);
+          pending = true;
+        }
+      }
+      if (lane == 0 && pending) bulk_wait0();  // stores complete before the CTA exits
+    }
     for (int tile = tile0; tile < tend && !P.all_s16; tile += tstep) {  // (every source S16: nothing to do here)
       for (int si = 0; si < c.nsrc; ++si) {
         const bool s16 = c.src[si].fmt == DEMFI_FMT_S16;  // already fp16 hi | lo rows: passed on as it landed
@@ -774,10 +844,10 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
       const float4 b = ld4(c.bias + i);
       sts128(bias_s + (uint32_t)i * 4u, make_uint4(__float_as_uint(b.x), __float_as_uint(b.y), __float_as_uint(b.z), __float_as_uint(b.w)));
     }
-    asm volatile("bar.sync 2, %0;" ::"n"(S3_EPI_THREADS) : "memory");
+    asm volatile("bar.sync 4, %0;" ::"n"(S3_EPI_THREADS) : "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");  // operand tiles and destinations belong to earlier kernels
+    const bool offload = P.offload != 0;
     const bool per_box = P.nsb > 1;  // entries are 32-channel boxes (else one entry per N block)
-    const uint32_t emask = per_box ? 0xffffffffu : 0u;
     for (int tile = tile0; tile < tend; tile += tstep) {
       const bool dummy = PAIR && tile >= P.ntiles;  // (odd tile count: the pair's second tile does not exist)
       int t = tile;
@@ -799,26 +869,11 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
       if (P.tma_epi && !dummy)
         for (int sb = 0; sb < ne; ++sb) nres_any += P.e_nres[e0 + sb];
       const long long t_top = dbg ? clock64() : 0;
-      if (P.tma_epi) {
+      if (P.tma_epi && !offload) {
         // the staging buffers are free once the previous tile's stores have read them; then fetch the operand tiles
         if (e_tid == 0) {
           if (store_pending) bulk_wait_read0();
-          if (nres_any > 0) {
-            uint32_t tx = 0;
-            for (int sb = 0; sb < ne; ++sb) tx += (uint32_t)(P.e_nres[e0 + sb] * (per_box ? 1 : nboxes) * S3_BOX_BYTES);
-            mbar_arrive_expect_tx(bar_resfull, tx);
-            for (int sb = 0; sb < ne; ++sb) {
-              const int e = e0 + sb, nr = P.e_nres[e];
-              if (nr == 0) continue;
-              const int sg = P.e_seg[e];
-              const int b0 = per_box ? sb : 0, b1 = per_box ? sb + 1 : nboxes;
-              for (int b = b0; b < b1; ++b) {
-                tma_load_4d(stg + (uint32_t)(P.e_roff[e] + b * S3_BOX_BYTES), &P.rmap[sg], bar_resfull, P.e_rc0[e] + 32 * (b - b0), tx0, ty0, n);
-                if (nr > 1)
-                  tma_load_4d(stg + (uint32_t)(P.stg2_off + b * S3_BOX_BYTES), &P.r2map[sg], bar_resfull, P.e_rc0[e] + 32 * (b - b0), tx0, ty0, n);
-              }
-            }
-          }
+          if (nres_any > 0) epi_fetch(nb, tx0, ty0, n, nboxes);
         }
         store_pending = true;
       }
@@ -884,10 +939,11 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
       const long long t_store = dbg ? clock64() : 0;
       if (P.tma_epi) {
         // ---- staged epilogue: bias, operands, activation -> swizzled box layout -> TMA store ----
+        if (offload) asm volatile("bar.sync 2, %0;" ::"n"(S3_EPI_THREADS + 32) : "memory");  // the store warp released the staging tile
         if (nres_any > 0) {
           mbar_wait(bar_resfull, res_phase);
           res_phase ^= 1u;
-        } else {
+        } else if (!offload) {
           asm volatile("bar.sync 2, %0;" ::"n"(S3_EPI_THREADS) : "memory");  // staging buffer released (thread 0 waited)
         }
         if (dbg) w_s1 += clock64() - t_store;  // waited for the staging tile / the operand tiles
@@ -898,71 +954,71 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
         // independent loads, no dependent chain across the unrolled steps -- whether the result is stored S16 (one hi chunk +
         // one lo chunk of the pixel's 128-byte group row; an operand tile in the same format is in the same place: read, then
         // overwritten in place) or fp32 (two 4-channel chunks), with which activation and operands.
-#pragma unroll
-        for (int col = 0; col < HMAX; col += 8) {
-          if (col < cnum && !(P.diag & 32)) {
-            const int chn = cbeg + col;
-            const uint32_t info = (uint32_t)P.e_info[e0 + (int)((uint32_t)(chn >> 5) & emask)];
-            const int sfmt = (int)(info & 7u), act = (int)((info >> 3) & 7u), nres = (int)((info >> 6) & 3u);
-            const uint32_t roff = (info & 256u) ? (uint32_t)P.stg2_off : 0u;
-            const uint32_t base = row + (uint32_t)((chn >> 5) * S3_BOX_BYTES);
-            const float4 b0 = as_f4(lds128(bias_s + (uint32_t)(n0 + chn) * 4u)), b1 = as_f4(lds128(bias_s + (uint32_t)(n0 + chn + 4) * 4u));
-            float4 v0 = make_float4(sum[col] + b0.x, sum[col + 1] + b0.y, sum[col + 2] + b0.z, sum[col + 3] + b0.w);
-            float4 v1 = make_float4(sum[col + 4] + b1.x, sum[col + 5] + b1.y, sum[col + 6] + b1.z, sum[col + 7] + b1.w);
-            float4 h0 = zero4, h1 = zero4, z0 = zero4, z1 = zero4;
-            if (sfmt & DEMFI_SEG_DST_S16) {
-              if (nres > 0) op_load8(base + roff, chn, sw, (sfmt & DEMFI_SEG_RES_S16) != 0, h0, h1);
-              if (nres > 1) op_load8(base + (uint32_t)P.stg2_off, chn, sw, (sfmt & DEMFI_SEG_RES2_S16) != 0, z0, z1);
-            } else {
-              if (nres > 0) {
-                h0 = op_load4(base + roff, chn, sw, (sfmt & DEMFI_SEG_RES_S16) != 0);
-                h1 = op_load4(base + roff, chn + 4, sw, (sfmt & DEMFI_SEG_RES_S16) != 0);
-              }
-              if (nres > 1) {
-                z0 = op_load4(base + (uint32_t)P.stg2_off, chn, sw, (sfmt & DEMFI_SEG_RES2_S16) != 0);
-                z1 = op_load4(base + (uint32_t)P.stg2_off, chn + 4, sw, (sfmt & DEMFI_SEG_RES2_S16) != 0);
-              }
+        auto step8 = [&](int col, int chn, uint32_t info) {
+          const int sfmt = (int)(info & 7u), act = (int)((info >> 3) & 7u), nres = (int)((info >> 6) & 3u);
+          const uint32_t roff = (info & 256u) ? (uint32_t)P.stg2_off : 0u;
+          const uint32_t base = row + (uint32_t)((chn >> 5) * S3_BOX_BYTES);
+          const float4 b0 = as_f4(lds128(bias_s + (uint32_t)(n0 + chn) * 4u)), b1 = as_f4(lds128(bias_s + (uint32_t)(n0 + chn + 4) * 4u));
+          float4 v0 = make_float4(sum[col] + b0.x, sum[col + 1] + b0.y, sum[col + 2] + b0.z, sum[col + 3] + b0.w);
+          float4 v1 = make_float4(sum[col + 4] + b1.x, sum[col + 5] + b1.y, sum[col + 6] + b1.z, sum[col + 7] + b1.w);
+          float4 h0 = zero4, h1 = zero4, z0 = zero4, z1 = zero4;
+          if (sfmt & DEMFI_SEG_DST_S16) {
+            if (nres > 0) op_load8(base + roff, chn, sw, (sfmt & DEMFI_SEG_RES_S16) != 0, h0, h1);
+            if (nres > 1) op_load8(base + (uint32_t)P.stg2_off, chn, sw, (sfmt & DEMFI_SEG_RES2_S16) != 0, z0, z1);
+          } else {
+            if (nres > 0) {
+              h0 = op_load4(base + roff, chn, sw, (sfmt & DEMFI_SEG_RES_S16) != 0);
+              h1 = op_load4(base + roff, chn + 4, sw, (sfmt & DEMFI_SEG_RES_S16) != 0);
             }
-            if (act == DEMFI_ACT_NONE || act == DEMFI_ACT_RELU) {  // the common case stays inline (a few FADD / FMNMX)
-              v0.x += h0.x; v0.y += h0.y; v0.z += h0.z; v0.w += h0.w;
-              v1.x += h1.x; v1.y += h1.y; v1.z += h1.z; v1.w += h1.w;
-              if (act == DEMFI_ACT_RELU) {
-                v0.x = fmaxf(v0.x, 0.0f); v0.y = fmaxf(v0.y, 0.0f); v0.z = fmaxf(v0.z, 0.0f); v0.w = fmaxf(v0.w, 0.0f);
-                v1.x = fmaxf(v1.x, 0.0f); v1.y = fmaxf(v1.y, 0.0f); v1.z = fmaxf(v1.z, 0.0f); v1.w = fmaxf(v1.w, 0.0f);
-              }
-            } else {
-              v0 = finish4v(act, v0, h0, z0);
-              v1 = finish4v(act, v1, h1, z1);
-            }
-            if (sfmt & DEMFI_SEG_DST_S16) {
-              const uint32_t g8 = (uint32_t)((chn & 31) >> 3);
-              uint4 hi, lo;
-              s16_encode8(v0, v1, hi, lo);
-              sts128(base + ((g8 ^ sw) << 4), hi);
-              sts128(base + (((g8 + 4u) ^ sw) << 4), lo);
-            } else {
-              const uint32_t q = (uint32_t)((chn & 31) >> 2);
-              sts128(base + ((q ^ sw) << 4), as_u4(v0));
-              sts128(base + (((q + 1u) ^ sw) << 4), as_u4(v1));
+            if (nres > 1) {
+              z0 = op_load4(base + (uint32_t)P.stg2_off, chn, sw, (sfmt & DEMFI_SEG_RES2_S16) != 0);
+              z1 = op_load4(base + (uint32_t)P.stg2_off, chn + 4, sw, (sfmt & DEMFI_SEG_RES2_S16) != 0);
             }
           }
+          if (act == DEMFI_ACT_NONE || act == DEMFI_ACT_RELU) {  // the common case stays inline (a few FADD / FMNMX)
+            v0.x += h0.x; v0.y += h0.y; v0.z += h0.z; v0.w += h0.w;
+            v1.x += h1.x; v1.y += h1.y; v1.z += h1.z; v1.w += h1.w;
+            if (act == DEMFI_ACT_RELU) {
+              v0.x = fmaxf(v0.x, 0.0f); v0.y = fmaxf(v0.y, 0.0f); v0.z = fmaxf(v0.z, 0.0f); v0.w = fmaxf(v0.w, 0.0f);
+              v1.x = fmaxf(v1.x, 0.0f); v1.y = fmaxf(v1.y, 0.0f); v1.z = fmaxf(v1.z, 0.0f); v1.w = fmaxf(v1.w, 0.0f);
+            }
+          } else {
+            v0 = finish4v(act, v0, h0, z0);
+            v1 = finish4v(act, v1, h1, z1);
+          }
+          if (sfmt & DEMFI_SEG_DST_S16) {
+            const uint32_t g8 = (uint32_t)((chn & 31) >> 3);
+            uint4 hi, lo;
+            s16_encode8(v0, v1, hi, lo);
+            sts128(base + ((g8 ^ sw) << 4), hi);
+            sts128(base + (((g8 + 4u) ^ sw) << 4), lo);
+          } else {
+            const uint32_t q = (uint32_t)((chn & 31) >> 2);
+            sts128(base + ((q ^ sw) << 4), as_u4(v0));
+            sts128(base + (((q + 1u) ^ sw) << 4), as_u4(v1));
+          }
+        };
+        // one entry per N block (the common case): its packed word is read once per tile; per-box plans look it up per step
+        if (!per_box) {
+          const uint32_t info = (uint32_t)P.e_info[e0];
+#pragma unroll
+          for (int col = 0; col < HMAX; col += 8)
+            if (col < cnum && !(P.diag & 32)) step8(col, cbeg + col, info);
+        } else {
+#pragma unroll
+          for (int col = 0; col < HMAX; col += 8)
+            if (col < cnum && !(P.diag & 32)) step8(col, cbeg + col, (uint32_t)P.e_info[e0 + ((cbeg + col) >> 5)]);
         }
         const long long t_s2 = dbg ? clock64() : 0;
         fence_async_smem();
-        asm volatile("bar.sync 3, %0;" ::"n"(S3_EPI_THREADS) : "memory");
+        if (offload) {
+          asm volatile("bar.arrive 3, %0;" ::"n"(S3_EPI_THREADS + 32) : "memory");  // the store warp takes it from here
+        } else {
+          asm volatile("bar.sync 3, %0;" ::"n"(S3_EPI_THREADS) : "memory");
+        }
         if (dbg) w_s2 += clock64() - t_s2;
         const long long t_s3 = dbg ? clock64() : 0;
-        if (e_tid == 0 && !dummy && !(P.diag & (1 | 32))) {
-          for (int sb = 0; sb < ne; ++sb) {
-            const int e = e0 + sb;
-            if (P.e_seg[e] < 0) continue;
-            const int b0 = per_box ? sb : 0, b1 = per_box ? sb + 1 : nboxes;
-            for (int j = P.e_o0[e]; j < P.e_o0[e] + P.e_on[e]; ++j)
-              for (int b = b0; b < b1; ++b)
-                tma_store_4d(&P.omap[P.ol_map[j]], stg + (uint32_t)(b * S3_BOX_BYTES), P.ol_c0[j] + 32 * (b - b0), tx0, ty0, n);
-          }
-          bulk_commit();
-        }
+        if (!offload && e_tid == 0 && !dummy && !(P.diag & (1 | 32))) epi_store(nb, tx0, ty0, n, nboxes);
         if (dbg) w_s3 += clock64() - t_s3;
       } else if (valid && !(P.diag & 1)) {
         const int ch_lo = n0 + cbeg, ch_hi = ch_lo + cnum;
@@ -982,7 +1038,7 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
       }
       if (dbg) w_store += clock64() - t_store;
     }
-    if (P.tma_epi && e_tid == 0 && store_pending) bulk_wait0();  // stores complete before the CTA exits
+    if (P.tma_epi && !offload && e_tid == 0 && store_pending) bulk_wait0();  // stores complete before the CTA exits
     if (dbg && e_tid == 0) {
       long long* d = P.dbg + (size_t)blockIdx.x * 16;
       d[4] = clock64() - t_begin; d[5] = w_tfull; d[6] = w_store; d[10] = w_ld; d[11] = w_arr; d[2] = w_s1; d[3] = w_s2;
@@ -1416,6 +1472,7 @@ static int s3_plan(const demfi_conv_t& c, S3Params& P, S3EpiPlan& E, int* smem_o
   P.all_s16 = 1;
   for (int s_ = 0; s_ < c.nsrc; ++s_)
     if (c.src[s_].fmt != DEMFI_FMT_S16) P.all_s16 = 0;
+  P.offload = (P.tma_epi && P.all_s16 && !(get_option("tc_diag") & 2048)) ? 1 : 0;
   for (int s_ = 0; s_ < c.nsrc; ++s_)
     if (c.src[s_].C % S3_KC != 0) P.all_full_chunks = 0;
   {  // accumulation segments: whole issue units, balanced over the tile

@@ -197,9 +197,10 @@ class Engine:
         # tiles: +10..35 %) and long K loops (>= 20 (chunk, tap) stages per tile: halved weight traffic / shared-memory reads,
         # +17..20 % on Ch_Reducer, w_gen, the GRU q convolutions).  The 18-stage 64 -> 64 3x3 ResBlock convolutions are bound by
         # their epilogue in both forms (a tie) and stay on one CTA per tile.
-        if stride == 1 and cout_pad in (32, 64) and os.environ.get("DEMFI_PAIR", "1") != "0":
+        pair_mode = os.environ.get("DEMFI_PAIR", "1")  # 0: never, 1: the measured rule, 2: every eligible convolution
+        if stride == 1 and cout_pad in (32, 64) and pair_mode != "0":
             stages = sum((vw.C + 31) // 32 for vw, _ in srcs) * KH * KW
-            if cout_pad == 32 or stages >= 20:
+            if cout_pad == 32 or stages >= 20 or pair_mode == "2":
                 return A.CONV_TC16P
         # 97..128 output channels as ONE N block (conv_s3 only: stride 1)
         # (measured at 1280x736, profiles/r2_conv_notes.md: GRU z|r 1.87 ms as one N = 128 block vs 1.64 ms as two N = 64 blocks -- the
