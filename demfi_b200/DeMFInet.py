@@ -9,8 +9,9 @@ pass is the plan in `demfi_b200/engine.py`, i.e. hand-written sm_100a kernels be
 ABI of `include/demfi_b200.h`.  There is no PyTorch/CPU fallback: without the CUDA library
 or a B200 the forward raises.
 
-Scope: inference forward.  Autograd through the kernels (training,
-`main.py:443`) is the "next" row f-2 and raises NotImplementedError for now.
+Scope: the inference forward on the fused engine; with `is_training=True` under grad mode (the
+training loop's call, `main.py:402`, followed by `.backward()` at `:443`) the call returns the same 7-tuple as an autograd graph
+over this library's kernels (`demfi_b200/train_net.py`, row f-2).
 """
 from __future__ import annotations
 
@@ -173,9 +174,11 @@ class DeMFInet(nn.Module):
         if not torch.cuda.is_available():
             raise RuntimeError("demfi_b200.DeMFInet needs a B200 (sm_100a) GPU: there is no CPU fallback")
         if is_training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("the fused inference engine keeps nothing for a backward pass: wrap the call in torch.no_grad(), "
-                                      "or use demfi_b200.train_net.forward_train(model, x, t, N_trn) for the differentiable forward "
-                                      "(SURVEY.md 8f-2)")
+            # the training loop's call (main.py:402, followed by total_loss.backward() at :443): the differentiable forward, an
+            # autograd graph whose heavy nodes are this library's kernels; the fused inference engine keeps nothing for a backward
+            from . import train_net
+            dev = x.device if x.is_cuda else self.device
+            return train_net.forward_train(self, x.to(dev), t_value.to(dev), 1 if num_update is None else int(num_update))
         dev = x.device if x.is_cuda else self.device
         B, C, T, H, W = x.size()
         if num_update is None:  # `summary()` dry run, DeMFInet.py:126-128

@@ -146,7 +146,9 @@ class FolderRunner:
         if self.cuda:
             with torch.cuda.stream(self.copy_stream):
                 f = normalize_bgr_u8(host.to(self.dev, non_blocking=True))
-            torch.cuda.current_stream(self.dev).wait_stream(self.copy_stream)
+            cur = torch.cuda.current_stream(self.dev)
+            cur.wait_stream(self.copy_stream)
+            f.record_stream(cur)  # allocated on the copy stream, consumed on the compute stream: no reuse before that is done
         else:
             f = normalize_bgr_u8(host)
         self.cache[path] = f
@@ -179,6 +181,11 @@ class FolderRunner:
         """Returns {"pairs", "interpolated", "deblurred", "files"} for this rank's share of the work."""
         work = enumerate_custom(custom_path, self.M)
         mine = [w for i, w in enumerate(work) if i % self.world == self.rank]
+        # The deblurred S1 of pair i and the deblurred S0 of pair i + 1 carry the same file name (main.py:1165-1172); the
+        # reference writes sequentially, so the S0 of the later pair is what stays on disk.  Here writes are asynchronous and
+        # neighbouring pairs may sit on different ranks: every such file is written ONCE, by the pair whose S0 it is; an S1 is
+        # written only where no later pair produces that name (the last pair of a scene).
+        s0_files = {(w[0], w[4]) for w in work}
         pending, futures = {}, []
         stats = {"pairs": 0, "interpolated": 0, "deblurred": 0, "files": []}
         for k, (scene, idx, paths, st, s0_name, s1_name) in enumerate(mine):
@@ -193,8 +200,10 @@ class FolderRunner:
                 s0, s1, stf = interpolate(self.net, x, tt, self.N, self.pb, reuse_prefix=j > 0)
                 if j == 0:  # main.py:1160-1169: the deblurred pair is written at the first time index only
                     self._save(os.path.join(out_dir, s0_name), s0[0], futures)
-                    self._save(os.path.join(out_dir, s1_name), s1[0], futures)
-                    stats["deblurred"] += 2
+                    stats["deblurred"] += 1
+                    if (scene, s1_name) not in s0_files:
+                        self._save(os.path.join(out_dir, s1_name), s1[0], futures)
+                        stats["deblurred"] += 1
                 self._save(os.path.join(out_dir, st_name), stf[0], futures)
                 stats["interpolated"] += 1
             stats["pairs"] += 1

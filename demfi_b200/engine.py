@@ -102,6 +102,7 @@ class Engine:
         self._graphs: Dict[tuple, tuple] = {}
         self._gx: Optional[torch.Tensor] = None
         self._tb: Optional[torch.Tensor] = None
+        self._prefix_valid = False  # the t-independent stage has run on this engine's buffers (reuse_prefix may be honoured)
         self._build()
 
     # ------------------------------------------------------------------ memory
@@ -521,6 +522,11 @@ class Engine:
         channel means).  Channel means come from `demfi_channel_absmean`; the per-sample normalisation is three small torch
         ops on [B, H*W] maps."""
         B, H, W, v = self.B, self.H, self.W, self.views
+        with torch.cuda.device(self.dev):
+            return self._fgac_maps_on_device(visualization)
+
+    def _fgac_maps_on_device(self, visualization: bool):
+        B, H, W, v = self.B, self.H, self.W, self.views
         st = torch.cuda.current_stream(self.dev).cuda_stream
 
         def absmean(a: View, b: Optional[View] = None) -> torch.Tensor:
@@ -678,6 +684,14 @@ class Engine:
         if self.dry:
             raise RuntimeError("a dry (host-only) engine cannot run: demfi_b200 has no CPU path")
         assert tuple(x.shape) == (B, 3, 4, H, W), (tuple(x.shape), (B, 3, 4, H, W))
+        if reuse_prefix and not self._prefix_valid:
+            raise RuntimeError("reuse_prefix=True, but this engine has not run the t-independent stage yet (new engine: first call, "
+                               "changed resolution or reloaded weights): call once with reuse_prefix=False for this frame pair")
+        with torch.cuda.device(self.dev):  # the C-ABI launches go to the current device: make it the one that owns the buffers
+            return self._forward_on_device(x, t_value, num_update, reuse_prefix, final_only, graph)
+
+    def _forward_on_device(self, x, t_value, num_update, reuse_prefix, final_only, graph):
+        B = self.B
         x = x.to(self.dev, torch.float32).contiguous()
         self.t_dev.copy_(t_value.reshape(B).to(torch.float32), non_blocking=True)
         if graph is None:
@@ -711,6 +725,7 @@ class Engine:
             A.check(lib.demfi_pack_input(x.data_ptr(), B, H, W, v["S2D"].ptr, v["REF"].ch(9, 12).ptr, 32,
                                          v["A3"].ch(28, 12).ptr, 40, self._tb.data_ptr(), st), "pack_input")
             self._run(self.ops_prefix_ff, st)
+            self._prefix_valid = True
         two_blurry = self._tb.clone()
         self._run(self.ops_stage1, st)
         SP, A3, DL0 = v["SP"], v["A3"], v["DL0"]

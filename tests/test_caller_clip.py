@@ -171,7 +171,10 @@ def test_folder_runner_writes_what_the_reference_loop_writes(tmp_path):
     _write_scene(root, "clip", 5, 24, 40, 3)  # 2 pairs
     m = BlendModel()
     stats = FolderRunner(m, multiple=4, num_update=1, io_threads=2).run(root)
-    assert stats["pairs"] == 2 and stats["interpolated"] == 6 and stats["deblurred"] == 4 and len(stats["files"]) == 10
+    # three deblurred files for two pairs: 00002.png is both S1 of pair 1 and S0 of pair 2 -- the reference's sequential loop leaves
+    # pair 2's S0 on disk (main.py:1165-1172), so that is the one write made (no unordered double write)
+    assert stats["pairs"] == 2 and stats["interpolated"] == 6 and stats["deblurred"] == 3 and len(stats["files"]) == 9
+    assert len(set(stats["files"])) == len(stats["files"])
     assert [c[2] for c in m.calls] == [False, True, True, False, True, True]  # prefix recomputed once per pair
     assert all(c[0] == (1, 3, 4, 32, 64) for c in m.calls)  # reflect-padded to x32
     out_dir = os.path.join(root, "clip_sharply_interpolated_x4")
@@ -193,6 +196,14 @@ def test_folder_runner_writes_what_the_reference_loop_writes(tmp_path):
     s0 = np.squeeze(res0[1][-1][0].numpy()).astype(np.float64)[..., :oh, :ow]
     img0 = np.transpose(((s0 + 1) / 2).clip(0, 1) * 255, [1, 2, 0]).astype(np.uint8)
     assert np.array_equal(cv2.imread(os.path.join(out_dir, "00001.png")), img0)
+    # the shared file holds the S0 of the LATER pair (idx = 2: frames 2, 3, 1, 4), the last pair's S1 is written too
+    frames2 = np.stack([cv2.imread(os.path.join(root, "clip", f"{i:05d}.png")) for i in (2, 3, 1, 4)], axis=0)
+    x2 = ((torch.Tensor(frames2.transpose(3, 0, 1, 2).astype(float)) / 255.0 - 0.5) * 2).unsqueeze(0)
+    x2p, _, _ = pad_to_multiple(x2, 32)
+    r2 = ref(x2p, torch.tensor([[0.25]]), 1)
+    for name, k in (("00002.png", 0), ("00003.png", 1)):
+        v = np.squeeze(r2[1][-1][k].numpy()).astype(np.float64)[..., :oh, :ow]
+        assert np.array_equal(cv2.imread(os.path.join(out_dir, name)), np.transpose(((v + 1) / 2).clip(0, 1) * 255, [1, 2, 0]).astype(np.uint8)), name
 
 
 def test_folder_runner_shards_pairs_across_ranks(tmp_path):
@@ -210,9 +221,8 @@ def test_folder_runner_shards_pairs_across_ranks(tmp_path):
         roots.append(os.path.join(root, "s_sharply_interpolated_x2"))
     import cv2
     assert sorted(os.listdir(roots[0])) == sorted(os.listdir(roots[1]))
-    for name in os.listdir(roots[0]):
-        if "_" in name:  # interpolated frames: one writer each (deblurred frames are written by two neighbouring pairs)
-            assert np.array_equal(cv2.imread(os.path.join(roots[0], name)), cv2.imread(os.path.join(roots[1], name))), name
+    for name in os.listdir(roots[0]):  # every file has exactly one writer, whatever the sharding: identical on disk
+        assert np.array_equal(cv2.imread(os.path.join(roots[0], name)), cv2.imread(os.path.join(roots[1], name))), name
 
 
 def _allreduce_worker(rank, world, port, q):

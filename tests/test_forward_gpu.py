@@ -152,8 +152,8 @@ def test_return_structure(net):
             assert float((got_m.cpu() - want_m).abs().max()) < 2e-3
         for got_f, want_f in zip(r7[6][0], want[6][0]):
             assert float((got_f.cpu() - want_f).abs().max()) < TOL
-    with pytest.raises(NotImplementedError):
-        net(x, t, 1, is_training=True)
+    r_grad = net(x, t, 1, is_training=True)   # under grad mode: the differentiable forward (tests/test_train_net_gpu.py)
+    assert len(r_grad) == 7 and r_grad[1][-1][2].requires_grad
     with pytest.raises(ValueError):
         with torch.no_grad():
             net(synth.make_frames(20, 24), t, 1)
@@ -219,6 +219,18 @@ def test_full_size_two_implementations_agree_on_every_conv_stack(state_dict):
         frac = float((e > 5e-4).float().mean())
         print(f"full size {k}: max-abs {float(e.max()):.3e}, fraction > 5e-4 {frac:.2e}")
         assert frac < 5e-3, (k, frac)
+
+
+def test_reuse_prefix_needs_a_prefix(state_dict):
+    """a fresh engine has no t-independent stage to reuse: asking for it is an error, not a forward on zero-filled buffers"""
+    from demfi_b200.engine import Engine
+    eng = Engine(state_dict, 1, 32, 32, DEV)
+    x = synth.make_frames(32, 32, seed=3).to(DEV)
+    t = torch.tensor([[0.5]], device=DEV)
+    with pytest.raises(RuntimeError, match="reuse_prefix"):
+        eng.forward(x, t, 1, reuse_prefix=True)
+    eng.forward(x, t, 1)
+    eng.forward(x, t, 1, reuse_prefix=True)
 
 
 def test_full_size_forward_is_bitwise_repeatable_and_batch_invariant(state_dict):
