@@ -382,15 +382,105 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_clip_workload(args):
+    """BASELINE config 3 as written: ONE 64-frame 1280x720 clip (61 frame pairs x 7 time indices = 427 interpolated frames)
+    sharded over the ranks -- strong scaling.  The clip sits in pinned host memory on every rank; a rank copies the frames of
+    its pairs to the device as it goes, reuses the t-independent prefix across the time indices of a pair and copies every
+    interpolated frame back to pinned host memory.  Timed from a barrier to the last rank done (device events, max over ranks).
+    --balance 1 (default) cuts the pairs of the last incomplete round into (pair, t) units (clip.schedule_units)."""
+    import torch.distributed as dist
+    from demfi_b200 import synth
+    from demfi_b200.DeMFInet import DeMFInet
+    from demfi_b200.caller import interpolate
+    from demfi_b200.clip import pair_indices, pair_input, schedule_units, t_values
+    world, rank, local = env_int("WORLD_SIZE", 1), env_int("RANK", 0), env_int("LOCAL_RANK", 0)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    net = DeMFInet(synth.default_args(gpu=local)).to(dev).eval()
+    net.load_state_dict(synth.make_state_dict(0), strict=True)
+    F_ = args.frames
+    base = synth.make_frames(H0, W0, seed=7)[0]                       # [3,4,H,W]: four distinct frames, cycled with a drift
+    clip = torch.stack([torch.roll(base[:, i % 4], shifts=i // 4, dims=2) for i in range(F_)]).contiguous().pin_memory()  # [F,3,H,W]
+    ts = t_values(MFI)
+    pairs = pair_indices(F_)
+    units = schedule_units(pairs, len(ts), rank, world, balance_tail=bool(args.balance))
+    out_pin = torch.empty((1, 3, H0, W0), dtype=torch.float32).pin_memory()
+
+    stage = torch.empty((4, 3, H0, W0), dtype=torch.float32, device=dev)
+
+    def load_pair(idx):
+        # four asynchronous copies straight from the pinned clip (no host-side gather), slot order B0, B1, B-1, B2
+        for k, f in enumerate((idx, idx + 1, idx - 1, idx + 2)):
+            stage[k].copy_(clip[f], non_blocking=True)
+        return stage.permute(1, 0, 2, 3).unsqueeze(0).contiguous()
+
+    def one_pass():
+        n = 0
+        for idx, js in units:
+            x = load_pair(idx)
+            for k, j in enumerate(js):
+                s0, s1, st = interpolate(net, x, torch.tensor([[ts[j]]], device=dev), N_TST, 32, reuse_prefix=k > 0)
+                out_pin.copy_(st, non_blocking=False)
+                n += 1
+        return n
+
+    x = pair_input(clip, pairs[0]).to(dev)
+    for w_ in range(3):  # warm-up: engine construction, weight packing, function attributes
+        interpolate(net, x, torch.tensor([[ts[w_]]], device=dev), N_TST, 32, reuse_prefix=w_ > 0)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    done = one_pass()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    tot = torch.tensor([float(done)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        print(json.dumps({"metric": "interpolated_frames_per_sec", "value": round(float(tot) / (float(ms) / 1e3), 3), "unit": "frames/s",
+                          "n_gpus": world, "steps": 1, "warmup": 3, "ms_per_step": round(float(ms), 1), "higher_is_better": True,
+                          "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": f"BASELINE config 3: one {F_}-frame {W0}x{H0} clip, x{MFI} MFI, N_tst={N_TST}: {len(pairs)} pairs x "
+                                                 f"{len(ts)} t = {int(tot)} interpolated frames, pairs sharded over {world} rank(s), prefix reused "
+                                                 f"within a pair, host frames in / host frames out", "balance_tail": bool(args.balance),
+                                     "units_per_rank_max": max(sum(len(js) for _, js in schedule_units(pairs, len(ts), r, world, bool(args.balance)))
+                                                               for r in range(world))}}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_train_workload(args):
+    """BASELINE config 4: one training step on 2 samples of 256x256 per GPU (batch 16 on 8 GPUs), N_trn = 5: differentiable forward
+    -> L1 losses with fused gradients -> backward -> gradient all-reduce (NCCL, one flat 29.6 MB bucket) -> Adam."""
+    sys.argv = [sys.argv[0], "--steps", str(max(args.steps, 2))]
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bench_train
+    bench_train.main()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=14)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="mfi", choices=["mfi", "clip", "train"],
+                    help="mfi: BASELINE's headline (default); clip: config 3 (one clip, strong scaling); train: config 4 (training step)")
+    ap.add_argument("--frames", type=int, default=64, help="--workload clip: frames in the clip")
+    ap.add_argument("--balance", type=int, default=1, help="--workload clip: cut the last round's pairs into (pair, t) units")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "clip":
+        run_clip_workload(args)
+    elif args.workload == "train":
+        run_train_workload(args)
     else:
         run_ours(args)
 

@@ -34,21 +34,43 @@ def pair_input(frames: torch.Tensor, idx: int) -> torch.Tensor:
     return sel.permute(1, 0, 2, 3).unsqueeze(0).contiguous()
 
 
+def schedule_units(pairs: Sequence[int], n_t: int, rank: int, world: int, balance_tail: bool = True) -> List[Tuple[int, List[int]]]:
+    """This rank's work on a clip as [(pair index, [time indices])].  Whole pairs go round-robin (`pair % world`, all time
+    indices of a pair on one rank: the t-independent prefix of the network is computed once per pair).  With balance_tail the
+    pairs of the last, incomplete round -- 61 pairs on 8 GPUs leave 5 pairs for 8 ranks -- are cut into their (pair, t)
+    units and dealt out in contiguous runs, so that no rank idles for a whole pair at the end (a rank that receives part of
+    a pair recomputes that pair's prefix: 12 ms against 33 ms per time index at 1280x720)."""
+    pairs = list(pairs)
+    full = len(pairs) // world * world if balance_tail else len(pairs)
+    if balance_tail and len(pairs) - full == 0:
+        full = len(pairs)
+    mine = [(p, list(range(n_t))) for i, p in enumerate(pairs[:full]) if i % world == rank]
+    units = [(p, j) for p in pairs[full:] for j in range(n_t)]
+    lo, hi = len(units) * rank // world, len(units) * (rank + 1) // world
+    for p, j in units[lo:hi]:
+        if mine and mine[-1][0] == p:  # (a tail pair: pair indices are unique, so this never merges into a whole pair)
+            mine[-1][1].append(j)
+        else:
+            mine.append((p, [j]))
+    return mine
+
+
 @torch.no_grad()
 def run_clip(model_net, frames: torch.Tensor, multiple: int, num_update: int, rank: int = 0, world: int = 1,
              reuse_prefix: bool = True, patch_boundary: int = 32,
-             sink: Callable[[int, float, Tuple[torch.Tensor, ...]], None] | None = None) -> int:
-    """Process this rank's pairs of a clip already resident on the model's device.  `sink(pair_idx, t, (S0,S1,St))`
-    receives the results.  Returns the number of interpolated frames produced on this rank."""
+             sink: Callable[[int, float, Tuple[torch.Tensor, ...]], None] | None = None, balance_tail: bool = False) -> int:
+    """Process this rank's share of a clip already resident on the model's device (see schedule_units).
+    `sink(pair_idx, t, (S0,S1,St))` receives the results.  Returns the number of interpolated frames produced on this rank."""
     dev = frames.device
     done = 0
-    for idx in shard_pairs(pair_indices(frames.shape[0]), rank, world):
+    ts = t_values(multiple)
+    for idx, js in schedule_units(pair_indices(frames.shape[0]), len(ts), rank, world, balance_tail):
         x = pair_input(frames, idx)
-        for j, t in enumerate(t_values(multiple)):
-            tt = torch.tensor([[t]], dtype=torch.float32, device=dev)
-            out = interpolate(model_net, x, tt, num_update, patch_boundary, reuse_prefix=reuse_prefix and j > 0)
+        for k, j in enumerate(js):
+            tt = torch.tensor([[ts[j]]], dtype=torch.float32, device=dev)
+            out = interpolate(model_net, x, tt, num_update, patch_boundary, reuse_prefix=reuse_prefix and k > 0)
             if sink is not None:
-                sink(idx, t, out)
+                sink(idx, ts[j], out)
             done += 1
     return done
 

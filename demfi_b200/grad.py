@@ -17,6 +17,7 @@ DEMFI_GRAD_PACK_CACHE=1 keeps the packed tensors until the parameter's version c
 from __future__ import annotations
 
 import os
+import weakref
 from typing import Tuple
 
 import numpy as np
@@ -51,47 +52,44 @@ def _pack(w: np.ndarray, b: np.ndarray, src_c: int, dev) -> Tuple[torch.Tensor, 
     return torch.from_numpy(packed).to(dev), torch.from_numpy(bias).to(dev), cout_pad
 
 
-_PACK_CACHE: dict = {}
-_PACK_CACHE_MAX = 4096
-
-
 def _cache_on() -> bool:
-    return os.environ.get("DEMFI_GRAD_PACK_CACHE", "0") == "1"
+    return os.environ.get("DEMFI_GRAD_PACK_CACHE", "1") == "1"
 
 
-def _key(t):
-    return None if t is None else (t.data_ptr(), t._version, tuple(t.shape))
+def _cached(weight: torch.Tensor, key: tuple, bias, make):
+    """Packed weights live ON the parameter they were made from (an attribute of the tensor object, or of its base for a
+    view such as the [:, :, 0] slice of a Conv3d weight): they die with it and are rebuilt when its version counter moves
+    (load_state_dict, torch optimizers and train.Adam all bump it) -- packed once per optimizer step instead of at every
+    call.  (A first version keyed a global table on (data_ptr, version, shape): a freed parameter's address is handed to the
+    next model, and its stale packed weights with it -- wrong gradients in the second model of a process.)"""
+    if not _cache_on():
+        return make()
+    holder = weight._base if weight._base is not None else weight
+    table = holder.__dict__.setdefault("_demfi_packed", {})
+    key = key + (weight.data_ptr() - holder.data_ptr(), tuple(weight.shape), tuple(weight.stride()))
+    ent = table.get(key)
+    bver = None if bias is None else bias._version
+    if ent is not None and ent[0] == weight._version and ent[1] == bver and (bias is None or ent[2]() is bias):
+        return ent[3]
+    out = make()
+    table[key] = (weight._version, bver, None if bias is None else weakref.ref(bias), out)
+    return out
 
 
 def _pack_forward(weight: torch.Tensor, bias, src_c: int, dev):
-    """packed forward weights of a layer.  With DEMFI_GRAD_PACK_CACHE=1 they are kept until the parameter's version counter
-    moves (load_state_dict, torch optimizers and train.Adam all bump it), i.e. packed once per optimizer step instead of at
-    every call; off by default until that mode has been through the GPU tests."""
-    key = ("f", _key(weight), _key(bias), src_c, str(dev)) if _cache_on() else None
-    if key is not None and key in _PACK_CACHE:
-        return _PACK_CACHE[key]
-    Co = weight.shape[0]
-    b = bias.detach().cpu().numpy() if bias is not None else np.zeros(Co, dtype=np.float32)
-    out = _pack(weight.detach().cpu().numpy(), b, src_c, dev)
-    if key is not None:
-        if len(_PACK_CACHE) >= _PACK_CACHE_MAX:
-            _PACK_CACHE.clear()
-        _PACK_CACHE[key] = out
-    return out
+    """packed forward weights of a layer (cached on the parameter, see _cached)"""
+    def make():
+        b = bias.detach().cpu().numpy() if bias is not None else np.zeros(weight.shape[0], dtype=np.float32)
+        return _pack(weight.detach().cpu().numpy(), b, src_c, dev)
+    return _cached(weight, ("f", src_c, str(dev)), bias, make)
 
 
 def _pack_rotated(weight: torch.Tensor, c0: int, c1: int, src_c: int, dev):
     """packed weights of the dx convolution for input channels [c0, c1): w_t[ci, co, ky, kx] = W[co, ci, KH-1-ky, KW-1-kx]"""
-    key = ("r", _key(weight), c0, c1, src_c, str(dev)) if _cache_on() else None
-    if key is not None and key in _PACK_CACHE:
-        return _PACK_CACHE[key]
-    w_rot = weight.detach().flip(2, 3).transpose(0, 1)[c0:c1].contiguous().cpu().numpy()
-    out = _pack(w_rot, np.zeros(c1 - c0, dtype=np.float32), src_c, dev)
-    if key is not None:
-        if len(_PACK_CACHE) >= _PACK_CACHE_MAX:
-            _PACK_CACHE.clear()
-        _PACK_CACHE[key] = out
-    return out
+    def make():
+        w_rot = weight.detach().flip(2, 3).transpose(0, 1)[c0:c1].contiguous().cpu().numpy()
+        return _pack(w_rot, np.zeros(c1 - c0, dtype=np.float32), src_c, dev)
+    return _cached(weight, ("r", c0, c1, src_c, str(dev)), None, make)
 
 
 def _conv_nhwc(x: torch.Tensor, C_: int, wdev: torch.Tensor, bdev: torch.Tensor, cout_pad: int, k: Tuple[int, int], act: int,

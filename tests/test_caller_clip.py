@@ -225,6 +225,27 @@ def test_folder_runner_shards_pairs_across_ranks(tmp_path):
         assert np.array_equal(cv2.imread(os.path.join(roots[0], name)), cv2.imread(os.path.join(roots[1], name))), name
 
 
+def test_clip_schedule_balances_the_last_round():
+    """BASELINE config 3: 64 frames = 61 pairs x 7 time indices on 8 ranks.  Whole pairs round-robin would leave 8,8,8,8,8,7,7,7
+    pairs (the last rank idle for a pair's worth of time, efficiency 61/64); cutting the last round's five pairs into (pair, t)
+    units gives 53 or 54 units to every rank, every unit exactly once"""
+    from demfi_b200.clip import pair_indices, schedule_units
+    pairs = pair_indices(64)
+    assert len(pairs) == 61
+    assert [len(schedule_units(pairs, 7, r, 8, balance_tail=False)) for r in range(8)] == [8, 8, 8, 8, 8, 7, 7, 7]
+    for world in (1, 2, 3, 8):
+        seen, loads = set(), []
+        for r in range(world):
+            units = schedule_units(pairs, 7, r, world)
+            loads.append(sum(len(js) for _, js in units))
+            for p, js in units:
+                assert js == sorted(js)
+                for j in js:
+                    assert (p, j) not in seen
+                    seen.add((p, j))
+        assert len(seen) == 61 * 7 and max(loads) - min(loads) <= (1 if world == 8 else 7), (world, loads)
+
+
 def _allreduce_worker(rank, world, port, q):
     import torch.distributed as dist
     from demfi_b200.train import allreduce_gradients

@@ -28,11 +28,10 @@ def test_forward_and_rotated_packs_equal_the_plain_expressions():
 
 def test_pack_cache_follows_the_version_counter(monkeypatch):
     monkeypatch.setenv("DEMFI_GRAD_PACK_CACHE", "1")
-    grad._PACK_CACHE.clear()
     w = torch.nn.Parameter(torch.randn(16, 8, 3, 3))
     b = torch.nn.Parameter(torch.zeros(16))
     a1 = grad._pack_forward(w, b, 8, CPU)
-    assert grad._pack_forward(w, b, 8, CPU)[0] is a1[0] and len(grad._PACK_CACHE) == 1          # hit
+    assert grad._pack_forward(w, b, 8, CPU)[0] is a1[0] and len(w._demfi_packed) == 1           # hit; kept ON the parameter
     r1 = grad._pack_rotated(w, 0, 8, 16, CPU)
     assert grad._pack_rotated(w, 0, 8, 16, CPU)[0] is r1[0]
     with torch.no_grad():
@@ -49,7 +48,12 @@ def test_pack_cache_follows_the_version_counter(monkeypatch):
     with torch.no_grad():
         w5.add_(1.0)
     assert grad._pack_forward(w5.squeeze(2), None, 8, CPU)[0] is not p1[0]
+    assert grad._pack_forward(w5.squeeze(2), None, 8, CPU)[0] is grad._pack_forward(w5.squeeze(2), None, 8, CPU)[0]  # views hit through the base
+    # another parameter at the same address (the first model of a process freed, the second allocated) never sees stale weights:
+    # the packed tensors live on the parameter object and die with it
+    w_new = torch.nn.Parameter(torch.randn(16, 8, 3, 3))
+    assert not hasattr(w_new, "_demfi_packed")
     monkeypatch.setenv("DEMFI_GRAD_PACK_CACHE", "0")
-    n = len(grad._PACK_CACHE)
-    grad._pack_forward(w, b, 8, CPU)
-    assert len(grad._PACK_CACHE) == n                                                            # off: nothing is kept
+    w_off = torch.nn.Parameter(torch.randn(16, 8, 3, 3))
+    grad._pack_forward(w_off, b, 8, CPU)
+    assert not hasattr(w_off, "_demfi_packed")                                                   # off: nothing is kept
