@@ -93,6 +93,7 @@ struct S3Params {
   int all_s16;          // every source is in the S16 format: the converter warps have nothing to do
   int pair;             // CTA-pair kernel (DEMFI_CONV_TC16P)
   int offload;          // the TMA duties of the epilogue (operand fetch, stores) run on a warp of their own (all sources S16)
+  int lean;             // lean epilogue: bit 0 = eligible, bit 1 = ReLU, bit 2 = one S16 operand added in place
   float comp;
   int diag;
   long long* dbg;
@@ -597,7 +598,10 @@ __device__ __forceinline__ void s3_issue(const S3Params& P, uint32_t smem_base, 
 // the leader; each CTA holds half of the weight rows, so the filter bank of a 64 -> 64 3x3 layer takes 72 KB instead of 144 KB
 // (room for four halo buffers instead of two), the B-operand reads per SM halve (the N = 64 MMA pair becomes bound by the
 // tensor pipe, 192 clk per k-step pair, instead of by shared-memory reads, 224) and a ring streams half the bytes from L2.
-template <int NMAX, bool DBG, int U, bool PAIR>
+// LEAN: the epilogue of the common ResBlock-type layer only (one full N block of 32 / 64 channels, S16 destination, ReLU or
+// no activation, at most one S16 operand added in place: s3_plan sets P.lean) -- a kernel of its own, so that neither epilogue
+// pays for the other's registers and instruction-cache footprint.
+template <int NMAX, bool DBG, int U, bool PAIR, bool LEAN>
 __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_constant__ S3Params P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -847,6 +851,16 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
     asm volatile("bar.sync 4, %0;" ::"n"(S3_EPI_THREADS) : "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");  // operand tiles and destinations belong to earlier kernels
     const bool offload = P.offload != 0;
+    // lean epilogue (host: s3_plan): one full N block (N == NMAX), one entry, S16 destination, activation none / ReLU, at most
+    // one S16 operand in the result tile
+    constexpr bool LEANOK = LEAN;
+    constexpr bool lean = LEAN;
+    const bool lean_relu = (P.lean & 2) != 0, lean_res = (P.lean & 4) != 0;
+    const uint32_t lean_c0 = (uint32_t)(grp * HMAX);  // first channel of this thread (N == NMAX: csplit == HMAX)
+    const uint32_t lean_bias = bias_s + lean_c0 * 4u;
+    // the thread's pixel row never changes: row of its staging box, swizzle key, first 16-byte chunk
+    const uint32_t lean_row = stg + (uint32_t)m * 128u + (lean_c0 >> 5) * (uint32_t)S3_BOX_BYTES;
+    const uint32_t lean_sw = (uint32_t)m & 7u, lean_g0 = (lean_c0 & 31u) >> 3;
     const bool per_box = P.nsb > 1;  // entries are 32-channel boxes (else one entry per N block)
     for (int tile = tile0; tile < tend; tile += tstep) {
       const bool dummy = PAIR && tile >= P.ntiles;  // (odd tile count: the pair's second tile does not exist)
@@ -891,10 +905,33 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
         const uint32_t tcorr = tbuf + (uint32_t)(PAIR ? grp * N + (N >> 1) : N + cbeg);
         const uint32_t tcorr2 = tbuf + (uint32_t)(2 * N + cbeg);
         const long long t_ld0 = dbg ? clock64() : 0;
+        if (LEANOK && lean && P.nseg == 1) {
+          // full block (N == NMAX), ONE accumulation segment per tile (no partial sums live): the thread's HMAX main columns
+          // and HMAX correction columns are requested together and waited for once (one tensor-memory round trip instead of
+          // two; a pair adds the Al x Bh columns in a second one)
+          uint32_t ra[HMAX], rb[HMAX];
+#pragma unroll
+          for (int col = 0; col < HMAX; col += 16) tmem_ld16_nowait(taddr + (uint32_t)col, ra + col);
+#pragma unroll
+          for (int col = 0; col < HMAX; col += 16) tmem_ld16_nowait(tcorr + (uint32_t)col, rb + col);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < HMAX; ++j) {
+            sum[j] = fmaf(__uint_as_float(rb[j]), 1.0f / S3_LO_SCALE, __uint_as_float(ra[j]) * gain);
+          }
+          if (PAIR) {
+#pragma unroll
+            for (int col = 0; col < HMAX; col += 16) tmem_ld16_nowait(tcorr2 + (uint32_t)col, rb + col);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < HMAX; ++j) sum[j] = fmaf(__uint_as_float(rb[j]), 1.0f / S3_LO_SCALE, sum[j]);
+          }
+        } else
         // 32 columns at a time (the wide N = 128 blocks hold 64 columns per thread: the partial sums stay in registers, the
         // drained values pass through a 32-register window)
 #pragma unroll
         for (int c32 = 0; c32 < HMAX; c32 += 32) {
+
           constexpr int RW = HMAX < 32 ? HMAX : 32;
           uint32_t r[RW];
 #pragma unroll
@@ -998,6 +1035,31 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
             sts128(base + (((q + 1u) ^ sw) << 4), as_u4(v1));
           }
         };
+        if (LEANOK && lean) {
+          // Lean store loop (full block, one entry, S16 destination, ReLU or none, at most one S16 operand updated in place):
+          // the thread's pixel row never changes, so its eight chunk addresses of the staging box are computed once per kernel
+          // and a step is two bias loads, the adds, the split and two stores -- no address arithmetic, no per-step lookups.
+#pragma unroll
+          for (int s8 = 0; s8 < HMAX / 8; ++s8) {
+            const float4 b0 = as_f4(lds128(lean_bias + (uint32_t)s8 * 32u)), b1 = as_f4(lds128(lean_bias + (uint32_t)s8 * 32u + 16u));
+            float4 v0 = make_float4(sum[8 * s8] + b0.x, sum[8 * s8 + 1] + b0.y, sum[8 * s8 + 2] + b0.z, sum[8 * s8 + 3] + b0.w);
+            float4 v1 = make_float4(sum[8 * s8 + 4] + b1.x, sum[8 * s8 + 5] + b1.y, sum[8 * s8 + 6] + b1.z, sum[8 * s8 + 7] + b1.w);
+            if (lean_res) {
+              float4 h0, h1;
+              s16_decode8(lds128(lean_row + ((((uint32_t)s8 + lean_g0) ^ lean_sw) << 4)), lds128(lean_row + ((((uint32_t)s8 + lean_g0 + 4u) ^ lean_sw) << 4)), h0, h1);
+              v0.x += h0.x; v0.y += h0.y; v0.z += h0.z; v0.w += h0.w;
+              v1.x += h1.x; v1.y += h1.y; v1.z += h1.z; v1.w += h1.w;
+            }
+            if (lean_relu) {
+              v0.x = fmaxf(v0.x, 0.0f); v0.y = fmaxf(v0.y, 0.0f); v0.z = fmaxf(v0.z, 0.0f); v0.w = fmaxf(v0.w, 0.0f);
+              v1.x = fmaxf(v1.x, 0.0f); v1.y = fmaxf(v1.y, 0.0f); v1.z = fmaxf(v1.z, 0.0f); v1.w = fmaxf(v1.w, 0.0f);
+            }
+            uint4 hi, lo;
+            s16_encode8(v0, v1, hi, lo);
+            sts128(lean_row + ((((uint32_t)s8 + lean_g0) ^ lean_sw) << 4), hi);
+            sts128(lean_row + ((((uint32_t)s8 + lean_g0 + 4u) ^ lean_sw) << 4), lo);
+          }
+        } else
         // one entry per N block (the common case): its packed word is read once per tile; per-box plans look it up per step
         if (!per_box) {
           const uint32_t info = (uint32_t)P.e_info[e0];
@@ -1127,20 +1189,30 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
   }
 }
 
-// Two translation units (compile time): S3_TU == 1 holds only the role-timer (DBG) instantiations of the kernel, S3_TU == 0
-// everything else.  __graft_entry__.build() compiles this file twice.
+// Three translation units (compile time): S3_TU == 1 holds the role-timer (DBG) instantiations of the kernel, S3_TU == 2 the
+// lean-epilogue ones, S3_TU == 0 everything else.  __graft_entry__.build() compiles this file three times.
 #ifndef S3_TU
 #define S3_TU 0
 #endif
 typedef void (*S3KernelFn)(S3Params);
-#define S3_ROW(N_, D_, P_) \
-  {conv_s3_kernel<N_, D_, 1, P_>, conv_s3_kernel<N_, D_, 3, P_>, conv_s3_kernel<N_, D_, 5, P_>, conv_s3_kernel<N_, D_, 7, P_>}
-S3KernelFn s3_dbg_kernel(int nidx, int uidx, int pair);
+#define S3_ROW(N_, D_, P_, L_) \
+  {conv_s3_kernel<N_, D_, 1, P_, L_>, conv_s3_kernel<N_, D_, 3, P_, L_>, conv_s3_kernel<N_, D_, 5, P_, L_>, conv_s3_kernel<N_, D_, 7, P_, L_>}
+S3KernelFn s3_dbg_kernel(int nidx, int uidx, int pair, int lean);
+S3KernelFn s3_lean_kernel(int nidx, int uidx, int pair);
 #if S3_TU == 1
-S3KernelFn s3_dbg_kernel(int nidx, int uidx, int pair) {
-  static const S3KernelFn table[4][4] = {S3_ROW(32, true, false), S3_ROW(64, true, false), S3_ROW(96, true, false), S3_ROW(128, true, false)};
-  static const S3KernelFn ptable[2][4] = {S3_ROW(32, true, true), S3_ROW(64, true, true)};
-  return pair ? ptable[nidx][uidx] : table[nidx][uidx];
+S3KernelFn s3_dbg_kernel(int nidx, int uidx, int pair, int lean) {
+  static const S3KernelFn table[4][4] = {S3_ROW(32, true, false, false), S3_ROW(64, true, false, false), S3_ROW(96, true, false, false),
+                                         S3_ROW(128, true, false, false)};
+  static const S3KernelFn ptable[2][4] = {S3_ROW(32, true, true, false), S3_ROW(64, true, true, false)};
+  static const S3KernelFn ltable[2][2][4] = {{S3_ROW(32, true, false, true), S3_ROW(64, true, false, true)},
+                                             {S3_ROW(32, true, true, true), S3_ROW(64, true, true, true)}};
+  return lean ? ltable[pair][nidx][uidx] : pair ? ptable[nidx][uidx] : table[nidx][uidx];
+}
+#elif S3_TU == 2
+S3KernelFn s3_lean_kernel(int nidx, int uidx, int pair) {
+  static const S3KernelFn ltable[2][2][4] = {{S3_ROW(32, false, false, true), S3_ROW(64, false, false, true)},
+                                             {S3_ROW(32, false, true, true), S3_ROW(64, false, true, true)}};
+  return ltable[pair][nidx][uidx];
 }
 #else
 // ---- host --------------------------------------------------------------------------------
@@ -1428,7 +1500,8 @@ static int s3_plan(const demfi_conv_t& c, S3Params& P, S3EpiPlan& E, int* smem_o
     P.ns = 0;
     P.gtaps = P.stages_per_tile;
     P.na = (3 * P.a_bytes + bank + fixed <= S3_SMEM_MAX) ? 3 : 2;
-    const int want = P.pair ? 5 : s3_want_buffers(P.taps, chunks);  // (a pair's halved filter bank leaves room: deeper prefetch)
+    int want = s3_want_buffers(P.taps, chunks);
+    if (P.pair && want < 5) want = 5;  // (a pair's halved filter bank leaves room: deeper prefetch)
     while (P.na < want && (P.na + 1) * P.a_bytes + bank + fixed <= S3_SMEM_MAX) ++P.na;
   } else {
     // ring of `ns` slots, each a group of `gtaps` consecutive stages (target <= 24 KB per slot, >= 3 slots); groups are whole
@@ -1454,7 +1527,8 @@ static int s3_plan(const demfi_conv_t& c, S3Params& P, S3EpiPlan& E, int* smem_o
       else break;
     }
     DEMFI_REQUIRE(fits(P.na, ns, g), "conv_s3: shared-memory plan does not fit");
-    const int want = P.pair ? 4 : s3_want_buffers(P.taps, chunks);
+    int want = s3_want_buffers(P.taps, chunks);
+    if (P.pair && want < 4) want = 4;
     while (P.na < want && fits(P.na + 1, ns, g)) ++P.na;
     P.ns = ns;
     P.gtaps = g;
@@ -1473,6 +1547,15 @@ static int s3_plan(const demfi_conv_t& c, S3Params& P, S3EpiPlan& E, int* smem_o
   for (int s_ = 0; s_ < c.nsrc; ++s_)
     if (c.src[s_].fmt != DEMFI_FMT_S16) P.all_s16 = 0;
   P.offload = (P.tma_epi && P.all_s16 && !(get_option("tc_diag") & 2048)) ? 1 : 0;
+  P.lean = 0;
+  if (P.tma_epi && P.n_blocks == 1 && P.nsb == 1 && (c.cout_pad == 32 || c.cout_pad == 64) && E.e_seg[0] >= 0 && !E.e_mixed[0] &&
+      !(get_option("tc_diag") & 4096)) {
+    const demfi_seg_t& g = c.seg[E.e_seg[0]];
+    const bool res_ok = E.e_nres[0] == 0 || (E.e_nres[0] == 1 && (g.fmt & DEMFI_SEG_RES_S16));
+    if ((g.fmt & DEMFI_SEG_DST_S16) && g.ch0 == 0 && g.nch == c.cout_pad && res_ok && g.store == DEMFI_STORE_NHWC &&
+        (g.act == DEMFI_ACT_NONE || g.act == DEMFI_ACT_RELU))
+      P.lean = 1 | (g.act == DEMFI_ACT_RELU ? 2 : 0) | (E.e_nres[0] == 1 ? 4 : 0);
+  }
   for (int s_ = 0; s_ < c.nsrc; ++s_)
     if (c.src[s_].C % S3_KC != 0) P.all_full_chunks = 0;
   {  // accumulation segments: whole issue units, balanced over the tile
@@ -1565,10 +1648,14 @@ int launch_conv_s3(const demfi_conv_t& c, cudaStream_t st) {
   }
   // one kernel per (N block width, issue unit): a single instantiation of the issue loop per kernel keeps its state in
   // uniform registers (a switch over four inlined copies did not)
-  static const S3KernelFn table[4][4] = {S3_ROW(32, false, false), S3_ROW(64, false, false), S3_ROW(96, false, false), S3_ROW(128, false, false)};
-  static const S3KernelFn ptable[2][4] = {S3_ROW(32, false, true), S3_ROW(64, false, true)};
+  static const S3KernelFn table[4][4] = {S3_ROW(32, false, false, false), S3_ROW(64, false, false, false), S3_ROW(96, false, false, false),
+                                         S3_ROW(128, false, false, false)};
+  static const S3KernelFn ptable[2][4] = {S3_ROW(32, false, true, false), S3_ROW(64, false, true, false)};
   const int nidx = P.nb_max <= 32 ? 0 : P.nb_max <= 64 ? 1 : P.nb_max <= 96 ? 2 : 3;
-  const S3KernelFn fn = P.dbg != nullptr ? s3_dbg_kernel(nidx, P.unit >> 1, P.pair) : P.pair ? ptable[nidx][P.unit >> 1] : table[nidx][P.unit >> 1];
+  const S3KernelFn fn = P.dbg != nullptr ? s3_dbg_kernel(nidx, P.unit >> 1, P.pair, P.lean != 0)
+                        : P.lean         ? s3_lean_kernel(nidx, P.unit >> 1, P.pair)
+                        : P.pair         ? ptable[nidx][P.unit >> 1]
+                                         : table[nidx][P.unit >> 1];
   {
     // cudaFuncSetAttribute applies per device: remember which devices have seen which kernel
     static std::mutex mu;

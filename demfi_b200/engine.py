@@ -180,7 +180,7 @@ class Engine:
             bs.append(self._sd[n + ".bias"])
         return (np.ascontiguousarray(torch.cat(ws, 0).numpy()), np.ascontiguousarray(torch.cat(bs, 0).numpy()))
 
-    def _pick_kind(self, KH, KW, stride, pad, srcs, cout_pad):
+    def _pick_kind(self, KH, KW, stride, pad, srcs, cout_pad, segs=None):
         """auto: every convolution the 3xFP16 tcgen05 kernel supports (stride 1 or 2, no up-sampled source) runs on
         it; the rest on the CUDA-core kernel.  tc = first-generation 3xTF32 kernel where eligible (comparison)."""
         no_up = all(u == 0 for _, u in srcs)
@@ -193,15 +193,20 @@ class Engine:
             return A.CONV_TC if tc_ok else A.CONV_FFMA
         if not tc16_ok:
             return A.CONV_FFMA
-        # CTA pairs (cta_group::2, two pixel tiles per MMA, half of the weight rows per CTA) where they were measured faster
-        # than one CTA per tile (profiles/r2_conv_notes.md): 32 output channels (the activation operand is read once for two
-        # tiles: +10..35 %) and long K loops (>= 20 (chunk, tap) stages per tile: halved weight traffic / shared-memory reads,
-        # +17..20 % on Ch_Reducer, w_gen, the GRU q convolutions).  The 18-stage 64 -> 64 3x3 ResBlock convolutions are bound by
-        # their epilogue in both forms (a tie) and stay on one CTA per tile.
-        pair_mode = os.environ.get("DEMFI_PAIR", "1")  # 0: never, 1: the measured rule, 2: every eligible convolution
+        # CTA pairs (cta_group::2, two pixel tiles per MMA, half of the weight rows per CTA) for stride-1 convolutions with 32 or
+        # 64 accumulator channels, where they were measured faster than one CTA per tile (profiles/r2_conv_notes.md): layers whose
+        # epilogue is the lean one (S16 destination, ReLU / none, at most an S16 skip operand: the ResBlock, dense-block and
+        # Mixer convolutions; +12..35 %) and very long K loops (Ch_Reducer: +19 %).  With MMAs issued at the tensor pipe's full
+        # rate a pair is bound by its epilogue, so the layers with heavy generic epilogues (GRU gates, fp32 heads with fp32
+        # operands, the 1x1 convolutions into fp32 buffers) stay on one CTA per tile.  DEMFI_PAIR=0: never, 2: every eligible one.
+        pair_mode = os.environ.get("DEMFI_PAIR", "1")
         if stride == 1 and cout_pad in (32, 64) and pair_mode != "0":
             stages = sum((vw.C + 31) // 32 for vw, _ in srcs) * KH * KW
-            if cout_pad == 32 or stages >= 20 or pair_mode == "2":
+            s16 = self.use_s16 and segs is not None and len(segs) == 1 and segs[0]["dst"].fmt == A.FMT_S16
+            lean = (s16 and segs[0].get("act", A.ACT_NONE) in (A.ACT_NONE, A.ACT_RELU) and segs[0]["nch"] == cout_pad
+                    and (segs[0].get("res") is None or segs[0]["res"].fmt == A.FMT_S16) and segs[0].get("res2") is None
+                    and segs[0].get("store", A.STORE_NHWC) == A.STORE_NHWC)
+            if lean or stages >= 40 or pair_mode == "2":
                 return A.CONV_TC16P
         # 97..128 output channels as ONE N block (conv_s3 only: stride 1)
         # (measured at 1280x736, profiles/r2_conv_notes.md: GRU z|r 1.87 ms as one N = 128 block vs 1.64 ms as two N = 64 blocks -- the
@@ -233,7 +238,7 @@ class Engine:
         if out_map is None:
             out_map = list(range(Co)) + [-1] * (cout_pad - Co)
         assert len(out_map) == cout_pad and sorted(m for m in out_map if m >= 0) == list(range(Co)), names
-        kind = self._pick_kind(KH, KW, stride, tuple(pad), srcs, cout_pad)
+        kind = self._pick_kind(KH, KW, stride, tuple(pad), srcs, cout_pad, segs)
         Ho, Wo = out_hw
         Hi, Wi = in_hw if in_hw is not None else (Ho * stride, Wo * stride)
         lib = self.lib
