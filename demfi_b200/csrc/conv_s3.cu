@@ -94,6 +94,7 @@ struct S3Params {
   int pair;             // CTA-pair kernel (DEMFI_CONV_TC16P)
   int offload;          // the TMA duties of the epilogue (operand fetch, stores) run on a warp of their own (all sources S16)
   int lean;             // lean epilogue: bit 0 = eligible, bit 1 = ReLU, bit 2 = one S16 operand added in place
+  int res_sep;          // the operand tile of a lean layer has a tile of its own (fetched one tile ahead by the store warp)
   float comp;
   int diag;
   long long* dbg;
@@ -167,6 +168,11 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
+}
+// L2 prefetch of a box (no shared-memory destination, no barrier): the later tma_load_4d of the same box hits L2
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
 }
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
@@ -763,26 +769,67 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
       // arrive, this warp waits) =====
       asm volatile("griddepcontrol.wait;" ::: "memory");
       bool pending = false;
-      for (int tile = tile0; tile < tend; tile += tstep) {
+      struct TilePos { int nb, tx0, ty0, n, nboxes; bool dummy; };
+      auto pos_of = [&](int tile) {
+        TilePos q;
         int t = tile;
-        const int nb = t % P.n_blocks;
+        q.nb = t % P.n_blocks;
         t /= P.n_blocks;
-        const int tx0 = (t % P.tiles_x) * S3_TW;
+        q.tx0 = (t % P.tiles_x) * S3_TW;
         t /= P.tiles_x;
-        const int ty0 = (t % P.tiles_y) * S3_TH;
-        const int n = t / P.tiles_y;
-        const int nboxes = (n_of(nb) + 31) >> 5;
-        const bool dummy = PAIR && tile >= P.ntiles;
-        if (lane == 0) {
-          if (pending) bulk_wait_read0();
-          if (!dummy) epi_fetch(nb, tx0, ty0, n, nboxes);
+        q.ty0 = (t % P.tiles_y) * S3_TH;
+        q.n = t / P.tiles_y;
+        q.nboxes = (n_of(q.nb) + 31) >> 5;
+        q.dummy = PAIR && tile >= P.ntiles;
+        return q;
+      };
+      if (!P.res_sep) {
+        for (int tile = tile0; tile < tend; tile += tstep) {
+          const TilePos q = pos_of(tile);
+          if (lane == 0) {
+            if (pending) bulk_wait_read0();
+            if (!q.dummy) epi_fetch(q.nb, q.tx0, q.ty0, q.n, q.nboxes);
+          }
+          __syncwarp();
+          asm volatile("bar.arrive 2, %0;" ::"n"(S3_EPI_THREADS + 32) : "memory");
+          asm volatile("bar.sync 3, %0;" ::"n"(S3_EPI_THREADS + 32) : "memory");
+          if (lane == 0 && !q.dummy) {
+            epi_store(q.nb, q.tx0, q.ty0, q.n, q.nboxes);
+            pending = true;
+          }
+        }
+      } else {
+        // operand tile of its own: fetched for the NEXT tile right after this tile's store loop is through with it (barrier
+        // 3), i.e. a whole TMA store + drain ahead of its use, and prefetched into L2 one tile earlier still
+        auto prefetch = [&](const TilePos& q) {
+          if (!q.dummy)
+            for (int b = 0; b < q.nboxes; ++b) tma_prefetch_4d(&P.rmap[P.e_seg[0]], P.e_rc0[0] + 32 * b, q.tx0, q.ty0, q.n);
+        };
+        if (tile0 < tend && lane == 0) {
+          const TilePos q = pos_of(tile0);
+          if (!q.dummy) epi_fetch(q.nb, q.tx0, q.ty0, q.n, q.nboxes);
+          if (tile0 + tstep < tend) prefetch(pos_of(tile0 + tstep));
         }
         __syncwarp();
-        asm volatile("bar.arrive 2, %0;" ::"n"(S3_EPI_THREADS + 32) : "memory");
-        asm volatile("bar.sync 3, %0;" ::"n"(S3_EPI_THREADS + 32) : "memory");
-        if (lane == 0 && !dummy) {
-          epi_store(nb, tx0, ty0, n, nboxes);
-          pending = true;
+        if (tile0 < tend) asm volatile("bar.arrive 2, %0;" ::"n"(S3_EPI_THREADS + 32) : "memory");
+        for (int tile = tile0; tile < tend; tile += tstep) {
+          const TilePos q = pos_of(tile);
+          const bool more = tile + tstep < tend;
+          asm volatile("bar.sync 3, %0;" ::"n"(S3_EPI_THREADS + 32) : "memory");
+          if (lane == 0) {
+            if (!q.dummy) {
+              epi_store(q.nb, q.tx0, q.ty0, q.n, q.nboxes);
+              pending = true;
+            }
+            if (more) {
+              const TilePos qn = pos_of(tile + tstep);
+              if (!qn.dummy) epi_fetch(qn.nb, qn.tx0, qn.ty0, qn.n, qn.nboxes);
+              if (tile + 2 * tstep < tend) prefetch(pos_of(tile + 2 * tstep));
+            }
+            if (pending) bulk_wait_read0();
+          }
+          __syncwarp();
+          if (more) asm volatile("bar.arrive 2, %0;" ::"n"(S3_EPI_THREADS + 32) : "memory");
         }
       }
       if (lane == 0 && pending) bulk_wait0();  // stores complete before the CTA exits
@@ -861,6 +908,7 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
     // the thread's pixel row never changes: row of its staging box, swizzle key, first 16-byte chunk
     const uint32_t lean_row = stg + (uint32_t)m * 128u + (lean_c0 >> 5) * (uint32_t)S3_BOX_BYTES;
     const uint32_t lean_sw = (uint32_t)m & 7u, lean_g0 = (lean_c0 & 31u) >> 3;
+    const uint32_t lean_res_row = lean_row + (uint32_t)P.e_roff[0];  // the skip operand: in place, or in the operand tile of its own
     const bool per_box = P.nsb > 1;  // entries are 32-channel boxes (else one entry per N block)
     for (int tile = tile0; tile < tend; tile += tstep) {
       const bool dummy = PAIR && tile >= P.ntiles;  // (odd tile count: the pair's second tile does not exist)
@@ -1046,7 +1094,8 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
             float4 v1 = make_float4(sum[8 * s8 + 4] + b1.x, sum[8 * s8 + 5] + b1.y, sum[8 * s8 + 6] + b1.z, sum[8 * s8 + 7] + b1.w);
             if (lean_res) {
               float4 h0, h1;
-              s16_decode8(lds128(lean_row + ((((uint32_t)s8 + lean_g0) ^ lean_sw) << 4)), lds128(lean_row + ((((uint32_t)s8 + lean_g0 + 4u) ^ lean_sw) << 4)), h0, h1);
+              s16_decode8(lds128(lean_res_row + ((((uint32_t)s8 + lean_g0) ^ lean_sw) << 4)),
+                          lds128(lean_res_row + ((((uint32_t)s8 + lean_g0 + 4u) ^ lean_sw) << 4)), h0, h1);
               v0.x += h0.x; v0.y += h0.y; v0.z += h0.z; v0.w += h0.w;
               v1.x += h1.x; v1.y += h1.y; v1.z += h1.z; v1.w += h1.w;
             }
@@ -1459,6 +1508,28 @@ static int s3_plan(const demfi_conv_t& c, S3Params& P, S3EpiPlan& E, int* smem_o
   for (int sg = 0; sg < c.nseg; ++sg)
     DEMFI_REQUIRE(c.seg[sg].fmt == 0 || P.tma_epi, "conv_s3: segment %d asks for the S16 format, which needs the TMA epilogue", sg);
   const int box_bytes_all = ((P.nb_max + 31) / 32) * S3_BOX_BYTES;
+  P.all_s16 = 1;
+  for (int s_ = 0; s_ < c.nsrc; ++s_)
+    if (c.src[s_].fmt != DEMFI_FMT_S16) P.all_s16 = 0;
+  P.offload = (P.tma_epi && P.all_s16 && !(get_option("tc_diag") & 2048)) ? 1 : 0;
+  P.lean = 0;
+  P.res_sep = 0;
+  if (P.tma_epi && P.n_blocks == 1 && E.nsb == 1 && (c.cout_pad == 32 || c.cout_pad == 64) && E.e_seg[0] >= 0 && !E.e_mixed[0] &&
+      !(get_option("tc_diag") & 4096)) {
+    const demfi_seg_t& g = c.seg[E.e_seg[0]];
+    const bool res_ok = E.e_nres[0] == 0 || (E.e_nres[0] == 1 && (g.fmt & DEMFI_SEG_RES_S16));
+    if ((g.fmt & DEMFI_SEG_DST_S16) && g.ch0 == 0 && g.nch == c.cout_pad && res_ok && g.store == DEMFI_STORE_NHWC &&
+        (g.act == DEMFI_ACT_NONE || g.act == DEMFI_ACT_RELU))
+      P.lean = 1 | (g.act == DEMFI_ACT_RELU ? 2 : 0) | (E.e_nres[0] == 1 ? 4 : 0);
+    // The skip operand of a lean layer in a tile of its OWN (pairs: the halved filter bank leaves the room): its load for the
+    // next tile is then issued as soon as this tile's store loop has read it, not after the result's TMA store has drained
+    // the shared staging tile -- measured, the epilogue waited ~2 kclk per tile for a residual fetched that late from HBM.
+    if ((P.lean & 4) && P.offload && P.pair && !(get_option("tc_diag") & 8192)) {
+      P.res_sep = 1;
+      E.e_mixed[0] = 1;
+      E.any_res2 = true;
+    }
+  }
   // second staging tile (operands that cannot share the result tile): only as many boxes as its last user needs
   int stg2_boxes = 0;
   if (P.tma_epi && E.any_res2)
@@ -1543,19 +1614,6 @@ static int s3_plan(const demfi_conv_t& c, S3Params& P, S3EpiPlan& E, int* smem_o
   *smem_out = smem;
 
   P.all_full_chunks = 1;
-  P.all_s16 = 1;
-  for (int s_ = 0; s_ < c.nsrc; ++s_)
-    if (c.src[s_].fmt != DEMFI_FMT_S16) P.all_s16 = 0;
-  P.offload = (P.tma_epi && P.all_s16 && !(get_option("tc_diag") & 2048)) ? 1 : 0;
-  P.lean = 0;
-  if (P.tma_epi && P.n_blocks == 1 && P.nsb == 1 && (c.cout_pad == 32 || c.cout_pad == 64) && E.e_seg[0] >= 0 && !E.e_mixed[0] &&
-      !(get_option("tc_diag") & 4096)) {
-    const demfi_seg_t& g = c.seg[E.e_seg[0]];
-    const bool res_ok = E.e_nres[0] == 0 || (E.e_nres[0] == 1 && (g.fmt & DEMFI_SEG_RES_S16));
-    if ((g.fmt & DEMFI_SEG_DST_S16) && g.ch0 == 0 && g.nch == c.cout_pad && res_ok && g.store == DEMFI_STORE_NHWC &&
-        (g.act == DEMFI_ACT_NONE || g.act == DEMFI_ACT_RELU))
-      P.lean = 1 | (g.act == DEMFI_ACT_RELU ? 2 : 0) | (E.e_nres[0] == 1 ? 4 : 0);
-  }
   for (int s_ = 0; s_ < c.nsrc; ++s_)
     if (c.src[s_].C % S3_KC != 0) P.all_full_chunks = 0;
   {  // accumulation segments: whole issue units, balanced over the tile
