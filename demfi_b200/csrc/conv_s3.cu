@@ -293,13 +293,18 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, uint32_t sbo
   return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) |
          (2ull << 61);
 }
-// a = h + l / 2048 for two values: returns the packed fp16 pairs (low half = first value)
+// a = h + l / 2048 for two values: returns the packed fp16 pairs (low half = first value).  Both conversions saturate
+// (cvt.rn.satfinite): a value beyond the fp16 range (|a| > 65504) becomes +-65504 + 32-ish instead of inf -- the network's
+// activations are O(1..100), but an inf here would turn into NaN in the next layer's MMAs (inf - inf in the lo term).
+__device__ __forceinline__ uint32_t cvt_f16x2_sat(float lo_val, float hi_val) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_val), "f"(lo_val));
+  return r;
+}
 __device__ __forceinline__ void split2(float a0, float a1, uint32_t& hi, uint32_t& lo) {
-  const __half2 h = __floats2half2_rn(a0, a1);
-  const float2 hf = __half22float2(h);
-  const __half2 l = __floats2half2_rn((a0 - hf.x) * S3_LO_SCALE, (a1 - hf.y) * S3_LO_SCALE);
-  hi = *reinterpret_cast<const uint32_t*>(&h);
-  lo = *reinterpret_cast<const uint32_t*>(&l);
+  hi = cvt_f16x2_sat(a0, a1);
+  const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  lo = cvt_f16x2_sat((a0 - hf.x) * S3_LO_SCALE, (a1 - hf.y) * S3_LO_SCALE);
 }
 // Transcendental epilogues (tanh / sigmoid heads, GRU gates), out of line: ONE copy of the exp / reciprocal expansions
 // instead of one per unrolled call site -- inlined they were a quarter of the kernel's 7 K instructions and the

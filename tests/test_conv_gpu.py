@@ -259,6 +259,61 @@ def test_tc16_operand_range():
         assert err <= max(4.0 * ref32, 2e-5 * float(want.abs().max())), (scale, err, ref32)
 
 
+def test_tc16_operand_and_weight_ranges():
+    """3xFP16 over the whole representable range: activations uniform up to 6e4 (fp16 max 65504), weights scaled 1e-4 .. 1e2 --
+    fp32-level accuracy relative to the result's magnitude; beyond the range the split saturates instead of producing inf / NaN"""
+    n, h, w_ = 1, 16, 32
+    g = np.random.Generator(np.random.PCG64(7))
+    w0, _ = wb(64, 64, 3, 3)
+    for xs, ws in ((6e4, 1.0), (6e4, 1e-4), (1.0, 1e2), (1e-3, 1e-4), (3e2, 1e2)):
+        x = torch.from_numpy(g.uniform(-xs, xs, (n, 64, h, w_)).astype(np.float32))
+        w = w0 * ws
+        xb, _ = nhwc(x)
+        for s16 in (False, True):   # fp32 source split by the converter warps / S16 source written by s16_encode
+            out = torch.zeros(n, h, w_, 64, device=DEV)
+            src = (s16_encode(xb), 64, 0, A.FMT_S16) if s16 else (xb, 64, 0)
+            run_conv(w, torch.zeros(64), [src], (h, w_), A.CONV_TC16, [dict(ch0=0, nch=64, dst=out)])
+            xv = s16_decode(src[0]).permute(0, 3, 1, 2).cpu() if s16 else x
+            want = ref_conv(xv, w, torch.zeros(64))
+            err = float((from_nhwc(out, 64).double() - want).abs().max())
+            print(f"|x| <= {xs:g}, weights x {ws:g}, s16={s16}: err {err:.3e}, max|ref| {float(want.abs().max()):.3e}")
+            assert err <= 2e-5 * float(want.abs().max()), (xs, ws, s16, err)
+    # out of range: finite results (saturated operands), never inf / NaN
+    x = torch.full((n, 64, h, w_), 1e6)
+    x[:, ::2] = -3e5
+    xb, _ = nhwc(x)
+    out = torch.zeros(n, h, w_, 64, device=DEV)
+    run_conv(w0, torch.zeros(64), [(xb, 64, 0)], (h, w_), A.CONV_TC16, [dict(ch0=0, nch=64, dst=out, fmt=A.SEG_DST_S16)])
+    assert bool(torch.isfinite(s16_decode(out)).all())
+
+
+def test_tc_accumulation_slope_is_what_the_compensation_assumes():
+    """The tensor core accumulates with truncation: a GAIN error of about -0.27 * 2^-24 per chained MMA (profiles/r1_tc_numerics.md),
+    which the epilogue compensates (tc_comp_milli = 270).  Re-measured here with the compensation off and one accumulation chain
+    per tile: if a driver / firmware change moved the rounding behaviour by more than 20 %, ~100 chained layers would drift."""
+    n, h, w_ = 1, 48, 64
+    x = rnd(n, 64, h, w_, seed=3)
+    w, _ = wb(64, 64, 3, 3, seed=1)
+    xb, _ = nhwc(x)
+    want = ref_conv(x, w, torch.zeros(64))
+    slopes = {}
+    try:
+        for comp in (0, 270):
+            A.set_option("tc_flush", 1000)     # one chain of 2 * 18 main MMAs per tile
+            A.set_option("tc_comp_milli", comp)
+            out = torch.zeros(n, h, w_, 64, device=DEV)
+            run_conv(w, torch.zeros(64), [(xb, 64, 0)], (h, w_), A.CONV_TC16, [dict(ch0=0, nch=64, dst=out)])
+            err = (from_nhwc(out, 64).double() - want).flatten()
+            slopes[comp] = float((err * want.flatten()).sum() / (want.flatten() ** 2).sum())
+    finally:
+        A.set_option("tc_flush", 20)
+        A.set_option("tc_comp_milli", 270)
+    per_mma = -slopes[0] / 36 * 2 ** 24
+    print(f"accumulation gain error per chained MMA: {per_mma:.3f} x 2^-24 (compensation assumes 0.27); residual slope with compensation {slopes[270]:.2e}")
+    assert 0.8 * 0.27 <= per_mma <= 1.2 * 0.27, per_mma
+    assert abs(slopes[270]) < 0.25 * abs(slopes[0])
+
+
 def test_tc_single_pass_is_not_parity_grade():
     """Documents SURVEY.md 7.3: one TF32 pass misses fp32 parity by orders of magnitude; 3xTF32 meets it."""
     n, h, w_ = 1, 16, 32
