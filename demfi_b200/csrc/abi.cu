@@ -47,6 +47,21 @@ int get_option(const char* name) {
   return -1;
 }
 
+// role timers of the last conv_s3 / conv_h3 launch made with tc_diag & 128: [ctas][16] cycles (tools/role_timers.py names the slots)
+constexpr int TC_DBG_CTAS = 256;
+static long long* g_tc_dbg = nullptr;
+int tc_debug_read(long long* host, int ctas) {
+  DEMFI_REQUIRE(g_tc_dbg != nullptr, "tc_debug_read: no launch was made with tc_diag & 128");
+  DEMFI_REQUIRE(ctas > 0 && ctas <= TC_DBG_CTAS, "tc_debug_read: ctas out of range");
+  DEMFI_REQUIRE(cudaMemcpy(host, g_tc_dbg, (size_t)ctas * 16 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess, "tc_debug_read: copy failed");
+  return 0;
+}
+long long* tc_debug_buffer(cudaStream_t st) {
+  if (g_tc_dbg == nullptr && cudaMalloc(&g_tc_dbg, TC_DBG_CTAS * 16 * sizeof(long long)) != cudaSuccess) return nullptr;
+  cudaMemsetAsync(g_tc_dbg, 0, TC_DBG_CTAS * 16 * sizeof(long long), st);
+  return g_tc_dbg;
+}
+
 int check_device() {
   static thread_local int ok_dev = -1;
   int dev = -1;
@@ -126,7 +141,7 @@ int demfi_get_option(const char* name, int32_t* value) {
 
 size_t demfi_packed_weight_floats(int32_t kind, int32_t KH, int32_t KW, const int32_t* src_C, int32_t nsrc,
                                   int32_t cout_pad) {
-  if (kind == DEMFI_CONV_TC) return tc_packed_floats(KH, KW, src_C, nsrc, cout_pad);
+  if (kind == DEMFI_CONV_TC) return 0;  // (retired, see demfi_pack_weights)
   if (kind == DEMFI_CONV_TC16 || kind == DEMFI_CONV_TC16W || kind == DEMFI_CONV_TC16P) return h3_packed_floats(KH, KW, src_C, nsrc, cout_pad);
   int k_total = 0;
   for (int s = 0; s < nsrc; ++s) k_total += src_C[s];
@@ -143,7 +158,7 @@ int demfi_pack_weights(int32_t kind, const float* w, int32_t Co, int32_t Ci, int
   DEMFI_REQUIRE(k_total > 0 && k_total % 4 == 0 && cout_pad > 0 && cout_pad % 4 == 0, "pack_weights: bad padding");
   for (int k = 0; k < k_total; ++k) DEMFI_REQUIRE(in_map[k] >= -1 && in_map[k] < Ci, "pack_weights: in_map[%d] out of range", k);
   for (int n = 0; n < cout_pad; ++n) DEMFI_REQUIRE(out_map[n] >= -1 && out_map[n] < Co, "pack_weights: out_map[%d] out of range", n);
-  if (kind == DEMFI_CONV_TC) return tc_pack_weights(w, Co, Ci, KH, KW, in_map, src_C, nsrc, out_map, cout_pad, out);
+  DEMFI_REQUIRE(kind != DEMFI_CONV_TC, "DEMFI_CONV_TC (the first-generation 3xTF32 kernel) was retired in round 2: use DEMFI_CONV_TC16");
   if (kind == DEMFI_CONV_TC16) return h3_pack_weights(w, Co, Ci, KH, KW, in_map, src_C, nsrc, out_map, cout_pad, out);
   if (kind == DEMFI_CONV_TC16P) return s3_pack_weights_pair(w, Co, Ci, KH, KW, in_map, src_C, nsrc, out_map, cout_pad, out);
   if (kind == DEMFI_CONV_TC16W)
@@ -171,7 +186,7 @@ int demfi_conv_describe(const demfi_conv_t* c, int32_t* info) {
   DEMFI_REQUIRE(c != nullptr && info != nullptr, "conv_describe: null argument");
   for (int i = 0; i < 16; ++i) info[i] = 0;
   if (c->kind == DEMFI_CONV_FFMA) return 0;
-  if (c->kind == DEMFI_CONV_TC) { info[0] = 1; return 0; }
+  DEMFI_REQUIRE(c->kind != DEMFI_CONV_TC, "conv_describe: DEMFI_CONV_TC was retired in round 2: use DEMFI_CONV_TC16");
   const bool s3_only = c->kind == DEMFI_CONV_TC16W || c->kind == DEMFI_CONV_TC16P;
   DEMFI_REQUIRE(c->kind == DEMFI_CONV_TC16 || s3_only, "conv_describe: unknown kind %d", c->kind);
   if (s3_only) DEMFI_REQUIRE(s3_supports(*c), "conv_describe: DEMFI_CONV_TC16W / TC16P need a convolution conv_s3 supports");
@@ -232,7 +247,7 @@ int demfi_conv2d(const demfi_conv_t* c, void* stream) {
                         s3_supports(*c) && s3_s16_ok(*c),
                     "conv2d: the S16 activation format is only implemented by the conv_s3 kernel (stride 1, TMA epilogue)");
   }
-  if (c->kind == DEMFI_CONV_TC) return launch_conv_tc(*c, (cudaStream_t)stream);
+  DEMFI_REQUIRE(c->kind != DEMFI_CONV_TC, "conv2d: DEMFI_CONV_TC (the first-generation 3xTF32 kernel) was retired in round 2: use DEMFI_CONV_TC16");
   if (c->kind == DEMFI_CONV_TC16) {
     if (g_opt_gen.load() == 3 && s3_supports(*c)) return launch_conv_s3(*c, (cudaStream_t)stream);
     return launch_conv_h3(*c, (cudaStream_t)stream);

@@ -122,7 +122,6 @@ __device__ __forceinline__ void seg_emit4(const SegCursor& c, int co, float4 v) 
 
 // conv launchers (one per kernel family)
 int launch_conv_ffma(const demfi_conv_t& c, cudaStream_t st);
-int launch_conv_tc(const demfi_conv_t& c, cudaStream_t st);
 int tc_debug_read(long long* host, int ctas);
 long long* tc_debug_buffer(cudaStream_t st);  // zeroed role-timer buffer (tc_diag & 128)
 int launch_conv_h3(const demfi_conv_t& c, cudaStream_t st);
@@ -137,9 +136,6 @@ int h3_pack_weights(const float* w, int Co, int Ci, int KH, int KW, const int32_
 int s3_nb_max(int kind, int cout_pad);
 int s3_pack_weights_pair(const float* w, int Co, int Ci, int KH, int KW, const int32_t* in_map, const int32_t* src_C, int nsrc,
                          const int32_t* out_map, int cout_pad, float* out);
-size_t tc_packed_floats(int KH, int KW, const int32_t* src_C, int nsrc, int cout_pad);
-int tc_pack_weights(const float* w, int Co, int Ci, int KH, int KW, const int32_t* in_map, const int32_t* src_C,
-                    int nsrc, const int32_t* out_map, int cout_pad, float* out);
 int get_option(const char* name);
 
 }  // namespace demfi

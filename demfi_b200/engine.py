@@ -84,7 +84,7 @@ class Engine:
         if not dry:
             A.check(self.lib.demfi_device_check(device.index or 0), "demfi_device_check")
         self.conv_kind = (conv_kind or os.environ.get("DEMFI_CONV_KIND", "auto")).lower()
-        assert self.conv_kind in ("auto", "ffma", "tc", "tc16", "tc16f32")
+        assert self.conv_kind in ("auto", "ffma", "tc16", "tc16f32")
         # S16 activation storage between convolutions (conv_s3 only); "tc16f32" keeps every buffer fp32 (comparison)
         self.use_s16 = self.conv_kind in ("auto", "tc16") and os.environ.get("DEMFI_S16", "1") != "0"
         # dense blocks in "push" form (_rdb_push_ops): needs conv_s3's per-box epilogue plans, i.e. the S16 / TMA-store path
@@ -182,15 +182,11 @@ class Engine:
 
     def _pick_kind(self, KH, KW, stride, pad, srcs, cout_pad, segs=None):
         """auto: every convolution the 3xFP16 tcgen05 kernel supports (stride 1 or 2, no up-sampled source) runs on
-        it; the rest on the CUDA-core kernel.  tc = first-generation 3xTF32 kernel where eligible (comparison)."""
+        it; the rest on the CUDA-core kernel."""
         no_up = all(u == 0 for _, u in srcs)
         tc16_ok = stride in (1, 2) and no_up and cout_pad % 16 == 0 and cout_pad <= 256
-        tc_ok = (stride == 1 and no_up and pad == (KH // 2, KW // 2) and KH % 2 == 1 and KW % 2 == 1
-                 and cout_pad % 16 == 0 and cout_pad <= 256 and min(vw.C for vw, _ in srcs) >= 16)
         if self.conv_kind == "ffma":
             return A.CONV_FFMA
-        if self.conv_kind == "tc":
-            return A.CONV_TC if tc_ok else A.CONV_FFMA
         if not tc16_ok:
             return A.CONV_FFMA
         # CTA pairs (cta_group::2, two pixel tiles per MMA, half of the weight rows per CTA) for stride-1 convolutions with 32 or

@@ -56,7 +56,7 @@ enum { DEMFI_FMT_F32 = 0, DEMFI_FMT_S16 = 1 };
 enum { DEMFI_SEG_DST_S16 = 1, DEMFI_SEG_RES_S16 = 2, DEMFI_SEG_RES2_S16 = 4 };
 enum {
   DEMFI_CONV_FFMA = 0, /* CUDA-core fp32 implicit GEMM (exact fp32)                                   */
-  DEMFI_CONV_TC = 1,   /* tcgen05 kind::tf32, 3xTF32 split (first-generation tensor-core kernel)       */
+  DEMFI_CONV_TC = 1,   /* RETIRED in round 2 (first-generation 3xTF32 kernel): every entry point rejects it     */
   DEMFI_CONV_TC16 = 2, /* tcgen05 kind::f16, 3xFP16 split + halo-tile activation staging; stride 1|2  */
   DEMFI_CONV_TC16W = 3, /* the same arithmetic on the conv_s3 kernel only (stride 1), with 97..128 output channels kept in
                           ONE N block (an N' = 256 MMA pair per k-step; weights packed for that blocking)              */

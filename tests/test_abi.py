@@ -71,31 +71,15 @@ def test_pack_weights_ffma_layout():
                 assert p[tap, k, n] == want
 
 
-def test_pack_weights_tc_layout_hi_lo_swizzle():
-    rng = np.random.default_rng(1)
-    w = rng.standard_normal((20, 44, 1, 5)).astype(np.float32)
-    src_C = [36, 8]  # two sources -> chunks: [0,32) [32,36)+pad | [0,8)+pad
-    in_map = list(range(36)) + list(range(36, 44))
-    out_map = list(range(20)) + [-1] * 12
-    N = 32
-    p = _pack(A.CONV_TC, w, src_C, in_map, out_map, N)
-    assert not np.isnan(p).any()
-    chunks = [(0, 0), (0, 32), (1, 0)]
-    p = p.reshape(len(chunks), 5, 2, N, 32)
-    kbase = [0, 36]
-    for ci, (s, c0) in enumerate(chunks):
-        for tap in range(5):
-            for n in range(N):
-                for k in range(32):
-                    c = c0 + k
-                    v = np.float32(0.0)
-                    if c < src_C[s] and out_map[n] >= 0:
-                        v = w[out_map[n], in_map[kbase[s] + c], 0, tap]
-                    hi = ((np.array([v]).view(np.uint32) + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)[0]
-                    col = ((k >> 2) ^ (n & 7)) * 4 + (k & 3)  # 128-byte swizzle of the 16-byte groups
-                    assert p[ci, tap, 0, n, col] == hi
-                    assert p[ci, tap, 1, n, col] == np.float32(v - hi)
-                    assert abs(float(hi) + float(p[ci, tap, 1, n, col]) - float(v)) == 0.0  # exact split
+def test_retired_first_generation_kind_is_rejected():
+    """DEMFI_CONV_TC (3xTF32, round 1) is no longer in the library: packing or describing with it is an error, not a fallback"""
+    w = np.zeros((16, 32, 3, 3), dtype=np.float32)
+    sC = (A.i32 * 1)(32)
+    out = np.zeros(16, dtype=np.float32)
+    rc = A.lib().demfi_pack_weights(A.CONV_TC, w.ctypes.data, 16, 32, 3, 3, (A.i32 * 32)(*range(32)), sC, 1, (A.i32 * 16)(*range(16)), 16,
+                                    out.ctypes.data)
+    assert rc != 0 and b"retired" in A.lib().demfi_last_error()
+    assert _describe(64, [(0, 64, A.ACT_RELU, False, 0)], kind=A.CONV_TC) is None
 
 
 def test_pack_weights_tc16_layout_fp16_hi_lo_swizzle64():
@@ -196,4 +180,3 @@ def test_conv_describe_reports_kernel_and_epilogue_plan():
     enc = _describe(64, [(0, 64, A.ACT_RELU, False, 0)], k=(4, 4), srcC=(204,), stride=2)
     assert enc[0] == 2                                                  # stride 2 -> conv_h3
     assert _describe(64, [(0, 64, A.ACT_RELU, False, 0)], kind=A.CONV_FFMA)[0] == 0
-    assert _describe(64, [(0, 64, A.ACT_RELU, False, 0)], kind=A.CONV_TC)[0] == 1

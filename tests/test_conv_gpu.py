@@ -12,7 +12,7 @@ from demfi_b200 import _abi as A
 from gpu_util import CONV_TC16_H3, DEV, from_nhwc, nhwc, run_conv, s16_decode, s16_encode
 
 pytestmark = pytest.mark.gpu
-KINDS = [pytest.param(A.CONV_FFMA, id="ffma"), pytest.param(A.CONV_TC, id="tc"), pytest.param(CONV_TC16_H3, id="tc16-h3"),
+KINDS = [pytest.param(A.CONV_FFMA, id="ffma"), pytest.param(CONV_TC16_H3, id="tc16-h3"),
          pytest.param(A.CONV_TC16, id="tc16-s3")]
 TOL = 2e-5  # max-abs relative to max(1, max|ref|): fp32 conv noise level (ref self-noise 2-3e-5)
 
@@ -312,49 +312,6 @@ def test_tc_accumulation_slope_is_what_the_compensation_assumes():
     print(f"accumulation gain error per chained MMA: {per_mma:.3f} x 2^-24 (compensation assumes 0.27); residual slope with compensation {slopes[270]:.2e}")
     assert 0.8 * 0.27 <= per_mma <= 1.2 * 0.27, per_mma
     assert abs(slopes[270]) < 0.25 * abs(slopes[0])
-
-
-def test_tc_single_pass_is_not_parity_grade():
-    """Documents SURVEY.md 7.3: one TF32 pass misses fp32 parity by orders of magnitude; 3xTF32 meets it."""
-    n, h, w_ = 1, 16, 32
-    x = rnd(n, 64, h, w_, seed=70)
-    w, b = wb(64, 64, 3, 3)
-    xb, _ = nhwc(x)
-    want = ref_conv(x, w, b)
-    errs = {}
-    try:
-        for split in (1, 3):
-            A.set_option("tc_split", split)
-            out = torch.zeros(n, h, w_, 64, device=DEV)
-            run_conv(w, b, [(xb, 64, 0)], (h, w_), A.CONV_TC, [dict(ch0=0, nch=64, dst=out)])
-            errs[split] = float((from_nhwc(out, 64).double() - want).abs().max())
-    finally:
-        A.set_option("tc_split", 3)
-    print("tf32 x1 err", errs[1], "3xTF32 err", errs[3])
-    assert errs[3] < 2e-5 and errs[1] > 10 * errs[3]
-
-
-def test_tc_operand_truncation_probe():
-    """Does the tensor core truncate fp32 operands to tf32 (mask_hi=0 equals mask_hi=1)?  Reported, and
-    the masked mode (default) must be exact either way."""
-    n, h, w_ = 1, 8, 16
-    x = rnd(n, 32, h, w_, seed=71)
-    w, b = wb(16, 32, 1, 1)
-    xb, _ = nhwc(x)
-    want = ref_conv(x, w, b)
-    res = {}
-    try:
-        for m in (1, 0):
-            A.set_option("tc_mask_hi", m)
-            out = torch.zeros(n, h, w_, 16, device=DEV)
-            run_conv(w, b, [(xb, 32, 0)], (h, w_), A.CONV_TC, [dict(ch0=0, nch=16, dst=out)])
-            res[m] = from_nhwc(out, 16)
-    finally:
-        A.set_option("tc_mask_hi", 1)
-    e1 = float((res[1].double() - want).abs().max())
-    e0 = float((res[0].double() - want).abs().max())
-    print(f"mask_hi=1 err {e1:.3e}; mask_hi=0 err {e0:.3e}; identical={torch.equal(res[0], res[1])}")
-    assert e1 < 2e-5
 
 
 # ---- CTA pairs (DEMFI_CONV_TC16P): cta_group::2 MMAs over two pixel tiles, each CTA holding half of the weight rows

@@ -97,7 +97,7 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--h", type=int, default=736)
     ap.add_argument("--w", type=int, default=1280)
-    ap.add_argument("--kinds", default="tc,ffma")
+    ap.add_argument("--kinds", default="tc16,ffma")
     ap.add_argument("--opts", default="")  # e.g. tc_mask_hi=0,tc_split=1
     ap.add_argument("--only", default="")
     ap.add_argument("--s16", action="store_true", help="sources / destination / residual in the S16 storage format where channel counts allow")
@@ -113,7 +113,7 @@ if __name__ == "__main__":
         macs = n * h * w * sum(srcC) * co * k[0] * k[1]
         row = {"conv": name, "GMAC": round(macs / 1e9, 2)}
         for kind_name in a.kinds.split(","):
-            kind = {"tc": A.CONV_TC, "tc16": A.CONV_TC16, "tc16h3": A.CONV_TC16, "ffma": A.CONV_FFMA, "tc16p": A.CONV_TC16P}[kind_name]
+            kind = {"tc16": A.CONV_TC16, "tc16h3": A.CONV_TC16, "ffma": A.CONV_FFMA, "tc16p": A.CONV_TC16P}[kind_name]
             if kind == A.CONV_TC16P and (co + 15) // 16 * 16 not in (32, 64):
                 continue
             A.set_option("tc_gen", 2 if kind_name == "tc16h3" else 3)

@@ -28,7 +28,7 @@ for relu_in in (False, True):
         A.set_option("tc_flush", flush)
         A.set_option("tc_comp_milli", comp)
         out = torch.zeros(n, h, w, co, device=DEV)
-        run_conv(wt, b, [(xb, ci, 0)], (h, w), A.CONV_TC, [dict(ch0=0, nch=co, dst=out)])
+        run_conv(wt, b, [(xb, ci, 0)], (h, w), A.CONV_TC16, [dict(ch0=0, nch=co, dst=out)])
         got = from_nhwc(out, co).double()
         err = (got - want).flatten(); wv = want.flatten()
         slope = float((err * wv).sum() / (wv * wv).sum())

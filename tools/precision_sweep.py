@@ -17,8 +17,8 @@ for case in ("c32x32_n1_noise", "c64x96_n3", "c256x256_n1"):
     gold = dict(np.load(os.path.join(ROOT, "tests/golden", case + ".npz")))
     x = synth.make_frames(cfg["h"], cfg["w"], 0, cfg["batch"], cfg["smooth"]).to(dev)
     t = torch.tensor(cfg["t"]).reshape(-1, 1).to(dev)
-    for kind, flush, mh, comp in (("ffma", 0, 1, 0), ("tc", 0, 1, 0), ("tc", 2, 1, 0), ("tc", 0, 1, 270), ("tc", 16, 1, 270), ("tc", 8, 1, 270),
-                                  ("tc", 4, 1, 270), ("tc", 2, 1, 270), ("tc", 2, 1, 300), ("tc", 1, 1, 300), ("tc", 8, 1, 240)):
+    for kind, flush, mh, comp in (("ffma", 0, 1, 0), ("tc16", 0, 1, 0), ("tc16", 2, 1, 0), ("tc16", 0, 1, 270), ("tc16", 16, 1, 270), ("tc16", 8, 1, 270),
+                                  ("tc16", 4, 1, 270), ("tc16", 2, 1, 270), ("tc16", 2, 1, 300), ("tc16", 1, 1, 300), ("tc16", 8, 1, 240)):
         A.set_option("tc_flush", flush)
         A.set_option("tc_mask_hi", mh)
         A.set_option("tc_comp_milli", comp)
