@@ -612,7 +612,10 @@ __device__ __forceinline__ void s3_issue(const S3Params& P, uint32_t smem_base, 
 // LEAN: the epilogue of the common ResBlock-type layer only (one full N block of 32 / 64 channels, S16 destination, ReLU or
 // no activation, at most one S16 operand added in place: s3_plan sets P.lean) -- a kernel of its own, so that neither epilogue
 // pays for the other's registers and instruction-cache footprint.
-template <int NMAX, bool DBG, int U, bool PAIR, bool LEAN>
+// LEAN == 2: the same structure for the layers with a transcendental epilogue (tanh / sigmoid / sigmoid x h / GRU update, up to
+// two S16 operands): the GRU convolutions and Ch_Reducer.  A third kernel family rather than a switch inside the ReLU one: the
+// out-of-line activation call in the same store loop cost the ReLU layers 18-30 % (measured).
+template <int NMAX, bool DBG, int U, bool PAIR, int LEAN>
 __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_constant__ S3Params P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -905,8 +908,8 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
     const bool offload = P.offload != 0;
     // lean epilogue (host: s3_plan): one full N block (N == NMAX), one entry, S16 destination, activation none / ReLU, at most
     // one S16 operand in the result tile
-    constexpr bool LEANOK = LEAN;
-    constexpr bool lean = LEAN;
+    constexpr bool LEANOK = LEAN != 0;
+    constexpr bool lean = LEAN != 0;
     const bool lean_relu = (P.lean & 2) != 0, lean_res = (P.lean & 4) != 0;
     const uint32_t lean_c0 = (uint32_t)(grp * HMAX);  // first channel of this thread (N == NMAX: csplit == HMAX)
     const uint32_t lean_bias = bias_s + lean_c0 * 4u;
@@ -1088,7 +1091,29 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
             sts128(base + (((q + 1u) ^ sw) << 4), as_u4(v1));
           }
         };
-        if (LEANOK && lean) {
+        if (LEAN == 2) {
+          // Lean store loop with an activation: as below, plus the operand tiles (h in place, z in the second tile) and the
+          // out-of-line exp / reciprocal expansions
+          const uint32_t info = (uint32_t)P.e_info[e0];
+          const int act = (int)((info >> 3) & 7u), nres = (int)((info >> 6) & 3u);
+          const uint32_t res2_row = lean_row + (uint32_t)P.stg2_off;
+#pragma unroll
+          for (int s8 = 0; s8 < HMAX / 8; ++s8) {
+            const uint32_t o_hi = (((uint32_t)s8 + lean_g0) ^ lean_sw) << 4, o_lo = (((uint32_t)s8 + lean_g0 + 4u) ^ lean_sw) << 4;
+            const float4 b0 = as_f4(lds128(lean_bias + (uint32_t)s8 * 32u)), b1 = as_f4(lds128(lean_bias + (uint32_t)s8 * 32u + 16u));
+            float4 v0 = make_float4(sum[8 * s8] + b0.x, sum[8 * s8 + 1] + b0.y, sum[8 * s8 + 2] + b0.z, sum[8 * s8 + 3] + b0.w);
+            float4 v1 = make_float4(sum[8 * s8 + 4] + b1.x, sum[8 * s8 + 5] + b1.y, sum[8 * s8 + 6] + b1.z, sum[8 * s8 + 7] + b1.w);
+            float4 h0 = make_float4(0.f, 0.f, 0.f, 0.f), h1 = h0, z0 = h0, z1 = h0;
+            if (nres > 0) s16_decode8(lds128(lean_res_row + o_hi), lds128(lean_res_row + o_lo), h0, h1);
+            if (nres > 1) s16_decode8(lds128(res2_row + o_hi), lds128(res2_row + o_lo), z0, z1);
+            v0 = finish4v(act, v0, h0, z0);
+            v1 = finish4v(act, v1, h1, z1);
+            uint4 hi, lo;
+            s16_encode8(v0, v1, hi, lo);
+            sts128(lean_row + o_hi, hi);
+            sts128(lean_row + o_lo, lo);
+          }
+        } else if (LEANOK && lean) {
           // Lean store loop (full block, one entry, S16 destination, ReLU or none, at most one S16 operand updated in place):
           // the thread's pixel row never changes, so its eight chunk addresses of the staging box are computed once per kernel
           // and a step is two bias loads, the adds, the split and two stores -- no address arithmetic, no per-step lookups.
@@ -1253,20 +1278,27 @@ typedef void (*S3KernelFn)(S3Params);
   {conv_s3_kernel<N_, D_, 1, P_, L_>, conv_s3_kernel<N_, D_, 3, P_, L_>, conv_s3_kernel<N_, D_, 5, P_, L_>, conv_s3_kernel<N_, D_, 7, P_, L_>}
 S3KernelFn s3_dbg_kernel(int nidx, int uidx, int pair, int lean);
 S3KernelFn s3_lean_kernel(int nidx, int uidx, int pair);
+S3KernelFn s3_lean2_kernel(int uidx, int pair);  // (64 accumulator channels only)
 #if S3_TU == 1
 S3KernelFn s3_dbg_kernel(int nidx, int uidx, int pair, int lean) {
-  static const S3KernelFn table[4][4] = {S3_ROW(32, true, false, false), S3_ROW(64, true, false, false), S3_ROW(96, true, false, false),
-                                         S3_ROW(128, true, false, false)};
-  static const S3KernelFn ptable[2][4] = {S3_ROW(32, true, true, false), S3_ROW(64, true, true, false)};
-  static const S3KernelFn ltable[2][2][4] = {{S3_ROW(32, true, false, true), S3_ROW(64, true, false, true)},
-                                             {S3_ROW(32, true, true, true), S3_ROW(64, true, true, true)}};
+  static const S3KernelFn table[4][4] = {S3_ROW(32, true, false, 0), S3_ROW(64, true, false, 0), S3_ROW(96, true, false, 0),
+                                         S3_ROW(128, true, false, 0)};
+  static const S3KernelFn ptable[2][4] = {S3_ROW(32, true, true, 0), S3_ROW(64, true, true, 0)};
+  static const S3KernelFn ltable[2][2][4] = {{S3_ROW(32, true, false, 1), S3_ROW(64, true, false, 1)},
+                                             {S3_ROW(32, true, true, 1), S3_ROW(64, true, true, 1)}};
+  if (lean == 2) return s3_lean2_kernel(uidx, pair);  // (no role-timer build of these)
   return lean ? ltable[pair][nidx][uidx] : pair ? ptable[nidx][uidx] : table[nidx][uidx];
 }
 #elif S3_TU == 2
 S3KernelFn s3_lean_kernel(int nidx, int uidx, int pair) {
-  static const S3KernelFn ltable[2][2][4] = {{S3_ROW(32, false, false, true), S3_ROW(64, false, false, true)},
-                                             {S3_ROW(32, false, true, true), S3_ROW(64, false, true, true)}};
+  static const S3KernelFn ltable[2][2][4] = {{S3_ROW(32, false, false, 1), S3_ROW(64, false, false, 1)},
+                                             {S3_ROW(32, false, true, 1), S3_ROW(64, false, true, 1)}};
   return ltable[pair][nidx][uidx];
+}
+#elif S3_TU == 3
+S3KernelFn s3_lean2_kernel(int uidx, int pair) {
+  static const S3KernelFn ltable[2][4] = {S3_ROW(64, false, false, 2), S3_ROW(64, false, true, 2)};
+  return ltable[pair][uidx];
 }
 #else
 // ---- host --------------------------------------------------------------------------------
@@ -1526,6 +1558,11 @@ static int s3_plan(const demfi_conv_t& c, S3Params& P, S3EpiPlan& E, int* smem_o
     if ((g.fmt & DEMFI_SEG_DST_S16) && g.ch0 == 0 && g.nch == c.cout_pad && res_ok && g.store == DEMFI_STORE_NHWC &&
         (g.act == DEMFI_ACT_NONE || g.act == DEMFI_ACT_RELU))
       P.lean = 1 | (g.act == DEMFI_ACT_RELU ? 2 : 0) | (E.e_nres[0] == 1 ? 4 : 0);
+    // the activation variant (kernels of their own, LEAN == 2; 64 channels): tanh / sigmoid / sigmoid x h / GRU, S16 operands
+    const bool ops_ok = (E.e_nres[0] < 1 || (g.fmt & DEMFI_SEG_RES_S16)) && (E.e_nres[0] < 2 || (g.fmt & DEMFI_SEG_RES2_S16));
+    if (P.lean == 0 && c.cout_pad == 64 && (g.fmt & DEMFI_SEG_DST_S16) && g.ch0 == 0 && g.nch == 64 && ops_ok &&
+        g.store == DEMFI_STORE_NHWC && g.act >= DEMFI_ACT_TANH && !(get_option("tc_diag") & 16384))
+      P.lean = 8;
     // The skip operand of a lean layer in a tile of its OWN (pairs: the halved filter bank leaves the room): its load for the
     // next tile is then issued as soon as this tile's store loop has read it, not after the result's TMA store has drained
     // the shared staging tile -- measured, the epilogue waited ~2 kclk per tile for a residual fetched that late from HBM.
@@ -1711,11 +1748,12 @@ int launch_conv_s3(const demfi_conv_t& c, cudaStream_t st) {
   }
   // one kernel per (N block width, issue unit): a single instantiation of the issue loop per kernel keeps its state in
   // uniform registers (a switch over four inlined copies did not)
-  static const S3KernelFn table[4][4] = {S3_ROW(32, false, false, false), S3_ROW(64, false, false, false), S3_ROW(96, false, false, false),
-                                         S3_ROW(128, false, false, false)};
-  static const S3KernelFn ptable[2][4] = {S3_ROW(32, false, true, false), S3_ROW(64, false, true, false)};
+  static const S3KernelFn table[4][4] = {S3_ROW(32, false, false, 0), S3_ROW(64, false, false, 0), S3_ROW(96, false, false, 0),
+                                         S3_ROW(128, false, false, 0)};
+  static const S3KernelFn ptable[2][4] = {S3_ROW(32, false, true, 0), S3_ROW(64, false, true, 0)};
   const int nidx = P.nb_max <= 32 ? 0 : P.nb_max <= 64 ? 1 : P.nb_max <= 96 ? 2 : 3;
-  const S3KernelFn fn = P.dbg != nullptr ? s3_dbg_kernel(nidx, P.unit >> 1, P.pair, P.lean != 0)
+  const S3KernelFn fn = P.dbg != nullptr ? s3_dbg_kernel(nidx, P.unit >> 1, P.pair, P.lean == 8 ? 2 : P.lean != 0)
+                        : P.lean == 8    ? s3_lean2_kernel(P.unit >> 1, P.pair)
                         : P.lean         ? s3_lean_kernel(nidx, P.unit >> 1, P.pair)
                         : P.pair         ? ptable[nidx][P.unit >> 1]
                                          : table[nidx][P.unit >> 1];

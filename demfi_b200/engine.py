@@ -199,9 +199,11 @@ class Engine:
         if stride == 1 and cout_pad in (32, 64) and pair_mode != "0":
             stages = sum((vw.C + 31) // 32 for vw, _ in srcs) * KH * KW
             s16 = self.use_s16 and segs is not None and len(segs) == 1 and segs[0]["dst"].fmt == A.FMT_S16
-            lean = (s16 and segs[0].get("act", A.ACT_NONE) in (A.ACT_NONE, A.ACT_RELU) and segs[0]["nch"] == cout_pad
-                    and (segs[0].get("res") is None or segs[0]["res"].fmt == A.FMT_S16) and segs[0].get("res2") is None
-                    and segs[0].get("store", A.STORE_NHWC) == A.STORE_NHWC)
+            ok_fmt = lambda v_: v_ is None or v_.fmt == A.FMT_S16
+            lean = (s16 and segs[0]["nch"] == cout_pad and ok_fmt(segs[0].get("res")) and ok_fmt(segs[0].get("res2"))
+                    and segs[0].get("store", A.STORE_NHWC) == A.STORE_NHWC
+                    and ((segs[0].get("act", A.ACT_NONE) in (A.ACT_NONE, A.ACT_RELU) and segs[0].get("res2") is None)
+                         or cout_pad == 64))   # (64 channels: the activation variant of the lean kernels covers tanh / sigmoid / GRU)
             if lean or stages >= 40 or pair_mode == "2":
                 return A.CONV_TC16P
         # 97..128 output channels as ONE N block (conv_s3 only: stride 1)
@@ -481,9 +483,16 @@ class Engine:
         ops.append(self.conv(p + "Mixer.conv_blend2", [v["BL1"]], (H, W), B, [full(X, 64, relu)]))
         # SepConvGRU (DeMFInet.py:838-857): z and r share one pass over [h, x]
         for s, k, h0, h1 in (("1", (1, 5), hin, hmid), ("2", (5, 1), hmid, hout)):
-            ops.append(self.conv([p + "GB.convz" + s, p + "GB.convr" + s], [h0, X], (H, W), B,
-                                 [full(Z, 64, sig, ch0=0), full(RH, 64, A.ACT_SIGMOID_MUL, h0, ch0=64)], k=k,
-                                 label=p + "GB.convzr" + s))
+            if self.use_s16 and os.environ.get("DEMFI_GRU_SPLIT", "1") != "0":
+                # z and r as two 64-channel convolutions: each is one full N block, i.e. runs on a CTA pair with the lean
+                # activation epilogue (measured against ONE 128-channel launch on one CTA per tile, which reads [h, x] once
+                # but is bound by its MMA issue and its generic epilogue: profiles/r2_conv_notes.md)
+                ops.append(self.conv(p + "GB.convz" + s, [h0, X], (H, W), B, [full(Z, 64, sig)], k=k))
+                ops.append(self.conv(p + "GB.convr" + s, [h0, X], (H, W), B, [full(RH, 64, A.ACT_SIGMOID_MUL, h0)], k=k))
+            else:
+                ops.append(self.conv([p + "GB.convz" + s, p + "GB.convr" + s], [h0, X], (H, W), B,
+                                     [full(Z, 64, sig, ch0=0), full(RH, 64, A.ACT_SIGMOID_MUL, h0, ch0=64)], k=k,
+                                     label=p + "GB.convzr" + s))
             ops.append(self.conv(p + "GB.convq" + s, [RH, X], (H, W), B, [full(h1, 64, A.ACT_GRU, h0, res2=Z)], k=k))
         ops.append(self.conv(p + "flow_occ.conv1", [hout], (H, W), B, [full(v["FO1"], 32, relu)]))
         ops.append(self.conv(p + "flow_occ.conv2", [v["FO1"]], (H, W), B, [full(DLo, 8, none, DLi)]))

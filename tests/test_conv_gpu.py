@@ -432,6 +432,45 @@ def test_s16_residual_two_sources_n32():
     check(from_nhwc(s16_decode(o2)[..., 96:192], 96), want, "s16 lff dst 2")
 
 
+def test_gru_gates_on_cta_pairs_with_the_lean_activation_epilogue():
+    """z, r and q as 64-channel convolutions on CTA pairs (the engine's form since round 2): sigmoid, sigmoid x h with an S16
+    operand in place, and the GRU update with two S16 operand tiles -- LEAN == 2 kernels"""
+    n, hh, w_ = 2, 40, 56
+    hx = rnd(n, 128, hh, w_, seed=21, scale=0.7)
+    hb, _ = nhwc(hx[:, :64]); xb, _ = nhwc(hx[:, 64:])
+    hs, xs = s16_encode(hb), s16_encode(xb)
+    h_val = s16_decode(hs).permute(0, 3, 1, 2).cpu().double()
+    srcs = [(hs, 64, 0, A.FMT_S16), (xs, 64, 0, A.FMT_S16)]
+    S = A.SEG_DST_S16
+    wz, bz = wb(64, 128, 1, 5, seed=7)
+    wr, br = wb(64, 128, 1, 5, seed=9)
+    Z = torch.zeros(n, hh, w_, 64, device=DEV); RH = torch.zeros(n, hh, w_, 64, device=DEV)
+    run_conv(wz, bz, srcs, (hh, w_), A.CONV_TC16P, [dict(ch0=0, nch=64, dst=Z, act=A.ACT_SIGMOID, fmt=S)])
+    run_conv(wr, br, srcs, (hh, w_), A.CONV_TC16P, [dict(ch0=0, nch=64, dst=RH, act=A.ACT_SIGMOID_MUL, res=hs, fmt=S | A.SEG_RES_S16)])
+    check(from_nhwc(s16_decode(Z), 64), torch.sigmoid(ref_conv(hx, wz, bz)), "pair lean2: z")
+    check(from_nhwc(s16_decode(RH), 64), torch.sigmoid(ref_conv(hx, wr, br)) * h_val, "pair lean2: r*h")
+    wq, bq = wb(64, 128, 5, 1, seed=8)
+    H1 = torch.zeros(n, hh, w_, 64, device=DEV)
+    run_conv(wq, bq, [(RH, 64, 0, A.FMT_S16), (xs, 64, 0, A.FMT_S16)], (hh, w_), A.CONV_TC16P,
+             [dict(ch0=0, nch=64, dst=H1, act=A.ACT_GRU, res=hs, res2=Z, fmt=S | A.SEG_RES_S16 | A.SEG_RES2_S16)])
+    rh_val = s16_decode(RH).permute(0, 3, 1, 2).cpu()
+    z_val = s16_decode(Z).permute(0, 3, 1, 2).cpu().double()
+    q = torch.tanh(ref_conv(torch.cat([rh_val, hx[:, 64:]], 1), wq, bq))
+    check(from_nhwc(s16_decode(H1), 64), (1 - z_val) * h_val + z_val * q, "pair lean2: GRU update")
+    # tanh head with a long K loop (Ch_Reducer's form) on one CTA per tile and on pairs
+    x3 = rnd(1, 192, 24, 40, seed=33)
+    w7, b7 = wb(64, 192, 7, 7, seed=34)
+    s3 = []
+    for i in range(3):
+        bf, _ = nhwc(x3[:, 64 * i:64 * i + 64])
+        s3.append((s16_encode(bf), 64, 0, A.FMT_S16))
+    xq = torch.cat([s16_decode(b_[0]).permute(0, 3, 1, 2).cpu() for b_ in s3], 1)
+    for kind in (A.CONV_TC16, A.CONV_TC16P):
+        o7 = torch.zeros(1, 24, 40, 64, device=DEV)
+        run_conv(w7, b7, s3, (24, 40), kind, [dict(ch0=0, nch=64, dst=o7, act=A.ACT_TANH, fmt=S)])
+        check(from_nhwc(s16_decode(o7), 64), torch.tanh(ref_conv(xq, w7, b7)), f"lean2 tanh 7x7 kind={kind}")
+
+
 @pytest.mark.parametrize("zr_kind", [pytest.param(A.CONV_TC16, id="zr-2x64"), pytest.param(A.CONV_TC16W, id="zr-1x128")])
 def test_s16_gru_epilogues(zr_kind):
     """zr conv: Z = sigmoid (S16 out), RH = sigmoid * h (S16 operand and out); q conv: (1 - z) h + z tanh(q) with S16 h and z.

@@ -122,9 +122,9 @@ def test_cuda_core_only_engine_matches_too(state_dict, golden_meta):
     cfg = golden_meta["cases"][case]["cfg"]
     x, t = case_inputs(cfg)
     gold = load_golden(case)
-    # ffma: CUDA cores only; tc: first-generation 3xTF32 tcgen05 kernel; tc16f32: the default kernels with every buffer in
-    # fp32 (no S16 storage, converter path everywhere); auto (default, S16) is what every other test runs
-    for kind in ("ffma", "tc", "tc16f32"):
+    # ffma: CUDA cores only; tc16f32: the default kernels with every buffer in fp32 (no S16 storage, converter path everywhere);
+    # auto (default, S16) is what every other test runs
+    for kind in ("ffma", "tc16f32"):
         eng = Engine(state_dict, 1, cfg["h"], cfg["w"], DEV, conv_kind=kind)
         res = eng.forward(x.to(DEV), t.to(DEV), cfg["n"])
         torch.cuda.synchronize()

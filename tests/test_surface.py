@@ -70,7 +70,7 @@ def test_plan_builds_on_host_and_accounts_for_every_conv(state_dict):
     # the 2 dead conv_source_k dropped) and the 2 loop-invariant Mixer convs are hoisted in front of the loop.
     assert n_conv == 108 - 10 + 4 + 2
     n_iter = sum(1 for op in e._iter_ops(0, True) if op[0] == "conv")
-    assert n_iter == 27 - 2 - 2  # conv_ref1/2 hoisted; z and r of each GRU half share one launch
+    assert n_iter == 27 - 2  # conv_ref1/2 hoisted (z and r of each GRU half are two 64-channel launches on CTA pairs since round 2)
     with pytest.raises(RuntimeError):
         e.forward(torch.zeros(1, 3, 4, 64, 96), torch.tensor([[0.5]]), 1)
 
@@ -110,7 +110,7 @@ def test_no_convolution_of_the_plan_falls_back_to_a_slower_path(state_dict):
             info = (A.i32 * 16)()
             A.check(lib.demfi_conv_describe(C.byref(op[1]), info), "describe")
             rows.append((op[2], op[1].stride, list(info)))
-    assert len(rows) == 104 + 23
+    assert len(rows) == 104 + 25
     for label, stride, info in rows:
         if stride == 2:
             assert info[0] == 2, label                      # the three UNet encoders: conv_h3
