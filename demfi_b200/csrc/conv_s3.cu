@@ -93,7 +93,8 @@ struct S3Params {
   int all_s16;          // every source is in the S16 format: the converter warps have nothing to do
   int pair;             // CTA-pair kernel (DEMFI_CONV_TC16P)
   int offload;          // the TMA duties of the epilogue (operand fetch, stores) run on a warp of their own (all sources S16)
-  int lean;             // lean epilogue: bit 0 = eligible, bit 1 = ReLU, bit 2 = one S16 operand added in place
+  int lean;             // lean epilogue: bit 0 = eligible, bit 1 = ReLU, bit 2 = one S16 operand; bit 3 = the general variant (LEAN == 2),
+                        // with bit 4 = fp32 destination, bit 5 = fp32 first operand
   int res_sep;          // the operand tile of a lean layer has a tile of its own (fetched one tile ahead by the store warp)
   float comp;
   int diag;
@@ -325,7 +326,9 @@ static __device__ __noinline__ float4 finish4v(int act, float4 v, float4 h, floa
     v.w = (1.0f - z.w) * h.w + z.w * tanh_fast(v.w);
   } else {
     v.x += h.x; v.y += h.y; v.z += h.z; v.w += h.w;
-    if (act == DEMFI_ACT_TANH) {
+    if (act == DEMFI_ACT_RELU) {
+      v.x = fmaxf(v.x, 0.0f); v.y = fmaxf(v.y, 0.0f); v.z = fmaxf(v.z, 0.0f); v.w = fmaxf(v.w, 0.0f);
+    } else if (act == DEMFI_ACT_TANH) {
       v.x = tanh_fast(v.x); v.y = tanh_fast(v.y); v.z = tanh_fast(v.z); v.w = tanh_fast(v.w);
     } else if (act == DEMFI_ACT_SIGMOID) {
       v.x = sigmoid_fast(v.x); v.y = sigmoid_fast(v.y); v.z = sigmoid_fast(v.z); v.w = sigmoid_fast(v.w);
@@ -1097,21 +1100,33 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
           const uint32_t info = (uint32_t)P.e_info[e0];
           const int act = (int)((info >> 3) & 7u), nres = (int)((info >> 6) & 3u);
           const uint32_t res2_row = lean_row + (uint32_t)P.stg2_off;
+          // fp32 destination (the layers that feed the warps: F0 / F1, rF0 / rF1, the FAC-FB encoder output) and / or fp32 operand:
+          // eight channels are two 16-byte chunks of the row instead of one hi + one lo chunk
+          const bool dst_f32 = (P.lean & 16) != 0, res_f32 = (P.lean & 32) != 0;
 #pragma unroll
           for (int s8 = 0; s8 < HMAX / 8; ++s8) {
             const uint32_t o_hi = (((uint32_t)s8 + lean_g0) ^ lean_sw) << 4, o_lo = (((uint32_t)s8 + lean_g0 + 4u) ^ lean_sw) << 4;
+            const uint32_t f_0 = ((2u * ((uint32_t)s8 + lean_g0)) ^ lean_sw) << 4, f_1 = ((2u * ((uint32_t)s8 + lean_g0) + 1u) ^ lean_sw) << 4;
             const float4 b0 = as_f4(lds128(lean_bias + (uint32_t)s8 * 32u)), b1 = as_f4(lds128(lean_bias + (uint32_t)s8 * 32u + 16u));
             float4 v0 = make_float4(sum[8 * s8] + b0.x, sum[8 * s8 + 1] + b0.y, sum[8 * s8 + 2] + b0.z, sum[8 * s8 + 3] + b0.w);
             float4 v1 = make_float4(sum[8 * s8 + 4] + b1.x, sum[8 * s8 + 5] + b1.y, sum[8 * s8 + 6] + b1.z, sum[8 * s8 + 7] + b1.w);
             float4 h0 = make_float4(0.f, 0.f, 0.f, 0.f), h1 = h0, z0 = h0, z1 = h0;
-            if (nres > 0) s16_decode8(lds128(lean_res_row + o_hi), lds128(lean_res_row + o_lo), h0, h1);
+            if (nres > 0) {
+              if (res_f32) { h0 = as_f4(lds128(lean_res_row + f_0)); h1 = as_f4(lds128(lean_res_row + f_1)); }
+              else s16_decode8(lds128(lean_res_row + o_hi), lds128(lean_res_row + o_lo), h0, h1);
+            }
             if (nres > 1) s16_decode8(lds128(res2_row + o_hi), lds128(res2_row + o_lo), z0, z1);
             v0 = finish4v(act, v0, h0, z0);
             v1 = finish4v(act, v1, h1, z1);
-            uint4 hi, lo;
-            s16_encode8(v0, v1, hi, lo);
-            sts128(lean_row + o_hi, hi);
-            sts128(lean_row + o_lo, lo);
+            if (dst_f32) {
+              sts128(lean_row + f_0, as_u4(v0));
+              sts128(lean_row + f_1, as_u4(v1));
+            } else {
+              uint4 hi, lo;
+              s16_encode8(v0, v1, hi, lo);
+              sts128(lean_row + o_hi, hi);
+              sts128(lean_row + o_lo, lo);
+            }
           }
         } else if (LEANOK && lean) {
           // Lean store loop (full block, one entry, S16 destination, ReLU or none, at most one S16 operand updated in place):
@@ -1551,18 +1566,20 @@ static int s3_plan(const demfi_conv_t& c, S3Params& P, S3EpiPlan& E, int* smem_o
   P.offload = (P.tma_epi && P.all_s16 && !(get_option("tc_diag") & 2048)) ? 1 : 0;
   P.lean = 0;
   P.res_sep = 0;
-  if (P.tma_epi && P.n_blocks == 1 && E.nsb == 1 && (c.cout_pad == 32 || c.cout_pad == 64) && E.e_seg[0] >= 0 && !E.e_mixed[0] &&
+  if (P.tma_epi && P.n_blocks == 1 && E.nsb == 1 && (c.cout_pad == 32 || c.cout_pad == 64) && E.e_seg[0] >= 0 &&
       !(get_option("tc_diag") & 4096)) {
     const demfi_seg_t& g = c.seg[E.e_seg[0]];
     const bool res_ok = E.e_nres[0] == 0 || (E.e_nres[0] == 1 && (g.fmt & DEMFI_SEG_RES_S16));
-    if ((g.fmt & DEMFI_SEG_DST_S16) && g.ch0 == 0 && g.nch == c.cout_pad && res_ok && g.store == DEMFI_STORE_NHWC &&
+    if ((g.fmt & DEMFI_SEG_DST_S16) && g.ch0 == 0 && g.nch == c.cout_pad && res_ok && g.store == DEMFI_STORE_NHWC && !E.e_mixed[0] &&
         (g.act == DEMFI_ACT_NONE || g.act == DEMFI_ACT_RELU))
       P.lean = 1 | (g.act == DEMFI_ACT_RELU ? 2 : 0) | (E.e_nres[0] == 1 ? 4 : 0);
     // the activation variant (kernels of their own, LEAN == 2; 64 channels): tanh / sigmoid / sigmoid x h / GRU, S16 operands
-    const bool ops_ok = (E.e_nres[0] < 1 || (g.fmt & DEMFI_SEG_RES_S16)) && (E.e_nres[0] < 2 || (g.fmt & DEMFI_SEG_RES2_S16));
-    if (P.lean == 0 && c.cout_pad == 64 && (g.fmt & DEMFI_SEG_DST_S16) && g.ch0 == 0 && g.nch == 64 && ops_ok &&
-        g.store == DEMFI_STORE_NHWC && g.act >= DEMFI_ACT_TANH && !(get_option("tc_diag") & 16384))
-      P.lean = 8;
+    // (any destination / first-operand format: fp32 rows are written / read as plain 16-byte chunks; a first operand in the other
+    // format than the destination sits in the second tile, as the planner arranged; the GRU's second operand is S16)
+    const bool ops_ok = E.e_nres[0] < 2 || ((g.fmt & DEMFI_SEG_RES2_S16) && (g.fmt & DEMFI_SEG_RES_S16) && (g.fmt & DEMFI_SEG_DST_S16));
+    if (P.lean == 0 && c.cout_pad == 64 && g.ch0 == 0 && g.nch == 64 && ops_ok && g.store == DEMFI_STORE_NHWC &&
+        (g.act >= DEMFI_ACT_TANH || !(g.fmt & DEMFI_SEG_DST_S16) || E.e_mixed[0]) && !(get_option("tc_diag") & 16384))
+      P.lean = 8 | ((g.fmt & DEMFI_SEG_DST_S16) ? 0 : 16) | ((E.e_nres[0] >= 1 && !(g.fmt & DEMFI_SEG_RES_S16)) ? 32 : 0);
     // The skip operand of a lean layer in a tile of its OWN (pairs: the halved filter bank leaves the room): its load for the
     // next tile is then issued as soon as this tile's store loop has read it, not after the result's TMA store has drained
     // the shared staging tile -- measured, the epilogue waited ~2 kclk per tile for a residual fetched that late from HBM.
@@ -1752,8 +1769,8 @@ int launch_conv_s3(const demfi_conv_t& c, cudaStream_t st) {
                                          S3_ROW(128, false, false, 0)};
   static const S3KernelFn ptable[2][4] = {S3_ROW(32, false, true, 0), S3_ROW(64, false, true, 0)};
   const int nidx = P.nb_max <= 32 ? 0 : P.nb_max <= 64 ? 1 : P.nb_max <= 96 ? 2 : 3;
-  const S3KernelFn fn = P.dbg != nullptr ? s3_dbg_kernel(nidx, P.unit >> 1, P.pair, P.lean == 8 ? 2 : P.lean != 0)
-                        : P.lean == 8    ? s3_lean2_kernel(P.unit >> 1, P.pair)
+  const S3KernelFn fn = P.dbg != nullptr ? s3_dbg_kernel(nidx, P.unit >> 1, P.pair, (P.lean & 8) ? 2 : P.lean != 0)
+                        : (P.lean & 8)   ? s3_lean2_kernel(P.unit >> 1, P.pair)
                         : P.lean         ? s3_lean_kernel(nidx, P.unit >> 1, P.pair)
                         : P.pair         ? ptable[nidx][P.unit >> 1]
                                          : table[nidx][P.unit >> 1];

@@ -198,12 +198,19 @@ class Engine:
         pair_mode = os.environ.get("DEMFI_PAIR", "1")
         if stride == 1 and cout_pad in (32, 64) and pair_mode != "0":
             stages = sum((vw.C + 31) // 32 for vw, _ in srcs) * KH * KW
-            s16 = self.use_s16 and segs is not None and len(segs) == 1 and segs[0]["dst"].fmt == A.FMT_S16
-            ok_fmt = lambda v_: v_ is None or v_.fmt == A.FMT_S16
-            lean = (s16 and segs[0]["nch"] == cout_pad and ok_fmt(segs[0].get("res")) and ok_fmt(segs[0].get("res2"))
-                    and segs[0].get("store", A.STORE_NHWC) == A.STORE_NHWC
-                    and ((segs[0].get("act", A.ACT_NONE) in (A.ACT_NONE, A.ACT_RELU) and segs[0].get("res2") is None)
-                         or cout_pad == 64))   # (64 channels: the activation variant of the lean kernels covers tanh / sigmoid / GRU)
+            single = (self.use_s16 and segs is not None and len(segs) == 1 and segs[0]["nch"] == cout_pad
+                      and segs[0].get("store", A.STORE_NHWC) == A.STORE_NHWC)
+            is_s16 = lambda v_: v_ is not None and v_.fmt == A.FMT_S16
+            sg0 = segs[0] if single else {}
+            # the ReLU / none kernels (S16 everywhere) and, for 64 channels, the general lean kernels (any activation, fp32 or S16
+            # destination and first operand; the GRU's two operands S16)
+            lean = single and (
+                (is_s16(sg0["dst"]) and sg0.get("act", A.ACT_NONE) in (A.ACT_NONE, A.ACT_RELU) and sg0.get("res2") is None
+                 and (sg0.get("res") is None or is_s16(sg0["res"])))
+                or (cout_pad == 64 and (sg0.get("res2") is None or (is_s16(sg0["res2"]) and is_s16(sg0.get("res")) and is_s16(sg0["dst"])))
+                    # (not the 1x1 convolutions into fp32 buffers -- FGAC's conv_ref_k / fusion: two MMA stages per tile, all
+                    # epilogue and fp32 conversion; measured 0.45 ms on pairs against 0.27 ms on one CTA per tile)
+                    and (KH * KW > 1 or is_s16(sg0["dst"]))))
             if lean or stages >= 40 or pair_mode == "2":
                 return A.CONV_TC16P
         # 97..128 output channels as ONE N block (conv_s3 only: stride 1)
@@ -363,10 +370,22 @@ class Engine:
         F01 = v["F01"]
         # FO = [occ logit, pad3, flow_01, flow_10]: the order of AGG1's channels 196..203 (UNet input), so that the same eight
         # accumulator channels go to both places from the epilogue (one result, two destinations) -- no copy kernels
-        upnet2_out = list(range(128)) + [132, -1, -1, -1, 128, 129, 130, 131] + [-1] * 8
-        ops.append(self.conv(p + "UPNet.2", [v["U"]], (H, W), B,
-                             [full(F01.frames(0, B), 64, tanh, ch0=0), full(F01.frames(B, B), 64, tanh, ch0=64),
-                              full(v["FO"], 8, none, ch0=128), full(v["AGG1"].ch(196, 8), 8, none, ch0=128)], out_map=upnet2_out))
+        w_u2, b_u2 = self._weight([p + "UPNet.2"])
+        if self.use_s16 and os.environ.get("DEMFI_SPLIT_HEADS", "1") != "0":
+            # three launches instead of one 144-channel convolution with N blocks of 64 / 64 / 16 on one CTA per tile: F0 and F1
+            # (tanh, fp32 destination) are full 64-channel blocks for the CTA-pair kernels with the lean activation epilogue,
+            # the five flow / occlusion channels go to both of their places from a 16-channel launch
+            for f in range(2):
+                ops.append(self.conv([p + f"UPNet.2.F{f}"], [v["U"]], (H, W), B, [full(F01.frames(f * B, B), 64, tanh)],
+                                     wb=(np.ascontiguousarray(w_u2[64 * f:64 * f + 64]), b_u2[64 * f:64 * f + 64])))
+            ops.append(self.conv([p + "UPNet.2.flows"], [v["U"]], (H, W), B,
+                                 [full(v["FO"], 8, none), full(v["AGG1"].ch(196, 8), 8, none)],
+                                 wb=(np.ascontiguousarray(w_u2[128:133]), b_u2[128:133]), out_map=[4, -1, -1, -1, 0, 1, 2, 3] + [-1] * 8))
+        else:
+            upnet2_out = list(range(128)) + [132, -1, -1, -1, 128, 129, 130, 131] + [-1] * 8
+            ops.append(self.conv(p + "UPNet.2", [v["U"]], (H, W), B,
+                                 [full(F01.frames(0, B), 64, tanh, ch0=0), full(F01.frames(B, B), 64, tanh, ch0=64),
+                                  full(v["FO"], 8, none, ch0=128), full(v["AGG1"].ch(196, 8), 8, none, ch0=128)], out_map=upnet2_out))
 
         # ---- FAC_FB (DeMFInet.py:335-358) : shared encoder on [F0;F1], then the two FGAC directions
         p = "FAC_FB_Module."
@@ -414,11 +433,23 @@ class Engine:
         ops.append(self.conv(p + "dec2", [v["UP1"], v["EN1"]], (h, w), B, [full(v["DE2"], 64, relu)]))
         ops.append(("upsample", v["DE2"], v["UP2"]))
         DECIN, DL0 = v["DECIN"], v["DL0"]
-        dec3_out = [5 + c for c in range(64)] + [69 + c for c in range(64)] + [0, 1, 2, 3, 4] + [-1] * 11
-        ops.append(self.conv(p + "dec3", [v["UP2"]], (H, W), B,
-                             [full(DECIN.frames(0, B), 64, tanh, AGG1.ch(0, 64), ch0=0),
-                              full(DECIN.frames(B, B), 64, tanh, AGG1.ch(64, 64), ch0=64),
-                              full(DL0, 8, none, AGG1.ch(192, 8), ch0=128)], out_map=dec3_out))
+        w_d3, b_d3 = self._weight([p + "dec3"])
+        if self.use_s16 and os.environ.get("DEMFI_SPLIT_HEADS", "1") != "0":
+            # as UPNet.2: rF0 and rF1 (tanh of conv + aligned feature, fp32) as two 64-channel launches on CTA pairs, the five
+            # flow / occlusion residuals as a 16-channel launch; reference output order: 5 heads, then rF0, rF1 (DeMFInet.py:596-601)
+            for f in range(2):
+                rows = slice(5 + 64 * f, 5 + 64 * f + 64)
+                ops.append(self.conv([p + f"dec3.rF{f}"], [v["UP2"]], (H, W), B,
+                                     [full(DECIN.frames(f * B, B), 64, tanh, AGG1.ch(64 * f, 64))],
+                                     wb=(np.ascontiguousarray(w_d3[rows]), b_d3[rows])))
+            ops.append(self.conv([p + "dec3.flows"], [v["UP2"]], (H, W), B, [full(DL0, 8, none, AGG1.ch(192, 8))],
+                                 wb=(np.ascontiguousarray(w_d3[0:5]), b_d3[0:5])))
+        else:
+            dec3_out = [5 + c for c in range(64)] + [69 + c for c in range(64)] + [0, 1, 2, 3, 4] + [-1] * 11
+            ops.append(self.conv(p + "dec3", [v["UP2"]], (H, W), B,
+                                 [full(DECIN.frames(0, B), 64, tanh, AGG1.ch(0, 64), ch0=0),
+                                  full(DECIN.frames(B, B), 64, tanh, AGG1.ch(64, 64), ch0=64),
+                                  full(DL0, 8, none, AGG1.ch(192, 8), ch0=128)], out_map=dec3_out))
         A3 = v["A3"]
         ops.append(("bwarp_blend", DECIN.frames(0, B), DECIN.frames(B, B), DL0.ch(0, 4), DL0.ch(4, 1),
                     DECIN.frames(2 * B, B), A3.ch(16, 1)))

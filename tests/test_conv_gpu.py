@@ -457,6 +457,25 @@ def test_gru_gates_on_cta_pairs_with_the_lean_activation_epilogue():
     z_val = s16_decode(Z).permute(0, 3, 1, 2).cpu().double()
     q = torch.tanh(ref_conv(torch.cat([rh_val, hx[:, 64:]], 1), wq, bq))
     check(from_nhwc(s16_decode(H1), 64), (1 - z_val) * h_val + z_val * q, "pair lean2: GRU update")
+    # fp32 destination and fp32 operand in place (UNet dec3: tanh(conv + aligned feature)); S16 operand beside an fp32 destination
+    # (the last FAC-FB ResBlock writes the fp32 SE buffer)
+    xs64 = rnd(2, 64, 40, 56, seed=41)
+    xb64 = s16_encode(nhwc(xs64)[0])
+    xq64 = s16_decode(xb64).permute(0, 3, 1, 2).cpu()
+    w3, b3 = wb(64, 64, 3, 3, seed=42)
+    r32 = rnd(2, 64, 40, 56, seed=43)
+    rb32, _ = nhwc(r32)
+    o32 = torch.zeros(2, 40, 56, 64, device=DEV)
+    run_conv(w3, b3, [(xb64, 64, 0, A.FMT_S16)], (40, 56), A.CONV_TC16P, [dict(ch0=0, nch=64, dst=o32, act=A.ACT_TANH, res=rb32)])
+    check(from_nhwc(o32, 64), torch.tanh(ref_conv(xq64, w3, b3) + r32.double()), "pair lean2: fp32 dst, fp32 operand, tanh")
+    rs16 = s16_encode(rb32)
+    r16v = s16_decode(rs16).permute(0, 3, 1, 2).cpu().double()
+    o32b = torch.zeros(2, 40, 56, 64, device=DEV)
+    run_conv(w3, b3, [(xb64, 64, 0, A.FMT_S16)], (40, 56), A.CONV_TC16P, [dict(ch0=0, nch=64, dst=o32b, res=rs16, fmt=A.SEG_RES_S16)])
+    check(from_nhwc(o32b, 64), ref_conv(xq64, w3, b3) + r16v, "pair lean2: fp32 dst, S16 operand in the second tile")
+    o32c = torch.zeros(2, 40, 56, 64, device=DEV)
+    run_conv(w3, b3, [(nhwc(xs64)[0], 64, 0)], (40, 56), A.CONV_TC16P, [dict(ch0=0, nch=64, dst=o32c, act=A.ACT_RELU)])
+    check(from_nhwc(o32c, 64), F.relu(ref_conv(xs64, w3, b3)), "pair lean2: fp32 source and destination, relu")
     # tanh head with a long K loop (Ch_Reducer's form) on one CTA per tile and on pairs
     x3 = rnd(1, 192, 24, 40, seed=33)
     w7, b7 = wb(64, 192, 7, 7, seed=34)
