@@ -1583,7 +1583,7 @@ static int s3_plan(const demfi_conv_t& c, S3Params& P, S3EpiPlan& E, int* smem_o
     // The skip operand of a lean layer in a tile of its OWN (pairs: the halved filter bank leaves the room): its load for the
     // next tile is then issued as soon as this tile's store loop has read it, not after the result's TMA store has drained
     // the shared staging tile -- measured, the epilogue waited ~2 kclk per tile for a residual fetched that late from HBM.
-    if ((P.lean & 4) && P.offload && P.pair && !(get_option("tc_diag") & 8192)) {
+    if (P.lean != 0 && E.e_nres[0] == 1 && P.offload && P.pair && !(get_option("tc_diag") & 8192)) {
       P.res_sep = 1;
       E.e_mixed[0] = 1;
       E.any_res2 = true;
