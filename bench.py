@@ -382,8 +382,11 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def run_clip_workload(args):
-    """BASELINE config 3 as written: ONE 64-frame 1280x720 clip (61 frame pairs x 7 time indices = 427 interpolated frames)
+def run_clip_workload(args, H0=H0, W0=W0, MFI=MFI, N_TST=N_TST, label="BASELINE config 3"):
+    """BASELINE config 5 (--workload 4k) is the same loop on a 3840x2160 clip, x16 MFI, N_tst = 5: the whole reflect-padded frame
+    (3840x2176) is one engine call per interpolated frame -- the reference tiles 4K frames for memory (utils.py:1757-1798); here the
+    liveness-planned workspace of a whole 4K frame takes ~65 GB of the 180 GB, so the sharding is by frame pair only.
+    BASELINE config 3 as written: ONE 64-frame 1280x720 clip (61 frame pairs x 7 time indices = 427 interpolated frames)
     sharded over the ranks -- strong scaling.  The clip sits in pinned host memory on every rank; a rank copies the frames of
     its pairs to the device as it goes, reuses the t-independent prefix across the time indices of a pair and copies every
     interpolated frame back to pinned host memory.  Timed from a barrier to the last rank done (device events, max over ranks).
@@ -456,9 +459,10 @@ def run_clip_workload(args):
         print(json.dumps({"metric": "interpolated_frames_per_sec", "value": round(float(tot) / (float(ms) / 1e3), 3), "unit": "frames/s",
                           "n_gpus": world, "steps": 1, "warmup": 3, "ms_per_step": round(float(ms), 1), "higher_is_better": True,
                           "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                          "config": {"workload": f"BASELINE config 3: one {F_}-frame {W0}x{H0} clip, x{MFI} MFI, N_tst={N_TST}: {len(pairs)} pairs x "
+                          "config": {"workload": f"{label}: one {F_}-frame {W0}x{H0} clip, x{MFI} MFI, N_tst={N_TST}: {len(pairs)} pairs x "
                                                  f"{len(ts)} t = {int(tot)} interpolated frames, pairs sharded over {world} rank(s), prefix reused "
                                                  f"within a pair, host frames in / host frames out", "balance_tail": bool(args.balance),
+                                     "workspace_GB": round(max(e.workspace_bytes() for e in net._engines.values()) / 1e9, 2),
                                      "units_per_rank_max": max(sum(len(js) for _, js in schedule_units(pairs, len(ts), r, world, bool(args.balance)))
                                                                for r in range(world))}}), flush=True)
     if world > 1:
@@ -480,15 +484,20 @@ def main():
     ap.add_argument("--steps", type=int, default=14)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="mfi", choices=["mfi", "clip", "train"],
-                    help="mfi: BASELINE's headline (default); clip: config 3 (one clip, strong scaling); train: config 4 (training step)")
-    ap.add_argument("--frames", type=int, default=64, help="--workload clip: frames in the clip")
+    ap.add_argument("--workload", default="mfi", choices=["mfi", "clip", "train", "4k"],
+                    help="mfi: BASELINE's headline (default); clip: config 3 (one clip, strong scaling); train: config 4 (training step); "
+                         "4k: config 5 (3840x2160 clip, x16 MFI, N_tst = 5, whole frames, pairs sharded over the ranks)")
+    ap.add_argument("--frames", type=int, default=0, help="--workload clip / 4k: frames in the clip (default 64 / 11)")
     ap.add_argument("--balance", type=int, default=1, help="--workload clip: cut the last round's pairs into (pair, t) units")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "clip":
+        args.frames = args.frames or 64
         run_clip_workload(args)
+    elif args.workload == "4k":
+        args.frames = args.frames or 11
+        run_clip_workload(args, H0=2160, W0=3840, MFI=16, N_TST=5, label="BASELINE config 5 (4K, whole frames, no tiler)")
     elif args.workload == "train":
         run_train_workload(args)
     else:

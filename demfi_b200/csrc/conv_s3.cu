@@ -53,7 +53,7 @@ constexpr int S3_MAX_NA = 6;   // halo-tile buffers (3 in general; up to 6 for 1
 constexpr int S3_MAX_NS = 8;   // weight ring
 constexpr int S3_BOX_BYTES = S3_BM * 128;  // one 32-channel staging box
 constexpr int S3_BAR_PEER = 3 * S3_MAX_NA + 4 + 2 + 2 * S3_MAX_NS;      // CTA pair: peerA[MAX_NA], peerW, peerB[MAX_NS] (leader's copies)
-constexpr int S3_NBARS = S3_BAR_PEER + S3_MAX_NA + 1 + S3_MAX_NS;
+constexpr int S3_NBARS = S3_BAR_PEER + S3_MAX_NA + 1 + S3_MAX_NS + 1;  // (+ the second operand-tile barrier, the last one)
 constexpr int S3_MAX_E = 8;    // epilogue plan entries (N blocks x sub-blocks)
 constexpr int S3_MAX_O = 8;    // destination tensor maps
 constexpr int S3_MAX_OL = 16;  // (entry, destination) pairs
@@ -95,7 +95,8 @@ struct S3Params {
   int offload;          // the TMA duties of the epilogue (operand fetch, stores) run on a warp of their own (all sources S16)
   int lean;             // lean epilogue: bit 0 = eligible, bit 1 = ReLU, bit 2 = one S16 operand; bit 3 = the general variant (LEAN == 2),
                         // with bit 4 = fp32 destination, bit 5 = fp32 first operand
-  int res_sep;          // the operand tile of a lean layer has a tile of its own (fetched one tile ahead by the store warp)
+  int res_sep;          // 1: the operand tile of a lean layer has a tile of its own (fetched one tile ahead by the store warp);
+                        // 2: two tiles used in turn, each holding a tile's operand and then, in place, its result (operand fetched TWO tiles ahead)
   float comp;
   int diag;
   long long* dbg;
@@ -316,7 +317,7 @@ __device__ __forceinline__ void split2(float a0, float a1, uint32_t& hi, uint32_
 __device__ __forceinline__ float sigmoid_fast(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
 __device__ __forceinline__ float tanh_fast(float v) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * v)); }
 // v = accumulator + bias; h = first operand (residual / GRU h; zeros when absent); z = second operand (GRU z)
-static __device__ __noinline__ float4 finish4v(int act, float4 v, float4 h, float4 z) {
+__device__ __forceinline__ float4 finish4_inl(int act, float4 v, float4 h, float4 z) {
   if (act == DEMFI_ACT_SIGMOID_MUL) {  // r * h (DeMFInet.py:846-847)
     v.x = sigmoid_fast(v.x) * h.x; v.y = sigmoid_fast(v.y) * h.y; v.z = sigmoid_fast(v.z) * h.z; v.w = sigmoid_fast(v.w) * h.w;
   } else if (act == DEMFI_ACT_GRU) {  // (1 - z) h + z tanh(q) (DeMFInet.py:847-848)
@@ -336,6 +337,7 @@ static __device__ __noinline__ float4 finish4v(int act, float4 v, float4 h, floa
   }
   return v;
 }
+static __device__ __noinline__ float4 finish4v(int act, float4 v, float4 h, float4 z) { return finish4_inl(act, v, h, z); }
 __device__ __forceinline__ float4 as_f4(uint4 u) {
   return make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
 }
@@ -634,6 +636,7 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
   auto bar_tempty = [&](int a) { return bars + 8u * (uint32_t)(3 * S3_MAX_NA + 2 + a); };
   const uint32_t bar_wfull = bars + 8u * (uint32_t)(3 * S3_MAX_NA + 4);
   const uint32_t bar_resfull = bars + 8u * (uint32_t)(3 * S3_MAX_NA + 5);
+  const uint32_t bar_resfull1 = bars + 8u * (uint32_t)(S3_NBARS - 1);  // operand of the odd tiles (P.res_sep == 2)
   auto bar_bfull = [&](int s) { return bars + 8u * (uint32_t)(3 * S3_MAX_NA + 6 + s); };
   auto bar_bfree = [&](int s) { return bars + 8u * (uint32_t)(3 * S3_MAX_NA + 6 + S3_MAX_NS + s); };
   auto bar_peer = [&](int i) { return bars + 8u * (uint32_t)(S3_BAR_PEER + i); };
@@ -665,6 +668,7 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
       for (int i = 0; i < S3_MAX_NA + 1 + S3_MAX_NS; ++i) mbar_init(bar_peer(i), 1);
     mbar_init(bar_wfull, 1);
     mbar_init(bar_resfull, 1);
+    mbar_init(bar_resfull1, 1);
     for (int s = 0; s < S3_MAX_NS; ++s) {
       mbar_init(bar_bfull(s), 1);
       mbar_init(bar_bfree(s), 1);
@@ -704,26 +708,26 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
   // shared-memory reads for as long again, and on an epilogue warp both delay that warp's next accumulator drain, i.e. the
   // hand-over every MMA of the next tile but one waits for (measured: 1.4-2 kclk per tile on the critical warp).
   const uint32_t stg_base = smem_base + (uint32_t)P.stg_off;
-  auto epi_fetch = [&](int nb, int tx0, int ty0, int n, int nboxes) {
+  auto epi_fetch = [&](int nb, int tx0, int ty0, int n, int nboxes, uint32_t xoff, uint32_t rbar) {
     const bool pb = P.nsb > 1;
     const int e0 = nb * P.nsb, ne = pb ? nboxes : 1;
     uint32_t tx = 0;
     for (int sb = 0; sb < ne; ++sb) tx += (uint32_t)(P.e_nres[e0 + sb] * (pb ? 1 : nboxes) * S3_BOX_BYTES);
     if (tx == 0) return;
-    mbar_arrive_expect_tx(bar_resfull, tx);
+    mbar_arrive_expect_tx(rbar, tx);
     for (int sb = 0; sb < ne; ++sb) {
       const int e = e0 + sb, nr = P.e_nres[e];
       if (nr == 0) continue;
       const int sg = P.e_seg[e];
       const int b0 = pb ? sb : 0, b1 = pb ? sb + 1 : nboxes;
       for (int b = b0; b < b1; ++b) {
-        tma_load_4d(stg_base + (uint32_t)(P.e_roff[e] + b * S3_BOX_BYTES), &P.rmap[sg], bar_resfull, P.e_rc0[e] + 32 * (b - b0), tx0, ty0, n);
+        tma_load_4d(stg_base + xoff + (uint32_t)(P.e_roff[e] + b * S3_BOX_BYTES), &P.rmap[sg], rbar, P.e_rc0[e] + 32 * (b - b0), tx0, ty0, n);
         if (nr > 1)
-          tma_load_4d(stg_base + (uint32_t)(P.stg2_off + b * S3_BOX_BYTES), &P.r2map[sg], bar_resfull, P.e_rc0[e] + 32 * (b - b0), tx0, ty0, n);
+          tma_load_4d(stg_base + (uint32_t)(P.stg2_off + b * S3_BOX_BYTES), &P.r2map[sg], rbar, P.e_rc0[e] + 32 * (b - b0), tx0, ty0, n);
       }
     }
   };
-  auto epi_store = [&](int nb, int tx0, int ty0, int n, int nboxes) {
+  auto epi_store = [&](int nb, int tx0, int ty0, int n, int nboxes, uint32_t xoff) {
     const bool pb = P.nsb > 1;
     const int e0 = nb * P.nsb, ne = pb ? nboxes : 1;
     for (int sb = 0; sb < ne; ++sb) {
@@ -732,7 +736,7 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
       const int b0 = pb ? sb : 0, b1 = pb ? sb + 1 : nboxes;
       for (int j = P.e_o0[e]; j < P.e_o0[e] + P.e_on[e]; ++j)
         for (int b = b0; b < b1; ++b)
-          tma_store_4d(&P.omap[P.ol_map[j]], stg_base + (uint32_t)(b * S3_BOX_BYTES), P.ol_c0[j] + 32 * (b - b0), tx0, ty0, n);
+          tma_store_4d(&P.omap[P.ol_map[j]], stg_base + xoff + (uint32_t)(b * S3_BOX_BYTES), P.ol_c0[j] + 32 * (b - b0), tx0, ty0, n);
     }
     bulk_commit();
   };
@@ -799,15 +803,59 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
           const TilePos q = pos_of(tile);
           if (lane == 0) {
             if (pending) bulk_wait_read0();
-            if (!q.dummy) epi_fetch(q.nb, q.tx0, q.ty0, q.n, q.nboxes);
+            if (!q.dummy) epi_fetch(q.nb, q.tx0, q.ty0, q.n, q.nboxes, 0u, bar_resfull);
           }
           __syncwarp();
           asm volatile("bar.arrive 2, %0;" ::"n"(S3_EPI_THREADS + 32) : "memory");
           asm volatile("bar.sync 3, %0;" ::"n"(S3_EPI_THREADS + 32) : "memory");
           if (lane == 0 && !q.dummy) {
-            epi_store(q.nb, q.tx0, q.ty0, q.n, q.nboxes);
+            epi_store(q.nb, q.tx0, q.ty0, q.n, q.nboxes, 0u);
             pending = true;
           }
+        }
+      } else if (P.res_sep == 2) {
+        // Two tiles X0 / X1 used in turn: tile k of this CTA finds its operand in X(k & 1), adds its result IN PLACE and the
+        // TMA store reads it from there.  The operand of tile k + 2 is requested as soon as the store of tile k has drained
+        // X(k & 1) -- a whole tile ahead of its use (with ONE operand tile the request went out ~0.7 kclk before the store
+        // loop needed it: role timers, 2.5 kclk of every 8.2 kclk tile of a ResBlock conv2 waited for it), and neither that
+        // drain nor the request sits between two store loops any more: barrier 2 is released right after the store is issued.
+        auto prefetch = [&](const TilePos& q) {
+          if (!q.dummy)
+            for (int b = 0; b < q.nboxes; ++b) tma_prefetch_4d(&P.rmap[P.e_seg[0]], P.e_rc0[0] + 32 * b, q.tx0, q.ty0, q.n);
+        };
+        const uint32_t x1 = (uint32_t)P.stg2_off;
+        uint32_t xoff = 0;
+        if (lane == 0) {
+          if (tile0 < tend) {
+            const TilePos q = pos_of(tile0);
+            if (!q.dummy) epi_fetch(q.nb, q.tx0, q.ty0, q.n, q.nboxes, 0u, bar_resfull);
+          }
+          if (tile0 + tstep < tend) {
+            const TilePos q = pos_of(tile0 + tstep);
+            if (!q.dummy) epi_fetch(q.nb, q.tx0, q.ty0, q.n, q.nboxes, x1, bar_resfull1);
+          }
+          if (tile0 + 2 * tstep < tend) prefetch(pos_of(tile0 + 2 * tstep));
+        }
+        __syncwarp();
+        if (tile0 < tend) asm volatile("bar.arrive 2, %0;" ::"n"(S3_EPI_THREADS + 32) : "memory");
+        for (int tile = tile0; tile < tend; tile += tstep) {
+          const TilePos q = pos_of(tile);
+          asm volatile("bar.sync 3, %0;" ::"n"(S3_EPI_THREADS + 32) : "memory");
+          if (lane == 0 && !q.dummy) {
+            epi_store(q.nb, q.tx0, q.ty0, q.n, q.nboxes, xoff);
+            pending = true;
+          }
+          __syncwarp();
+          // the next tile works in the OTHER buffer: drained and re-filled during the previous iteration
+          if (tile + tstep < tend) asm volatile("bar.arrive 2, %0;" ::"n"(S3_EPI_THREADS + 32) : "memory");
+          if (lane == 0 && tile + 2 * tstep < tend) {
+            if (pending) bulk_wait_read0();
+            const TilePos qn = pos_of(tile + 2 * tstep);
+            if (!qn.dummy) epi_fetch(qn.nb, qn.tx0, qn.ty0, qn.n, qn.nboxes, xoff, xoff ? bar_resfull1 : bar_resfull);
+            if (tile + 3 * tstep < tend) prefetch(pos_of(tile + 3 * tstep));
+          }
+          __syncwarp();
+          xoff ^= x1;
         }
       } else {
         // operand tile of its own: fetched for the NEXT tile right after this tile's store loop is through with it (barrier
@@ -818,7 +866,7 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
         };
         if (tile0 < tend && lane == 0) {
           const TilePos q = pos_of(tile0);
-          if (!q.dummy) epi_fetch(q.nb, q.tx0, q.ty0, q.n, q.nboxes);
+          if (!q.dummy) epi_fetch(q.nb, q.tx0, q.ty0, q.n, q.nboxes, 0u, bar_resfull);
           if (tile0 + tstep < tend) prefetch(pos_of(tile0 + tstep));
         }
         __syncwarp();
@@ -829,12 +877,12 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
           asm volatile("bar.sync 3, %0;" ::"n"(S3_EPI_THREADS + 32) : "memory");
           if (lane == 0) {
             if (!q.dummy) {
-              epi_store(q.nb, q.tx0, q.ty0, q.n, q.nboxes);
+              epi_store(q.nb, q.tx0, q.ty0, q.n, q.nboxes, 0u);
               pending = true;
             }
             if (more) {
               const TilePos qn = pos_of(tile + tstep);
-              if (!qn.dummy) epi_fetch(qn.nb, qn.tx0, qn.ty0, qn.n, qn.nboxes);
+              if (!qn.dummy) epi_fetch(qn.nb, qn.tx0, qn.ty0, qn.n, qn.nboxes, 0u, bar_resfull);
               if (tile + 2 * tstep < tend) prefetch(pos_of(tile + 2 * tstep));
             }
             if (pending) bulk_wait_read0();
@@ -894,7 +942,9 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
     const int m = wq * 32 + lane;
     constexpr int HMAX = (NMAX / 2 + 15) / 16 * 16;
     int acc = 0;
-    uint32_t acc_phase = 0, res_phase = 0;
+    uint32_t acc_phase = 0, res_phase = 0, res_phase1 = 0;
+    const bool res_alt = LEAN == 1 && P.res_sep == 2;  // operand and result share one of two tiles, used in turn (store warp)
+    uint32_t xoff = 0;                                  // this tile's: 0 or P.stg2_off
     long long w_tfull = 0, w_store = 0, w_ld = 0, w_arr = 0, w_s1 = 0, w_s2 = 0, w_s3 = 0, w_top = 0;
     const long long t_begin = dbg ? clock64() : 0;
     const uint32_t stg = smem_base + (uint32_t)P.stg_off;
@@ -917,9 +967,9 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
     const uint32_t lean_c0 = (uint32_t)(grp * HMAX);  // first channel of this thread (N == NMAX: csplit == HMAX)
     const uint32_t lean_bias = bias_s + lean_c0 * 4u;
     // the thread's pixel row never changes: row of its staging box, swizzle key, first 16-byte chunk
-    const uint32_t lean_row = stg + (uint32_t)m * 128u + (lean_c0 >> 5) * (uint32_t)S3_BOX_BYTES;
+    const uint32_t lean_row0 = stg + (uint32_t)m * 128u + (lean_c0 >> 5) * (uint32_t)S3_BOX_BYTES;
     const uint32_t lean_sw = (uint32_t)m & 7u, lean_g0 = (lean_c0 & 31u) >> 3;
-    const uint32_t lean_res_row = lean_row + (uint32_t)P.e_roff[0];  // the skip operand: in place, or in the operand tile of its own
+    const uint32_t lean_res_row0 = lean_row0 + (uint32_t)P.e_roff[0];  // the skip operand: in place, or in the operand tile of its own
     const bool per_box = P.nsb > 1;  // entries are 32-channel boxes (else one entry per N block)
     for (int tile = tile0; tile < tend; tile += tstep) {
       const bool dummy = PAIR && tile >= P.ntiles;  // (odd tile count: the pair's second tile does not exist)
@@ -946,7 +996,7 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
         // the staging buffers are free once the previous tile's stores have read them; then fetch the operand tiles
         if (e_tid == 0) {
           if (store_pending) bulk_wait_read0();
-          if (nres_any > 0) epi_fetch(nb, tx0, ty0, n, nboxes);
+          if (nres_any > 0) epi_fetch(nb, tx0, ty0, n, nboxes, 0u, bar_resfull);
         }
         store_pending = true;
       }
@@ -1037,8 +1087,13 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
         // ---- staged epilogue: bias, operands, activation -> swizzled box layout -> TMA store ----
         if (offload) asm volatile("bar.sync 2, %0;" ::"n"(S3_EPI_THREADS + 32) : "memory");  // the store warp released the staging tile
         if (nres_any > 0) {
-          mbar_wait(bar_resfull, res_phase);
-          res_phase ^= 1u;
+          if (res_alt && xoff != 0u) {
+            mbar_wait(bar_resfull1, res_phase1);
+            res_phase1 ^= 1u;
+          } else {
+            mbar_wait(bar_resfull, res_phase);
+            res_phase ^= 1u;
+          }
         } else if (!offload) {
           asm volatile("bar.sync 2, %0;" ::"n"(S3_EPI_THREADS) : "memory");  // staging buffer released (thread 0 waited)
         }
@@ -1094,11 +1149,17 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
             sts128(base + (((q + 1u) ^ sw) << 4), as_u4(v1));
           }
         };
-        if (LEAN == 2) {
+        if (LEAN >= 2) {
           // Lean store loop with an activation: as below, plus the operand tiles (h in place, z in the second tile) and the
           // out-of-line exp / reciprocal expansions
           const uint32_t info = (uint32_t)P.e_info[e0];
-          const int act = (int)((info >> 3) & 7u), nres = (int)((info >> 6) & 3u);
+          // LEAN >= 3: the activation LEAN - 3 is a compile-time constant and its expansion inline (kernels of their own for the
+          // layers of the network, s3_lean2_act_kernel).  Role timers on the run-time-activation kernel: 5.6 kclk per tile in this
+          // loop against 2.0 kclk for the ReLU kernels, whatever the activation (a 1x1 with none: 5.6) -- the out-of-line call per
+          // four channels (the thread's 32 partial sums live across 16 calls), not the exp / reciprocal, was the cost.
+          const int act = LEAN >= 3 ? LEAN - 3 : (int)((info >> 3) & 7u);
+          const int nres = (int)((info >> 6) & 3u);
+          const uint32_t lean_row = lean_row0, lean_res_row = lean_res_row0;
           const uint32_t res2_row = lean_row + (uint32_t)P.stg2_off;
           // fp32 destination (the layers that feed the warps: F0 / F1, rF0 / rF1, the FAC-FB encoder output) and / or fp32 operand:
           // eight channels are two 16-byte chunks of the row instead of one hi + one lo chunk
@@ -1116,8 +1177,13 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
               else s16_decode8(lds128(lean_res_row + o_hi), lds128(lean_res_row + o_lo), h0, h1);
             }
             if (nres > 1) s16_decode8(lds128(res2_row + o_hi), lds128(res2_row + o_lo), z0, z1);
-            v0 = finish4v(act, v0, h0, z0);
-            v1 = finish4v(act, v1, h1, z1);
+            if (LEAN >= 3) {
+              v0 = finish4_inl(act, v0, h0, z0);
+              v1 = finish4_inl(act, v1, h1, z1);
+            } else {
+              v0 = finish4v(act, v0, h0, z0);
+              v1 = finish4v(act, v1, h1, z1);
+            }
             if (dst_f32) {
               sts128(lean_row + f_0, as_u4(v0));
               sts128(lean_row + f_1, as_u4(v1));
@@ -1132,6 +1198,8 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
           // Lean store loop (full block, one entry, S16 destination, ReLU or none, at most one S16 operand updated in place):
           // the thread's pixel row never changes, so its eight chunk addresses of the staging box are computed once per kernel
           // and a step is two bias loads, the adds, the split and two stores -- no address arithmetic, no per-step lookups.
+          const uint32_t lean_row = lean_row0 + xoff;                           // (res_alt: the tile of this turn)
+          const uint32_t lean_res_row = res_alt ? lean_row : lean_res_row0;    // ... whose operand is updated in place
 #pragma unroll
           for (int s8 = 0; s8 < HMAX / 8; ++s8) {
             const float4 b0 = as_f4(lds128(lean_bias + (uint32_t)s8 * 32u)), b1 = as_f4(lds128(lean_bias + (uint32_t)s8 * 32u + 16u));
@@ -1174,7 +1242,7 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
         }
         if (dbg) w_s2 += clock64() - t_s2;
         const long long t_s3 = dbg ? clock64() : 0;
-        if (!offload && e_tid == 0 && !dummy && !(P.diag & (1 | 32))) epi_store(nb, tx0, ty0, n, nboxes);
+        if (!offload && e_tid == 0 && !dummy && !(P.diag & (1 | 32))) epi_store(nb, tx0, ty0, n, nboxes, 0u);
         if (dbg) w_s3 += clock64() - t_s3;
       } else if (valid && !(P.diag & 1)) {
         const int ch_lo = n0 + cbeg, ch_hi = ch_lo + cnum;
@@ -1193,6 +1261,7 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
         }
       }
       if (dbg) w_store += clock64() - t_store;
+      if (res_alt) xoff ^= (uint32_t)P.stg2_off;
     }
     if (P.tma_epi && !offload && e_tid == 0 && store_pending) bulk_wait0();  // stores complete before the CTA exits
     if (dbg && e_tid == 0) {
@@ -1294,6 +1363,7 @@ typedef void (*S3KernelFn)(S3Params);
 S3KernelFn s3_dbg_kernel(int nidx, int uidx, int pair, int lean);
 S3KernelFn s3_lean_kernel(int nidx, int uidx, int pair);
 S3KernelFn s3_lean2_kernel(int uidx, int pair);  // (64 accumulator channels only)
+S3KernelFn s3_lean2_act_kernel(int uidx, int pair, int act);  // activation at compile time: the network's layers; else nullptr
 #if S3_TU == 1
 S3KernelFn s3_dbg_kernel(int nidx, int uidx, int pair, int lean) {
   static const S3KernelFn table[4][4] = {S3_ROW(32, true, false, 0), S3_ROW(64, true, false, 0), S3_ROW(96, true, false, 0),
@@ -1301,7 +1371,8 @@ S3KernelFn s3_dbg_kernel(int nidx, int uidx, int pair, int lean) {
   static const S3KernelFn ptable[2][4] = {S3_ROW(32, true, true, 0), S3_ROW(64, true, true, 0)};
   static const S3KernelFn ltable[2][2][4] = {{S3_ROW(32, true, false, 1), S3_ROW(64, true, false, 1)},
                                              {S3_ROW(32, true, true, 1), S3_ROW(64, true, true, 1)}};
-  if (lean == 2) return s3_lean2_kernel(uidx, pair);  // (no role-timer build of these)
+  static const S3KernelFn l2table[2][4] = {S3_ROW(64, true, false, 2), S3_ROW(64, true, true, 2)};
+  if (lean == 2) return l2table[pair][uidx];
   return lean ? ltable[pair][nidx][uidx] : pair ? ptable[nidx][uidx] : table[nidx][uidx];
 }
 #elif S3_TU == 2
@@ -1314,6 +1385,21 @@ S3KernelFn s3_lean_kernel(int nidx, int uidx, int pair) {
 S3KernelFn s3_lean2_kernel(int uidx, int pair) {
   static const S3KernelFn ltable[2][4] = {S3_ROW(64, false, false, 2), S3_ROW(64, false, true, 2)};
   return ltable[pair][uidx];
+}
+#elif S3_TU == 4
+S3KernelFn s3_lean2_act_kernel(int uidx, int pair, int act) {
+  // (issue unit, pair, activation) of the layers the engine builds: GRU z / r / q (1x5 and 5x1 on pairs), Ch_Reducer (7x7, tanh),
+  // the tanh feature heads of UPNet.2 / UNet dec3 and the FAC-FB encoder output (3x3 on pairs), FGAC's 1x1s (one CTA per tile)
+  if (pair && uidx == 2) {
+    if (act == DEMFI_ACT_SIGMOID) return conv_s3_kernel<64, false, 5, true, 3 + DEMFI_ACT_SIGMOID>;
+    if (act == DEMFI_ACT_SIGMOID_MUL) return conv_s3_kernel<64, false, 5, true, 3 + DEMFI_ACT_SIGMOID_MUL>;
+    if (act == DEMFI_ACT_GRU) return conv_s3_kernel<64, false, 5, true, 3 + DEMFI_ACT_GRU>;
+  }
+  if (pair && uidx == 3 && act == DEMFI_ACT_TANH) return conv_s3_kernel<64, false, 7, true, 3 + DEMFI_ACT_TANH>;
+  if (pair && uidx == 1 && act == DEMFI_ACT_TANH) return conv_s3_kernel<64, false, 3, true, 3 + DEMFI_ACT_TANH>;
+  if (pair && uidx == 1 && act == DEMFI_ACT_NONE) return conv_s3_kernel<64, false, 3, true, 3 + DEMFI_ACT_NONE>;
+  if (!pair && uidx == 0 && act == DEMFI_ACT_NONE) return conv_s3_kernel<64, false, 1, false, 3 + DEMFI_ACT_NONE>;
+  return nullptr;
 }
 #else
 // ---- host --------------------------------------------------------------------------------
@@ -1587,6 +1673,8 @@ static int s3_plan(const demfi_conv_t& c, S3Params& P, S3EpiPlan& E, int* smem_o
       P.res_sep = 1;
       E.e_mixed[0] = 1;
       E.any_res2 = true;
+      // ReLU / none kernels with an S16 operand (the ResBlock conv2): the two tiles take turns, operand and result in place
+      if ((P.lean & 1) && (P.lean & 4) && !(get_option("tc_diag") & 32768)) P.res_sep = 2;
     }
   }
   // second staging tile (operands that cannot share the result tile): only as many boxes as its last user needs
@@ -1612,6 +1700,10 @@ static int s3_plan(const demfi_conv_t& c, S3Params& P, S3EpiPlan& E, int* smem_o
       P.e_roff[e] = E.e_mixed[e] ? box_bytes_all : 0;
       P.e_info[e] = E.e_seg[e] < 0 ? 0 : (c.seg[E.e_seg[e]].fmt & 7) | (c.seg[E.e_seg[e]].act << 3) | (E.e_nres[e] << 6) | (E.e_mixed[e] ? 256 : 0);
       if (E.e_seg[e] >= 0) P.e_rc0[e] = E.e_c0[e] - c.seg[E.e_seg[e]].ch0;
+    }
+    if (P.res_sep == 2) {  // the operand lands in the tile of its turn (the store warp adds 0 / stg2_off), not in a tile of its own
+      P.e_roff[0] = 0;
+      P.e_info[0] &= ~256;
     }
     for (int j = 0; j < E.n_ol; ++j) {
       const demfi_seg_t& g = c.seg[E.ol_seg[j]];
@@ -1769,7 +1861,11 @@ int launch_conv_s3(const demfi_conv_t& c, cudaStream_t st) {
                                          S3_ROW(128, false, false, 0)};
   static const S3KernelFn ptable[2][4] = {S3_ROW(32, false, true, 0), S3_ROW(64, false, true, 0)};
   const int nidx = P.nb_max <= 32 ? 0 : P.nb_max <= 64 ? 1 : P.nb_max <= 96 ? 2 : 3;
+  S3KernelFn fn_act = nullptr;
+  if ((P.lean & 8) && P.dbg == nullptr && !(get_option("tc_diag") & 65536))
+    fn_act = s3_lean2_act_kernel(P.unit >> 1, P.pair, c.seg[E.e_seg[0]].act);
   const S3KernelFn fn = P.dbg != nullptr ? s3_dbg_kernel(nidx, P.unit >> 1, P.pair, (P.lean & 8) ? 2 : P.lean != 0)
+                        : fn_act != nullptr ? fn_act
                         : (P.lean & 8)   ? s3_lean2_kernel(P.unit >> 1, P.pair)
                         : P.lean         ? s3_lean_kernel(nidx, P.unit >> 1, P.pair)
                         : P.pair         ? ptable[nidx][P.unit >> 1]

@@ -73,9 +73,10 @@ class View:
 
 class Engine:
     def __init__(self, state_dict: Dict[str, torch.Tensor], B: int, H: int, W: int, device: torch.device,
-                 conv_kind: Optional[str] = None, dry: bool = False):
+                 conv_kind: Optional[str] = None, dry: bool = False, arena: Optional[bool] = None):
         """dry=True builds the plan (buffers, channel maps, packed weights) on the host without a
-        GPU so that the host logic can be checked on CPU; such an engine cannot run."""
+        GPU so that the host logic can be checked on CPU; such an engine cannot run.  arena=False (or DEMFI_ARENA=0) gives
+        every buffer memory of its own, so that intermediates can be read back after a call (tests)."""
         if H % 8 or W % 8:
             raise ValueError(f"H and W must be multiples of 8 (UNet's three stride-2 convs, DeMFInet.py:575-577); got {H}x{W}")
         self.lib = A.lib()
@@ -94,9 +95,28 @@ class Engine:
         self._keep: list = []  # weights, ctypes structs
         self.bufs: Dict[str, torch.Tensor] = {}
         self.views: Dict[str, View] = {}
-        self._alloc()
         self._sd = {k: v.detach().to("cpu", torch.float32).contiguous() for k, v in state_dict.items()}
         self._wcache: Dict[tuple, tuple] = {}
+        # Workspace as ONE arena with liveness-planned offsets (_plan_arena): buffers whose lifetimes in the op sequence do not
+        # overlap share memory (736x1280: 14.2 GB of buffers in 7.4 GB; 4K: 125 GB -> 65 GB).  DEMFI_ARENA=0: one allocation each.
+        self.use_arena = (os.environ.get("DEMFI_ARENA", "1") != "0") if arena is None else bool(arena)
+        self._planning = False
+        self._arena: Optional[torch.Tensor] = None
+        self._offsets: Dict[str, int] = {}
+        self._numel: Dict[str, int] = {}
+        self.liveness: Dict[str, Tuple[int, int]] = {}
+        if self.use_arena:
+            # planning pass: the op lists are built once over placeholder buffers (nothing is launched, nothing large is
+            # allocated; the packed weights it caches are the ones the real pass uses), then laid out
+            self._planning = True
+            self._alloc()
+            self._build()
+            self._plan_arena()
+            self._planning = False
+            self.bufs.clear()
+            self.views.clear()
+            self._keep.clear()
+        self._alloc()
         self.profile: Optional[list] = None  # when a list: (op, start_event, end_event) per launched op
         self.use_graph = os.environ.get("DEMFI_GRAPH", "0") == "1"
         self._graphs: Dict[tuple, tuple] = {}
@@ -108,7 +128,14 @@ class Engine:
     # ------------------------------------------------------------------ memory
     def _buf(self, name, N, H, W, ld, s16=False) -> View:
         """s16=True: a buffer only convolutions touch -> stored in the S16 format when the tensor-core kernels run"""
-        t = torch.zeros(N * H * W * ld, dtype=torch.float32, device=self.dev)
+        numel = N * H * W * ld
+        if self._planning:
+            self._numel[name] = numel
+            t = torch.zeros(1, dtype=torch.float32)  # placeholder: its identity stands for the buffer in the liveness analysis
+        elif self._arena is not None:
+            t = self._arena[self._offsets[name]:self._offsets[name] + numel]
+        else:
+            t = torch.zeros(numel, dtype=torch.float32, device=self.dev)
         self.bufs[name] = t
         return View(t, N, H, W, ld, fmt=A.FMT_S16 if (s16 and self.use_s16) else A.FMT_F32)
 
@@ -167,7 +194,132 @@ class Engine:
         self.t_dev = torch.zeros(B, dtype=torch.float32, device=self.dev)
 
     def workspace_bytes(self) -> int:
+        if self._arena is not None:
+            return self._arena.numel() * 4
         return sum(t.numel() * 4 for t in self.bufs.values())
+
+    # ------------------------------------------------------------------ arena
+    @staticmethod
+    def _op_views(op) -> Tuple[List["View"], List["View"]]:
+        """(views read, views written) by one op of the plan"""
+        k = op[0]
+        if k == "conv":
+            return op[5]["src"] + op[5]["res"], op[5]["dst"]
+        if k == "zero":
+            return [], [op[1]]
+        if k in ("copy", "upsample"):
+            return [op[1]], [op[2]]
+        if k == "gather":
+            return [sv for sv, _ in op[2]], [op[1]]
+        if k == "cfr_splat":
+            return [op[1], op[2]], [op[2]]
+        if k == "cfr_finalize":
+            return [op[1]], [op[2]]
+        if k == "bwarp_blend":
+            return list(op[1:5]), [o for o in op[5:7] if o is not None]
+        if k == "pwb":
+            return [op[1], op[2]], [op[3]]
+        if k == "fgac_sample":
+            return [op[1], op[2]], [op[3]]
+        if k == "fgac_blend":
+            return list(op[1:4]), [op[4]]
+        raise AssertionError(k)
+
+    def op_sequence(self, reuse_prefix: bool = False, iterations: int = 6) -> List[Tuple[str, List["View"], List["View"]]]:
+        """One forward as (phase, views read, views written) steps, incl. what the host side touches: pack_input before the
+        first op, the exports after stage I and after every iteration, and the buffers read after the call (FGAC side outputs
+        of the training / visualisation tuples, tests).  Six iterations cover the rotation of the iteration buffers."""
+        v = self.views
+        seq = []
+        if not reuse_prefix:
+            seq.append(("pack_input", [], [v["S2D"], v["REF"].ch(9, 12), v["A3"].ch(28, 12)]))
+            seq += [("prefix",) + self._op_views(op) for op in self.ops_prefix_ff]
+        seq += [("stage1",) + self._op_views(op) for op in self.ops_stage1]
+        seq.append(("stage1", [v["SP"], v["DL0"], v["A3"]], []))
+        for itr in range(iterations):
+            seq += [("iter",) + self._op_views(op) for op in self._iter_ops(itr, True)]
+            seq.append(("iter", [v["DL0"] if itr % 2 else v["DL1"], v["D2O"]], []))
+        seq.append(("after", [v[n] for n in self._READ_AFTER], []))
+        return seq
+
+    # read after the forward has returned: fgac_maps (SE, RK, WL, AGG1), tests and tools (F01, FO, SE)
+    _READ_AFTER = ("SE", "RK", "WL", "AGG1", "F01", "FO")
+
+    def _plan_arena(self):
+        """Lifetimes over the op sequence, then first-fit offsets by decreasing size.  A buffer lives from its first to its last
+        step, except: (1) anything touched in the boosting iterations lives to the end (the iteration buffers rotate and carry
+        state from one iteration to the next, for any N_tst); (2) anything written in the t-independent prefix and read later
+        lives to the end -- `reuse_prefix` calls run stage I and the iterations again on what an EARLIER call's prefix left, so
+        nothing those phases touch may share its memory; (3) the buffers read after the call live to the end.  A buffer that
+        lives to the end is never shared with anything that starts later, hence channels of it that no kernel ever writes
+        (padding of A3 / REF) keep the zeros of the allocation."""
+        name_of = {id(t): n for n, t in self.bufs.items()}
+        seq = self.op_sequence()
+        end = len(seq)
+        first: Dict[str, int] = {}
+        last: Dict[str, int] = {}
+        phases: Dict[str, set] = {}
+        for i, (ph, rd, wr) in enumerate(seq):
+            for vw in rd + wr:
+                n = name_of[id(vw.t)]
+                first.setdefault(n, i)
+                last[n] = i
+                phases.setdefault(n, set()).add(ph)
+        live = {}
+        for n in self.bufs:
+            if n not in first:
+                continue  # (never touched by this plan, e.g. the partial sums of the opt-in push form: no memory)
+            ph = phases[n]
+            to_end = "iter" in ph or "after" in ph or (bool(ph & {"pack_input", "prefix"}) and bool(ph - {"pack_input", "prefix"}))
+            live[n] = (first[n], end if to_end else last[n])
+        al = 256  # floats: 1 KB (TMA needs 16 bytes; torch allocations are 512-byte aligned)
+        size = {n: _ru(self._numel[n], al) for n in self.bufs}
+        off: Dict[str, int] = {}
+        for n in sorted(live, key=lambda n_: (-size[n_], n_)):
+            f, l = live[n]
+            busy = sorted((off[m], off[m] + size[m]) for m in off if not (live[m][1] < f or live[m][0] > l))
+            o = 0
+            for a, b in busy:
+                if o + size[n] <= a:
+                    break
+                o = max(o, b)
+            off[n] = o
+        for n in self.bufs:
+            off.setdefault(n, 0)  # untouched buffers: any address (never read or written)
+        total = max([off[n] + size[n] for n in live] + [al])
+        self._offsets, self.liveness = off, live
+        self._arena = torch.zeros(total, dtype=torch.float32, device=self.dev)
+
+    def check_arena(self) -> int:
+        """Replay four calls (full, reuse_prefix, full with another N_tst, reuse_prefix) over the arena layout and check that
+        every buffer an op -- or the host after the call -- reads was written before and that no OTHER buffer has been written
+        into its memory since.  Independent of the planner's own rules (it only looks at addresses and the op sequence).
+        Host-only: runs on a dry engine.  Returns the number of reads checked."""
+        if self._arena is None:
+            return 0
+        name_of = {id(t): n for n, t in self.bufs.items()}
+        rng = {n: (self._offsets[n], self._offsets[n] + self._numel[n]) for n in self.bufs}
+        foreign = {n: False for n in self.bufs}
+        written = set()
+        checked = 0
+        for call, (reuse, iters) in enumerate(((False, 6), (True, 6), (False, 3), (True, 2))):
+            for step, (ph, rd, wr) in enumerate(self.op_sequence(reuse_prefix=reuse, iterations=iters)):
+                for vw in rd:
+                    n = name_of[id(vw.t)]
+                    if n in [name_of[id(w_.t)] for w_ in wr] and n not in written:
+                        continue  # read-modify-write of a buffer this very op initialises
+                    assert n in written, f"call {call} step {step} ({ph}): {n} is read before anything wrote it"
+                    assert not foreign[n], f"call {call} step {step} ({ph}): {n} is read after another buffer was written into its memory"
+                    checked += 1
+                for vw in wr:
+                    n = name_of[id(vw.t)]
+                    a0, a1 = rng[n]
+                    for m, (b0, b1) in rng.items():
+                        if m != n and a0 < b1 and b0 < a1:
+                            foreign[m] = True
+                    foreign[n] = False
+                    written.add(n)
+        return checked
 
     # ------------------------------------------------------------------ op construction
     def _weight(self, names: Sequence[str]) -> Tuple[np.ndarray, np.ndarray]:

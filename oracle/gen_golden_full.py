@@ -17,6 +17,8 @@ count changes, which this script measures at the same size (1 thread against all
 (`self_noise` in tests/golden/full_736x1280_n3.json) as the yardstick of tests/test_full_size_parity.py.
 
     python oracle/gen_golden_full.py          # ~2 min with 8 threads + ~5 min for the 1-thread self-noise run
+    python oracle/gen_golden_full.py 4k       # the same for the BASELINE config 5 shape scaled by 1/4 per side: 3840x2176 -> 960x544,
+                                              # N_tst = 5, t = 7/16 (x16 MFI) -> tests/golden/full_544x960_n5.{npz,json}
 """
 from __future__ import annotations
 
@@ -35,8 +37,12 @@ from demfi_b200 import synth  # noqa: E402
 from gen_golden import load_reference, name_outputs  # noqa: E402
 
 H, W, N, T, SEED = 736, 1280, 3, 0.375, 0
-PTS = ["Stp", "St_final0", "St_final2", "S0_final2", "flow0", "flow3", "occ3"]
-BLK = ["S0p", "S1p", "Stp", "St_final0", "St_final1", "St_final2", "S0_final2", "S1_final2", "flow0", "flow3", "occ0", "occ3"]
+if len(sys.argv) > 1 and sys.argv[1] == "4k":
+    H, W, N, T = 544, 960, 5, 0.4375
+STEM = "full_%dx%d_n%d" % (H, W, N)
+L = N - 1  # last boosting iteration
+PTS = ["Stp", "St_final0", f"St_final{L}", f"S0_final{L}", "flow0", f"flow{N}", f"occ{N}"]
+BLK = ["S0p", "S1p", "Stp", "St_final0", "St_final1", f"St_final{L}", f"S0_final{L}", f"S1_final{L}", "flow0", f"flow{N}", "occ0", f"occ{N}"]
 TOL = 5e-4
 
 
@@ -70,9 +76,9 @@ def main():
         out[k + "/pts"] = pts(full[k])
     for k in BLK:
         out[k + "/blk"] = blk(full[k]).astype(np.float32)
-    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "full_736x1280_n3.npz"), **out)
-    meta = {"what": "unmodified reference DeMFInet.forward (torch CPU fp32, %d threads) on synth.make_frames(736, 1280, seed=0), "
-                    "synth.make_state_dict(0), t = 0.375, N_tst = 3" % nt,
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", STEM + ".npz"), **out)
+    meta = {"what": "unmodified reference DeMFInet.forward (torch CPU fp32, %d threads) on synth.make_frames(%d, %d, seed=0), "
+                    "synth.make_state_dict(0), t = %g, N_tst = %d" % (nt, H, W, T, N),
             "torch": torch.__version__, "shape": [H, W], "N_tst": N, "t": T, "seconds": sec_all,
             "pts": "v[..., 1::4, 2::4]", "blk": "8x8 block sums (float64 accumulation)"}
     # the reference against itself: one thread vs all threads, the same figures the GPU test computes
@@ -86,7 +92,7 @@ def main():
                                "pts_frac_gt_5e-4": float((ep > TOL).mean()), "pts_max_abs": float(ep.max()),
                                "blk_mean_max_abs": float(np.abs(blk(one[k]) - blk(full[k])).max() / 64)}
     meta["self_noise"] = noise
-    with open(os.path.join(ROOT, "tests", "golden", "full_736x1280_n3.json"), "w") as f:
+    with open(os.path.join(ROOT, "tests", "golden", STEM + ".json"), "w") as f:
         json.dump(meta, f, indent=1)
     print(json.dumps(meta, indent=1))
 

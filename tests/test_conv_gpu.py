@@ -383,6 +383,39 @@ def test_cta_pair_close_to_single_cta():
     assert float((a - b_).abs().max()) <= 2.0 ** -20 * float(a.abs().max())
 
 
+@pytest.mark.parametrize("grid", [2, 6, 148])
+@pytest.mark.parametrize("h,w_,act", [(156, 312, A.ACT_NONE), (48, 24, A.ACT_RELU), (80, 40, A.ACT_NONE)])
+def test_cta_pair_skip_operand_two_tiles_in_turn(grid, h, w_, act):
+    """ResBlock conv2 on CTA pairs (S16 everywhere, one S16 skip operand): operand and result share one of TWO shared-memory
+    tiles used in turn, the operand requested two tiles ahead (conv_s3: P.res_sep == 2).  Few CTAs = long tile sequences per
+    CTA, odd tile counts = a half-empty last pair; the result must equal, bit for bit, the kernel with ONE operand tile
+    (tc_diag & 32768), repeatedly, and the float64 convolution within the usual tolerance."""
+    n = 2
+    x, r = rnd(n, 64, h, w_, seed=61), rnd(n, 64, h, w_, seed=62)
+    xb, rb = s16_encode(nhwc(x)[0]), s16_encode(nhwc(r)[0])
+    xv = s16_decode(xb).permute(0, 3, 1, 2).cpu()
+    rv = s16_decode(rb).permute(0, 3, 1, 2).cpu()
+    w, b = wb(64, 64, 3, 3, seed=63)
+    outs = {}
+    try:
+        A.set_option("tc_grid", grid)
+        for diag in (32768, 0, 0, 0):
+            A.set_option("tc_diag", diag)
+            out = torch.zeros(n, h, w_, 64, device=DEV)
+            run_conv(w, b, [(xb, 64, 0, A.FMT_S16)], (h, w_), A.CONV_TC16P,
+                     [dict(ch0=0, nch=64, dst=out, res=rb, act=act, fmt=A.SEG_DST_S16 | A.SEG_RES_S16)])
+            outs.setdefault(diag, []).append(out.clone())
+    finally:
+        A.set_option("tc_grid", 0)
+        A.set_option("tc_diag", 0)
+    want = ref_conv(xv, w, b) + rv.double()
+    if act == A.ACT_RELU:
+        want = F.relu(want)
+    check(from_nhwc(s16_decode(outs[0][0]), 64), want, f"two operand tiles in turn, grid {grid}, {h}x{w_}")
+    for o in outs[0]:
+        assert torch.equal(o.view(torch.int32), outs[32768][0].view(torch.int32)), "differs from the one-operand-tile kernel"
+
+
 # ---- S16 ("split fp16") activation format: conv_s3 reads it without a conversion pass and writes it from its epilogue
 def test_s16_roundtrip_host():
     x = rnd(2, 5, 7, 64, seed=5, scale=3.0)

@@ -63,7 +63,7 @@ def test_intermediates_match_oracle(state_dict, golden_meta):
     inter = {}
     O.forward(state_dict, x, t, cfg["n"], intermediates=inter)
     B, H, W = 1, cfg["h"], cfg["w"]
-    eng = Engine(state_dict, B, H, W, DEV)
+    eng = Engine(state_dict, B, H, W, DEV, arena=False)  # every intermediate keeps memory of its own to be read back below
     eng.forward(x.to(DEV), t.to(DEV), cfg["n"])
     torch.cuda.synchronize()
     v = eng.views
@@ -85,6 +85,33 @@ def test_intermediates_match_oracle(state_dict, golden_meta):
         print(f"intermediate {k}: max-abs {d:.3e} (max|ref| {float(inter[k].abs().max()):.2f})")
     bad = {k: d for k, d in worst.items() if d > TOL}
     assert not bad, bad
+
+
+def test_arena_workspace_changes_nothing(state_dict, golden_meta):
+    """The liveness-planned arena (buffers with disjoint lifetimes share memory) against one allocation per buffer: same
+    outputs for a full call, a reuse_prefix call at another t and a call with another N_tst (the CFR splat's fp32 atomics make
+    two runs agree to rounding, not bit for bit: 2e-5, as below)."""
+    cfg = golden_meta["cases"]["c64x96_n3"]["cfg"]
+    x, _ = case_inputs(cfg)
+    xd = x.to(DEV)
+    outs = []
+    for arena in (True, False):
+        eng = Engine(state_dict, 1, cfg["h"], cfg["w"], DEV, arena=arena)
+        assert (eng._arena is not None) == arena
+        o = [eng.forward(xd, torch.tensor([[0.25]], device=DEV), 3),
+             eng.forward(xd, torch.tensor([[0.75]], device=DEV), 3, reuse_prefix=True),
+             eng.forward(xd, torch.tensor([[0.5]], device=DEV), 5),
+             eng.forward(xd, torch.tensor([[0.5]], device=DEV), 2, reuse_prefix=True, final_only=True)]
+        torch.cuda.synchronize()
+        outs.append([O.flatten_outputs(r) if r[1][0] is not None else {"St": r[1][-1][2], "flow": r[2][-1]} for r in o])
+        if arena:
+            small = eng.workspace_bytes()
+        else:
+            assert small < 0.75 * eng.workspace_bytes()
+    for a_, b_ in zip(*outs):
+        for k in a_:
+            d = float((a_[k] - b_[k]).abs().max())
+            assert d <= 2e-5, (k, d)
 
 
 def test_prefix_reuse_and_final_only_change_nothing(net, golden_meta):

@@ -126,6 +126,35 @@ def test_no_convolution_of_the_plan_falls_back_to_a_slower_path(state_dict):
     assert deep.get("FF_RDB_Module.GFF.0", 0) >= 4 and deep.get("FAC_FB_Module.shared_FGAC.conv_ref_k", 0) == 6, deep
 
 
+@pytest.mark.parametrize("hw", [(64, 96), (736, 1280)])
+def test_workspace_arena_layout(state_dict, hw):
+    """The workspace is one arena with liveness-planned offsets: buffers share memory only when no op sequence (full calls,
+    reuse_prefix calls, any N_tst) reads one after the other was written; everything the host reads after a call and
+    everything the t-independent prefix hands to later phases keeps memory of its own."""
+    e = Engine(state_dict, 1, *hw, torch.device("cpu"), dry=True)
+    assert e.check_arena() > 1000
+    total = sum(e._numel[n] for n in e.liveness) * 4
+    assert e.workspace_bytes() < 0.6 * total, (e.workspace_bytes(), total)
+    rng = {n: (e._offsets[n], e._offsets[n] + e._numel[n]) for n in e.liveness}
+    end = max(l for _, l in e.liveness.values())
+    for n in ("F01", "FO", "AGG1", "SE", "RK", "WL", "A3", "REF", "P0", "FR0", "DL0", "D2O"):
+        assert e.liveness[n][1] == end, n
+        for m, (b0, b1) in rng.items():  # shares memory with nothing that starts after it
+            if m != n and rng[n][0] < b1 and b0 < rng[n][1]:
+                assert e.liveness[m][1] < e.liveness[n][0], (n, m)
+    for n, (a0, a1) in rng.items():
+        assert a0 % 256 == 0 and a1 <= e._arena.numel()
+    # the views point into the arena
+    assert e.views["T"].ptr == e._arena.data_ptr() + 4 * e._offsets["T"]
+    # DEMFI_ARENA=0 keeps one allocation per buffer
+    os.environ["DEMFI_ARENA"] = "0"
+    try:
+        f = Engine(state_dict, 1, 64, 96, torch.device("cpu"), dry=True)
+    finally:
+        del os.environ["DEMFI_ARENA"]
+    assert f._arena is None and f.check_arena() == 0 and f.workspace_bytes() > e.workspace_bytes() * (1 if hw == (64, 96) else 0)
+
+
 def test_shape_constraints():
     with pytest.raises(ValueError):
         Engine(synth.make_state_dict(0), 1, 36, 64, torch.device("cpu"), dry=True)

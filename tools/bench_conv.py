@@ -84,6 +84,11 @@ SHAPES = [  # name, batch, res divisor, srcC, cout, k
     ("Ch_Reducer 192->64 7x7", 1, 1, [64, 64, 64], 64, (7, 7)),
     ("GRU zr 128->128 1x5", 1, 1, [64, 64], 128, (1, 5)),
     ("GRU q 128->64 5x1", 1, 1, [64, 64], 64, (5, 1)),
+    ("GRU z 128->64 1x5", 1, 1, [64, 64], 64, (1, 5)),
+    ("GRU z 128->64 1x5 sigmoid", 1, 1, [64, 64], 64, (1, 5)),
+    ("GRU r 128->64 1x5 sigmoid_mul +res", 1, 1, [64, 64], 64, (1, 5)),
+    ("one source 128->64 1x5", 1, 1, [128], 64, (1, 5)),
+    ("resblock 64->64 5x5 (x1 frame)", 1, 1, [64], 64, (5, 5)),
     ("RDB conv 192->32 3x3 @1/2", 1, 2, [192], 32, (3, 3)),
     ("LFF 224->96 1x1 @1/2", 1, 2, [224], 96, (1, 1)),
     ("UPNet.0 96->256 3x3 @1/2", 1, 2, [96], 256, (3, 3)),
@@ -117,7 +122,7 @@ if __name__ == "__main__":
             if kind == A.CONV_TC16P and (co + 15) // 16 * 16 not in (32, 64):
                 continue
             A.set_option("tc_gen", 2 if kind_name == "tc16h3" else 3)
-            d, keep = make_conv(kind, n, h, w, srcC, co, k, res="+res" in name, act=A.ACT_NONE if "+res" in name else A.ACT_RELU, s16=a.s16)
+            d, keep = make_conv(kind, n, h, w, srcC, co, k, res="+res" in name, act=(A.ACT_SIGMOID_MUL if "sigmoid_mul" in name else A.ACT_SIGMOID if "sigmoid" in name else A.ACT_NONE if "+res" in name else A.ACT_RELU), s16=a.s16)
             ms = time_conv(d)
             row[kind_name + "_ms"] = round(ms, 3)
             row[kind_name + "_TFLOPs"] = round(2 * macs / ms / 1e9, 1)
