@@ -28,7 +28,7 @@ static std::atomic<int> g_opt_comp{270};
 static std::atomic<int> g_opt_stages{0};  // diagnostics: cap on pipeline stages (0 = as many as fit)
 static std::atomic<int> g_opt_grid{0};    // diagnostics: cap on persistent CTAs (0 = one per SM)
 static std::atomic<int> g_opt_pdl{0};     // programmatic dependent launch between consecutive conv_s3 kernels (measured: 47.6 vs 46.6 ms per forward, off)
-static std::atomic<int> g_opt_prefetch{2};  // conv_s3: halo-tile chunks prefetched into L2 beyond the TMA loads in flight
+static std::atomic<int> g_opt_prefetch{0};  // conv_s3: every activation chunk is also prefetched into L2 this many tiles ahead of the CTA's sequence
 static std::atomic<int> g_opt_nwide{1};     // conv_s3: Cout 97..128 as ONE N block (N' = 256 MMAs) instead of blocks of 64
 static std::atomic<int> g_opt_gen{3};     // DEMFI_CONV_TC16 kernel generation: 3 = conv_s3 where supported, 2 = conv_h3 only
 int get_option(const char* name) {

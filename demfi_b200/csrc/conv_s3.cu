@@ -95,6 +95,7 @@ struct S3Params {
   int offload;          // the TMA duties of the epilogue (operand fetch, stores) run on a warp of their own (all sources S16)
   int lean;             // lean epilogue: bit 0 = eligible, bit 1 = ReLU, bit 2 = one S16 operand; bit 3 = the general variant (LEAN == 2),
                         // with bit 4 = fp32 destination, bit 5 = fp32 first operand
+  int pf;               // L2 prefetch of the activation chunks this many tiles ahead (0: none)
   int res_sep;          // 1: the operand tile of a lean layer has a tile of its own (fetched one tile ahead by the store warp);
                         // 2: two tiles used in turn, each holding a tile's operand and then, in place, its result (operand fetched TWO tiles ahead)
   float comp;
@@ -1307,6 +1308,18 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_s3_kernel(const __grid_con
           } else {
             mbar_arrive_expect_tx(bar_rawfull(abuf), a_tx);
             tma_load_4d(smem_base + (uint32_t)(abuf * P.a_bytes), &P.tmap[a_src], bar_rawfull(abuf), a_c0, tx0, ty0, n);
+            // L2 prefetch of the same chunk `pf` tiles ahead of this CTA's sequence: bytes in flight beyond what the halo
+            // buffers hold (the HBM-bound layers -- skip-operand ResBlock convs, GRU gates, 1x1s -- sat at 3.5-3.9 TB/s with
+            // one or two 23 KB chunks outstanding per SM)
+            if (P.pf > 0) {
+              const int pt = a_tile + P.pf * tstep;
+              if (pt < P.ntiles) {
+                int t2 = pt / P.n_blocks;
+                const int px0 = (t2 % P.tiles_x) * S3_TW - c.pad_w;
+                t2 /= P.tiles_x;
+                tma_prefetch_4d(&P.tmap[a_src], a_c0, px0, (t2 % P.tiles_y) * S3_TH - c.pad_h, t2 / P.tiles_y);
+              }
+            }
           }
           if (++abuf == NA) { abuf = 0; aphase ^= 1u; }
           a_c0 += S3_KC;
@@ -1781,6 +1794,7 @@ static int s3_plan(const demfi_conv_t& c, S3Params& P, S3EpiPlan& E, int* smem_o
     P.ngrp = (units + P.grp_units - 1) / P.grp_units;
     P.grp_last = units - (P.ngrp - 1) * P.grp_units;
   }
+  P.pf = get_option("tc_prefetch");
   P.comp = (float)get_option("tc_comp_milli") * 1e-3f * 5.9604645e-8f;
   P.diag = get_option("tc_diag") & (1 | 16 | 32 | 64 | 128 | 256 | 512 | 1024);
   return 0;
