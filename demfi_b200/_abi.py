@@ -54,6 +54,7 @@ SYMBOLS = {
     "demfi_last_error": (C.c_char_p, []),
     "demfi_device_check": (i32, [i32]),
     "demfi_packed_weight_floats": (C.c_size_t, [i32, i32, i32, C.POINTER(i32), i32, i32]),
+    "demfi_pack_weights_device": (i32, [i32, vp, i32, i32, i32, i32, i32, i32, vp, vp]),
     "demfi_pack_weights": (i32, [i32, vp, i32, i32, i32, i32, C.POINTER(i32), C.POINTER(i32), i32,
                                  C.POINTER(i32), i32, vp]),
     "demfi_conv2d": (i32, [C.POINTER(Conv), vp]),

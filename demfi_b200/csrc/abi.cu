@@ -139,6 +139,14 @@ int demfi_get_option(const char* name, int32_t* value) {
   return 0;
 }
 
+int demfi_pack_weights_device(int32_t kind, const float* w, int32_t Co, int32_t Ci, int32_t KH, int32_t KW, int32_t src_c,
+                              int32_t cout_pad, float* out, void* stream) {
+  DEMFI_REQUIRE(w && out, "pack_weights_device: null argument");
+  DEMFI_REQUIRE(kind == DEMFI_CONV_TC16, "pack_weights_device: kind DEMFI_CONV_TC16 only (the training path's kernel)");
+  DEMFI_REQUIRE(Co > 0 && Ci > 0 && KH > 0 && KW > 0, "pack_weights_device: bad shape");
+  return h3_pack_weights_device(w, Co, Ci, KH, KW, src_c, cout_pad, out, static_cast<cudaStream_t>(stream));
+}
+
 size_t demfi_packed_weight_floats(int32_t kind, int32_t KH, int32_t KW, const int32_t* src_C, int32_t nsrc,
                                   int32_t cout_pad) {
   if (kind == DEMFI_CONV_TC) return 0;  // (retired, see demfi_pack_weights)

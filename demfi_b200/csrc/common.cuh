@@ -131,6 +131,7 @@ bool s3_supports(const demfi_conv_t& c);
 bool s3_s16_ok(const demfi_conv_t& c);
 int s3_describe(const demfi_conv_t& c, int32_t* info);  // host-only plan summary (demfi_conv_describe)  // the S16 requests of this convolution can be honoured (TMA epilogue plan exists)
 size_t h3_packed_floats(int KH, int KW, const int32_t* src_C, int nsrc, int cout_pad);
+int h3_pack_weights_device(const float* w, int Co, int Ci, int KH, int KW, int src_c, int cout_pad, float* out, cudaStream_t st);
 int h3_pack_weights(const float* w, int Co, int Ci, int KH, int KW, const int32_t* in_map, const int32_t* src_C,
                     int nsrc, const int32_t* out_map, int cout_pad, float* out, int nb_max = 0);
 int s3_nb_max(int kind, int cout_pad);

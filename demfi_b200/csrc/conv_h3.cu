@@ -670,4 +670,42 @@ int h3_pack_weights(const float* w, int Co, int Ci, int KH, int KW, const int32_
   return 0;
 }
 
+// The same layout written on the DEVICE from a device-resident OIHW weight (one source of src_c >= Ci channels, identity channel
+// maps with zero padding): the training step repacks every weight after every optimizer step and must not wait for the GPU to do
+// it on the host.  One thread per (output channel, chunk, tap, k).  Out-of-range values saturate to the fp16 limits.
+__global__ void h3_pack_kernel(const float* __restrict__ w, int Co, int Ci, int taps, int cout_pad, int nbm, int chunks, __half* __restrict__ o) {
+  const long long total = (long long)cout_pad * chunks * taps * H3_KC;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(idx & (H3_KC - 1));
+    long long t = idx / H3_KC;
+    const int tap = (int)(t % taps);
+    t /= taps;
+    const int chunk = (int)(t % chunks);
+    const int ng = (int)(t / chunks);
+    const int nb = ng / nbm, n = ng - nb * nbm;
+    const int N = (cout_pad - nb * nbm) < nbm ? (cout_pad - nb * nbm) : nbm;
+    __half* tile = o + (size_t)nb * chunks * taps * 2 * nbm * H3_KC + ((size_t)chunk * taps + tap) * (size_t)(2 * N * H3_KC);
+    const int cc = chunk * H3_KC + k;
+    float v = (cc < Ci && ng < Co) ? w[((size_t)ng * Ci + cc) * taps + tap] : 0.0f;
+    v = fminf(fmaxf(v, -65504.0f), 65504.0f);
+    const __half h = __float2half_rn(v);
+    const __half l = __float2half_rn(fminf(fmaxf((v - __half2float(h)) * H3_LO_SCALE, -65504.0f), 65504.0f));
+    const int rh = n, rl = N + n;
+    tile[(size_t)rh * H3_KC + (size_t)((((k >> 3) ^ ((rh >> 1) & 3)) << 3) + (k & 7))] = h;
+    tile[(size_t)rl * H3_KC + (size_t)((((k >> 3) ^ ((rl >> 1) & 3)) << 3) + (k & 7))] = l;
+  }
+}
+
+int h3_pack_weights_device(const float* w, int Co, int Ci, int KH, int KW, int src_c, int cout_pad, float* out, cudaStream_t st) {
+  DEMFI_REQUIRE(cout_pad % 16 == 0 && cout_pad <= 256 && Co <= cout_pad, "pack_weights_device: cout_pad must be a multiple of 16, >= Co and <= 256");
+  DEMFI_REQUIRE(src_c >= Ci && src_c % 4 == 0, "pack_weights_device: src_c must be >= Ci and a multiple of 4");
+  const int chunks = (src_c + H3_KC - 1) / H3_KC;
+  const long long total = (long long)cout_pad * chunks * KH * KW * H3_KC;
+  const int threads = 256;
+  const int blocks = (int)((total + threads - 1) / threads < 4096 ? (total + threads - 1) / threads : 4096);
+  h3_pack_kernel<<<blocks, threads, 0, st>>>(w, Co, Ci, KH * KW, cout_pad, h3_nb_max(cout_pad), chunks, reinterpret_cast<__half*>(out));
+  DEMFI_LAUNCH_CHECK("h3_pack_kernel");
+  return 0;
+}
+
 }  // namespace demfi

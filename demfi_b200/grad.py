@@ -11,8 +11,8 @@ whose dx runs on the CUDA-core `demfi_conv2d_dgrad_strided`) and is differentiab
 
 What the reference gets from autograd through `nn.Conv2d` (main.py:443).  NCHW tensors at the boundary (imported / exported
 with the ABI's layout kernels), NHWC inside.  No CPU or ATen fallback: CPU tensors raise.  `train_net.forward_train` builds the
-whole network's training graph from this function.  Weights are packed on the host at every call (first version);
-DEMFI_GRAD_PACK_CACHE=1 keeps the packed tensors until the parameter's version counter moves.
+whole network's training graph from this function.  Weights are packed on the device (demfi_pack_weights_device, stream-ordered;
+DEMFI_GRAD_HOST_PACK=1: on the host, as the first version did) once per change of the parameter (its version counter).
 """
 from __future__ import annotations
 
@@ -52,6 +52,29 @@ def _pack(w: np.ndarray, b: np.ndarray, src_c: int, dev) -> Tuple[torch.Tensor, 
     return torch.from_numpy(packed).to(dev), torch.from_numpy(bias).to(dev), cout_pad
 
 
+def _pack_dev(w: torch.Tensor, b, src_c: int, dev) -> Tuple[torch.Tensor, torch.Tensor, int]:
+    """the same packed layout made ON the device from a device-resident OIHW weight (demfi_pack_weights_device): stream-ordered,
+    no host round trip -- every weight is repacked once per optimizer step, and a `.cpu()` per layer made the host wait for the
+    GPU ~400 times per training step"""
+    lib = A.lib()
+    Co, Ci, KH, KW = w.shape
+    cout_pad = _ru(Co, 16)
+    sC = (A.i32 * 1)(src_c)
+    n = lib.demfi_packed_weight_floats(A.CONV_TC16, KH, KW, sC, 1, cout_pad)
+    w = w.detach().to(torch.float32).contiguous()
+    packed = torch.empty(n, dtype=torch.float32, device=dev)
+    A.check(lib.demfi_pack_weights_device(A.CONV_TC16, w.data_ptr(), Co, Ci, KH, KW, src_c, cout_pad, packed.data_ptr(), _stream(dev)),
+            "demfi_pack_weights_device")
+    bias = torch.zeros(cout_pad, dtype=torch.float32, device=dev)
+    if b is not None:
+        bias[:Co] = b.detach()
+    return packed, bias, cout_pad
+
+
+def _host_pack() -> bool:
+    return os.environ.get("DEMFI_GRAD_HOST_PACK", "0") == "1"
+
+
 def _cache_on() -> bool:
     return os.environ.get("DEMFI_GRAD_PACK_CACHE", "1") == "1"
 
@@ -79,6 +102,8 @@ def _cached(weight: torch.Tensor, key: tuple, bias, make):
 def _pack_forward(weight: torch.Tensor, bias, src_c: int, dev):
     """packed forward weights of a layer (cached on the parameter, see _cached)"""
     def make():
+        if not _host_pack():
+            return _pack_dev(weight, bias, src_c, dev)
         b = bias.detach().cpu().numpy() if bias is not None else np.zeros(weight.shape[0], dtype=np.float32)
         return _pack(weight.detach().cpu().numpy(), b, src_c, dev)
     return _cached(weight, ("f", src_c, str(dev)), bias, make)
@@ -87,8 +112,10 @@ def _pack_forward(weight: torch.Tensor, bias, src_c: int, dev):
 def _pack_rotated(weight: torch.Tensor, c0: int, c1: int, src_c: int, dev):
     """packed weights of the dx convolution for input channels [c0, c1): w_t[ci, co, ky, kx] = W[co, ci, KH-1-ky, KW-1-kx]"""
     def make():
-        w_rot = weight.detach().flip(2, 3).transpose(0, 1)[c0:c1].contiguous().cpu().numpy()
-        return _pack(w_rot, np.zeros(c1 - c0, dtype=np.float32), src_c, dev)
+        w_rot = weight.detach().flip(2, 3).transpose(0, 1)[c0:c1].contiguous()
+        if not _host_pack():
+            return _pack_dev(w_rot, None, src_c, dev)
+        return _pack(w_rot.cpu().numpy(), np.zeros(c1 - c0, dtype=np.float32), src_c, dev)
     return _cached(weight, ("r", c0, c1, src_c, str(dev)), None, make)
 
 

@@ -126,6 +126,13 @@ int demfi_pack_weights(int32_t kind, const float* w_oihw_host, int32_t Co, int32
                        const int32_t* in_map, const int32_t* src_C, int32_t nsrc, const int32_t* out_map,
                        int32_t cout_pad, float* out_host);
 
+/* DEVICE -> DEVICE form of demfi_pack_weights for kind DEMFI_CONV_TC16 and ONE source of src_c >= Ci channels (identity channel
+ * maps; input channels Ci..src_c-1 and output channels Co..cout_pad-1 are zero padding), stream-ordered: the training step
+ * (main.py:443-445: backward, optimizer step, next forward) repacks every weight once per step and must not wait for the GPU
+ * to do it on the host.  Same bytes as demfi_pack_weights for in-range weights; values beyond the fp16 range saturate. */
+int demfi_pack_weights_device(int32_t kind, const float* w_oihw_dev, int32_t Co, int32_t Ci, int32_t KH, int32_t KW,
+                              int32_t src_c, int32_t cout_pad, float* out_dev, void* stream);
+
 /* ---- convolution (DeMFInet.py: every nn.Conv call; see demfi_conv_t) -------------------- */
 int demfi_conv2d(const demfi_conv_t* conv, void* stream);
 

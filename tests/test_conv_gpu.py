@@ -416,6 +416,29 @@ def test_cta_pair_skip_operand_two_tiles_in_turn(grid, h, w_, act):
         assert torch.equal(o.view(torch.int32), outs[32768][0].view(torch.int32)), "differs from the one-operand-tile kernel"
 
 
+@pytest.mark.parametrize("co,ci,k,src_c", [(64, 64, (3, 3), 64), (3, 64, (3, 3), 64), (96, 48, (5, 5), 48), (256, 96, (3, 3), 96),
+                                           (32, 5, (7, 7), 8), (64, 128, (1, 5), 128), (133, 64, (3, 3), 64), (64, 204, (4, 4), 208)])
+def test_device_weight_packing_equals_host_packing(co, ci, k, src_c):
+    """demfi_pack_weights_device (the training step repacks every weight once per optimizer step, stream-ordered) writes the
+    bytes demfi_pack_weights writes on the host: N blocking, hi / lo rows, 64-byte swizzle, zero padding of channels."""
+    import ctypes as C
+    lib = A.lib()
+    w, _ = wb(co, ci, *k, seed=71)
+    cout_pad = (co + 15) // 16 * 16
+    sC = (A.i32 * 1)(src_c)
+    n = lib.demfi_packed_weight_floats(A.CONV_TC16, k[0], k[1], sC, 1, cout_pad)
+    host = np.empty(n, dtype=np.float32)
+    wn = np.ascontiguousarray(w.numpy())
+    A.check(lib.demfi_pack_weights(A.CONV_TC16, wn.ctypes.data, co, ci, k[0], k[1], (A.i32 * src_c)(*(list(range(ci)) + [-1] * (src_c - ci))),
+                                   sC, 1, (A.i32 * cout_pad)(*(list(range(co)) + [-1] * (cout_pad - co))), cout_pad, host.ctypes.data), "pack")
+    wd = w.to(DEV).contiguous()
+    out = torch.full((n,), float("nan"), device=DEV)
+    A.check(lib.demfi_pack_weights_device(A.CONV_TC16, wd.data_ptr(), co, ci, k[0], k[1], src_c, cout_pad, out.data_ptr(),
+                                          torch.cuda.current_stream(DEV).cuda_stream), "pack_device")
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy().view(np.uint32), host.view(np.uint32))
+
+
 # ---- S16 ("split fp16") activation format: conv_s3 reads it without a conversion pass and writes it from its epilogue
 def test_s16_roundtrip_host():
     x = rnd(2, 5, 7, 64, seed=5, scale=3.0)
