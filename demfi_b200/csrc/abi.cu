@@ -30,6 +30,7 @@ static std::atomic<int> g_opt_grid{0};    // diagnostics: cap on persistent CTAs
 static std::atomic<int> g_opt_pdl{0};     // programmatic dependent launch between consecutive conv_s3 kernels (measured: 47.6 vs 46.6 ms per forward, off)
 static std::atomic<int> g_opt_prefetch{0};  // conv_s3: every activation chunk is also prefetched into L2 this many tiles ahead of the CTA's sequence
 static std::atomic<int> g_opt_nwide{1};     // conv_s3: Cout 97..128 as ONE N block (N' = 256 MMAs) instead of blocks of 64
+static std::atomic<int> g_opt_wgrad{1};   // demfi_conv2d_wgrad: 1 = mma.sync 3xTF32 kernel, 0 = CUDA-core fp32 kernel
 static std::atomic<int> g_opt_gen{3};     // DEMFI_CONV_TC16 kernel generation: 3 = conv_s3 where supported, 2 = conv_h3 only
 int get_option(const char* name) {
   if (!strcmp(name, "tc_mask_hi")) return g_opt_mask_hi.load();
@@ -44,6 +45,7 @@ int get_option(const char* name) {
   if (!strcmp(name, "tc_pdl")) return g_opt_pdl.load();
   if (!strcmp(name, "tc_prefetch")) return g_opt_prefetch.load();
   if (!strcmp(name, "tc_nwide")) return g_opt_nwide.load();
+  if (!strcmp(name, "wgrad_kind")) return g_opt_wgrad.load();
   return -1;
 }
 
@@ -123,6 +125,7 @@ int demfi_set_option(const char* name, int32_t value) {
   if (!strcmp(name, "tc_pdl")) { g_opt_pdl.store(value ? 1 : 0); return 0; }
   if (!strcmp(name, "tc_prefetch")) { g_opt_prefetch.store(value < 0 ? 0 : value); return 0; }
   if (!strcmp(name, "tc_nwide")) { g_opt_nwide.store(value ? 1 : 0); return 0; }
+  if (!strcmp(name, "wgrad_kind")) { g_opt_wgrad.store(value ? 1 : 0); return 0; }
   if (!strcmp(name, "tc_gen")) {
     DEMFI_REQUIRE(value == 2 || value == 3, "set_option: tc_gen must be 2 or 3");
     g_opt_gen.store(value);

@@ -79,6 +79,138 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const WgradParams P) {
   }
 }
 
+// ---- tensor-core wgrad (legacy mma.sync path: m16n8k8 TF32 fragments, fp32 accumulate) -------------------------------------
+// Same decomposition as conv_wgrad_kernel -- one CTA per (pixel chunk, tap, 64 x 64 block of [Cout, Cin]), pixels as the reduction
+// dimension, fp32 atomic adds per chunk -- with the inner product on the tensor cores.  fp32 parity through the 3xTF32 split
+// (a = ah + al, ah = tf32(a), al = tf32(a - ah): D += al * bh + ah * bl + ah * bh; the dropped al * bl term is 2^-22 relative), the
+// small products first.  GEMM view per CTA: D[co, ci] += sum_p A[co, p] * B[p, ci] with A[m][k] = dz[p0 + k][co0 + m] and
+// B[k][n] = x[p0 + k shifted by the tap][ci0 + n], both staged in shared memory as [pixel][channel] rows of 72 floats (the fragment
+// loads (k = t or t + 4, channel = g) then hit 32 distinct banks).  8 warps: warp w owns rows (w & 3) * 16 .. + 16 of the 64
+// output channels and columns (w >> 2) * 32 .. + 32 of the 64 input channels = four m16n8 accumulator tiles.
+// tcgen05 would need the pixel-major operands as MN-major UMMA tiles ("What comes next"); this kernel is the step from
+// 9-18 TFLOP/s on the CUDA cores to the legacy tensor-core path with the launch structure unchanged.
+constexpr int WM_KP = 32;   // pixels per shared-memory stage (four k8 steps)
+constexpr int WM_LD = 72;   // row stride in floats: 72 mod 32 = 8
+
+__device__ __forceinline__ uint32_t tf32_rna(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(256) conv_wgrad_mma_kernel(const WgradParams P) {
+  __shared__ __align__(16) float zs[WM_KP][WM_LD];
+  __shared__ __align__(16) float xs[WM_KP][WM_LD];
+  const int tap = blockIdx.y, ky = tap / P.KW, kx = tap % P.KW;
+  const int cb = blockIdx.z / P.ci_blocks, ib = blockIdx.z % P.ci_blocks;
+  const int co0 = cb * WG_T, ci0 = ib * WG_T;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int m0 = (warp & 3) * 16, n0 = (warp >> 2) * 32;
+  const bool do_bias = (P.db != nullptr && tap == 0 && ib == 0 && (warp >> 2) == 0);
+  // acc: the tensor core's running sums of ONE stage (12 chained MMAs per tile); tot: their fp32 round-to-nearest sum over the
+  // chunk.  The tensor core accumulates with truncation -- a gain error of ~0.27 * 2^-24 per chained MMA (profiles/r1_tc_numerics.md):
+  // over the 768 MMAs of a 2048-pixel chunk that was 1.2e-5 of dW (measured), over 12 it is 2e-7.
+  float acc[4][4] = {}, tot[4][4] = {};
+  float bsum0 = 0.0f, bsum1 = 0.0f;   // rows m0 + g and m0 + g + 8 over this lane's k
+  const long long p0 = (long long)blockIdx.x * WG_CHUNK;
+  const long long p1 = min(p0 + (long long)WG_CHUNK, P.npix);
+  const int lc = threadIdx.x & 63, lr0 = threadIdx.x >> 6;  // loader: channel lc of rows lr0, lr0 + 4, ... (8 rows per stage)
+  const bool z_ok = co0 + lc < P.Cout, x_ok = ci0 + lc < P.Cin;
+  // pixel coordinates of the loader's next row, advanced incrementally (one division per CTA, not three per row: with them the
+  // index arithmetic, not the inner product, set the pace of this kernel and of the CUDA-core one alike)
+  int cx, cy;
+  long long cn;
+  {
+    const long long p = p0 + lr0;
+    cx = (int)(p % P.W);
+    cy = (int)((p / P.W) % P.H);
+    cn = p / ((long long)P.W * P.H);
+  }
+  float zr[WM_KP / 4], xr[WM_KP / 4];
+  auto load_stage = [&](long long pb) {  // global -> registers, rows pb + lr0 + 4 i
+#pragma unroll
+    for (int i = 0; i < WM_KP / 4; ++i) {
+      const long long p = pb + lr0 + 4 * i;
+      float zv = 0.0f, xv = 0.0f;
+      if (p < p1) {
+        if (z_ok) zv = P.dz[p * P.dz_ld + co0 + lc];
+        const int sy = cy * P.stride + ky - P.pad_h, sx = cx * P.stride + kx - P.pad_w;
+        if (x_ok && sy >= 0 && sy < P.Hi && sx >= 0 && sx < P.Wi) xv = P.x[((cn * P.Hi + sy) * P.Wi + sx) * P.x_ld + ci0 + lc];
+      }
+      zr[i] = zv;
+      xr[i] = xv;
+      cx += 4;
+      while (cx >= P.W) {
+        cx -= P.W;
+        if (++cy == P.H) { cy = 0; ++cn; }
+      }
+    }
+  };
+  load_stage(p0);
+  for (long long pb = p0; pb < p1; pb += WM_KP) {
+#pragma unroll
+    for (int i = 0; i < WM_KP / 4; ++i) {
+      zs[lr0 + 4 * i][lc] = zr[i];
+      xs[lr0 + 4 * i][lc] = xr[i];
+    }
+    __syncthreads();
+    if (pb + WM_KP < p1) load_stage(pb + WM_KP);  // the next stage's loads are in flight during this stage's MMAs
+#pragma unroll
+    for (int k0 = 0; k0 < WM_KP; k0 += 8) {
+      const float af[4] = {zs[k0 + t][m0 + g], zs[k0 + t][m0 + g + 8], zs[k0 + t + 4][m0 + g], zs[k0 + t + 4][m0 + g + 8]};
+      uint32_t ah[4], al[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        ah[i] = tf32_rna(af[i]);
+        al[i] = tf32_rna(af[i] - __uint_as_float(ah[i]));
+      }
+      bsum0 += af[0] + af[2];
+      bsum1 += af[1] + af[3];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float b0f = xs[k0 + t][n0 + 8 * j + g], b1f = xs[k0 + t + 4][n0 + 8 * j + g];
+        const uint32_t b0h = tf32_rna(b0f), b1h = tf32_rna(b1f);
+        const uint32_t b0l = tf32_rna(b0f - __uint_as_float(b0h)), b1l = tf32_rna(b1f - __uint_as_float(b1h));
+        mma_tf32(acc[j], al, b0h, b1h);
+        mma_tf32(acc[j], ah, b0l, b1l);
+        mma_tf32(acc[j], ah, b0h, b1h);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        tot[j][i] += acc[j][i];
+        acc[j][i] = 0.0f;
+      }
+    __syncthreads();
+  }
+  // accumulator tile j: c0 (row g, col 2t), c1 (g, 2t + 1), c2 (g + 8, 2t), c3 (g + 8, 2t + 1)
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int co = co0 + m0 + g + (i >> 1) * 8, ci = ci0 + n0 + 8 * j + 2 * t + (i & 1);
+      if (co < P.Cout && ci < P.Cin) atomicAdd(&P.dw[(((size_t)co * P.Cin + ci) * P.KH + ky) * P.KW + kx], tot[j][i]);
+    }
+  }
+  if (do_bias) {  // the four lanes of a quad hold disjoint k of the same two rows
+    bsum0 += __shfl_xor_sync(0xffffffffu, bsum0, 1);
+    bsum0 += __shfl_xor_sync(0xffffffffu, bsum0, 2);
+    bsum1 += __shfl_xor_sync(0xffffffffu, bsum1, 1);
+    bsum1 += __shfl_xor_sync(0xffffffffu, bsum1, 2);
+    if (t == 0) {
+      if (co0 + m0 + g < P.Cout) atomicAdd(&P.db[co0 + m0 + g], bsum0);
+      if (co0 + m0 + g + 8 < P.Cout) atomicAdd(&P.db[co0 + m0 + g + 8], bsum1);
+    }
+  }
+}
+
 // dx of a STRIDED convolution (the three 4x4 stride-2 UNet encoders, DeMFInet.py:566-571), gather form on CUDA cores:
 // dx[n, yi, xi, ci] = sum over taps (ky, kx) with (yi + pad - ky) and (xi + pad - kx) divisible by the stride, and over co, of
 // dz[n, (yi + pad - ky) / s, (xi + pad - kx) / s, co] * W[co, ci, ky, kx].  One thread per (input pixel, input channel); the 32
@@ -150,7 +282,9 @@ int demfi_conv2d_wgrad(const float* x, int32_t x_ld, int32_t Cin, const float* d
   P.npix = (long long)N * H * W;
   DEMFI_REQUIRE(P.co_blocks * P.ci_blocks <= 65535, "conv2d_wgrad: too many channel blocks");
   dim3 grid((unsigned)((P.npix + WG_CHUNK - 1) / WG_CHUNK), KH * KW, P.co_blocks * P.ci_blocks);
-  conv_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P);
+  // wgrad_kind 1 (default): the mma.sync 3xTF32 kernel; 0: the CUDA-core kernel (the independent fp32 implementation of the tests)
+  if (get_option("wgrad_kind") != 0) conv_wgrad_mma_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P);
+  else conv_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P);
   DEMFI_LAUNCH_CHECK("conv_wgrad");
   return 0;
 }

@@ -102,7 +102,7 @@ def _cached(weight: torch.Tensor, key: tuple, bias, make):
 def _pack_forward(weight: torch.Tensor, bias, src_c: int, dev):
     """packed forward weights of a layer (cached on the parameter, see _cached)"""
     def make():
-        if not _host_pack():
+        if weight.is_cuda and not _host_pack():  # (host tensors: only the host-side tests of the packing helpers get here)
             return _pack_dev(weight, bias, src_c, dev)
         b = bias.detach().cpu().numpy() if bias is not None else np.zeros(weight.shape[0], dtype=np.float32)
         return _pack(weight.detach().cpu().numpy(), b, src_c, dev)
@@ -113,7 +113,7 @@ def _pack_rotated(weight: torch.Tensor, c0: int, c1: int, src_c: int, dev):
     """packed weights of the dx convolution for input channels [c0, c1): w_t[ci, co, ky, kx] = W[co, ci, KH-1-ky, KW-1-kx]"""
     def make():
         w_rot = weight.detach().flip(2, 3).transpose(0, 1)[c0:c1].contiguous()
-        if not _host_pack():
+        if w_rot.is_cuda and not _host_pack():
             return _pack_dev(w_rot, None, src_c, dev)
         return _pack(w_rot.cpu().numpy(), np.zeros(c1 - c0, dtype=np.float32), src_c, dev)
     return _cached(weight, ("r", c0, c1, src_c, str(dev)), None, make)

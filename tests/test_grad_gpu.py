@@ -1,11 +1,11 @@
 """Backward of a convolution layer through the C ABI (training row f-2, first slice): demfi_b200.grad.conv2d against torch
-autograd on the same layer in float64.  Forward and dx run on the tcgen05 kernel (fp32 parity), dW / db on the CUDA-core
-wgrad kernel (fp32 atomics): tolerances relative to the gradient's own scale."""
+autograd on the same layer in float64.  Forward and dx run on the tcgen05 kernel (fp32 parity), dW / db on the mma.sync 3xTF32
+wgrad kernel and on the CUDA-core one (both with fp32 atomics): tolerances relative to the gradient's own scale."""
 import pytest
 import torch
 import torch.nn.functional as F
 
-from demfi_b200 import grad
+from demfi_b200 import _abi as A, grad
 
 pytestmark = pytest.mark.gpu
 DEV = torch.device("cuda:0")
@@ -20,7 +20,16 @@ ACT = {"none": lambda v: v, "relu": torch.relu, "tanh": torch.tanh, "sigmoid": t
     (96, 133, (3, 3), "none", 1, 24, 24),      # more output channels than one 64-wide block, ragged
     (224, 96, (1, 1), "sigmoid", 1, 20, 36),   # 1x1 (LFF-like)
 ])
-def test_conv2d_layer_gradients(ci, co, k, act, n, h, w):
+@pytest.mark.parametrize("wgrad_kind", [pytest.param(1, id="wgrad-mma-3xtf32"), pytest.param(0, id="wgrad-cuda-core")])
+def test_conv2d_layer_gradients(ci, co, k, act, n, h, w, wgrad_kind):
+    A.set_option("wgrad_kind", wgrad_kind)
+    try:
+        _layer_gradients(ci, co, k, act, n, h, w)
+    finally:
+        A.set_option("wgrad_kind", 1)
+
+
+def _layer_gradients(ci, co, k, act, n, h, w):
     g = torch.Generator().manual_seed(ci * 1000 + co)
     x = torch.randn(n, ci, h, w, generator=g)
     wt = torch.randn(co, ci, *k, generator=g) / (ci * k[0] * k[1]) ** 0.5

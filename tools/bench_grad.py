@@ -30,15 +30,20 @@ def main():
         dz = torch.randn(N, H, W, co, device=DEV)
         dw = torch.zeros(co, ci, *k, device=DEV)
         db = torch.zeros(co, device=DEV)
-        ms = timed(lambda: A.check(lib.demfi_conv2d_wgrad(x.data_ptr(), ci, ci, dz.data_ptr(), co, co, N, H, W, k[0], k[1], k[0] // 2,
-                                                          k[1] // 2, 1, dw.data_ptr(), db.data_ptr(), st), "wgrad"))
+        wg = lambda: A.check(lib.demfi_conv2d_wgrad(x.data_ptr(), ci, ci, dz.data_ptr(), co, co, N, H, W, k[0], k[1], k[0] // 2,
+                                                    k[1] // 2, 1, dw.data_ptr(), db.data_ptr(), st), "wgrad")
+        A.set_option("wgrad_kind", 0)
+        ms = timed(wg)
+        A.set_option("wgrad_kind", 1)
+        ms_mma = timed(wg)
         flop = 2.0 * N * H * W * ci * co * k[0] * k[1]
         # dx through the forward tensor-core kernel
         wt = torch.randn(ci, co, *k) / (co * k[0] * k[1]) ** 0.5           # already "transposed": maps co -> ci
         wdev, bdev, cpad = grad._pack(wt.numpy(), torch.zeros(ci).numpy(), co, DEV)
         ms_dx = timed(lambda: grad._conv_nhwc(dz, co, wdev, bdev, cpad, k, A.ACT_NONE))
         print(json.dumps({"layer": f"{ci}->{co} {k[0]}x{k[1]} @ {N}x{H}x{W}", "GFLOP": round(flop / 1e9, 2),
-                          "wgrad_cuda_core_ms": round(ms, 3), "wgrad_TFLOPs": round(flop / ms / 1e9, 2),
+                          "wgrad_cuda_core_ms": round(ms, 3), "wgrad_cuda_core_TFLOPs": round(flop / ms / 1e9, 2),
+                          "wgrad_mma_3xtf32_ms": round(ms_mma, 3), "wgrad_mma_TFLOPs": round(flop / ms_mma / 1e9, 2),
                           "dx_tcgen05_ms": round(ms_dx, 3), "dx_TFLOPs": round(flop / ms_dx / 1e9, 1)}), flush=True)
     # warp / splat backward (HBM- and atomic-bound): algorithmic bytes = a, b, dout read + da, db read-modify-write
     C = 64

@@ -7,7 +7,7 @@ was spent): first thing to run in round 2, together with DEMFI_TRAIN_E2E=1 pytes
     DEMFI_GRAD_PACK_CACHE=1 python tools/bench_train.py        # weights packed once per optimizer step instead of per call
     python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tools/bench_train.py
 """
-import argparse, json, os, sys
+import argparse, json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import torch.distributed as dist
@@ -37,8 +37,10 @@ def main():
     t = torch.rand(args.batch, 1, generator=torch.Generator().manual_seed(rank)).clamp(0.125, 0.875).to(dev)
     ev = lambda: torch.cuda.Event(enable_timing=True)
     rows = []
-    for step in range(args.steps + 1):                     # step 0 = warm-up
+    WARM = 2                                               # steps 0-1 = warm-up (allocator growth, first packing of every weight)
+    for step in range(args.steps + WARM):
         e = [ev() for _ in range(5)]
+        t_host = time.perf_counter()
         opt.zero_grad()
         e[0].record()
         res = train_net.forward_train(model, x, t, args.n_trn)
@@ -51,8 +53,10 @@ def main():
         opt.step()
         e[4].record()
         torch.cuda.synchronize(dev)
-        if step:
+        if step >= WARM:
             rows.append([e[i].elapsed_time(e[i + 1]) for i in range(4)] + [total])
+            if os.environ.get("DEMFI_TRAIN_VERBOSE") == "1" and rank == 0:
+                print("step", step, [round(v, 1) for v in rows[-1][:4]], "host s", round(time.perf_counter() - t_host, 3), flush=True)
     if world > 1:
         worst = torch.tensor([sum(r[:4]) for r in rows], device=dev).mean().reshape(1)
         dist.all_reduce(worst, op=dist.ReduceOp.MAX)
