@@ -306,7 +306,11 @@ uint64_t demfi_launch_count(void);
  * "tc_a_tmem" (1: activation operand through tensor memory, 0: through shared memory), "tc_stages" /
  * "tc_grid" (caps on pipeline depth / persistent CTAs, 0 = auto), "tc_diag" (timing diagnostics bitmask),
  * "tc_gen" (DEMFI_CONV_TC16 kernel: 3 = conv_s3 where it applies (default), 2 = conv_h3 only), "tc_pdl" (1: programmatic
- * dependent launch between consecutive conv_s3 kernels; default 0 -- measured slightly slower on the full forward).
+ * dependent launch between consecutive conv_s3 kernels; default 0 -- measured slightly slower on the full forward),
+ * "tc_prefetch" (conv_s3: every activation chunk is also prefetched into L2 this many tiles ahead; default 0 -- measured: no gain),
+ * "wgrad_kind" (demfi_conv2d_wgrad: 1 = mma.sync 3xTF32 kernel (default), 0 = CUDA-core fp32 kernel).  "tc_diag" bits used by
+ * tools/ and tests/: 128 role timers, 32768 one operand tile for the skip operand of a lean layer (instead of two used in turn),
+ * 65536 lean activation kernels with the activation read at run time (instead of the compile-time ones).
  * Returns non-zero for an unknown option. */
 int demfi_set_option(const char* name, int32_t value);
 int demfi_get_option(const char* name, int32_t* value);
