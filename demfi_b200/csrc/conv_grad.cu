@@ -13,7 +13,7 @@ namespace demfi {
 
 constexpr int WG_T = 64;     // output tile: WG_T output channels x WG_T input channels
 constexpr int WG_KP = 16;    // pixels per shared-memory stage
-constexpr int WG_CHUNK = 2048;  // pixels reduced by one CTA before its atomic adds
+constexpr int WG_CHUNK = 1024;  // pixels reduced by one CTA before its atomic adds (2048: 576 CTAs of a 64 -> 64 3x3 layer at 2 x 256 x 256 = 1.3 waves of the 444 resident CTAs)
 
 struct WgradParams {
   const float* x; const float* dz; float* dw; float* db;
