@@ -339,6 +339,9 @@ def run_ours(args):
         "algorithmic_flops_per_step": 2 * tc["macs"] // K,
         "peak_basis": basis,
         "traffic_basis": ncu.get("kernel"),
+        "traffic_capture": {"commit": ncu.get("commit"), "file": "profiles/conv_s3_ncu_summary.json", "duration_us": ncu.get("duration_us"),
+                            "algorithmic_bytes_per_launch": ncu.get("algorithmic_bytes_per_launch"),
+                            "tensor_pipe_active_pct": ncu.get("tensor_pipe_active_pct")},
         "top_shapes": [{"conv": k, "launches_per_step": v["launches"] // K, "ms_per_launch": round(v["ms"] / v["launches"], 3),
                         "TFLOP/s": round(2 * v["macs"] / (v["ms"] / 1e3) / 1e12, 1)} for k, v in top],
         "other_kernels_ms_per_step": {k: round(v["ms"] / K, 3) for k, v in prof.items() if k != "conv_tc"},
