@@ -92,6 +92,8 @@ class Engine:
         # (measured: 0.43 ms per block against 0.39 ms in the reference's pull form -- the K = 32 launches are bound by their
         # epilogue (fp32 partial sums read and written per tile), not by the MMAs they save -- so it is opt-in)
         self.rdb_push = self.use_s16 and os.environ.get("DEMFI_RDB_PUSH", "0") == "1"
+        # Dec_first_2's loop-invariant input channels convolved once per forward instead of once per iteration (see _build): opt-in
+        self.hoist_d2 = self.use_s16 and os.environ.get("DEMFI_HOIST_D2", "0") == "1"
         self._keep: list = []  # weights, ctypes structs
         self.bufs: Dict[str, torch.Tensor] = {}
         self.views: Dict[str, View] = {}
@@ -191,6 +193,8 @@ class Engine:
         v["RH"] = self._buf("RH", B, H, W, 64, s16=True)
         v["FO1"] = self._buf("FO1", B, H, W, 32, s16=True)
         v["D2O"] = self._buf("D2O", B, H, W, 12)  # S0_final pad | S1_final pad | St_final pad
+        if self.hoist_d2:
+            v["DFS"] = self._buf("DFS", B, H, W, 64, s16=True)  # Dec_first_2 over the loop-invariant channels of Agg3 (+ bias)
         self.t_dev = torch.zeros(B, dtype=torch.float32, device=self.dev)
 
     def workspace_bytes(self) -> int:
@@ -622,6 +626,27 @@ class Engine:
                     [(FO.ch(4, 4), 21), (DL0.ch(0, 5), 25)]))
         ops.append(("gather", A3, [(SP.frames(f * B, B).ch(0, 3), 4 * f) for f in range(2)] +
                     [(DL0.ch(0, 4), 20), (FO.ch(4, 4), 24)]))
+        # Dec_first_2 (DeMFInet.py:157) is linear in its 99 input channels and 27 of them never change inside the boosting loop
+        # (S0', S1', occ_0, rflow, flow_01 / flow_10, the four blurry inputs: DeMFInet.py:151-155): their part of the convolution,
+        # with the bias, is computed ONCE here and enters every iteration as the S16 skip operand of the convolution over the
+        # other 72 (St_new, flow_final, occ_final, F_rec).  27 instead of 36 (tap, 32-channel) stages per iteration, and the
+        # filter bank (108 KB instead of 144) leaves room for a third halo buffer (two: the issuer waited for activations 40 %
+        # of the time).  Measured (tools/hoist_ab.py, same box, interleaved): 42.23 / 42.07 ms per forward against 42.30 / 42.24 --
+        # the 241 MB skip operand per iteration costs what the nine stages save -- so it is opt-in: DEMFI_HOIST_D2=1.
+        # internal A3 channel -> reference Agg3 channel (DeMFInet.py:151-155), then F_rec
+        self._agg3_map = ([0, 1, 2, -1, 3, 4, 5, -1, 6, 7, 8, 86, 82, 83, 84, 85, 73, -1, -1, -1, 74, 75, 76, 77, 80, 81, 78, 79]
+                          + list(range(87, 99)) + list(range(9, 73)))
+        if self.hoist_d2:
+            w_df, b_df = self._weight(["Dec_first_2"])
+            def part(internal):  # (weights over the reference channels these internal channels carry, in_map into them)
+                refs = [self._agg3_map[k] for k in internal]
+                real = [r for r in refs if r >= 0]
+                pos = {r: i for i, r in enumerate(real)}
+                return np.ascontiguousarray(w_df[:, real]), [pos[r] if r >= 0 else -1 for r in refs]
+            w_st, map_st = part(list(range(0, 8)) + list(range(16, 40)))
+            self._d2_var = part(list(range(8, 16)) + list(range(40, 104)))
+            ops.append(self.conv(["Dec_first_2.static"], [A3.ch(0, 8), A3.ch(16, 24)], (H, W), B, [full(v["DFS"], 64, none)],
+                                 wb=(w_st, b_df), in_map=map_st))
         # Ch_Reducer (DeMFInet.py:114) over cat(rF0, rF1, rFt)
         FR = [v["FR0"], v["FR1"], v["FR2"]]
         ops.append(self.conv("Ch_Reducer", [DECIN.frames(0, B), DECIN.frames(B, B), DECIN.frames(2 * B, B)], (H, W), B,
@@ -640,9 +665,6 @@ class Engine:
                     assert op[1].fmt == A.FMT_F32 and all(sv.fmt == A.FMT_F32 for sv, _ in op[2])
                 elif op[0] not in ("conv", "upsample"):
                     assert all(a_.fmt == A.FMT_F32 for a_ in op[1:] if isinstance(a_, View)), op[0]
-        # internal A3 channel -> reference Agg3 channel (DeMFInet.py:151-155), then F_rec
-        self._agg3_map = ([0, 1, 2, -1, 3, 4, 5, -1, 6, 7, 8, 86, 82, 83, 84, 85, 73, -1, -1, -1, 74, 75, 76, 77, 80, 81, 78, 79]
-                          + list(range(87, 99)) + list(range(9, 73)))
 
     def _iter_ops(self, itr: int, decode: bool) -> list:
         key = (itr % 6, decode)  # FR rotates with period 3, DL with period 2
@@ -695,7 +717,12 @@ class Engine:
         # PWB (DeMFInet.py:146-149) + D2 (DeMFInet.py:151-165)
         ops.append(("pwb", A3.ch(0, 8), DLo, A3.ch(8, 8)))
         pool = [v["P0"].frames(0, B), v["P1"].frames(0, B), v["P2"].frames(0, B)]
-        ops.append(self.conv("Dec_first_2", [A3, hout], (H, W), B, [full(pool[0], 64, relu)], in_map=self._agg3_map))
+        if self.hoist_d2:
+            w_var, map_var = self._d2_var
+            ops.append(self.conv(["Dec_first_2.loop"], [A3.ch(8, 8), hout], (H, W), B, [full(pool[0], 64, relu, v["DFS"])],
+                                 wb=(w_var, np.zeros(64, dtype=np.float32)), in_map=map_var, label="Dec_first_2"))
+        else:
+            ops.append(self.conv("Dec_first_2", [A3, hout], (H, W), B, [full(pool[0], 64, relu)], in_map=self._agg3_map))
         a, b_, c_ = pool
         for i in range(5):
             ops.append(self.conv(f"Decoder_res_2.{i}.conv1", [a], (H, W), B, [full(b_, 64, relu)]))

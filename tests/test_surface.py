@@ -155,6 +155,21 @@ def test_workspace_arena_layout(state_dict, hw):
     assert f._arena is None and f.check_arena() == 0 and f.workspace_bytes() > e.workspace_bytes() * (1 if hw == (64, 96) else 0)
 
 
+def test_opt_in_hoist_of_the_loop_invariant_part_of_dec_first_2(state_dict, monkeypatch):
+    """DEMFI_HOIST_D2=1: Dec_first_2 is linear in its 99 input channels and 27 of them never change inside the boosting loop
+    (DeMFInet.py:151-157): one more launch in front of the loop, 27 * 64 * 9 = 15 552 MAC/px fewer per further iteration; the
+    storage formats and the arena layout stay consistent.  (Measured: no gain -- opt-in; parity run on the GPU by tools/hoist_ab.py.)"""
+    monkeypatch.setenv("DEMFI_HOIST_D2", "1")
+    e = Engine(state_dict, 1, 64, 96, torch.device("cpu"), dry=True)
+    base = lambda n: 3919552 + 843520 * n - 2 * 4096 - 56256 * (n - 1)
+    for n in (1, 3):
+        assert e.conv_macs(n) == (base(n) - 15552 * (n - 1)) * 64 * 96
+    assert sum(1 for op in e.ops_stage1 if op[0] == "conv" and op[2] == "Dec_first_2.static") == 1
+    assert "DFS" in e.liveness and e.liveness["DFS"][1] == max(l for _, l in e.liveness.values())
+    e.check_formats(3)
+    assert e.check_arena() > 1000
+
+
 def test_shape_constraints():
     with pytest.raises(ValueError):
         Engine(synth.make_state_dict(0), 1, 36, 64, torch.device("cpu"), dry=True)
