@@ -119,6 +119,18 @@ def test_pack_weights_tc16_layout_fp16_hi_lo_swizzle64():
     assert base == halves.size
 
 
+def test_pack_weights_device_validates_before_it_launches():
+    """demfi_pack_weights_device (device -> device, the training step's packer): argument errors are reported without a GPU"""
+    lib = A.lib()
+    assert lib.demfi_pack_weights_device(A.CONV_TC16, None, 64, 64, 3, 3, 64, 64, None, None) != 0              # null pointers
+    assert b"null" in lib.demfi_last_error()
+    buf = (C.c_float * 4)()
+    assert lib.demfi_pack_weights_device(A.CONV_TC16P, C.addressof(buf), 64, 64, 3, 3, 64, 64, C.addressof(buf), None) != 0
+    assert b"DEMFI_CONV_TC16 only" in lib.demfi_last_error()
+    assert lib.demfi_pack_weights_device(A.CONV_TC16, C.addressof(buf), 64, 64, 3, 3, 32, 64, C.addressof(buf), None) != 0   # src_c < Ci
+    assert lib.demfi_pack_weights_device(A.CONV_TC16, C.addressof(buf), 64, 64, 3, 3, 64, 48, C.addressof(buf), None) != 0   # cout_pad < Co
+
+
 def test_pack_weights_rejects_bad_maps():
     w = np.zeros((4, 4, 1, 1), dtype=np.float32)
     with pytest.raises(A.DemfiError):
